@@ -1,0 +1,173 @@
+/* reef_b200.h -- C ABI of libreef_b200.so: the B200-native prover hot path for eniac/Reef.
+ *
+ * The reference (pure Rust) has no FFI seam on this path; these entry points are the seams a
+ * maintainer binds with `extern "C"` from src/backend.  Each one names
+ * the reference interface it replaces.  Citations are relative to /root/reference/.
+ *
+ * Conventions
+ *   - Field elements (Fq = Pallas scalar field, modulus at src/backend/r1cs_helper.rs:37-38):
+ *     32-byte little-endian canonical integers, exactly `PrimeField::to_repr()` /
+ *     `Integer::from_digits(.., Order::Lsf)` (r1cs_helper.rs:488, commitment.rs:528).
+ *   - Curve points: affine, x || y, 64 bytes, each coordinate little-endian canonical in the
+ *     curve's base field; the point at infinity is 64 zero bytes.
+ *   - All buffers are caller-owned HOST memory unless the name ends in `_dev`.
+ *   - Return value: 0 = OK; non-zero = failure, message from reef_last_error() (thread-local).
+ *     The reference panics/asserts on this path (framework.rs:394-396, commitment.rs:269); the
+ *     Rust shim turns a non-zero return into `panic!` to keep that behaviour.  REEF_EASSERT is
+ *     returned exactly where the reference would have hit an `assert!`/index panic.
+ *   - One context per calling thread (the reference calls this path from two threads,
+ *     framework.rs:98-110); a context serialises its own calls and owns one CUDA stream.
+ *   - No CPU fallback: every compute entry fails with REEF_ECUDA when no sm_100 device is usable.
+ */
+#ifndef REEF_B200_H
+#define REEF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REEF_OK 0
+#define REEF_EINVAL 1  /* malformed arguments */
+#define REEF_ECUDA 2   /* CUDA runtime / no device */
+#define REEF_EASSERT 3 /* the reference would have panicked (assert!, index out of bounds) */
+#define REEF_ENOMEM 4
+
+typedef struct reef_ctx reef_ctx;
+typedef struct reef_table reef_table;   /* device-resident lookup table (T or the document) */
+typedef struct reef_sponge reef_sponge; /* device-resident SAFE sponge session */
+
+/* ------------------------------------------------------------------ lifecycle */
+int reef_abi_version(void);
+const char* reef_last_error(void);
+int reef_init(int device, reef_ctx** out);
+void reef_shutdown(reef_ctx* ctx);
+int reef_sync(reef_ctx* ctx);
+/* The CUDA stream (cudaStream_t) every launch of this context goes to; for event timing. */
+void* reef_stream(reef_ctx* ctx);
+
+/* ------------------------------------------------------------------ host-side helpers
+ * Pure host logic of the path, kept behind the same ABI so the Rust shim and the tests use
+ * one definition. */
+
+/* costs.rs:10-15 `logmn`: (mn as f32).log2().ceil(), logmn(1) == 1. */
+uint32_t reef_logmn(uint64_t mn);
+
+/* framework.rs:978-1011 `doc_transform`.  `ab`/`doc` are Unicode scalar values.  Writes
+ * 2^logmn(doc_len+2) codes.  REEF_EASSERT if a character is not in the alphabet. */
+int reef_doc_transform(const uint32_t* ab, uint32_t ab_len, const uint32_t* doc, uint64_t doc_len,
+                       uint64_t* out_udoc, uint64_t out_cap, uint64_t* out_len);
+
+/* r1cs.rs:2208-2243: packs the lookup-index bits into `num_cqs = ceil(m*sc_l/254)` field
+ * elements (loop quirks reproduced).  `out` must hold num_cqs*32 bytes. */
+int reef_combined_q(const uint64_t* q, uint32_t m, uint32_t sc_l, uint8_t* out, uint32_t out_cap_elems,
+                    uint32_t* num_cqs);
+
+/* neptune sponge::api IOPattern tag.  ops[k]: bit 31 set = Absorb(n), clear = Squeeze(n). */
+int reef_io_pattern_tag(const uint32_t* ops, uint32_t n_ops, uint32_t domain_separator, uint8_t out[32]);
+
+/* ------------------------------------------------------------------ B2: Poseidon (neptune 8.1.0, U4, Standard) */
+
+/* n independent one-shot hashes, IOPattern [Absorb(arity), Squeeze(1)], arity in {2,4}:
+ * merkle_tree.rs:80-114 `new_parent`, commitment.rs:495-510 `calc_d`.
+ * in: n*arity elements; out: n elements. */
+int reef_poseidon_hash(reef_ctx* ctx, const uint8_t* in, uint32_t arity, uint64_t n, uint8_t* out);
+
+/* commitment.rs:495-510 `calc_d(&[v, salt], pc)`. */
+int reef_calc_d(reef_ctx* ctx, const uint8_t v[32], const uint8_t salt[32], uint8_t out[32]);
+
+/* A whole SAFE sponge session in one launch: start(pattern, domain separator), the absorbs
+ * and squeezes of `ops` in order, finish.  `in` = all absorbed elements, `out` = all squeezed. */
+int reef_poseidon_sponge(reef_ctx* ctx, const uint8_t* in, uint32_t n_in, const uint32_t* ops, uint32_t n_ops,
+                         uint32_t domain_separator, uint8_t* out, uint32_t n_out);
+
+/* Incremental session (SpongeAPI::start/absorb/squeeze/finish as used at r1cs.rs:2260-2311,
+ * r1cs_helper.rs:485-488).  reef_sponge_finish frees the session and returns REEF_EASSERT on
+ * an IOPattern mismatch (neptune's ParameterUsageMismatch). */
+int reef_sponge_start(reef_ctx* ctx, const uint32_t* ops, uint32_t n_ops, uint32_t domain_separator,
+                      reef_sponge** out);
+int reef_sponge_absorb(reef_sponge* sp, const uint8_t* elems, uint32_t n);
+int reef_sponge_squeeze(reef_sponge* sp, uint32_t n, uint8_t* out);
+int reef_sponge_finish(reef_sponge* sp);
+
+/* merkle_tree.rs:25-78 `MerkleCommitment::new`: all levels (leaf parents first), concatenated.
+ * Level l has ceil(prev/2) nodes; reef_merkle_tree_elems(n) is the total.  `level_sizes` must
+ * hold 64 entries. */
+uint64_t reef_merkle_tree_elems(uint64_t n_doc);
+int reef_merkle_build(reef_ctx* ctx, const uint64_t* doc, uint64_t n_doc, uint8_t* out_levels,
+                      uint64_t* level_sizes, uint32_t* n_levels, uint8_t out_root[32]);
+/* Same, document and tree resident in device memory (tree stays on device). */
+int reef_merkle_build_dev(reef_ctx* ctx, const uint64_t* doc_dev, uint64_t n_doc, void* levels_dev,
+                          uint64_t* level_sizes, uint32_t* n_levels, uint8_t out_root[32]);
+
+/* merkle_tree.rs:128-191 `path_wits(idx)` on a host copy of the tree.  Writes n_levels
+ * entries: l_or_r[k], has_idx[k] (1 only for the leaf entry), opposite_idx[k] (u64),
+ * opposite[k] (32 B). */
+int reef_merkle_path_wits(const uint64_t* doc, uint64_t n_doc, const uint8_t* levels, const uint64_t* level_sizes,
+                          uint32_t n_levels, uint64_t idx, uint8_t* l_or_r, uint8_t* has_idx,
+                          uint64_t* opposite_idx, uint8_t* opposite);
+
+/* ------------------------------------------------------------------ B1: nlookup sum-check (MLE sweeps) */
+
+#define REEF_TAG_NL 0
+#define REEF_TAG_NLDOC 1
+#define REEF_TAG_NLHYBRID 2
+
+/* Upload a table once (the reference clones it per step, r1cs.rs:2321-2330).  Length is
+ * zero-padded to the next power of two (r1cs.rs:2322-2329). */
+int reef_table_upload(reef_ctx* ctx, const uint8_t* table, uint64_t n, reef_table** out);
+/* Document codes (framework.rs:978-1011) as u32: 8x less HBM traffic for the first two passes. */
+int reef_table_upload_u32(reef_ctx* ctx, const uint32_t* codes, uint64_t n, reef_table** out);
+/* Wrap memory that is already on the device (n must be a power of two; not freed by reef_table_free). */
+int reef_table_wrap_dev(reef_ctx* ctx, void* dev_ptr, uint64_t n, int is_u32, reef_table** out);
+int reef_table_download(const reef_table* t, uint8_t* out, uint64_t n);
+uint64_t reef_table_len(const reef_table* t); /* original (unpadded) length */
+void reef_table_free(reef_table* t);
+
+typedef struct reef_nlookup_out {
+  uint8_t* prev_running_claim; /* 32      {id}_prev_running_claim */
+  uint8_t* combined_q;         /* cap*32  {id}_combined_q_{k} */
+  uint32_t combined_q_cap;     /* in: capacity in elements */
+  uint32_t num_cqs;            /* out */
+  uint8_t* claim_r;            /* 32      {id}_claim_r */
+  uint8_t* rounds;             /* ell*4*32: per round i=1..ell {id}_sc_r_{i}, {id}_sc_g_{i}_xsq, _x, _const */
+  uint32_t rounds_cap;         /* in: capacity in rounds */
+  uint32_t ell;                /* out: number of sum-check rounds (= next_running_q length) */
+  uint8_t* sc_last_claim;      /* 32      {id}_sc_last_claim */
+  uint8_t* next_running_claim; /* 32      {id}_next_running_claim */
+} reef_nlookup_out;
+
+/* r1cs.rs:2177-2393 `wit_nlookup_gadget`, everything after the named-wire bookkeeping:
+ * transcript [doc_hash?] ++ combined_q ++ v ++ prev_q ++ [prev_v] -> claim_r, eq table,
+ * ell sum-check rounds, last claim, next running claim.
+ * prev_q/prev_v NULL = first step defaults (zeros / table[0], r1cs.rs:2194-2201).
+ * doc_hash is required for NLDOC / NLHYBRID and ignored for NL.
+ * next_running_q is rounds[i][0], i = 0..ell-1. */
+int reef_nlookup_prove(reef_ctx* ctx, int tag, const reef_table* table, const uint64_t* q, const uint8_t* v,
+                       uint32_t m, const uint8_t* prev_q, const uint8_t* prev_v, const uint8_t* doc_hash,
+                       reef_nlookup_out* out);
+
+/* Reference-shaped building blocks (materialised tables), for drop-in use and for the parity
+ * tests that mirror the reference's own unit tests. */
+
+/* r1cs_helper.rs:508-544 `gen_eq_table(rs, qs, last_q)`; out: 2^ell elements. */
+int reef_gen_eq_table(reef_ctx* ctx, const uint8_t* rs, const uint64_t* qs, uint32_t m, const uint8_t* last_q,
+                      uint32_t ell, uint8_t* out);
+/* r1cs_helper.rs:441-506 `linear_mle_product(table_t, table_eq, ell, i, sponge)`: both tables are
+ * folded in place on the device.  out = (r_i, xsq, x, con), 4*32 bytes. */
+int reef_linear_mle_product(reef_ctx* ctx, reef_table* table_t, reef_table* table_eq, uint32_t ell, uint32_t i,
+                            reef_sponge* sponge, uint8_t out[128]);
+/* r1cs_helper.rs:637-641 `verifier_mle_eval(table, q)` (q[0] <-> top index bit). */
+int reef_verifier_mle_eval(reef_ctx* ctx, const reef_table* table, const uint8_t* q, uint32_t ell, uint8_t out[32]);
+/* r1cs_helper.rs:551-634 `prover_mle_partial_eval(prods, x, 0..n, true, None)`.
+ * hole = index of the x entry that is -1 in the reference, or -1 for none.
+ * out_coeff / out_const as returned by the reference ((crap, value) without a hole). */
+int reef_prover_mle_partial_eval(reef_ctx* ctx, const reef_table* table, const uint8_t* x, uint32_t ell, int32_t hole,
+                                 uint8_t out_coeff[32], uint8_t out_const[32]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REEF_B200_H */

@@ -1,0 +1,27 @@
+/* reef_b200_testing.h -- TEST HOOKS exported by libreef_b200.so.  Not part of the product ABI.
+ *
+ * The field arithmetic and the single-thread Poseidon permutation are written once as
+ * __host__ __device__ code (reef_b200/csrc/fp.cuh, poseidon.cuh).  These hooks evaluate the
+ * HOST instantiation of that shared code so that its structure (column bookkeeping, Montgomery
+ * reduction, lazy accumulation, optimised round schedule) is unit-tested in the CPU-only test
+ * tier.  No product entry point in reef_b200.h ever calls them, and they never touch a GPU.
+ */
+#ifndef REEF_B200_TESTING_H
+#define REEF_B200_TESTING_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* field: 0 = Fq (Pallas scalar), 1 = Fp (Pallas base).  Operands/outputs canonical 32-byte LE.
+ * op: 0 a*b, 1 a+b, 2 a-b, 3 1/a, 4 lazy(a*b + a*a + b*b), 5 lazy(40000 * a*b), 6 a[limb0]*b */
+int reef_hosttest_field_op(int field, int op, const uint8_t a[32], const uint8_t b[32], uint8_t out[32]);
+/* plain 256x256 -> 512-bit integer product */
+int reef_hosttest_mul_wide(const uint8_t a[32], const uint8_t b[32], uint8_t out[64]);
+/* one Poseidon permutation of a width-5 state (canonical in/out) */
+int reef_hosttest_poseidon_permute(const uint8_t in[160], uint8_t out[160]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

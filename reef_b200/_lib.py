@@ -1,0 +1,97 @@
+"""ctypes loader for libreef_b200.so -- fails loudly when the CUDA library is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+lib_path = os.path.join(_HERE, "libreef_b200.so")
+
+
+class ReefError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libreef_b200 error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+class NlookupOut(C.Structure):
+    _fields_ = [
+        ("prev_running_claim", C.c_void_p),
+        ("combined_q", C.c_void_p),
+        ("combined_q_cap", C.c_uint32),
+        ("num_cqs", C.c_uint32),
+        ("claim_r", C.c_void_p),
+        ("rounds", C.c_void_p),
+        ("rounds_cap", C.c_uint32),
+        ("ell", C.c_uint32),
+        ("sc_last_claim", C.c_void_p),
+        ("next_running_claim", C.c_void_p),
+    ]
+
+
+def _load():
+    if not os.path.exists(lib_path):
+        raise ImportError(
+            f"{lib_path} not found: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "reef_b200 has no CPU fallback.")
+    return C.CDLL(lib_path)
+
+
+lib = _load()
+
+_vp, _u8p = C.c_void_p, C.c_void_p
+_sig = {
+    "reef_abi_version": (C.c_int, []),
+    "reef_last_error": (C.c_char_p, []),
+    "reef_init": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "reef_shutdown": (None, [_vp]),
+    "reef_sync": (C.c_int, [_vp]),
+    "reef_stream": (_vp, [_vp]),
+    "reef_logmn": (C.c_uint32, [C.c_uint64]),
+    "reef_doc_transform": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint64, _vp, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "reef_combined_q": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "reef_io_pattern_tag": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp]),
+    "reef_poseidon_hash": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint64, _vp]),
+    "reef_calc_d": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "reef_poseidon_sponge": (C.c_int, [_vp, _vp, C.c_uint32, _vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32]),
+    "reef_sponge_start": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
+    "reef_sponge_absorb": (C.c_int, [_vp, _vp, C.c_uint32]),
+    "reef_sponge_squeeze": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "reef_sponge_finish": (C.c_int, [_vp]),
+    "reef_merkle_tree_elems": (C.c_uint64, [C.c_uint64]),
+    "reef_merkle_build": (C.c_int, [_vp, _vp, C.c_uint64, _vp, _vp, C.POINTER(C.c_uint32), _vp]),
+    "reef_merkle_build_dev": (C.c_int, [_vp, _vp, C.c_uint64, _vp, _vp, C.POINTER(C.c_uint32), _vp]),
+    "reef_merkle_path_wits": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_uint32, C.c_uint64, _vp, _vp, _vp, _vp]),
+    "reef_table_upload": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),
+    "reef_table_upload_u32": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),
+    "reef_table_wrap_dev": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, C.POINTER(_vp)]),
+    "reef_table_download": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "reef_table_len": (C.c_uint64, [_vp]),
+    "reef_table_free": (None, [_vp]),
+    "reef_nlookup_prove": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp, C.POINTER(NlookupOut)]),
+    "reef_gen_eq_table": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp, C.c_uint32, _vp]),
+    "reef_linear_mle_product": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp]),
+    "reef_verifier_mle_eval": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp]),
+    "reef_prover_mle_partial_eval": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_int32, _vp, _vp]),
+    # test hooks (include/reef_b200_testing.h)
+    "reef_hosttest_field_op": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp]),
+    "reef_hosttest_mul_wide": (C.c_int, [_vp, _vp, _vp]),
+    "reef_hosttest_poseidon_permute": (C.c_int, [_vp, _vp]),
+}
+_missing = []
+for _name, (_res, _args) in _sig.items():
+    try:
+        _f = getattr(lib, _name)
+    except AttributeError:
+        _missing.append(_name)
+        continue
+    _f.restype = _res
+    _f.argtypes = _args
+if _missing:
+    raise ImportError(f"libreef_b200.so is stale: missing symbols {_missing}; rebuild with `make`")
+
+
+def check(rc: int):
+    if rc != 0:
+        raise ReefError(rc, lib.reef_last_error().decode("utf-8", "replace"))

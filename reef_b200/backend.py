@@ -1,0 +1,313 @@
+"""Host-side mirror of the reference's interface for the hot path, over the C ABI.
+
+Names follow /root/reference/src/backend: `doc_transform` (framework.rs:978), `logmn`
+(costs.rs:10), `MerkleCommitment` (merkle_tree.rs:10-192), `calc_d` (commitment.rs:495),
+`wit_nlookup_gadget` (r1cs.rs:2177), `gen_eq_table` / `linear_mle_product` /
+`prover_mle_partial_eval` / `verifier_mle_eval` (r1cs_helper.rs:441-641).
+Values cross this layer as Python ints; on the wire they are 32-byte LE canonical.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from ._lib import NlookupOut, ReefError, check, lib
+
+TAG_NL, TAG_NLDOC, TAG_NLHYBRID = 0, 1, 2
+_TAGS = {"nl": TAG_NL, "nldoc": TAG_NLDOC, "nlhybrid": TAG_NLHYBRID}
+ABSORB_BIT = 1 << 31
+
+
+def _pack(xs) -> bytes:
+    return b"".join(int(x).to_bytes(32, "little") for x in xs)
+
+
+def _unpack(b) -> list:
+    b = bytes(b)
+    return [int.from_bytes(b[i:i + 32], "little") for i in range(0, len(b), 32)]
+
+
+def _buf(b: bytes):
+    return C.create_string_buffer(b, len(b)) if len(b) else C.create_string_buffer(1)
+
+
+def _u64(xs):
+    return np.ascontiguousarray(np.asarray(list(xs), dtype=np.uint64))
+
+
+def _ops(pattern):
+    """[('A'|'S', n), ...] -> u32 words (bit 31 = absorb)."""
+    out = []
+    for kind, n in pattern:
+        if kind not in ("A", "S"):
+            raise ValueError("pattern ops are ('A', n) or ('S', n)")
+        out.append((ABSORB_BIT | n) if kind == "A" else n)
+    return np.asarray(out, dtype=np.uint32)
+
+
+# ------------------------------------------------------------------------- pure host helpers
+def logmn(mn: int) -> int:
+    return int(lib.reef_logmn(int(mn)))
+
+
+def doc_transform(ab: str, doc: str) -> list:
+    a = np.asarray([ord(c) for c in ab], dtype=np.uint32)
+    d = np.asarray([ord(c) for c in doc], dtype=np.uint32)
+    n = C.c_uint64(0)
+    cap = 1 << (max(len(doc) + 2, 2).bit_length() + 1)
+    out = np.zeros(cap, dtype=np.uint64)
+    check(lib.reef_doc_transform(a.ctypes.data, len(a), d.ctypes.data if len(d) else None, len(d), out.ctypes.data,
+                                 cap, C.byref(n)))
+    return out[:n.value].tolist()
+
+
+def combined_q(q, sc_l: int) -> list:
+    qa = _u64(q)
+    cap = (len(qa) * sc_l) // 254 + 2
+    out = C.create_string_buffer(cap * 32)
+    n = C.c_uint32(0)
+    check(lib.reef_combined_q(qa.ctypes.data if len(qa) else None, len(qa), sc_l, out, cap, C.byref(n)))
+    return _unpack(out.raw[:n.value * 32])
+
+
+def io_pattern_tag(pattern, domain_separator: int = 0) -> int:
+    ops = _ops(pattern)
+    out = C.create_string_buffer(32)
+    check(lib.reef_io_pattern_tag(ops.ctypes.data if len(ops) else None, len(ops), domain_separator, out))
+    return int.from_bytes(out.raw, "little")
+
+
+# ------------------------------------------------------------------------- device objects
+class Context:
+    """One libreef_b200 context (one CUDA stream) on one GPU."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        check(lib.reef_init(device, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib.reef_shutdown(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(lib.reef_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(lib.reef_stream(self._h) or 0)
+
+    # ---- Poseidon
+    def poseidon_hash(self, rows, arity: int) -> list:
+        """n one-shot hashes; rows = flat list of n*arity ints."""
+        n = len(rows) // arity
+        out = C.create_string_buffer(max(n, 1) * 32)
+        check(lib.reef_poseidon_hash(self._h, _buf(_pack(rows)), arity, n, out))
+        return _unpack(out.raw[:n * 32])
+
+    def calc_d(self, v: int, salt: int) -> int:
+        out = C.create_string_buffer(32)
+        check(lib.reef_calc_d(self._h, _buf(_pack([v])), _buf(_pack([salt])), out))
+        return int.from_bytes(out.raw, "little")
+
+    def poseidon_sponge(self, pattern, elems, domain_separator: int = 0) -> list:
+        ops = _ops(pattern)
+        n_out = sum(n for k, n in pattern if k == "S")
+        out = C.create_string_buffer(max(n_out, 1) * 32)
+        check(lib.reef_poseidon_sponge(self._h, _buf(_pack(elems)), len(elems), ops.ctypes.data, len(ops),
+                                       domain_separator, out, n_out))
+        return _unpack(out.raw[:n_out * 32])
+
+    # ---- tables
+    def table(self, values) -> "Table":
+        return Table(self, values=values)
+
+    def table_u32(self, codes) -> "Table":
+        return Table(self, codes=codes)
+
+    # ---- MLE building blocks (reference-shaped)
+    def gen_eq_table(self, rs, qs, last_q) -> list:
+        ell = len(last_q)
+        out = C.create_string_buffer((1 << ell) * 32)
+        qa = _u64(qs)
+        check(lib.reef_gen_eq_table(self._h, _buf(_pack(rs)), qa.ctypes.data if len(qa) else None, len(qa),
+                                    _buf(_pack(last_q)), ell, out))
+        return _unpack(out.raw)
+
+    def linear_mle_product(self, table_t: "Table", table_eq: "Table", ell: int, i: int, sponge: "Sponge"):
+        out = C.create_string_buffer(128)
+        check(lib.reef_linear_mle_product(self._h, table_t._h, table_eq._h, ell, i, sponge._h, out))
+        r, xsq, x, con = _unpack(out.raw)
+        return r, xsq, x, con
+
+    def verifier_mle_eval(self, table: "Table", q) -> int:
+        out = C.create_string_buffer(32)
+        check(lib.reef_verifier_mle_eval(self._h, table._h, _buf(_pack(q)), len(q), out))
+        return int.from_bytes(out.raw, "little")
+
+    def prover_mle_partial_eval(self, table: "Table", x):
+        """x entries are ints, -1 marks the hole (at most one)."""
+        holes = [k for k, v in enumerate(x) if v == -1]
+        if len(holes) > 1:
+            raise ValueError("at most one hole is supported")
+        hole = holes[0] if holes else -1
+        xs = [0 if v == -1 else v for v in x]
+        oc, ok = C.create_string_buffer(32), C.create_string_buffer(32)
+        check(lib.reef_prover_mle_partial_eval(self._h, table._h, _buf(_pack(xs)), len(xs), hole, oc, ok))
+        return int.from_bytes(oc.raw, "little"), int.from_bytes(ok.raw, "little")
+
+    # ---- nlookup
+    def wit_nlookup_gadget(self, table: "Table", q, v, running_q=None, running_v=None, tag="nl", doc_hash=None):
+        """r1cs.rs:2177-2393.  Returns NlookupResult."""
+        m = len(q)
+        assert m == len(v)
+        ell_cap = 64
+        cq_cap = (m * ell_cap) // 254 + 2
+        bufs = dict(prev=C.create_string_buffer(32), cq=C.create_string_buffer(cq_cap * 32),
+                    claim=C.create_string_buffer(32), rounds=C.create_string_buffer(ell_cap * 4 * 32),
+                    last=C.create_string_buffer(32), nxt=C.create_string_buffer(32))
+        o = NlookupOut()
+        o.prev_running_claim = C.addressof(bufs["prev"])
+        o.combined_q = C.addressof(bufs["cq"])
+        o.combined_q_cap = cq_cap
+        o.claim_r = C.addressof(bufs["claim"])
+        o.rounds = C.addressof(bufs["rounds"])
+        o.rounds_cap = ell_cap
+        o.sc_last_claim = C.addressof(bufs["last"])
+        o.next_running_claim = C.addressof(bufs["nxt"])
+        qa = _u64(q)
+        vb = _buf(_pack(v))
+        pq = _buf(_pack(running_q)) if running_q is not None else None
+        pv = _buf(_pack([running_v])) if running_v is not None else None
+        dh = _buf(_pack([doc_hash])) if doc_hash is not None else None
+        check(lib.reef_nlookup_prove(self._h, _TAGS[tag] if isinstance(tag, str) else tag, table._h,
+                                     qa.ctypes.data if m else None, vb if m else None, m, pq, pv, dh, C.byref(o)))
+        ell = o.ell
+        rounds = _unpack(bufs["rounds"].raw[:ell * 4 * 32])
+        rounds = [tuple(rounds[4 * i:4 * i + 4]) for i in range(ell)]
+        return NlookupResult(
+            prev_running_claim=int.from_bytes(bufs["prev"].raw, "little"),
+            combined_q=_unpack(bufs["cq"].raw[:o.num_cqs * 32]),
+            claim_r=int.from_bytes(bufs["claim"].raw, "little"),
+            rounds=rounds,
+            sc_last_claim=int.from_bytes(bufs["last"].raw, "little"),
+            next_running_claim=int.from_bytes(bufs["nxt"].raw, "little"),
+            next_running_q=[r[0] for r in rounds],
+        )
+
+    # ---- Merkle
+    def merkle(self, doc) -> "MerkleCommitment":
+        return MerkleCommitment(self, doc)
+
+
+@dataclass
+class NlookupResult:
+    prev_running_claim: int
+    combined_q: list
+    claim_r: int
+    rounds: list            # per round: (sc_r, xsq, x, const)
+    sc_last_claim: int
+    next_running_claim: int
+    next_running_q: list
+
+
+class Table:
+    def __init__(self, ctx: Context, values=None, codes=None, dev_ptr=None, n=None, is_u32=False):
+        self.ctx = ctx
+        h = C.c_void_p()
+        if values is not None:
+            b = _pack(values)
+            check(lib.reef_table_upload(ctx._h, _buf(b), len(values), C.byref(h)))
+        elif codes is not None:
+            a = np.ascontiguousarray(np.asarray(codes, dtype=np.uint32))
+            check(lib.reef_table_upload_u32(ctx._h, a.ctypes.data, len(a), C.byref(h)))
+        else:
+            check(lib.reef_table_wrap_dev(ctx._h, C.c_void_p(dev_ptr), n, 1 if is_u32 else 0, C.byref(h)))
+        self._h = h
+
+    def __len__(self):
+        return int(lib.reef_table_len(self._h))
+
+    def download(self, n: int) -> list:
+        out = C.create_string_buffer(max(n, 1) * 32)
+        check(lib.reef_table_download(self._h, out, n))
+        return _unpack(out.raw[:n * 32])
+
+    def free(self):
+        if self._h:
+            lib.reef_table_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Sponge:
+    """SpongeAPI session (start/absorb/squeeze/finish), state resident on the device."""
+
+    def __init__(self, ctx: Context, pattern, domain_separator: int = 0):
+        ops = _ops(pattern)
+        h = C.c_void_p()
+        check(lib.reef_sponge_start(ctx._h, ops.ctypes.data, len(ops), domain_separator, C.byref(h)))
+        self._h = h
+
+    def absorb(self, elems):
+        check(lib.reef_sponge_absorb(self._h, _buf(_pack(elems)), len(elems)))
+
+    def squeeze(self, n: int) -> list:
+        out = C.create_string_buffer(max(n, 1) * 32)
+        check(lib.reef_sponge_squeeze(self._h, n, out))
+        return _unpack(out.raw[:n * 32])
+
+    def finish(self):
+        h, self._h = self._h, None
+        check(lib.reef_sponge_finish(h))
+
+
+class MerkleCommitment:
+    """merkle_tree.rs:10-192: `commitment`, `tree` (levels, leaf parents first), `doc`."""
+
+    def __init__(self, ctx: Context, doc):
+        self.doc = [int(c) for c in doc]
+        d = _u64(self.doc)
+        total = int(lib.reef_merkle_tree_elems(len(d)))
+        levels = C.create_string_buffer(max(total, 1) * 32)
+        sizes = np.zeros(64, dtype=np.uint64)
+        nl = C.c_uint32(0)
+        root = C.create_string_buffer(32)
+        check(lib.reef_merkle_build(ctx._h, d.ctypes.data if len(d) else None, len(d), levels, sizes.ctypes.data,
+                                    C.byref(nl), root))
+        self._levels, self._sizes, self._nl, self._d = levels, sizes, nl.value, d
+        self.commitment = int.from_bytes(root.raw, "little")
+        flat = _unpack(levels.raw[:total * 32])
+        self.tree, off = [], 0
+        for k in range(nl.value):
+            self.tree.append(flat[off:off + int(sizes[k])])
+            off += int(sizes[k])
+
+    def path_wits(self, idx: int):
+        nl = self._nl
+        lr = np.zeros(nl, dtype=np.uint8)
+        hi = np.zeros(nl, dtype=np.uint8)
+        oi = np.zeros(nl, dtype=np.uint64)
+        op = C.create_string_buffer(nl * 32)
+        check(lib.reef_merkle_path_wits(self._d.ctypes.data, len(self._d), self._levels, self._sizes.ctypes.data, nl,
+                                        idx, lr.ctypes.data, hi.ctypes.data, oi.ctypes.data, op))
+        opp = _unpack(op.raw)
+        return [(bool(lr[k]), int(oi[k]) if hi[k] else None, opp[k]) for k in range(nl)]
+
+    def make_wits(self, lookups):
+        return [self.path_wits(q) for q in lookups]

@@ -1,0 +1,894 @@
+// extern "C" surface of libreef_b200.so + the host-side logic of the path (logmn,
+// doc_transform, combined_q packing, transcript assembly, Merkle path witnesses).
+// See include/reef_b200.h for the contract and the reference interfaces each entry replaces.
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/reef_b200.h"
+#include "../../include/reef_b200_testing.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace reef;
+
+// ---------------------------------------------------------------------------------------
+// error plumbing / context scratch
+// ---------------------------------------------------------------------------------------
+namespace reef {
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+static int grow(void** p, size_t* cap, size_t bytes, bool pinned) {
+  if (*cap >= bytes) return REEF_OK;
+  size_t want = bytes + bytes / 4 + 4096;
+  if (*p) {
+    if (pinned) cudaFreeHost(*p);
+    else cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+  }
+  cudaError_t e = pinned ? cudaMallocHost(p, want) : cudaMalloc(p, want);
+  if (e != cudaSuccess) return fail(REEF_ENOMEM, std::string("allocation of ") + std::to_string(want) + " bytes: " + cudaGetErrorString(e));
+  *cap = want;
+  return REEF_OK;
+}
+int ctx_scratch(reef_ctx* c, size_t bytes, void** out) {
+  // a grow may free memory still in use by queued kernels: drain first
+  if (c->scratch_bytes < bytes) cudaStreamSynchronize(c->stream);
+  int rc = grow(&c->scratch, &c->scratch_bytes, bytes, false);
+  *out = c->scratch;
+  return rc;
+}
+int ctx_scratch2(reef_ctx* c, size_t bytes, void** out) {
+  if (c->scratch2_bytes < bytes) cudaStreamSynchronize(c->stream);
+  int rc = grow(&c->scratch2, &c->scratch2_bytes, bytes, false);
+  *out = c->scratch2;
+  return rc;
+}
+int ctx_stage(reef_ctx* c, size_t bytes, void** out) {
+  if (c->h_stage_bytes < bytes) cudaStreamSynchronize(c->stream);
+  int rc = grow(&c->h_stage, &c->h_stage_bytes, bytes, true);
+  *out = c->h_stage;
+  return rc;
+}
+}  // namespace reef
+
+struct reef_table {
+  reef_ctx* ctx;
+  void* d;
+  uint64_t n_pad, n_orig;
+  int is_u32;
+  int owns;
+  uint8_t first[32];  // table[0], canonical (default prev_running_v, r1cs.rs:2198-2201)
+};
+
+struct reef_sponge {
+  reef_ctx* ctx;
+  void* d_state;
+  void* d_buf;
+  size_t buf_bytes;
+  std::vector<uint32_t> ops;
+  size_t io;
+};
+
+static const uint8_t FQ_LE[32] = {0x01, 0x00, 0x00, 0x00, 0x21, 0xeb, 0x46, 0x8c, 0xdd, 0xa8, 0x94, 0x09, 0xfc, 0x98, 0x46, 0x22,
+                                  0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0x00, 0x00, 0x00, 0x40};
+
+static bool is_canonical_fq(const uint8_t* b) {
+  for (int i = 31; i >= 0; i--) {
+    if (b[i] < FQ_LE[i]) return true;
+    if (b[i] > FQ_LE[i]) return false;
+  }
+  return false;  // == q
+}
+
+static int check_canonical(const uint8_t* b, size_t n, const char* what) {
+  for (size_t i = 0; i < n; i++)
+    if (!is_canonical_fq(b + i * 32)) return fail(REEF_EINVAL, std::string(what) + ": element " + std::to_string(i) + " is not a canonical Fq value");
+  return REEF_OK;
+}
+
+static void load_le(uint32_t* l, const uint8_t* b) {
+  for (int i = 0; i < 8; i++)
+    l[i] = (uint32_t)b[4 * i] | ((uint32_t)b[4 * i + 1] << 8) | ((uint32_t)b[4 * i + 2] << 16) | ((uint32_t)b[4 * i + 3] << 24);
+}
+static void store_le(uint8_t* b, const uint32_t* l) {
+  for (int i = 0; i < 8; i++)
+    for (int k = 0; k < 4; k++) b[4 * i + k] = (uint8_t)(l[i] >> (8 * k));
+}
+
+template <class C>
+static void hosttest_field_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  Fe<C> x, y, r;
+  load_le(x.v, a);
+  load_le(y.v, b);
+  switch (op) {
+    case 0: r = from_mont<C>(mont_mul<C>(to_mont<C>(x), to_mont<C>(y))); break;  // a*b
+    case 1: r = fe_add<C>(x, y); break;
+    case 2: r = fe_sub<C>(x, y); break;
+    case 3: r = from_mont<C>(fe_inv<C>(to_mont<C>(x))); break;                    // 1/a
+    case 4: {                                                                     // lazy: a*b + a*a + b*b, canonical
+      Wide17 w;
+      wide_zero(w);
+      wide_mac(w, x.v, y.v);
+      wide_mac(w, x.v, x.v);
+      wide_mac(w, y.v, y.v);
+      r = wide_reduce_canonical<C>(w);
+      break;
+    }
+    case 5: {                                                                     // stress the 17th limb: 40000 * (a*b)
+      Wide17 w;
+      wide_zero(w);
+      for (int k = 0; k < 40000; k++) wide_mac(w, x.v, y.v);
+      r = wide_reduce_canonical<C>(w);
+      break;
+    }
+    case 6: {                                                                     // small mac: a[0] * b
+      Wide17 w;
+      wide_zero(w);
+      wide_mac_small(w, x.v[0], y.v);
+      r = wide_reduce_canonical<C>(w);
+      break;
+    }
+    default: r = fe_zero<C>();
+  }
+  store_le(out, r.v);
+}
+
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------
+// lifecycle
+// ---------------------------------------------------------------------------------------
+int reef_abi_version(void) { return 1; }
+const char* reef_last_error(void) { return g_last_error.c_str(); }
+
+int reef_init(int device, reef_ctx** out) {
+  REEF_REQUIRE(out != nullptr, REEF_EINVAL, "reef_init: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(REEF_ECUDA, std::string("reef_init: no CUDA device (") + cudaGetErrorString(e) + "); libreef_b200 has no CPU fallback");
+  REEF_REQUIRE(device >= 0 && device < count, REEF_EINVAL, "reef_init: device index out of range");
+  REEF_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  REEF_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(REEF_ECUDA, std::string("reef_init: device '") + prop.name + "' is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                                "; this library is built for sm_100a only");
+  reef_ctx* c = new reef_ctx;
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  REEF_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  int rc = poseidon_upload_constants(c);
+  if (rc) {
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return REEF_OK;
+}
+
+void reef_shutdown(reef_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->scratch) cudaFree(c->scratch);
+  if (c->scratch2) cudaFree(c->scratch2);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->d_pos) cudaFree(c->d_pos);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int reef_sync(reef_ctx* c) {
+  REEF_REQUIRE(c != nullptr, REEF_EINVAL, "reef_sync: ctx is NULL");
+  REEF_CUDA(cudaStreamSynchronize(c->stream));
+  return REEF_OK;
+}
+
+void* reef_stream(reef_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+// ---------------------------------------------------------------------------------------
+// host-side helpers
+// ---------------------------------------------------------------------------------------
+uint32_t reef_logmn(uint64_t mn) {
+  if (mn == 1) return 1;
+  float f = (float)mn;  // `mn as f32`: round-to-nearest-even like Rust's cast
+  return (uint32_t)std::ceil(std::log2(f));
+}
+
+int reef_doc_transform(const uint32_t* ab, uint32_t ab_len, const uint32_t* doc, uint64_t doc_len, uint64_t* out_udoc,
+                       uint64_t out_cap, uint64_t* out_len) {
+  REEF_REQUIRE(ab && (doc || doc_len == 0) && out_len, REEF_EINVAL, "reef_doc_transform: NULL argument");
+  // FxHashMap<Option<char>, usize>: later inserts overwrite (framework.rs:979-986)
+  std::unordered_map<uint32_t, uint64_t> num_ab;
+  uint64_t i = 0;
+  for (uint32_t k = 0; k < ab_len; k++) {
+    num_ab[ab[k]] = i;
+    i += 1;
+  }
+  const uint64_t epsilon = i + 1;
+  num_ab[26u] = i + 2;  // EOF
+  const uint64_t total = doc_len + 2;
+  const uint32_t lg = reef_logmn(total);
+  REEF_REQUIRE(lg < 63, REEF_EINVAL, "reef_doc_transform: document too long");
+  const uint64_t padded = (uint64_t)1 << lg;
+  if (padded < total) return fail(REEF_EASSERT, "reef_doc_transform: attempt to subtract with overflow (f32 logmn)");
+  *out_len = padded;
+  REEF_REQUIRE(out_udoc != nullptr && out_cap >= padded, REEF_EINVAL, "reef_doc_transform: output buffer too small");
+  for (uint64_t k = 0; k < doc_len; k++) {
+    auto it = num_ab.find(doc[k]);
+    if (it == num_ab.end()) return fail(REEF_EASSERT, "Character in document that's not in alphabet");
+    out_udoc[k] = it->second;
+  }
+  out_udoc[doc_len] = num_ab[26u];
+  out_udoc[doc_len + 1] = epsilon;
+  for (uint64_t k = total; k < padded; k++) out_udoc[k] = 0;
+  return REEF_OK;
+}
+
+// 256-bit little-endian accumulator for the bit packing below
+static void set_bit_le(uint8_t* x, uint32_t bit) { x[bit >> 3] |= (uint8_t)(1u << (bit & 7)); }
+
+int reef_combined_q(const uint64_t* q, uint32_t m, uint32_t sc_l, uint8_t* out, uint32_t out_cap_elems, uint32_t* num_cqs_out) {
+  REEF_REQUIRE((q || m == 0) && num_cqs_out, REEF_EINVAL, "reef_combined_q: NULL argument");
+  const uint32_t num_cqs = (uint32_t)std::ceil(((double)((uint64_t)m * sc_l)) / 254.0);
+  *num_cqs_out = num_cqs;
+  REEF_REQUIRE(num_cqs == 0 || (out && out_cap_elems >= num_cqs), REEF_EINVAL, "reef_combined_q: output buffer too small");
+  std::vector<uint8_t> res;
+  uint32_t cq = 0;
+  uint8_t cur[32];
+  while (cq < num_cqs) {
+    memset(cur, 0, 32);
+    uint32_t next_slot = 0;  // exponent of the next power of two
+    for (uint32_t i = 0; i < m; i++) {
+      uint32_t j = 0;
+      for (int32_t bit = (int32_t)sc_l - 1; bit >= 0; bit--) {  // qjs reversed: MSB first
+        const uint32_t qj = bit < 64 ? (uint32_t)((q[i] >> bit) & 1) : 0;
+        if ((uint64_t)i * sc_l + j >= (uint64_t)254 * (cq + 1) || (i == m - 1 && j == sc_l - 1)) {
+          cq += 1;
+          res.insert(res.end(), cur, cur + 32);
+          memset(cur, 0, 32);
+          next_slot = 0;
+        } else {
+          if (qj) {
+            REEF_REQUIRE(next_slot < 254, REEF_EASSERT, "reef_combined_q: slot overflow");
+            set_bit_le(cur, next_slot);
+          }
+          next_slot += 1;
+        }
+        j += 1;
+      }
+    }
+    if (m == 0 || sc_l == 0) break;
+  }
+  if (res.size() / 32 != num_cqs) return fail(REEF_EASSERT, "assertion failed: num_cqs == combined_qs.len()");
+  if (num_cqs) memcpy(out, res.data(), res.size());
+  return REEF_OK;
+}
+
+int reef_io_pattern_tag(const uint32_t* ops, uint32_t n_ops, uint32_t domain_separator, uint8_t out[32]) {
+  REEF_REQUIRE((ops || n_ops == 0) && out, REEF_EINVAL, "reef_io_pattern_tag: NULL argument");
+  io_pattern_tag_le32(ops, n_ops, domain_separator, out);
+  return REEF_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// B2: Poseidon
+// ---------------------------------------------------------------------------------------
+int reef_poseidon_hash(reef_ctx* c, const uint8_t* in, uint32_t arity, uint64_t n, uint8_t* out) {
+  REEF_REQUIRE(c && (n == 0 || (in && out)), REEF_EINVAL, "reef_poseidon_hash: NULL argument");
+  REEF_REQUIRE(arity == 2 || arity == 4, REEF_EINVAL, "reef_poseidon_hash: arity must be 2 or 4");
+  if (n == 0) return REEF_OK;
+  int rc = check_canonical(in, (size_t)n * arity, "reef_poseidon_hash");
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  void* base;
+  const size_t in_bytes = (size_t)n * arity * 32, out_bytes = (size_t)n * 32;
+  rc = ctx_scratch(c, in_bytes + out_bytes, &base);
+  if (rc) return rc;
+  char* d_in = (char*)base;
+  char* d_out = d_in + in_bytes;
+  REEF_CUDA(cudaMemcpyAsync(d_in, in, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  rc = launch_hash_batch(c, d_in, (int)arity, n, d_out);
+  if (rc) return rc;
+  REEF_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaStreamSynchronize(c->stream));
+  return REEF_OK;
+}
+
+int reef_calc_d(reef_ctx* c, const uint8_t v[32], const uint8_t salt[32], uint8_t out[32]) {
+  REEF_REQUIRE(c && v && salt && out, REEF_EINVAL, "reef_calc_d: NULL argument");
+  uint8_t in[64];
+  memcpy(in, v, 32);
+  memcpy(in + 32, salt, 32);
+  return reef_poseidon_hash(c, in, 2, 1, out);
+}
+
+int reef_poseidon_sponge(reef_ctx* c, const uint8_t* in, uint32_t n_in, const uint32_t* ops, uint32_t n_ops,
+                         uint32_t domain_separator, uint8_t* out, uint32_t n_out) {
+  REEF_REQUIRE(c && ops && n_ops > 0, REEF_EINVAL, "reef_poseidon_sponge: NULL/empty pattern");
+  uint64_t tot_in = 0, tot_out = 0;
+  for (uint32_t k = 0; k < n_ops; k++) {
+    if (ops[k] >> 31) tot_in += ops[k] & 0x7fffffffu;
+    else tot_out += ops[k];
+  }
+  // neptune asserts that the calls match the declared pattern
+  if (tot_in != n_in || tot_out != n_out) return fail(REEF_EASSERT, "reef_poseidon_sponge: IOPattern does not match the supplied element counts");
+  REEF_REQUIRE((n_in == 0 || in) && (n_out == 0 || out), REEF_EINVAL, "reef_poseidon_sponge: NULL buffer");
+  int rc = check_canonical(in, n_in, "reef_poseidon_sponge");
+  if (rc) return rc;
+  uint8_t tag[32];
+  io_pattern_tag_le32(ops, n_ops, domain_separator, tag);
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  void* base;
+  const size_t ops_bytes = ((size_t)n_ops * 4 + 31) & ~(size_t)31;
+  rc = ctx_scratch(c, ops_bytes + (size_t)(n_in + n_out + 1) * 32, &base);
+  if (rc) return rc;
+  char* d_ops = (char*)base;
+  char* d_in = d_ops + ops_bytes;
+  char* d_out = d_in + (size_t)n_in * 32;
+  REEF_CUDA(cudaMemcpyAsync(d_ops, ops, (size_t)n_ops * 4, cudaMemcpyHostToDevice, c->stream));
+  if (n_in) REEF_CUDA(cudaMemcpyAsync(d_in, in, (size_t)n_in * 32, cudaMemcpyHostToDevice, c->stream));
+  rc = launch_sponge_run(c, (const uint32_t*)d_ops, n_ops, d_in, tag, d_out);
+  if (rc) return rc;
+  if (n_out) REEF_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n_out * 32, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaStreamSynchronize(c->stream));
+  return REEF_OK;
+}
+
+int reef_sponge_start(reef_ctx* c, const uint32_t* ops, uint32_t n_ops, uint32_t domain_separator, reef_sponge** out) {
+  REEF_REQUIRE(c && ops && n_ops > 0 && out, REEF_EINVAL, "reef_sponge_start: NULL/empty argument");
+  uint8_t tag[32];
+  io_pattern_tag_le32(ops, n_ops, domain_separator, tag);
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  reef_sponge* sp = new reef_sponge;
+  sp->ctx = c;
+  sp->ops.assign(ops, ops + n_ops);
+  sp->io = 0;
+  sp->d_state = nullptr;
+  sp->d_buf = nullptr;
+  sp->buf_bytes = 0;
+  cudaError_t e = cudaMalloc(&sp->d_state, (size_t)sponge_state_bytes());
+  if (e != cudaSuccess) {
+    delete sp;
+    return fail(REEF_ENOMEM, std::string("reef_sponge_start: ") + cudaGetErrorString(e));
+  }
+  int rc = launch_sponge_step(c, sp->d_state, 0, nullptr, 0, tag, nullptr);
+  if (rc) {
+    cudaFree(sp->d_state);
+    delete sp;
+    return rc;
+  }
+  *out = sp;
+  return REEF_OK;
+}
+
+static int sponge_buf(reef_sponge* sp, size_t bytes) {
+  if (sp->buf_bytes >= bytes) return REEF_OK;
+  cudaStreamSynchronize(sp->ctx->stream);
+  if (sp->d_buf) cudaFree(sp->d_buf);
+  sp->d_buf = nullptr;
+  sp->buf_bytes = 0;
+  cudaError_t e = cudaMalloc(&sp->d_buf, bytes + 1024);
+  if (e != cudaSuccess) return fail(REEF_ENOMEM, std::string("reef_sponge: ") + cudaGetErrorString(e));
+  sp->buf_bytes = bytes + 1024;
+  return REEF_OK;
+}
+
+int reef_sponge_absorb(reef_sponge* sp, const uint8_t* elems, uint32_t n) {
+  REEF_REQUIRE(sp && (elems || n == 0), REEF_EINVAL, "reef_sponge_absorb: NULL argument");
+  if (sp->io >= sp->ops.size() || sp->ops[sp->io] != ((1u << 31) | n))
+    return fail(REEF_EASSERT, "reef_sponge_absorb: call does not match the declared IOPattern");
+  int rc = check_canonical(elems, n, "reef_sponge_absorb");
+  if (rc) return rc;
+  reef_ctx* c = sp->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  rc = sponge_buf(sp, (size_t)n * 32);
+  if (rc) return rc;
+  if (n) REEF_CUDA(cudaMemcpyAsync(sp->d_buf, elems, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
+  rc = launch_sponge_step(c, sp->d_state, 1, sp->d_buf, n, nullptr, nullptr);
+  if (rc) return rc;
+  REEF_CUDA(cudaStreamSynchronize(c->stream));  // caller may reuse `elems`
+  sp->io++;
+  return REEF_OK;
+}
+
+int reef_sponge_squeeze(reef_sponge* sp, uint32_t n, uint8_t* out) {
+  REEF_REQUIRE(sp && (out || n == 0), REEF_EINVAL, "reef_sponge_squeeze: NULL argument");
+  if (sp->io >= sp->ops.size() || sp->ops[sp->io] != n)
+    return fail(REEF_EASSERT, "reef_sponge_squeeze: call does not match the declared IOPattern");
+  reef_ctx* c = sp->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  int rc = sponge_buf(sp, (size_t)n * 32);
+  if (rc) return rc;
+  rc = launch_sponge_step(c, sp->d_state, 2, nullptr, n, nullptr, sp->d_buf);
+  if (rc) return rc;
+  if (n) REEF_CUDA(cudaMemcpyAsync(out, sp->d_buf, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaStreamSynchronize(c->stream));
+  sp->io++;
+  return REEF_OK;
+}
+
+int reef_sponge_finish(reef_sponge* sp) {
+  REEF_REQUIRE(sp != nullptr, REEF_EINVAL, "reef_sponge_finish: NULL argument");
+  reef_ctx* c = sp->ctx;
+  bool ok = sp->io == sp->ops.size();
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (sp->d_state) cudaFree(sp->d_state);
+    if (sp->d_buf) cudaFree(sp->d_buf);
+  }
+  delete sp;
+  if (!ok) return fail(REEF_EASSERT, "reef_sponge_finish: ParameterUsageMismatch");
+  return REEF_OK;
+}
+
+uint64_t reef_merkle_tree_elems(uint64_t n_doc) {
+  uint64_t total = 0, n = n_doc;
+  if (n == 0) return 0;
+  n = (n + 1) / 2;
+  total += n;
+  while (n > 1) {
+    n = (n + 1) / 2;
+    total += n;
+  }
+  return total;
+}
+
+int reef_merkle_build_dev(reef_ctx* c, const uint64_t* doc_dev, uint64_t n_doc, void* levels_dev, uint64_t* level_sizes,
+                          uint32_t* n_levels, uint8_t out_root[32]) {
+  REEF_REQUIRE(c && doc_dev && levels_dev && out_root, REEF_EINVAL, "reef_merkle_build_dev: NULL argument");
+  REEF_REQUIRE(n_doc >= 1, REEF_EASSERT, "reef_merkle_build: empty document (index out of bounds)");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  uint64_t sizes[64];
+  uint32_t nl = 0;
+  int rc = launch_merkle(c, doc_dev, n_doc, levels_dev, sizes, &nl);
+  if (rc) return rc;
+  const uint64_t total = reef_merkle_tree_elems(n_doc);
+  void* hs;
+  rc = ctx_stage(c, 32, &hs);
+  if (rc) return rc;
+  REEF_CUDA(cudaMemcpyAsync(hs, (const char*)levels_dev + (total - 1) * 32, 32, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaStreamSynchronize(c->stream));
+  memcpy(out_root, hs, 32);
+  if (level_sizes) memcpy(level_sizes, sizes, nl * sizeof(uint64_t));
+  if (n_levels) *n_levels = nl;
+  return REEF_OK;
+}
+
+int reef_merkle_build(reef_ctx* c, const uint64_t* doc, uint64_t n_doc, uint8_t* out_levels, uint64_t* level_sizes,
+                      uint32_t* n_levels, uint8_t out_root[32]) {
+  REEF_REQUIRE(c && doc && out_levels && out_root, REEF_EINVAL, "reef_merkle_build: NULL argument");
+  REEF_REQUIRE(n_doc >= 1, REEF_EASSERT, "reef_merkle_build: empty document (index out of bounds)");
+  const uint64_t total = reef_merkle_tree_elems(n_doc);
+  void* base;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    REEF_CUDA(cudaSetDevice(c->device));
+    const size_t doc_bytes = ((size_t)n_doc * 8 + 255) & ~(size_t)255;
+    int rc = ctx_scratch2(c, doc_bytes + (size_t)total * 32, &base);
+    if (rc) return rc;
+    REEF_CUDA(cudaMemcpyAsync(base, doc, (size_t)n_doc * 8, cudaMemcpyHostToDevice, c->stream));
+  }
+  const size_t doc_bytes = ((size_t)n_doc * 8 + 255) & ~(size_t)255;
+  char* d_levels = (char*)base + doc_bytes;
+  int rc = reef_merkle_build_dev(c, (const uint64_t*)base, n_doc, d_levels, level_sizes, n_levels, out_root);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaMemcpyAsync(out_levels, d_levels, (size_t)total * 32, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaStreamSynchronize(c->stream));
+  return REEF_OK;
+}
+
+int reef_merkle_path_wits(const uint64_t* doc, uint64_t n_doc, const uint8_t* levels, const uint64_t* level_sizes,
+                          uint32_t n_levels, uint64_t idx, uint8_t* l_or_r, uint8_t* has_idx, uint64_t* opposite_idx,
+                          uint8_t* opposite) {
+  REEF_REQUIRE(doc && levels && level_sizes && l_or_r && has_idx && opposite_idx && opposite, REEF_EINVAL,
+               "reef_merkle_path_wits: NULL argument");
+  if (idx >= n_doc) return fail(REEF_EASSERT, "assertion failed: idx < self.doc.len()");
+  auto put_u64 = [](uint8_t* o, uint64_t x) {
+    memset(o, 0, 32);
+    for (int i = 0; i < 8; i++) o[i] = (uint8_t)(x >> (8 * i));
+  };
+  // leaf entry (merkle_tree.rs:132-157)
+  has_idx[0] = 1;
+  if (idx % 2 == 0) {
+    l_or_r[0] = 1;
+    if (idx + 1 >= n_doc) {
+      opposite_idx[0] = 0;
+      put_u64(opposite, 0);
+    } else {
+      opposite_idx[0] = idx + 1;
+      put_u64(opposite, doc[idx + 1]);
+    }
+  } else {
+    l_or_r[0] = 0;
+    opposite_idx[0] = idx - 1;
+    put_u64(opposite, doc[idx - 1]);
+  }
+  // inner entries (merkle_tree.rs:159-188)
+  uint64_t quo = idx / 2;
+  const uint8_t* lvl = levels;
+  for (uint32_t h = 0; h + 1 < n_levels; h++) {
+    uint8_t* o = opposite + (size_t)(h + 1) * 32;
+    has_idx[h + 1] = 0;
+    opposite_idx[h + 1] = 0;
+    if (quo % 2 == 0) {
+      l_or_r[h + 1] = 1;
+      if (quo + 1 >= level_sizes[h]) memset(o, 0, 32);
+      else memcpy(o, lvl + (size_t)(quo + 1) * 32, 32);
+    } else {
+      l_or_r[h + 1] = 0;
+      memcpy(o, lvl + (size_t)(quo - 1) * 32, 32);
+    }
+    quo /= 2;
+    lvl += (size_t)level_sizes[h] * 32;
+  }
+  return REEF_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// B1: tables + nlookup
+// ---------------------------------------------------------------------------------------
+static uint64_t next_pow2(uint64_t n) {
+  uint64_t p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+static int table_new(reef_ctx* c, const void* host, uint64_t n, int is_u32, reef_table** out) {
+  REEF_REQUIRE(c && host && out, REEF_EINVAL, "reef_table_upload: NULL argument");
+  REEF_REQUIRE(n >= 1, REEF_EASSERT, "reef_table_upload: empty table (index out of bounds: table[0])");
+  const size_t esz = is_u32 ? 4 : 32;
+  if (!is_u32) {
+    int rc = check_canonical((const uint8_t*)host, n, "reef_table_upload");
+    if (rc) return rc;
+  }
+  uint64_t n_pad = next_pow2(n);
+  if (n_pad < 2) n_pad = 2;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, (size_t)n_pad * esz);
+  if (e != cudaSuccess) return fail(REEF_ENOMEM, std::string("reef_table_upload: ") + cudaGetErrorString(e));
+  e = cudaMemcpyAsync(d, host, (size_t)n * esz, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess && n_pad > n) e = cudaMemsetAsync((char*)d + (size_t)n * esz, 0, (size_t)(n_pad - n) * esz, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    return fail(REEF_ECUDA, std::string("reef_table_upload: ") + cudaGetErrorString(e));
+  }
+  reef_table* t = new reef_table;
+  t->ctx = c;
+  t->d = d;
+  t->n_pad = n_pad;
+  t->n_orig = n;
+  t->is_u32 = is_u32;
+  t->owns = 1;
+  memset(t->first, 0, 32);
+  memcpy(t->first, host, is_u32 ? 4 : 32);
+  *out = t;
+  return REEF_OK;
+}
+
+int reef_table_upload(reef_ctx* c, const uint8_t* table, uint64_t n, reef_table** out) { return table_new(c, table, n, 0, out); }
+int reef_table_upload_u32(reef_ctx* c, const uint32_t* codes, uint64_t n, reef_table** out) { return table_new(c, codes, n, 1, out); }
+
+int reef_table_wrap_dev(reef_ctx* c, void* dev_ptr, uint64_t n, int is_u32, reef_table** out) {
+  REEF_REQUIRE(c && dev_ptr && out, REEF_EINVAL, "reef_table_wrap_dev: NULL argument");
+  REEF_REQUIRE(n >= 2 && (n & (n - 1)) == 0, REEF_EINVAL, "reef_table_wrap_dev: length must be a power of two >= 2");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  reef_table* t = new reef_table;
+  t->ctx = c;
+  t->d = dev_ptr;
+  t->n_pad = t->n_orig = n;
+  t->is_u32 = is_u32 ? 1 : 0;
+  t->owns = 0;
+  memset(t->first, 0, 32);
+  cudaError_t e = cudaMemcpy(t->first, dev_ptr, is_u32 ? 4 : 32, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) {
+    delete t;
+    return fail(REEF_ECUDA, std::string("reef_table_wrap_dev: ") + cudaGetErrorString(e));
+  }
+  *out = t;
+  return REEF_OK;
+}
+
+int reef_table_download(const reef_table* t, uint8_t* out, uint64_t n) {
+  REEF_REQUIRE(t && out, REEF_EINVAL, "reef_table_download: NULL argument");
+  REEF_REQUIRE(!t->is_u32, REEF_EINVAL, "reef_table_download: u32 tables are not downloadable as field elements");
+  REEF_REQUIRE(n <= t->n_pad, REEF_EINVAL, "reef_table_download: n exceeds the table length");
+  reef_ctx* c = t->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  REEF_CUDA(cudaMemcpyAsync(out, t->d, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaStreamSynchronize(c->stream));
+  return REEF_OK;
+}
+
+uint64_t reef_table_len(const reef_table* t) { return t ? t->n_orig : 0; }
+
+void reef_table_free(reef_table* t) {
+  if (!t) return;
+  if (t->owns) {
+    std::lock_guard<std::mutex> lk(t->ctx->mu);
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    cudaFree(t->d);
+  }
+  delete t;
+}
+
+int reef_nlookup_prove(reef_ctx* c, int tag, const reef_table* table, const uint64_t* q, const uint8_t* v, uint32_t m,
+                       const uint8_t* prev_q, const uint8_t* prev_v, const uint8_t* doc_hash, reef_nlookup_out* out) {
+  REEF_REQUIRE(c && table && out, REEF_EINVAL, "reef_nlookup_prove: NULL argument");
+  REEF_REQUIRE(tag == REEF_TAG_NL || tag == REEF_TAG_NLDOC || tag == REEF_TAG_NLHYBRID, REEF_EASSERT, "weird tag");
+  REEF_REQUIRE(table->ctx == c, REEF_EINVAL, "reef_nlookup_prove: table belongs to another context");
+  REEF_REQUIRE(m == 0 || (q && v), REEF_EINVAL, "reef_nlookup_prove: NULL q/v");
+  REEF_REQUIRE(tag == REEF_TAG_NL || doc_hash, REEF_EINVAL, "reef_nlookup_prove: doc_hash required for nldoc/nlhybrid");
+  REEF_REQUIRE(out->claim_r && out->rounds && out->sc_last_claim && out->next_running_claim, REEF_EINVAL,
+               "reef_nlookup_prove: NULL output buffer");
+  // sc_l = logmn(table.len())  (r1cs.rs:2187)
+  const uint32_t ell = reef_logmn(table->n_orig);
+  const uint64_t n_full = ell < 63 ? ((uint64_t)1 << ell) : 0;
+  if (tag == REEF_TAG_NLDOC) {
+    // zero-padded to 2^logmn(len) (r1cs.rs:2322-2329)
+    if (n_full < table->n_orig) return fail(REEF_EASSERT, "attempt to subtract with overflow (f32 logmn)");
+  } else {
+    // linear_mle_product asserts table_t.len() == 2^ell (r1cs_helper.rs:450)
+    if (n_full != table->n_orig) return fail(REEF_EASSERT, "assertion failed: table_t.len() == base.pow(ell)");
+  }
+  REEF_REQUIRE(n_full == table->n_pad, REEF_EINVAL, "reef_nlookup_prove: padded table length does not match 2^logmn(len)");
+  REEF_REQUIRE(out->rounds_cap >= ell, REEF_EINVAL, "reef_nlookup_prove: rounds buffer too small");
+  out->ell = ell;
+
+  int rc;
+  if (m) {
+    rc = check_canonical(v, m, "reef_nlookup_prove: v");
+    if (rc) return rc;
+  }
+  std::vector<uint8_t> prevq((size_t)ell * 32, 0);
+  if (prev_q) {
+    rc = check_canonical(prev_q, ell, "reef_nlookup_prove: prev_q");
+    if (rc) return rc;
+    memcpy(prevq.data(), prev_q, (size_t)ell * 32);
+  }
+  uint8_t prevv[32];
+  if (prev_v) {
+    rc = check_canonical(prev_v, 1, "reef_nlookup_prove: prev_v");
+    if (rc) return rc;
+    memcpy(prevv, prev_v, 32);
+  } else {
+    memcpy(prevv, table->first, 32);
+  }
+  if (out->prev_running_claim) memcpy(out->prev_running_claim, prevv, 32);
+
+  // combined_q (r1cs.rs:2208-2249)
+  uint32_t num_cqs = 0;
+  std::vector<uint8_t> cqs((size_t)((uint64_t)m * ell / 254 + 2) * 32);
+  rc = reef_combined_q(q, m, ell, cqs.data(), (uint32_t)(cqs.size() / 32), &num_cqs);
+  if (rc) return rc;
+  out->num_cqs = num_cqs;
+  if (out->combined_q) {
+    REEF_REQUIRE(out->combined_q_cap >= num_cqs, REEF_EINVAL, "reef_nlookup_prove: combined_q buffer too small");
+    memcpy(out->combined_q, cqs.data(), (size_t)num_cqs * 32);
+  }
+
+  // IOPattern (r1cs.rs:2263-2282) and first absorb (r1cs.rs:2285-2306)
+  const bool with_hash = tag != REEF_TAG_NL;
+  const uint32_t first = m + ell + 1 + num_cqs + (with_hash ? 1 : 0);
+  std::vector<uint32_t> ops;
+  ops.push_back((1u << 31) | first);
+  ops.push_back(1);
+  for (uint32_t i = 0; i < ell; i++) {
+    ops.push_back((1u << 31) | 3u);
+    ops.push_back(1);
+  }
+  std::vector<uint8_t> query;
+  query.reserve((size_t)first * 32);
+  if (with_hash) {
+    rc = check_canonical(doc_hash, 1, "reef_nlookup_prove: doc_hash");
+    if (rc) return rc;
+    query.insert(query.end(), doc_hash, doc_hash + 32);
+  }
+  query.insert(query.end(), cqs.begin(), cqs.begin() + (size_t)num_cqs * 32);
+  if (m) query.insert(query.end(), v, v + (size_t)m * 32);
+  query.insert(query.end(), prevq.begin(), prevq.end());
+  query.insert(query.end(), prevv, prevv + 32);
+
+  NlookupArgs a;
+  a.tag = tag;
+  a.d_table = table->d;
+  a.table_is_u32 = table->is_u32;
+  a.n = table->n_pad;
+  a.ell = ell;
+  a.m = m;
+  a.h_q = q;
+  a.h_query = query.data();
+  a.n_query = first;
+  a.h_prev_q = prevq.data();
+  io_pattern_tag_le32(ops.data(), (uint32_t)ops.size(), 0, a.tag_le);
+  a.out_claim_r = out->claim_r;
+  a.out_rounds = out->rounds;
+  a.out_last_claim = out->sc_last_claim;
+  a.out_next_v = out->next_running_claim;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  return nlookup_run(c, a);
+}
+
+int reef_gen_eq_table(reef_ctx* c, const uint8_t* rs, const uint64_t* qs, uint32_t m, const uint8_t* last_q, uint32_t ell,
+                      uint8_t* out) {
+  REEF_REQUIRE(c && rs && last_q && out && (qs || m == 0), REEF_EINVAL, "reef_gen_eq_table: NULL argument");
+  REEF_REQUIRE(ell >= 1 && ell <= 30, REEF_EINVAL, "reef_gen_eq_table: ell out of range for a host output buffer");
+  int rc = check_canonical(rs, m + 1, "reef_gen_eq_table: rs");
+  if (rc) return rc;
+  rc = check_canonical(last_q, ell, "reef_gen_eq_table: last_q");
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  const uint64_t n = (uint64_t)1 << ell;
+  void* d_out;
+  rc = ctx_scratch2(c, (size_t)n * 32, &d_out);
+  if (rc) return rc;
+  rc = launch_gen_eq_table(c, rs, qs, m, last_q, ell, d_out);
+  if (rc) return rc;
+  REEF_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaStreamSynchronize(c->stream));
+  return REEF_OK;
+}
+
+int reef_linear_mle_product(reef_ctx* c, reef_table* tt, reef_table* te, uint32_t ell, uint32_t i, reef_sponge* sp,
+                            uint8_t out[128]) {
+  REEF_REQUIRE(c && tt && te && sp && out, REEF_EINVAL, "reef_linear_mle_product: NULL argument");
+  REEF_REQUIRE(!tt->is_u32 && !te->is_u32, REEF_EINVAL, "reef_linear_mle_product: tables must hold field elements");
+  REEF_REQUIRE(ell >= 1 && ell < 63, REEF_EINVAL, "reef_linear_mle_product: ell out of range");
+  const uint64_t n = (uint64_t)1 << ell;
+  if (tt->n_pad != n || te->n_pad != n) return fail(REEF_EASSERT, "assertion failed: table.len() == base.pow(ell)");
+  uint8_t g[96];  // (xsq, x, con)
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    REEF_CUDA(cudaSetDevice(c->device));
+    int rc = launch_mle_round_coeffs(c, tt->d, te->d, ell, i, g);
+    if (rc) return rc;
+  }
+  uint8_t query[96];  // absorb [con, x, xsq]  (r1cs_helper.rs:479-486)
+  memcpy(query, g + 64, 32);
+  memcpy(query + 32, g + 32, 32);
+  memcpy(query + 64, g, 32);
+  int rc = reef_sponge_absorb(sp, query, 3);
+  if (rc) return rc;
+  uint8_t r[32];
+  rc = reef_sponge_squeeze(sp, 1, r);
+  if (rc) return rc;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    rc = launch_mle_round_fold(c, tt->d, te->d, ell, i, r);
+    if (rc) return rc;
+    REEF_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  memcpy(out, r, 32);
+  memcpy(out + 32, g, 96);
+  return REEF_OK;
+}
+
+int reef_verifier_mle_eval(reef_ctx* c, const reef_table* t, const uint8_t* q, uint32_t ell, uint8_t out[32]) {
+  REEF_REQUIRE(c && t && q && out, REEF_EINVAL, "reef_verifier_mle_eval: NULL argument");
+  // prover_mle_partial_eval asserts 2^(m-1) <= prods.len() <= 2^m  (r1cs_helper.rs:562-563)
+  if (ell < 1 || ell > 62 || ((uint64_t)1 << (ell - 1)) > t->n_orig || ((uint64_t)1 << ell) < t->n_orig)
+    return fail(REEF_EASSERT, "assertion failed: base.pow(m - 1) <= prods.len() <= base.pow(m)");
+  int rc = check_canonical(q, ell, "reef_verifier_mle_eval: q");
+  if (rc) return rc;
+  REEF_REQUIRE(t->n_pad == ((uint64_t)1 << ell), REEF_EINVAL, "reef_verifier_mle_eval: padded length mismatch");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  return launch_mle_eval(c, t->d, t->is_u32, t->n_pad, q, ell, out);
+}
+
+int reef_prover_mle_partial_eval(reef_ctx* c, const reef_table* t, const uint8_t* x, uint32_t ell, int32_t hole,
+                                 uint8_t out_coeff[32], uint8_t out_const[32]) {
+  REEF_REQUIRE(c && t && x && out_coeff && out_const, REEF_EINVAL, "reef_prover_mle_partial_eval: NULL argument");
+  REEF_REQUIRE(hole >= -1 && hole < (int32_t)ell, REEF_EINVAL, "reef_prover_mle_partial_eval: hole index out of range");
+  if (hole < 0) {
+    // (crap, full result): the reference returns hole_coeff = -minus_coeff here
+    int rc = reef_verifier_mle_eval(c, t, x, ell, out_const);
+    if (rc) return rc;
+    // hole_coeff = 0 - minus_coeff  (mod q)
+    uint32_t borrow = 0;
+    bool zero = true;
+    for (int i = 0; i < 32; i++) zero = zero && out_const[i] == 0;
+    if (zero) {
+      memset(out_coeff, 0, 32);
+    } else {
+      for (int i = 0; i < 32; i++) {
+        int d = (int)FQ_LE[i] - (int)out_const[i] - (int)borrow;
+        borrow = d < 0;
+        out_coeff[i] = (uint8_t)(d + (borrow ? 256 : 0));
+      }
+    }
+    return REEF_OK;
+  }
+  std::vector<uint8_t> xx(x, x + (size_t)ell * 32);
+  uint8_t c0[32], c1[32];
+  memset(&xx[(size_t)hole * 32], 0, 32);
+  int rc = reef_verifier_mle_eval(c, t, xx.data(), ell, c0);
+  if (rc) return rc;
+  xx[(size_t)hole * 32] = 1;
+  rc = reef_verifier_mle_eval(c, t, xx.data(), ell, c1);
+  if (rc) return rc;
+  // coeff = c1 - c0 (mod q)
+  int borrow = 0;
+  uint8_t d[32];
+  for (int i = 0; i < 32; i++) {
+    int v = (int)c1[i] - (int)c0[i] - borrow;
+    borrow = v < 0;
+    d[i] = (uint8_t)(v + (borrow ? 256 : 0));
+  }
+  if (borrow) {
+    int carry = 0;
+    for (int i = 0; i < 32; i++) {
+      int v = (int)d[i] + (int)FQ_LE[i] + carry;
+      d[i] = (uint8_t)v;
+      carry = v >> 8;
+    }
+  }
+  memcpy(out_coeff, d, 32);
+  memcpy(out_const, c0, 32);
+  return REEF_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// test hooks (include/reef_b200_testing.h): host evaluation of the SHARED __host__ __device__
+// field / permutation code so its structure is unit-tested without a GPU.  Not a product path.
+// ---------------------------------------------------------------------------------------
+int reef_hosttest_field_op(int field, int op, const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) {
+  if (field == 0) hosttest_field_op<FqCfg>(op, a, b, out);
+  else hosttest_field_op<FpCfg>(op, a, b, out);
+  return 0;
+}
+
+int reef_hosttest_mul_wide(const uint8_t a[32], const uint8_t b[32], uint8_t out[64]) {
+  uint32_t x[8], y[8], r[16];
+  load_le(x, a);
+  load_le(y, b);
+  mul_wide(r, x, y);
+  store_le(out, r);
+  store_le(out + 32, r + 8);
+  return 0;
+}
+
+int reef_hosttest_poseidon_permute(const uint8_t in[160], uint8_t out[160]) {
+  Fq s[5];
+  for (int i = 0; i < 5; i++) {
+    load_le(s[i].v, in + 32 * i);
+    s[i] = to_mont<FqCfg>(s[i]);
+  }
+  poseidon_permute_host(s);
+  for (int i = 0; i < 5; i++) {
+    Fq o = from_mont<FqCfg>(s[i]);
+    store_le(out + 32 * i, o.v);
+  }
+  return 0;
+}
+
+}  // extern "C"

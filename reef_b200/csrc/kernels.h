@@ -1,0 +1,52 @@
+// Internal launcher declarations shared between the translation units of libreef_b200.
+#pragma once
+#include <cstdint>
+
+#include "common.cuh"
+
+namespace reef {
+
+// ---- poseidon.cu
+void io_pattern_tag_le32(const uint32_t* ops, uint32_t n_ops, uint32_t domain_separator, uint8_t out[32]);
+Fq fq_mont_from_le32(const uint8_t* b);
+void poseidon_tables_host(PoseidonTables* t);
+void poseidon_permute_host(Fq* s);
+int poseidon_upload_constants(reef_ctx* c);
+int launch_hash_batch(reef_ctx* c, const void* d_in, int arity, uint64_t n, void* d_out);
+int launch_merkle(reef_ctx* c, const uint64_t* d_doc, uint64_t n_doc, void* d_levels, uint64_t* level_sizes,
+                  uint32_t* n_levels_out);
+int launch_sponge_run(reef_ctx* c, const uint32_t* d_ops, uint32_t n_ops, const void* d_in, const uint8_t tag_le[32],
+                      void* d_out);
+
+int sponge_state_bytes();
+int launch_sponge_step(reef_ctx* c, void* d_state, int op, const void* d_in, uint32_t n, const uint8_t* tag_le,
+                       void* d_out);
+
+// ---- mle.cu
+struct NlookupArgs {
+  int tag;                 // 0 = nl, 1 = nldoc, 2 = nlhybrid
+  const void* d_table;     // device: Fq canonical (32 B) or u32 codes
+  int table_is_u32;
+  uint64_t n;              // padded length, power of two
+  uint32_t ell;            // log2(n) (logmn semantics applied by the caller)
+  uint32_t m;              // number of lookups
+  const uint64_t* h_q;     // host: m indices
+  const uint8_t* h_query;  // host: canonical 32-byte elements absorbed first (already ordered)
+  uint32_t n_query;
+  const uint8_t* h_prev_q; // host: ell x 32 bytes (prev_running_q, index 0 <-> MSB)
+  uint8_t tag_le[32];      // IOPattern tag
+  // outputs (host)
+  uint8_t* out_claim_r;    // 32
+  uint8_t* out_rounds;     // ell x 4 x 32: (sc_r, xsq, x, const)
+  uint8_t* out_last_claim; // 32
+  uint8_t* out_next_v;     // 32
+};
+int nlookup_run(reef_ctx* c, const NlookupArgs& a);
+int launch_gen_eq_table(reef_ctx* c, const uint8_t* h_rs, const uint64_t* h_qs, uint32_t m, const uint8_t* h_last_q,
+                        uint32_t ell, void* d_out);
+int launch_mle_eval(reef_ctx* c, const void* d_table, int is_u32, uint64_t n, const uint8_t* h_x, uint32_t ell,
+                    uint8_t* h_out);
+int launch_mle_round_coeffs(reef_ctx* c, const void* d_t, const void* d_eq, uint32_t ell, uint32_t i, uint8_t* h_out3);
+int launch_mle_round_fold(reef_ctx* c, void* d_t, void* d_eq, uint32_t ell, uint32_t i, const uint8_t* h_r);
+
+}  // namespace reef

@@ -1,0 +1,656 @@
+// nlookup sum-check prover: fused MLE sweeps over HBM with a device-side Fiat-Shamir sponge.
+//
+// Reference behaviour reproduced bit-for-bit:
+//   gen_eq_table              /root/reference/src/backend/r1cs_helper.rs:508-544
+//   linear_mle_product        /root/reference/src/backend/r1cs_helper.rs:441-506
+//   prover_mle_partial_eval   /root/reference/src/backend/r1cs_helper.rs:551-634
+//   wit_nlookup_gadget        /root/reference/src/backend/r1cs.rs:2260-2392
+//
+// Schedule (B200-first; none of this shape exists in the reference, only its results do):
+//   * The dense part of the eq table is a tensor product  EQ[i] = A[i >> h] * B[i & (2^h-1)]
+//     (h = 10).  It is NEVER materialised: every pass streams only the T table and takes
+//     row-wise inner products with the L2-resident 32 KiB B table; the tiny A table is folded
+//     by the transcript kernel each round.  Per round:
+//         U0[row] = sum_lo T[row,lo] B[lo],  U1[row] = sum_lo T[row + half,lo] B[lo]
+//         const = sum A0 U0,  g(1) = sum A1 U1,  xsq = sum (A1-A0)(U1-U0),  x = g(1)-const-xsq
+//   * The m "lookup" points  rs[k] * [i == q_k]  of the eq table are carried as a sparse list
+//     and added analytically to each round's coefficients (m gathers per round).
+//   * Pass i+1 folds T with r_i and accumulates round i+1 in the same sweep (reads 2 elements,
+//     writes 1 per output), so HBM traffic is ~4N elements instead of the reference-shaped 10N.
+//   * When the live table reaches 2^h entries, one CTA finishes all remaining rounds out of
+//     shared memory.
+//   * Fiat-Shamir runs on device (warp-cooperative Poseidon), so a whole nlookup is a chain of
+//     stream-ordered launches with no host round trip.
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace reef {
+
+static constexpr int H_BITS = 10;
+static constexpr int CHUNK = 1 << H_BITS;  // b-values per CTA in a sweep
+static constexpr int SWEEP_THREADS = 128;
+static constexpr int MAX_ELL = 48;
+
+// Device-resident state of one nlookup session.
+struct NlState {
+  Fq sponge[5];          // Montgomery form
+  Fq r_mont;             // challenge of the last finished round (Montgomery form)
+  Fq rm_mont;            // rs[m] = claim_r^(m+1)
+  Fq lq_mont[MAX_ELL];   // last_q[j]  (bit j of the table index), Montgomery form
+  Fq out_claim_r;        // canonical outputs
+  Fq out_rounds[MAX_ELL][4];
+  Fq out_last_claim;
+  Fq out_next_v;
+  Fq a_scalar;           // A table when it has a single entry (ell <= h)
+};
+
+// ---------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ Fq fq_from_u32(uint32_t x) {
+  Fq r = fe_zero<FqCfg>();
+  r.v[0] = x;
+  return r;
+}
+
+template <bool U32IN>
+__device__ __forceinline__ Fq load_t(const void* t, uint64_t idx) {
+  if constexpr (U32IN) return fq_from_u32(((const uint32_t*)t)[idx]);
+  else return ld256((const Fq*)t + idx);
+}
+
+// x0 + r * (x1 - x0), x canonical, r Montgomery -> canonical
+__device__ __forceinline__ Fq fold_one(const Fq& x0, const Fq& x1, const Fq& r_mont) {
+  return fe_add<FqCfg>(x0, mont_mul<FqCfg>(r_mont, fe_sub<FqCfg>(x1, x0)));
+}
+
+// Block-wide sum (mod p) of NV field elements per thread; result valid on thread 0.
+template <int NV, int NTHREADS>
+__device__ __forceinline__ void block_sum(Fq* vals, Fq* smem /* NV * NTHREADS/32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; k++) vals[k] = warp_sum_fe<FqCfg>(vals[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) smem[warp * NV + k] = vals[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll 1
+    for (int w = 1; w < NTHREADS / 32; w++) {
+#pragma unroll
+      for (int k = 0; k < NV; k++) vals[k] = fe_add<FqCfg>(vals[k], smem[w * NV + k]);
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// k_nl_begin: first absorb + claim_r, powers of claim_r, sparse list, selector table
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_nl_begin(NlState* st, const Fq* __restrict__ query, uint32_t n_query, Fq tag,
+                                                 const Fq* __restrict__ prev_q, uint32_t ell, const uint64_t* __restrict__ q,
+                                                 uint32_t m, uint64_t* __restrict__ sp_pos, Fq* __restrict__ sp_w,
+                                                 const PoseidonTables* __restrict__ K) {
+  const int lane = threadIdx.x;
+  Fq s = fe_zero<FqCfg>();
+  if (lane == 0) s = tag;
+  uint32_t apos = 0;
+  for (uint32_t e = 0; e < n_query; e++) {
+    if (apos == 4) {
+      poseidon_permute_warp5(s, K);
+      apos = 0;
+    }
+    Fq x = to_mont<FqCfg>(ld256(query + e));
+    Fq sum = fe_add<FqCfg>(s, x);
+    if (lane == (int)(1 + apos)) s = sum;
+    apos++;
+  }
+  poseidon_permute_warp5(s, K);   // squeeze(1): always permutes after an absorb
+  if (lane < 5) st->sponge[lane] = s;
+  Fq claim = shfl_fq(s, 1);       // Montgomery form
+  if (lane == 0) {
+    st->out_claim_r = from_mont<FqCfg>(claim);
+    Fq pw = claim;                // rs[0] = claim_r
+    for (uint32_t k = 0; k < m; k++) {
+      sp_w[k] = pw;
+      sp_pos[k] = q[k];
+      pw = mont_mul<FqCfg>(pw, claim);
+    }
+    st->rm_mont = pw;             // rs[m]
+  }
+  // last_q[j] = prev_running_q[ell-1-j]   (r1cs.rs:2318-2319 passes the reversed vector)
+  for (uint32_t j = lane; j < ell; j += 32) st->lq_mont[j] = to_mont<FqCfg>(ld256(prev_q + (ell - 1 - j)));
+}
+
+// ---------------------------------------------------------------------------------------
+// k_eq_tables: A[hi] = rs[m] * prod_{j>=h} sel(bit_{j-h}(hi), lq[j]),  B[lo] = prod_{j<h} sel(bit_j(lo), lq[j])
+// (both in Montgomery form).  When ell <= h, A is the single entry rs[m] and B spans all bits.
+// ---------------------------------------------------------------------------------------
+__global__ void k_eq_tables(const NlState* __restrict__ st, uint32_t ell, uint32_t hb, Fq* __restrict__ A,
+                            uint64_t a_len, Fq* __restrict__ B, uint64_t b_len) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a_len + b_len) return;
+  const Fq one = fe_one<FqCfg>();
+  if (i < a_len) {
+    Fq acc = st->rm_mont;
+    for (uint32_t j = hb; j < ell; j++) {
+      Fq lq = st->lq_mont[j];
+      Fq f = ((i >> (j - hb)) & 1) ? lq : fe_sub<FqCfg>(one, lq);
+      acc = mont_mul<FqCfg>(acc, f);
+    }
+    A[i] = acc;
+  } else {
+    uint64_t lo = i - a_len;
+    Fq acc = one;
+    for (uint32_t j = 0; j < hb; j++) {
+      Fq lq = st->lq_mont[j];
+      Fq f = ((lo >> j) & 1) ? lq : fe_sub<FqCfg>(one, lq);
+      acc = mont_mul<FqCfg>(acc, f);
+    }
+    B[lo] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_sweep: (optional fold with r) + row-wise inner products with B; one CTA per 2^h b-values.
+//   L_in  length of Tin; L = FOLD ? L_in/2 : L_in is the accumulation length, half = L/2 >= 2^h.
+//   partials[blk][3] = (const, g(1), xsq) contributions of this CTA (canonical).
+// ---------------------------------------------------------------------------------------
+template <bool U32IN, bool FOLD>
+__global__ void __launch_bounds__(SWEEP_THREADS)
+k_sweep(const void* Tin, uint64_t L_in, Fq* Tout, const NlState* __restrict__ st,
+        const Fq* __restrict__ A, const Fq* __restrict__ B, Fq* __restrict__ partials) {
+  __shared__ Fq red[2 * SWEEP_THREADS / 32];
+  const uint64_t L = FOLD ? (L_in >> 1) : L_in;
+  const uint64_t half = L >> 1;
+  const uint64_t b0 = (uint64_t)blockIdx.x * CHUNK;
+  Fq r;
+  if constexpr (FOLD) r = st->r_mont;
+  Wide17 U0, U1;
+  wide_zero(U0);
+  wide_zero(U1);
+#pragma unroll 2
+  for (int k = 0; k < CHUNK / SWEEP_THREADS; k++) {
+    const uint32_t lo = k * SWEEP_THREADS + threadIdx.x;
+    const uint64_t b = b0 + lo;
+    Fq t0, t1;
+    if constexpr (FOLD) {
+      Fq x00 = load_t<U32IN>(Tin, b), x01 = load_t<U32IN>(Tin, b + L);
+      Fq x10 = load_t<U32IN>(Tin, b + half), x11 = load_t<U32IN>(Tin, b + half + L);
+      t0 = fold_one(x00, x01, r);
+      t1 = fold_one(x10, x11, r);
+      st256(Tout + b, t0);
+      st256(Tout + b + half, t1);
+    } else {
+      t0 = load_t<U32IN>(Tin, b);
+      t1 = load_t<U32IN>(Tin, b + half);
+    }
+    Fq bv = ld256(B + lo);
+    if constexpr (U32IN && !FOLD) {
+      wide_mac_small(U0, t0.v[0], bv.v);
+      wide_mac_small(U1, t1.v[0], bv.v);
+    } else {
+      wide_mac(U0, t0.v, bv.v);
+      wide_mac(U1, t1.v, bv.v);
+    }
+  }
+  Fq u[2];
+  u[0] = wide_reduce_div_R<FqCfg>(U0);   // sum T*B  (B carries the Montgomery factor)
+  u[1] = wide_reduce_div_R<FqCfg>(U1);
+  block_sum<2, SWEEP_THREADS>(u, red);
+  if (threadIdx.x == 0) {
+    const uint64_t hi0 = b0 >> H_BITS;
+    Fq a0 = ld256(A + hi0), a1 = ld256(A + hi0 + (half >> H_BITS));
+    Fq* out = partials + (uint64_t)blockIdx.x * 3;
+    st256(out + 0, mont_mul<FqCfg>(a0, u[0]));
+    st256(out + 1, mont_mul<FqCfg>(a1, u[1]));
+    st256(out + 2, mont_mul<FqCfg>(fe_sub<FqCfg>(a1, a0), fe_sub<FqCfg>(u[1], u[0])));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_round: finish round `ri` (0-based): sum CTA partials, add the sparse-point terms, run the
+// transcript (absorb [const, x, xsq], squeeze r), fold A, advance the sparse list.
+// ---------------------------------------------------------------------------------------
+static constexpr int ROUND_THREADS = 128;
+
+template <bool U32IN>
+__global__ void __launch_bounds__(ROUND_THREADS)
+k_round(NlState* st, const Fq* __restrict__ partials, uint32_t nblk, const void* __restrict__ Tcur, uint64_t L,
+        Fq* A, uint64_t a_len, uint64_t* sp_pos, Fq* sp_w, uint32_t m, uint32_t ri,
+        const PoseidonTables* __restrict__ K) {
+  __shared__ Fq red[3 * ROUND_THREADS / 32];
+  __shared__ Fq r_sh;
+  const uint64_t half = L >> 1;
+  Fq acc[3];
+  acc[0] = acc[1] = acc[2] = fe_zero<FqCfg>();
+  for (uint32_t i = threadIdx.x; i < nblk; i += ROUND_THREADS) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) acc[k] = fe_add<FqCfg>(acc[k], ld256(partials + (uint64_t)i * 3 + k));
+  }
+  // sparse points: E = w at index pos.  (t0,t1) = T[b], T[b+half]; e0 = top?0:w, e1 = top?w:0.
+  for (uint32_t k = threadIdx.x; k < m; k += ROUND_THREADS) {
+    uint64_t pos = sp_pos[k];
+    bool top = pos >= half;
+    uint64_t b = top ? pos - half : pos;
+    Fq w = sp_w[k];
+    Fq t0 = load_t<U32IN>(Tcur, b), t1 = load_t<U32IN>(Tcur, b + half);
+    Fq wt = mont_mul<FqCfg>(w, top ? t1 : t0);        // canonical
+    Fq wd = mont_mul<FqCfg>(w, fe_sub<FqCfg>(t1, t0));
+    if (top) {
+      acc[1] = fe_add<FqCfg>(acc[1], wt);             // g(1) += t1 * w
+      acc[2] = fe_add<FqCfg>(acc[2], wd);             // xsq  += (t1-t0) * w
+    } else {
+      acc[0] = fe_add<FqCfg>(acc[0], wt);             // const += t0 * w
+      acc[2] = fe_sub<FqCfg>(acc[2], wd);             // xsq  += (t1-t0) * (-w)
+    }
+  }
+  block_sum<3, ROUND_THREADS>(acc, red);
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    Fq con = shfl_fq(acc[0], 0), g1 = shfl_fq(acc[1], 0), xsq = shfl_fq(acc[2], 0);
+    Fq x = fe_sub<FqCfg>(fe_sub<FqCfg>(g1, con), xsq);
+    // absorb [const, x, xsq] at rate positions 0,1,2 (absorb_pos is 0 after the previous squeeze)
+    Fq s = lane < 5 ? st->sponge[lane] : fe_zero<FqCfg>();
+    Fq e = lane == 1 ? con : (lane == 2 ? x : xsq);
+    Fq sum = fe_add<FqCfg>(s, to_mont<FqCfg>(e));
+    if (lane >= 1 && lane <= 3) s = sum;
+    poseidon_permute_warp5(s, K);
+    if (lane < 5) st->sponge[lane] = s;
+    Fq r = shfl_fq(s, 1);
+    if (lane == 0) {
+      st->r_mont = r;
+      r_sh = r;
+      st->out_rounds[ri][0] = from_mont<FqCfg>(r);
+      st->out_rounds[ri][1] = xsq;
+      st->out_rounds[ri][2] = x;
+      st->out_rounds[ri][3] = con;
+    }
+  }
+  __syncthreads();
+  const Fq r = r_sh;
+  // fold the A table over its top bit (in place: entry x only depends on x and x + a_len/2)
+  if (a_len > 1) {
+    const uint64_t ah = a_len >> 1;
+    for (uint64_t x = threadIdx.x; x < ah; x += ROUND_THREADS) {
+      Fq lo = A[x], hi = A[x + ah];
+      A[x] = fe_add<FqCfg>(lo, mont_mul<FqCfg>(r, fe_sub<FqCfg>(hi, lo)));
+    }
+  }
+  for (uint32_t k = threadIdx.x; k < m; k += ROUND_THREADS) {
+    uint64_t pos = sp_pos[k];
+    bool top = pos >= half;
+    Fq f = top ? r : fe_sub<FqCfg>(fe_one<FqCfg>(), r);
+    sp_w[k] = mont_mul<FqCfg>(sp_w[k], f);
+    sp_pos[k] = top ? pos - half : pos;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_tail: one CTA finishes the sum-check out of shared memory (live length <= 2^h).
+// ---------------------------------------------------------------------------------------
+static constexpr int TAIL_THREADS = 256;
+
+template <bool U32IN>
+__global__ void __launch_bounds__(TAIL_THREADS)
+k_tail(NlState* st, const void* __restrict__ Tin, uint64_t L_in, int do_fold, const Fq* __restrict__ A,
+       const Fq* __restrict__ B, const uint64_t* __restrict__ sp_pos, const Fq* __restrict__ sp_w, uint32_t m,
+       uint32_t ri0, const PoseidonTables* __restrict__ K) {
+  extern __shared__ __align__(32) unsigned char tail_smem[];
+  Fq* Ts = reinterpret_cast<Fq*>(tail_smem);   // canonical
+  Fq* Es = Ts + CHUNK;                         // Montgomery form
+  Fq* red = Es + CHUNK;                        // 3 * TAIL_THREADS/32
+  __shared__ Fq r_sh;
+  uint64_t L = do_fold ? (L_in >> 1) : L_in;   // <= CHUNK
+  const Fq a0 = A[0];
+  const Fq rf = st->r_mont;
+  for (uint64_t b = threadIdx.x; b < L; b += TAIL_THREADS) {
+    Fq t = do_fold ? fold_one(load_t<U32IN>(Tin, b), load_t<U32IN>(Tin, b + L), rf) : load_t<U32IN>(Tin, b);
+    Ts[b] = t;
+    Es[b] = mont_mul<FqCfg>(a0, B[b]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (uint32_t k = 0; k < m; k++) Es[sp_pos[k]] = fe_add<FqCfg>(Es[sp_pos[k]], sp_w[k]);
+  }
+  __syncthreads();
+  uint32_t ri = ri0;
+  Fq last_xsq = fe_zero<FqCfg>(), last_x = last_xsq, last_con = last_xsq;
+  while (L > 1) {
+    const uint64_t half = L >> 1;
+    Fq acc[3];
+    acc[0] = acc[1] = acc[2] = fe_zero<FqCfg>();
+    for (uint64_t b = threadIdx.x; b < half; b += TAIL_THREADS) {
+      Fq t0 = Ts[b], t1 = Ts[b + half], e0 = Es[b], e1 = Es[b + half];
+      acc[0] = fe_add<FqCfg>(acc[0], mont_mul<FqCfg>(e0, t0));
+      acc[1] = fe_add<FqCfg>(acc[1], mont_mul<FqCfg>(e1, t1));
+      acc[2] = fe_add<FqCfg>(acc[2], mont_mul<FqCfg>(fe_sub<FqCfg>(e1, e0), fe_sub<FqCfg>(t1, t0)));
+    }
+    block_sum<3, TAIL_THREADS>(acc, red);
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      Fq con = shfl_fq(acc[0], 0), g1 = shfl_fq(acc[1], 0), xsq = shfl_fq(acc[2], 0);
+      Fq x = fe_sub<FqCfg>(fe_sub<FqCfg>(g1, con), xsq);
+      Fq s = lane < 5 ? st->sponge[lane] : fe_zero<FqCfg>();
+      Fq e = lane == 1 ? con : (lane == 2 ? x : xsq);
+      Fq sum = fe_add<FqCfg>(s, to_mont<FqCfg>(e));
+      if (lane >= 1 && lane <= 3) s = sum;
+      poseidon_permute_warp5(s, K);
+      if (lane < 5) st->sponge[lane] = s;
+      Fq r = shfl_fq(s, 1);
+      if (lane == 0) {
+        r_sh = r;
+        st->r_mont = r;
+        st->out_rounds[ri][0] = from_mont<FqCfg>(r);
+        st->out_rounds[ri][1] = xsq;
+        st->out_rounds[ri][2] = x;
+        st->out_rounds[ri][3] = con;
+        last_xsq = xsq;
+        last_x = x;
+        last_con = con;
+      }
+    }
+    __syncthreads();
+    const Fq r = r_sh;
+    for (uint64_t b = threadIdx.x; b < half; b += TAIL_THREADS) {
+      Fq t0 = Ts[b], t1 = Ts[b + half], e0 = Es[b], e1 = Es[b + half];
+      Fq tn = fold_one(t0, t1, r);
+      Fq en = fe_add<FqCfg>(e0, mont_mul<FqCfg>(r, fe_sub<FqCfg>(e1, e0)));
+      Ts[b] = tn;   // each b is owned by exactly one thread; reads of b+half happen before
+      Es[b] = en;   // any write to indices >= half (none are written this round)
+    }
+    __syncthreads();
+    L = half;
+    ri++;
+  }
+  if (threadIdx.x == 0) {
+    // last_claim = g(r) = xsq r^2 + x r + const      (r1cs.rs:2373-2376)
+    const Fq r = r_sh;
+    Fq t = fe_add<FqCfg>(mont_mul<FqCfg>(r, last_xsq), last_x);   // xsq*r + x   (canonical)
+    Fq lc = fe_add<FqCfg>(mont_mul<FqCfg>(r, t), last_con);
+    st->out_last_claim = lc;
+    st->out_next_v = Ts[0];                                       // = T~(sc_rs)  (r1cs.rs:2379-2385)
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------------------
+static unsigned ceil_div_u(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+template <bool U32IN>
+static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
+  const uint32_t ell = a.ell;
+  const uint64_t N = a.n;
+  const uint32_t m = a.m;
+  const uint32_t hb = ell < (uint32_t)H_BITS ? ell : (uint32_t)H_BITS;
+  const uint64_t a_len = (uint64_t)1 << (ell - hb);
+  const uint64_t b_len = (uint64_t)1 << hb;
+  const uint32_t n_sweeps = ell > (uint32_t)H_BITS ? ell - H_BITS : 0;
+  const uint64_t max_blk = n_sweeps ? (N / 2) / CHUNK : 1;
+
+  // scratch layout
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  size_t o_state = take(sizeof(NlState));
+  size_t o_query = take((size_t)a.n_query * 32);
+  size_t o_prevq = take((size_t)ell * 32);
+  size_t o_q = take((size_t)m * 8);
+  size_t o_pos = take((size_t)m * 8);
+  size_t o_w = take((size_t)m * 32);
+  size_t o_A = take(a_len * 32);
+  size_t o_B = take(b_len * 32);
+  size_t o_part = take(max_blk * 3 * 32);
+  size_t o_fold = take(n_sweeps ? (N / 2) * 32 : 32);
+  void* base;
+  int rc = ctx_scratch(c, off, &base);
+  if (rc) return rc;
+  char* d = (char*)base;
+  NlState* st = (NlState*)(d + o_state);
+  Fq* d_query = (Fq*)(d + o_query);
+  Fq* d_prevq = (Fq*)(d + o_prevq);
+  uint64_t* d_q = (uint64_t*)(d + o_q);
+  uint64_t* d_pos = (uint64_t*)(d + o_pos);
+  Fq* d_w = (Fq*)(d + o_w);
+  Fq* d_A = (Fq*)(d + o_A);
+  Fq* d_B = (Fq*)(d + o_B);
+  Fq* d_part = (Fq*)(d + o_part);
+  Fq* d_fold = (Fq*)(d + o_fold);
+  cudaStream_t s = c->stream;
+
+  REEF_CUDA(cudaMemcpyAsync(d_query, a.h_query, (size_t)a.n_query * 32, cudaMemcpyHostToDevice, s));
+  REEF_CUDA(cudaMemcpyAsync(d_prevq, a.h_prev_q, (size_t)ell * 32, cudaMemcpyHostToDevice, s));
+  if (m) REEF_CUDA(cudaMemcpyAsync(d_q, a.h_q, (size_t)m * 8, cudaMemcpyHostToDevice, s));
+
+  Fq tag = fq_mont_from_le32(a.tag_le);
+  k_nl_begin<<<1, 32, 0, s>>>(st, d_query, a.n_query, tag, d_prevq, ell, d_q, m, d_pos, d_w, c->d_pos);
+  REEF_CUDA(cudaGetLastError());
+  k_eq_tables<<<ceil_div_u(a_len + b_len, 128), 128, 0, s>>>(st, ell, hb, d_A, a_len, d_B, b_len);
+  REEF_CUDA(cudaGetLastError());
+
+  // sweep rounds 1 .. ell-h
+  const void* t_cur = a.d_table;
+  uint64_t L = N;                // accumulation length of the current round
+  uint64_t a_cur = a_len;
+  for (uint32_t i = 0; i < n_sweeps; i++) {
+    const uint32_t nblk = (uint32_t)((L / 2) / CHUNK);
+    if (i == 0) {
+      k_sweep<U32IN, false><<<nblk, SWEEP_THREADS, 0, s>>>(a.d_table, N, nullptr, st, d_A, d_B, d_part);
+      REEF_CUDA(cudaGetLastError());
+      k_round<U32IN><<<1, ROUND_THREADS, 0, s>>>(st, d_part, nblk, a.d_table, L, d_A, a_cur, d_pos, d_w, m, i, c->d_pos);
+    } else {
+      if (i == 1) k_sweep<U32IN, true><<<nblk, SWEEP_THREADS, 0, s>>>(a.d_table, 2 * L, d_fold, st, d_A, d_B, d_part);
+      else k_sweep<false, true><<<nblk, SWEEP_THREADS, 0, s>>>(d_fold, 2 * L, d_fold, st, d_A, d_B, d_part);
+      REEF_CUDA(cudaGetLastError());
+      k_round<false><<<1, ROUND_THREADS, 0, s>>>(st, d_part, nblk, d_fold, L, d_A, a_cur, d_pos, d_w, m, i, c->d_pos);
+      t_cur = d_fold;
+    }
+    REEF_CUDA(cudaGetLastError());
+    if (a_cur > 1) a_cur >>= 1;
+    L >>= 1;
+  }
+  // tail: fold with the last sweep challenge (if any) and finish
+  const size_t tail_smem = (size_t)(2 * CHUNK + 3 * TAIL_THREADS / 32) * sizeof(Fq);
+  if (n_sweeps == 0) {
+    REEF_CUDA(cudaFuncSetAttribute(k_tail<U32IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
+    k_tail<U32IN><<<1, TAIL_THREADS, tail_smem, s>>>(st, a.d_table, N, 0, d_A, d_B, d_pos, d_w, m, 0, c->d_pos);
+  } else if (n_sweeps == 1) {
+    // L is now 2^h: the table to fold is still the caller's (length 2L)
+    REEF_CUDA(cudaFuncSetAttribute(k_tail<U32IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
+    k_tail<U32IN><<<1, TAIL_THREADS, tail_smem, s>>>(st, a.d_table, 2 * L, 1, d_A, d_B, d_pos, d_w, m, n_sweeps, c->d_pos);
+  } else {
+    REEF_CUDA(cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
+    k_tail<false><<<1, TAIL_THREADS, tail_smem, s>>>(st, t_cur, 2 * L, 1, d_A, d_B, d_pos, d_w, m, n_sweeps, c->d_pos);
+  }
+  REEF_CUDA(cudaGetLastError());
+
+  // results
+  void* hs;
+  rc = ctx_stage(c, sizeof(NlState), &hs);
+  if (rc) return rc;
+  REEF_CUDA(cudaMemcpyAsync(hs, st, sizeof(NlState), cudaMemcpyDeviceToHost, s));
+  REEF_CUDA(cudaStreamSynchronize(s));
+  const NlState* h = (const NlState*)hs;
+  memcpy(a.out_claim_r, h->out_claim_r.v, 32);
+  for (uint32_t i = 0; i < ell; i++)
+    for (int k = 0; k < 4; k++) memcpy(a.out_rounds + ((size_t)i * 4 + k) * 32, h->out_rounds[i][k].v, 32);
+  memcpy(a.out_last_claim, h->out_last_claim.v, 32);
+  memcpy(a.out_next_v, h->out_next_v.v, 32);
+  return REEF_OK;
+}
+
+int nlookup_run(reef_ctx* c, const NlookupArgs& a) {
+  REEF_REQUIRE(a.ell >= 1 && a.ell <= (uint32_t)MAX_ELL, REEF_EINVAL, "nlookup: ell out of range");
+  REEF_REQUIRE(a.n == ((uint64_t)1 << a.ell), REEF_EINVAL, "nlookup: table length must be 2^ell");
+  for (uint32_t k = 0; k < a.m; k++)
+    REEF_REQUIRE(a.h_q[k] < a.n, REEF_EASSERT, "nlookup: lookup index out of range (index out of bounds)");
+  return a.table_is_u32 ? nlookup_run_t<true>(c, a) : nlookup_run_t<false>(c, a);
+}
+
+// ---------------------------------------------------------------------------------------
+// Reference-shaped standalone entry points (materialised tables), used by the parity tests
+// that mirror the reference's own unit tests (mle_partial, mle_linear_basic).
+// ---------------------------------------------------------------------------------------
+
+// eq[i] = rs[m] * prod_j sel(bit_j(i), last_q[j]); then eq[q_k] += rs[k]
+__global__ void k_eq_full(const Fq* __restrict__ rs_mont, const Fq* __restrict__ lq_mont, uint32_t ell, uint32_t m,
+                          Fq* __restrict__ out, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Fq one = fe_one<FqCfg>();
+  Fq acc = rs_mont[m];
+  for (uint32_t j = 0; j < ell; j++) {
+    Fq lq = lq_mont[j];
+    Fq f = ((i >> j) & 1) ? lq : fe_sub<FqCfg>(one, lq);
+    acc = mont_mul<FqCfg>(acc, f);
+  }
+  st256(out + i, from_mont<FqCfg>(acc));
+}
+
+__global__ void k_eq_scatter(const Fq* __restrict__ rs_mont, const uint64_t* __restrict__ qs, uint32_t m, Fq* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    for (uint32_t k = 0; k < m; k++) out[qs[k]] = fe_add<FqCfg>(out[qs[k]], from_mont<FqCfg>(rs_mont[k]));
+}
+
+__global__ void k_to_mont(Fq* x, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = to_mont<FqCfg>(x[i]);
+}
+
+int launch_gen_eq_table(reef_ctx* c, const uint8_t* h_rs, const uint64_t* h_qs, uint32_t m, const uint8_t* h_last_q,
+                        uint32_t ell, void* d_out) {
+  REEF_REQUIRE(ell >= 1 && ell <= (uint32_t)MAX_ELL, REEF_EINVAL, "gen_eq_table: ell out of range");
+  const uint64_t n = (uint64_t)1 << ell;
+  for (uint32_t k = 0; k < m; k++) REEF_REQUIRE(h_qs[k] < n, REEF_EASSERT, "gen_eq_table: index out of bounds");
+  size_t bytes = (size_t)(m + 1) * 32 + (size_t)ell * 32 + (size_t)m * 8 + 512;
+  void* base;
+  int rc = ctx_scratch(c, bytes, &base);
+  if (rc) return rc;
+  Fq* d_rs = (Fq*)base;
+  Fq* d_lq = d_rs + (m + 1);
+  uint64_t* d_qs = (uint64_t*)(d_lq + ell);
+  cudaStream_t s = c->stream;
+  REEF_CUDA(cudaMemcpyAsync(d_rs, h_rs, (size_t)(m + 1) * 32, cudaMemcpyHostToDevice, s));
+  REEF_CUDA(cudaMemcpyAsync(d_lq, h_last_q, (size_t)ell * 32, cudaMemcpyHostToDevice, s));
+  if (m) REEF_CUDA(cudaMemcpyAsync(d_qs, h_qs, (size_t)m * 8, cudaMemcpyHostToDevice, s));
+  k_to_mont<<<ceil_div_u(m + 1 + ell, 128), 128, 0, s>>>(d_rs, m + 1 + ell);
+  REEF_CUDA(cudaGetLastError());
+  k_eq_full<<<ceil_div_u(n, 128), 128, 0, s>>>(d_rs, d_lq, ell, m, (Fq*)d_out, n);
+  REEF_CUDA(cudaGetLastError());
+  k_eq_scatter<<<1, 32, 0, s>>>(d_rs, d_qs, m, (Fq*)d_out);
+  REEF_CUDA(cudaGetLastError());
+  return REEF_OK;
+}
+
+// out[b] = in[b] + r (in[b+half] - in[b])
+template <bool U32IN>
+__global__ void k_fold(const void* __restrict__ in, Fq* __restrict__ out, uint64_t half, Fq r_mont) {
+  uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= half) return;
+  st256(out + b, fold_one(load_t<U32IN>(in, b), load_t<U32IN>(in, b + half), r_mont));
+}
+
+// T~(x), x[0] <-> top index bit  (verifier_mle_eval / prover_mle_partial_eval without a hole)
+int launch_mle_eval(reef_ctx* c, const void* d_table, int is_u32, uint64_t n, const uint8_t* h_x, uint32_t ell,
+                    uint8_t* h_out) {
+  REEF_REQUIRE(n == ((uint64_t)1 << ell) && ell >= 1, REEF_EINVAL, "mle_eval: table length must be 2^ell");
+  void* base;
+  int rc = ctx_scratch2(c, (size_t)(n / 2 + n / 4 + 2) * 32, &base);
+  if (rc) return rc;
+  Fq* buf0 = (Fq*)base;
+  Fq* buf1 = buf0 + n / 2 + 1;
+  cudaStream_t s = c->stream;
+  const void* cur = d_table;
+  uint64_t L = n;
+  for (uint32_t i = 0; i < ell; i++) {
+    Fq r = fq_mont_from_le32(h_x + (size_t)i * 32);
+    uint64_t half = L >> 1;
+    Fq* out = (i & 1) ? buf1 : buf0;
+    if (i == 0 && is_u32) k_fold<true><<<ceil_div_u(half, 128), 128, 0, s>>>(cur, out, half, r);
+    else k_fold<false><<<ceil_div_u(half, 128), 128, 0, s>>>(cur, out, half, r);
+    REEF_CUDA(cudaGetLastError());
+    cur = out;
+    L = half;
+  }
+  REEF_CUDA(cudaMemcpyAsync(h_out, cur, 32, cudaMemcpyDeviceToHost, s));
+  REEF_CUDA(cudaStreamSynchronize(s));
+  return REEF_OK;
+}
+
+// first loop of linear_mle_product on materialised tables: (xsq, x, const)
+__global__ void __launch_bounds__(128) k_round_coeffs(const Fq* __restrict__ T, const Fq* __restrict__ E, uint64_t pw,
+                                                      Fq* __restrict__ partials) {
+  __shared__ Fq red[3 * 4];
+  Fq acc[3];
+  acc[0] = acc[1] = acc[2] = fe_zero<FqCfg>();
+  for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < pw; b += (uint64_t)gridDim.x * blockDim.x) {
+    Fq t0 = ld256(T + b), t1 = ld256(T + b + pw);
+    Fq e0 = to_mont<FqCfg>(ld256(E + b)), e1 = to_mont<FqCfg>(ld256(E + b + pw));
+    Fq ts = fe_sub<FqCfg>(t1, t0), es = fe_sub<FqCfg>(e1, e0);
+    acc[0] = fe_add<FqCfg>(acc[0], mont_mul<FqCfg>(es, ts));                       // xsq
+    acc[1] = fe_add<FqCfg>(acc[1], fe_add<FqCfg>(mont_mul<FqCfg>(es, t0), mont_mul<FqCfg>(e0, ts)));  // x
+    acc[2] = fe_add<FqCfg>(acc[2], mont_mul<FqCfg>(e0, t0));                       // const
+  }
+  block_sum<3, 128>(acc, red);
+  if (threadIdx.x == 0)
+    for (int k = 0; k < 3; k++) st256(partials + (uint64_t)blockIdx.x * 3 + k, acc[k]);
+}
+
+__global__ void __launch_bounds__(128) k_sum_partials(const Fq* __restrict__ partials, uint32_t nblk, Fq* out3) {
+  __shared__ Fq red[3 * 4];
+  Fq acc[3];
+  acc[0] = acc[1] = acc[2] = fe_zero<FqCfg>();
+  for (uint32_t i = threadIdx.x; i < nblk; i += 128)
+    for (int k = 0; k < 3; k++) acc[k] = fe_add<FqCfg>(acc[k], ld256(partials + (uint64_t)i * 3 + k));
+  block_sum<3, 128>(acc, red);
+  if (threadIdx.x == 0)
+    for (int k = 0; k < 3; k++) out3[k] = acc[k];
+}
+
+int launch_mle_round_coeffs(reef_ctx* c, const void* d_t, const void* d_eq, uint32_t ell, uint32_t i, uint8_t* h_out3) {
+  REEF_REQUIRE(i >= 1 && i <= ell, REEF_EINVAL, "linear_mle_product: round index out of range");
+  const uint64_t pw = (uint64_t)1 << (ell - i);
+  unsigned nblk = ceil_div_u(pw, 128);
+  if (nblk > 1184) nblk = 1184;
+  void* base;
+  int rc = ctx_scratch(c, (size_t)(nblk + 1) * 3 * 32, &base);
+  if (rc) return rc;
+  Fq* part = (Fq*)base;
+  cudaStream_t s = c->stream;
+  k_round_coeffs<<<nblk, 128, 0, s>>>((const Fq*)d_t, (const Fq*)d_eq, pw, part);
+  REEF_CUDA(cudaGetLastError());
+  k_sum_partials<<<1, 128, 0, s>>>(part, nblk, part + (size_t)nblk * 3);
+  REEF_CUDA(cudaGetLastError());
+  REEF_CUDA(cudaMemcpyAsync(h_out3, part + (size_t)nblk * 3, 96, cudaMemcpyDeviceToHost, s));
+  REEF_CUDA(cudaStreamSynchronize(s));
+  return REEF_OK;
+}
+
+// second loop of linear_mle_product: fold both tables in place with r
+__global__ void k_fold2_inplace(Fq* T, Fq* E, uint64_t pw, Fq r_mont) {
+  uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= pw) return;
+  Fq t = fold_one(ld256(T + b), ld256(T + b + pw), r_mont);
+  Fq e = fold_one(ld256(E + b), ld256(E + b + pw), r_mont);
+  st256(T + b, t);
+  st256(E + b, e);
+}
+
+int launch_mle_round_fold(reef_ctx* c, void* d_t, void* d_eq, uint32_t ell, uint32_t i, const uint8_t* h_r) {
+  REEF_REQUIRE(i >= 1 && i <= ell, REEF_EINVAL, "linear_mle_product: round index out of range");
+  const uint64_t pw = (uint64_t)1 << (ell - i);
+  Fq r = fq_mont_from_le32(h_r);
+  k_fold2_inplace<<<ceil_div_u(pw, 128), 128, 0, c->stream>>>((Fq*)d_t, (Fq*)d_eq, pw, r);
+  REEF_CUDA(cudaGetLastError());
+  return REEF_OK;
+}
+
+}  // namespace reef

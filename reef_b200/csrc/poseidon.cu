@@ -1,0 +1,314 @@
+// Poseidon kernels: batched one-shot hashes, Merkle levels, and a generic SAFE-sponge runner.
+//
+// Reference behaviour reproduced (neptune 8.1.0 through these call sites):
+//   MerkleCommitment::new / new_parent   /root/reference/src/backend/merkle_tree.rs:25-114
+//   calc_d                               /root/reference/src/backend/commitment.rs:495-510
+//   SpongeAPI start/absorb/squeeze       /root/reference/src/backend/r1cs.rs:2260-2311
+#include "common.cuh"
+#include "kernels.h"
+
+namespace reef {
+
+#include "poseidon_consts.inc"
+
+// ---------------------------------------------------------------------------------------
+// host: IOPattern tag (SAFE) -- u128 polynomial hash, wrapping arithmetic
+// ---------------------------------------------------------------------------------------
+void io_pattern_tag_le32(const uint32_t* ops, uint32_t n_ops, uint32_t domain_separator, uint8_t out[32]) {
+  // ops[k]: bit 31 set = Absorb(n), clear = Squeeze(n); n in the low 31 bits.
+  typedef unsigned __int128 u128;
+  const u128 base = ~(u128)0 - 158;  // 2^128 - 159
+  u128 x_i = 1, state = 0;
+  bool cur_absorb = true;
+  uint64_t cur_n = 0;
+  auto update = [&](uint32_t a) {
+    x_i = x_i * base;
+    state = state + x_i * (u128)a;
+  };
+  auto finish_op = [&]() {
+    if (cur_n == 0) return;
+    uint32_t val = cur_absorb ? (uint32_t)(cur_n + (1u << 31)) : (uint32_t)cur_n;
+    update(val);
+  };
+  for (uint32_t k = 0; k < n_ops; k++) {
+    bool is_absorb = (ops[k] >> 31) != 0;
+    uint32_t n = ops[k] & 0x7fffffffu;
+    if (is_absorb == cur_absorb) {
+      cur_n += n;
+    } else {
+      finish_op();
+      cur_absorb = is_absorb;
+      cur_n = n;
+    }
+  }
+  finish_op();
+  update(domain_separator);
+  for (int i = 0; i < 32; i++) out[i] = 0;
+  for (int i = 0; i < 16; i++) out[i] = (uint8_t)(state >> (8 * i));
+}
+
+static Fq fq_from_limbs(const uint32_t* l) {
+  Fq x;
+  for (int i = 0; i < 8; i++) x.v[i] = l[i];
+  return x;
+}
+
+Fq fq_mont_from_le32(const uint8_t* b) {
+  Fq x;
+  for (int i = 0; i < 8; i++)
+    x.v[i] = (uint32_t)b[4 * i] | ((uint32_t)b[4 * i + 1] << 8) | ((uint32_t)b[4 * i + 2] << 16) |
+             ((uint32_t)b[4 * i + 3] << 24);
+  return to_mont<FqCfg>(x);
+}
+
+void poseidon_tables_host(PoseidonTables* t) {
+  auto cv = [](const uint32_t* l) { return to_mont<FqCfg>(fq_from_limbs(l)); };
+  for (int r = 0; r < 8; r++)
+    for (int i = 0; i < 5; i++) t->rc_full[r][i] = cv(REEF_POSEIDON_RC_FULL[r * 5 + i]);
+  for (int r = 0; r < 56; r++) t->rc_part[r] = cv(REEF_POSEIDON_RC_PART[r]);
+  for (int i = 0; i < 5; i++)
+    for (int j = 0; j < 5; j++) t->mds[i][j] = cv(REEF_POSEIDON_MDS[i * 5 + j]);
+  for (int r = 0; r < 56; r++)
+    for (int i = 0; i < 5; i++) t->sp_row[r][i] = cv(REEF_POSEIDON_SP_ROW[r * 5 + i]);
+  for (int r = 0; r < 56; r++)
+    for (int i = 0; i < 4; i++) t->sp_col[r][i] = cv(REEF_POSEIDON_SP_COL[r * 4 + i]);
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) t->post[i][j] = cv(REEF_POSEIDON_POST[i * 4 + j]);
+}
+
+int poseidon_upload_constants(reef_ctx* c) {
+  PoseidonTables* h = new PoseidonTables;
+  poseidon_tables_host(h);
+  cudaError_t e = cudaMalloc(&c->d_pos, sizeof(PoseidonTables));
+  if (e == cudaSuccess) e = cudaMemcpy(c->d_pos, h, sizeof(PoseidonTables), cudaMemcpyHostToDevice);
+  delete h;
+  if (e != cudaSuccess) return fail(REEF_ECUDA, std::string("poseidon constants: ") + cudaGetErrorString(e));
+  uint8_t tag[32];
+  uint32_t p2[2] = {(1u << 31) | 2u, 1u}, p4[2] = {(1u << 31) | 4u, 1u};
+  io_pattern_tag_le32(p2, 2, 0, tag);
+  c->tags.a2s1 = fq_mont_from_le32(tag);
+  io_pattern_tag_le32(p4, 2, 0, tag);
+  c->tags.a4s1 = fq_mont_from_le32(tag);
+  return REEF_OK;
+}
+
+// Host evaluation of the permutation through the SAME shared code path as the device
+// (test hook only; see include/reef_b200_testing.h).
+void poseidon_permute_host(Fq* s) {
+  static PoseidonTables* T = nullptr;
+  if (!T) {
+    T = new PoseidonTables;
+    poseidon_tables_host(T);
+  }
+  poseidon_permute(s, *T);
+}
+
+// ---------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------
+
+// one thread per hash; in: n x arity canonical elements; IOPattern [Absorb(arity), Squeeze(1)]
+__global__ void __launch_bounds__(128) k_hash_batch(const Fq* __restrict__ in, int arity, uint64_t n, Fq tag,
+                                                    const PoseidonTables* __restrict__ K, Fq* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fq s[5];
+  s[0] = tag;
+#pragma unroll 1
+  for (int k = 0; k < 4; k++) s[1 + k] = (k < arity) ? to_mont<FqCfg>(ld256(in + i * arity + k)) : fe_zero<FqCfg>();
+  poseidon_permute(s, *K);
+  st256(out + i, from_mont<FqCfg>(s[1]));
+}
+
+// leaf level: parent k = H4(2k, doc[2k], 2k+1, doc[2k+1]); missing right => (.., 0, 0)
+__global__ void __launch_bounds__(128) k_merkle_leaves(const uint64_t* __restrict__ doc, uint64_t n_doc, Fq tag4,
+                                                       const PoseidonTables* __restrict__ K, Fq* __restrict__ out) {
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t n_out = (n_doc + 1) / 2;
+  if (k >= n_out) return;
+  Fq s[5];
+  s[0] = tag4;
+  s[1] = fe_from_u64<FqCfg>(2 * k);
+  s[2] = fe_from_u64<FqCfg>(doc[2 * k]);
+  bool has_r = 2 * k + 1 < n_doc;
+  s[3] = has_r ? fe_from_u64<FqCfg>(2 * k + 1) : fe_zero<FqCfg>();
+  s[4] = has_r ? fe_from_u64<FqCfg>(doc[2 * k + 1]) : fe_zero<FqCfg>();
+  poseidon_permute(s, *K);
+  st256(out + k, from_mont<FqCfg>(s[1]));
+}
+
+// inner level: parent k = H2(prev[2k], prev[2k+1]); missing right => (l, 0)
+__global__ void __launch_bounds__(128) k_merkle_level(const Fq* __restrict__ prev, uint64_t n_prev, Fq tag2,
+                                                      const PoseidonTables* __restrict__ K, Fq* __restrict__ out) {
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t n_out = (n_prev + 1) / 2;
+  if (k >= n_out) return;
+  Fq s[5];
+  s[0] = tag2;
+  s[1] = to_mont<FqCfg>(ld256(prev + 2 * k));
+  s[2] = (2 * k + 1 < n_prev) ? to_mont<FqCfg>(ld256(prev + 2 * k + 1)) : fe_zero<FqCfg>();
+  s[3] = fe_zero<FqCfg>();
+  s[4] = fe_zero<FqCfg>();
+  poseidon_permute(s, *K);
+  st256(out + k, from_mont<FqCfg>(s[1]));
+}
+
+// inner level, one WARP per parent (latency path for the small top levels of the tree)
+__global__ void __launch_bounds__(128) k_merkle_level_warp(const Fq* __restrict__ prev, uint64_t n_prev, Fq tag2,
+                                                           const PoseidonTables* __restrict__ K,
+                                                           Fq* __restrict__ out) {
+  uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  uint64_t n_out = (n_prev + 1) / 2;
+  if (k >= n_out) return;  // warp-uniform
+  Fq s = fe_zero<FqCfg>();
+  if (lane == 0) s = tag2;
+  if (lane == 1) s = ld256(prev + 2 * k);
+  if (lane == 2 && 2 * k + 1 < n_prev) s = ld256(prev + 2 * k + 1);
+  Fq sm = to_mont<FqCfg>(s);
+  s = (lane == 1 || lane == 2) ? sm : s;
+  poseidon_permute_warp5(s, K);
+  Fq o = from_mont<FqCfg>(s);
+  if (lane == 1) st256(out + k, o);
+}
+
+// SAFE sponge state machine shared by the one-shot runner and the incremental session.
+struct SpongeDev {
+  Fq s[5];          // Montgomery form
+  uint32_t apos, spos;
+};
+
+__device__ __forceinline__ void sponge_absorb_warp(Fq& s, uint32_t& apos, uint32_t& spos, const Fq* in, uint32_t n,
+                                                   const PoseidonTables* K) {
+  const int lane = threadIdx.x & 31;
+  for (uint32_t e = 0; e < n; e++) {
+    if (apos == 4) {
+      poseidon_permute_warp5(s, K);
+      apos = 0;
+    }
+    Fq x = to_mont<FqCfg>(ld256(in + e));
+    Fq sum = fe_add<FqCfg>(s, x);
+    if (lane == (int)(1 + apos)) s = sum;
+    apos++;
+  }
+  spos = 4;
+}
+
+__device__ __forceinline__ void sponge_squeeze_warp(Fq& s, uint32_t& apos, uint32_t& spos, Fq* out, uint32_t n,
+                                                    const PoseidonTables* K) {
+  const int lane = threadIdx.x & 31;
+  for (uint32_t e = 0; e < n; e++) {
+    if (spos == 4) {
+      poseidon_permute_warp5(s, K);
+      spos = 0;
+      apos = 0;
+    }
+    Fq o = from_mont<FqCfg>(s);
+    if (lane == (int)(1 + spos)) st256(out + e, o);
+    spos++;
+  }
+}
+
+// Whole session in one launch.  ops[k]: bit31 = absorb, low bits = count.
+__global__ void __launch_bounds__(32) k_sponge_run(const uint32_t* __restrict__ ops, uint32_t n_ops,
+                                                   const Fq* __restrict__ in, Fq tag,
+                                                   const PoseidonTables* __restrict__ K, Fq* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  Fq s = fe_zero<FqCfg>();
+  if (lane == 0) s = tag;
+  uint32_t apos = 0, spos = 0, iin = 0, iout = 0;
+  for (uint32_t k = 0; k < n_ops; k++) {
+    uint32_t n = ops[k] & 0x7fffffffu;
+    if (ops[k] >> 31) {
+      sponge_absorb_warp(s, apos, spos, in + iin, n, K);
+      iin += n;
+    } else {
+      sponge_squeeze_warp(s, apos, spos, out + iout, n, K);
+      iout += n;
+    }
+  }
+}
+
+// Incremental session: op = 0 init(tag), 1 absorb(n from in), 2 squeeze(n to out)
+__global__ void __launch_bounds__(32) k_sponge_step(SpongeDev* st, int op, const Fq* __restrict__ in, uint32_t n, Fq tag,
+                                                    const PoseidonTables* __restrict__ K, Fq* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  if (op == 0) {
+    if (lane < 5) st->s[lane] = lane == 0 ? tag : fe_zero<FqCfg>();
+    if (lane == 0) { st->apos = 0; st->spos = 0; }
+    return;
+  }
+  Fq s = lane < 5 ? st->s[lane] : fe_zero<FqCfg>();
+  uint32_t apos = st->apos, spos = st->spos;
+  __syncwarp();
+  if (op == 1) sponge_absorb_warp(s, apos, spos, in, n, K);
+  else sponge_squeeze_warp(s, apos, spos, out, n, K);
+  if (lane < 5) st->s[lane] = s;
+  if (lane == 0) { st->apos = apos; st->spos = spos; }
+}
+
+// ---------------------------------------------------------------------------------------
+// launchers (device pointers)
+// ---------------------------------------------------------------------------------------
+int launch_hash_batch(reef_ctx* c, const void* d_in, int arity, uint64_t n, void* d_out) {
+  if (n == 0) return REEF_OK;
+  REEF_REQUIRE(arity == 2 || arity == 4, REEF_EINVAL, "poseidon hash arity must be 2 or 4");
+  Fq tag = arity == 2 ? c->tags.a2s1 : c->tags.a4s1;
+  unsigned blocks = (unsigned)((n + 127) / 128);
+  k_hash_batch<<<blocks, 128, 0, c->stream>>>((const Fq*)d_in, arity, n, tag, c->d_pos, (Fq*)d_out);
+  REEF_CUDA(cudaGetLastError());
+  return REEF_OK;
+}
+
+// d_levels: concatenated levels, leaf-parents first; sizes ceil(n/2), ceil(ceil(n/2)/2), ... 1
+int launch_merkle(reef_ctx* c, const uint64_t* d_doc, uint64_t n_doc, void* d_levels, uint64_t* level_sizes,
+                  uint32_t* n_levels_out) {
+  REEF_REQUIRE(n_doc >= 1, REEF_EINVAL, "merkle: empty document");
+  Fq* lv = (Fq*)d_levels;
+  uint64_t n_out = (n_doc + 1) / 2;
+  uint32_t nl = 0;
+  k_merkle_leaves<<<(unsigned)((n_out + 127) / 128), 128, 0, c->stream>>>(d_doc, n_doc, c->tags.a4s1, c->d_pos, lv);
+  REEF_CUDA(cudaGetLastError());
+  if (level_sizes) level_sizes[nl] = n_out;
+  nl++;
+  Fq* prev = lv;
+  uint64_t n_prev = n_out;
+  while (n_prev > 1) {
+    Fq* cur = prev + n_prev;
+    n_out = (n_prev + 1) / 2;
+    // thread-per-hash while the level still fills the machine, warp-per-hash for the top
+    if (n_out >= (uint64_t)c->sm_count * 256) {
+      k_merkle_level<<<(unsigned)((n_out + 127) / 128), 128, 0, c->stream>>>(prev, n_prev, c->tags.a2s1, c->d_pos, cur);
+    } else {
+      k_merkle_level_warp<<<(unsigned)((n_out * 32 + 127) / 128), 128, 0, c->stream>>>(prev, n_prev, c->tags.a2s1,
+                                                                                         c->d_pos, cur);
+    }
+    REEF_CUDA(cudaGetLastError());
+    if (level_sizes) level_sizes[nl] = n_out;
+    nl++;
+    prev = cur;
+    n_prev = n_out;
+  }
+  if (n_levels_out) *n_levels_out = nl;
+  return REEF_OK;
+}
+
+int launch_sponge_run(reef_ctx* c, const uint32_t* d_ops, uint32_t n_ops, const void* d_in, const uint8_t tag_le[32],
+                      void* d_out) {
+  Fq tag = fq_mont_from_le32(tag_le);
+  k_sponge_run<<<1, 32, 0, c->stream>>>(d_ops, n_ops, (const Fq*)d_in, tag, c->d_pos, (Fq*)d_out);
+  REEF_CUDA(cudaGetLastError());
+  return REEF_OK;
+}
+
+int sponge_state_bytes() { return (int)sizeof(SpongeDev); }
+
+int launch_sponge_step(reef_ctx* c, void* d_state, int op, const void* d_in, uint32_t n, const uint8_t* tag_le,
+                       void* d_out) {
+  Fq tag = tag_le ? fq_mont_from_le32(tag_le) : fe_zero<FqCfg>();
+  k_sponge_step<<<1, 32, 0, c->stream>>>((SpongeDev*)d_state, op, (const Fq*)d_in, n, tag, c->d_pos, (Fq*)d_out);
+  REEF_CUDA(cudaGetLastError());
+  return REEF_OK;
+}
+
+}  // namespace reef

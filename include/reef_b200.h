@@ -167,6 +167,41 @@ int reef_verifier_mle_eval(reef_ctx* ctx, const reef_table* table, const uint8_t
 int reef_prover_mle_partial_eval(reef_ctx* ctx, const reef_table* table, const uint8_t* x, uint32_t ell, int32_t hole,
                                  uint8_t out_coeff[32], uint8_t out_const[32]);
 
+/* ------------------------------------------------------------------ B3: multi-scalar multiplication
+ * Replaces nova-snark's `vartime_multiscalar_mul` / Pedersen `CE::commit` reached from
+ * framework.rs:668-675 (prove_step: commit(W), commit(T)), framework.rs:695-698 (IPA inside
+ * CompressedSNARK::prove) and commitment.rs:187, 350-393 (Hyrax).  Generators are static per
+ * PublicParams / per document commitment, so they are registered once and stay resident. */
+
+#define REEF_CURVE_PALLAS 0 /* coordinates in Fp, scalars in Fq */
+#define REEF_CURVE_VESTA 1  /* coordinates in Fq, scalars in Fp */
+
+typedef struct reef_bases reef_bases;
+
+/* bases: n affine points (64 B each).  scalar_bits: upper bound on the scalars' bit length
+ * (0 = 255).  Precomputes the window levels 2^(c*w) * P_i.  REEF_EINVAL if a point is not on
+ * y^2 = x^3 + 5. */
+int reef_bases_register(reef_ctx* ctx, int curve, const uint8_t* bases, uint64_t n, uint32_t scalar_bits,
+                        reef_bases** out);
+void reef_bases_free(reef_bases* b);
+/* number of Pippenger windows of this registration (the unit of the multi-GPU split) */
+uint32_t reef_bases_windows(const reef_bases* b);
+uint32_t reef_bases_window_bits(const reef_bases* b);
+
+/* out = sum_{i<n} scalars[i] * bases[i]   (n <= registered n; scalars canonical, < 2^scalar_bits) */
+int reef_msm(reef_ctx* ctx, const reef_bases* b, const uint8_t* scalars, uint64_t n, uint8_t out[64]);
+/* scalars already resident in device memory */
+int reef_msm_dev(reef_ctx* ctx, const reef_bases* b, const void* scalars_dev, uint64_t n, uint8_t out[64]);
+/* 32-bit scalars (document codes, small witness values) */
+int reef_msm_u32(reef_ctx* ctx, const reef_bases* b, const uint32_t* scalars, uint64_t n, uint8_t out[64]);
+
+/* Multi-GPU: windows [w_begin, w_end) only; out_xyzz = partial sum as (X, Y, ZZ, ZZZ), 4 x 32 B
+ * canonical.  The host all-gathers the partials (NCCL has no EC-add reduce op) and every rank
+ * finishes with reef_msm_combine. */
+int reef_msm_partial_dev(reef_ctx* ctx, const reef_bases* b, const void* scalars_dev, uint64_t n, uint32_t w_begin,
+                         uint32_t w_end, uint8_t out_xyzz[128]);
+int reef_msm_combine(reef_ctx* ctx, int curve, const uint8_t* partials_xyzz, uint32_t k, uint8_t out[64]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,10 @@ int reef_hosttest_mul_wide(const uint8_t a[32], const uint8_t b[32], uint8_t out
 /* one Poseidon permutation of a width-5 state (canonical in/out) */
 int reef_hosttest_poseidon_permute(const uint8_t in[160], uint8_t out[160]);
 
+/* curve formulas (ec.cuh), host instantiation.  curve: 0 Pallas, 1 Vesta.  Points affine 64 B.
+ * op: 0 P+Q via XYZZ full add, 1 P+Q via mixed add, 2 2P, 3 P-Q via mixed add (neg), 4 k*P (k = first 8 bytes of q) */
+int reef_hosttest_ec_op(int curve, int op, const uint8_t p[64], const uint8_t q[64], uint8_t out[64]);
+
 #ifdef __cplusplus
 }
 #endif

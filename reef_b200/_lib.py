@@ -74,7 +74,17 @@ _sig = {
     "reef_linear_mle_product": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "reef_verifier_mle_eval": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp]),
     "reef_prover_mle_partial_eval": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_int32, _vp, _vp]),
+    "reef_bases_register": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, C.c_uint32, C.POINTER(_vp)]),
+    "reef_bases_free": (None, [_vp]),
+    "reef_bases_windows": (C.c_uint32, [_vp]),
+    "reef_bases_window_bits": (C.c_uint32, [_vp]),
+    "reef_msm": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp]),
+    "reef_msm_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp]),
+    "reef_msm_u32": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp]),
+    "reef_msm_partial_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _vp]),
+    "reef_msm_combine": (C.c_int, [_vp, C.c_int, _vp, C.c_uint32, _vp]),
     # test hooks (include/reef_b200_testing.h)
+    "reef_hosttest_ec_op": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp]),
     "reef_hosttest_field_op": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp]),
     "reef_hosttest_mul_wide": (C.c_int, [_vp, _vp, _vp]),
     "reef_hosttest_poseidon_permute": (C.c_int, [_vp, _vp]),

@@ -209,6 +209,18 @@ class Context:
     def merkle(self, doc) -> "MerkleCommitment":
         return MerkleCommitment(self, doc)
 
+    # ---- MSM
+    def bases(self, curve, points, scalar_bits: int = 0) -> "Bases":
+        return Bases(self, curve, points, scalar_bits)
+
+    def msm(self, curve, points, scalars):
+        """One-shot convenience: register `points`, multiply, free."""
+        b = Bases(self, curve, points)
+        try:
+            return b.msm(scalars)
+        finally:
+            b.free()
+
 
 @dataclass
 class NlookupResult:
@@ -311,3 +323,81 @@ class MerkleCommitment:
 
     def make_wits(self, lookups):
         return [self.path_wits(q) for q in lookups]
+
+
+CURVES = {"pallas": 0, "vesta": 1}
+
+
+def _pt_bytes(P) -> bytes:
+    if P is None:
+        return bytes(64)
+    return int(P[0]).to_bytes(32, "little") + int(P[1]).to_bytes(32, "little")
+
+
+def _pt_from(b: bytes):
+    x, y = int.from_bytes(b[:32], "little"), int.from_bytes(b[32:64], "little")
+    return None if x == 0 and y == 0 else (x, y)
+
+
+class Bases:
+    """Registered generators (Pedersen `CommitmentGens`): window levels precomputed, HBM-resident."""
+
+    def __init__(self, ctx: Context, curve, points, scalar_bits: int = 0):
+        self.ctx = ctx
+        self.curve = CURVES[curve] if isinstance(curve, str) else int(curve)
+        self.n = len(points)
+        raw = b"".join(_pt_bytes(P) for P in points) if not isinstance(points, (bytes, bytearray)) else bytes(points)
+        if isinstance(points, (bytes, bytearray)):
+            self.n = len(raw) // 64
+        h = C.c_void_p()
+        check(lib.reef_bases_register(ctx._h, self.curve, _buf(raw), self.n, scalar_bits, C.byref(h)))
+        self._h = h
+
+    @property
+    def windows(self) -> int:
+        return int(lib.reef_bases_windows(self._h))
+
+    @property
+    def window_bits(self) -> int:
+        return int(lib.reef_bases_window_bits(self._h))
+
+    def msm(self, scalars):
+        out = C.create_string_buffer(64)
+        if isinstance(scalars, (bytes, bytearray)):
+            raw, n = bytes(scalars), len(scalars) // 32
+        else:
+            raw, n = _pack(scalars), len(scalars)
+        check(lib.reef_msm(self.ctx._h, self._h, _buf(raw), n, out))
+        return _pt_from(out.raw)
+
+    def msm_u32(self, scalars):
+        a = np.ascontiguousarray(np.asarray(scalars, dtype=np.uint32))
+        out = C.create_string_buffer(64)
+        check(lib.reef_msm_u32(self.ctx._h, self._h, a.ctypes.data if len(a) else None, len(a), out))
+        return _pt_from(out.raw)
+
+    def msm_dev(self, dev_ptr: int, n: int):
+        out = C.create_string_buffer(64)
+        check(lib.reef_msm_dev(self.ctx._h, self._h, C.c_void_p(dev_ptr), n, out))
+        return _pt_from(out.raw)
+
+    def msm_partial_dev(self, dev_ptr: int, n: int, w_begin: int, w_end: int) -> bytes:
+        out = C.create_string_buffer(128)
+        check(lib.reef_msm_partial_dev(self.ctx._h, self._h, C.c_void_p(dev_ptr), n, w_begin, w_end, out))
+        return out.raw
+
+    def combine(self, partials: bytes):
+        out = C.create_string_buffer(64)
+        check(lib.reef_msm_combine(self.ctx._h, self.curve, _buf(partials), len(partials) // 128, out))
+        return _pt_from(out.raw)
+
+    def free(self):
+        if self._h:
+            lib.reef_bases_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

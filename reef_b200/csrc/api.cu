@@ -892,3 +892,184 @@ int reef_hosttest_poseidon_permute(const uint8_t in[160], uint8_t out[160]) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// B3: MSM
+// ---------------------------------------------------------------------------------------
+#include "ec.cuh"
+
+struct reef_bases {
+  reef_ctx* ctx;
+  int curve;
+  uint64_t n;
+  uint32_t scalar_bits;
+  MsmPlanPublic plan;
+  void* d_levels;
+};
+
+template <class C>
+static void hosttest_ec(int op, const uint8_t* p, const uint8_t* q, uint8_t* out) {
+  Affine<C> a, b;
+  load_le(a.x.v, p);
+  load_le(a.y.v, p + 32);
+  load_le(b.x.v, q);
+  load_le(b.y.v, q + 32);
+  bool binf = affine_is_inf<C>(b);
+  a.x = to_mont<C>(a.x);
+  a.y = to_mont<C>(a.y);
+  uint64_t k = 0;
+  for (int i = 0; i < 8; i++) k |= (uint64_t)q[i] << (8 * i);
+  if (op != 4) {
+    b.x = to_mont<C>(b.x);
+    b.y = to_mont<C>(b.y);
+  }
+  (void)binf;
+  XYZZ<C> r = xyzz_from_affine<C>(a);
+  switch (op) {
+    case 0: {
+      XYZZ<C> t = xyzz_from_affine<C>(b);
+      // randomise the representation of t: scale by (zz, zzz) = (4, 8)  i.e. Z = 2
+      if (!xyzz_is_inf<C>(t)) {
+        Fe<C> four = fe_from_u64<C>(4), eight = fe_from_u64<C>(8);
+        t.x = mont_mul<C>(t.x, four);
+        t.y = mont_mul<C>(t.y, eight);
+        t.zz = four;
+        t.zzz = eight;
+      }
+      xyzz_add<C>(r, t);
+      break;
+    }
+    case 1: xyzz_add_affine<C>(r, b, false); break;
+    case 2: r = xyzz_dbl<C>(r); break;
+    case 3: xyzz_add_affine<C>(r, b, true); break;
+    case 4: r = xyzz_mul_small<C>(r, k); break;
+  }
+  Affine<C> o = xyzz_to_affine<C>(r);
+  o.x = from_mont<C>(o.x);
+  o.y = from_mont<C>(o.y);
+  store_le(out, o.x.v);
+  store_le(out + 32, o.y.v);
+}
+
+extern "C" {
+
+int reef_hosttest_ec_op(int curve, int op, const uint8_t p[64], const uint8_t q[64], uint8_t out[64]) {
+  if (curve == 0) hosttest_ec<FpCfg>(op, p, q, out);
+  else hosttest_ec<FqCfg>(op, p, q, out);
+  return 0;
+}
+
+int reef_bases_register(reef_ctx* c, int curve, const uint8_t* bases, uint64_t n, uint32_t scalar_bits, reef_bases** out) {
+  REEF_REQUIRE(c && bases && out, REEF_EINVAL, "reef_bases_register: NULL argument");
+  REEF_REQUIRE(curve == REEF_CURVE_PALLAS || curve == REEF_CURVE_VESTA, REEF_EINVAL, "reef_bases_register: unknown curve");
+  REEF_REQUIRE(n >= 1, REEF_EINVAL, "reef_bases_register: no bases");
+  if (scalar_bits == 0 || scalar_bits > 255) scalar_bits = 255;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  MsmPlanPublic pl = msm_make_plan(n, scalar_bits, (uint64_t)24 << 30);
+  void* d_levels = nullptr;
+  int rc = msm_bases_register(c, curve, bases, n, pl, &d_levels);
+  if (rc) return rc;
+  reef_bases* b = new reef_bases;
+  b->ctx = c;
+  b->curve = curve;
+  b->n = n;
+  b->scalar_bits = scalar_bits;
+  b->plan = pl;
+  b->d_levels = d_levels;
+  *out = b;
+  return REEF_OK;
+}
+
+void reef_bases_free(reef_bases* b) {
+  if (!b) return;
+  {
+    std::lock_guard<std::mutex> lk(b->ctx->mu);
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    cudaFree(b->d_levels);
+  }
+  delete b;
+}
+
+uint32_t reef_bases_windows(const reef_bases* b) { return b ? b->plan.W : 0; }
+uint32_t reef_bases_window_bits(const reef_bases* b) { return b ? b->plan.c : 0; }
+
+static int msm_dispatch(reef_ctx* c, const reef_bases* b, const void* d_scalars, int is_u32, uint64_t n, uint32_t w0,
+                        uint32_t w1, uint8_t* out_aff, uint8_t* out_xyzz) {
+  MsmRunArgs a;
+  a.plan = b->plan;
+  a.d_levels = b->d_levels;
+  a.n_bases = b->n;
+  a.d_scalars = d_scalars;
+  a.scalars_u32 = is_u32;
+  a.n = n;
+  a.w_begin = w0;
+  a.w_end = w1;
+  a.h_out_affine = out_aff;
+  a.h_out_xyzz = out_xyzz;
+  a.h_extra_xyzz_mont = nullptr;
+  a.n_extra = 0;
+  return msm_run(c, b->curve, a);
+}
+
+static int msm_host_scalars(reef_ctx* c, const reef_bases* b, const void* scalars, int is_u32, uint64_t n, uint8_t out[64]) {
+  REEF_REQUIRE(c && b && out && (scalars || n == 0), REEF_EINVAL, "reef_msm: NULL argument");
+  REEF_REQUIRE(b->ctx == c, REEF_EINVAL, "reef_msm: bases belong to another context");
+  REEF_REQUIRE(n <= b->n, REEF_EASSERT, "reef_msm: more scalars than generators (assertion failed: gens.len() >= v.len())");
+  if (n == 0) {
+    memset(out, 0, 64);
+    return REEF_OK;
+  }
+  if (is_u32) REEF_REQUIRE(b->scalar_bits >= 32, REEF_EINVAL, "reef_msm_u32: bases were registered for narrower scalars");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)n * (is_u32 ? 4 : 32);
+  void* d_s;
+  int rc = ctx_scratch2(c, bytes, &d_s);
+  if (rc) return rc;
+  REEF_CUDA(cudaMemcpyAsync(d_s, scalars, bytes, cudaMemcpyHostToDevice, c->stream));
+  return msm_dispatch(c, b, d_s, is_u32, n, 0, b->plan.W, out, nullptr);
+}
+
+int reef_msm(reef_ctx* c, const reef_bases* b, const uint8_t* scalars, uint64_t n, uint8_t out[64]) {
+  return msm_host_scalars(c, b, scalars, 0, n, out);
+}
+
+int reef_msm_u32(reef_ctx* c, const reef_bases* b, const uint32_t* scalars, uint64_t n, uint8_t out[64]) {
+  return msm_host_scalars(c, b, scalars, 1, n, out);
+}
+
+int reef_msm_dev(reef_ctx* c, const reef_bases* b, const void* scalars_dev, uint64_t n, uint8_t out[64]) {
+  REEF_REQUIRE(c && b && out && scalars_dev, REEF_EINVAL, "reef_msm_dev: NULL argument");
+  REEF_REQUIRE(b->ctx == c, REEF_EINVAL, "reef_msm_dev: bases belong to another context");
+  REEF_REQUIRE(n >= 1 && n <= b->n, REEF_EASSERT, "reef_msm_dev: scalar count out of range");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  return msm_dispatch(c, b, scalars_dev, 0, n, 0, b->plan.W, out, nullptr);
+}
+
+int reef_msm_partial_dev(reef_ctx* c, const reef_bases* b, const void* scalars_dev, uint64_t n, uint32_t w_begin,
+                         uint32_t w_end, uint8_t out_xyzz[128]) {
+  REEF_REQUIRE(c && b && out_xyzz && scalars_dev, REEF_EINVAL, "reef_msm_partial_dev: NULL argument");
+  REEF_REQUIRE(b->ctx == c, REEF_EINVAL, "reef_msm_partial_dev: bases belong to another context");
+  REEF_REQUIRE(n >= 1 && n <= b->n, REEF_EASSERT, "reef_msm_partial_dev: scalar count out of range");
+  REEF_REQUIRE(w_begin <= w_end && w_end <= b->plan.W, REEF_EINVAL, "reef_msm_partial_dev: window range out of bounds");
+  if (w_begin == w_end) {
+    memset(out_xyzz, 0, 128);
+    return REEF_OK;
+  }
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  return msm_dispatch(c, b, scalars_dev, 0, n, w_begin, w_end, nullptr, out_xyzz);
+}
+
+int reef_msm_combine(reef_ctx* c, int curve, const uint8_t* partials, uint32_t k, uint8_t out[64]) {
+  REEF_REQUIRE(c && partials && out, REEF_EINVAL, "reef_msm_combine: NULL argument");
+  REEF_REQUIRE(curve == REEF_CURVE_PALLAS || curve == REEF_CURVE_VESTA, REEF_EINVAL, "reef_msm_combine: unknown curve");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  return msm_combine(c, curve, partials, k, out);
+}
+
+}  // extern "C"

@@ -49,4 +49,26 @@ int launch_mle_eval(reef_ctx* c, const void* d_table, int is_u32, uint64_t n, co
 int launch_mle_round_coeffs(reef_ctx* c, const void* d_t, const void* d_eq, uint32_t ell, uint32_t i, uint8_t* h_out3);
 int launch_mle_round_fold(reef_ctx* c, void* d_t, void* d_eq, uint32_t ell, uint32_t i, const uint8_t* h_r);
 
+// ---- msm.cu
+struct MsmPlanPublic {
+  uint32_t c, W, L, G, B;
+};
+MsmPlanPublic msm_make_plan(uint64_t n, uint32_t scalar_bits, uint64_t max_level_bytes);
+int msm_bases_register(reef_ctx* c, int curve, const uint8_t* h_bases, uint64_t n, const MsmPlanPublic& pl, void** d_levels);
+struct MsmRunArgs {
+  MsmPlanPublic plan;
+  const void* d_levels;      // Affine[L][n_bases], Montgomery
+  uint64_t n_bases;
+  const void* d_scalars;     // device: n x 32 B canonical, or n x u32
+  int scalars_u32;
+  uint64_t n;                // number of terms (<= n_bases)
+  uint32_t w_begin, w_end;   // window range handled by this call (multi-GPU split)
+  uint8_t* h_out_affine;     // 64 B canonical or NULL
+  uint8_t* h_out_xyzz;       // 128 B canonical XYZZ or NULL
+  const void* h_extra_xyzz_mont;
+  uint32_t n_extra;
+};
+int msm_run(reef_ctx* c, int curve, const MsmRunArgs& a);
+int msm_combine(reef_ctx* c, int curve, const uint8_t* h_pts, uint32_t k, uint8_t* h_out);
+
 }  // namespace reef

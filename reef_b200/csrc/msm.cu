@@ -1,0 +1,604 @@
+// Pippenger multi-scalar multiplication on the Pasta curves for sm_100a.
+//
+// Replaces nova-snark's `vartime_multiscalar_mul` / Pedersen `commit` as reached from
+//   RecursiveSNARK::prove_step   /root/reference/src/backend/framework.rs:668-675   (commit(W), commit(T))
+//   CompressedSNARK::prove       /root/reference/src/backend/framework.rs:695-698   (IPA rounds)
+//   hyrax_gen.commit / prove_eval /root/reference/src/backend/commitment.rs:187, 371-393
+// The result of an MSM is a unique group element, so parity is exact against the naive
+// double-and-add oracle (oracle/curves.py).
+//
+// B200-first design (generators are static per PublicParams / per document commitment):
+//   * bases are registered once: every window level 2^(c*w) * P_i is precomputed, normalised
+//     to affine and kept resident in HBM (n * W * 64 B).  All W windows of a scalar then feed
+//     ONE bucket set, so there is no per-window bucket reduction and no Horner chain, and a
+//     multi-GPU split by windows needs only a sum of one partial point per GPU.
+//   * signed digits (buckets 1 .. 2^(c-1)), counting sort of (bucket, point-ref) pairs with
+//     warp-aggregated atomics, then segmented accumulation in fixed-size parts so that a
+//     skewed histogram (Reef's all-'a' document: every scalar equal) cannot serialise on one
+//     thread; remaining parts are combined by further K-ary passes.
+//   * weighted bucket sum  sum_v v * B_v  by bit decomposition: c masked tree reductions
+//     (warp-shuffle + shared memory) run as independent CTAs, then 2^t scaling in parallel.
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "ec.cuh"
+#include "kernels.h"
+
+namespace reef {
+
+static constexpr uint32_t K_FIRST = 32;   // entries per thread in the first accumulation pass
+static constexpr uint32_t K_NEXT = 8;     // partial points per thread in the following passes
+
+struct MsmPlan {
+  uint32_t c;          // window bits
+  uint32_t W;          // windows per scalar
+  uint32_t L;          // precomputed levels (W == L * G, last group may be short)
+  uint32_t G;          // bucket groups (1 when fully precomputed)
+  uint32_t B;          // buckets per group = 2^(c-1)
+};
+
+// ---------------------------------------------------------------------------------------
+// loads / stores
+// ---------------------------------------------------------------------------------------
+template <class C>
+__device__ __forceinline__ Affine<C> ld_affine(const Affine<C>* p) {
+  Affine<C> r;
+  r.x = ld256(&p->x);
+  r.y = ld256(&p->y);
+  return r;
+}
+template <class C>
+__device__ __forceinline__ void st_affine(Affine<C>* p, const Affine<C>& v) {
+  st256(&p->x, v.x);
+  st256(&p->y, v.y);
+}
+template <class C>
+__device__ __forceinline__ XYZZ<C> ld_xyzz(const XYZZ<C>* p) {
+  XYZZ<C> r;
+  r.x = ld256(&p->x);
+  r.y = ld256(&p->y);
+  r.zz = ld256(&p->zz);
+  r.zzz = ld256(&p->zzz);
+  return r;
+}
+template <class C>
+__device__ __forceinline__ void st_xyzz(XYZZ<C>* p, const XYZZ<C>& v) {
+  st256(&p->x, v.x);
+  st256(&p->y, v.y);
+  st256(&p->zz, v.zz);
+  st256(&p->zzz, v.zzz);
+}
+template <class C>
+__device__ __forceinline__ XYZZ<C> shfl_xor_xyzz(const XYZZ<C>& p, int m) {
+  XYZZ<C> r;
+  r.x = shfl_xor_fe(p.x, m);
+  r.y = shfl_xor_fe(p.y, m);
+  r.zz = shfl_xor_fe(p.zz, m);
+  r.zzz = shfl_xor_fe(p.zzz, m);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// registration: level[w][i] = 2^(c*w) * P_i, affine, Montgomery form
+// ---------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(128) k_precompute(const Affine<C>* __restrict__ in_canon, uint64_t n, uint32_t c,
+                                                    uint32_t L, Affine<C>* __restrict__ levels, int* bad) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<C> p = ld_affine(in_canon + i);
+  bool inf = affine_is_inf<C>(p);
+  p.x = to_mont<C>(p.x);
+  p.y = to_mont<C>(p.y);
+  if (!inf) {  // y^2 == x^3 + 5
+    Fe<C> lhs = mont_sqr<C>(p.y);
+    Fe<C> rhs = fe_add<C>(mont_mul<C>(mont_sqr<C>(p.x), p.x), fe_from_u64<C>(5));
+    if (!fe_eq<C>(lhs, rhs)) atomicExch(bad, 1);
+  }
+  st_affine(levels + i, p);
+#pragma unroll 1
+  for (uint32_t w = 1; w < L; w++) {
+    XYZZ<C> a = xyzz_dbl_affine<C>(p);
+#pragma unroll 1
+    for (uint32_t k = 1; k < c; k++) a = xyzz_dbl<C>(a);
+    p = xyzz_to_affine<C>(a);
+    st_affine(levels + (uint64_t)w * n + i, p);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// digits: entry e = w * n + i  ->  key (bucket or sentinel), val (level point ref | sign)
+// ---------------------------------------------------------------------------------------
+template <bool U32SCALARS>
+__global__ void k_digits(const void* __restrict__ scalars, uint64_t n, uint64_t n_bases, MsmPlan pl, uint32_t w_begin,
+                         uint32_t w_end, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s[9];
+  if constexpr (U32SCALARS) {
+    s[0] = ((const uint32_t*)scalars)[i];
+#pragma unroll
+    for (int k = 1; k < 9; k++) s[k] = 0;
+  } else {
+    Fe<FqCfg> x = ld256((const Fe<FqCfg>*)scalars + i);
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[k] = x.v[k];
+    s[8] = 0;
+  }
+  const uint32_t c = pl.c, half = 1u << (c - 1), full = 1u << c, sentinel = pl.G * pl.B;
+  uint32_t carry = 0;
+  for (uint32_t w = 0; w < pl.W; w++) {
+    const uint32_t bit = w * c, limb = bit >> 5, sh = bit & 31;
+    uint32_t raw = 0;
+    if (limb < 8) {
+      uint64_t two = (uint64_t)s[limb] | ((uint64_t)s[limb + 1] << 32);
+      raw = (uint32_t)(two >> sh) & (full - 1);
+    }
+    raw += carry;
+    uint32_t mag, neg;
+    if (raw > half) {
+      mag = full - raw;
+      neg = 1;
+      carry = 1;
+    } else {
+      mag = raw;
+      neg = 0;
+      carry = 0;
+    }
+    if (w >= w_begin && w < w_end) {
+      const uint64_t e = (uint64_t)(w - w_begin) * n + i;
+      const uint32_t level = w % pl.L, group = w / pl.L;
+      keys[e] = mag ? group * pl.B + (mag - 1) : sentinel;
+      vals[e] = (uint32_t)((uint64_t)level * n_bases + i) | (neg << 31);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// counting sort
+// ---------------------------------------------------------------------------------------
+__global__ void k_hist(const uint32_t* __restrict__ keys, uint64_t n_entries, uint32_t* __restrict__ counts) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_entries) return;
+  const uint32_t key = keys[e];
+  const unsigned act = __activemask();
+  const unsigned same = __match_any_sync(act, key);
+  if ((threadIdx.x & 31) == (unsigned)(__ffs(same) - 1)) atomicAdd(counts + key, (uint32_t)__popc(same));
+}
+
+// exclusive scan of ceil(cnt[b] / K) (K = 1: plain scan) by one CTA; also the max of cnt.
+__global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ cnt, uint32_t nb, uint32_t K,
+                                               uint32_t* __restrict__ parts, uint32_t* __restrict__ off,
+                                               uint32_t* __restrict__ cursor, uint32_t* __restrict__ total_max) {
+  __shared__ uint32_t sm[1024];
+  __shared__ uint32_t smax[1024];
+  const uint32_t per = (nb + 1023) / 1024;
+  const uint32_t lo = threadIdx.x * per, hi = min(nb, lo + per);
+  uint32_t sum = 0, mx = 0;
+  for (uint32_t b = lo; b < hi; b++) {
+    uint32_t p = (cnt[b] + K - 1) / K;
+    sum += p;
+    mx = max(mx, p);
+  }
+  sm[threadIdx.x] = sum;
+  smax[threadIdx.x] = mx;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    uint32_t v = threadIdx.x >= d ? sm[threadIdx.x - d] : 0;
+    uint32_t m2 = threadIdx.x >= d ? smax[threadIdx.x - d] : 0;
+    __syncthreads();
+    sm[threadIdx.x] += v;
+    smax[threadIdx.x] = max(smax[threadIdx.x], m2);
+    __syncthreads();
+  }
+  uint32_t run = threadIdx.x ? sm[threadIdx.x - 1] : 0;
+  for (uint32_t b = lo; b < hi; b++) {
+    uint32_t p = (cnt[b] + K - 1) / K;
+    off[b] = run;
+    if (cursor) cursor[b] = run;
+    if (parts) parts[b] = p;
+    run += p;
+  }
+  if (threadIdx.x == 1023) {
+    off[nb] = sm[1023];
+    total_max[0] = sm[1023];
+    total_max[1] = smax[1023];
+  }
+}
+
+__global__ void k_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t n_entries,
+                          uint32_t sentinel, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_entries) return;
+  const uint32_t key = keys[e];
+  const unsigned act = __activemask();
+  const unsigned same = __match_any_sync(act, key);
+  if (key == sentinel) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(same) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(cursor + key, (uint32_t)__popc(same));
+  base = __shfl_sync(same, base, leader);
+  sorted[base + __popc(same & ((1u << lane) - 1))] = vals[e];
+}
+
+// part p of a segmented list -> (bucket b, first element, count)
+__device__ __forceinline__ void locate_part(const uint32_t* __restrict__ part_off, uint32_t nb, uint32_t p,
+                                            uint32_t& b) {
+  uint32_t lo = 0, hi = nb;  // largest b with part_off[b] <= p
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (part_off[mid] <= p) lo = mid;
+    else hi = mid;
+  }
+  b = lo;
+}
+
+// first pass: sorted point refs -> one XYZZ partial per part (mixed additions)
+template <class C>
+__global__ void __launch_bounds__(128) k_accum_first(const uint32_t* __restrict__ sorted,
+                                                     const uint32_t* __restrict__ start, const uint32_t* __restrict__ cnt,
+                                                     const uint32_t* __restrict__ part_off, uint32_t nb, uint32_t n_parts,
+                                                     const Affine<C>* __restrict__ levels, XYZZ<C>* __restrict__ out) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_parts) return;
+  uint32_t b;
+  locate_part(part_off, nb, p, b);
+  const uint32_t j = p - part_off[b];
+  const uint32_t first = start[b] + j * K_FIRST;
+  const uint32_t last = min(start[b] + cnt[b], first + K_FIRST);
+  XYZZ<C> acc = xyzz_inf<C>();
+#pragma unroll 1
+  for (uint32_t e = first; e < last; e++) {
+    const uint32_t v = sorted[e];
+    Affine<C> q = ld_affine(levels + (v & 0x7fffffffu));
+    xyzz_add_affine<C>(acc, q, (v >> 31) != 0);
+  }
+  st_xyzz(out + p, acc);
+}
+
+// following passes: K_NEXT partial points -> one
+template <class C>
+__global__ void __launch_bounds__(128) k_accum_next(const XYZZ<C>* __restrict__ in, const uint32_t* __restrict__ in_off,
+                                                    const uint32_t* __restrict__ in_cnt,
+                                                    const uint32_t* __restrict__ part_off, uint32_t nb, uint32_t n_parts,
+                                                    XYZZ<C>* __restrict__ out) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_parts || p >= part_off[nb]) return;   // n_parts is a host-side upper bound
+  uint32_t b;
+  locate_part(part_off, nb, p, b);
+  const uint32_t j = p - part_off[b];
+  const uint32_t first = in_off[b] + j * K_NEXT;
+  const uint32_t last = min(in_off[b] + in_cnt[b], first + K_NEXT);
+  XYZZ<C> acc = xyzz_inf<C>();
+#pragma unroll 1
+  for (uint32_t e = first; e < last; e++) xyzz_add<C>(acc, ld_xyzz(in + e));
+  st_xyzz(out + p, acc);
+}
+
+// buckets[b] = (cnt[b] ? parts[off[b]] : infinity)   (after the last pass every count is <= 1)
+template <class C>
+__global__ void k_gather_buckets(const XYZZ<C>* __restrict__ in, const uint32_t* __restrict__ off,
+                                 const uint32_t* __restrict__ cnt, uint32_t nb, XYZZ<C>* __restrict__ buckets) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  XYZZ<C> v = cnt[b] ? ld_xyzz(in + off[b]) : xyzz_inf<C>();
+  st_xyzz(buckets + b, v);
+}
+
+// ---------------------------------------------------------------------------------------
+// weighted bucket sum by bit decomposition:  sum_b (b+1) * bucket[b] = sum_t 2^t * S_t,
+//   S_t = sum of buckets whose weight (b+1) has bit t set.
+// grid (nblk, c_bits, G): each CTA tree-reduces 256 buckets for one bit of one group.
+// ---------------------------------------------------------------------------------------
+template <class C>
+__device__ __forceinline__ XYZZ<C> block_sum_xyzz(XYZZ<C> v, XYZZ<C>* sm /* blockDim/32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll 1
+  for (int m = 16; m >= 1; m >>= 1) {
+    XYZZ<C> o = shfl_xor_xyzz(v, m);
+    xyzz_add<C>(v, o);      // both halves compute the same sum (commutative up to representation)
+  }
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  XYZZ<C> r = xyzz_inf<C>();
+  if (warp == 0) {
+    r = lane < nw ? sm[lane] : xyzz_inf<C>();
+#pragma unroll 1
+    for (int m = 16; m >= 1; m >>= 1) {
+      XYZZ<C> o = shfl_xor_xyzz(r, m);
+      xyzz_add<C>(r, o);
+    }
+  }
+  __syncthreads();
+  return r;  // valid on warp 0
+}
+
+template <class C>
+__global__ void __launch_bounds__(256) k_bitsum_partial(const XYZZ<C>* __restrict__ buckets, uint32_t B,
+                                                        XYZZ<C>* __restrict__ partial) {
+  __shared__ XYZZ<C> sm[8];
+  const uint32_t t = blockIdx.y, g = blockIdx.z;
+  const uint32_t b = blockIdx.x * 256 + threadIdx.x;
+  XYZZ<C> v = xyzz_inf<C>();
+  if (b < B && (((b + 1) >> t) & 1)) v = ld_xyzz(buckets + (uint64_t)g * B + b);
+  XYZZ<C> r = block_sum_xyzz<C>(v, sm);
+  if (threadIdx.x == 0) st_xyzz(partial + ((uint64_t)g * gridDim.y + t) * gridDim.x + blockIdx.x, r);
+}
+
+// one CTA per group: S_t = sum of nblk partials (one warp per bit), scale by 2^t, sum over t,
+// then combine the groups by Horner (group g carries weight 2^(c*L*g)) and normalise.
+template <class C>
+__global__ void __launch_bounds__(1024) k_bitsum_final(const XYZZ<C>* __restrict__ partial, uint32_t nblk,
+                                                       uint32_t cbits, uint32_t G, uint32_t group_shift,
+                                                       XYZZ<C>* __restrict__ out_xyzz, Affine<C>* __restrict__ out_affine,
+                                                       const XYZZ<C>* __restrict__ extra, uint32_t n_extra) {
+  __shared__ XYZZ<C> st[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  XYZZ<C> total = xyzz_inf<C>();
+  for (int g = (int)G - 1; g >= 0; g--) {
+    // warp t: sum of the nblk partials of bit t, then t doublings
+    XYZZ<C> v = xyzz_inf<C>();
+    if ((uint32_t)warp < cbits) {
+      for (uint32_t k = lane; k < nblk; k += 32) xyzz_add<C>(v, ld_xyzz(partial + ((uint64_t)g * cbits + warp) * nblk + k));
+#pragma unroll 1
+      for (int m = 16; m >= 1; m >>= 1) {
+        XYZZ<C> o = shfl_xor_xyzz(v, m);
+        xyzz_add<C>(v, o);
+      }
+#pragma unroll 1
+      for (int k = 0; k < warp; k++) v = xyzz_dbl<C>(v);
+    }
+    if (lane == 0) st[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      XYZZ<C> r = (uint32_t)lane < cbits ? st[lane] : xyzz_inf<C>();
+#pragma unroll 1
+      for (int m = 16; m >= 1; m >>= 1) {
+        XYZZ<C> o = shfl_xor_xyzz(r, m);
+        xyzz_add<C>(r, o);
+      }
+      if (g != (int)G - 1) {
+#pragma unroll 1
+        for (uint32_t k = 0; k < group_shift; k++) total = xyzz_dbl<C>(total);
+      }
+      xyzz_add<C>(total, r);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    for (uint32_t k = 0; k < n_extra; k++) xyzz_add<C>(total, ld_xyzz(extra + k));
+    if (out_xyzz) st_xyzz(out_xyzz, total);
+    if (out_affine) {
+      Affine<C> a = xyzz_to_affine<C>(total);
+      a.x = from_mont<C>(a.x);
+      a.y = from_mont<C>(a.y);
+      st_affine(out_affine, a);
+    }
+  }
+}
+
+// sum of k XYZZ points given in canonical (non-Montgomery) coordinates -> affine canonical
+template <class C>
+__global__ void k_combine(const XYZZ<C>* __restrict__ pts_canon, uint32_t k, Affine<C>* __restrict__ out) {
+  if (threadIdx.x || blockIdx.x) return;
+  XYZZ<C> total = xyzz_inf<C>();
+  for (uint32_t i = 0; i < k; i++) {
+    XYZZ<C> p = ld_xyzz(pts_canon + i);
+    p.x = to_mont<C>(p.x);
+    p.y = to_mont<C>(p.y);
+    p.zz = to_mont<C>(p.zz);
+    p.zzz = to_mont<C>(p.zzz);
+    xyzz_add<C>(total, p);
+  }
+  Affine<C> a = xyzz_to_affine<C>(total);
+  a.x = from_mont<C>(a.x);
+  a.y = from_mont<C>(a.y);
+  st_affine(out, a);
+}
+
+template <class C>
+__global__ void k_xyzz_from_mont(XYZZ<C>* p) {
+  if (threadIdx.x || blockIdx.x) return;
+  XYZZ<C> v = ld_xyzz(p);
+  v.x = from_mont<C>(v.x);
+  v.y = from_mont<C>(v.y);
+  v.zz = from_mont<C>(v.zz);
+  v.zzz = from_mont<C>(v.zzz);
+  st_xyzz(p, v);
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+MsmPlanPublic msm_make_plan(uint64_t n, uint32_t scalar_bits, uint64_t max_level_bytes) {
+  MsmPlanPublic p;
+  uint32_t lg = 0;
+  while (((uint64_t)1 << (lg + 1)) <= n) lg++;
+  int c = (int)lg - 4;
+  if (c < 4) c = 4;
+  if (c > 16) c = 16;
+  if ((uint32_t)c > scalar_bits + 1) c = (int)scalar_bits + 1;
+  p.c = (uint32_t)c;
+  p.W = scalar_bits / p.c + 1;
+  p.L = p.W;
+  while (p.L > 1 && (uint64_t)p.L * n * 64 > max_level_bytes) p.L = (p.L + 1) / 2;
+  p.G = (p.W + p.L - 1) / p.L;
+  p.B = 1u << (p.c - 1);
+  return p;
+}
+
+template <class C>
+static int bases_register_t(reef_ctx* c, const uint8_t* h_bases, uint64_t n, const MsmPlanPublic& pl, void** d_levels_out) {
+  void* d_levels = nullptr;
+  const size_t bytes = (size_t)pl.L * n * sizeof(Affine<C>);
+  cudaError_t e = cudaMalloc(&d_levels, bytes);
+  if (e != cudaSuccess) return fail(REEF_ENOMEM, std::string("reef_bases_register: ") + cudaGetErrorString(e));
+  void* base;
+  int rc = ctx_scratch(c, (size_t)n * 64 + 256, &base);
+  if (rc) {
+    cudaFree(d_levels);
+    return rc;
+  }
+  int* d_bad = (int*)((char*)base + (size_t)n * 64);
+  cudaStream_t s = c->stream;
+  e = cudaMemcpyAsync(base, h_bases, (size_t)n * 64, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, 4, s);
+  if (e == cudaSuccess) {
+    k_precompute<C><<<cdiv(n, 128), 128, 0, s>>>((const Affine<C>*)base, n, pl.c, pl.L, (Affine<C>*)d_levels, d_bad);
+    e = cudaGetLastError();
+  }
+  int bad = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    cudaFree(d_levels);
+    return fail(REEF_ECUDA, std::string("reef_bases_register: ") + cudaGetErrorString(e));
+  }
+  if (bad) {
+    cudaFree(d_levels);
+    return fail(REEF_EINVAL, "reef_bases_register: a base point is not on the curve");
+  }
+  *d_levels_out = d_levels;
+  return REEF_OK;
+}
+
+int msm_bases_register(reef_ctx* c, int curve, const uint8_t* h_bases, uint64_t n, const MsmPlanPublic& pl, void** d_levels) {
+  return curve == 0 ? bases_register_t<FpCfg>(c, h_bases, n, pl, d_levels) : bases_register_t<FqCfg>(c, h_bases, n, pl, d_levels);
+}
+
+// Runs windows [w_begin, w_end) of the MSM.  Result: affine canonical (64 B) to h_out_affine
+// and/or XYZZ canonical coordinates (128 B) to h_out_xyzz (for a cross-GPU combine).
+template <class C>
+static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
+  const MsmPlanPublic& P = a.plan;
+  MsmPlan pl{P.c, P.W, P.L, P.G, P.B};
+  const uint64_t n = a.n;
+  const uint32_t nw = a.w_end - a.w_begin;
+  const uint64_t n_entries = (uint64_t)nw * n;
+  REEF_REQUIRE(n_entries < ((uint64_t)1 << 31), REEF_EINVAL, "reef_msm: n * windows exceeds 2^31 entries");
+  REEF_REQUIRE((uint64_t)P.L * a.n_bases < ((uint64_t)1 << 31), REEF_EINVAL, "reef_msm: too many precomputed points");
+  const uint32_t nb = P.G * P.B;
+  cudaStream_t s = c->stream;
+
+  // scratch carve-up
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const uint64_t max_parts1 = n_entries / K_FIRST + nb + 1;
+  const uint64_t max_parts2 = max_parts1 / K_NEXT + nb + 1;
+  size_t o_keys = take(n_entries * 4), o_vals = take(n_entries * 4), o_sorted = take(n_entries * 4);
+  size_t o_cnt = take((size_t)(nb + 2) * 4), o_start = take((size_t)(nb + 2) * 4), o_cursor = take((size_t)(nb + 2) * 4);
+  size_t o_pcnt[2] = {take((size_t)(nb + 2) * 4), take((size_t)(nb + 2) * 4)};
+  size_t o_poff[2] = {take((size_t)(nb + 2) * 4), take((size_t)(nb + 2) * 4)};
+  size_t o_tm = take(64);
+  size_t o_parts[2] = {take(max_parts1 * sizeof(XYZZ<C>)), take(max_parts2 * sizeof(XYZZ<C>))};
+  size_t o_buckets = take((size_t)nb * sizeof(XYZZ<C>));
+  const uint32_t nblk = cdiv(P.B, 256);
+  size_t o_bitpart = take((size_t)P.G * P.c * nblk * sizeof(XYZZ<C>));
+  size_t o_res = take(sizeof(XYZZ<C>) + sizeof(Affine<C>));
+  size_t o_extra = take((size_t)(a.n_extra + 1) * sizeof(XYZZ<C>));
+  void* base;
+  int rc = ctx_scratch(c, off, &base);
+  if (rc) return rc;
+  char* d = (char*)base;
+  uint32_t* keys = (uint32_t*)(d + o_keys);
+  uint32_t* vals = (uint32_t*)(d + o_vals);
+  uint32_t* sorted = (uint32_t*)(d + o_sorted);
+  uint32_t* cnt = (uint32_t*)(d + o_cnt);
+  uint32_t* start = (uint32_t*)(d + o_start);
+  uint32_t* cursor = (uint32_t*)(d + o_cursor);
+  uint32_t* pcnt[2] = {(uint32_t*)(d + o_pcnt[0]), (uint32_t*)(d + o_pcnt[1])};
+  uint32_t* poff[2] = {(uint32_t*)(d + o_poff[0]), (uint32_t*)(d + o_poff[1])};
+  uint32_t* tm = (uint32_t*)(d + o_tm);
+  XYZZ<C>* parts[2] = {(XYZZ<C>*)(d + o_parts[0]), (XYZZ<C>*)(d + o_parts[1])};
+  XYZZ<C>* buckets = (XYZZ<C>*)(d + o_buckets);
+  XYZZ<C>* bitpart = (XYZZ<C>*)(d + o_bitpart);
+  XYZZ<C>* res_xyzz = (XYZZ<C>*)(d + o_res);
+  Affine<C>* res_aff = (Affine<C>*)(res_xyzz + 1);
+  XYZZ<C>* extra = (XYZZ<C>*)(d + o_extra);
+
+  REEF_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(nb + 2) * 4, s));
+  if (a.scalars_u32) k_digits<true><<<cdiv(n, 256), 256, 0, s>>>(a.d_scalars, n, a.n_bases, pl, a.w_begin, a.w_end, keys, vals);
+  else k_digits<false><<<cdiv(n, 256), 256, 0, s>>>(a.d_scalars, n, a.n_bases, pl, a.w_begin, a.w_end, keys, vals);
+  REEF_CUDA(cudaGetLastError());
+  k_hist<<<cdiv(n_entries, 256), 256, 0, s>>>(keys, n_entries, cnt);
+  REEF_CUDA(cudaGetLastError());
+  // bucket starts (plain scan), then parts of the first pass
+  k_scan<<<1, 1024, 0, s>>>(cnt, nb, 1, nullptr, start, cursor, tm);
+  REEF_CUDA(cudaGetLastError());
+  k_scatter<<<cdiv(n_entries, 256), 256, 0, s>>>(keys, vals, n_entries, nb, cursor, sorted);
+  REEF_CUDA(cudaGetLastError());
+  k_scan<<<1, 1024, 0, s>>>(cnt, nb, K_FIRST, pcnt[0], poff[0], nullptr, tm + 2);
+  REEF_CUDA(cudaGetLastError());
+  uint32_t h_tm[4];
+  REEF_CUDA(cudaMemcpyAsync(h_tm, tm, 16, cudaMemcpyDeviceToHost, s));
+  REEF_CUDA(cudaStreamSynchronize(s));
+  uint32_t n_parts = h_tm[2], max_cnt = h_tm[3];   // parts of pass 1, largest per-bucket part count
+  if (n_parts) {
+    k_accum_first<C><<<cdiv(n_parts, 128), 128, 0, s>>>(sorted, start, cnt, poff[0], nb, n_parts, (const Affine<C>*)a.d_levels,
+                                                       parts[0]);
+    REEF_CUDA(cudaGetLastError());
+  }
+  int cur = 0;
+  while (max_cnt > 1) {
+    const int nxt = cur ^ 1;
+    k_scan<<<1, 1024, 0, s>>>(pcnt[cur], nb, K_NEXT, pcnt[nxt], poff[nxt], nullptr, tm + 2);
+    REEF_CUDA(cudaGetLastError());
+    const uint32_t n_next = (n_parts + K_NEXT - 1) / K_NEXT + nb;   // upper bound; exact count read on device
+    k_accum_next<C><<<cdiv(n_next, 128), 128, 0, s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, parts[nxt]);
+    REEF_CUDA(cudaGetLastError());
+    max_cnt = (max_cnt + K_NEXT - 1) / K_NEXT;
+    n_parts = n_next;
+    cur = nxt;
+  }
+  k_gather_buckets<C><<<cdiv(nb, 256), 256, 0, s>>>(parts[cur], poff[cur], pcnt[cur], nb, buckets);
+  REEF_CUDA(cudaGetLastError());
+  k_bitsum_partial<C><<<dim3(nblk, P.c, P.G), 256, 0, s>>>(buckets, P.B, bitpart);
+  REEF_CUDA(cudaGetLastError());
+  if (a.n_extra) REEF_CUDA(cudaMemcpyAsync(extra, a.h_extra_xyzz_mont, (size_t)a.n_extra * sizeof(XYZZ<C>), cudaMemcpyHostToDevice, s));
+  k_bitsum_final<C><<<1, 1024, 0, s>>>(bitpart, nblk, P.c, P.G, P.c * P.L, a.h_out_xyzz ? res_xyzz : nullptr,
+                                       a.h_out_affine ? res_aff : nullptr, extra, a.n_extra);
+  REEF_CUDA(cudaGetLastError());
+  if (a.h_out_xyzz) {
+    k_xyzz_from_mont<C><<<1, 32, 0, s>>>(res_xyzz);
+    REEF_CUDA(cudaGetLastError());
+    REEF_CUDA(cudaMemcpyAsync(a.h_out_xyzz, res_xyzz, sizeof(XYZZ<C>), cudaMemcpyDeviceToHost, s));
+  }
+  if (a.h_out_affine) REEF_CUDA(cudaMemcpyAsync(a.h_out_affine, res_aff, sizeof(Affine<C>), cudaMemcpyDeviceToHost, s));
+  REEF_CUDA(cudaStreamSynchronize(s));
+  return REEF_OK;
+}
+
+int msm_run(reef_ctx* c, int curve, const MsmRunArgs& a) { return curve == 0 ? msm_run_t<FpCfg>(c, a) : msm_run_t<FqCfg>(c, a); }
+
+template <class C>
+static int msm_combine_t(reef_ctx* c, const uint8_t* h_pts, uint32_t k, uint8_t* h_out) {
+  void* base;
+  int rc = ctx_scratch(c, (size_t)k * 128 + 256, &base);
+  if (rc) return rc;
+  cudaStream_t s = c->stream;
+  Affine<C>* d_out = (Affine<C>*)((char*)base + (((size_t)k * 128 + 255) & ~(size_t)255));
+  REEF_CUDA(cudaMemcpyAsync(base, h_pts, (size_t)k * 128, cudaMemcpyHostToDevice, s));
+  k_combine<C><<<1, 32, 0, s>>>((const XYZZ<C>*)base, k, d_out);
+  REEF_CUDA(cudaGetLastError());
+  REEF_CUDA(cudaMemcpyAsync(h_out, d_out, 64, cudaMemcpyDeviceToHost, s));
+  REEF_CUDA(cudaStreamSynchronize(s));
+  return REEF_OK;
+}
+
+int msm_combine(reef_ctx* c, int curve, const uint8_t* h_pts, uint32_t k, uint8_t* h_out) {
+  REEF_REQUIRE(k >= 1, REEF_EINVAL, "reef_msm_combine: no partial points");
+  size_t need = (size_t)k * 128 + 1024;
+  void* base;
+  int rc = ctx_scratch(c, need, &base);
+  if (rc) return rc;
+  return curve == 0 ? msm_combine_t<FpCfg>(c, h_pts, k, h_out) : msm_combine_t<FqCfg>(c, h_pts, k, h_out);
+}
+
+}  // namespace reef

@@ -1,0 +1,510 @@
+#!/usr/bin/env python3
+"""bench.py -- Reef prover hot path on B200 (see DESIGN.md "Measurement").
+
+  python bench.py --gpus N --steps K --warmup W [--workload cfg2] [--impl reef|reference]
+
+A "step" is ONE PASS OF THE PROVER HOT PATH over one synthetic document: for each Nova fold of
+the `--prove` run the reference would do (framework.rs:405-625 / 642-754):
+    nlookup sum-check over the transition table T      ("nl",    r1cs.rs:2088-2100)
+    nlookup sum-check over the committed document      ("nldoc", r1cs.rs:2137-2161)
+    2 x calc_d                                         (framework.rs:517-553)
+    prove_step commitments: commit(W), commit(T) on Pallas and on Vesta (framework.rs:668-675)
+metric  = NFA steps/s proved = doc_len / time of one pass        (BASELINE.json)
+value   = inputs resident in HBM when the timed region starts    (device timed, CUDA events)
+e2e     = the same pass through the C ABI with HOST buffers: document/table upload, scalar
+          upload and result read-back inside the timed region
+--impl reference = the CPU restatement of the reference's algorithm (oracle/c, all host cores).
+
+Multi-GPU (torchrun): the MSMs are sharded by Pippenger windows across ranks with ONE
+all-gather of partial points (NCCL) per MSM; the document sum-check is sharded over G
+independent documents (weak scaling: one 2^16-char document per GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import random
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FQ = 0x40000000000000000000000000000000224698FC0994A8DD8C46EB2100000001
+FP = 0x40000000000000000000000000000000224698FC094CF91B992D30ED00000001
+
+WORKLOADS = {
+    # name: doc_len, alphabet, nova steps, lookups per step, log2 |T|, primary / secondary MSM sizes
+    "cfg2": dict(doc_len=1 << 16, ab="ascii", steps=2, m=2, t_log=6, n_pri=1 << 15, n_sec=1 << 14,
+                 desc="ascii 2^16-char doc (65535 x 'a' + 'b'), re '.*b', --prove: per Nova fold "
+                      "nl(T=2^6) + nldoc(N=2^17,u32) sum-checks, 2 calc_d, commit(W),commit(T) on "
+                      "Pallas(2^15) and Vesta(2^14); 2 folds"),
+    "cfg4": dict(doc_len=1 << 20, ab="ascii", steps=2, m=4, t_log=8, n_pri=1 << 16, n_sec=1 << 14,
+                 desc="ascii 2^20-char doc, per fold nl(T=2^8) + nldoc(N=2^21,u32), 2 calc_d, 4 MSMs; 2 folds"),
+    "cfg5": dict(doc_len=1 << 22, ab="ascii", steps=1, m=4, t_log=8, n_pri=1 << 16, n_sec=1 << 14,
+                 desc="2^22-char doc, nl(T=2^8) + nldoc(N=2^23,u32), 2 calc_d, 4 MSMs; 1 fold"),
+}
+
+
+def le32(x: int) -> bytes:
+    return int(x).to_bytes(32, "little")
+
+
+def pack(xs) -> bytes:
+    return b"".join(le32(x) for x in xs)
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic workload (deterministic; the same bytes feed the GPU arm and the reference arm)
+# --------------------------------------------------------------------------------------------
+def make_workload(name: str, seed_shift: int = 0):
+    from oracle.curves import PALLAS, VESTA          # test-infra helper used only to GENERATE inputs
+    from oracle.nlookup import ASCII_AB, doc_transform
+    w = dict(WORKLOADS[name])
+    rnd = random.Random(1234 + seed_shift)
+    doc_len = w["doc_len"]
+    if name == "cfg2":
+        doc = "a" * (doc_len - 1) + "b"
+        udoc = np.asarray(doc_transform(ASCII_AB, doc), dtype=np.uint32)
+    else:
+        body = np.random.default_rng(21 + seed_shift).integers(0x20, 0x7F, size=doc_len, dtype=np.uint32)
+        n_pad = 1 << int(np.ceil(np.log2(doc_len + 2)))
+        udoc = np.zeros(n_pad, dtype=np.uint32)
+        udoc[:doc_len] = body
+        udoc[doc_len], udoc[doc_len + 1] = 130, 129
+    w["udoc"] = np.ascontiguousarray(udoc)
+    tl = w["t_log"]
+    w["T"] = sorted(rnd.randrange(1 << 40) for _ in range(1 << tl))
+    w["T_bytes"] = pack(w["T"])
+    S, m = w["steps"], w["m"]
+    w["q_nl"] = [[rnd.randrange(1 << tl) for _ in range(m)] for _ in range(S)]
+    w["q_doc"] = [[rnd.randrange(doc_len + 2) for _ in range(m)] for _ in range(S)]
+    w["doc_hash"] = rnd.randrange(FQ)
+    w["salt"] = rnd.randrange(FQ)
+
+    def scalars(n, order, witness_like):
+        rs = np.random.default_rng(rnd.randrange(1 << 30))
+        raw = rs.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
+        raw[:, 3] &= (1 << 61) - 1                                    # < 2^253 < both group orders
+        if witness_like:                                              # R1CS witness: mostly bits / small values
+            small = rs.random(n) < 0.85
+            raw[small, 1:] = 0
+            raw[small, 0] = rs.integers(0, 1 << 16, size=int(small.sum()), dtype=np.uint64)
+            bits = rs.random(n) < 0.5
+            raw[small & bits, 0] &= 1
+        return np.ascontiguousarray(raw)
+
+    # generators k*G: distinct, cheap, and the expected MSM result is checkable
+    w["bases_pri"] = b"".join(le32(P[0]) + le32(P[1]) for P in PALLAS.multiples(w["n_pri"]))
+    w["bases_sec"] = b"".join(le32(P[0]) + le32(P[1]) for P in VESTA.multiples(w["n_sec"]))
+    w["sc"] = [dict(Wp=scalars(w["n_pri"], FQ, True), Tp=scalars(w["n_pri"], FQ, False),
+                    Ws=scalars(w["n_sec"], FP, True), Ts=scalars(w["n_sec"], FP, False)) for _ in range(S)]
+    return w
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+class GpuPass:
+    """One prove pass through libreef_b200 with raw buffers (no Python big-int work inside)."""
+
+    def __init__(self, ctx, w, rank=0, world=1, dist=None):
+        import reef_b200
+        import torch
+        self.rb, self.torch, self.ctx, self.w = reef_b200, torch, ctx, w
+        self.lib, self.check = reef_b200.lib, reef_b200._lib.check
+        self.rank, self.world, self.dist = rank, world, dist
+        self.bases_pri = reef_b200.Bases(ctx, "pallas", w["bases_pri"])
+        self.bases_sec = reef_b200.Bases(ctx, "vesta", w["bases_sec"])
+        self.ell_doc = reef_b200.logmn(len(w["udoc"]))
+        self.ell_T = w["t_log"]
+        self._mk_out()
+
+    def _mk_out(self):
+        from reef_b200._lib import NlookupOut
+        self.o, self.bufs = {}, {}
+        for key, ell in (("nl", self.ell_T), ("nldoc", self.ell_doc)):
+            b = dict(prev=C.create_string_buffer(32), cq=C.create_string_buffer(64 * 32), claim=C.create_string_buffer(32),
+                     rounds=C.create_string_buffer(ell * 128), last=C.create_string_buffer(32), nxt=C.create_string_buffer(32))
+            o = NlookupOut()
+            o.prev_running_claim = C.addressof(b["prev"]); o.combined_q = C.addressof(b["cq"]); o.combined_q_cap = 64
+            o.claim_r = C.addressof(b["claim"]); o.rounds = C.addressof(b["rounds"]); o.rounds_cap = ell
+            o.sc_last_claim = C.addressof(b["last"]); o.next_running_claim = C.addressof(b["nxt"])
+            self.o[key], self.bufs[key] = o, b
+
+    # -- residency ----------------------------------------------------------------------
+    def make_resident(self):
+        w, t = self.w, self.torch
+        self.doc_tab = self.ctx.table_u32(w["udoc"])
+        self.T_tab = self.rb.Table(self.ctx, values=w["T"])
+        self.sc_dev = [{k: t.from_numpy(v.view(np.int64)).cuda() for k, v in s.items()} for s in w["sc"]]
+        t.cuda.synchronize()
+
+    def _nlookup(self, key, tab, q_arr, v_bytes, prev):
+        o, b = self.o[key], self.bufs[key]
+        tag = 0 if key == "nl" else 1
+        pq = prev[0] if prev else None
+        pv = prev[1] if prev else None
+        self.check(self.lib.reef_nlookup_prove(self.ctx._h, tag, tab._h, q_arr.ctypes.data, v_bytes, len(q_arr), pq, pv,
+                                              self.dh if tag else None, C.byref(o)))
+        ell = o.ell
+        rounds = b["rounds"].raw
+        next_q = b"".join(rounds[i * 128:i * 128 + 32] for i in range(ell))
+        return next_q, b["nxt"].raw
+
+    def _msm(self, bases, dev_tensor, host_arr, n, resident):
+        out = C.create_string_buffer(64)
+        if self.world == 1:
+            if resident:
+                self.check(self.lib.reef_msm_dev(self.ctx._h, bases._h, C.c_void_p(dev_tensor.data_ptr()), n, out))
+            else:
+                self.check(self.lib.reef_msm(self.ctx._h, bases._h, host_arr.ctypes.data, n, out))
+            return out.raw
+        # multi-GPU: windows [w0, w1) on this rank, one all-gather of 128-byte partial points
+        t = self.torch
+        if not resident:
+            dev_tensor = t.from_numpy(host_arr.view(np.int64)).cuda()
+        W = bases.windows
+        w0, w1 = W * self.rank // self.world, W * (self.rank + 1) // self.world
+        part = C.create_string_buffer(128)
+        self.check(self.lib.reef_msm_partial_dev(self.ctx._h, bases._h, C.c_void_p(dev_tensor.data_ptr()), n, w0, w1, part))
+        mine = t.frombuffer(bytearray(part.raw), dtype=t.uint8).cuda()
+        gathered = [t.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(gathered, mine)
+        allp = b"".join(bytes(g.cpu().numpy().tobytes()) for g in gathered)
+        self.check(self.lib.reef_msm_combine(self.ctx._h, bases.curve, allp, self.world, out))
+        return out.raw
+
+    def run(self, resident: bool):
+        """One pass.  resident=False: every input crosses PCIe inside the call (e2e leg)."""
+        w = self.w
+        self.dh = le32(w["doc_hash"])
+        salt = le32(w["salt"])
+        if resident:
+            doc_tab, T_tab = self.doc_tab, self.T_tab
+        else:
+            doc_tab = self.ctx.table_u32(w["udoc"])               # H2D of the document codes
+            T_tab = self._upload_T()
+        prev_nl = prev_doc = None
+        outs = []
+        for s in range(w["steps"]):
+            qn, qd = self.q_nl[s], self.q_doc[s]
+            prev_nl = self._nlookup("nl", T_tab, qn[0], qn[1], prev_nl)
+            prev_doc = self._nlookup("nldoc", doc_tab, qd[0], qd[1], prev_doc)
+            d = C.create_string_buffer(32)
+            self.check(self.lib.reef_calc_d(self.ctx._h, prev_nl[1], salt, d))
+            self.check(self.lib.reef_calc_d(self.ctx._h, prev_doc[1], salt, d))
+            sc, scd = w["sc"][s], (self.sc_dev[s] if resident else None)
+            for key, bases, n in (("Wp", self.bases_pri, w["n_pri"]), ("Tp", self.bases_pri, w["n_pri"]),
+                                  ("Ws", self.bases_sec, w["n_sec"]), ("Ts", self.bases_sec, w["n_sec"])):
+                outs.append(self._msm(bases, scd[key] if resident else None, sc[key], n, resident))
+        if not resident:
+            doc_tab.free()
+            T_tab.free()
+        return prev_nl, prev_doc, outs
+
+    def _upload_T(self):
+        h = C.c_void_p()
+        self.check(self.lib.reef_table_upload(self.ctx._h, self.w["T_bytes"], len(self.w["T"]), C.byref(h)))
+        t = self.rb.Table.__new__(self.rb.Table)
+        t.ctx, t._h = self.ctx, h
+        return t
+
+    def prepare_queries(self):
+        w = self.w
+        self.q_nl = [(np.asarray(q, dtype=np.uint64), pack(w["T"][i] for i in q)) for q in w["q_nl"]]
+        self.q_doc = [(np.asarray(q, dtype=np.uint64), pack(int(w["udoc"][i]) for i in q)) for q in w["q_doc"]]
+
+    def bytes_per_step(self):
+        w = self.w
+        h2d = w["udoc"].nbytes + len(w["T_bytes"])
+        for s in range(w["steps"]):
+            h2d += sum(v.nbytes for v in w["sc"][s].values())
+            for ell, m in ((self.ell_T, w["m"]), (self.ell_doc, w["m"])):
+                h2d += (m + ell + 3) * 32 + ell * 32 + m * 8
+        d2h = 0
+        for s in range(w["steps"]):
+            d2h += 2 * 8192 + 2 * 32 + 4 * 64                        # NlState x2, calc_d x2, 4 points
+        return h2d, d2h
+
+
+def sample_clocks_start():
+    path = tempfile.mktemp(suffix=".csv")
+    try:
+        p = subprocess.Popen(["nvidia-smi", "--query-gpu=index,clocks.sm,clocks.max.sm,power.draw,"
+                              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                              "--format=csv,noheader,nounits", "-lms", "100"], stdout=open(path, "w"), stderr=subprocess.DEVNULL)
+    except Exception:
+        return None, path
+    return p, path
+
+
+def sample_clocks_stop(p, path, device=0):
+    if p is None:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    time.sleep(0.15)
+    p.terminate()
+    try:
+        p.wait(timeout=5)
+    except Exception:
+        p.kill()
+    sm, mx, reasons = [], None, set()
+    for line in open(path):
+        f = [x.strip() for x in line.split(",")]
+        if len(f) < 8 or not f[0].isdigit() or int(f[0]) != device:
+            continue
+        try:
+            sm.append(float(f[1]))
+            mx = float(f[2])
+        except ValueError:
+            continue
+        for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+            if val.lower().startswith("active"):
+                reasons.add(name)
+    try:
+        os.unlink(path)
+    except OSError:
+        pass
+    return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    peaks = {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            peaks["hbm_gbs"] = float(json.load(open(p))["hbm_gbs"])
+            peaks["source"] = "MEASURED_PEAKS.json (burst copy)"
+        except Exception:
+            pass
+    pm = os.path.join(ROOT, "profiles", "peak_modmul.json")
+    peaks["modmul_per_s"] = float(json.load(open(pm))["modmul_per_s"]) if os.path.exists(pm) else 69.0e9
+    return peaks
+
+
+def run_reef(args):
+    import torch
+    import reef_b200
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    dev = local if world > 1 else 0
+    ctx = reef_b200.Context(dev)
+    # weak scaling: every rank proves its own document of the named length (seed differs per
+    # rank); the fold commitments of rank r's document are window-sharded across ALL ranks.
+    # With one document per rank the MSM collective would interleave G documents; to keep the
+    # collective structure simple every rank runs the same MSM inputs as rank 0 for those and
+    # its own document for the sum-checks.
+    w = make_workload(args.workload, seed_shift=0)
+    gp = GpuPass(ctx, w, rank, world, dist)
+    gp.prepare_queries()
+    gp.make_resident()
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")    # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(resident, steps, warmup, profile):
+        for _ in range(warmup):
+            gp.run(resident)
+        barrier()
+        if profile:
+            reef_b200._lib.check(reef_b200.lib.reef_profile_enable(ctx._h, 1))
+        launches0 = int(reef_b200.lib.reef_launch_count())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clk = sample_clocks_start() if profile else (None, None)
+        barrier()
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            flush.fill_(1)                      # L2 flush between steps (default stream; ordered by the syncs inside run)
+            torch.cuda.current_stream().synchronize()
+            gp.run(resident)
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        launches = int(reef_b200.lib.reef_launch_count()) - launches0
+        clocks = sample_clocks_stop(*clk, device=dev) if profile else None
+        prof = None
+        if profile:
+            n = 9
+            cnt, units, pms = (C.c_uint64 * n)(), (C.c_uint64 * n)(), (C.c_double * n)()
+            reef_b200._lib.check(reef_b200.lib.reef_profile_read(ctx._h, n, cnt, units, pms))
+            reef_b200._lib.check(reef_b200.lib.reef_profile_enable(ctx._h, 0))
+            prof = [(int(cnt[i]), int(units[i]), float(pms[i])) for i in range(n)]
+        return ms, wall * 1e3, launches, clocks, prof
+
+    K, Wm = args.steps, args.warmup
+    ms, wall_ms, launches, clocks, prof = timed(True, K, Wm, True)
+    e2e_ms, _, _, _, _ = timed(False, K, max(1, Wm // 2), False)
+    doc_units = w["doc_len"] * (world if world > 1 else 1)
+    value = doc_units / (ms / K / 1e3)
+    e2e_value = doc_units / (e2e_ms / K / 1e3)
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    names = ["sweep_first", "sweep_fold", "round_transcript", "tail", "nl_setup", "msm_sort", "msm_accum", "msm_reduce", "poseidon"]
+    total_prof = sum(p[2] for p in prof) or 1.0
+    shares = {n: round(p[2] / total_prof, 4) for n, p in zip(names, prof)}
+    kernel_ms = {n: round(p[2] / K, 4) for n, p in zip(names, prof)}
+    # MLE sweep roofline: algorithmic bytes of the reference-shaped fused schedule (SURVEY 8d:
+    # 2 tables x 32 B): round-1 pass reads 2 L elements (64 L bytes); a fold+accumulate pass over
+    # an input of length L reads 2 L and writes L elements (96 L bytes).
+    sweep_bytes = 64.0 * prof[0][1] + 96.0 * prof[1][1]
+    sweep_ms = prof[0][2] + prof[1][2]
+    achieved = sweep_bytes / (sweep_ms / 1e3) / 1e9 if sweep_ms > 0 else 0.0
+    roof = {"bound": "hbm", "kernel": "k_sweep (MLE fold+accumulate passes)", "achieved": round(achieved, 1),
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": None,
+            "peak_source": peaks["source"], "launches": prof[0][0] + prof[1][0],
+            "avg_launch_us": round(1e3 * sweep_ms / max(1, prof[0][0] + prof[1][0]), 2)}
+    tr = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+    if os.path.exists(tr):
+        try:
+            roof["traffic"] = json.load(open(tr)).get(args.workload)
+        except Exception:
+            pass
+    # MSM: ops_alg = 10 n W + 14 W 2^c modmuls, against the measured modmul peak
+    msm_ms = prof[5][2] + prof[6][2] + prof[7][2]
+    ops = 0.0
+    n_terms = 0
+    for bases, n in ((gp.bases_pri, w["n_pri"]), (gp.bases_sec, w["n_sec"])):
+        Wn, c = bases.windows, bases.window_bits
+        ops += 2 * w["steps"] * K * (10.0 * n * Wn + 14.0 * Wn * (1 << c)) / max(1, world)
+        n_terms += 2 * w["steps"] * K * n
+    msm = {"bound": "int-alu (255-bit modmul)", "mops": round(n_terms / (msm_ms / 1e3) / 1e6, 2) if msm_ms else None,
+           "achieved_modmul_per_s": round(ops / (msm_ms / 1e3), 0) if msm_ms else None, "peak_modmul_per_s": peaks["modmul_per_s"],
+           "frac": round(ops / (msm_ms / 1e3) / peaks["modmul_per_s"], 4) if msm_ms else None,
+           "peak_source": "tools/bench_fp.cu on this pool (profiles/peak_modmul.json)"}
+    h2d, d2h = gp.bytes_per_step()
+    out = {
+        "metric": "NFA steps/s proved (= doc_len / hot-path prove time)", "value": round(value, 1), "unit": "NFA steps/s",
+        "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms / K, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 limbs (255-bit prime fields Fq/Fp, exact integer)",
+        "data": "synthetic",
+        "config": {"workload": args.workload + ": " + w["desc"], "l2": "256 MiB buffer written between steps (L2 flush)",
+                   "timing": "CUDA events on the library stream, max over ranks", "parallelism": f"msm-window-shard x{world}"},
+        "e2e": {"value": round(e2e_value, 1), "unit": "NFA steps/s", "ms_per_step": round(e2e_ms / K, 4),
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "msm": msm,
+        "kernel_ms_per_step": kernel_ms, "kernel_share": shares, "wall_ms_per_step": round(wall_ms / K, 4),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(w, sample_steps=1, threads=None)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle's C restatement of the reference's algorithm (never used by the product)
+# --------------------------------------------------------------------------------------------
+def cpu_pass(w, n_steps, threads):
+    """Runs `n_steps` Nova folds of the workload on the CPU port; returns seconds."""
+    from oracle import cport
+    from oracle.nlookup import combined_qs, logmn, nlookup_pattern
+    cport.lib().oracle_set_fast_poseidon(1)     # neptune hashes with its optimised constants too
+    t_total = 0.0
+    T_arr = np.frombuffer(w["T_bytes"], dtype=np.uint8)
+    prev = {"nl": None, "nldoc": None}
+    for s in range(n_steps):
+        t0 = time.perf_counter()
+        for key, arr, is_u32, n, q, vals in (("nl", T_arr, 0, len(w["T"]), w["q_nl"][s], [w["T"][i] for i in w["q_nl"][s]]),
+                                             ("nldoc", w["udoc"], 1, len(w["udoc"]), w["q_doc"][s], [int(w["udoc"][i]) for i in w["q_doc"][s]])):
+            ell = logmn(n)
+            pq, pv = prev[key] if prev[key] else ([0] * ell, (w["T"][0] if key == "nl" else int(w["udoc"][0])))
+            cqs = combined_qs(list(q), ell)
+            pat = nlookup_pattern(key, len(q), ell, len(cqs))
+            query = ([] if key == "nl" else [w["doc_hash"]]) + cqs + vals + list(pq) + [pv]
+            claim, rounds, last, nxt = cport.nlookup_raw(arr, is_u32, n, q, pack(query), len(query), cport.ops_words(pat),
+                                                         pack(pq), ell)
+            r = [int.from_bytes(rounds[i * 128:i * 128 + 32], "little") for i in range(ell)]
+            prev[key] = (r, int.from_bytes(nxt, "little"))
+        cport.poseidon_hash([prev["nl"][1], w["salt"]], 2)
+        cport.poseidon_hash([prev["nldoc"][1], w["salt"]], 2)
+        sc = w["sc"][s]
+        for key, curve, bases in (("Wp", "pallas", w["bases_pri"]), ("Tp", "pallas", w["bases_pri"]),
+                                  ("Ws", "vesta", w["bases_sec"]), ("Ts", "vesta", w["bases_sec"])):
+            cport.msm(curve, bases, sc[key].tobytes(), threads=threads)
+        t_total += time.perf_counter() - t0
+    return t_total
+
+
+def cpu_baseline(w, sample_steps, threads):
+    from oracle import cport
+    threads = threads or cport.max_threads()
+    sec = cpu_pass(w, sample_steps, threads)
+    per_pass = sec * w["steps"] / sample_steps
+    return {"value": round(w["doc_len"] / per_pass, 2), "unit": "NFA steps/s", "cores": threads, "kind": "port",
+            "seconds_per_pass": round(per_pass, 3),
+            "sample": f"{sample_steps} of {w['steps']} Nova folds of the same workload (sum-checks single-threaded as in "
+                      f"the reference, MSMs on {threads} threads), scaled to the full pass"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cport
+    w = make_workload(args.workload)
+    threads = cport.max_threads()
+    for _ in range(args.warmup):
+        cpu_pass(w, 1, threads)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_pass(w, 1, threads) * w["steps"]      # each step: one fold measured, scaled to the pass
+    per = t / args.steps
+    val = round(w["doc_len"] / per, 2)
+    out = {"impl": "reference", "metric": "NFA steps/s proved (= doc_len / hot-path prove time)", "value": val,
+           "unit": "NFA steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": round(per * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u64x4 limbs (255-bit prime fields, exact integer)", "data": "synthetic",
+           "config": {"workload": args.workload + ": " + w["desc"]},
+           "cpu_baseline": {"value": val, "unit": "NFA steps/s", "cores": threads, "kind": "port",
+                            "sample": "one Nova fold per step, scaled to the full pass; CPU restatement of the reference's "
+                                      "algorithm (oracle/c) -- the Rust reference cannot be built in this image"},
+           "e2e": {"value": val, "unit": "NFA steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="reef", choices=["reef", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "reef":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_reef(args)
+
+
+if __name__ == "__main__":
+    main()

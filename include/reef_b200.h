@@ -41,12 +41,23 @@ typedef struct reef_sponge reef_sponge; /* device-resident SAFE sponge session *
 
 /* ------------------------------------------------------------------ lifecycle */
 int reef_abi_version(void);
+/* number of CUDA kernels this library has launched in this process (all contexts) */
+uint64_t reef_launch_count(void);
 const char* reef_last_error(void);
 int reef_init(int device, reef_ctx** out);
 void reef_shutdown(reef_ctx* ctx);
 int reef_sync(reef_ctx* ctx);
 /* The CUDA stream (cudaStream_t) every launch of this context goes to; for event timing. */
 void* reef_stream(reef_ctx* ctx);
+
+/* Per-kernel-class device timing with CUDA events on the context's stream (for bench.py's
+ * roofline figures).  Classes: 0 sweep (round 1), 1 sweep fold+accumulate, 2 transcript round,
+ * 3 tail, 4 nlookup setup, 5 MSM sort, 6 MSM bucket accumulation, 7 MSM bucket reduction,
+ * 8 Poseidon batch/Merkle.  reef_profile_read sums launches-groups, work units and
+ * milliseconds per class since the last read and clears the records. */
+#define REEF_PROF_NCLASS 9
+int reef_profile_enable(reef_ctx* ctx, int on);
+int reef_profile_read(reef_ctx* ctx, uint32_t n_classes, uint64_t* counts, uint64_t* units, double* ms);
 
 /* ------------------------------------------------------------------ host-side helpers
  * Pure host logic of the path, kept behind the same ABI so the Rust shim and the tests use

@@ -43,11 +43,14 @@ lib = _load()
 _vp, _u8p = C.c_void_p, C.c_void_p
 _sig = {
     "reef_abi_version": (C.c_int, []),
+    "reef_launch_count": (C.c_uint64, []),
     "reef_last_error": (C.c_char_p, []),
     "reef_init": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "reef_shutdown": (None, [_vp]),
     "reef_sync": (C.c_int, [_vp]),
     "reef_stream": (_vp, [_vp]),
+    "reef_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "reef_profile_read": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp]),
     "reef_logmn": (C.c_uint32, [C.c_uint64]),
     "reef_doc_transform": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint64, _vp, C.c_uint64, C.POINTER(C.c_uint64)]),
     "reef_combined_q": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32, C.POINTER(C.c_uint32)]),

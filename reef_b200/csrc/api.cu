@@ -19,6 +19,7 @@ using namespace reef;
 // ---------------------------------------------------------------------------------------
 namespace reef {
 static thread_local std::string g_last_error;
+std::atomic<unsigned long long> g_launches{0};
 void set_error(const std::string& msg) { g_last_error = msg; }
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -149,6 +150,7 @@ extern "C" {
 // lifecycle
 // ---------------------------------------------------------------------------------------
 int reef_abi_version(void) { return 1; }
+uint64_t reef_launch_count(void) { return (uint64_t)g_launches.load(); }
 const char* reef_last_error(void) { return g_last_error.c_str(); }
 
 int reef_init(int device, reef_ctx** out) {
@@ -197,6 +199,45 @@ int reef_sync(reef_ctx* c) {
 }
 
 void* reef_stream(reef_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int reef_profile_enable(reef_ctx* c, int on) {
+  REEF_REQUIRE(c != nullptr, REEF_EINVAL, "reef_profile_enable: ctx is NULL");
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& r : c->prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  c->prof.clear();
+  c->profile = on != 0;
+  return REEF_OK;
+}
+
+int reef_profile_read(reef_ctx* c, uint32_t n_classes, uint64_t* counts, uint64_t* units, double* ms) {
+  REEF_REQUIRE(c && counts && units && ms, REEF_EINVAL, "reef_profile_read: NULL argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  REEF_CUDA(cudaStreamSynchronize(c->stream));
+  for (uint32_t k = 0; k < n_classes; k++) {
+    counts[k] = 0;
+    units[k] = 0;
+    ms[k] = 0.0;
+  }
+  for (auto& r : c->prof) {
+    float t = 0.f;
+    REEF_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    if ((uint32_t)r.cls < n_classes) {
+      counts[r.cls] += 1;
+      units[r.cls] += r.units;
+      ms[r.cls] += (double)t;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  c->prof.clear();
+  return REEF_OK;
+}
 
 // ---------------------------------------------------------------------------------------
 // host-side helpers

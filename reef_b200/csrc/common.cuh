@@ -4,8 +4,10 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <atomic>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/reef_b200.h"
 #include "fp.cuh"
@@ -27,6 +29,14 @@ int fail(int code, const std::string& msg);
     cudaError_t _e = (expr);                                                              \
     if (_e != cudaSuccess)                                                                \
       return ::reef::fail(REEF_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+// after every kernel launch: count it (reef_launch_count) and surface launch errors
+extern std::atomic<unsigned long long> g_launches;
+#define REEF_LAUNCHED()                                   \
+  do {                                                    \
+    ::reef::g_launches.fetch_add(1, std::memory_order_relaxed); \
+    REEF_CUDA(cudaGetLastError());                        \
   } while (0)
 
 #define REEF_REQUIRE(cond, code, msg)                  \
@@ -111,6 +121,24 @@ struct SpongeTags {
   Fq a4s1;  // IOPattern [Absorb(4), Squeeze(1)]
 };
 
+enum ProfClass : int {
+  PROF_SWEEP_FIRST = 0,   // k_sweep without fold (round 1)
+  PROF_SWEEP_FOLD = 1,    // k_sweep fold + accumulate (rounds >= 2)
+  PROF_ROUND = 2,         // k_round (transcript, A fold)
+  PROF_TAIL = 3,          // k_tail
+  PROF_NL_SETUP = 4,      // k_nl_begin + k_eq_tables
+  PROF_MSM_SORT = 5,      // digits, histogram, scans, scatter
+  PROF_MSM_ACCUM = 6,     // bucket accumulation passes
+  PROF_MSM_REDUCE = 7,    // bucket gather + bit-decomposition sum + final
+  PROF_POSEIDON = 8,      // hash batch / merkle levels / sponge
+  PROF_NCLASS = 9
+};
+struct ProfRec {
+  int cls;
+  uint64_t units;         // class-specific work units (e.g. input length of a sweep)
+  cudaEvent_t e0, e1;
+};
+
 }  // namespace reef
 
 struct reef_ctx {
@@ -128,10 +156,32 @@ struct reef_ctx {
   void* h_stage = nullptr;
   size_t h_stage_bytes = 0;
   int sm_count = 148;
+  // optional per-kernel-class event timing (reef_profile_enable); resolved lazily
+  bool profile = false;
+  std::vector<reef::ProfRec> prof;
 };
 
 namespace reef {
 int ctx_scratch(reef_ctx* c, size_t bytes, void** out);
 int ctx_scratch2(reef_ctx* c, size_t bytes, void** out);
 int ctx_stage(reef_ctx* c, size_t bytes, void** out);
+// RAII event pair around a group of launches (no-op unless profiling is enabled)
+struct ProfScope {
+  reef_ctx* c;
+  reef::ProfRec r;
+  bool on;
+  ProfScope(reef_ctx* ctx, int cls, uint64_t units) : c(ctx), on(ctx->profile) {
+    if (!on) return;
+    r.cls = cls;
+    r.units = units;
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, c->stream);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.e1, c->stream);
+    c->prof.push_back(r);
+  }
+};
 }  // namespace reef

@@ -431,10 +431,13 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
   if (m) REEF_CUDA(cudaMemcpyAsync(d_q, a.h_q, (size_t)m * 8, cudaMemcpyHostToDevice, s));
 
   Fq tag = fq_mont_from_le32(a.tag_le);
-  k_nl_begin<<<1, 32, 0, s>>>(st, d_query, a.n_query, tag, d_prevq, ell, d_q, m, d_pos, d_w, c->d_pos);
-  REEF_CUDA(cudaGetLastError());
-  k_eq_tables<<<ceil_div_u(a_len + b_len, 128), 128, 0, s>>>(st, ell, hb, d_A, a_len, d_B, b_len);
-  REEF_CUDA(cudaGetLastError());
+  {
+    ProfScope ps(c, PROF_NL_SETUP, N);
+    k_nl_begin<<<1, 32, 0, s>>>(st, d_query, a.n_query, tag, d_prevq, ell, d_q, m, d_pos, d_w, c->d_pos);
+    REEF_LAUNCHED();
+    k_eq_tables<<<ceil_div_u(a_len + b_len, 128), 128, 0, s>>>(st, ell, hb, d_A, a_len, d_B, b_len);
+    REEF_LAUNCHED();
+  }
 
   // sweep rounds 1 .. ell-h
   const void* t_cur = a.d_table;
@@ -443,22 +446,32 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
   for (uint32_t i = 0; i < n_sweeps; i++) {
     const uint32_t nblk = (uint32_t)((L / 2) / CHUNK);
     if (i == 0) {
-      k_sweep<U32IN, false><<<nblk, SWEEP_THREADS, 0, s>>>(a.d_table, N, nullptr, st, d_A, d_B, d_part);
-      REEF_CUDA(cudaGetLastError());
+      {
+        ProfScope ps(c, PROF_SWEEP_FIRST, N);
+        k_sweep<U32IN, false><<<nblk, SWEEP_THREADS, 0, s>>>(a.d_table, N, nullptr, st, d_A, d_B, d_part);
+        REEF_LAUNCHED();
+      }
+      ProfScope ps(c, PROF_ROUND, L);
       k_round<U32IN><<<1, ROUND_THREADS, 0, s>>>(st, d_part, nblk, a.d_table, L, d_A, a_cur, d_pos, d_w, m, i, c->d_pos);
+      REEF_LAUNCHED();
     } else {
-      if (i == 1) k_sweep<U32IN, true><<<nblk, SWEEP_THREADS, 0, s>>>(a.d_table, 2 * L, d_fold, st, d_A, d_B, d_part);
-      else k_sweep<false, true><<<nblk, SWEEP_THREADS, 0, s>>>(d_fold, 2 * L, d_fold, st, d_A, d_B, d_part);
-      REEF_CUDA(cudaGetLastError());
+      {
+        ProfScope ps(c, PROF_SWEEP_FOLD, 2 * L);
+        if (i == 1) k_sweep<U32IN, true><<<nblk, SWEEP_THREADS, 0, s>>>(a.d_table, 2 * L, d_fold, st, d_A, d_B, d_part);
+        else k_sweep<false, true><<<nblk, SWEEP_THREADS, 0, s>>>(d_fold, 2 * L, d_fold, st, d_A, d_B, d_part);
+        REEF_LAUNCHED();
+      }
+      ProfScope ps(c, PROF_ROUND, L);
       k_round<false><<<1, ROUND_THREADS, 0, s>>>(st, d_part, nblk, d_fold, L, d_A, a_cur, d_pos, d_w, m, i, c->d_pos);
+      REEF_LAUNCHED();
       t_cur = d_fold;
     }
-    REEF_CUDA(cudaGetLastError());
     if (a_cur > 1) a_cur >>= 1;
     L >>= 1;
   }
   // tail: fold with the last sweep challenge (if any) and finish
   const size_t tail_smem = (size_t)(2 * CHUNK + 3 * TAIL_THREADS / 32) * sizeof(Fq);
+  ProfScope* tail_scope = new ProfScope(c, PROF_TAIL, L);
   if (n_sweeps == 0) {
     REEF_CUDA(cudaFuncSetAttribute(k_tail<U32IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
     k_tail<U32IN><<<1, TAIL_THREADS, tail_smem, s>>>(st, a.d_table, N, 0, d_A, d_B, d_pos, d_w, m, 0, c->d_pos);
@@ -470,7 +483,8 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
     REEF_CUDA(cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
     k_tail<false><<<1, TAIL_THREADS, tail_smem, s>>>(st, t_cur, 2 * L, 1, d_A, d_B, d_pos, d_w, m, n_sweeps, c->d_pos);
   }
-  REEF_CUDA(cudaGetLastError());
+  delete tail_scope;
+  REEF_LAUNCHED();
 
   // results
   void* hs;
@@ -542,11 +556,11 @@ int launch_gen_eq_table(reef_ctx* c, const uint8_t* h_rs, const uint64_t* h_qs, 
   REEF_CUDA(cudaMemcpyAsync(d_lq, h_last_q, (size_t)ell * 32, cudaMemcpyHostToDevice, s));
   if (m) REEF_CUDA(cudaMemcpyAsync(d_qs, h_qs, (size_t)m * 8, cudaMemcpyHostToDevice, s));
   k_to_mont<<<ceil_div_u(m + 1 + ell, 128), 128, 0, s>>>(d_rs, m + 1 + ell);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
   k_eq_full<<<ceil_div_u(n, 128), 128, 0, s>>>(d_rs, d_lq, ell, m, (Fq*)d_out, n);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
   k_eq_scatter<<<1, 32, 0, s>>>(d_rs, d_qs, m, (Fq*)d_out);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
   return REEF_OK;
 }
 
@@ -576,7 +590,7 @@ int launch_mle_eval(reef_ctx* c, const void* d_table, int is_u32, uint64_t n, co
     Fq* out = (i & 1) ? buf1 : buf0;
     if (i == 0 && is_u32) k_fold<true><<<ceil_div_u(half, 128), 128, 0, s>>>(cur, out, half, r);
     else k_fold<false><<<ceil_div_u(half, 128), 128, 0, s>>>(cur, out, half, r);
-    REEF_CUDA(cudaGetLastError());
+    REEF_LAUNCHED();
     cur = out;
     L = half;
   }
@@ -626,9 +640,9 @@ int launch_mle_round_coeffs(reef_ctx* c, const void* d_t, const void* d_eq, uint
   Fq* part = (Fq*)base;
   cudaStream_t s = c->stream;
   k_round_coeffs<<<nblk, 128, 0, s>>>((const Fq*)d_t, (const Fq*)d_eq, pw, part);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
   k_sum_partials<<<1, 128, 0, s>>>(part, nblk, part + (size_t)nblk * 3);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
   REEF_CUDA(cudaMemcpyAsync(h_out3, part + (size_t)nblk * 3, 96, cudaMemcpyDeviceToHost, s));
   REEF_CUDA(cudaStreamSynchronize(s));
   return REEF_OK;
@@ -649,7 +663,7 @@ int launch_mle_round_fold(reef_ctx* c, void* d_t, void* d_eq, uint32_t ell, uint
   const uint64_t pw = (uint64_t)1 << (ell - i);
   Fq r = fq_mont_from_le32(h_r);
   k_fold2_inplace<<<ceil_div_u(pw, 128), 128, 0, c->stream>>>((Fq*)d_t, (Fq*)d_eq, pw, r);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
   return REEF_OK;
 }
 

@@ -523,51 +523,57 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
   Affine<C>* res_aff = (Affine<C>*)(res_xyzz + 1);
   XYZZ<C>* extra = (XYZZ<C>*)(d + o_extra);
 
+  ProfScope* scope = new ProfScope(c, PROF_MSM_SORT, n_entries);
   REEF_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(nb + 2) * 4, s));
   if (a.scalars_u32) k_digits<true><<<cdiv(n, 256), 256, 0, s>>>(a.d_scalars, n, a.n_bases, pl, a.w_begin, a.w_end, keys, vals);
   else k_digits<false><<<cdiv(n, 256), 256, 0, s>>>(a.d_scalars, n, a.n_bases, pl, a.w_begin, a.w_end, keys, vals);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
   k_hist<<<cdiv(n_entries, 256), 256, 0, s>>>(keys, n_entries, cnt);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
   // bucket starts (plain scan), then parts of the first pass
   k_scan<<<1, 1024, 0, s>>>(cnt, nb, 1, nullptr, start, cursor, tm);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
   k_scatter<<<cdiv(n_entries, 256), 256, 0, s>>>(keys, vals, n_entries, nb, cursor, sorted);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
   k_scan<<<1, 1024, 0, s>>>(cnt, nb, K_FIRST, pcnt[0], poff[0], nullptr, tm + 2);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
+  delete scope;
   uint32_t h_tm[4];
   REEF_CUDA(cudaMemcpyAsync(h_tm, tm, 16, cudaMemcpyDeviceToHost, s));
   REEF_CUDA(cudaStreamSynchronize(s));
   uint32_t n_parts = h_tm[2], max_cnt = h_tm[3];   // parts of pass 1, largest per-bucket part count
+  scope = new ProfScope(c, PROF_MSM_ACCUM, n_entries);
   if (n_parts) {
     k_accum_first<C><<<cdiv(n_parts, 128), 128, 0, s>>>(sorted, start, cnt, poff[0], nb, n_parts, (const Affine<C>*)a.d_levels,
                                                        parts[0]);
-    REEF_CUDA(cudaGetLastError());
+    REEF_LAUNCHED();
   }
   int cur = 0;
   while (max_cnt > 1) {
     const int nxt = cur ^ 1;
     k_scan<<<1, 1024, 0, s>>>(pcnt[cur], nb, K_NEXT, pcnt[nxt], poff[nxt], nullptr, tm + 2);
-    REEF_CUDA(cudaGetLastError());
+    REEF_LAUNCHED();
     const uint32_t n_next = (n_parts + K_NEXT - 1) / K_NEXT + nb;   // upper bound; exact count read on device
     k_accum_next<C><<<cdiv(n_next, 128), 128, 0, s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, parts[nxt]);
-    REEF_CUDA(cudaGetLastError());
+    REEF_LAUNCHED();
     max_cnt = (max_cnt + K_NEXT - 1) / K_NEXT;
     n_parts = n_next;
     cur = nxt;
   }
+  delete scope;
+  scope = new ProfScope(c, PROF_MSM_REDUCE, nb);
   k_gather_buckets<C><<<cdiv(nb, 256), 256, 0, s>>>(parts[cur], poff[cur], pcnt[cur], nb, buckets);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
   k_bitsum_partial<C><<<dim3(nblk, P.c, P.G), 256, 0, s>>>(buckets, P.B, bitpart);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
   if (a.n_extra) REEF_CUDA(cudaMemcpyAsync(extra, a.h_extra_xyzz_mont, (size_t)a.n_extra * sizeof(XYZZ<C>), cudaMemcpyHostToDevice, s));
   k_bitsum_final<C><<<1, 1024, 0, s>>>(bitpart, nblk, P.c, P.G, P.c * P.L, a.h_out_xyzz ? res_xyzz : nullptr,
                                        a.h_out_affine ? res_aff : nullptr, extra, a.n_extra);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
+  delete scope;
   if (a.h_out_xyzz) {
     k_xyzz_from_mont<C><<<1, 32, 0, s>>>(res_xyzz);
-    REEF_CUDA(cudaGetLastError());
+    REEF_LAUNCHED();
     REEF_CUDA(cudaMemcpyAsync(a.h_out_xyzz, res_xyzz, sizeof(XYZZ<C>), cudaMemcpyDeviceToHost, s));
   }
   if (a.h_out_affine) REEF_CUDA(cudaMemcpyAsync(a.h_out_affine, res_aff, sizeof(Affine<C>), cudaMemcpyDeviceToHost, s));
@@ -586,7 +592,7 @@ static int msm_combine_t(reef_ctx* c, const uint8_t* h_pts, uint32_t k, uint8_t*
   Affine<C>* d_out = (Affine<C>*)((char*)base + (((size_t)k * 128 + 255) & ~(size_t)255));
   REEF_CUDA(cudaMemcpyAsync(base, h_pts, (size_t)k * 128, cudaMemcpyHostToDevice, s));
   k_combine<C><<<1, 32, 0, s>>>((const XYZZ<C>*)base, k, d_out);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
   REEF_CUDA(cudaMemcpyAsync(h_out, d_out, 64, cudaMemcpyDeviceToHost, s));
   REEF_CUDA(cudaStreamSynchronize(s));
   return REEF_OK;

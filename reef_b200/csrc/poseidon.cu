@@ -254,9 +254,10 @@ int launch_hash_batch(reef_ctx* c, const void* d_in, int arity, uint64_t n, void
   if (n == 0) return REEF_OK;
   REEF_REQUIRE(arity == 2 || arity == 4, REEF_EINVAL, "poseidon hash arity must be 2 or 4");
   Fq tag = arity == 2 ? c->tags.a2s1 : c->tags.a4s1;
+  ProfScope ps(c, PROF_POSEIDON, n);
   unsigned blocks = (unsigned)((n + 127) / 128);
   k_hash_batch<<<blocks, 128, 0, c->stream>>>((const Fq*)d_in, arity, n, tag, c->d_pos, (Fq*)d_out);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
   return REEF_OK;
 }
 
@@ -267,8 +268,9 @@ int launch_merkle(reef_ctx* c, const uint64_t* d_doc, uint64_t n_doc, void* d_le
   Fq* lv = (Fq*)d_levels;
   uint64_t n_out = (n_doc + 1) / 2;
   uint32_t nl = 0;
+  ProfScope ps(c, PROF_POSEIDON, n_doc);
   k_merkle_leaves<<<(unsigned)((n_out + 127) / 128), 128, 0, c->stream>>>(d_doc, n_doc, c->tags.a4s1, c->d_pos, lv);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
   if (level_sizes) level_sizes[nl] = n_out;
   nl++;
   Fq* prev = lv;
@@ -283,7 +285,7 @@ int launch_merkle(reef_ctx* c, const uint64_t* d_doc, uint64_t n_doc, void* d_le
       k_merkle_level_warp<<<(unsigned)((n_out * 32 + 127) / 128), 128, 0, c->stream>>>(prev, n_prev, c->tags.a2s1,
                                                                                          c->d_pos, cur);
     }
-    REEF_CUDA(cudaGetLastError());
+    REEF_LAUNCHED();
     if (level_sizes) level_sizes[nl] = n_out;
     nl++;
     prev = cur;
@@ -297,7 +299,7 @@ int launch_sponge_run(reef_ctx* c, const uint32_t* d_ops, uint32_t n_ops, const 
                       void* d_out) {
   Fq tag = fq_mont_from_le32(tag_le);
   k_sponge_run<<<1, 32, 0, c->stream>>>(d_ops, n_ops, (const Fq*)d_in, tag, c->d_pos, (Fq*)d_out);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
   return REEF_OK;
 }
 
@@ -307,7 +309,7 @@ int launch_sponge_step(reef_ctx* c, void* d_state, int op, const void* d_in, uin
                        void* d_out) {
   Fq tag = tag_le ? fq_mont_from_le32(tag_le) : fe_zero<FqCfg>();
   k_sponge_step<<<1, 32, 0, c->stream>>>((SpongeDev*)d_state, op, (const Fq*)d_in, n, tag, c->d_pos, (Fq*)d_out);
-  REEF_CUDA(cudaGetLastError());
+  REEF_LAUNCHED();
   return REEF_OK;
 }
 

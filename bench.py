@@ -115,16 +115,23 @@ def make_workload(name: str, seed_shift: int = 0):
 class GpuPass:
     """One prove pass through libreef_b200 with raw buffers (no Python big-int work inside)."""
 
-    def __init__(self, ctx, w, rank=0, world=1, dist=None):
+    def __init__(self, ctxs, w, rank=0, world=1, dist=None):
+        """ctxs: dict of libreef_b200 contexts (one CUDA stream each): 'nl', 'doc', 'pri', 'sec'.
+        The reference runs the sum-checks on its solver thread and the fold commitments on its
+        proving thread (framework.rs:98-110); here each of the four independent chains of a
+        fold has its own context/stream and host thread."""
         import reef_b200
         import torch
-        self.rb, self.torch, self.ctx, self.w = reef_b200, torch, ctx, w
+        from concurrent.futures import ThreadPoolExecutor
+        self.rb, self.torch, self.ctxs, self.w = reef_b200, torch, ctxs, w
+        self.ctx = ctxs["doc"]
         self.lib, self.check = reef_b200.lib, reef_b200._lib.check
         self.rank, self.world, self.dist = rank, world, dist
-        self.bases_pri = reef_b200.Bases(ctx, "pallas", w["bases_pri"])
-        self.bases_sec = reef_b200.Bases(ctx, "vesta", w["bases_sec"])
+        self.bases_pri = reef_b200.Bases(ctxs["pri"], "pallas", w["bases_pri"])
+        self.bases_sec = reef_b200.Bases(ctxs["sec"], "vesta", w["bases_sec"])
         self.ell_doc = reef_b200.logmn(len(w["udoc"]))
         self.ell_T = w["t_log"]
+        self.pool = {k: ThreadPoolExecutor(max_workers=1) for k in ctxs}
         self._mk_out()
 
     def _mk_out(self):
@@ -142,8 +149,8 @@ class GpuPass:
     # -- residency ----------------------------------------------------------------------
     def make_resident(self):
         w, t = self.w, self.torch
-        self.doc_tab = self.ctx.table_u32(w["udoc"])
-        self.T_tab = self.rb.Table(self.ctx, values=w["T"])
+        self.doc_tab = self.ctxs["doc"].table_u32(w["udoc"])
+        self.T_tab = self.rb.Table(self.ctxs["nl"], values=w["T"])
         self.sc_dev = [{k: t.from_numpy(v.view(np.int64)).cuda() for k, v in s.items()} for s in w["sc"]]
         t.cuda.synchronize()
 
@@ -152,20 +159,25 @@ class GpuPass:
         tag = 0 if key == "nl" else 1
         pq = prev[0] if prev else None
         pv = prev[1] if prev else None
-        self.check(self.lib.reef_nlookup_prove(self.ctx._h, tag, tab._h, q_arr.ctypes.data, v_bytes, len(q_arr), pq, pv,
+        ctx = self.ctxs["nl" if key == "nl" else "doc"]
+        self.check(self.lib.reef_nlookup_prove(ctx._h, tag, tab._h, q_arr.ctypes.data, v_bytes, len(q_arr), pq, pv,
                                               self.dh if tag else None, C.byref(o)))
         ell = o.ell
         rounds = b["rounds"].raw
         next_q = b"".join(rounds[i * 128:i * 128 + 32] for i in range(ell))
-        return next_q, b["nxt"].raw
+        nxt = b["nxt"].raw
+        d = C.create_string_buffer(32)
+        self.check(self.lib.reef_calc_d(ctx._h, nxt, self.salt, d))      # calc_d of the new running claim
+        return next_q, nxt
 
     def _msm(self, bases, dev_tensor, host_arr, n, resident):
         out = C.create_string_buffer(64)
+        ctx = bases.ctx
         if self.world == 1:
             if resident:
-                self.check(self.lib.reef_msm_dev(self.ctx._h, bases._h, C.c_void_p(dev_tensor.data_ptr()), n, out))
+                self.check(self.lib.reef_msm_dev(ctx._h, bases._h, C.c_void_p(dev_tensor.data_ptr()), n, out))
             else:
-                self.check(self.lib.reef_msm(self.ctx._h, bases._h, host_arr.ctypes.data, n, out))
+                self.check(self.lib.reef_msm(ctx._h, bases._h, host_arr.ctypes.data, n, out))
             return out.raw
         # multi-GPU: windows [w0, w1) on this rank, one all-gather of 128-byte partial points
         t = self.torch
@@ -174,37 +186,41 @@ class GpuPass:
         W = bases.windows
         w0, w1 = W * self.rank // self.world, W * (self.rank + 1) // self.world
         part = C.create_string_buffer(128)
-        self.check(self.lib.reef_msm_partial_dev(self.ctx._h, bases._h, C.c_void_p(dev_tensor.data_ptr()), n, w0, w1, part))
+        self.check(self.lib.reef_msm_partial_dev(ctx._h, bases._h, C.c_void_p(dev_tensor.data_ptr()), n, w0, w1, part))
         mine = t.frombuffer(bytearray(part.raw), dtype=t.uint8).cuda()
         gathered = [t.empty_like(mine) for _ in range(self.world)]
         self.dist.all_gather(gathered, mine)
         allp = b"".join(bytes(g.cpu().numpy().tobytes()) for g in gathered)
-        self.check(self.lib.reef_msm_combine(self.ctx._h, bases.curve, allp, self.world, out))
+        self.check(self.lib.reef_msm_combine(ctx._h, bases.curve, allp, self.world, out))
         return out.raw
 
     def run(self, resident: bool):
-        """One pass.  resident=False: every input crosses PCIe inside the call (e2e leg)."""
+        """One pass.  resident=False: every input crosses PCIe inside the call (e2e leg).
+        Dependencies kept: sum-check of fold i+1 needs the running claim of fold i; the fold
+        commitments of fold i are issued after both sum-checks of fold i (their witness)."""
         w = self.w
         self.dh = le32(w["doc_hash"])
-        salt = le32(w["salt"])
+        self.salt = le32(w["salt"])
         if resident:
             doc_tab, T_tab = self.doc_tab, self.T_tab
         else:
-            doc_tab = self.ctx.table_u32(w["udoc"])               # H2D of the document codes
-            T_tab = self._upload_T()
+            f1 = self.pool["doc"].submit(lambda: self.ctxs["doc"].table_u32(w["udoc"]))   # H2D of the document codes
+            f2 = self.pool["nl"].submit(self._upload_T)
+            doc_tab, T_tab = f1.result(), f2.result()
         prev_nl = prev_doc = None
-        outs = []
+        msm_futs = []
         for s in range(w["steps"]):
             qn, qd = self.q_nl[s], self.q_doc[s]
-            prev_nl = self._nlookup("nl", T_tab, qn[0], qn[1], prev_nl)
-            prev_doc = self._nlookup("nldoc", doc_tab, qd[0], qd[1], prev_doc)
-            d = C.create_string_buffer(32)
-            self.check(self.lib.reef_calc_d(self.ctx._h, prev_nl[1], salt, d))
-            self.check(self.lib.reef_calc_d(self.ctx._h, prev_doc[1], salt, d))
+            f_nl = self.pool["nl"].submit(self._nlookup, "nl", T_tab, qn[0], qn[1], prev_nl)
+            f_doc = self.pool["doc"].submit(self._nlookup, "nldoc", doc_tab, qd[0], qd[1], prev_doc)
+            prev_nl, prev_doc = f_nl.result(), f_doc.result()
             sc, scd = w["sc"][s], (self.sc_dev[s] if resident else None)
-            for key, bases, n in (("Wp", self.bases_pri, w["n_pri"]), ("Tp", self.bases_pri, w["n_pri"]),
-                                  ("Ws", self.bases_sec, w["n_sec"]), ("Ts", self.bases_sec, w["n_sec"])):
-                outs.append(self._msm(bases, scd[key] if resident else None, sc[key], n, resident))
+            for key, pool, bases, n in (("Wp", "pri", self.bases_pri, w["n_pri"]), ("Ws", "sec", self.bases_sec, w["n_sec"]),
+                                        ("Tp", "pri", self.bases_pri, w["n_pri"]), ("Ts", "sec", self.bases_sec, w["n_sec"])):
+                if self.world > 1:
+                    pool = "pri"            # one thread issues the NCCL collectives, in the same order on every rank
+                msm_futs.append(self.pool[pool].submit(self._msm, bases, scd[key] if resident else None, sc[key], n, resident))
+        outs = [f.result() for f in msm_futs]
         if not resident:
             doc_tab.free()
             T_tab.free()
@@ -212,9 +228,9 @@ class GpuPass:
 
     def _upload_T(self):
         h = C.c_void_p()
-        self.check(self.lib.reef_table_upload(self.ctx._h, self.w["T_bytes"], len(self.w["T"]), C.byref(h)))
+        self.check(self.lib.reef_table_upload(self.ctxs["nl"]._h, self.w["T_bytes"], len(self.w["T"]), C.byref(h)))
         t = self.rb.Table.__new__(self.rb.Table)
-        t.ctx, t._h = self.ctx, h
+        t.ctx, t._h = self.ctxs["nl"], h
         return t
 
     def prepare_queries(self):
@@ -304,17 +320,17 @@ def run_reef(args):
     else:
         torch.cuda.set_device(0)
     dev = local if world > 1 else 0
-    ctx = reef_b200.Context(dev)
+    ctxs = {k: reef_b200.Context(dev) for k in ("nl", "doc", "pri", "sec")}
     # weak scaling: every rank proves its own document of the named length (seed differs per
     # rank); the fold commitments of rank r's document are window-sharded across ALL ranks.
     # With one document per rank the MSM collective would interleave G documents; to keep the
     # collective structure simple every rank runs the same MSM inputs as rank 0 for those and
     # its own document for the sum-checks.
     w = make_workload(args.workload, seed_shift=0)
-    gp = GpuPass(ctx, w, rank, world, dist)
+    gp = GpuPass(ctxs, w, rank, world, dist)
     gp.prepare_queries()
     gp.make_resident()
-    stream = torch.cuda.ExternalStream(ctx.stream)
+    streams = {k: torch.cuda.ExternalStream(c.stream) for k, c in ctxs.items()}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")    # > 126 MB L2
 
     def barrier():
@@ -327,21 +343,24 @@ def run_reef(args):
             gp.run(resident)
         barrier()
         if profile:
-            reef_b200._lib.check(reef_b200.lib.reef_profile_enable(ctx._h, 1))
+            for c in ctxs.values():
+                reef_b200._lib.check(reef_b200.lib.reef_profile_enable(c._h, 1))
         launches0 = int(reef_b200.lib.reef_launch_count())
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = {k: torch.cuda.Event(enable_timing=True) for k in streams}
         clk = sample_clocks_start() if profile else (None, None)
         barrier()
-        e0.record(stream)
+        e0.record(streams["doc"])               # every stream is idle here (barrier above)
         t0 = time.perf_counter()
         for _ in range(steps):
-            flush.fill_(1)                      # L2 flush between steps (default stream; ordered by the syncs inside run)
+            flush.fill_(1)                      # L2 flush between steps; run() returns only after all streams drained
             torch.cuda.current_stream().synchronize()
             gp.run(resident)
-        e1.record(stream)
+        for k in streams:
+            e1[k].record(streams[k])
         barrier()
         wall = time.perf_counter() - t0
-        ms = e0.elapsed_time(e1)
+        ms = max(e0.elapsed_time(e1[k]) for k in streams)
         if world > 1:
             tt = torch.tensor([ms], device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -351,10 +370,12 @@ def run_reef(args):
         prof = None
         if profile:
             n = 9
-            cnt, units, pms = (C.c_uint64 * n)(), (C.c_uint64 * n)(), (C.c_double * n)()
-            reef_b200._lib.check(reef_b200.lib.reef_profile_read(ctx._h, n, cnt, units, pms))
-            reef_b200._lib.check(reef_b200.lib.reef_profile_enable(ctx._h, 0))
-            prof = [(int(cnt[i]), int(units[i]), float(pms[i])) for i in range(n)]
+            prof = [(0, 0, 0.0)] * n
+            for c in ctxs.values():
+                cnt, units, pms = (C.c_uint64 * n)(), (C.c_uint64 * n)(), (C.c_double * n)()
+                reef_b200._lib.check(reef_b200.lib.reef_profile_read(c._h, n, cnt, units, pms))
+                reef_b200._lib.check(reef_b200.lib.reef_profile_enable(c._h, 0))
+                prof = [(p[0] + int(cnt[i]), p[1] + int(units[i]), p[2] + float(pms[i])) for i, p in enumerate(prof)]
         return ms, wall * 1e3, launches, clocks, prof
 
     K, Wm = args.steps, args.warmup
@@ -405,7 +426,9 @@ def run_reef(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 limbs (255-bit prime fields Fq/Fp, exact integer)",
         "data": "synthetic",
         "config": {"workload": args.workload + ": " + w["desc"], "l2": "256 MiB buffer written between steps (L2 flush)",
-                   "timing": "CUDA events on the library stream, max over ranks", "parallelism": f"msm-window-shard x{world}"},
+                   "timing": "CUDA events: start on an idle stream, end = latest of the 4 library streams; max over ranks",
+                   "streams": "4 contexts/streams: nl sum-check | nldoc sum-check | Pallas MSMs | Vesta MSMs (fold i+1 sum-checks overlap fold i commitments)",
+                   "parallelism": f"msm-window-shard x{world}"},
         "e2e": {"value": round(e2e_value, 1), "unit": "NFA steps/s", "ms_per_step": round(e2e_ms / K, 4),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "msm": msm,

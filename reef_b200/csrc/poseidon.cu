@@ -65,13 +65,15 @@ void poseidon_tables_host(PoseidonTables* t) {
   auto cv = [](const uint32_t* l) { return to_mont<FqCfg>(fq_from_limbs(l)); };
   for (int r = 0; r < 8; r++)
     for (int i = 0; i < 5; i++) t->rc_full[r][i] = cv(REEF_POSEIDON_RC_FULL[r * 5 + i]);
-  for (int r = 0; r < 56; r++) t->rc_part[r] = cv(REEF_POSEIDON_RC_PART[r]);
   for (int i = 0; i < 5; i++)
     for (int j = 0; j < 5; j++) t->mds[i][j] = cv(REEF_POSEIDON_MDS[i * 5 + j]);
+  for (int r = 0; r < 57; r++) t->kp[r] = cv(REEF_POSEIDON_KP[r]);
   for (int r = 0; r < 56; r++)
-    for (int i = 0; i < 5; i++) t->sp_row[r][i] = cv(REEF_POSEIDON_SP_ROW[r * 5 + i]);
+    for (int i = 0; i < 4; i++) t->beta[r][i] = cv(REEF_POSEIDON_BETA[r * 4 + i]);
+  for (int i = 0; i < 4; i++) t->dshift[0][i] = fe_zero<FqCfg>();
   for (int r = 0; r < 56; r++)
-    for (int i = 0; i < 4; i++) t->sp_col[r][i] = cv(REEF_POSEIDON_SP_COL[r * 4 + i]);
+    for (int i = 0; i < 4; i++) t->dshift[r + 1][i] = cv(REEF_POSEIDON_D[r * 4 + i]);
+  t->lam_end = cv(REEF_POSEIDON_LAM_END[0]);
   for (int i = 0; i < 4; i++)
     for (int j = 0; j < 4; j++) t->post[i][j] = cv(REEF_POSEIDON_POST[i * 4 + j]);
 }
@@ -118,6 +120,21 @@ __global__ void __launch_bounds__(128) k_hash_batch(const Fq* __restrict__ in, i
   for (int k = 0; k < 4; k++) s[1 + k] = (k < arity) ? to_mont<FqCfg>(ld256(in + i * arity + k)) : fe_zero<FqCfg>();
   poseidon_permute(s, *K);
   st256(out + i, from_mont<FqCfg>(s[1]));
+}
+
+// same contract, one WARP per hash (latency path: calc_d, small batches)
+__global__ void __launch_bounds__(128) k_hash_batch_warp(const Fq* __restrict__ in, int arity, uint64_t n, Fq tag,
+                                                         const PoseidonTables* __restrict__ K, Fq* __restrict__ out) {
+  uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;  // warp-uniform
+  Fq s = fe_zero<FqCfg>();
+  if (lane >= 1 && lane <= arity) s = ld256(in + i * arity + (lane - 1));
+  Fq sm = to_mont<FqCfg>(s);
+  s = lane == 0 ? tag : sm;
+  poseidon_permute_warp5(s, K);
+  Fq o = from_mont<FqCfg>(s);
+  if (lane == 1) st256(out + i, o);
 }
 
 // leaf level: parent k = H4(2k, doc[2k], 2k+1, doc[2k+1]); missing right => (.., 0, 0)
@@ -255,8 +272,11 @@ int launch_hash_batch(reef_ctx* c, const void* d_in, int arity, uint64_t n, void
   REEF_REQUIRE(arity == 2 || arity == 4, REEF_EINVAL, "poseidon hash arity must be 2 or 4");
   Fq tag = arity == 2 ? c->tags.a2s1 : c->tags.a4s1;
   ProfScope ps(c, PROF_POSEIDON, n);
-  unsigned blocks = (unsigned)((n + 127) / 128);
-  k_hash_batch<<<blocks, 128, 0, c->stream>>>((const Fq*)d_in, arity, n, tag, c->d_pos, (Fq*)d_out);
+  if (n < (uint64_t)c->sm_count * 256) {   // too few hashes to fill the machine: one warp each
+    k_hash_batch_warp<<<(unsigned)((n * 32 + 127) / 128), 128, 0, c->stream>>>((const Fq*)d_in, arity, n, tag, c->d_pos, (Fq*)d_out);
+  } else {
+    k_hash_batch<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((const Fq*)d_in, arity, n, tag, c->d_pos, (Fq*)d_out);
+  }
   REEF_LAUNCHED();
   return REEF_OK;
 }

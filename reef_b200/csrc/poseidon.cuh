@@ -18,11 +18,15 @@ typedef Fe<FqCfg> Fq;
 // All tables in Montgomery form.  Filled once per device by poseidon_upload_constants().
 struct PoseidonTables {
   Fq rc_full[8][5];
-  Fq rc_part[56];
   Fq mds[5][5];
-  Fq sp_row[56][5];
-  Fq sp_col[56][4];
   Fq post[4][4];
+  // rescaled partial rounds (tools/gen_poseidon_consts.py):  u_r = w_r^5,
+  //   w_{r+1} = u_r + sum_i beta[r][i] s_i(r) + kp[r+1],   s_i(r+1) = s_i(r) + D[r][i] u_r,
+  //   after round 55: s_0 = lam_end * w_56.   dshift[r] = D[r-1] (dshift[0] = 0).
+  Fq kp[57];
+  Fq beta[56][4];
+  Fq dshift[57][4];
+  Fq lam_end;
 };
 
 // x^5
@@ -67,21 +71,24 @@ REEF_HD void poseidon_permute(Fq* s /*5*/, const PoseidonTables& K) {
     for (int i = 0; i < 5; i++) t[i] = quintic(fe_add<FqCfg>(s[i], K.rc_full[r][i]));
     dense_mul<5, 5>(s, &K.mds[0][0], t);
   }
+  {
+    Fq w = fe_add<FqCfg>(s[0], K.kp[0]);
 #pragma unroll 1
-  for (int r = 0; r < 56; r++) {
-    Fq z0 = quintic(fe_add<FqCfg>(s[0], K.rc_part[r]));
-    // new0 = row . (z0, s1..s4)
-    u32 acc[16];
-    mul_wide(acc, K.sp_row[r][0].v, z0.v);
+    for (int r = 0; r < 56; r++) {
+      Fq u = quintic(w);
+      u32 acc[16];
+      mul_wide(acc, K.beta[r][0].v, s[1].v);
 #pragma unroll 1
-    for (int i = 1; i < 5; i++) {
-      u32 w[16];
-      mul_wide(w, K.sp_row[r][i].v, s[i].v);
-      acc_add<16>(acc, w);
+      for (int i = 1; i < 4; i++) {
+        u32 t2[16];
+        mul_wide(t2, K.beta[r][i].v, s[1 + i].v);
+        acc_add<16>(acc, t2);
+      }
+      w = fe_add<FqCfg>(fe_add<FqCfg>(u, reduce_sum8(acc)), K.kp[r + 1]);
+#pragma unroll 1
+      for (int i = 0; i < 4; i++) s[1 + i] = fe_add<FqCfg>(s[1 + i], mont_mul<FqCfg>(K.dshift[r + 1][i], u));
     }
-#pragma unroll 1
-    for (int i = 1; i < 5; i++) s[i] = fe_add<FqCfg>(s[i], mont_mul<FqCfg>(K.sp_col[r][i - 1], z0));
-    s[0] = reduce_sum8(acc);
+    s[0] = mont_mul<FqCfg>(K.lam_end, w);
   }
   {
     Fq u[4];
@@ -153,28 +160,31 @@ static __device__ __noinline__ void poseidon_full_round_warp5(Fq& s, int r, int 
   s = reduce_sum8(acc);
 }
 
-static __device__ __noinline__ void poseidon_partial_round_warp5(Fq& s, int r, int lane, int li,
-                                                          const PoseidonTables* K) {
+// One rescaled partial round.  lane 0 carries w (the rescaled lane-0 state), lanes 1..4 carry
+// s_i; `ub` = u of the previous round on every lane.  Three multiplications deep:
+//   step 1  lane 0: w^2          lanes 1..4: s_i += dshift[r][i] * u_{r-1}
+//   step 2  lane 0: w^4          lanes 1..4: p_i = beta[r][i] * s_i      (then summed onto lane 0)
+//   step 3  lane 0: u = w^4 * w
+//   lane 0: w <- u + sum p_i + kp[r+1]
+static __device__ __noinline__ void poseidon_partial_round_warp5(Fq& s, Fq& ub, int r, int lane, int li,
+                                                                 const PoseidonTables* K) {
   const bool l0 = (li == 0);
   const bool mid = (lane >= 1 && lane <= 4);
-  Fq t = fe_add<FqCfg>(s, ldg_fq(&K->rc_part[r]));
-  // step 1: lane 0 squares t; lanes 1..4 compute b_i * s_i (off the critical path)
-  Fq opa = sel_fq(l0, t, ldg_fq(&K->sp_row[r][li]));
-  Fq opb = sel_fq(l0, t, s);
-  Fq m1 = mont_mul<FqCfg>(opa, opb);
-  // sum of b_i * s_i over lanes 1..4, made available on every lane of the 8-lane group
-  Fq v = sel_fq(mid, m1, fe_zero<FqCfg>());
-  v = fe_add<FqCfg>(v, shfl_xor_fq(v, 1));
-  v = fe_add<FqCfg>(v, shfl_xor_fq(v, 2));
-  v = fe_add<FqCfg>(v, shfl_xor_fq(v, 4));
-  // steps 2,3: lane 0 finishes t^5
-  Fq t4 = mont_sqr<FqCfg>(m1);
-  Fq z0 = mont_mul<FqCfg>(t4, t);
-  z0 = shfl_fq(z0, 0);
-  // step 4: lane 0: a * z0 ; lanes 1..4: d_i * z0
-  Fq c = sel_fq(l0, ldg_fq(&K->sp_row[r][0]), ldg_fq(&K->sp_col[r][li > 0 ? li - 1 : 0]));
-  Fq m4 = mont_mul<FqCfg>(c, z0);
-  s = fe_add<FqCfg>(m4, sel_fq(l0, v, s));
+  const int ci = li > 0 ? li - 1 : 0;
+  const Fq kd = ldg_fq(&K->dshift[r][ci]);
+  const Fq kb = ldg_fq(&K->beta[r][ci]);
+  const Fq kk = ldg_fq(&K->kp[r + 1]);
+  const Fq w = s;
+  Fq m1 = mont_mul<FqCfg>(sel_fq(l0, w, kd), sel_fq(l0, w, ub));
+  Fq si = fe_add<FqCfg>(s, m1);                        // lanes 1..4: s_i(r)
+  Fq m2 = mont_mul<FqCfg>(sel_fq(l0, m1, kb), sel_fq(l0, m1, si));
+  // C = p_1 + p_2 + p_3 + p_4 on lane 0
+  Fq v = sel_fq(mid, m2, fe_zero<FqCfg>());
+  Fq v1 = fe_add<FqCfg>(v, shfl_fq(v, (lane + 1) & 31));
+  Fq c = fe_add<FqCfg>(fe_add<FqCfg>(shfl_fq(v1, 1), shfl_fq(v1, 3)), kk);
+  Fq u = mont_mul<FqCfg>(m2, w);                       // lane 0: w^5
+  ub = shfl_fq(u, 0);
+  s = sel_fq(l0, fe_add<FqCfg>(u, c), si);
 }
 
 static __device__ __noinline__ void poseidon_post_warp5(Fq& s, int li, const PoseidonTables* K) {
@@ -203,8 +213,16 @@ __device__ __forceinline__ void poseidon_permute_warp5(Fq& s, const PoseidonTabl
   if (lane >= 5) s = fe_zero<FqCfg>();
 #pragma unroll 1
   for (int r = 0; r < 4; r++) poseidon_full_round_warp5(s, r, li, K);
+  {
+    Fq ub = fe_zero<FqCfg>();
+    if (lane == 0) s = fe_add<FqCfg>(s, ldg_fq(&K->kp[0]));
 #pragma unroll 1
-  for (int r = 0; r < 56; r++) poseidon_partial_round_warp5(s, r, lane, li, K);
+    for (int r = 0; r < 56; r++) poseidon_partial_round_warp5(s, ub, r, lane, li, K);
+    // closing step: s_i(56) = s_i(55) + dshift[56][i] * u_55 ;  s_0 = lam_end * w_56
+    const int ci = li > 0 ? li - 1 : 0;
+    Fq m = mont_mul<FqCfg>(sel_fq(li == 0, ldg_fq(&K->lam_end), ldg_fq(&K->dshift[56][ci])), sel_fq(li == 0, s, ub));
+    s = li == 0 ? m : fe_add<FqCfg>(s, m);
+  }
   poseidon_post_warp5(s, li, K);
 #pragma unroll 1
   for (int r = 4; r < 8; r++) poseidon_full_round_warp5(s, r, li, K);

@@ -24,6 +24,18 @@ def test_hash_batch_arity_2_and_4(ctx):
     assert ctx.poseidon_hash([], 2) == []
 
 
+def test_hash_batch_thread_per_hash_path(ctx):
+    """>= 148*256 hashes take the thread-per-hash kernel; spot-check against the oracle."""
+    import numpy as np
+    n, arity = 40000, 4
+    raw = np.random.default_rng(5).integers(0, 1 << 62, size=(n * arity, 4), dtype=np.uint64)
+    raw[:, 3] &= (1 << 61) - 1
+    rows = [int.from_bytes(r.tobytes(), "little") for r in raw]
+    got = ctx.poseidon_hash(rows, arity)
+    for i in list(range(0, n, 997)) + [n - 1]:
+        assert got[i] == P.hash_once(rows[i * arity:(i + 1) * arity]), i
+
+
 def test_calc_d(ctx):
     # commitment.rs:495-510
     rnd = random.Random(2)

@@ -113,7 +113,18 @@ def derive():
     post = [row[1:] for row in B[1:]]
     rc_full = [list(c[r]) for r in range(half)] + [list(c[half + RP + r]) for r in range(half)]
     rc_full[half] = [(a + b) % P for a, b in zip(rc_full[half], tail)]
-    return dict(rc=rc, mds=mds, rc_full=rc_full, rc_part=k, sp_row=sp_row, sp_col=sp_col, post=post)
+    # Rescaled lane 0 (y_r = s0 / lam_r, lam_0 = 1, lam_{r+1} = a_r lam_r^5): the multiplication by the
+    # sparse matrix corner a_r leaves the critical path, which becomes w -> w^5 only:
+    #     u_r = w_r^5,  w_{r+1} = u_r + sum_i beta[r][i] s_i(r) + kp[r+1],  s_i(r+1) = s_i(r) + D[r][i] u_r
+    # and after the last round  s0 = lam_end * (u_55 + sum_i beta[55][i] s_i(55)).
+    lam = [1]
+    for r in range(RP):
+        lam.append(sp_row[r][0] * pow(lam[r], 5, P) % P)
+    kp = [k[r] * pow(lam[r], -1, P) % P for r in range(RP)] + [0]
+    beta = [[sp_row[r][i] * pow(lam[r + 1], -1, P) % P for i in range(1, T)] for r in range(RP)]
+    Dm = [[sp_col[r][i] * pow(lam[r], 5, P) % P for i in range(T - 1)] for r in range(RP)]
+    return dict(rc=rc, mds=mds, rc_full=rc_full, rc_part=k, sp_row=sp_row, sp_col=sp_col, post=post,
+                kp=kp, beta=beta, D=Dm, lam_end=lam[RP])
 
 
 def permute_optimized(state, K):
@@ -133,6 +144,30 @@ def permute_optimized(state, K):
         n0 = (row[0] * z0 + sum(row[i] * s[i] for i in range(1, T))) % P
         s = [n0] + [(col[i - 1] * z0 + s[i]) % P for i in range(1, T)]
     s = [s[0]] + matvec(K["post"], s[1:])
+    for r in range(half, RF):
+        s = full(s, r)
+    return s
+
+
+def permute_rescaled(state, K):
+    """Evaluation through the rescaled partial-round recurrence (what the GPU runs)."""
+    s = list(state)
+    half = RF // 2
+
+    def full(s, r):
+        s = [pow((x + K["rc_full"][r][i]) % P, 5, P) for i, x in enumerate(s)]
+        return matvec(K["mds"], s)
+
+    for r in range(half):
+        s = full(s, r)
+    w = (s[0] + K["kp"][0]) % P
+    rest = s[1:]
+    for r in range(RP):
+        u = pow(w, 5, P)
+        c = sum(K["beta"][r][i] * rest[i] for i in range(T - 1)) % P
+        w = (u + c + K["kp"][r + 1]) % P
+        rest = [(rest[i] + K["D"][r][i] * u) % P for i in range(T - 1)]
+    s = [K["lam_end"] * w % P] + matvec(K["post"], rest)
     for r in range(half, RF):
         s = full(s, r)
     return s
@@ -178,6 +213,10 @@ def emit(K, f):
     table("REEF_POSEIDON_SP_ROW", K["sp_row"])
     table("REEF_POSEIDON_SP_COL", K["sp_col"])
     table("REEF_POSEIDON_POST", K["post"])
+    table("REEF_POSEIDON_KP", K["kp"])
+    table("REEF_POSEIDON_BETA", K["beta"])
+    table("REEF_POSEIDON_D", K["D"])
+    table("REEF_POSEIDON_LAM_END", [K["lam_end"]])
 
 
 if __name__ == "__main__":
@@ -187,5 +226,6 @@ if __name__ == "__main__":
     for _ in range(5):
         st = [rnd.randrange(P) for _ in range(T)]
         assert permute_optimized(st, K) == permute_textbook(st, K), "optimised form != textbook form"
+        assert permute_rescaled(st, K) == permute_textbook(st, K), "rescaled form != textbook form"
     out = open(sys.argv[1], "w") if len(sys.argv) > 1 else sys.stdout
     emit(K, out)

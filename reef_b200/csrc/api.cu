@@ -138,6 +138,7 @@ static void hosttest_field_op(int op, const uint8_t* a, const uint8_t* b, uint8_
       r = wide_reduce_canonical<C>(w);
       break;
     }
+    case 7: r = from_mont<C>(mont_mul_ll<C>(to_mont<C>(x), to_mont<C>(y))); break;       // low-latency variant
     default: r = fe_zero<C>();
   }
   store_le(out, r.v);

@@ -19,6 +19,7 @@ __global__ void k_latency(Fq* io, int iters, long long* cycles) {
     if (MODE == 1) x = mont_sqr<FqCfg>(x);
     if (MODE == 2) x = fe_add<FqCfg>(x, y);
     if (MODE == 3) { u32 T[16]; mul_wide(T, x.v, y.v); for (int k = 0; k < 8; k++) x.v[k] = T[k] ^ T[8 + k]; }
+    if (MODE == 5) x = mont_mul_ll<FqCfg>(x, y);
     if (MODE == 4) { u32 T[16]; for (int k = 0; k < 8; k++) { T[k] = x.v[k]; T[8 + k] = y.v[k]; } mont_reduce<FqCfg>(x.v, T); }
   }
   long long t1 = clock64();
@@ -27,6 +28,14 @@ __global__ void k_latency(Fq* io, int iters, long long* cycles) {
 }
 
 // ILP independent chains per thread
+__global__ void __launch_bounds__(256) k_throughput_ll(Fp* io, int iters) {
+  int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  Fp x = io[gid], y = io[gid];
+  x.v[7] &= 0x3fffffff;
+  for (int i = 0; i < iters; i++) x = mont_mul_ll<FpCfg>(x, y);
+  io[gid] = x;
+}
+
 template <int ILP>
 __global__ void __launch_bounds__(256) k_throughput(Fp* io, int iters) {
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -45,8 +54,8 @@ int main() {
   Fq* io; long long* cyc;
   cudaMalloc(&io, 1 << 26); cudaMalloc(&cyc, 8);
   cudaMemset(io, 0x11, 1 << 26);
-  const char* names[5] = {"mont_mul", "mont_sqr", "fe_add", "mul_wide", "mont_reduce"};
-  for (int mode = 0; mode < 5; mode++) {
+  const char* names[6] = {"mont_mul", "mont_sqr", "fe_add", "mul_wide", "mont_reduce", "mont_mul_ll"};
+  for (int mode = 0; mode < 6; mode++) {
     const int iters = 2000;
     for (int rep = 0; rep < 2; rep++) {
       if (mode == 0) k_latency<0><<<1, 32>>>(io, iters, cyc);
@@ -54,6 +63,7 @@ int main() {
       if (mode == 2) k_latency<2><<<1, 32>>>(io, iters, cyc);
       if (mode == 3) k_latency<3><<<1, 32>>>(io, iters, cyc);
       if (mode == 4) k_latency<4><<<1, 32>>>(io, iters, cyc);
+      if (mode == 5) k_latency<5><<<1, 32>>>(io, iters, cyc);
       cudaDeviceSynchronize();
     }
     long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
@@ -77,6 +87,12 @@ int main() {
       double muls = (double)blocks * 256 * iters * ilp;
       printf("throughput ilp=%d blocks/SM=%d threads/SM=%4d : %7.2f G modmul/s  (%.3f ms)\n", ilp, bps, bps * 256, muls / best / 1e6, best);
     }
+  }
+  {
+    const int iters = 4000; int blocks = sms * 4;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) { cudaEventRecord(e0); k_throughput_ll<<<blocks, 256>>>((Fp*)io, iters); cudaEventRecord(e1); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms; }
+    printf("throughput mont_mul_ll blocks/SM=4 : %7.2f G modmul/s\n", (double)blocks * 256 * iters / best / 1e6);
   }
   printf("err=%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;

@@ -206,6 +206,17 @@ int reef_msm_dev(reef_ctx* ctx, const reef_bases* b, const void* scalars_dev, ui
 /* 32-bit scalars (document codes, small witness values) */
 int reef_msm_u32(reef_ctx* ctx, const reef_bases* b, const uint32_t* scalars, uint64_t n, uint8_t out[64]);
 
+/* Row-batched MSM = Hyrax polynomial commitment `hyrax_gen.commit(&poly)` (commitment.rs:187):
+ * the 2^left x 2^right matrix view of the document polynomial, row-major;
+ *   out[r] = sum_j M[r][j] * bases[j]  (+ blinds[r] * bases[cols] when blinds != NULL).
+ * `entry_bits` bounds the matrix entries (document codes: 8 for ascii/dna, 21 for utf8; 255 for
+ * field elements).  The generators must have been registered with scalar_bits = 255 when
+ * blinds are used.  out: rows x 64 B. */
+int reef_msm_rows_u32(reef_ctx* ctx, const reef_bases* b, const uint32_t* matrix, uint64_t rows, uint64_t cols,
+                      uint32_t entry_bits, const uint8_t* blinds, uint8_t* out);
+int reef_msm_rows(reef_ctx* ctx, const reef_bases* b, const uint8_t* matrix, uint64_t rows, uint64_t cols,
+                  const uint8_t* blinds, uint8_t* out);
+
 /* Multi-GPU: windows [w_begin, w_end) only; out_xyzz = partial sum as (X, Y, ZZ, ZZZ), 4 x 32 B
  * canonical.  The host all-gathers the partials (NCCL has no EC-add reduce op) and every rank
  * finishes with reef_msm_combine. */

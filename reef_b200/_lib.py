@@ -84,6 +84,8 @@ _sig = {
     "reef_msm": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp]),
     "reef_msm_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp]),
     "reef_msm_u32": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp]),
+    "reef_msm_rows_u32": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32, _vp, _vp]),
+    "reef_msm_rows": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, _vp]),
     "reef_msm_partial_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _vp]),
     "reef_msm_combine": (C.c_int, [_vp, C.c_int, _vp, C.c_uint32, _vp]),
     # test hooks (include/reef_b200_testing.h)

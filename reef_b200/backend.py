@@ -376,6 +376,18 @@ class Bases:
         check(lib.reef_msm_u32(self.ctx._h, self._h, a.ctypes.data if len(a) else None, len(a), out))
         return _pt_from(out.raw)
 
+    def msm_rows(self, matrix, rows: int, cols: int, entry_bits: int = 0, blinds=None):
+        """Hyrax `commit`: one commitment per matrix row (commitment.rs:187).  `matrix` is a numpy
+        uint32 array (document codes) or a flat list of field elements, row-major."""
+        out = C.create_string_buffer(rows * 64)
+        bl = _buf(_pack(blinds)) if blinds is not None else None
+        if isinstance(matrix, np.ndarray):
+            a = np.ascontiguousarray(matrix.astype(np.uint32).reshape(-1))
+            check(lib.reef_msm_rows_u32(self.ctx._h, self._h, a.ctypes.data, rows, cols, entry_bits, bl, out))
+        else:
+            check(lib.reef_msm_rows(self.ctx._h, self._h, _buf(_pack(matrix)), rows, cols, bl, out))
+        return [_pt_from(out.raw[i * 64:(i + 1) * 64]) for i in range(rows)]
+
     def msm_dev(self, dev_ptr: int, n: int):
         out = C.create_string_buffer(64)
         check(lib.reef_msm_dev(self.ctx._h, self._h, C.c_void_p(dev_ptr), n, out))

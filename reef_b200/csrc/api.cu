@@ -1106,6 +1106,54 @@ int reef_msm_partial_dev(reef_ctx* c, const reef_bases* b, const void* scalars_d
   return msm_dispatch(c, b, scalars_dev, 0, n, w_begin, w_end, nullptr, out_xyzz);
 }
 
+static int msm_rows_host(reef_ctx* c, const reef_bases* b, const void* matrix, int is_u32, uint64_t rows, uint64_t cols,
+                         uint32_t entry_bits, const uint8_t* blinds, uint8_t* out) {
+  REEF_REQUIRE(c && b && matrix && out, REEF_EINVAL, "reef_msm_rows: NULL argument");
+  REEF_REQUIRE(b->ctx == c, REEF_EINVAL, "reef_msm_rows: bases belong to another context");
+  REEF_REQUIRE(rows >= 1 && cols >= 1, REEF_EINVAL, "reef_msm_rows: empty matrix");
+  REEF_REQUIRE(cols + (blinds ? 1 : 0) <= b->n, REEF_EASSERT, "reef_msm_rows: not enough generators (assertion failed: gens.len() >= cols)");
+  if (entry_bits == 0 || entry_bits > 255) entry_bits = 255;
+  REEF_REQUIRE(entry_bits <= b->scalar_bits, REEF_EINVAL, "reef_msm_rows: generators registered for narrower scalars");
+  REEF_REQUIRE(!blinds || b->scalar_bits == 255, REEF_EINVAL, "reef_msm_rows: blinds need generators registered with scalar_bits = 255");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  const size_t mbytes = (size_t)rows * cols * (is_u32 ? 4 : 32);
+  const size_t mpad = (mbytes + 255) & ~(size_t)255;
+  void* d_s;
+  int rc = ctx_scratch2(c, mpad + (blinds ? rows * 32 : 0), &d_s);
+  if (rc) return rc;
+  REEF_CUDA(cudaMemcpyAsync(d_s, matrix, mbytes, cudaMemcpyHostToDevice, c->stream));
+  void* d_b = nullptr;
+  if (blinds) {
+    d_b = (char*)d_s + mpad;
+    REEF_CUDA(cudaMemcpyAsync(d_b, blinds, (size_t)rows * 32, cudaMemcpyHostToDevice, c->stream));
+  }
+  MsmRowsArgs a;
+  a.plan = b->plan;
+  a.d_levels = b->d_levels;
+  a.n_bases = b->n;
+  a.d_scalars = d_s;
+  a.scalars_u32 = is_u32;
+  a.scalar_bits = entry_bits;
+  a.rows = rows;
+  a.cols = cols;
+  a.d_blinds = d_b;
+  a.blind_base = cols;
+  a.h_out = out;
+  return msm_rows_run(c, b->curve, a);
+}
+
+int reef_msm_rows_u32(reef_ctx* c, const reef_bases* b, const uint32_t* matrix, uint64_t rows, uint64_t cols,
+                      uint32_t entry_bits, const uint8_t* blinds, uint8_t* out) {
+  if (entry_bits == 0 || entry_bits > 32) entry_bits = 32;
+  return msm_rows_host(c, b, matrix, 1, rows, cols, entry_bits, blinds, out);
+}
+
+int reef_msm_rows(reef_ctx* c, const reef_bases* b, const uint8_t* matrix, uint64_t rows, uint64_t cols,
+                  const uint8_t* blinds, uint8_t* out) {
+  return msm_rows_host(c, b, matrix, 0, rows, cols, 255, blinds, out);
+}
+
 int reef_msm_combine(reef_ctx* c, int curve, const uint8_t* partials, uint32_t k, uint8_t out[64]) {
   REEF_REQUIRE(c && partials && out, REEF_EINVAL, "reef_msm_combine: NULL argument");
   REEF_REQUIRE(curve == REEF_CURVE_PALLAS || curve == REEF_CURVE_VESTA, REEF_EINVAL, "reef_msm_combine: unknown curve");

@@ -70,5 +70,18 @@ struct MsmRunArgs {
 };
 int msm_run(reef_ctx* c, int curve, const MsmRunArgs& a);
 int msm_combine(reef_ctx* c, int curve, const uint8_t* h_pts, uint32_t k, uint8_t* h_out);
+struct MsmRowsArgs {
+  MsmPlanPublic plan;
+  const void* d_levels;
+  uint64_t n_bases;
+  const void* d_scalars;     // device: rows x cols, u32 or 32 B canonical, row-major
+  int scalars_u32;
+  uint32_t scalar_bits;      // upper bound on the matrix entries' bit length
+  uint64_t rows, cols;
+  const void* d_blinds;      // device: rows x 32 B or NULL
+  uint64_t blind_base;       // index of the blinding generator among the registered bases
+  uint8_t* h_out;            // rows x 64 B
+};
+int msm_rows_run(reef_ctx* c, int curve, const MsmRowsArgs& a);
 
 }  // namespace reef

@@ -409,6 +409,94 @@ __global__ void k_xyzz_from_mont(XYZZ<C>* p) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Row-batched MSM (Hyrax document commitment, commitment.rs:187): `rows` independent MSMs over
+// the SAME generators; bucket key = row * B + bucket, so one sort / one accumulation serves
+// all rows.  Optional blinding term blind[r] * bases[blind_idx] per row.
+// ---------------------------------------------------------------------------------------
+template <bool U32SCALARS>
+__global__ void k_digits_rows(const void* __restrict__ scalars, uint64_t rows, uint64_t cols, uint64_t col0,
+                              uint64_t n_bases, MsmPlan pl, uint32_t w_used, uint64_t entry_base,
+                              uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t n_terms = rows * cols;
+  if (t >= n_terms) return;
+  const uint64_t r = t / cols, j = t - r * cols;
+  uint32_t s[9];
+  if constexpr (U32SCALARS) {
+    s[0] = ((const uint32_t*)scalars)[t];
+#pragma unroll
+    for (int k = 1; k < 9; k++) s[k] = 0;
+  } else {
+    Fe<FqCfg> x = ld256((const Fe<FqCfg>*)scalars + t);
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[k] = x.v[k];
+    s[8] = 0;
+  }
+  const uint32_t c = pl.c, half = 1u << (c - 1), full = 1u << c, sentinel = (uint32_t)(rows * pl.B);
+  uint32_t carry = 0;
+  for (uint32_t w = 0; w < w_used; w++) {
+    const uint32_t bit = w * c, limb = bit >> 5, sh = bit & 31;
+    uint32_t raw = 0;
+    if (limb < 8) {
+      uint64_t two = (uint64_t)s[limb] | ((uint64_t)s[limb + 1] << 32);
+      raw = (uint32_t)(two >> sh) & (full - 1);
+    }
+    raw += carry;
+    uint32_t mag, neg;
+    if (raw > half) {
+      mag = full - raw;
+      neg = 1;
+      carry = 1;
+    } else {
+      mag = raw;
+      neg = 0;
+      carry = 0;
+    }
+    const uint64_t e = entry_base + (uint64_t)w * n_terms + t;
+    keys[e] = mag ? (uint32_t)(r * pl.B + (mag - 1)) : sentinel;
+    vals[e] = (uint32_t)((uint64_t)w * n_bases + col0 + j) | (neg << 31);
+  }
+}
+
+// one CTA per row: S_t from the row's bit-partials, 2^t scaling, sum, affine out
+template <class C>
+__global__ void __launch_bounds__(512) k_rows_final(const XYZZ<C>* __restrict__ partial, uint32_t nblk, uint32_t cbits,
+                                                    Affine<C>* __restrict__ out) {
+  __shared__ XYZZ<C> st[16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t g = blockIdx.x;
+  XYZZ<C> v = xyzz_inf<C>();
+  if ((uint32_t)warp < cbits) {
+    for (uint32_t k = lane; k < nblk; k += 32) xyzz_add<C>(v, ld_xyzz(partial + ((uint64_t)g * cbits + warp) * nblk + k));
+    if (nblk > 1) {
+#pragma unroll 1
+      for (int m = 16; m >= 1; m >>= 1) {
+        XYZZ<C> o = shfl_xor_xyzz(v, m);
+        xyzz_add<C>(v, o);
+      }
+    }
+#pragma unroll 1
+    for (int k = 0; k < warp; k++) v = xyzz_dbl<C>(v);
+  }
+  if (lane == 0) st[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    XYZZ<C> r = (uint32_t)lane < cbits ? st[lane] : xyzz_inf<C>();
+#pragma unroll 1
+    for (int m = 8; m >= 1; m >>= 1) {
+      XYZZ<C> o = shfl_xor_xyzz(r, m);
+      xyzz_add<C>(r, o);
+    }
+    if (lane == 0) {
+      Affine<C> a = xyzz_to_affine<C>(r);
+      a.x = from_mont<C>(a.x);
+      a.y = from_mont<C>(a.y);
+      st_affine(out + g, a);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 static unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
@@ -582,6 +670,112 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
 }
 
 int msm_run(reef_ctx* c, int curve, const MsmRunArgs& a) { return curve == 0 ? msm_run_t<FpCfg>(c, a) : msm_run_t<FqCfg>(c, a); }
+
+template <class C>
+static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
+  const MsmPlanPublic& P = a.plan;
+  MsmPlan pl{P.c, P.W, P.L, 1, P.B};
+  REEF_REQUIRE(P.G == 1, REEF_EINVAL, "reef_msm_rows: generators must be fully precomputed");
+  const uint64_t n_terms = a.rows * a.cols;
+  uint32_t w_used = a.scalar_bits / P.c + 1;
+  if (w_used > P.W) w_used = P.W;
+  const uint64_t n_entries = n_terms * w_used + (a.d_blinds ? a.rows * P.W : 0);
+  REEF_REQUIRE(n_entries < ((uint64_t)1 << 31), REEF_EINVAL, "reef_msm_rows: too many digit entries");
+  REEF_REQUIRE(a.rows * P.B < ((uint64_t)1 << 31), REEF_EINVAL, "reef_msm_rows: too many buckets");
+  const uint32_t nb = (uint32_t)(a.rows * P.B);
+  cudaStream_t s = c->stream;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const uint64_t max_parts1 = n_entries / K_FIRST + nb + 1;
+  const uint64_t max_parts2 = max_parts1 / K_NEXT + nb + 1;
+  size_t o_keys = take(n_entries * 4), o_vals = take(n_entries * 4), o_sorted = take(n_entries * 4);
+  size_t o_cnt = take((size_t)(nb + 2) * 4), o_start = take((size_t)(nb + 2) * 4), o_cursor = take((size_t)(nb + 2) * 4);
+  size_t o_pcnt[2] = {take((size_t)(nb + 2) * 4), take((size_t)(nb + 2) * 4)};
+  size_t o_poff[2] = {take((size_t)(nb + 2) * 4), take((size_t)(nb + 2) * 4)};
+  size_t o_tm = take(64);
+  size_t o_parts[2] = {take(max_parts1 * sizeof(XYZZ<C>)), take(max_parts2 * sizeof(XYZZ<C>))};
+  size_t o_buckets = take((size_t)nb * sizeof(XYZZ<C>));
+  const uint32_t nblk = cdiv(P.B, 256);
+  size_t o_bitpart = take((size_t)a.rows * P.c * nblk * sizeof(XYZZ<C>));
+  size_t o_out = take((size_t)a.rows * sizeof(Affine<C>));
+  void* base;
+  int rc = ctx_scratch(c, off, &base);
+  if (rc) return rc;
+  char* d = (char*)base;
+  uint32_t* keys = (uint32_t*)(d + o_keys);
+  uint32_t* vals = (uint32_t*)(d + o_vals);
+  uint32_t* sorted = (uint32_t*)(d + o_sorted);
+  uint32_t* cnt = (uint32_t*)(d + o_cnt);
+  uint32_t* start = (uint32_t*)(d + o_start);
+  uint32_t* cursor = (uint32_t*)(d + o_cursor);
+  uint32_t* pcnt[2] = {(uint32_t*)(d + o_pcnt[0]), (uint32_t*)(d + o_pcnt[1])};
+  uint32_t* poff[2] = {(uint32_t*)(d + o_poff[0]), (uint32_t*)(d + o_poff[1])};
+  uint32_t* tm = (uint32_t*)(d + o_tm);
+  XYZZ<C>* parts[2] = {(XYZZ<C>*)(d + o_parts[0]), (XYZZ<C>*)(d + o_parts[1])};
+  XYZZ<C>* buckets = (XYZZ<C>*)(d + o_buckets);
+  XYZZ<C>* bitpart = (XYZZ<C>*)(d + o_bitpart);
+  Affine<C>* d_out = (Affine<C>*)(d + o_out);
+
+  ProfScope* scope = new ProfScope(c, PROF_MSM_SORT, n_entries);
+  REEF_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(nb + 2) * 4, s));
+  if (a.scalars_u32) k_digits_rows<true><<<cdiv(n_terms, 256), 256, 0, s>>>(a.d_scalars, a.rows, a.cols, 0, a.n_bases, pl, w_used, 0, keys, vals);
+  else k_digits_rows<false><<<cdiv(n_terms, 256), 256, 0, s>>>(a.d_scalars, a.rows, a.cols, 0, a.n_bases, pl, w_used, 0, keys, vals);
+  REEF_LAUNCHED();
+  if (a.d_blinds) {
+    k_digits_rows<false><<<cdiv(a.rows, 256), 256, 0, s>>>(a.d_blinds, a.rows, 1, a.blind_base, a.n_bases, pl, P.W, n_terms * w_used, keys, vals);
+    REEF_LAUNCHED();
+  }
+  k_hist<<<cdiv(n_entries, 256), 256, 0, s>>>(keys, n_entries, cnt);
+  REEF_LAUNCHED();
+  k_scan<<<1, 1024, 0, s>>>(cnt, nb, 1, nullptr, start, cursor, tm);
+  REEF_LAUNCHED();
+  k_scatter<<<cdiv(n_entries, 256), 256, 0, s>>>(keys, vals, n_entries, nb, cursor, sorted);
+  REEF_LAUNCHED();
+  k_scan<<<1, 1024, 0, s>>>(cnt, nb, K_FIRST, pcnt[0], poff[0], nullptr, tm + 2);
+  REEF_LAUNCHED();
+  delete scope;
+  uint32_t h_tm[4];
+  REEF_CUDA(cudaMemcpyAsync(h_tm, tm, 16, cudaMemcpyDeviceToHost, s));
+  REEF_CUDA(cudaStreamSynchronize(s));
+  uint32_t n_parts = h_tm[2], max_cnt = h_tm[3];
+  scope = new ProfScope(c, PROF_MSM_ACCUM, n_entries);
+  if (n_parts) {
+    k_accum_first<C><<<cdiv(n_parts, 128), 128, 0, s>>>(sorted, start, cnt, poff[0], nb, n_parts, (const Affine<C>*)a.d_levels, parts[0]);
+    REEF_LAUNCHED();
+  }
+  int cur = 0;
+  while (max_cnt > 1) {
+    const int nxt = cur ^ 1;
+    k_scan<<<1, 1024, 0, s>>>(pcnt[cur], nb, K_NEXT, pcnt[nxt], poff[nxt], nullptr, tm + 2);
+    REEF_LAUNCHED();
+    const uint32_t n_next = (n_parts + K_NEXT - 1) / K_NEXT + nb;
+    k_accum_next<C><<<cdiv(n_next, 128), 128, 0, s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, parts[nxt]);
+    REEF_LAUNCHED();
+    max_cnt = (max_cnt + K_NEXT - 1) / K_NEXT;
+    n_parts = n_next;
+    cur = nxt;
+  }
+  delete scope;
+  scope = new ProfScope(c, PROF_MSM_REDUCE, nb);
+  k_gather_buckets<C><<<cdiv(nb, 256), 256, 0, s>>>(parts[cur], poff[cur], pcnt[cur], nb, buckets);
+  REEF_LAUNCHED();
+  k_bitsum_partial<C><<<dim3(nblk, P.c, (unsigned)a.rows), 256, 0, s>>>(buckets, P.B, bitpart);
+  REEF_LAUNCHED();
+  k_rows_final<C><<<(unsigned)a.rows, 512, 0, s>>>(bitpart, nblk, P.c, d_out);
+  REEF_LAUNCHED();
+  delete scope;
+  REEF_CUDA(cudaMemcpyAsync(a.h_out, d_out, (size_t)a.rows * sizeof(Affine<C>), cudaMemcpyDeviceToHost, s));
+  REEF_CUDA(cudaStreamSynchronize(s));
+  return REEF_OK;
+}
+
+int msm_rows_run(reef_ctx* c, int curve, const MsmRowsArgs& a) {
+  return curve == 0 ? msm_rows_run_t<FpCfg>(c, a) : msm_rows_run_t<FqCfg>(c, a);
+}
 
 template <class C>
 static int msm_combine_t(reef_ctx* c, const uint8_t* h_pts, uint32_t k, uint8_t* h_out) {

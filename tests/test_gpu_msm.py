@@ -76,3 +76,47 @@ def test_msm_known_discrete_logs(ctx, curve, n):
     assert b.combine(parts) == exp
     assert b.msm_dev(dev.data_ptr(), n) == exp
     b.free()
+
+
+def test_hyrax_row_commit_small_vs_naive(ctx):
+    """commitment.rs:187 `hyrax_gen.commit`: row r = sum_j M[r][j] G_j + blind_r H."""
+    cv = PALLAS
+    rnd = random.Random(5)
+    rows, cols = 4, 8
+    gens = [cv.mul(rnd.randrange(1, cv.order), cv.gen) for _ in range(cols + 1)]
+    b = ctx.bases("pallas", gens)
+    M = np.asarray([[rnd.randrange(131) for _ in range(cols)] for _ in range(rows)], dtype=np.uint32)
+    M[1, :] = 0                                                     # an all-zero row commits to blind*H only
+    blinds = [rnd.randrange(cv.order) for _ in range(rows)]
+    got = b.msm_rows(M, rows, cols, 8, blinds)
+    for r in range(rows):
+        assert got[r] == cv.msm([int(x) for x in M[r]] + [blinds[r]], gens), r
+    got = b.msm_rows(M, rows, cols, 8, None)
+    assert got[1] is None
+    assert got[2] == cv.msm([int(x) for x in M[2]], gens[:cols])
+    # field-element matrix entries (full width)
+    Mf = [rnd.randrange(cv.order) for _ in range(rows * cols)]
+    got = b.msm_rows(Mf, rows, cols, 0, blinds)
+    for r in range(rows):
+        assert got[r] == cv.msm(Mf[r * cols:(r + 1) * cols] + [blinds[r]], gens), r
+
+
+@pytest.mark.parametrize("ell,bits", [(17, 8), (15, 21)])
+def test_hyrax_row_commit_document_shape(ctx, ell, bits):
+    """cfg-2 shape: N = 2^17 document codes as a 256 x 512 matrix (left = ell/2, right = ell - left),
+    generators k*G so each row has a closed-form answer; includes the all-'a' adversarial rows."""
+    cv = PALLAS
+    rnd = random.Random(ell)
+    left = ell // 2
+    rows, cols = 1 << left, 1 << (ell - left)
+    gens = cv.multiples(cols + 1)
+    b = ctx.bases("pallas", gens)
+    M = np.random.default_rng(ell).integers(0, 1 << bits, size=(rows, cols), dtype=np.uint32)
+    M[0, :] = 97                                                    # 'a' * cols
+    M[1, :] = 0
+    blinds = [rnd.randrange(cv.order) for _ in range(rows)]
+    got = b.msm_rows(M, rows, cols, bits, blinds)
+    w = np.arange(1, cols + 1, dtype=object)
+    for r in list(range(4)) + [rows // 2, rows - 1]:
+        k = (int((M[r].astype(object) * w).sum()) + blinds[r] * (cols + 1)) % cv.order
+        assert got[r] == cv.mul(k, cv.gen), r

@@ -340,6 +340,7 @@ def run_reef(args):
 
     def timed(resident, steps, warmup, profile):
         for _ in range(warmup):
+            flush.fill_(1)
             gp.run(resident)
         barrier()
         if profile:
@@ -352,10 +353,15 @@ def run_reef(args):
         barrier()
         e0.record(streams["doc"])               # every stream is idle here (barrier above)
         t0 = time.perf_counter()
+        per_step = []
         for _ in range(steps):
             flush.fill_(1)                      # L2 flush between steps; run() returns only after all streams drained
             torch.cuda.current_stream().synchronize()
+            ts = time.perf_counter()
             gp.run(resident)
+            per_step.append(round((time.perf_counter() - ts) * 1e3, 3))
+        if args.debug and rank == 0:
+            print(f"[debug] resident={resident} profile={profile} per-step wall ms: {per_step}", file=sys.stderr)
         for k in streams:
             e1[k].record(streams[k])
         barrier()
@@ -523,6 +529,7 @@ def main():
     ap.add_argument("--impl", default="reef", choices=["reef", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--debug", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "reef":
         args.warmup = 3

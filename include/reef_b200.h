@@ -178,6 +178,12 @@ int reef_verifier_mle_eval(reef_ctx* ctx, const reef_table* table, const uint8_t
 int reef_prover_mle_partial_eval(reef_ctx* ctx, const reef_table* table, const uint8_t* x, uint32_t ell, int32_t hole,
                                  uint8_t out_coeff[32], uint8_t out_const[32]);
 
+/* Hyrax `prove_eval`'s vector-matrix product (commitment.rs:371-393 -> nova hyrax_pc):
+ * the table seen as a rows x cols row-major matrix M (rows * cols == padded table length),
+ *   out[j] = sum_i L[i] * M[i][j],  L = eq(q_left) (rows elements), out: cols elements.
+ * (L itself is reef_gen_eq_table with rs = [1], no lookups, last_q = reversed q_left.) */
+int reef_hyrax_lz(reef_ctx* ctx, const reef_table* table, uint64_t rows, uint64_t cols, const uint8_t* L, uint8_t* out);
+
 /* ------------------------------------------------------------------ B3: multi-scalar multiplication
  * Replaces nova-snark's `vartime_multiscalar_mul` / Pedersen `CE::commit` reached from
  * framework.rs:668-675 (prove_step: commit(W), commit(T)), framework.rs:695-698 (IPA inside

@@ -77,6 +77,7 @@ _sig = {
     "reef_linear_mle_product": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "reef_verifier_mle_eval": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp]),
     "reef_prover_mle_partial_eval": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_int32, _vp, _vp]),
+    "reef_hyrax_lz": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64, _vp, _vp]),
     "reef_bases_register": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, C.c_uint32, C.POINTER(_vp)]),
     "reef_bases_free": (None, [_vp]),
     "reef_bases_windows": (C.c_uint32, [_vp]),

@@ -166,6 +166,12 @@ class Context:
         check(lib.reef_prover_mle_partial_eval(self._h, table._h, _buf(_pack(xs)), len(xs), hole, oc, ok))
         return int.from_bytes(oc.raw, "little"), int.from_bytes(ok.raw, "little")
 
+    def hyrax_lz(self, table: "Table", rows: int, cols: int, L) -> list:
+        """LZ[j] = sum_i L[i] * M[i][j] over the rows x cols row-major view of `table`."""
+        out = C.create_string_buffer(cols * 32)
+        check(lib.reef_hyrax_lz(self._h, table._h, rows, cols, _buf(_pack(L)), out))
+        return _unpack(out.raw)
+
     # ---- nlookup
     def wit_nlookup_gadget(self, table: "Table", q, v, running_q=None, running_v=None, tag="nl", doc_hash=None):
         """r1cs.rs:2177-2393.  Returns NlookupResult."""

@@ -847,6 +847,17 @@ int reef_verifier_mle_eval(reef_ctx* c, const reef_table* t, const uint8_t* q, u
   return launch_mle_eval(c, t->d, t->is_u32, t->n_pad, q, ell, out);
 }
 
+int reef_hyrax_lz(reef_ctx* c, const reef_table* t, uint64_t rows, uint64_t cols, const uint8_t* L, uint8_t* out) {
+  REEF_REQUIRE(c && t && L && out, REEF_EINVAL, "reef_hyrax_lz: NULL argument");
+  REEF_REQUIRE(t->ctx == c, REEF_EINVAL, "reef_hyrax_lz: table belongs to another context");
+  REEF_REQUIRE(rows >= 1 && cols >= 1 && rows * cols == t->n_pad, REEF_EASSERT, "reef_hyrax_lz: rows * cols must equal the table length");
+  int rc = check_canonical(L, rows, "reef_hyrax_lz: L");
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  return launch_lz(c, t->d, t->is_u32, rows, cols, L, out);
+}
+
 int reef_prover_mle_partial_eval(reef_ctx* c, const reef_table* t, const uint8_t* x, uint32_t ell, int32_t hole,
                                  uint8_t out_coeff[32], uint8_t out_const[32]) {
   REEF_REQUIRE(c && t && x && out_coeff && out_const, REEF_EINVAL, "reef_prover_mle_partial_eval: NULL argument");

@@ -525,7 +525,74 @@ REEF_HD Fe<C> fe_pow_pm2(const Fe<C>& a) {
   return acc;
 }
 
+// Modular inverse by the binary extended Euclidean algorithm on the CANONICAL integer
+// (about 10x fewer instructions than a^(p-2)); returns 0 for 0.  Branchy: meant for the
+// single-thread tails (final affine conversion), not for SIMT-wide use.
 template <class C>
-REEF_HD Fe<C> fe_inv(const Fe<C>& a) { return fe_pow_pm2<C>(a); }
+REEF_HD void inv_canonical(u32* out, const u32* a_in) {
+  u32 p[8], u[8], v[8], x1[8], x2[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { p[i] = modulus_limb<C>(i); u[i] = a_in[i]; v[i] = p[i]; x1[i] = 0; x2[i] = 0; }
+  x1[0] = 1;
+  u32 nz = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) nz |= u[i];
+  if (nz == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = 0;
+    return;
+  }
+  auto is_one = [](const u32* x) {
+    u32 o = x[0] ^ 1u;
+    for (int i = 1; i < 8; i++) o |= x[i];
+    return o == 0;
+  };
+  auto shr1 = [](u32* x, u32 top) {
+    for (int i = 0; i < 7; i++) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+    x[7] = (x[7] >> 1) | (top << 31);
+  };
+  auto halve_mod = [&](u32* x) {   // x <- x / 2 mod p
+    u32 carry = 0;
+    if (x[0] & 1u) carry = acc_add<8>(x, p);
+    shr1(x, carry);
+  };
+  auto geq = [](const u32* x, const u32* y) {
+    for (int i = 7; i >= 0; i--) {
+      if (x[i] > y[i]) return true;
+      if (x[i] < y[i]) return false;
+    }
+    return true;
+  };
+  auto sub_mod = [&](u32* x, const u32* y) {   // x <- x - y mod p
+    if (acc_sub<8>(x, y)) acc_add<8>(x, p);
+  };
+  while (!is_one(u) && !is_one(v)) {
+    while (!(u[0] & 1u)) { shr1(u, 0); halve_mod(x1); }
+    while (!(v[0] & 1u)) { shr1(v, 0); halve_mod(x2); }
+    if (geq(u, v)) { acc_sub<8>(u, v); sub_mod(x1, x2); }
+    else { acc_sub<8>(v, u); sub_mod(x2, x1); }
+  }
+  const bool uo = is_one(u);
+#pragma unroll
+  for (int i = 0; i < 8; i++) out[i] = uo ? x1[i] : x2[i];
+}
+
+template <class C>
+REEF_HD Fe<C> fe_r3() {
+  Fe<C> z;
+#pragma unroll
+  for (int i = 0; i < 8; i++) z.v[i] = C::r3(i);
+  return z;
+}
+
+// inverse of a Montgomery-form element, result in Montgomery form:
+// inv(aR) = a^-1 R^-1 (as an integer);  mont_mul(., R^3) = a^-1 R^-1 R^3 R^-1 = a^-1 R.
+template <class C>
+REEF_HD Fe<C> fe_inv(const Fe<C>& a) {
+  Fe<C> t;
+  inv_canonical<C>(t.v, a.v);
+  return mont_mul<C>(t, fe_r3<C>());
+}
+
 
 }  // namespace reef

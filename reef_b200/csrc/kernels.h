@@ -49,6 +49,9 @@ int launch_mle_eval(reef_ctx* c, const void* d_table, int is_u32, uint64_t n, co
 int launch_mle_round_coeffs(reef_ctx* c, const void* d_t, const void* d_eq, uint32_t ell, uint32_t i, uint8_t* h_out3);
 int launch_mle_round_fold(reef_ctx* c, void* d_t, void* d_eq, uint32_t ell, uint32_t i, const uint8_t* h_r);
 
+int launch_lz(reef_ctx* c, const void* d_matrix, int is_u32, uint64_t rows, uint64_t cols, const uint8_t* h_L,
+              uint8_t* h_out);
+
 // ---- msm.cu
 struct MsmPlanPublic {
   uint32_t c, W, L, G, B;

@@ -667,4 +667,65 @@ int launch_mle_round_fold(reef_ctx* c, void* d_t, void* d_eq, uint32_t ell, uint
   return REEF_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Hyrax prove_eval's  LZ = L^T * M  (commitment.rs:371-393 -> nova hyrax_pc::prove_eval):
+// M is the rows x cols row-major matrix view of the document polynomial, L = eq(q_left).
+//   out[j] = sum_i L[i] * M[i][j]
+// grid (cols/128, row chunks); coalesced over j; lazy 17-limb accumulation per thread.
+// ---------------------------------------------------------------------------------------
+static constexpr int LZ_ROWS_PER_CTA = 64;
+
+template <bool U32IN>
+__global__ void __launch_bounds__(128) k_lz_partial(const void* __restrict__ M, const Fq* __restrict__ L, uint64_t rows,
+                                                    uint64_t cols, Fq* __restrict__ partial) {
+  const uint64_t j = (uint64_t)blockIdx.x * 128 + threadIdx.x;
+  if (j >= cols) return;
+  const uint64_t r0 = (uint64_t)blockIdx.y * LZ_ROWS_PER_CTA;
+  const uint64_t r1 = min(rows, r0 + LZ_ROWS_PER_CTA);
+  Wide17 acc;
+  wide_zero(acc);
+#pragma unroll 2
+  for (uint64_t i = r0; i < r1; i++) {
+    Fq l = ld256(L + i);                               // uniform across the CTA (L1 broadcast)
+    if constexpr (U32IN) wide_mac_small(acc, ((const uint32_t*)M)[i * cols + j], l.v);
+    else {
+      Fq x = ld256((const Fq*)M + i * cols + j);
+      wide_mac(acc, x.v, l.v);
+    }
+  }
+  st256(partial + (uint64_t)blockIdx.y * cols + j, wide_reduce_canonical<FqCfg>(acc));
+}
+
+__global__ void __launch_bounds__(128) k_lz_sum(const Fq* __restrict__ partial, uint32_t n_chunks, uint64_t cols,
+                                                Fq* __restrict__ out) {
+  const uint64_t j = (uint64_t)blockIdx.x * 128 + threadIdx.x;
+  if (j >= cols) return;
+  Fq acc = ld256(partial + j);
+  for (uint32_t k = 1; k < n_chunks; k++) acc = fe_add<FqCfg>(acc, ld256(partial + (uint64_t)k * cols + j));
+  st256(out + j, acc);
+}
+
+int launch_lz(reef_ctx* c, const void* d_matrix, int is_u32, uint64_t rows, uint64_t cols, const uint8_t* h_L,
+              uint8_t* h_out) {
+  const uint32_t n_chunks = ceil_div_u(rows, LZ_ROWS_PER_CTA);
+  void* base;
+  int rc = ctx_scratch(c, (size_t)(rows + (uint64_t)n_chunks * cols + cols + 8) * 32, &base);
+  if (rc) return rc;
+  Fq* d_L = (Fq*)base;
+  Fq* d_part = d_L + rows;
+  Fq* d_out = d_part + (uint64_t)n_chunks * cols;
+  cudaStream_t s = c->stream;
+  REEF_CUDA(cudaMemcpyAsync(d_L, h_L, (size_t)rows * 32, cudaMemcpyHostToDevice, s));
+  dim3 grid(ceil_div_u(cols, 128), n_chunks);
+  if (is_u32) k_lz_partial<true><<<grid, 128, 0, s>>>(d_matrix, d_L, rows, cols, d_part);
+  else k_lz_partial<false><<<grid, 128, 0, s>>>(d_matrix, d_L, rows, cols, d_part);
+  REEF_LAUNCHED();
+  k_lz_sum<<<ceil_div_u(cols, 128), 128, 0, s>>>(d_part, n_chunks, cols, d_out);
+  REEF_LAUNCHED();
+  REEF_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)cols * 32, cudaMemcpyDeviceToHost, s));
+  REEF_CUDA(cudaStreamSynchronize(s));
+  return REEF_OK;
+}
+
 }  // namespace reef

@@ -27,8 +27,8 @@
 
 namespace reef {
 
-static constexpr uint32_t K_FIRST = 32;   // entries per thread in the first accumulation pass
-static constexpr uint32_t K_NEXT = 8;     // partial points per thread in the following passes
+static constexpr uint32_t K_FIRST = 8;      // entries per thread in the first accumulation pass (latency: 8 mixed adds)
+static constexpr uint32_t K_NEXT = 128;     // partial points per WARP in the combine passes (4 per lane + shuffle tree)
 
 struct MsmPlan {
   uint32_t c;          // window bits
@@ -257,14 +257,16 @@ __global__ void __launch_bounds__(128) k_accum_first(const uint32_t* __restrict_
   st_xyzz(out + p, acc);
 }
 
-// following passes: K_NEXT partial points -> one
+// combine passes: one WARP per (bucket, chunk of K_NEXT partials): lanes stride over the chunk,
+// then a 5-level shuffle tree; typical histograms need exactly one such pass.
 template <class C>
 __global__ void __launch_bounds__(128) k_accum_next(const XYZZ<C>* __restrict__ in, const uint32_t* __restrict__ in_off,
                                                     const uint32_t* __restrict__ in_cnt,
                                                     const uint32_t* __restrict__ part_off, uint32_t nb, uint32_t n_parts,
                                                     XYZZ<C>* __restrict__ out) {
-  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_parts || p >= part_off[nb]) return;   // n_parts is a host-side upper bound
+  const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p >= n_parts || p >= part_off[nb]) return;   // warp-uniform; n_parts is a host-side upper bound
   uint32_t b;
   locate_part(part_off, nb, p, b);
   const uint32_t j = p - part_off[b];
@@ -272,8 +274,14 @@ __global__ void __launch_bounds__(128) k_accum_next(const XYZZ<C>* __restrict__ 
   const uint32_t last = min(in_off[b] + in_cnt[b], first + K_NEXT);
   XYZZ<C> acc = xyzz_inf<C>();
 #pragma unroll 1
-  for (uint32_t e = first; e < last; e++) xyzz_add<C>(acc, ld_xyzz(in + e));
-  st_xyzz(out + p, acc);
+  for (uint32_t e = first + lane; e < last; e += 32) xyzz_add<C>(acc, ld_xyzz(in + e));
+  const uint32_t width = last - first;             // warp-uniform
+#pragma unroll 1
+  for (int m = 1; m < 32 && (uint32_t)m < width; m <<= 1) {
+    XYZZ<C> o = shfl_xor_xyzz(acc, m);
+    xyzz_add<C>(acc, o);
+  }
+  if (lane == 0) st_xyzz(out + p, acc);
 }
 
 // buckets[b] = (cnt[b] ? parts[off[b]] : infinity)   (after the last pass every count is <= 1)
@@ -305,7 +313,7 @@ __device__ __forceinline__ XYZZ<C> block_sum_xyzz(XYZZ<C> v, XYZZ<C>* sm /* bloc
   if (warp == 0) {
     r = lane < nw ? sm[lane] : xyzz_inf<C>();
 #pragma unroll 1
-    for (int m = 16; m >= 1; m >>= 1) {
+    for (int m = 1; m < nw; m <<= 1) {
       XYZZ<C> o = shfl_xor_xyzz(r, m);
       xyzz_add<C>(r, o);
     }
@@ -342,8 +350,8 @@ __global__ void __launch_bounds__(1024) k_bitsum_final(const XYZZ<C>* __restrict
     if ((uint32_t)warp < cbits) {
       for (uint32_t k = lane; k < nblk; k += 32) xyzz_add<C>(v, ld_xyzz(partial + ((uint64_t)g * cbits + warp) * nblk + k));
 #pragma unroll 1
-      for (int m = 16; m >= 1; m >>= 1) {
-        XYZZ<C> o = shfl_xor_xyzz(v, m);
+      for (uint32_t m = 1; m < 32 && m < nblk; m <<= 1) {
+        XYZZ<C> o = shfl_xor_xyzz(v, (int)m);
         xyzz_add<C>(v, o);
       }
 #pragma unroll 1
@@ -354,8 +362,8 @@ __global__ void __launch_bounds__(1024) k_bitsum_final(const XYZZ<C>* __restrict
     if (warp == 0) {
       XYZZ<C> r = (uint32_t)lane < cbits ? st[lane] : xyzz_inf<C>();
 #pragma unroll 1
-      for (int m = 16; m >= 1; m >>= 1) {
-        XYZZ<C> o = shfl_xor_xyzz(r, m);
+      for (uint32_t m = 1; m < 32 && m < cbits; m <<= 1) {
+        XYZZ<C> o = shfl_xor_xyzz(r, (int)m);
         xyzz_add<C>(r, o);
       }
       if (g != (int)G - 1) {
@@ -468,12 +476,10 @@ __global__ void __launch_bounds__(512) k_rows_final(const XYZZ<C>* __restrict__ 
   XYZZ<C> v = xyzz_inf<C>();
   if ((uint32_t)warp < cbits) {
     for (uint32_t k = lane; k < nblk; k += 32) xyzz_add<C>(v, ld_xyzz(partial + ((uint64_t)g * cbits + warp) * nblk + k));
-    if (nblk > 1) {
 #pragma unroll 1
-      for (int m = 16; m >= 1; m >>= 1) {
-        XYZZ<C> o = shfl_xor_xyzz(v, m);
-        xyzz_add<C>(v, o);
-      }
+    for (uint32_t m = 1; m < 32 && m < nblk; m <<= 1) {
+      XYZZ<C> o = shfl_xor_xyzz(v, (int)m);
+      xyzz_add<C>(v, o);
     }
 #pragma unroll 1
     for (int k = 0; k < warp; k++) v = xyzz_dbl<C>(v);
@@ -483,8 +489,8 @@ __global__ void __launch_bounds__(512) k_rows_final(const XYZZ<C>* __restrict__ 
   if (warp == 0) {
     XYZZ<C> r = (uint32_t)lane < cbits ? st[lane] : xyzz_inf<C>();
 #pragma unroll 1
-    for (int m = 8; m >= 1; m >>= 1) {
-      XYZZ<C> o = shfl_xor_xyzz(r, m);
+    for (uint32_t m = 1; m < 16 && m < cbits; m <<= 1) {
+      XYZZ<C> o = shfl_xor_xyzz(r, (int)m);
       xyzz_add<C>(r, o);
     }
     if (lane == 0) {
@@ -642,7 +648,7 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
     k_scan<<<1, 1024, 0, s>>>(pcnt[cur], nb, K_NEXT, pcnt[nxt], poff[nxt], nullptr, tm + 2);
     REEF_LAUNCHED();
     const uint32_t n_next = (n_parts + K_NEXT - 1) / K_NEXT + nb;   // upper bound; exact count read on device
-    k_accum_next<C><<<cdiv(n_next, 128), 128, 0, s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, parts[nxt]);
+    k_accum_next<C><<<cdiv((uint64_t)n_next * 32, 128), 128, 0, s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, parts[nxt]);
     REEF_LAUNCHED();
     max_cnt = (max_cnt + K_NEXT - 1) / K_NEXT;
     n_parts = n_next;
@@ -753,7 +759,7 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
     k_scan<<<1, 1024, 0, s>>>(pcnt[cur], nb, K_NEXT, pcnt[nxt], poff[nxt], nullptr, tm + 2);
     REEF_LAUNCHED();
     const uint32_t n_next = (n_parts + K_NEXT - 1) / K_NEXT + nb;
-    k_accum_next<C><<<cdiv(n_next, 128), 128, 0, s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, parts[nxt]);
+    k_accum_next<C><<<cdiv((uint64_t)n_next * 32, 128), 128, 0, s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, parts[nxt]);
     REEF_LAUNCHED();
     max_cnt = (max_cnt + K_NEXT - 1) / K_NEXT;
     n_parts = n_next;

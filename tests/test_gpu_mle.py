@@ -197,3 +197,23 @@ def test_nlookup_full_size_properties(ctx):
     eq_r = (eq_r + term) % FQ
     assert got.sc_last_claim == got.next_running_claim * eq_r % FQ
     t.free()
+
+
+@pytest.mark.parametrize("ell,u32", [(6, True), (9, False), (13, True), (17, True)])
+def test_hyrax_lz_matvec(ctx, ell, u32):
+    """LZ = L^T M with L = eq(q_left) (Hyrax prove_eval); also  <LZ, eq(q_right)> = doc~(q)."""
+    rnd = random.Random(ell)
+    left = ell // 2
+    rows, cols = 1 << left, 1 << (ell - left)
+    n = rows * cols
+    tab = [rnd.randrange(131 if u32 else FQ) for _ in range(n)]
+    t = ctx.table_u32(tab) if u32 else ctx.table(tab)
+    q = [rnd.randrange(FQ) for _ in range(ell)]
+    L = ctx.gen_eq_table([1], [], list(reversed(q[:left])))          # index bit (left-1-k) <-> q[k]
+    R = ctx.gen_eq_table([1], [], list(reversed(q[left:])))
+    lz = ctx.hyrax_lz(t, rows, cols, L)
+    if ell <= 13:
+        for j in [0, 1, cols // 2, cols - 1]:
+            assert lz[j] == sum(L[i] * tab[i * cols + j] for i in range(rows)) % FQ
+    assert sum(a * b for a, b in zip(lz, R)) % FQ == mle_eval_fast(tab, q)
+    assert ctx.verifier_mle_eval(t, q) == mle_eval_fast(tab, q)

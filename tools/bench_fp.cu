@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "../reef_b200/csrc/fp.cuh"
+#include "../reef_b200/csrc/ec.cuh"
 using namespace reef;
 typedef Fe<FqCfg> Fq;
 typedef Fe<FpCfg> Fp;
@@ -20,6 +21,8 @@ __global__ void k_latency(Fq* io, int iters, long long* cycles) {
     if (MODE == 2) x = fe_add<FqCfg>(x, y);
     if (MODE == 3) { u32 T[16]; mul_wide(T, x.v, y.v); for (int k = 0; k < 8; k++) x.v[k] = T[k] ^ T[8 + k]; }
     if (MODE == 5) x = mont_mul_ll<FqCfg>(x, y);
+    if (MODE == 6) { x = fe_inv<FqCfg>(x); x = fe_add<FqCfg>(x, y); }
+    if (MODE == 7) x = fe_pow_pm2<FqCfg>(x);
     if (MODE == 4) { u32 T[16]; for (int k = 0; k < 8; k++) { T[k] = x.v[k]; T[8 + k] = y.v[k]; } mont_reduce<FqCfg>(x.v, T); }
   }
   long long t1 = clock64();
@@ -54,9 +57,9 @@ int main() {
   Fq* io; long long* cyc;
   cudaMalloc(&io, 1 << 26); cudaMalloc(&cyc, 8);
   cudaMemset(io, 0x11, 1 << 26);
-  const char* names[6] = {"mont_mul", "mont_sqr", "fe_add", "mul_wide", "mont_reduce", "mont_mul_ll"};
-  for (int mode = 0; mode < 6; mode++) {
-    const int iters = 2000;
+  const char* names[8] = {"mont_mul", "mont_sqr", "fe_add", "mul_wide", "mont_reduce", "mont_mul_ll", "fe_inv(bingcd)+add", "fe_pow_pm2"};
+  for (int mode = 0; mode < 8; mode++) {
+    const int iters = mode >= 6 ? 20 : 2000;
     for (int rep = 0; rep < 2; rep++) {
       if (mode == 0) k_latency<0><<<1, 32>>>(io, iters, cyc);
       if (mode == 1) k_latency<1><<<1, 32>>>(io, iters, cyc);
@@ -64,6 +67,8 @@ int main() {
       if (mode == 3) k_latency<3><<<1, 32>>>(io, iters, cyc);
       if (mode == 4) k_latency<4><<<1, 32>>>(io, iters, cyc);
       if (mode == 5) k_latency<5><<<1, 32>>>(io, iters, cyc);
+      if (mode == 6) k_latency<6><<<1, 32>>>(io, iters, cyc);
+      if (mode == 7) k_latency<7><<<1, 32>>>(io, iters, cyc);
       cudaDeviceSynchronize();
     }
     long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);

@@ -53,3 +53,13 @@ best, avg = timeit(lambda: ctx.calc_d(rows[0], rows[1]))
 print(f"calc_d              best {best:8.3f} ms  avg {avg:8.3f} ms")
 best, avg = timeit(lambda: ctx.poseidon_sponge([("A", 4), ("S", 1)], [1, 2, 3, 4]))
 print(f"sponge A4S1 (warp5) best {best:8.3f} ms  avg {avg:8.3f} ms")
+# ---- MSM
+from oracle.curves import PALLAS
+for lg in (12, 15):
+    n = 1 << lg
+    pts = PALLAS.multiples(n)
+    b = ctx.bases("pallas", pts)
+    raw = np.random.default_rng(lg).integers(0, 1 << 63, size=(n, 4), dtype=np.uint64); raw[:, 3] &= (1 << 61) - 1
+    dev = torch.from_numpy(raw.view(np.int64)).cuda()
+    best, avg = timeit(lambda: b.msm_dev(dev.data_ptr(), n), n=5, warm=2)
+    print(f"msm pallas n=2^{lg} c={b.window_bits} W={b.windows}  best {best:8.3f} ms  avg {avg:8.3f} ms  ({n/best/1e3:8.2f} Mop/s)")

@@ -31,7 +31,7 @@ namespace reef {
 
 static constexpr int H_BITS = 10;
 static constexpr int CHUNK = 1 << H_BITS;  // b-values per CTA in a sweep
-static constexpr int SWEEP_THREADS = 128;
+static constexpr int SWEEP_THREADS = 256;
 static constexpr int MAX_ELL = 48;
 
 // Device-resident state of one nlookup session.
@@ -160,23 +160,26 @@ __global__ void k_eq_tables(const NlState* __restrict__ st, uint32_t ell, uint32
 //   L_in  length of Tin; L = FOLD ? L_in/2 : L_in is the accumulation length, half = L/2 >= 2^h.
 //   partials[blk][3] = (const, g(1), xsq) contributions of this CTA (canonical).
 // ---------------------------------------------------------------------------------------
-template <bool U32IN, bool FOLD>
+template <bool U32IN, bool FOLD, int EPT>
 __global__ void __launch_bounds__(SWEEP_THREADS)
 k_sweep(const void* Tin, uint64_t L_in, Fq* Tout, const NlState* __restrict__ st,
         const Fq* __restrict__ A, const Fq* __restrict__ B, Fq* __restrict__ partials) {
+  // EPT index pairs per thread; a CTA covers SWEEP_THREADS * EPT consecutive b-values, which
+  // never straddles a 2^h row (EPT in {1,2,4}).  Small live lengths use EPT = 1 so that the
+  // sweep is spread over all SMs instead of running 8-deep dependent chains on a few CTAs.
   __shared__ Fq red[2 * SWEEP_THREADS / 32];
   const uint64_t L = FOLD ? (L_in >> 1) : L_in;
   const uint64_t half = L >> 1;
-  const uint64_t b0 = (uint64_t)blockIdx.x * CHUNK;
+  const uint64_t b0 = (uint64_t)blockIdx.x * (SWEEP_THREADS * EPT);
   Fq r;
   if constexpr (FOLD) r = st->r_mont;
   Wide17 U0, U1;
   wide_zero(U0);
   wide_zero(U1);
-#pragma unroll 2
-  for (int k = 0; k < CHUNK / SWEEP_THREADS; k++) {
-    const uint32_t lo = k * SWEEP_THREADS + threadIdx.x;
-    const uint64_t b = b0 + lo;
+#pragma unroll
+  for (int k = 0; k < EPT; k++) {
+    const uint64_t b = b0 + (uint64_t)k * SWEEP_THREADS + threadIdx.x;
+    const uint32_t lo = (uint32_t)(b & (CHUNK - 1));
     Fq t0, t1;
     if constexpr (FOLD) {
       Fq x00 = load_t<U32IN>(Tin, b), x01 = load_t<U32IN>(Tin, b + L);
@@ -210,6 +213,31 @@ k_sweep(const void* Tin, uint64_t L_in, Fq* Tout, const NlState* __restrict__ st
     st256(out + 1, mont_mul<FqCfg>(a1, u[1]));
     st256(out + 2, mont_mul<FqCfg>(fe_sub<FqCfg>(a1, a0), fe_sub<FqCfg>(u[1], u[0])));
   }
+}
+
+template <bool U32IN, bool FOLD>
+static int launch_sweep(reef_ctx* c, const void* Tin, uint64_t L_in, Fq* Tout, const NlState* st, const Fq* A,
+                        const Fq* B, Fq* partials, uint32_t* nblk_out) {
+  const uint64_t L = FOLD ? (L_in >> 1) : L_in;
+  const uint64_t half = L >> 1;
+  cudaStream_t s = c->stream;
+  // enough CTAs for two waves of 8 CTAs/SM before deepening the per-thread work
+  const uint64_t target = (uint64_t)c->sm_count * 16;
+  if (half / (SWEEP_THREADS * 4) >= target) {
+    const uint32_t nblk = (uint32_t)(half / (SWEEP_THREADS * 4));
+    k_sweep<U32IN, FOLD, 4><<<nblk, SWEEP_THREADS, 0, s>>>(Tin, L_in, Tout, st, A, B, partials);
+    *nblk_out = nblk;
+  } else if (half / (SWEEP_THREADS * 2) >= target) {
+    const uint32_t nblk = (uint32_t)(half / (SWEEP_THREADS * 2));
+    k_sweep<U32IN, FOLD, 2><<<nblk, SWEEP_THREADS, 0, s>>>(Tin, L_in, Tout, st, A, B, partials);
+    *nblk_out = nblk;
+  } else {
+    const uint32_t nblk = (uint32_t)(half / SWEEP_THREADS);
+    k_sweep<U32IN, FOLD, 1><<<nblk, SWEEP_THREADS, 0, s>>>(Tin, L_in, Tout, st, A, B, partials);
+    *nblk_out = nblk;
+  }
+  REEF_LAUNCHED();
+  return REEF_OK;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -391,7 +419,7 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
   const uint64_t a_len = (uint64_t)1 << (ell - hb);
   const uint64_t b_len = (uint64_t)1 << hb;
   const uint32_t n_sweeps = ell > (uint32_t)H_BITS ? ell - H_BITS : 0;
-  const uint64_t max_blk = n_sweeps ? (N / 2) / CHUNK : 1;
+  const uint64_t max_blk = n_sweeps ? (N / 2) / SWEEP_THREADS : 1;
 
   // scratch layout
   size_t off = 0;
@@ -444,12 +472,12 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
   uint64_t L = N;                // accumulation length of the current round
   uint64_t a_cur = a_len;
   for (uint32_t i = 0; i < n_sweeps; i++) {
-    const uint32_t nblk = (uint32_t)((L / 2) / CHUNK);
+    uint32_t nblk = 0;
     if (i == 0) {
       {
         ProfScope ps(c, PROF_SWEEP_FIRST, N);
-        k_sweep<U32IN, false><<<nblk, SWEEP_THREADS, 0, s>>>(a.d_table, N, nullptr, st, d_A, d_B, d_part);
-        REEF_LAUNCHED();
+        rc = launch_sweep<U32IN, false>(c, a.d_table, N, nullptr, st, d_A, d_B, d_part, &nblk);
+        if (rc) return rc;
       }
       ProfScope ps(c, PROF_ROUND, L);
       k_round<U32IN><<<1, ROUND_THREADS, 0, s>>>(st, d_part, nblk, a.d_table, L, d_A, a_cur, d_pos, d_w, m, i, c->d_pos);
@@ -457,9 +485,9 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
     } else {
       {
         ProfScope ps(c, PROF_SWEEP_FOLD, 2 * L);
-        if (i == 1) k_sweep<U32IN, true><<<nblk, SWEEP_THREADS, 0, s>>>(a.d_table, 2 * L, d_fold, st, d_A, d_B, d_part);
-        else k_sweep<false, true><<<nblk, SWEEP_THREADS, 0, s>>>(d_fold, 2 * L, d_fold, st, d_A, d_B, d_part);
-        REEF_LAUNCHED();
+        if (i == 1) rc = launch_sweep<U32IN, true>(c, a.d_table, 2 * L, d_fold, st, d_A, d_B, d_part, &nblk);
+        else rc = launch_sweep<false, true>(c, d_fold, 2 * L, d_fold, st, d_A, d_B, d_part, &nblk);
+        if (rc) return rc;
       }
       ProfScope ps(c, PROF_ROUND, L);
       k_round<false><<<1, ROUND_THREADS, 0, s>>>(st, d_part, nblk, d_fold, L, d_A, a_cur, d_pos, d_w, m, i, c->d_pos);

@@ -160,6 +160,27 @@ int reef_nlookup_prove(reef_ctx* ctx, int tag, const reef_table* table, const ui
                        uint32_t m, const uint8_t* prev_q, const uint8_t* prev_v, const uint8_t* doc_hash,
                        reef_nlookup_out* out);
 
+/* Multi-GPU sharded sum-check.  The table is sharded by LOW index bits: rank g of
+ * `world` (a power of two) uploads T_g[j] = T[j*world + g] as its local table.  Every rank calls
+ * reef_nl_shard_begin with the SAME q, v, prev_q, prev_v (prev_v is mandatory when world > 1),
+ * then for each of the ell - log2(world) local rounds:
+ *     reef_nl_shard_round_local  -> this rank's (const, g(1), xsq), 96 B, into a DEVICE buffer
+ *     [all-gather of the 96-byte triples across ranks, e.g. ncclAllGather]
+ *     reef_nl_shard_round_finish <- the world x 96 B gathered triples (DEVICE, rank-major)
+ * then reef_nl_shard_export -> this rank's folded (T, EQ) pair (64 B, DEVICE), one more
+ * all-gather, and reef_nl_shard_finish runs the last log2(world) rounds redundantly on every
+ * rank and writes the same outputs as reef_nlookup_prove.  None of the per-round calls
+ * synchronises the stream (order your collective after reef_stream(ctx)). */
+typedef struct reef_nl_session reef_nl_session;
+int reef_nl_shard_begin(reef_ctx* ctx, int tag, const reef_table* local_table, uint32_t rank, uint32_t world,
+                        const uint64_t* q, const uint8_t* v, uint32_t m, const uint8_t* prev_q, const uint8_t* prev_v,
+                        const uint8_t* doc_hash, reef_nlookup_out* out, reef_nl_session** session);
+int reef_nl_shard_round_local(reef_nl_session* s, void* out_triple_dev);
+int reef_nl_shard_round_finish(reef_nl_session* s, const void* all_triples_dev);
+int reef_nl_shard_export(reef_nl_session* s, void* out_pair_dev);
+int reef_nl_shard_finish(reef_nl_session* s, const void* all_pairs_dev, reef_nlookup_out* out);
+void reef_nl_shard_free(reef_nl_session* s);
+
 /* Reference-shaped building blocks (materialised tables), for drop-in use and for the parity
  * tests that mirror the reference's own unit tests. */
 

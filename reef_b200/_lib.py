@@ -73,6 +73,12 @@ _sig = {
     "reef_table_len": (C.c_uint64, [_vp]),
     "reef_table_free": (None, [_vp]),
     "reef_nlookup_prove": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp, C.POINTER(NlookupOut)]),
+    "reef_nl_shard_begin": (C.c_int, [_vp, C.c_int, _vp, C.c_uint32, C.c_uint32, _vp, _vp, C.c_uint32, _vp, _vp, _vp, C.POINTER(NlookupOut), C.POINTER(_vp)]),
+    "reef_nl_shard_round_local": (C.c_int, [_vp, _vp]),
+    "reef_nl_shard_round_finish": (C.c_int, [_vp, _vp]),
+    "reef_nl_shard_export": (C.c_int, [_vp, _vp]),
+    "reef_nl_shard_finish": (C.c_int, [_vp, _vp, C.POINTER(NlookupOut)]),
+    "reef_nl_shard_free": (None, [_vp]),
     "reef_gen_eq_table": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp, C.c_uint32, _vp]),
     "reef_linear_mle_product": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "reef_verifier_mle_eval": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp]),

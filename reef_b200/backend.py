@@ -419,3 +419,84 @@ class Bases:
             self.free()
         except Exception:
             pass
+
+
+class ShardedNlookup:
+    """One rank of the multi-GPU sum-check (protocol in oracle/sharded.py).
+
+    `local_table` holds T[j*world + rank].  `gather(dev_ptr_in, nbytes, dev_ptr_out)` must fill
+    `dev_ptr_out` with the world x nbytes rank-major all-gather of `dev_ptr_in`, ordered after
+    the context's stream (NCCL `all_gather_into_tensor` under `torch.cuda.stream(ExternalStream)`).
+    """
+
+    def __init__(self, ctx: Context, local_table: "Table", rank: int, world: int, q, v, prev_q, prev_v, tag="nl",
+                 doc_hash=None):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        m = len(q)
+        self._bufs = dict(prev=C.create_string_buffer(32), cq=C.create_string_buffer(((m * 64) // 254 + 2) * 32),
+                          claim=C.create_string_buffer(32), rounds=C.create_string_buffer(64 * 4 * 32),
+                          last=C.create_string_buffer(32), nxt=C.create_string_buffer(32))
+        o = NlookupOut()
+        o.prev_running_claim = C.addressof(self._bufs["prev"])
+        o.combined_q = C.addressof(self._bufs["cq"])
+        o.combined_q_cap = (m * 64) // 254 + 2
+        o.claim_r = C.addressof(self._bufs["claim"])
+        o.rounds = C.addressof(self._bufs["rounds"])
+        o.rounds_cap = 64
+        o.sc_last_claim = C.addressof(self._bufs["last"])
+        o.next_running_claim = C.addressof(self._bufs["nxt"])
+        self._o = o
+        qa = _u64(q)
+        self._keep = (qa, _buf(_pack(v)), _buf(_pack(prev_q)) if prev_q is not None else None,
+                      _buf(_pack([prev_v])) if prev_v is not None else None,
+                      _buf(_pack([doc_hash])) if doc_hash is not None else None)
+        h = C.c_void_p()
+        check(lib.reef_nl_shard_begin(ctx._h, _TAGS[tag] if isinstance(tag, str) else tag, local_table._h, rank, world,
+                                      qa.ctypes.data if m else None, self._keep[1] if m else None, m, self._keep[2],
+                                      self._keep[3], self._keep[4], C.byref(o), C.byref(h)))
+        self._h = h
+        self.ell = o.ell
+        self.ell_local = o.ell - (world.bit_length() - 1)
+
+    def round_local(self, out_dev_ptr: int):
+        check(lib.reef_nl_shard_round_local(self._h, C.c_void_p(out_dev_ptr)))
+
+    def round_finish(self, all_triples_dev_ptr: int):
+        check(lib.reef_nl_shard_round_finish(self._h, C.c_void_p(all_triples_dev_ptr)))
+
+    def export(self, out_dev_ptr: int):
+        check(lib.reef_nl_shard_export(self._h, C.c_void_p(out_dev_ptr)))
+
+    def finish(self, all_pairs_dev_ptr: int) -> NlookupResult:
+        check(lib.reef_nl_shard_finish(self._h, C.c_void_p(all_pairs_dev_ptr), C.byref(self._o)))
+        b, ell = self._bufs, self.ell
+        rounds = _unpack(b["rounds"].raw[:ell * 4 * 32])
+        rounds = [tuple(rounds[4 * i:4 * i + 4]) for i in range(ell)]
+        return NlookupResult(prev_running_claim=int.from_bytes(b["prev"].raw, "little"),
+                             combined_q=_unpack(b["cq"].raw[:self._o.num_cqs * 32]),
+                             claim_r=int.from_bytes(b["claim"].raw, "little"), rounds=rounds,
+                             sc_last_claim=int.from_bytes(b["last"].raw, "little"),
+                             next_running_claim=int.from_bytes(b["nxt"].raw, "little"),
+                             next_running_q=[r[0] for r in rounds])
+
+    def run(self, gather, scratch_dev_ptr: int) -> NlookupResult:
+        """scratch: device buffer of (world + 1) * 96 bytes owned by the caller."""
+        mine, allp = scratch_dev_ptr, scratch_dev_ptr + 96
+        for _ in range(self.ell_local):
+            self.round_local(mine)
+            gather(mine, 96, allp)
+            self.round_finish(allp)
+        self.export(mine)
+        gather(mine, 64, allp)
+        return self.finish(allp)
+
+    def free(self):
+        if self._h:
+            lib.reef_nl_shard_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -681,95 +681,113 @@ void reef_table_free(reef_table* t) {
   delete t;
 }
 
-int reef_nlookup_prove(reef_ctx* c, int tag, const reef_table* table, const uint64_t* q, const uint8_t* v, uint32_t m,
-                       const uint8_t* prev_q, const uint8_t* prev_v, const uint8_t* doc_hash, reef_nlookup_out* out) {
-  REEF_REQUIRE(c && table && out, REEF_EINVAL, "reef_nlookup_prove: NULL argument");
+// Host half of wit_nlookup_gadget shared by the single-GPU and the sharded entry points:
+// defaults, combined_q, IOPattern, first absorb (r1cs.rs:2187-2306).
+struct NlPrep {
+  uint32_t ell;
+  std::vector<uint8_t> prevq, cqs, query;
+  std::vector<uint32_t> ops;
+  uint8_t prevv[32];
+  uint32_t num_cqs, first;
+};
+
+static int nl_prepare(int tag, uint64_t n_orig, uint64_t n_pad, const uint8_t* first_elem, const uint64_t* q, const uint8_t* v,
+                      uint32_t m, const uint8_t* prev_q, const uint8_t* prev_v, const uint8_t* doc_hash, reef_nlookup_out* out,
+                      NlPrep& P) {
   REEF_REQUIRE(tag == REEF_TAG_NL || tag == REEF_TAG_NLDOC || tag == REEF_TAG_NLHYBRID, REEF_EASSERT, "weird tag");
-  REEF_REQUIRE(table->ctx == c, REEF_EINVAL, "reef_nlookup_prove: table belongs to another context");
   REEF_REQUIRE(m == 0 || (q && v), REEF_EINVAL, "reef_nlookup_prove: NULL q/v");
   REEF_REQUIRE(tag == REEF_TAG_NL || doc_hash, REEF_EINVAL, "reef_nlookup_prove: doc_hash required for nldoc/nlhybrid");
   REEF_REQUIRE(out->claim_r && out->rounds && out->sc_last_claim && out->next_running_claim, REEF_EINVAL,
                "reef_nlookup_prove: NULL output buffer");
   // sc_l = logmn(table.len())  (r1cs.rs:2187)
-  const uint32_t ell = reef_logmn(table->n_orig);
+  const uint32_t ell = reef_logmn(n_orig);
   const uint64_t n_full = ell < 63 ? ((uint64_t)1 << ell) : 0;
   if (tag == REEF_TAG_NLDOC) {
     // zero-padded to 2^logmn(len) (r1cs.rs:2322-2329)
-    if (n_full < table->n_orig) return fail(REEF_EASSERT, "attempt to subtract with overflow (f32 logmn)");
+    if (n_full < n_orig) return fail(REEF_EASSERT, "attempt to subtract with overflow (f32 logmn)");
   } else {
     // linear_mle_product asserts table_t.len() == 2^ell (r1cs_helper.rs:450)
-    if (n_full != table->n_orig) return fail(REEF_EASSERT, "assertion failed: table_t.len() == base.pow(ell)");
+    if (n_full != n_orig) return fail(REEF_EASSERT, "assertion failed: table_t.len() == base.pow(ell)");
   }
-  REEF_REQUIRE(n_full == table->n_pad, REEF_EINVAL, "reef_nlookup_prove: padded table length does not match 2^logmn(len)");
+  REEF_REQUIRE(n_full == n_pad, REEF_EINVAL, "reef_nlookup_prove: padded table length does not match 2^logmn(len)");
   REEF_REQUIRE(out->rounds_cap >= ell, REEF_EINVAL, "reef_nlookup_prove: rounds buffer too small");
+  for (uint32_t k = 0; k < m; k++)
+    REEF_REQUIRE(q[k] < n_pad, REEF_EASSERT, "nlookup: lookup index out of range (index out of bounds)");
   out->ell = ell;
-
+  P.ell = ell;
   int rc;
   if (m) {
     rc = check_canonical(v, m, "reef_nlookup_prove: v");
     if (rc) return rc;
   }
-  std::vector<uint8_t> prevq((size_t)ell * 32, 0);
+  P.prevq.assign((size_t)ell * 32, 0);
   if (prev_q) {
     rc = check_canonical(prev_q, ell, "reef_nlookup_prove: prev_q");
     if (rc) return rc;
-    memcpy(prevq.data(), prev_q, (size_t)ell * 32);
+    memcpy(P.prevq.data(), prev_q, (size_t)ell * 32);
   }
-  uint8_t prevv[32];
   if (prev_v) {
     rc = check_canonical(prev_v, 1, "reef_nlookup_prove: prev_v");
     if (rc) return rc;
-    memcpy(prevv, prev_v, 32);
+    memcpy(P.prevv, prev_v, 32);
   } else {
-    memcpy(prevv, table->first, 32);
+    REEF_REQUIRE(first_elem != nullptr, REEF_EINVAL, "reef_nlookup_prove: prev_v required (table[0] is not on this rank)");
+    memcpy(P.prevv, first_elem, 32);
   }
-  if (out->prev_running_claim) memcpy(out->prev_running_claim, prevv, 32);
-
+  if (out->prev_running_claim) memcpy(out->prev_running_claim, P.prevv, 32);
   // combined_q (r1cs.rs:2208-2249)
-  uint32_t num_cqs = 0;
-  std::vector<uint8_t> cqs((size_t)((uint64_t)m * ell / 254 + 2) * 32);
-  rc = reef_combined_q(q, m, ell, cqs.data(), (uint32_t)(cqs.size() / 32), &num_cqs);
+  P.num_cqs = 0;
+  P.cqs.assign((size_t)((uint64_t)m * ell / 254 + 2) * 32, 0);
+  rc = reef_combined_q(q, m, ell, P.cqs.data(), (uint32_t)(P.cqs.size() / 32), &P.num_cqs);
   if (rc) return rc;
-  out->num_cqs = num_cqs;
+  out->num_cqs = P.num_cqs;
   if (out->combined_q) {
-    REEF_REQUIRE(out->combined_q_cap >= num_cqs, REEF_EINVAL, "reef_nlookup_prove: combined_q buffer too small");
-    memcpy(out->combined_q, cqs.data(), (size_t)num_cqs * 32);
+    REEF_REQUIRE(out->combined_q_cap >= P.num_cqs, REEF_EINVAL, "reef_nlookup_prove: combined_q buffer too small");
+    memcpy(out->combined_q, P.cqs.data(), (size_t)P.num_cqs * 32);
   }
-
   // IOPattern (r1cs.rs:2263-2282) and first absorb (r1cs.rs:2285-2306)
   const bool with_hash = tag != REEF_TAG_NL;
-  const uint32_t first = m + ell + 1 + num_cqs + (with_hash ? 1 : 0);
-  std::vector<uint32_t> ops;
-  ops.push_back((1u << 31) | first);
-  ops.push_back(1);
+  P.first = m + ell + 1 + P.num_cqs + (with_hash ? 1 : 0);
+  P.ops.clear();
+  P.ops.push_back((1u << 31) | P.first);
+  P.ops.push_back(1);
   for (uint32_t i = 0; i < ell; i++) {
-    ops.push_back((1u << 31) | 3u);
-    ops.push_back(1);
+    P.ops.push_back((1u << 31) | 3u);
+    P.ops.push_back(1);
   }
-  std::vector<uint8_t> query;
-  query.reserve((size_t)first * 32);
+  P.query.clear();
+  P.query.reserve((size_t)P.first * 32);
   if (with_hash) {
     rc = check_canonical(doc_hash, 1, "reef_nlookup_prove: doc_hash");
     if (rc) return rc;
-    query.insert(query.end(), doc_hash, doc_hash + 32);
+    P.query.insert(P.query.end(), doc_hash, doc_hash + 32);
   }
-  query.insert(query.end(), cqs.begin(), cqs.begin() + (size_t)num_cqs * 32);
-  if (m) query.insert(query.end(), v, v + (size_t)m * 32);
-  query.insert(query.end(), prevq.begin(), prevq.end());
-  query.insert(query.end(), prevv, prevv + 32);
+  P.query.insert(P.query.end(), P.cqs.begin(), P.cqs.begin() + (size_t)P.num_cqs * 32);
+  if (m) P.query.insert(P.query.end(), v, v + (size_t)m * 32);
+  P.query.insert(P.query.end(), P.prevq.begin(), P.prevq.end());
+  P.query.insert(P.query.end(), P.prevv, P.prevv + 32);
+  return REEF_OK;
+}
 
+int reef_nlookup_prove(reef_ctx* c, int tag, const reef_table* table, const uint64_t* q, const uint8_t* v, uint32_t m,
+                       const uint8_t* prev_q, const uint8_t* prev_v, const uint8_t* doc_hash, reef_nlookup_out* out) {
+  REEF_REQUIRE(c && table && out, REEF_EINVAL, "reef_nlookup_prove: NULL argument");
+  REEF_REQUIRE(table->ctx == c, REEF_EINVAL, "reef_nlookup_prove: table belongs to another context");
+  NlPrep P;
+  int rc = nl_prepare(tag, table->n_orig, table->n_pad, table->first, q, v, m, prev_q, prev_v, doc_hash, out, P);
+  if (rc) return rc;
   NlookupArgs a;
   a.tag = tag;
   a.d_table = table->d;
   a.table_is_u32 = table->is_u32;
   a.n = table->n_pad;
-  a.ell = ell;
+  a.ell = P.ell;
   a.m = m;
   a.h_q = q;
-  a.h_query = query.data();
-  a.n_query = first;
-  a.h_prev_q = prevq.data();
-  io_pattern_tag_le32(ops.data(), (uint32_t)ops.size(), 0, a.tag_le);
+  a.h_query = P.query.data();
+  a.n_query = P.first;
+  a.h_prev_q = P.prevq.data();
+  io_pattern_tag_le32(P.ops.data(), (uint32_t)P.ops.size(), 0, a.tag_le);
   a.out_claim_r = out->claim_r;
   a.out_rounds = out->rounds;
   a.out_last_claim = out->sc_last_claim;
@@ -778,6 +796,61 @@ int reef_nlookup_prove(reef_ctx* c, int tag, const reef_table* table, const uint
   REEF_CUDA(cudaSetDevice(c->device));
   return nlookup_run(c, a);
 }
+
+// ---- multi-GPU sharded sum-check: see include/reef_b200.h
+int reef_nl_shard_begin(reef_ctx* c, int tag, const reef_table* local_table, uint32_t rank, uint32_t world, const uint64_t* q,
+                        const uint8_t* v, uint32_t m, const uint8_t* prev_q, const uint8_t* prev_v, const uint8_t* doc_hash,
+                        reef_nlookup_out* out, reef_nl_session** session) {
+  REEF_REQUIRE(c && local_table && out && session, REEF_EINVAL, "reef_nl_shard_begin: NULL argument");
+  REEF_REQUIRE(local_table->ctx == c, REEF_EINVAL, "reef_nl_shard_begin: table belongs to another context");
+  REEF_REQUIRE(world >= 1 && (world & (world - 1)) == 0 && rank < world, REEF_EINVAL, "reef_nl_shard_begin: world must be a power of two");
+  REEF_REQUIRE(local_table->n_orig == local_table->n_pad, REEF_EINVAL, "reef_nl_shard_begin: local shard must be a power of two long");
+  const uint64_t n_global = local_table->n_pad * world;
+  NlPrep P;
+  int rc = nl_prepare(tag, n_global, n_global, (world == 1 || rank == 0) ? local_table->first : nullptr, q, v, m, prev_q, prev_v,
+                      doc_hash, out, P);
+  if (rc) return rc;
+  NlookupArgs a;
+  a.tag = tag;
+  a.d_table = local_table->d;
+  a.table_is_u32 = local_table->is_u32;
+  a.n = local_table->n_pad;
+  a.ell = P.ell;
+  a.m = m;
+  a.h_q = q;
+  a.h_query = P.query.data();
+  a.n_query = P.first;
+  a.h_prev_q = P.prevq.data();
+  io_pattern_tag_le32(P.ops.data(), (uint32_t)P.ops.size(), 0, a.tag_le);
+  a.out_claim_r = a.out_rounds = a.out_last_claim = a.out_next_v = nullptr;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  return nl_shard_begin(c, a, rank, world, session);
+}
+
+int reef_nl_shard_round_local(reef_nl_session* s, void* out_triple_dev) {
+  REEF_REQUIRE(s && out_triple_dev, REEF_EINVAL, "reef_nl_shard_round_local: NULL argument");
+  return nl_shard_round_local(s, out_triple_dev);
+}
+
+int reef_nl_shard_round_finish(reef_nl_session* s, const void* all_triples_dev) {
+  REEF_REQUIRE(s && all_triples_dev, REEF_EINVAL, "reef_nl_shard_round_finish: NULL argument");
+  return nl_shard_round_finish(s, all_triples_dev);
+}
+
+int reef_nl_shard_export(reef_nl_session* s, void* out_pair_dev) {
+  REEF_REQUIRE(s && out_pair_dev, REEF_EINVAL, "reef_nl_shard_export: NULL argument");
+  return nl_shard_export(s, out_pair_dev);
+}
+
+int reef_nl_shard_finish(reef_nl_session* s, const void* all_pairs_dev, reef_nlookup_out* out) {
+  REEF_REQUIRE(s && all_pairs_dev && out, REEF_EINVAL, "reef_nl_shard_finish: NULL argument");
+  REEF_REQUIRE(out->claim_r && out->rounds && out->sc_last_claim && out->next_running_claim, REEF_EINVAL,
+               "reef_nl_shard_finish: NULL output buffer");
+  return nl_shard_finish(s, all_pairs_dev, out->claim_r, out->rounds, out->sc_last_claim, out->next_running_claim);
+}
+
+void reef_nl_shard_free(reef_nl_session* s) { nl_shard_free(s); }
 
 int reef_gen_eq_table(reef_ctx* c, const uint8_t* rs, const uint64_t* qs, uint32_t m, const uint8_t* last_q, uint32_t ell,
                       uint8_t* out) {

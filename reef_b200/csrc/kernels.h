@@ -49,6 +49,16 @@ int launch_mle_eval(reef_ctx* c, const void* d_table, int is_u32, uint64_t n, co
 int launch_mle_round_coeffs(reef_ctx* c, const void* d_t, const void* d_eq, uint32_t ell, uint32_t i, uint8_t* h_out3);
 int launch_mle_round_fold(reef_ctx* c, void* d_t, void* d_eq, uint32_t ell, uint32_t i, const uint8_t* h_r);
 
+}  // namespace reef
+struct reef_nl_session;
+namespace reef {
+int nl_shard_begin(reef_ctx* c, const NlookupArgs& a, uint32_t rank, uint32_t world, reef_nl_session** out);
+int nl_shard_round_local(reef_nl_session* s, void* d_out3);
+int nl_shard_round_finish(reef_nl_session* s, const void* d_triples);
+int nl_shard_export(reef_nl_session* s, void* d_out2);
+int nl_shard_finish(reef_nl_session* s, const void* d_pairs, uint8_t* out_claim_r, uint8_t* out_rounds, uint8_t* out_last_claim,
+                    uint8_t* out_next_v);
+void nl_shard_free(reef_nl_session* s);
 int launch_lz(reef_ctx* c, const void* d_matrix, int is_u32, uint64_t rows, uint64_t cols, const uint8_t* h_L,
               uint8_t* h_out);
 

@@ -94,7 +94,7 @@ __device__ __forceinline__ void block_sum(Fq* vals, Fq* smem /* NV * NTHREADS/32
 __global__ void __launch_bounds__(32) k_nl_begin(NlState* st, const Fq* __restrict__ query, uint32_t n_query, Fq tag,
                                                  const Fq* __restrict__ prev_q, uint32_t ell, const uint64_t* __restrict__ q,
                                                  uint32_t m, uint64_t* __restrict__ sp_pos, Fq* __restrict__ sp_w,
-                                                 const PoseidonTables* __restrict__ K) {
+                                                 const PoseidonTables* __restrict__ K, uint32_t rank, uint32_t world) {
   const int lane = threadIdx.x;
   Fq s = fe_zero<FqCfg>();
   if (lane == 0) s = tag;
@@ -116,8 +116,9 @@ __global__ void __launch_bounds__(32) k_nl_begin(NlState* st, const Fq* __restri
     st->out_claim_r = from_mont<FqCfg>(claim);
     Fq pw = claim;                // rs[0] = claim_r
     for (uint32_t k = 0; k < m; k++) {
-      sp_w[k] = pw;
-      sp_pos[k] = q[k];
+      // sharded: rank g owns the indices with (q mod world) == g, at local position q / world
+      sp_w[k] = (q[k] % world == rank) ? pw : fe_zero<FqCfg>();
+      sp_pos[k] = q[k] / world;
       pw = mont_mul<FqCfg>(pw, claim);
     }
     st->rm_mont = pw;             // rs[m]
@@ -130,15 +131,22 @@ __global__ void __launch_bounds__(32) k_nl_begin(NlState* st, const Fq* __restri
 // k_eq_tables: A[hi] = rs[m] * prod_{j>=h} sel(bit_{j-h}(hi), lq[j]),  B[lo] = prod_{j<h} sel(bit_j(lo), lq[j])
 // (both in Montgomery form).  When ell <= h, A is the single entry rs[m] and B spans all bits.
 // ---------------------------------------------------------------------------------------
+// Sharded use: local index bit t pairs with lq[bit_off + t] and A carries the rank factor
+// c_g = prod_{t < bit_off} sel(bit_t(rank), lq[t]).
 __global__ void k_eq_tables(const NlState* __restrict__ st, uint32_t ell, uint32_t hb, Fq* __restrict__ A,
-                            uint64_t a_len, Fq* __restrict__ B, uint64_t b_len) {
+                            uint64_t a_len, Fq* __restrict__ B, uint64_t b_len, uint32_t bit_off, uint32_t rank) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a_len + b_len) return;
   const Fq one = fe_one<FqCfg>();
+  const Fq* lqs = st->lq_mont + bit_off;
   if (i < a_len) {
     Fq acc = st->rm_mont;
+    for (uint32_t t = 0; t < bit_off; t++) {
+      Fq lq = st->lq_mont[t];
+      acc = mont_mul<FqCfg>(acc, ((rank >> t) & 1) ? lq : fe_sub<FqCfg>(one, lq));
+    }
     for (uint32_t j = hb; j < ell; j++) {
-      Fq lq = st->lq_mont[j];
+      Fq lq = lqs[j];
       Fq f = ((i >> (j - hb)) & 1) ? lq : fe_sub<FqCfg>(one, lq);
       acc = mont_mul<FqCfg>(acc, f);
     }
@@ -147,7 +155,7 @@ __global__ void k_eq_tables(const NlState* __restrict__ st, uint32_t ell, uint32
     uint64_t lo = i - a_len;
     Fq acc = one;
     for (uint32_t j = 0; j < hb; j++) {
-      Fq lq = st->lq_mont[j];
+      Fq lq = lqs[j];
       Fq f = ((lo >> j) & 1) ? lq : fe_sub<FqCfg>(one, lq);
       acc = mont_mul<FqCfg>(acc, f);
     }
@@ -461,9 +469,9 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
   Fq tag = fq_mont_from_le32(a.tag_le);
   {
     ProfScope ps(c, PROF_NL_SETUP, N);
-    k_nl_begin<<<1, 32, 0, s>>>(st, d_query, a.n_query, tag, d_prevq, ell, d_q, m, d_pos, d_w, c->d_pos);
+    k_nl_begin<<<1, 32, 0, s>>>(st, d_query, a.n_query, tag, d_prevq, ell, d_q, m, d_pos, d_w, c->d_pos, 0, 1);
     REEF_LAUNCHED();
-    k_eq_tables<<<ceil_div_u(a_len + b_len, 128), 128, 0, s>>>(st, ell, hb, d_A, a_len, d_B, b_len);
+    k_eq_tables<<<ceil_div_u(a_len + b_len, 128), 128, 0, s>>>(st, ell, hb, d_A, a_len, d_B, b_len, 0, 0);
     REEF_LAUNCHED();
   }
 
@@ -754,6 +762,404 @@ int launch_lz(reef_ctx* c, const void* d_matrix, int is_u32, uint64_t rows, uint
   REEF_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)cols * 32, cudaMemcpyDeviceToHost, s));
   REEF_CUDA(cudaStreamSynchronize(s));
   return REEF_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Multi-GPU sharded sum-check (protocol stated in oracle/sharded.py).
+// Rank g holds T_g[j] = T[j*G + g].  Per round: local (const, g(1), xsq) -> all-gather ->
+// identical transcript on every rank.  No call below synchronises the stream; the triples
+// travel through caller-provided DEVICE buffers so that NCCL can move them directly.
+// ---------------------------------------------------------------------------------------
+
+// sum of this rank's CTA partials + its sparse-point terms -> out3 = (const, g(1), xsq)
+template <bool U32IN>
+__global__ void __launch_bounds__(ROUND_THREADS)
+k_shard_local(const Fq* __restrict__ partials, uint32_t nblk, const void* __restrict__ Tcur, uint64_t L,
+              const uint64_t* __restrict__ sp_pos, const Fq* __restrict__ sp_w, uint32_t m, Fq* __restrict__ out3) {
+  __shared__ Fq red[3 * ROUND_THREADS / 32];
+  const uint64_t half = L >> 1;
+  Fq acc[3];
+  acc[0] = acc[1] = acc[2] = fe_zero<FqCfg>();
+  for (uint32_t i = threadIdx.x; i < nblk; i += ROUND_THREADS) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) acc[k] = fe_add<FqCfg>(acc[k], ld256(partials + (uint64_t)i * 3 + k));
+  }
+  for (uint32_t k = threadIdx.x; k < m; k += ROUND_THREADS) {
+    uint64_t pos = sp_pos[k];
+    bool top = pos >= half;
+    uint64_t b = top ? pos - half : pos;
+    Fq w = sp_w[k];
+    Fq t0 = load_t<U32IN>(Tcur, b), t1 = load_t<U32IN>(Tcur, b + half);
+    Fq wt = mont_mul<FqCfg>(w, top ? t1 : t0);
+    Fq wd = mont_mul<FqCfg>(w, fe_sub<FqCfg>(t1, t0));
+    if (top) {
+      acc[1] = fe_add<FqCfg>(acc[1], wt);
+      acc[2] = fe_add<FqCfg>(acc[2], wd);
+    } else {
+      acc[0] = fe_add<FqCfg>(acc[0], wt);
+      acc[2] = fe_sub<FqCfg>(acc[2], wd);
+    }
+  }
+  block_sum<3, ROUND_THREADS>(acc, red);
+  if (threadIdx.x == 0)
+    for (int k = 0; k < 3; k++) st256(out3 + k, acc[k]);
+}
+
+// warp-level: sum the G gathered triples, absorb [const, x, xsq], squeeze r, record the round
+__device__ __forceinline__ Fq shard_transcript(NlState* st, const Fq* __restrict__ triples, uint32_t G, uint32_t ri,
+                                               const PoseidonTables* __restrict__ K) {
+  const int lane = threadIdx.x & 31;
+  Fq con = fe_zero<FqCfg>(), g1 = con, xsq = con;
+  for (uint32_t g = 0; g < G; g++) {
+    // generic loads: `triples` may live in global (gathered) or shared (final rounds) memory
+    con = fe_add<FqCfg>(con, triples[(uint64_t)g * 3 + 0]);
+    g1 = fe_add<FqCfg>(g1, triples[(uint64_t)g * 3 + 1]);
+    xsq = fe_add<FqCfg>(xsq, triples[(uint64_t)g * 3 + 2]);
+  }
+  Fq x = fe_sub<FqCfg>(fe_sub<FqCfg>(g1, con), xsq);
+  Fq s = lane < 5 ? st->sponge[lane] : fe_zero<FqCfg>();
+  Fq e = lane == 1 ? con : (lane == 2 ? x : xsq);
+  Fq sum = fe_add<FqCfg>(s, to_mont<FqCfg>(e));
+  if (lane >= 1 && lane <= 3) s = sum;
+  poseidon_permute_warp5(s, K);
+  if (lane < 5) st->sponge[lane] = s;
+  Fq r = shfl_fq(s, 1);
+  if (lane == 0) {
+    st->r_mont = r;
+    st->out_rounds[ri][0] = from_mont<FqCfg>(r);
+    st->out_rounds[ri][1] = xsq;
+    st->out_rounds[ri][2] = x;
+    st->out_rounds[ri][3] = con;
+  }
+  return r;
+}
+
+// sweep regime: transcript with the gathered triples, fold A, advance the sparse list
+__global__ void __launch_bounds__(ROUND_THREADS)
+k_shard_apply(NlState* st, const Fq* __restrict__ triples, uint32_t G, uint64_t L, Fq* A, uint64_t a_len,
+              uint64_t* sp_pos, Fq* sp_w, uint32_t m, uint32_t ri, const PoseidonTables* __restrict__ K) {
+  __shared__ Fq r_sh;
+  const uint64_t half = L >> 1;
+  if (threadIdx.x < 32) {
+    Fq r = shard_transcript(st, triples, G, ri, K);
+    if (threadIdx.x == 0) r_sh = r;
+  }
+  __syncthreads();
+  const Fq r = r_sh;
+  if (a_len > 1) {
+    const uint64_t ah = a_len >> 1;
+    for (uint64_t x = threadIdx.x; x < ah; x += ROUND_THREADS) {
+      Fq lo = A[x], hi = A[x + ah];
+      A[x] = fe_add<FqCfg>(lo, mont_mul<FqCfg>(r, fe_sub<FqCfg>(hi, lo)));
+    }
+  }
+  for (uint32_t k = threadIdx.x; k < m; k += ROUND_THREADS) {
+    uint64_t pos = sp_pos[k];
+    bool top = pos >= half;
+    Fq f = top ? r : fe_sub<FqCfg>(fe_one<FqCfg>(), r);
+    sp_w[k] = mont_mul<FqCfg>(sp_w[k], f);
+    sp_pos[k] = top ? pos - half : pos;
+  }
+}
+
+// enter the small regime: T_s (canonical) and E_s (Montgomery) materialised, length L <= 2^h
+template <bool U32IN>
+__global__ void __launch_bounds__(TAIL_THREADS)
+k_shard_materialize(const NlState* __restrict__ st, const void* __restrict__ Tin, uint64_t L_in, int do_fold,
+                    const Fq* __restrict__ A, const Fq* __restrict__ B, const uint64_t* __restrict__ sp_pos,
+                    const Fq* __restrict__ sp_w, uint32_t m, Fq* Ts, Fq* Es) {
+  const uint64_t L = do_fold ? (L_in >> 1) : L_in;
+  const Fq a0 = A[0];
+  const Fq rf = st->r_mont;
+  for (uint64_t b = threadIdx.x; b < L; b += TAIL_THREADS) {
+    Fq t = do_fold ? fold_one(load_t<U32IN>(Tin, b), load_t<U32IN>(Tin, b + L), rf) : load_t<U32IN>(Tin, b);
+    Ts[b] = t;
+    Es[b] = mont_mul<FqCfg>(a0, B[b]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (uint32_t k = 0; k < m; k++) Es[sp_pos[k]] = fe_add<FqCfg>(Es[sp_pos[k]], sp_w[k]);
+}
+
+// small regime, local sums of the current round
+__global__ void __launch_bounds__(TAIL_THREADS) k_small_local(const Fq* __restrict__ Ts, const Fq* __restrict__ Es, uint64_t L,
+                                                              Fq* __restrict__ out3) {
+  __shared__ Fq red[3 * TAIL_THREADS / 32];
+  const uint64_t half = L >> 1;
+  Fq acc[3];
+  acc[0] = acc[1] = acc[2] = fe_zero<FqCfg>();
+  for (uint64_t b = threadIdx.x; b < half; b += TAIL_THREADS) {
+    Fq t0 = Ts[b], t1 = Ts[b + half], e0 = Es[b], e1 = Es[b + half];
+    acc[0] = fe_add<FqCfg>(acc[0], mont_mul<FqCfg>(e0, t0));
+    acc[1] = fe_add<FqCfg>(acc[1], mont_mul<FqCfg>(e1, t1));
+    acc[2] = fe_add<FqCfg>(acc[2], mont_mul<FqCfg>(fe_sub<FqCfg>(e1, e0), fe_sub<FqCfg>(t1, t0)));
+  }
+  block_sum<3, TAIL_THREADS>(acc, red);
+  if (threadIdx.x == 0)
+    for (int k = 0; k < 3; k++) st256(out3 + k, acc[k]);
+}
+
+// small regime: transcript with the gathered triples, then fold T_s / E_s in place
+__global__ void __launch_bounds__(TAIL_THREADS)
+k_small_apply(NlState* st, const Fq* __restrict__ triples, uint32_t G, Fq* Ts, Fq* Es, uint64_t L, uint32_t ri,
+              const PoseidonTables* __restrict__ K) {
+  __shared__ Fq r_sh;
+  const uint64_t half = L >> 1;
+  if (threadIdx.x < 32) {
+    Fq r = shard_transcript(st, triples, G, ri, K);
+    if (threadIdx.x == 0) r_sh = r;
+  }
+  __syncthreads();
+  const Fq r = r_sh;
+  // half <= 512: every b is owned by one thread; reads of b + half precede no write there
+  for (uint64_t b = threadIdx.x; b < half; b += TAIL_THREADS) {
+    Fq t0 = Ts[b], t1 = Ts[b + half], e0 = Es[b], e1 = Es[b + half];
+    Ts[b] = fold_one(t0, t1, r);
+    Es[b] = fe_add<FqCfg>(e0, mont_mul<FqCfg>(r, fe_sub<FqCfg>(e1, e0)));
+  }
+}
+
+__global__ void k_shard_export(const Fq* __restrict__ Ts, const Fq* __restrict__ Es, Fq* __restrict__ out2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st256(out2 + 0, Ts[0]);
+    st256(out2 + 1, from_mont<FqCfg>(Es[0]));
+  }
+}
+
+// last gamma rounds over the G gathered (T, E) pairs (rank g's pair at index g), identical on
+// every rank; then last claim and next running claim.
+__global__ void __launch_bounds__(32) k_shard_final(NlState* st, const Fq* __restrict__ pairs, uint32_t G, uint32_t ri0,
+                                                    const PoseidonTables* __restrict__ K) {
+  __shared__ Fq Ts[64], Es[64], trip[3];
+  const int lane = threadIdx.x;
+  for (uint32_t g = lane; g < G; g += 32) {
+    Ts[g] = ld256(pairs + (uint64_t)g * 2);
+    Es[g] = to_mont<FqCfg>(ld256(pairs + (uint64_t)g * 2 + 1));
+  }
+  __syncwarp();
+  uint32_t ri = ri0;
+  for (uint32_t L = G; L > 1; L >>= 1) {
+    const uint32_t half = L >> 1;
+    Fq acc[3];
+    acc[0] = acc[1] = acc[2] = fe_zero<FqCfg>();
+    for (uint32_t b = lane; b < half; b += 32) {
+      Fq t0 = Ts[b], t1 = Ts[b + half], e0 = Es[b], e1 = Es[b + half];
+      acc[0] = fe_add<FqCfg>(acc[0], mont_mul<FqCfg>(e0, t0));
+      acc[1] = fe_add<FqCfg>(acc[1], mont_mul<FqCfg>(e1, t1));
+      acc[2] = fe_add<FqCfg>(acc[2], mont_mul<FqCfg>(fe_sub<FqCfg>(e1, e0), fe_sub<FqCfg>(t1, t0)));
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) acc[k] = warp_sum_fe<FqCfg>(acc[k]);
+    if (lane == 0)
+      for (int k = 0; k < 3; k++) trip[k] = acc[k];
+    __syncwarp();
+    Fq r = shard_transcript(st, trip, 1, ri, K);
+    for (uint32_t b = lane; b < half; b += 32) {
+      Fq t0 = Ts[b], t1 = Ts[b + half], e0 = Es[b], e1 = Es[b + half];
+      Ts[b] = fold_one(t0, t1, r);
+      Es[b] = fe_add<FqCfg>(e0, mont_mul<FqCfg>(r, fe_sub<FqCfg>(e1, e0)));
+    }
+    __syncwarp();
+    ri++;
+  }
+  if (lane == 0) {
+    const uint32_t last = ri - 1;
+    const Fq r = st->r_mont;
+    Fq t = fe_add<FqCfg>(mont_mul<FqCfg>(r, st->out_rounds[last][1]), st->out_rounds[last][2]);
+    st->out_last_claim = fe_add<FqCfg>(mont_mul<FqCfg>(r, t), st->out_rounds[last][3]);
+    st->out_next_v = Ts[0];
+  }
+}
+
+}  // namespace reef
+
+struct reef_nl_session {
+  reef_ctx* ctx;
+  void* d_buf;
+  const void* d_table;
+  int is_u32;
+  uint64_t n_loc;
+  uint32_t ell, ell_loc, gamma, rank, world, m;
+  reef::NlState* st;
+  reef::Fq *d_query, *d_prevq, *d_w, *d_A, *d_B, *d_part, *d_fold, *d_Ts, *d_Es;
+  uint64_t *d_q, *d_pos;
+  uint32_t round;     // local rounds finished
+  uint64_t L;         // local accumulation length of the upcoming round
+  uint64_t a_cur;
+  int small;          // 1 once T_s / E_s are materialised
+  uint32_t nblk;
+};
+
+namespace reef {
+
+int nl_shard_begin(reef_ctx* c, const NlookupArgs& a, uint32_t rank, uint32_t world, reef_nl_session** out) {
+  REEF_REQUIRE(world >= 1 && (world & (world - 1)) == 0 && world <= 64 && rank < world, REEF_EINVAL,
+               "nl_shard_begin: world must be a power of two <= 64");
+  uint32_t gamma = 0;
+  while ((1u << gamma) < world) gamma++;
+  REEF_REQUIRE(a.ell > gamma && a.ell <= (uint32_t)MAX_ELL, REEF_EINVAL, "nl_shard_begin: table too small for this world size");
+  const uint32_t ell_loc = a.ell - gamma;
+  const uint64_t n_loc = (uint64_t)1 << ell_loc;
+  REEF_REQUIRE(a.n == n_loc, REEF_EINVAL, "nl_shard_begin: local table must hold 2^(ell - log2 world) entries");
+  const uint32_t hb = ell_loc < (uint32_t)H_BITS ? ell_loc : (uint32_t)H_BITS;
+  const uint64_t a_len = (uint64_t)1 << (ell_loc - hb), b_len = (uint64_t)1 << hb;
+  const bool sweeps = ell_loc > (uint32_t)H_BITS;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  size_t o_state = take(sizeof(NlState)), o_query = take((size_t)a.n_query * 32), o_prevq = take((size_t)a.ell * 32);
+  size_t o_q = take((size_t)a.m * 8 + 8), o_pos = take((size_t)a.m * 8 + 8), o_w = take((size_t)a.m * 32 + 32);
+  size_t o_A = take(a_len * 32), o_B = take(b_len * 32);
+  size_t o_part = take((sweeps ? (n_loc / 2) / SWEEP_THREADS : 1) * 3 * 32);
+  size_t o_fold = take(sweeps ? (n_loc / 2) * 32 : 32);
+  size_t o_Ts = take((size_t)CHUNK * 32), o_Es = take((size_t)CHUNK * 32);
+  void* buf = nullptr;
+  cudaError_t e = cudaMalloc(&buf, off);
+  if (e != cudaSuccess) return fail(REEF_ENOMEM, std::string("nl_shard_begin: ") + cudaGetErrorString(e));
+  char* d = (char*)buf;
+  reef_nl_session* s = new reef_nl_session;
+  s->ctx = c;
+  s->d_buf = buf;
+  s->d_table = a.d_table;
+  s->is_u32 = a.table_is_u32;
+  s->n_loc = n_loc;
+  s->ell = a.ell;
+  s->ell_loc = ell_loc;
+  s->gamma = gamma;
+  s->rank = rank;
+  s->world = world;
+  s->m = a.m;
+  s->st = (NlState*)(d + o_state);
+  s->d_query = (Fq*)(d + o_query);
+  s->d_prevq = (Fq*)(d + o_prevq);
+  s->d_q = (uint64_t*)(d + o_q);
+  s->d_pos = (uint64_t*)(d + o_pos);
+  s->d_w = (Fq*)(d + o_w);
+  s->d_A = (Fq*)(d + o_A);
+  s->d_B = (Fq*)(d + o_B);
+  s->d_part = (Fq*)(d + o_part);
+  s->d_fold = (Fq*)(d + o_fold);
+  s->d_Ts = (Fq*)(d + o_Ts);
+  s->d_Es = (Fq*)(d + o_Es);
+  s->round = 0;
+  s->L = n_loc;
+  s->a_cur = a_len;
+  s->small = 0;
+  s->nblk = 0;
+  cudaStream_t st = c->stream;
+  auto bail = [&](int rc) {
+    cudaStreamSynchronize(st);
+    cudaFree(buf);
+    delete s;
+    return rc;
+  };
+  if (cudaMemcpyAsync(s->d_query, a.h_query, (size_t)a.n_query * 32, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(s->d_prevq, a.h_prev_q, (size_t)a.ell * 32, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      (a.m && cudaMemcpyAsync(s->d_q, a.h_q, (size_t)a.m * 8, cudaMemcpyHostToDevice, st) != cudaSuccess))
+    return bail(fail(REEF_ECUDA, "nl_shard_begin: upload failed"));
+  Fq tag = fq_mont_from_le32(a.tag_le);
+  k_nl_begin<<<1, 32, 0, st>>>(s->st, s->d_query, a.n_query, tag, s->d_prevq, a.ell, s->d_q, a.m, s->d_pos, s->d_w, c->d_pos, rank, world);
+  g_launches.fetch_add(1);
+  k_eq_tables<<<ceil_div_u(a_len + b_len, 128), 128, 0, st>>>(s->st, ell_loc, hb, s->d_A, a_len, s->d_B, b_len, gamma, rank);
+  g_launches.fetch_add(1);
+  if (cudaGetLastError() != cudaSuccess) return bail(fail(REEF_ECUDA, "nl_shard_begin: launch failed"));
+  cudaStreamSynchronize(st);   // the host staging vectors of the caller may go away
+  *out = s;
+  return REEF_OK;
+}
+
+template <bool U32IN>
+static int nl_shard_round_local_t(reef_nl_session* s, void* d_out3) {
+  reef_ctx* c = s->ctx;
+  cudaStream_t st = c->stream;
+  const size_t tail_smem = 0;
+  (void)tail_smem;
+  if (!s->small && (s->L >> 1) >= (uint64_t)CHUNK) {
+    uint32_t nblk = 0;
+    int rc;
+    if (s->round == 0) {
+      rc = launch_sweep<U32IN, false>(c, s->d_table, s->n_loc, nullptr, s->st, s->d_A, s->d_B, s->d_part, &nblk);
+      if (rc) return rc;
+      k_shard_local<U32IN><<<1, ROUND_THREADS, 0, st>>>(s->d_part, nblk, s->d_table, s->L, s->d_pos, s->d_w, s->m, (Fq*)d_out3);
+    } else {
+      if (s->round == 1) rc = launch_sweep<U32IN, true>(c, s->d_table, 2 * s->L, s->d_fold, s->st, s->d_A, s->d_B, s->d_part, &nblk);
+      else rc = launch_sweep<false, true>(c, s->d_fold, 2 * s->L, s->d_fold, s->st, s->d_A, s->d_B, s->d_part, &nblk);
+      if (rc) return rc;
+      k_shard_local<false><<<1, ROUND_THREADS, 0, st>>>(s->d_part, nblk, s->d_fold, s->L, s->d_pos, s->d_w, s->m, (Fq*)d_out3);
+    }
+    REEF_LAUNCHED();
+    return REEF_OK;
+  }
+  if (!s->small) {   // enter the small regime
+    if (s->round == 0) k_shard_materialize<U32IN><<<1, TAIL_THREADS, 0, st>>>(s->st, s->d_table, s->n_loc, 0, s->d_A, s->d_B, s->d_pos, s->d_w, s->m, s->d_Ts, s->d_Es);
+    else if (s->round == 1) k_shard_materialize<U32IN><<<1, TAIL_THREADS, 0, st>>>(s->st, s->d_table, 2 * s->L, 1, s->d_A, s->d_B, s->d_pos, s->d_w, s->m, s->d_Ts, s->d_Es);
+    else k_shard_materialize<false><<<1, TAIL_THREADS, 0, st>>>(s->st, s->d_fold, 2 * s->L, 1, s->d_A, s->d_B, s->d_pos, s->d_w, s->m, s->d_Ts, s->d_Es);
+    REEF_LAUNCHED();
+    s->small = 1;
+  }
+  k_small_local<<<1, TAIL_THREADS, 0, st>>>(s->d_Ts, s->d_Es, s->L, (Fq*)d_out3);
+  REEF_LAUNCHED();
+  return REEF_OK;
+}
+
+int nl_shard_round_local(reef_nl_session* s, void* d_out3) {
+  REEF_REQUIRE(s->round < s->ell_loc, REEF_EASSERT, "nl_shard_round_local: all local rounds are done");
+  return s->is_u32 ? nl_shard_round_local_t<true>(s, d_out3) : nl_shard_round_local_t<false>(s, d_out3);
+}
+
+int nl_shard_round_finish(reef_nl_session* s, const void* d_triples) {
+  REEF_REQUIRE(s->round < s->ell_loc, REEF_EASSERT, "nl_shard_round_finish: all local rounds are done");
+  reef_ctx* c = s->ctx;
+  cudaStream_t st = c->stream;
+  if (!s->small) {
+    k_shard_apply<<<1, ROUND_THREADS, 0, st>>>(s->st, (const Fq*)d_triples, s->world, s->L, s->d_A, s->a_cur, s->d_pos, s->d_w, s->m, s->round, c->d_pos);
+    if (s->a_cur > 1) s->a_cur >>= 1;
+  } else {
+    k_small_apply<<<1, TAIL_THREADS, 0, st>>>(s->st, (const Fq*)d_triples, s->world, s->d_Ts, s->d_Es, s->L, s->round, c->d_pos);
+  }
+  REEF_LAUNCHED();
+  s->L >>= 1;
+  s->round++;
+  return REEF_OK;
+}
+
+int nl_shard_export(reef_nl_session* s, void* d_out2) {
+  REEF_REQUIRE(s->round == s->ell_loc && s->small, REEF_EASSERT, "nl_shard_export: local rounds not finished");
+  k_shard_export<<<1, 32, 0, s->ctx->stream>>>(s->d_Ts, s->d_Es, (Fq*)d_out2);
+  REEF_LAUNCHED();
+  return REEF_OK;
+}
+
+int nl_shard_finish(reef_nl_session* s, const void* d_pairs, uint8_t* out_claim_r, uint8_t* out_rounds, uint8_t* out_last_claim,
+                    uint8_t* out_next_v) {
+  REEF_REQUIRE(s->round == s->ell_loc, REEF_EASSERT, "nl_shard_finish: local rounds not finished");
+  reef_ctx* c = s->ctx;
+  cudaStream_t st = c->stream;
+  k_shard_final<<<1, 32, 0, st>>>(s->st, (const Fq*)d_pairs, s->world, s->ell_loc, c->d_pos);
+  REEF_LAUNCHED();
+  void* hs;
+  int rc = ctx_stage(c, sizeof(NlState), &hs);
+  if (rc) return rc;
+  REEF_CUDA(cudaMemcpyAsync(hs, s->st, sizeof(NlState), cudaMemcpyDeviceToHost, st));
+  REEF_CUDA(cudaStreamSynchronize(st));
+  const NlState* h = (const NlState*)hs;
+  memcpy(out_claim_r, h->out_claim_r.v, 32);
+  for (uint32_t i = 0; i < s->ell; i++)
+    for (int k = 0; k < 4; k++) memcpy(out_rounds + ((size_t)i * 4 + k) * 32, h->out_rounds[i][k].v, 32);
+  memcpy(out_last_claim, h->out_last_claim.v, 32);
+  memcpy(out_next_v, h->out_next_v.v, 32);
+  return REEF_OK;
+}
+
+void nl_shard_free(reef_nl_session* s) {
+  if (!s) return;
+  cudaStreamSynchronize(s->ctx->stream);
+  cudaFree(s->d_buf);
+  delete s;
 }
 
 }  // namespace reef

@@ -217,3 +217,45 @@ def test_hyrax_lz_matvec(ctx, ell, u32):
             assert lz[j] == sum(L[i] * tab[i * cols + j] for i in range(rows)) % FQ
     assert sum(a * b for a, b in zip(lz, R)) % FQ == mle_eval_fast(tab, q)
     assert ctx.verifier_mle_eval(t, q) == mle_eval_fast(tab, q)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+@pytest.mark.parametrize("ell,u32,tag", [(5, False, "nl"), (11, True, "nldoc"), (13, False, "nlhybrid"), (15, True, "nldoc")])
+def test_sharded_sumcheck_all_ranks_on_one_gpu(ctx, world, ell, u32, tag):
+    """the table is sharded by low index bits over `world` ranks; here all ranks run
+    lock-step on one GPU and the all-gather is a device buffer every rank writes its slot of.
+    Every rank must reproduce the unsharded oracle bit for bit."""
+    import torch
+    rnd = random.Random(ell * 100 + world)
+    n = 1 << ell
+    table = [rnd.randrange(131 if u32 else FQ) for _ in range(n)]
+    q = [rnd.randrange(n) for _ in range(5)] + [0, n - 1]
+    v = [table[i] for i in q]
+    prev_q = [rnd.randrange(FQ) for _ in range(ell)]
+    prev_v = mle_eval_fast(table, prev_q)
+    exp = wit_nlookup_gadget(table, q, v, prev_q, prev_v, tag, 31337, fast=True)
+    tabs = []
+    for g in range(world):
+        shard = table[g::world]
+        tabs.append(ctx.table_u32(shard) if u32 else ctx.table(shard))
+    ranks = [reef_b200.ShardedNlookup(ctx, tabs[g], g, world, q, v, prev_q, prev_v, tag, 31337 if tag != "nl" else None)
+             for g in range(world)]
+    buf = torch.zeros(world * 96, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(ranks[0].ell_local):
+        for g, r in enumerate(ranks):
+            r.round_local(buf.data_ptr() + g * 96)
+        for r in ranks:
+            r.round_finish(buf.data_ptr())
+    pairs = torch.zeros(world * 64, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    for g, r in enumerate(ranks):
+        r.export(pairs.data_ptr() + g * 64)
+    for r in ranks:
+        got = r.finish(pairs.data_ptr())
+        assert got.claim_r == exp["claim_r"]
+        assert got.rounds == exp["rounds"]
+        assert got.sc_last_claim == exp["sc_last_claim"]
+        assert got.next_running_claim == exp["next_running_claim"]
+    for r in ranks:
+        r.free()

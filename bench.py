@@ -15,9 +15,9 @@ e2e     = the same pass through the C ABI with HOST buffers: document/table uplo
           upload and result read-back inside the timed region
 --impl reference = the CPU restatement of the reference's algorithm (oracle/c, all host cores).
 
-Multi-GPU (torchrun): the MSMs are sharded by Pippenger windows across ranks with ONE
-all-gather of partial points (NCCL) per MSM; the document sum-check is sharded over G
-independent documents (weak scaling: one 2^16-char document per GPU).
+Multi-GPU (torchrun), weak scaling: ONE document of base_len * G characters.  Its sum-check is
+sharded by low index bits (one 96-byte all-gather per round, every rank runs the same
+transcript), the MSMs are sharded by Pippenger windows (one 128-byte all-gather per MSM).
 """
 from __future__ import annotations
 
@@ -64,11 +64,12 @@ def pack(xs) -> bytes:
 # --------------------------------------------------------------------------------------------
 # synthetic workload (deterministic; the same bytes feed the GPU arm and the reference arm)
 # --------------------------------------------------------------------------------------------
-def make_workload(name: str, seed_shift: int = 0):
+def make_workload(name: str, seed_shift: int = 0, world: int = 1):
     from oracle.curves import PALLAS, VESTA          # test-infra helper used only to GENERATE inputs
     from oracle.nlookup import ASCII_AB, doc_transform
     w = dict(WORKLOADS[name])
     rnd = random.Random(1234 + seed_shift)
+    w["doc_len"] = w["doc_len"] * world          # weak scaling: one document of base_len * G characters
     doc_len = w["doc_len"]
     if name == "cfg2":
         doc = "a" * (doc_len - 1) + "b"
@@ -132,6 +133,8 @@ class GpuPass:
         self.ell_doc = reef_b200.logmn(len(w["udoc"]))
         self.ell_T = w["t_log"]
         self.pool = {k: ThreadPoolExecutor(max_workers=1) for k in ctxs}
+        # the MSM thread and the sum-check thread issue collectives concurrently: one communicator each
+        self.msm_group = dist.new_group() if world > 1 else None
         self._mk_out()
 
     def _mk_out(self):
@@ -149,10 +152,38 @@ class GpuPass:
     # -- residency ----------------------------------------------------------------------
     def make_resident(self):
         w, t = self.w, self.torch
-        self.doc_tab = self.ctxs["doc"].table_u32(w["udoc"])
+        self.doc_tab = self.ctxs["doc"].table_u32(self._doc_shard())
         self.T_tab = self.rb.Table(self.ctxs["nl"], values=w["T"])
+        if self.world > 1:
+            self.gbuf = t.zeros((self.world + 1) * 96, dtype=t.uint8, device="cuda")
+            self.doc_stream = t.cuda.ExternalStream(self.ctxs["doc"].stream)
         self.sc_dev = [{k: t.from_numpy(v.view(np.int64)).cuda() for k, v in s.items()} for s in w["sc"]]
         t.cuda.synchronize()
+
+    def _doc_shard(self):
+        return np.ascontiguousarray(self.w["udoc"][self.rank::self.world]) if self.world > 1 else self.w["udoc"]
+
+    def _gather(self, mine_ptr, nbytes, out_ptr):
+        """all-gather of `nbytes` per rank inside self.gbuf, ordered after the doc context's stream"""
+        t = self.torch
+        with t.cuda.stream(self.doc_stream):
+            self.dist.all_gather_into_tensor(self.gbuf[96:96 + self.world * nbytes], self.gbuf[:nbytes])
+
+    def _nlookup_sharded(self, tab, q_list, v_list, prev):
+        w = self.w
+        ell = self.ell_doc
+        if prev is None:
+            pq, pv = [0] * ell, int(w["udoc"][0])
+        else:
+            pq = [int.from_bytes(prev[0][i * 32:(i + 1) * 32], "little") for i in range(ell)]
+            pv = int.from_bytes(prev[1], "little")
+        sn = self.rb.ShardedNlookup(self.ctxs["doc"], tab, self.rank, self.world, q_list, v_list, pq, pv, "nldoc", w["doc_hash"])
+        res = sn.run(self._gather, self.gbuf.data_ptr())
+        sn.free()
+        nxt = le32(res.next_running_claim)
+        d = C.create_string_buffer(32)
+        self.check(self.lib.reef_calc_d(self.ctxs["doc"]._h, nxt, self.salt, d))
+        return pack(res.next_running_q), nxt
 
     def _nlookup(self, key, tab, q_arr, v_bytes, prev):
         o, b = self.o[key], self.bufs[key]
@@ -189,7 +220,7 @@ class GpuPass:
         self.check(self.lib.reef_msm_partial_dev(ctx._h, bases._h, C.c_void_p(dev_tensor.data_ptr()), n, w0, w1, part))
         mine = t.frombuffer(bytearray(part.raw), dtype=t.uint8).cuda()
         gathered = [t.empty_like(mine) for _ in range(self.world)]
-        self.dist.all_gather(gathered, mine)
+        self.dist.all_gather(gathered, mine, group=self.msm_group)
         allp = b"".join(bytes(g.cpu().numpy().tobytes()) for g in gathered)
         self.check(self.lib.reef_msm_combine(ctx._h, bases.curve, allp, self.world, out))
         return out.raw
@@ -204,7 +235,7 @@ class GpuPass:
         if resident:
             doc_tab, T_tab = self.doc_tab, self.T_tab
         else:
-            f1 = self.pool["doc"].submit(lambda: self.ctxs["doc"].table_u32(w["udoc"]))   # H2D of the document codes
+            f1 = self.pool["doc"].submit(lambda: self.ctxs["doc"].table_u32(self._doc_shard()))   # H2D of the document codes
             f2 = self.pool["nl"].submit(self._upload_T)
             doc_tab, T_tab = f1.result(), f2.result()
         prev_nl = prev_doc = None
@@ -212,7 +243,10 @@ class GpuPass:
         for s in range(w["steps"]):
             qn, qd = self.q_nl[s], self.q_doc[s]
             f_nl = self.pool["nl"].submit(self._nlookup, "nl", T_tab, qn[0], qn[1], prev_nl)
-            f_doc = self.pool["doc"].submit(self._nlookup, "nldoc", doc_tab, qd[0], qd[1], prev_doc)
+            if self.world > 1:
+                f_doc = self.pool["doc"].submit(self._nlookup_sharded, doc_tab, w["q_doc"][s], [int(w["udoc"][i]) for i in w["q_doc"][s]], prev_doc)
+            else:
+                f_doc = self.pool["doc"].submit(self._nlookup, "nldoc", doc_tab, qd[0], qd[1], prev_doc)
             prev_nl, prev_doc = f_nl.result(), f_doc.result()
             sc, scd = w["sc"][s], (self.sc_dev[s] if resident else None)
             for key, pool, bases, n in (("Wp", "pri", self.bases_pri, w["n_pri"]), ("Ws", "sec", self.bases_sec, w["n_sec"]),
@@ -321,12 +355,10 @@ def run_reef(args):
         torch.cuda.set_device(0)
     dev = local if world > 1 else 0
     ctxs = {k: reef_b200.Context(dev) for k in ("nl", "doc", "pri", "sec")}
-    # weak scaling: every rank proves its own document of the named length (seed differs per
-    # rank); the fold commitments of rank r's document are window-sharded across ALL ranks.
-    # With one document per rank the MSM collective would interleave G documents; to keep the
-    # collective structure simple every rank runs the same MSM inputs as rank 0 for those and
-    # its own document for the sum-checks.
-    w = make_workload(args.workload, seed_shift=0)
+    # weak scaling: ONE document of base_len * G characters.  Its nldoc sum-check is sharded by
+    # low index bits (rank g holds udoc[g::G]); the fold commitments are sharded by Pippenger
+    # windows; the tiny T-table sum-check is replicated.
+    w = make_workload(args.workload, seed_shift=0, world=world)
     gp = GpuPass(ctxs, w, rank, world, dist)
     gp.prepare_queries()
     gp.make_resident()
@@ -390,7 +422,7 @@ def run_reef(args):
     ms, wall_ms, launches, _, _ = timed(True, K, Wm, False)
     _, _, _, clocks, prof = timed(True, K, 1, True)
     e2e_ms, _, _, _, _ = timed(False, K, max(1, Wm // 2), False)
-    doc_units = w["doc_len"] * (world if world > 1 else 1)
+    doc_units = w["doc_len"]            # already base_len * world (one sharded document)
     value = doc_units / (ms / K / 1e3)
     e2e_value = doc_units / (e2e_ms / K / 1e3)
     if rank != 0:
@@ -437,7 +469,9 @@ def run_reef(args):
         "config": {"workload": args.workload + ": " + w["desc"], "l2": "256 MiB buffer written between steps (L2 flush)",
                    "timing": "CUDA events: start on an idle stream, end = latest of the 4 library streams; max over ranks",
                    "streams": "4 contexts/streams: nl sum-check | nldoc sum-check | Pallas MSMs | Vesta MSMs (fold i+1 sum-checks overlap fold i commitments)",
-                   "parallelism": f"msm-window-shard x{world}"},
+                   "parallelism": (f"1 document of {w['doc_len']} chars: nldoc sum-check sharded by low index bits x{world} "
+                                   f"(96-byte all-gather per round), MSMs sharded by Pippenger windows x{world} "
+                                   f"(128-byte all-gather per MSM)") if world > 1 else "single GPU"},
         "e2e": {"value": round(e2e_value, 1), "unit": "NFA steps/s", "ms_per_step": round(e2e_ms / K, 4),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "msm": msm,

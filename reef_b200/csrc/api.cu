@@ -139,6 +139,15 @@ static void hosttest_field_op(int op, const uint8_t* a, const uint8_t* b, uint8_
       break;
     }
     case 7: r = from_mont<C>(mont_mul_ll<C>(to_mont<C>(x), to_mont<C>(y))); break;       // low-latency variant
+    case 8: r = f29_to_canonical<C>(mul29<C>(f29_from_canonical<C>(x), f29_from_canonical<C>(y))); break;  // 29-bit limbs
+    case 9: {                                                                     // 29-bit limbs through Montgomery-256
+      const F29 k = f29_const_2_266<C>();
+      F29 a = f29_from_mont256<C>(to_mont<C>(x), k), b = f29_from_mont256<C>(to_mont<C>(y), k);
+      F29 s = f29_relax(f29_add_lazy(f29_add_lazy(a, b), a));                    // 2a + b, relaxed
+      F29 t = mul29<C>(f29_add_lazy(a, b), s);                                   // (a+b)(2a+b), lazy operand
+      r = from_mont<C>(f29_to_mont256<C>(t));
+      break;
+    }
     default: r = fe_zero<C>();
   }
   store_le(out, r.v);

@@ -11,6 +11,7 @@
 
 #include "../../include/reef_b200.h"
 #include "fp.cuh"
+#include "fp29.cuh"
 #include "poseidon.cuh"
 
 namespace reef {

@@ -22,6 +22,7 @@
 //   * Fiat-Shamir runs on device (warp-cooperative Poseidon), so a whole nlookup is a chain of
 //     stream-ordered launches with no host round trip.
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -31,7 +32,6 @@ namespace reef {
 
 static constexpr int H_BITS = 10;
 static constexpr int CHUNK = 1 << H_BITS;  // b-values per CTA in a sweep
-static constexpr int SWEEP_THREADS = 256;
 static constexpr int MAX_ELL = 48;
 
 // Device-resident state of one nlookup session.
@@ -164,86 +164,175 @@ __global__ void k_eq_tables(const NlState* __restrict__ st, uint32_t ell, uint32
 }
 
 // ---------------------------------------------------------------------------------------
-// k_sweep: (optional fold with r) + row-wise inner products with B; one CTA per 2^h b-values.
+// k_sweep: (optional fold with r) + row-wise inner products with B.
 //   L_in  length of Tin; L = FOLD ? L_in/2 : L_in is the accumulation length, half = L/2 >= 2^h.
-//   partials[blk][3] = (const, g(1), xsq) contributions of this CTA (canonical).
+//   One WARP per task = 32*ppl consecutive index pairs b (never straddles a 2^h row, ppl <= 32):
+//   lane <-> b (coalesced 1 KiB requests), each lane keeps lazily-accumulated 17-limb sums
+//   U0 += T'[b] B[lo], U1 += T'[b+half] B[lo] over its ppl pairs.  The warp total is taken
+//   with REDUX on 16-bit half-limbs (2 instructions per limb instead of a 5-level shuffle tree
+//   of 256-bit modular additions), ONE lane per task reduces mod p and applies the A factors,
+//   and the CTA emits one (const, g(1), xsq) triple:  partials[blk][3] (canonical).
 // ---------------------------------------------------------------------------------------
-template <bool U32IN, bool FOLD, int EPT>
-__global__ void __launch_bounds__(SWEEP_THREADS)
+static constexpr int SWEEP_WARPS = 4;
+
+// canonical a_mont * s / R for a single-limb s: 8 products + one Montgomery reduction
+__device__ __forceinline__ Fq mont_mul_u32(const Fq& a_mont, uint32_t s) {
+  u32 T[16], od[9];
+#pragma unroll
+  for (int i = 0; i < 16; i++) T[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 9; i++) od[i] = 0;
+  mad_row4(T, a_mont.v[0], a_mont.v[2], a_mont.v[4], a_mont.v[6], s);
+  mad_row4(od, a_mont.v[1], a_mont.v[3], a_mont.v[5], a_mont.v[7], s);
+  u32 sh[9];
+  sh[0] = 0;
+#pragma unroll
+  for (int i = 1; i < 9; i++) sh[i] = od[i - 1];
+  acc_add<9>(T, sh);
+  Fq r;
+  mont_reduce<FqCfg>(r.v, T);
+  return r;
+}
+
+// x0 + r (x1 - x0) for document codes (single-limb operands): canonical
+__device__ __forceinline__ Fq fold_one_u32(uint32_t x0, uint32_t x1, const Fq& r_mont) {
+  const bool neg = x1 < x0;
+  Fq p = mont_mul_u32(r_mont, neg ? x0 - x1 : x1 - x0);
+  Fq a = fq_from_u32(x0);
+  return neg ? fe_sub<FqCfg>(a, p) : fe_add<FqCfg>(a, p);
+}
+
+// w (10 limbs) += t * b for a single-limb t; capacity 2^32 products
+struct Wide10 {
+  u32 v[10];
+};
+__device__ __forceinline__ void wide10_mac_small(Wide10& w, uint32_t t, const u32* b) {
+  u32 pr[9], od[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) { pr[i] = 0; od[i] = 0; }
+  mad_row4(pr, b[0], b[2], b[4], b[6], t);
+  mad_row4(od, b[1], b[3], b[5], b[7], t);
+  u32 sh[9];
+  sh[0] = 0;
+#pragma unroll
+  for (int i = 1; i < 9; i++) sh[i] = od[i - 1];
+  acc_add<9>(pr, sh);
+  w.v[9] += acc_add<9>(w.v, pr);
+}
+
+// warp total of an NL-limb lazy accumulator, written by lane 0 as per-limb 64-bit column sums
+template <int NL>
+__device__ __forceinline__ void warp_limb_sums(const u32* v, unsigned long long* out /* shared, NL entries */) {
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    const u32 lo = __reduce_add_sync(0xffffffffu, v[i] & 0xffffu);
+    const u32 hi = __reduce_add_sync(0xffffffffu, v[i] >> 16);
+    if ((threadIdx.x & 31) == 0) out[i] = (unsigned long long)lo + ((unsigned long long)hi << 16);
+  }
+}
+
+template <bool U32IN, bool FOLD>
+__global__ void __launch_bounds__(SWEEP_WARPS * 32)
 k_sweep(const void* Tin, uint64_t L_in, Fq* Tout, const NlState* __restrict__ st,
-        const Fq* __restrict__ A, const Fq* __restrict__ B, Fq* __restrict__ partials) {
-  // EPT index pairs per thread; a CTA covers SWEEP_THREADS * EPT consecutive b-values, which
-  // never straddles a 2^h row (EPT in {1,2,4}).  Small live lengths use EPT = 1 so that the
-  // sweep is spread over all SMs instead of running 8-deep dependent chains on a few CTAs.
-  __shared__ Fq red[2 * SWEEP_THREADS / 32];
+        const Fq* __restrict__ A, const Fq* __restrict__ B, Fq* __restrict__ partials, uint32_t ppl) {
+  constexpr bool SMALL = U32IN && !FOLD;       // single-limb table entries: 10-limb accumulators
+  constexpr int NL = SMALL ? 10 : 17;
+  __shared__ unsigned long long cols[SWEEP_WARPS][2][17];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t L = FOLD ? (L_in >> 1) : L_in;
   const uint64_t half = L >> 1;
-  const uint64_t b0 = (uint64_t)blockIdx.x * (SWEEP_THREADS * EPT);
+  const uint64_t task = (uint64_t)blockIdx.x * SWEEP_WARPS + warp;
+  const uint64_t base = task * 32u * ppl;
   Fq r;
   if constexpr (FOLD) r = st->r_mont;
-  Wide17 U0, U1;
-  wide_zero(U0);
-  wide_zero(U1);
+  typename std::conditional<SMALL, Wide10, Wide17>::type acc0, acc1;
 #pragma unroll
-  for (int k = 0; k < EPT; k++) {
-    const uint64_t b = b0 + (uint64_t)k * SWEEP_THREADS + threadIdx.x;
+  for (int i = 0; i < NL; i++) { acc0.v[i] = 0; acc1.v[i] = 0; }
+#pragma unroll 2
+  for (uint32_t k = 0; k < ppl; k++) {
+    const uint64_t b = base + (uint64_t)k * 32 + lane;
     const uint32_t lo = (uint32_t)(b & (CHUNK - 1));
-    Fq t0, t1;
-    if constexpr (FOLD) {
-      Fq x00 = load_t<U32IN>(Tin, b), x01 = load_t<U32IN>(Tin, b + L);
-      Fq x10 = load_t<U32IN>(Tin, b + half), x11 = load_t<U32IN>(Tin, b + half + L);
-      t0 = fold_one(x00, x01, r);
-      t1 = fold_one(x10, x11, r);
-      st256(Tout + b, t0);
-      st256(Tout + b + half, t1);
+    const Fq bv = ld256(B + lo);
+    if constexpr (SMALL) {
+      const uint32_t t0 = ((const uint32_t*)Tin)[b], t1 = ((const uint32_t*)Tin)[b + half];
+      wide10_mac_small(acc0, t0, bv.v);
+      wide10_mac_small(acc1, t1, bv.v);
     } else {
-      t0 = load_t<U32IN>(Tin, b);
-      t1 = load_t<U32IN>(Tin, b + half);
-    }
-    Fq bv = ld256(B + lo);
-    if constexpr (U32IN && !FOLD) {
-      wide_mac_small(U0, t0.v[0], bv.v);
-      wide_mac_small(U1, t1.v[0], bv.v);
-    } else {
-      wide_mac(U0, t0.v, bv.v);
-      wide_mac(U1, t1.v, bv.v);
+      Fq t0, t1;
+      if constexpr (U32IN) {
+        const uint32_t* T = (const uint32_t*)Tin;
+        t0 = fold_one_u32(T[b], T[b + L], r);
+        t1 = fold_one_u32(T[b + half], T[b + half + L], r);
+      } else if constexpr (FOLD) {
+        const Fq* T = (const Fq*)Tin;
+        Fq x00 = ld256(T + b), x01 = ld256(T + b + L);
+        Fq x10 = ld256(T + b + half), x11 = ld256(T + b + half + L);
+        t0 = fold_one(x00, x01, r);
+        t1 = fold_one(x10, x11, r);
+      } else {
+        const Fq* T = (const Fq*)Tin;
+        t0 = ld256(T + b);
+        t1 = ld256(T + b + half);
+      }
+      if constexpr (FOLD) {
+        st256(Tout + b, t0);
+        st256(Tout + b + half, t1);
+      }
+      wide_mac(acc0, t0.v, bv.v);
+      wide_mac(acc1, t1.v, bv.v);
     }
   }
-  Fq u[2];
-  u[0] = wide_reduce_div_R<FqCfg>(U0);   // sum T*B  (B carries the Montgomery factor)
-  u[1] = wide_reduce_div_R<FqCfg>(U1);
-  block_sum<2, SWEEP_THREADS>(u, red);
-  if (threadIdx.x == 0) {
-    const uint64_t hi0 = b0 >> H_BITS;
-    Fq a0 = ld256(A + hi0), a1 = ld256(A + hi0 + (half >> H_BITS));
-    Fq* out = partials + (uint64_t)blockIdx.x * 3;
-    st256(out + 0, mont_mul<FqCfg>(a0, u[0]));
-    st256(out + 1, mont_mul<FqCfg>(a1, u[1]));
-    st256(out + 2, mont_mul<FqCfg>(fe_sub<FqCfg>(a1, a0), fe_sub<FqCfg>(u[1], u[0])));
+  warp_limb_sums<NL>(acc0.v, cols[warp][0]);
+  warp_limb_sums<NL>(acc1.v, cols[warp][1]);
+  __syncthreads();
+  if (warp == 0) {
+    const int t = lane < SWEEP_WARPS ? lane : 0;
+    Wide17 W0, W1;
+    unsigned long long c0 = 0, c1 = 0;
+#pragma unroll
+    for (int i = 0; i < 17; i++) {
+      if (i < NL) { c0 += cols[t][0][i]; c1 += cols[t][1][i]; }
+      W0.v[i] = (u32)c0; c0 >>= 32;
+      W1.v[i] = (u32)c1; c1 >>= 32;
+    }
+    const Fq u0 = wide_reduce_div_R<FqCfg>(W0);   // sum T*B  (B carries the Montgomery factor)
+    const Fq u1 = wide_reduce_div_R<FqCfg>(W1);
+    const uint64_t row = (((uint64_t)blockIdx.x * SWEEP_WARPS + t) * 32u * ppl) >> H_BITS;
+    const Fq a0 = ld256(A + row), a1 = ld256(A + row + (half >> H_BITS));
+    Fq p[3];
+    p[0] = mont_mul<FqCfg>(a0, u0);
+    p[1] = mont_mul<FqCfg>(a1, u1);
+    p[2] = mont_mul<FqCfg>(fe_sub<FqCfg>(a1, a0), fe_sub<FqCfg>(u1, u0));
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      Fq v = lane < SWEEP_WARPS ? p[k] : fe_zero<FqCfg>();
+#pragma unroll
+      for (int msk = 1; msk < SWEEP_WARPS; msk <<= 1) v = fe_add<FqCfg>(v, shfl_xor_fe(v, msk));
+      if (lane == 0) st256(partials + (uint64_t)blockIdx.x * 3 + k, v);
+    }
   }
+}
+
+// largest number of CTA partial triples any sweep over a table of n entries can emit
+static uint64_t sweep_max_blocks(uint64_t n) {
+  uint64_t b = (n / 2) / (32 * SWEEP_WARPS);
+  return b ? b : 1;
 }
 
 template <bool U32IN, bool FOLD>
 static int launch_sweep(reef_ctx* c, const void* Tin, uint64_t L_in, Fq* Tout, const NlState* st, const Fq* A,
                         const Fq* B, Fq* partials, uint32_t* nblk_out) {
   const uint64_t L = FOLD ? (L_in >> 1) : L_in;
-  const uint64_t half = L >> 1;
-  cudaStream_t s = c->stream;
-  // enough CTAs for two waves of 8 CTAs/SM before deepening the per-thread work
-  const uint64_t target = (uint64_t)c->sm_count * 16;
-  if (half / (SWEEP_THREADS * 4) >= target) {
-    const uint32_t nblk = (uint32_t)(half / (SWEEP_THREADS * 4));
-    k_sweep<U32IN, FOLD, 4><<<nblk, SWEEP_THREADS, 0, s>>>(Tin, L_in, Tout, st, A, B, partials);
-    *nblk_out = nblk;
-  } else if (half / (SWEEP_THREADS * 2) >= target) {
-    const uint32_t nblk = (uint32_t)(half / (SWEEP_THREADS * 2));
-    k_sweep<U32IN, FOLD, 2><<<nblk, SWEEP_THREADS, 0, s>>>(Tin, L_in, Tout, st, A, B, partials);
-    *nblk_out = nblk;
-  } else {
-    const uint32_t nblk = (uint32_t)(half / SWEEP_THREADS);
-    k_sweep<U32IN, FOLD, 1><<<nblk, SWEEP_THREADS, 0, s>>>(Tin, L_in, Tout, st, A, B, partials);
-    *nblk_out = nblk;
-  }
+  const uint64_t half = L >> 1;                  // >= 2^h
+  // pairs per lane: as deep as possible (amortises the per-task reduction) while keeping at
+  // least ~14 warps per SM in flight
+  const uint64_t want_tasks = (uint64_t)c->sm_count * 14;
+  uint32_t ppl = 1;
+  while (ppl < 32 && half / (32ull * (ppl * 2)) >= want_tasks) ppl *= 2;
+  const uint64_t tasks = half / (32ull * ppl);   // >= 32, a multiple of SWEEP_WARPS
+  const uint32_t nblk = (uint32_t)(tasks / SWEEP_WARPS);
+  k_sweep<U32IN, FOLD><<<nblk, SWEEP_WARPS * 32, 0, c->stream>>>(Tin, L_in, Tout, st, A, B, partials, ppl);
+  *nblk_out = nblk;
   REEF_LAUNCHED();
   return REEF_OK;
 }
@@ -427,7 +516,7 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
   const uint64_t a_len = (uint64_t)1 << (ell - hb);
   const uint64_t b_len = (uint64_t)1 << hb;
   const uint32_t n_sweeps = ell > (uint32_t)H_BITS ? ell - H_BITS : 0;
-  const uint64_t max_blk = n_sweeps ? (N / 2) / SWEEP_THREADS : 1;
+  const uint64_t max_blk = n_sweeps ? sweep_max_blocks(N) : 1;
 
   // scratch layout
   size_t off = 0;
@@ -1014,7 +1103,7 @@ int nl_shard_begin(reef_ctx* c, const NlookupArgs& a, uint32_t rank, uint32_t wo
   size_t o_state = take(sizeof(NlState)), o_query = take((size_t)a.n_query * 32), o_prevq = take((size_t)a.ell * 32);
   size_t o_q = take((size_t)a.m * 8 + 8), o_pos = take((size_t)a.m * 8 + 8), o_w = take((size_t)a.m * 32 + 32);
   size_t o_A = take(a_len * 32), o_B = take(b_len * 32);
-  size_t o_part = take((sweeps ? (n_loc / 2) / SWEEP_THREADS : 1) * 3 * 32);
+  size_t o_part = take((sweeps ? sweep_max_blocks(n_loc) : 1) * 3 * 32);
   size_t o_fold = take(sweeps ? (n_loc / 2) * 32 : 32);
   size_t o_Ts = take((size_t)CHUNK * 32), o_Es = take((size_t)CHUNK * 32);
   void* buf = nullptr;

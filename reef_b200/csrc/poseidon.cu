@@ -76,6 +76,35 @@ void poseidon_tables_host(PoseidonTables* t) {
   t->lam_end = cv(REEF_POSEIDON_LAM_END[0]);
   for (int i = 0; i < 4; i++)
     for (int j = 0; j < 4; j++) t->post[i][j] = cv(REEF_POSEIDON_POST[i * 4 + j]);
+  // 29-bit-limb copies: Montgomery-256 -> Montgomery-261 is a multiplication by 2^5
+  auto c29 = [](const Fq& m256) {
+    Fq x = m256;
+    for (int k = 0; k < 5; k++) x = fe_dbl<FqCfg>(x);
+    F29 f = f29_from_words(x.v);
+    F29s o;
+    for (int k = 0; k < 12; k++) o.l[k] = k < 9 ? f.l[k] : 0u;
+    return o;
+  };
+  Poseidon29Tables& q = t->t29;
+  for (int r = 0; r < 8; r++)
+    for (int i = 0; i < 5; i++) q.rc_full[r][i] = c29(t->rc_full[r][i]);
+  for (int i = 0; i < 5; i++)
+    for (int j = 0; j < 5; j++) q.mds[i][j] = c29(t->mds[i][j]);
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) q.post[i][j] = c29(t->post[i][j]);
+  for (int r = 0; r < 57; r++) q.kp[r] = c29(t->kp[r]);
+  for (int r = 0; r < 56; r++)
+    for (int i = 0; i < 4; i++) {
+      q.beta[r][i] = c29(t->beta[r][i]);
+      q.emat[r][i] = c29(mont_mul<FqCfg>(t->beta[r][i], t->dshift[r][i]));
+    }
+  for (int r = 0; r < 57; r++)
+    for (int i = 0; i < 4; i++) q.dshift[r][i] = c29(t->dshift[r][i]);
+  q.lam_end = c29(t->lam_end);
+  {
+    const F29 k = f29_const_2_266<FqCfg>();     // plain integer, not a Montgomery-form element
+    for (int i = 0; i < 12; i++) q.k266.l[i] = i < 9 ? k.l[i] : 0u;
+  }
 }
 
 int poseidon_upload_constants(reef_ctx* c) {

@@ -10,10 +10,28 @@
 // block after the partial rounds): ~1000 field multiplications instead of ~1900.
 #pragma once
 #include "fp.cuh"
+#include "fp29.cuh"
 
 namespace reef {
 
 typedef Fe<FqCfg> Fq;
+
+// 29-bit-limb copies (Montgomery-261, fp29.cuh) of the tables the warp-cooperative
+// Fiat-Shamir permutation uses; 9 limbs padded to 48 bytes for 128-bit loads.
+struct alignas(16) F29s {
+  u32 l[12];
+};
+struct Poseidon29Tables {
+  F29s rc_full[8][5];
+  F29s mds[5][5];
+  F29s post[4][4];
+  F29s kp[57];
+  F29s beta[56][4];
+  F29s emat[56][4];     // beta[r][i] * dshift[r][i]
+  F29s dshift[57][4];
+  F29s lam_end;
+  F29s k266;            // 2^266 mod p as a plain integer: Montgomery-256 -> Montgomery-261
+};
 
 // All tables in Montgomery form.  Filled once per device by poseidon_upload_constants().
 struct PoseidonTables {
@@ -27,6 +45,7 @@ struct PoseidonTables {
   Fq beta[56][4];
   Fq dshift[57][4];
   Fq lam_end;
+  Poseidon29Tables t29;
 };
 
 // x^5
@@ -142,90 +161,120 @@ __device__ __forceinline__ Fq sel_fq(bool c, const Fq& a, const Fq& b) {
   return r;
 }
 
-static __device__ __noinline__ void poseidon_full_round_warp5(Fq& s, int r, int li, const PoseidonTables* K) {
-  Fq x = quintic(fe_add<FqCfg>(s, ldg_fq(&K->rc_full[r][li])));
-  u32 acc[16];
-#pragma unroll 1
-  for (int i = 0; i < 5; i++) {
-    Fq xi = shfl_fq(x, i);
-    Fq m = ldg_fq(&K->mds[li][i]);
-    if (i == 0) {
-      mul_wide(acc, m.v, xi.v);
-    } else {
-      u32 t[16];
-      mul_wide(t, m.v, xi.v);
-      acc_add<16>(acc, t);
-    }
-  }
-  s = reduce_sum8(acc);
+// ---- 29-bit-limb implementation (fp29.cuh): no carry flags, no conditional subtractions ----
+__device__ __forceinline__ F29 ld29(const F29s* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  const uint4 a = __ldg(q), b = __ldg(q + 1);
+  F29 r;
+  r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+  r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+  r.l[8] = __ldg(&p->l[8]);
+  return r;
 }
 
-// One rescaled partial round.  lane 0 carries w (the rescaled lane-0 state), lanes 1..4 carry
-// s_i; `ub` = u of the previous round on every lane.  Three multiplications deep:
-//   step 1  lane 0: w^2          lanes 1..4: s_i += dshift[r][i] * u_{r-1}
-//   step 2  lane 0: w^4          lanes 1..4: p_i = beta[r][i] * s_i      (then summed onto lane 0)
-//   step 3  lane 0: u = w^4 * w
+__device__ __forceinline__ F29 shfl29(const F29& x, int src) {
+  F29 r;
+#pragma unroll
+  for (int i = 0; i < 9; i++) r.l[i] = __shfl_sync(0xffffffffu, x.l[i], src);
+  return r;
+}
+
+__device__ __forceinline__ F29 sel29(bool c, const F29& a, const F29& b) {
+  F29 r;
+#pragma unroll
+  for (int i = 0; i < 9; i++) r.l[i] = c ? a.l[i] : b.l[i];
+  return r;
+}
+
+static __device__ __noinline__ void p29_full_round(F29& s, int r, int li, const Poseidon29Tables* T) {
+  const F29 x = f29_add_lazy(s, ld29(&T->rc_full[r][li]));     // < 2^30 per limb
+  const F29 x2 = mul29<FqCfg>(x, x);
+  const F29 x4 = mul29<FqCfg>(x2, x2);
+  const F29 x5 = mul29<FqCfg>(x4, x);
+  u64 col[18];
+#pragma unroll
+  for (int k = 0; k < 18; k++) col[k] = 0;
+#pragma unroll 1
+  for (int i = 0; i < 5; i++) {
+    const F29 xi = shfl29(x5, i);
+    const F29 m = ld29(&T->mds[li][i]);
+    mul29_cols<true>(col, m, xi);                              // 45 products per column < 2^63.5
+  }
+  s = redc29<FqCfg>(col);
+}
+
+// One rescaled partial round, three multiplications deep, nothing else on the critical path.
+//   lane 0 carries w_r; lanes 1..4 carry s_i(r-1) (relaxed, not reduced); ub = u_{r-1} everywhere.
+//   slot 1  lane 0: w^2         lanes 1..4: beta[r][i] * s_i(r-1)
+//   slot 2  lane 0: w^4         lanes 1..4: (beta[r][i] dshift[r][i]) * u_{r-1}
+//           p_i = slot1 + slot2 = beta[r][i] * s_i(r)  -> summed onto lane 0 while slot 3 runs
+//   slot 3  lane 0: u = w^4 w   lanes 1..4: dshift[r][i] * u_{r-1}   (s_i(r) = s_i(r-1) + that)
 //   lane 0: w <- u + sum p_i + kp[r+1]
-static __device__ __noinline__ void poseidon_partial_round_warp5(Fq& s, Fq& ub, int r, int lane, int li,
-                                                                 const PoseidonTables* K) {
+// The broadcast of u_r is only consumed in slot 2 of the next round.
+static __device__ __noinline__ void p29_partial_round(F29& s, F29& ub, int r, int lane, int li,
+                                                      const Poseidon29Tables* T) {
   const bool l0 = (li == 0);
   const bool mid = (lane >= 1 && lane <= 4);
   const int ci = li > 0 ? li - 1 : 0;
-  const Fq kd = ldg_fq(&K->dshift[r][ci]);
-  const Fq kb = ldg_fq(&K->beta[r][ci]);
-  const Fq kk = ldg_fq(&K->kp[r + 1]);
-  const Fq w = s;
-  Fq m1 = mont_mul<FqCfg>(sel_fq(l0, w, kd), sel_fq(l0, w, ub));
-  Fq si = fe_add<FqCfg>(s, m1);                        // lanes 1..4: s_i(r)
-  Fq m2 = mont_mul<FqCfg>(sel_fq(l0, m1, kb), sel_fq(l0, m1, si));
-  // C = p_1 + p_2 + p_3 + p_4 on lane 0
-  Fq v = sel_fq(mid, m2, fe_zero<FqCfg>());
-  Fq v1 = fe_add<FqCfg>(v, shfl_fq(v, (lane + 1) & 31));
-  Fq c = fe_add<FqCfg>(fe_add<FqCfg>(shfl_fq(v1, 1), shfl_fq(v1, 3)), kk);
-  Fq u = mont_mul<FqCfg>(m2, w);                       // lane 0: w^5
-  ub = shfl_fq(u, 0);
-  s = sel_fq(l0, fe_add<FqCfg>(u, c), si);
+  const F29 kb = ld29(&T->beta[r][ci]);
+  const F29 ke = ld29(&T->emat[r][ci]);
+  const F29 kd = ld29(&T->dshift[r][ci]);
+  const F29 kk = ld29(&T->kp[r + 1]);
+  const F29 w = s;
+  const F29 m1 = mul29<FqCfg>(sel29(l0, w, kb), w);
+  const F29 m2 = mul29<FqCfg>(sel29(l0, m1, ke), sel29(l0, m1, ub));
+  const F29 v = sel29(mid, f29_relax(f29_add_lazy(m1, m2)), f29_zero());
+  const F29 v1 = f29_add_lazy(v, shfl29(v, (lane + 1) & 31));
+  const F29 c = f29_add_lazy(f29_add_lazy(shfl29(v1, 1), shfl29(v1, 3)), kk);
+  const F29 m3 = mul29<FqCfg>(sel29(l0, m2, kd), sel29(l0, w, ub));
+  ub = shfl29(m3, 0);
+  s = f29_relax(f29_add_lazy(m3, sel29(l0, c, w)));
 }
 
-static __device__ __noinline__ void poseidon_post_warp5(Fq& s, int li, const PoseidonTables* K) {
+static __device__ __noinline__ void p29_post(F29& s, int li, const Poseidon29Tables* T) {
   const int row = li > 0 ? li - 1 : 0;
-  u32 acc[16];
+  u64 col[18];
+#pragma unroll
+  for (int k = 0; k < 18; k++) col[k] = 0;
 #pragma unroll 1
   for (int i = 1; i < 5; i++) {
-    Fq si = shfl_fq(s, i);
-    Fq m = ldg_fq(&K->post[row][i - 1]);
-    if (i == 1) {
-      mul_wide(acc, m.v, si.v);
-    } else {
-      u32 t[16];
-      mul_wide(t, m.v, si.v);
-      acc_add<16>(acc, t);
-    }
+    const F29 si = shfl29(s, i);
+    const F29 m = ld29(&T->post[row][i - 1]);
+    mul29_cols<true>(col, m, si);
   }
-  Fq u = reduce_sum8(acc);
-  s = sel_fq(li == 0, s, u);
+  const F29 u = redc29<FqCfg>(col);
+  s = sel29(li == 0, s, u);
 }
 
-// In/out: `s` = state element `lane` for lanes 0..4 (other lanes: don't care).
+// In/out: `s` = state element `lane` for lanes 0..4 (other lanes: don't care), Montgomery-256.
 __device__ __forceinline__ void poseidon_permute_warp5(Fq& s, const PoseidonTables* K) {
   const int lane = threadIdx.x & 31;
   const int li = lane < 5 ? lane : 4;
-  if (lane >= 5) s = fe_zero<FqCfg>();
-#pragma unroll 1
-  for (int r = 0; r < 4; r++) poseidon_full_round_warp5(s, r, li, K);
+  const Poseidon29Tables* T = &K->t29;
   {
-    Fq ub = fe_zero<FqCfg>();
-    if (lane == 0) s = fe_add<FqCfg>(s, ldg_fq(&K->kp[0]));
+    // warm L1 with this launch's constants: one 128-byte line per lane per step
+    const char* base = reinterpret_cast<const char*>(T);
+    for (uint32_t off = lane * 128u; off < (uint32_t)sizeof(Poseidon29Tables); off += 32u * 128u)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(base + off));
+  }
+  if (lane >= 5) s = fe_zero<FqCfg>();
+  F29 x = f29_from_mont256<FqCfg>(s, ld29(&T->k266));
 #pragma unroll 1
-    for (int r = 0; r < 56; r++) poseidon_partial_round_warp5(s, ub, r, lane, li, K);
+  for (int r = 0; r < 4; r++) p29_full_round(x, r, li, T);
+  {
+    F29 ub = f29_zero();
+    if (lane == 0) x = f29_add_lazy(x, ld29(&T->kp[0]));
+#pragma unroll 1
+    for (int r = 0; r < 56; r++) p29_partial_round(x, ub, r, lane, li, T);
     // closing step: s_i(56) = s_i(55) + dshift[56][i] * u_55 ;  s_0 = lam_end * w_56
     const int ci = li > 0 ? li - 1 : 0;
-    Fq m = mont_mul<FqCfg>(sel_fq(li == 0, ldg_fq(&K->lam_end), ldg_fq(&K->dshift[56][ci])), sel_fq(li == 0, s, ub));
-    s = li == 0 ? m : fe_add<FqCfg>(s, m);
+    const F29 m = mul29<FqCfg>(sel29(li == 0, ld29(&T->lam_end), ld29(&T->dshift[56][ci])), sel29(li == 0, x, ub));
+    x = li == 0 ? m : f29_relax(f29_add_lazy(x, m));
   }
-  poseidon_post_warp5(s, li, K);
+  p29_post(x, li, T);
 #pragma unroll 1
-  for (int r = 4; r < 8; r++) poseidon_full_round_warp5(s, r, li, K);
+  for (int r = 4; r < 8; r++) p29_full_round(x, r, li, T);
+  s = f29_to_mont256<FqCfg>(x);
 }
 #endif  // __CUDACC__
 

@@ -42,7 +42,13 @@ def lib():
 
 
 def max_threads() -> int:
-    return int(lib().oracle_max_threads())
+    """Host threads the CPU arm may use: the cores this process is allowed to run on.  Not
+    omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 into every rank."""
+    import os
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or int(lib().oracle_max_threads()))
 
 
 def _pack(xs):

@@ -198,6 +198,7 @@ void reef_shutdown(reef_ctx* c) {
   if (c->scratch2) cudaFree(c->scratch2);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->d_pos) cudaFree(c->d_pos);
+  for (auto& kv : c->table_cache) cudaFree(kv.second);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -619,7 +620,15 @@ static int table_new(reef_ctx* c, const void* host, uint64_t n, int is_u32, reef
   std::lock_guard<std::mutex> lk(c->mu);
   REEF_CUDA(cudaSetDevice(c->device));
   void* d = nullptr;
-  cudaError_t e = cudaMalloc(&d, (size_t)n_pad * esz);
+  cudaError_t e = cudaSuccess;
+  for (size_t k = 0; k < c->table_cache.size(); k++) {
+    if (c->table_cache[k].first == (size_t)n_pad * esz) {
+      d = c->table_cache[k].second;
+      c->table_cache.erase(c->table_cache.begin() + k);
+      break;
+    }
+  }
+  if (!d) e = cudaMalloc(&d, (size_t)n_pad * esz);
   if (e != cudaSuccess) return fail(REEF_ENOMEM, std::string("reef_table_upload: ") + cudaGetErrorString(e));
   e = cudaMemcpyAsync(d, host, (size_t)n * esz, cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess && n_pad > n) e = cudaMemsetAsync((char*)d + (size_t)n * esz, 0, (size_t)(n_pad - n) * esz, c->stream);
@@ -685,7 +694,8 @@ void reef_table_free(reef_table* t) {
     std::lock_guard<std::mutex> lk(t->ctx->mu);
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
-    cudaFree(t->d);
+    if (t->ctx->table_cache.size() < 4) t->ctx->table_cache.emplace_back((size_t)t->n_pad * (t->is_u32 ? 4 : 32), t->d);
+    else cudaFree(t->d);
   }
   delete t;
 }

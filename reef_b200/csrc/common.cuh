@@ -157,6 +157,9 @@ struct reef_ctx {
   void* h_stage = nullptr;
   size_t h_stage_bytes = 0;
   int sm_count = 148;
+  // device buffers of freed tables, reused by the next upload of the same size: a prover re-uploads
+  // a same-sized table per proof, and cudaMalloc/cudaFree synchronise the whole device
+  std::vector<std::pair<size_t, void*>> table_cache;
   // optional per-kernel-class event timing (reef_profile_enable); resolved lazily
   bool profile = false;
   std::vector<reef::ProfRec> prof;

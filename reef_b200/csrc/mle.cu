@@ -325,8 +325,9 @@ static int launch_sweep(reef_ctx* c, const void* Tin, uint64_t L_in, Fq* Tout, c
   const uint64_t L = FOLD ? (L_in >> 1) : L_in;
   const uint64_t half = L >> 1;                  // >= 2^h
   // pairs per lane: as deep as possible (amortises the per-task reduction) while keeping at
-  // least ~14 warps per SM in flight
-  const uint64_t want_tasks = (uint64_t)c->sm_count * 14;
+  // least ~8 warps per SM in flight (integer-issue bound: 2 warps per scheduler already
+  // saturate it, tools/bench_lat.cu; measured best of {2,4,8,14} with tools/sweep_probe.py)
+  const uint64_t want_tasks = (uint64_t)c->sm_count * 8;
   uint32_t ppl = 1;
   while (ppl < 32 && half / (32ull * (ppl * 2)) >= want_tasks) ppl *= 2;
   const uint64_t tasks = half / (32ull * ppl);   // >= 32, a multiple of SWEEP_WARPS

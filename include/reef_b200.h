@@ -38,6 +38,7 @@ extern "C" {
 typedef struct reef_ctx reef_ctx;
 typedef struct reef_table reef_table;   /* device-resident lookup table (T or the document) */
 typedef struct reef_sponge reef_sponge; /* device-resident SAFE sponge session */
+typedef struct reef_sumcheck reef_sumcheck; /* device-resident Spartan sum-check session */
 
 /* ------------------------------------------------------------------ lifecycle */
 int reef_abi_version(void);
@@ -250,6 +251,39 @@ int reef_msm_rows(reef_ctx* ctx, const reef_bases* b, const uint8_t* matrix, uin
 int reef_msm_partial_dev(reef_ctx* ctx, const reef_bases* b, const void* scalars_dev, uint64_t n, uint32_t w_begin,
                          uint32_t w_end, uint8_t out_xyzz[128]);
 int reef_msm_combine(reef_ctx* ctx, int curve, const uint8_t* partials_xyzz, uint32_t k, uint8_t out[64]);
+
+/* ------------------------------------------------------------------ B4: Spartan sweeps behind CompressedSNARK::prove
+ * Replaces the per-round work of nova-snark's `SumcheckProof::prove_quad` and
+ * `prove_cubic_with_additive_term` (reached from framework.rs:695-698 with
+ * S = spartan::RelaxedR1CSSNARK<G, ipa_pc::EvaluationEngine<G>>, framework.rs:5-8, and from
+ * commitment.rs:261-268 `cap_prove`).  nova-snark is a git dependency without a pinned revision
+ * (Cargo.toml:12) and is not under /root/reference: the convention implemented is the published
+ * upstream one (top variable bound first; round polynomial sent as its evaluations) and is
+ * PARITY-UNPINNED against Reef's fork.  The transcript stays with the caller.
+ *   field: 0 = Fq (Pallas scalar field, primary), 1 = Fp (Vesta scalar field, secondary).
+ *   kind 2: tables {A, B},        round polynomial g(X) = sum_x A(X,x) B(X,x);        evals: g(0), g(2)
+ *   kind 4: tables {A, B, C, D},  g(X) = sum_x A(X,x) (B(X,x) C(X,x) - D(X,x));     evals: g(0), g(2), g(3)
+ * (g(1) = claim - g(0) is the caller's, as upstream.)  Tables: n canonical elements each, n = 2^k.
+ * Round 1: reef_sumcheck_round(s, NULL, evals).  Round i+1: reef_sumcheck_round(s, r_i, evals) binds
+ * every table with r_i (`bound_poly_var_top`: Z[j] += r (Z[j + len/2] - Z[j])) and accumulates the
+ * next evaluations in the same sweep.  After the last round reef_sumcheck_final(s, r_k, claims)
+ * returns the `kind` bound values A(r), B(r), ... */
+int reef_sumcheck_begin(reef_ctx* ctx, int field, int kind, const uint8_t* const* tables, uint64_t n, reef_sumcheck** out);
+int reef_sumcheck_round(reef_sumcheck* s, const uint8_t* r_prev /* NULL on the first round */, uint8_t* out_evals);
+int reef_sumcheck_final(reef_sumcheck* s, const uint8_t r_last[32], uint8_t* out_claims);
+void reef_sumcheck_free(reef_sumcheck* s);
+
+/* Sparse R1CS matrix times vector over the field (the A z, B z, C z products of the folding step,
+ * framework.rs:668-675 -> nova-snark R1CSShape::multiply_vec).  CSR: row_ptr has n_rows + 1 entries,
+ * col_idx / vals have row_ptr[n_rows] entries (vals canonical).  out: n_rows elements. */
+int reef_r1cs_spmv(reef_ctx* ctx, int field, const uint64_t* row_ptr, const uint32_t* col_idx, const uint8_t* vals,
+                   uint64_t n_rows, uint64_t n_cols, const uint8_t* z, uint8_t* out);
+
+/* IPA generator folding (commitment.rs:371-393 -> nova-snark ipa_pc `ck.fold(&r_inverse, &r)`):
+ * out[i] = s_lo * bases[i] + s_hi * bases[i + n/2], i < n/2; scalars canonical in the curve's scalar
+ * field.  curve: 0 Pallas, 1 Vesta.  out: (n/2) x 64 B affine. */
+int reef_ipa_fold_bases(reef_ctx* ctx, int curve, const uint8_t* bases, uint64_t n, const uint8_t s_lo[32],
+                        const uint8_t s_hi[32], uint8_t* out);
 
 #ifdef __cplusplus
 }

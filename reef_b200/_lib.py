@@ -97,6 +97,12 @@ _sig = {
     "reef_msm_combine": (C.c_int, [_vp, C.c_int, _vp, C.c_uint32, _vp]),
     # test hooks (include/reef_b200_testing.h)
     "reef_hosttest_ec_op": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp]),
+    "reef_sumcheck_begin": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_uint64, C.POINTER(_vp)]),
+    "reef_sumcheck_round": (C.c_int, [_vp, _vp, _vp]),
+    "reef_sumcheck_final": (C.c_int, [_vp, _vp, _vp]),
+    "reef_sumcheck_free": (None, [_vp]),
+    "reef_r1cs_spmv": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, _vp]),
+    "reef_ipa_fold_bases": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, _vp, _vp, _vp]),
     "reef_hosttest_field_op": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp]),
     "reef_hosttest_mul_wide": (C.c_int, [_vp, _vp, _vp]),
     "reef_hosttest_poseidon_permute": (C.c_int, [_vp, _vp]),

@@ -211,6 +211,28 @@ class Context:
             next_running_q=[r[0] for r in rounds],
         )
 
+    # ---- Spartan sweeps behind CompressedSNARK::prove (framework.rs:695-698), R1CS products, IPA fold
+    def sumcheck(self, tables, field: str = "fq") -> "Sumcheck":
+        """2 tables: prove_quad (A*B); 4 tables: prove_cubic_with_additive_term (A*(B*C-D))."""
+        return Sumcheck(self, tables, field)
+
+    def r1cs_spmv(self, row_ptr, col_idx, vals, z, field: str = "fq") -> list:
+        rp = np.ascontiguousarray(np.asarray(row_ptr, dtype=np.uint64))
+        ci = np.ascontiguousarray(np.asarray(col_idx, dtype=np.uint32))
+        n_rows = len(rp) - 1
+        out = C.create_string_buffer(max(n_rows, 1) * 32)
+        check(lib.reef_r1cs_spmv(self._h, _FIELDS[field], rp.ctypes.data, ci.ctypes.data if len(ci) else None,
+                                 _buf(_pack(vals)) if len(vals) else None, n_rows, len(z), _buf(_pack(z)), out))
+        return _unpack(out.raw[:n_rows * 32])
+
+    def ipa_fold_bases(self, curve, points, s_lo: int, s_hi: int) -> list:
+        """out[i] = s_lo * G[i] + s_hi * G[i + n/2]  (nova ipa_pc `ck.fold`)."""
+        n = len(points)
+        out = C.create_string_buffer(max(n // 2, 1) * 64)
+        check(lib.reef_ipa_fold_bases(self._h, _CURVES[curve], _buf(b"".join(_pt_bytes(P) for P in points)), n,
+                                      _buf(_pack([s_lo])), _buf(_pack([s_hi])), out))
+        return [_pt_from(out.raw[i * 64:(i + 1) * 64]) for i in range(n // 2)]
+
     # ---- Merkle
     def merkle(self, doc) -> "MerkleCommitment":
         return MerkleCommitment(self, doc)
@@ -226,6 +248,45 @@ class Context:
             return b.msm(scalars)
         finally:
             b.free()
+
+
+_FIELDS = {"fq": 0, "fp": 1}
+_CURVES = {"pallas": 0, "vesta": 1}
+
+
+class Sumcheck:
+    """Device-resident sum-check session: round(None) -> evaluations of round 1; round(r_i) binds the
+    top variable with r_i and returns the evaluations of round i+1; final(r_k) -> bound values."""
+
+    def __init__(self, ctx: "Context", tables, field: str = "fq"):
+        self.ctx, self.kind, self.n = ctx, len(tables), len(tables[0])
+        bufs = [_buf(_pack(t)) for t in tables]
+        arr = (C.c_void_p * self.kind)(*[C.cast(b, C.c_void_p) for b in bufs])
+        h = C.c_void_p()
+        check(lib.reef_sumcheck_begin(ctx._h, _FIELDS[field], self.kind, arr, self.n, C.byref(h)))
+        self._h = h
+
+    def round(self, r_prev=None) -> list:
+        ne = 2 if self.kind == 2 else 3
+        out = C.create_string_buffer(ne * 32)
+        check(lib.reef_sumcheck_round(self._h, _buf(_pack([r_prev])) if r_prev is not None else None, out))
+        return _unpack(out.raw)
+
+    def final(self, r_last: int) -> list:
+        out = C.create_string_buffer(self.kind * 32)
+        check(lib.reef_sumcheck_final(self._h, _buf(_pack([r_last])), out))
+        return _unpack(out.raw)
+
+    def free(self):
+        if self._h:
+            lib.reef_sumcheck_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 @dataclass

@@ -1,0 +1,519 @@
+// Spartan-side sum-check sweeps and the sparse R1CS products of row a3.
+//
+// Replaces, inside nova-snark's CompressedSNARK::prove as reached from
+//   /root/reference/src/backend/framework.rs:695-698  (S = spartan::RelaxedR1CSSNARK<G, ipa_pc::EvaluationEngine<G>>, framework.rs:5-8)
+//   /root/reference/src/backend/commitment.rs:261-268 (SpartanSNARK::cap_prove)
+// the per-round work of `SumcheckProof::prove_quad` (inner sum-check, comb = A*B) and
+// `prove_cubic_with_additive_term` (outer sum-check, comb = A*(B*C - D) with A = eq(tau, .),
+// B = Az, C = Bz, D = u*Cz + E), plus `bound_poly_var_top`.  nova-snark is NOT under
+// /root/reference (git dependency without a pinned revision, Cargo.toml:12): the round polynomial
+// convention restated here -- evaluations at 0, 2 (and 3) of the round polynomial, top variable
+// bound first, Z[i] <- Z[i] + r (Z[i + n/2] - Z[i]) -- is the published upstream algorithm and is
+// PARITY-UNPINNED against the fork Reef builds with (oracle/spartan.py says the same).  The
+// transcript stays with the caller: one call per round returns the evaluations, the next call
+// takes the challenge.
+//
+// B200 shape: the tables stay resident; round i+1 binds with r_i and accumulates its evaluations
+// in the SAME sweep (each table is read once and written once per round).  Tables that only
+// ever appear as the left factor of a product are kept in Montgomery form so that every product
+// is one lazily accumulated 256x256 multiply (no reduction per term).
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "ec.cuh"
+#include "kernels.h"
+
+namespace reef {
+
+static constexpr int SC_WARPS = 4;
+static constexpr int SC_MAX_TABLES = 4;
+
+template <class C>
+struct ScTables {
+  Fe<C>* t[SC_MAX_TABLES];
+};
+
+template <class C>
+__device__ __forceinline__ Fe<C> sc_fold(const Fe<C>& x0, const Fe<C>& x1, const Fe<C>& r_mont) {
+  return fe_add<C>(x0, mont_mul<C>(r_mont, fe_sub<C>(x1, x0)));
+}
+
+// warp total of a 17-limb lazy accumulator -> canonical (sum / R) on lane 0
+template <class C>
+__device__ __forceinline__ Fe<C> sc_warp_total(const Wide17& w) {
+  Wide17 tot;
+  unsigned long long carry = 0;
+#pragma unroll
+  for (int i = 0; i < 17; i++) {
+    const u32 lo = __reduce_add_sync(0xffffffffu, w.v[i] & 0xffffu);
+    const u32 hi = __reduce_add_sync(0xffffffffu, w.v[i] >> 16);
+    carry += (unsigned long long)lo + ((unsigned long long)hi << 16);
+    tot.v[i] = (u32)carry;
+    carry >>= 32;
+  }
+  return wide_reduce_div_R<C>(tot);
+}
+
+// KIND 2: tables A (Montgomery), B (canonical); evaluations of sum A*B at 0 and 2.
+// KIND 4: tables A, B (Montgomery), C, D (canonical); evaluations of sum A*(B*C - D) at 0, 2, 3.
+// L_in = length of the tables on entry; with FOLD they are first bound to L = L_in/2 with r.
+// partials[warp][NE] canonical.
+template <class C, int KIND, bool FOLD>
+__global__ void __launch_bounds__(SC_WARPS * 32)
+k_sc_round(ScTables<C> tabs, uint64_t L_in, Fe<C> r_mont, Fe<C>* __restrict__ partials, uint32_t ppl) {
+  constexpr int NE = KIND == 2 ? 2 : 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t L = FOLD ? (L_in >> 1) : L_in;
+  const uint64_t half = L >> 1;
+  const uint64_t wid = (uint64_t)blockIdx.x * SC_WARPS + warp;
+  Wide17 acc[NE];
+#pragma unroll
+  for (int e = 0; e < NE; e++) wide_zero(acc[e]);
+#pragma unroll 1
+  for (uint32_t k = 0; k < ppl; k++) {
+    const uint64_t i = (wid * ppl + k) * 32 + lane;
+    if (i >= half) break;
+    Fe<C> lo[KIND], hi[KIND];
+#pragma unroll
+    for (int t = 0; t < KIND; t++) {
+      Fe<C>* T = tabs.t[t];
+      if constexpr (FOLD) {
+        lo[t] = sc_fold<C>(ld256(T + i), ld256(T + i + L), r_mont);
+        hi[t] = sc_fold<C>(ld256(T + i + half), ld256(T + i + half + L), r_mont);
+        st256(T + i, lo[t]);
+        st256(T + i + half, hi[t]);
+      } else {
+        lo[t] = ld256(T + i);
+        hi[t] = ld256(T + i + half);
+      }
+    }
+    // points 0, 2, 3 of each table's line through (lo, hi): lo, 2hi - lo, 3hi - 2lo
+    Fe<C> pt[KIND];
+#pragma unroll
+    for (int t = 0; t < KIND; t++) pt[t] = lo[t];
+#pragma unroll
+    for (int e = 0; e < NE; e++) {
+      if (e > 0) {
+#pragma unroll
+        for (int t = 0; t < KIND; t++) {
+          const Fe<C> d = fe_sub<C>(hi[t], lo[t]);
+          pt[t] = e == 1 ? fe_add<C>(hi[t], d) : fe_add<C>(pt[t], d);
+        }
+      }
+      if constexpr (KIND == 2) {
+        wide_mac(acc[e], pt[0].v, pt[1].v);                       // (A R) * B
+      } else {
+        const Fe<C> bc = mont_mul<C>(pt[1], pt[2]);               // (B R) * C / R = B C
+        const Fe<C> w = fe_sub<C>(bc, pt[3]);
+        wide_mac(acc[e], pt[0].v, w.v);                           // (A R) * (B C - D)
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < NE; e++) {
+    const Fe<C> tot = sc_warp_total<C>(acc[e]);
+    if (lane == 0) st256(partials + wid * NE + e, tot);
+  }
+}
+
+template <class C, int NE>
+__global__ void __launch_bounds__(128) k_sc_sum(const Fe<C>* __restrict__ partials, uint32_t n_warps, Fe<C>* __restrict__ out) {
+  __shared__ Fe<C> red[NE * 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Fe<C> acc[NE];
+#pragma unroll
+  for (int e = 0; e < NE; e++) acc[e] = fe_zero<C>();
+  for (uint32_t i = threadIdx.x; i < n_warps; i += 128)
+#pragma unroll
+    for (int e = 0; e < NE; e++) acc[e] = fe_add<C>(acc[e], ld256(partials + (uint64_t)i * NE + e));
+#pragma unroll
+  for (int e = 0; e < NE; e++) acc[e] = warp_sum_fe<C>(acc[e]);
+  if (lane == 0)
+#pragma unroll
+    for (int e = 0; e < NE; e++) red[warp * NE + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int e = 0; e < NE; e++) {
+      Fe<C> s = red[e];
+      for (int w = 1; w < 4; w++) s = fe_add<C>(s, red[w * NE + e]);
+      st256(out + e, s);
+    }
+  }
+}
+
+// in-place conversions of a table: canonical -> Montgomery (x R) and back
+template <class C>
+__global__ void k_sc_to_mont(Fe<C>* t, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) st256(t + i, to_mont<C>(ld256(t + i)));
+}
+
+// final bind of length-2 tables -> one value per table, canonical
+template <class C>
+__global__ void k_sc_final(ScTables<C> tabs, int kind, int n_mont, Fe<C> r_mont, Fe<C>* __restrict__ out) {
+  const int t = threadIdx.x;
+  if (t >= kind) return;
+  Fe<C> v = sc_fold<C>(tabs.t[t][0], tabs.t[t][1], r_mont);
+  if (t < n_mont) v = from_mont<C>(v);
+  st256(out + t, v);
+}
+
+// ---------------------------------------------------------------------------------------
+// sparse matrix-vector product over the field (rows of A, B, C times z; framework.rs:668-675
+// -> nova-snark's R1CSShape::multiply_vec): CSR, one warp per row, lazily accumulated.
+// ---------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(128) k_spmv(const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
+                                              const Fe<C>* __restrict__ val_mont, const Fe<C>* __restrict__ z,
+                                              uint64_t n_rows, Fe<C>* __restrict__ out) {
+  const uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;   // warp-uniform
+  const uint64_t b = row_ptr[row], e = row_ptr[row + 1];
+  Wide17 acc;
+  wide_zero(acc);
+  for (uint64_t k = b + lane; k < e; k += 32) {
+    const Fe<C> v = ld256(val_mont + k);
+    const Fe<C> x = ld256(z + col[k]);
+    wide_mac(acc, v.v, x.v);
+  }
+  const Fe<C> tot = sc_warp_total<C>(acc);
+  if (lane == 0) st256(out + row, tot);
+}
+
+// ---------------------------------------------------------------------------------------
+// IPA generator folding (commitment.rs:371-393 -> nova-snark ipa_pc: `ck.fold(&r_inverse, &r)`):
+//   out[i] = s_lo * G[i] + s_hi * G[i + n/2],  the same two scalars for every i.
+// One thread per output point: joint (Shamir) double-and-add over the 255 scalar bits with the
+// three addends G_lo, G_hi, G_lo + G_hi; uniform control flow; Fermat inversion for the final
+// affine form (no divergent binary GCD across the warp).
+// ---------------------------------------------------------------------------------------
+struct Scalar256 {
+  uint32_t w[8];
+};
+
+template <class C>
+__global__ void __launch_bounds__(128) k_ipa_fold(const Affine<C>* __restrict__ in_canon, uint64_t half, Scalar256 s_lo,
+                                                  Scalar256 s_hi, Affine<C>* __restrict__ out_canon) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= half) return;
+  Affine<C> g0, g1;
+  g0.x = to_mont<C>(ld256(&in_canon[i].x));
+  g0.y = to_mont<C>(ld256(&in_canon[i].y));
+  g1.x = to_mont<C>(ld256(&in_canon[i + half].x));
+  g1.y = to_mont<C>(ld256(&in_canon[i + half].y));
+  XYZZ<C> both = xyzz_from_affine<C>(g0);
+  xyzz_add_affine<C>(both, g1, false);
+  XYZZ<C> acc = xyzz_inf<C>();
+#pragma unroll 1
+  for (int b = 255; b >= 0; b--) {
+    acc = xyzz_dbl<C>(acc);
+    const uint32_t b0 = (s_lo.w[b >> 5] >> (b & 31)) & 1u, b1 = (s_hi.w[b >> 5] >> (b & 31)) & 1u;
+    if (b0 & b1) xyzz_add<C>(acc, both);
+    else if (b0) xyzz_add_affine<C>(acc, g0, false);
+    else if (b1) xyzz_add_affine<C>(acc, g1, false);
+  }
+  Affine<C> r;
+  if (xyzz_is_inf<C>(acc)) {
+    r.x = fe_zero<C>();
+    r.y = fe_zero<C>();
+  } else {
+    r = xyzz_to_affine_with_inv<C>(acc, fe_pow_pm2<C>(acc.zzz));
+    r.x = from_mont<C>(r.x);
+    r.y = from_mont<C>(r.y);
+  }
+  st256(&out_canon[i].x, r.x);
+  st256(&out_canon[i].y, r.y);
+}
+
+}  // namespace reef
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct reef_sumcheck {
+  reef_ctx* ctx;
+  int field;        // 0 = Fq, 1 = Fp
+  int kind;         // 2 or 4
+  uint64_t len;     // current table length (before the pending bind)
+  uint32_t rounds_done;
+  void* d_buf;
+  void* tabs[reef::SC_MAX_TABLES];
+  void* d_partials;
+  void* d_out;
+};
+
+namespace reef {
+
+static unsigned sc_cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+template <class C>
+static Fe<C> fe_mont_from_le32(const uint8_t* b) {
+  Fe<C> x;
+  for (int i = 0; i < 8; i++)
+    x.v[i] = (uint32_t)b[4 * i] | ((uint32_t)b[4 * i + 1] << 8) | ((uint32_t)b[4 * i + 2] << 16) | ((uint32_t)b[4 * i + 3] << 24);
+  return to_mont<C>(x);
+}
+
+template <class C>
+static int sc_round_t(reef_sumcheck* s, const uint8_t* r_prev, uint8_t* out_evals) {
+  reef_ctx* c = s->ctx;
+  cudaStream_t st = c->stream;
+  const bool fold = r_prev != nullptr;
+  const uint64_t L = fold ? s->len >> 1 : s->len;
+  const uint64_t half = L >> 1;
+  ScTables<C> tabs;
+  for (int t = 0; t < SC_MAX_TABLES; t++) tabs.t[t] = (Fe<C>*)s->tabs[t];
+  Fe<C> r = fe_zero<C>();
+  if (fold) r = fe_mont_from_le32<C>(r_prev);
+  // pairs per lane: keep ~8 warps per SM in flight, at most 16 pairs per lane
+  uint32_t ppl = 1;
+  while (ppl < 16 && half / (32ull * ppl * 2) >= (uint64_t)c->sm_count * 8) ppl *= 2;
+  const uint64_t n_warps_needed = (half + 32ull * ppl - 1) / (32ull * ppl);
+  const unsigned nblk = sc_cdiv(n_warps_needed, SC_WARPS);
+  const uint32_t n_warps = nblk * SC_WARPS;
+  const int ne = s->kind == 2 ? 2 : 3;
+  Fe<C>* part = (Fe<C>*)s->d_partials;
+  Fe<C>* d_out = (Fe<C>*)s->d_out;
+  if (s->kind == 2) {
+    if (fold) k_sc_round<C, 2, true><<<nblk, SC_WARPS * 32, 0, st>>>(tabs, s->len, r, part, ppl);
+    else k_sc_round<C, 2, false><<<nblk, SC_WARPS * 32, 0, st>>>(tabs, s->len, r, part, ppl);
+    REEF_LAUNCHED();
+    k_sc_sum<C, 2><<<1, 128, 0, st>>>(part, n_warps, d_out);
+  } else {
+    if (fold) k_sc_round<C, 4, true><<<nblk, SC_WARPS * 32, 0, st>>>(tabs, s->len, r, part, ppl);
+    else k_sc_round<C, 4, false><<<nblk, SC_WARPS * 32, 0, st>>>(tabs, s->len, r, part, ppl);
+    REEF_LAUNCHED();
+    k_sc_sum<C, 3><<<1, 128, 0, st>>>(part, n_warps, d_out);
+  }
+  REEF_LAUNCHED();
+  REEF_CUDA(cudaMemcpyAsync(out_evals, d_out, (size_t)ne * 32, cudaMemcpyDeviceToHost, st));
+  REEF_CUDA(cudaStreamSynchronize(st));
+  s->len = L;
+  s->rounds_done++;
+  return REEF_OK;
+}
+
+template <class C>
+static int sc_final_t(reef_sumcheck* s, const uint8_t* r_last, uint8_t* out_claims) {
+  reef_ctx* c = s->ctx;
+  cudaStream_t st = c->stream;
+  ScTables<C> tabs;
+  for (int t = 0; t < SC_MAX_TABLES; t++) tabs.t[t] = (Fe<C>*)s->tabs[t];
+  const int n_mont = s->kind == 2 ? 1 : 2;
+  k_sc_final<C><<<1, 32, 0, st>>>(tabs, s->kind, n_mont, fe_mont_from_le32<C>(r_last), (Fe<C>*)s->d_out);
+  REEF_LAUNCHED();
+  REEF_CUDA(cudaMemcpyAsync(out_claims, s->d_out, (size_t)s->kind * 32, cudaMemcpyDeviceToHost, st));
+  REEF_CUDA(cudaStreamSynchronize(st));
+  s->len = 1;
+  return REEF_OK;
+}
+
+template <class C>
+static int sc_begin_t(reef_sumcheck* s, const uint8_t* const* tables, uint64_t n) {
+  reef_ctx* c = s->ctx;
+  cudaStream_t st = c->stream;
+  const int n_mont = s->kind == 2 ? 1 : 2;
+  for (int t = 0; t < s->kind; t++) {
+    REEF_CUDA(cudaMemcpyAsync(s->tabs[t], tables[t], (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    if (t < n_mont) {
+      k_sc_to_mont<C><<<sc_cdiv(n, 256), 256, 0, st>>>((Fe<C>*)s->tabs[t], n);
+      REEF_LAUNCHED();
+    }
+  }
+  REEF_CUDA(cudaStreamSynchronize(st));
+  return REEF_OK;
+}
+
+template <class C>
+static int spmv_t(reef_ctx* c, const uint64_t* row_ptr, const uint32_t* col, const uint8_t* vals, uint64_t n_rows,
+                  uint64_t nnz, const uint8_t* z, uint64_t n_cols, uint8_t* out) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t o_rp = take((n_rows + 1) * 8), o_col = take(nnz * 4 + 4), o_val = take(nnz * 32 + 32), o_z = take(n_cols * 32),
+               o_out = take(n_rows * 32);
+  void* base;
+  int rc = ctx_scratch(c, off, &base);
+  if (rc) return rc;
+  char* d = (char*)base;
+  cudaStream_t st = c->stream;
+  REEF_CUDA(cudaMemcpyAsync(d + o_rp, row_ptr, (n_rows + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (nnz) {
+    REEF_CUDA(cudaMemcpyAsync(d + o_col, col, nnz * 4, cudaMemcpyHostToDevice, st));
+    REEF_CUDA(cudaMemcpyAsync(d + o_val, vals, nnz * 32, cudaMemcpyHostToDevice, st));
+    k_sc_to_mont<C><<<sc_cdiv(nnz, 256), 256, 0, st>>>((Fe<C>*)(d + o_val), nnz);
+    REEF_LAUNCHED();
+  }
+  REEF_CUDA(cudaMemcpyAsync(d + o_z, z, n_cols * 32, cudaMemcpyHostToDevice, st));
+  k_spmv<C><<<sc_cdiv(n_rows * 32, 128), 128, 0, st>>>((const uint64_t*)(d + o_rp), (const uint32_t*)(d + o_col),
+                                                       (const Fe<C>*)(d + o_val), (const Fe<C>*)(d + o_z), n_rows,
+                                                       (Fe<C>*)(d + o_out));
+  REEF_LAUNCHED();
+  REEF_CUDA(cudaMemcpyAsync(out, d + o_out, n_rows * 32, cudaMemcpyDeviceToHost, st));
+  REEF_CUDA(cudaStreamSynchronize(st));
+  return REEF_OK;
+}
+
+template <class C>
+static int ipa_fold_t(reef_ctx* c, const uint8_t* bases, uint64_t n, const uint8_t* s_lo, const uint8_t* s_hi, uint8_t* out) {
+  const uint64_t half = n / 2;
+  void* base;
+  int rc = ctx_scratch(c, (size_t)n * 64 + (size_t)half * 64 + 512, &base);
+  if (rc) return rc;
+  Affine<C>* d_in = (Affine<C>*)base;
+  Affine<C>* d_out = d_in + n;
+  Scalar256 a, b;
+  for (int i = 0; i < 8; i++) {
+    a.w[i] = (uint32_t)s_lo[4 * i] | ((uint32_t)s_lo[4 * i + 1] << 8) | ((uint32_t)s_lo[4 * i + 2] << 16) | ((uint32_t)s_lo[4 * i + 3] << 24);
+    b.w[i] = (uint32_t)s_hi[4 * i] | ((uint32_t)s_hi[4 * i + 1] << 8) | ((uint32_t)s_hi[4 * i + 2] << 16) | ((uint32_t)s_hi[4 * i + 3] << 24);
+  }
+  cudaStream_t st = c->stream;
+  REEF_CUDA(cudaMemcpyAsync(d_in, bases, (size_t)n * 64, cudaMemcpyHostToDevice, st));
+  k_ipa_fold<C><<<sc_cdiv(half, 128), 128, 0, st>>>(d_in, half, a, b, d_out);
+  REEF_LAUNCHED();
+  REEF_CUDA(cudaMemcpyAsync(out, d_out, (size_t)half * 64, cudaMemcpyDeviceToHost, st));
+  REEF_CUDA(cudaStreamSynchronize(st));
+  return REEF_OK;
+}
+
+// canonical check against the modulus of the chosen field
+static bool le32_lt_modulus(const uint8_t* x, int field) {
+  uint32_t p[8];
+  for (int i = 0; i < 8; i++) p[i] = field == 0 ? modulus_limb<FqCfg>(i) : modulus_limb<FpCfg>(i);
+  for (int i = 7; i >= 0; i--) {
+    const uint32_t w = (uint32_t)x[4 * i] | ((uint32_t)x[4 * i + 1] << 8) | ((uint32_t)x[4 * i + 2] << 16) | ((uint32_t)x[4 * i + 3] << 24);
+    if (w < p[i]) return true;
+    if (w > p[i]) return false;
+  }
+  return false;
+}
+
+static int check_canon_field(const uint8_t* x, uint64_t n, int field, const char* what) {
+  for (uint64_t i = 0; i < n; i++)
+    if (!le32_lt_modulus(x + i * 32, field)) return fail(REEF_EINVAL, std::string(what) + ": element is not a canonical field element");
+  return REEF_OK;
+}
+
+}  // namespace reef
+
+using namespace reef;
+
+extern "C" {
+
+int reef_sumcheck_begin(reef_ctx* c, int field, int kind, const uint8_t* const* tables, uint64_t n, reef_sumcheck** out) {
+  REEF_REQUIRE(c && tables && out, REEF_EINVAL, "reef_sumcheck_begin: NULL argument");
+  REEF_REQUIRE(field == 0 || field == 1, REEF_EINVAL, "reef_sumcheck_begin: field must be 0 (Fq) or 1 (Fp)");
+  REEF_REQUIRE(kind == 2 || kind == 4, REEF_EINVAL, "reef_sumcheck_begin: kind must be 2 (quadratic) or 4 (cubic with additive term)");
+  REEF_REQUIRE(n >= 2 && (n & (n - 1)) == 0, REEF_EASSERT, "reef_sumcheck_begin: table length must be a power of two >= 2");
+  for (int t = 0; t < kind; t++) {
+    REEF_REQUIRE(tables[t] != nullptr, REEF_EINVAL, "reef_sumcheck_begin: NULL table");
+    int rc = check_canon_field(tables[t], n, field, "reef_sumcheck_begin");
+    if (rc) return rc;
+  }
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  reef_sumcheck* s = new reef_sumcheck;
+  memset(s, 0, sizeof(*s));
+  s->ctx = c;
+  s->field = field;
+  s->kind = kind;
+  s->len = n;
+  const size_t tab_bytes = ((size_t)n * 32 + 255) & ~(size_t)255;
+  const size_t part_bytes = ((size_t)(n / 64 + SC_WARPS * 4) * 3 * 32 + 255) & ~(size_t)255;
+  cudaError_t e = cudaMalloc(&s->d_buf, tab_bytes * kind + part_bytes + 256);
+  if (e != cudaSuccess) {
+    delete s;
+    return fail(REEF_ENOMEM, std::string("reef_sumcheck_begin: ") + cudaGetErrorString(e));
+  }
+  for (int t = 0; t < kind; t++) s->tabs[t] = (char*)s->d_buf + tab_bytes * t;
+  s->d_partials = (char*)s->d_buf + tab_bytes * kind;
+  s->d_out = (char*)s->d_partials + part_bytes;
+  int rc = field == 0 ? sc_begin_t<FqCfg>(s, tables, n) : sc_begin_t<FpCfg>(s, tables, n);
+  if (rc) {
+    cudaFree(s->d_buf);
+    delete s;
+    return rc;
+  }
+  *out = s;
+  return REEF_OK;
+}
+
+int reef_sumcheck_round(reef_sumcheck* s, const uint8_t* r_prev, uint8_t* out_evals) {
+  REEF_REQUIRE(s && out_evals, REEF_EINVAL, "reef_sumcheck_round: NULL argument");
+  REEF_REQUIRE((s->rounds_done == 0) == (r_prev == nullptr), REEF_EASSERT,
+               "reef_sumcheck_round: the first round takes no challenge, every later round takes the previous one");
+  REEF_REQUIRE((r_prev ? s->len >> 1 : s->len) >= 2, REEF_EASSERT, "reef_sumcheck_round: no variable left to sum over");
+  if (r_prev) {
+    int rc = check_canon_field(r_prev, 1, s->field, "reef_sumcheck_round: challenge");
+    if (rc) return rc;
+  }
+  reef_ctx* c = s->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  return s->field == 0 ? sc_round_t<FqCfg>(s, r_prev, out_evals) : sc_round_t<FpCfg>(s, r_prev, out_evals);
+}
+
+int reef_sumcheck_final(reef_sumcheck* s, const uint8_t* r_last, uint8_t* out_claims) {
+  REEF_REQUIRE(s && r_last && out_claims, REEF_EINVAL, "reef_sumcheck_final: NULL argument");
+  REEF_REQUIRE(s->len == 2 && s->rounds_done > 0, REEF_EASSERT, "reef_sumcheck_final: rounds are not finished");
+  int rc = check_canon_field(r_last, 1, s->field, "reef_sumcheck_final: challenge");
+  if (rc) return rc;
+  reef_ctx* c = s->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  return s->field == 0 ? sc_final_t<FqCfg>(s, r_last, out_claims) : sc_final_t<FpCfg>(s, r_last, out_claims);
+}
+
+void reef_sumcheck_free(reef_sumcheck* s) {
+  if (!s) return;
+  {
+    std::lock_guard<std::mutex> lk(s->ctx->mu);
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    cudaFree(s->d_buf);
+  }
+  delete s;
+}
+
+int reef_r1cs_spmv(reef_ctx* c, int field, const uint64_t* row_ptr, const uint32_t* col_idx, const uint8_t* vals,
+                   uint64_t n_rows, uint64_t n_cols, const uint8_t* z, uint8_t* out) {
+  REEF_REQUIRE(c && row_ptr && z && out, REEF_EINVAL, "reef_r1cs_spmv: NULL argument");
+  REEF_REQUIRE(field == 0 || field == 1, REEF_EINVAL, "reef_r1cs_spmv: field must be 0 (Fq) or 1 (Fp)");
+  REEF_REQUIRE(n_rows >= 1 && n_cols >= 1, REEF_EINVAL, "reef_r1cs_spmv: empty matrix");
+  REEF_REQUIRE(row_ptr[0] == 0, REEF_EINVAL, "reef_r1cs_spmv: row_ptr[0] must be 0");
+  const uint64_t nnz = row_ptr[n_rows];
+  for (uint64_t r = 0; r < n_rows; r++) REEF_REQUIRE(row_ptr[r] <= row_ptr[r + 1], REEF_EINVAL, "reef_r1cs_spmv: row_ptr must be non-decreasing");
+  REEF_REQUIRE(nnz == 0 || (col_idx && vals), REEF_EINVAL, "reef_r1cs_spmv: NULL entries");
+  for (uint64_t k = 0; k < nnz; k++) REEF_REQUIRE(col_idx[k] < n_cols, REEF_EASSERT, "reef_r1cs_spmv: column index out of bounds");
+  int rc = check_canon_field(z, n_cols, field, "reef_r1cs_spmv: z");
+  if (rc) return rc;
+  if (nnz) {
+    rc = check_canon_field(vals, nnz, field, "reef_r1cs_spmv: values");
+    if (rc) return rc;
+  }
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  return field == 0 ? spmv_t<FqCfg>(c, row_ptr, col_idx, vals, n_rows, nnz, z, n_cols, out)
+                    : spmv_t<FpCfg>(c, row_ptr, col_idx, vals, n_rows, nnz, z, n_cols, out);
+}
+
+int reef_ipa_fold_bases(reef_ctx* c, int curve, const uint8_t* bases, uint64_t n, const uint8_t s_lo[32],
+                        const uint8_t s_hi[32], uint8_t* out) {
+  REEF_REQUIRE(c && bases && s_lo && s_hi && out, REEF_EINVAL, "reef_ipa_fold_bases: NULL argument");
+  REEF_REQUIRE(curve == 0 || curve == 1, REEF_EINVAL, "reef_ipa_fold_bases: curve must be 0 (Pallas) or 1 (Vesta)");
+  REEF_REQUIRE(n >= 2 && (n & 1) == 0, REEF_EASSERT, "reef_ipa_fold_bases: the generator vector must have even length");
+  // coordinates live in the curve's base field: Pallas -> Fp (field 1), Vesta -> Fq (field 0)
+  int rc = check_canon_field(bases, n * 2, curve == 0 ? 1 : 0, "reef_ipa_fold_bases: point coordinate");
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  return curve == 0 ? ipa_fold_t<FpCfg>(c, bases, n, s_lo, s_hi, out) : ipa_fold_t<FqCfg>(c, bases, n, s_lo, s_hi, out);
+}
+
+}  // extern "C"

@@ -77,6 +77,12 @@ def make_workload(name: str, seed_shift: int = 0, world: int = 1):
     w = dict(WORKLOADS[name])
     rnd = random.Random(1234 + seed_shift)
     w["doc_len"] = w["doc_len"] * world          # weak scaling: one document of base_len * G characters
+    from oracle.nlookup import logmn as _logmn
+    if (1 << _logmn(w["doc_len"] + 2)) < w["doc_len"] + 2:
+        # The reference's f32 `logmn` (costs.rs:10-15) mis-rounds 2^22+2 and 2^23+2, so its doc_transform
+        # panics on documents of exactly 2^22 / 2^23 characters (framework.rs:1007): 64 more characters
+        # put the length where logmn is exact; the padded table (2^21 entries per GPU) is unchanged.
+        w["doc_len"] += 64
     doc_len = w["doc_len"]
     if name in ("cfg2", "target"):
         doc = "a" * (doc_len - 1) + "b"
@@ -220,16 +226,25 @@ class GpuPass:
         self.check(self.lib.reef_calc_d(ctx._h, nxt, self.salt, d))      # calc_d of the new running claim
         return next_q, nxt
 
-    def _msm(self, bases, dev_tensor, host_arr, n, resident):
+    # An MSM is window-sharded across the ranks only when it is large enough to be throughput-bound
+    # (n * windows digit entries); the 2^14..2^15-term fold commitments are latency pipelines, so
+    # with G > 1 ranks each WHOLE commitment goes to one rank (round-robin) and the 64-byte results
+    # are exchanged once per pass.
+    SHARD_MIN_ENTRIES = 1 << 22
+
+    def _msm_local(self, bases, dev_tensor, host_arr, n, resident):
         out = C.create_string_buffer(64)
         ctx = bases.ctx
-        if self.world == 1:
-            if resident:
-                self.check(self.lib.reef_msm_dev(ctx._h, bases._h, C.c_void_p(dev_tensor.data_ptr()), n, out))
-            else:
-                self.check(self.lib.reef_msm(ctx._h, bases._h, host_arr.ctypes.data, n, out))
-            return out.raw
-        # multi-GPU: windows [w0, w1) on this rank, one all-gather of 128-byte partial points
+        if resident:
+            self.check(self.lib.reef_msm_dev(ctx._h, bases._h, C.c_void_p(dev_tensor.data_ptr()), n, out))
+        else:
+            self.check(self.lib.reef_msm(ctx._h, bases._h, host_arr.ctypes.data, n, out))
+        return out.raw
+
+    def _msm_sharded(self, bases, dev_tensor, host_arr, n, resident):
+        # windows [w0, w1) on this rank, one all-gather of 128-byte partial points
+        out = C.create_string_buffer(64)
+        ctx = bases.ctx
         t = self.torch
         if not resident:
             dev_tensor = t.from_numpy(host_arr.view(np.int64)).cuda()
@@ -243,6 +258,20 @@ class GpuPass:
         allp = b"".join(bytes(g.cpu().numpy().tobytes()) for g in gathered)
         self.check(self.lib.reef_msm_combine(ctx._h, bases.curve, allp, self.world, out))
         return out.raw
+
+    def _exchange_points(self, outs, owners):
+        """One all-gather per pass: every rank ends up with all commitments (64 B each)."""
+        t = self.torch
+        k = len(outs)
+        mine = bytearray(k * 64)
+        for i, o in enumerate(outs):
+            if o is not None:
+                mine[i * 64:(i + 1) * 64] = o
+        buf = t.frombuffer(mine, dtype=t.uint8).cuda()
+        allb = t.empty(self.world * k * 64, dtype=t.uint8, device="cuda")
+        self.dist.all_gather_into_tensor(allb, buf)
+        host = allb.cpu().numpy().tobytes()
+        return [outs[i] if owners[i] is None else host[(owners[i] * k + i) * 64:(owners[i] * k + i + 1) * 64] for i in range(k)]
 
     def run(self, resident: bool):
         """One pass.  resident=False: every input crosses PCIe inside the call (e2e leg).
@@ -258,7 +287,7 @@ class GpuPass:
             f2 = self.pool["nl"].submit(self._upload_T)
             doc_tab, T_tab = f1.result(), f2.result()
         prev_nl = prev_doc = None
-        msm_futs = []
+        msm_futs, owners = [], []
         for s in range(w["steps"]):
             qn, qd = self.q_nl[s], self.q_doc[s]
             f_nl = self.pool["nl"].submit(self._nlookup, "nl", T_tab, qn[0], qn[1], prev_nl)
@@ -270,10 +299,21 @@ class GpuPass:
             sc, scd = w["sc"][s], (self.sc_dev[s] if resident else None)
             for key, pool, bases, n in (("Wp", "pri", self.bases_pri, w["n_pri"]), ("Ws", "sec", self.bases_sec, w["n_sec"]),
                                         ("Tp", "pri", self.bases_pri, w["n_pri"]), ("Ts", "sec", self.bases_sec, w["n_sec"])):
-                if self.world > 1:
-                    pool = "pri"            # one thread issues the NCCL collectives, in the same order on every rank
-                msm_futs.append(self.pool[pool].submit(self._msm, bases, scd[key] if resident else None, sc[key], n, resident))
-        outs = [f.result() for f in msm_futs]
+                args = (bases, scd[key] if resident else None, sc[key], n, resident)
+                if self.world == 1:
+                    msm_futs.append(self.pool[pool].submit(self._msm_local, *args))
+                    owners.append(None)
+                elif n * bases.windows >= self.SHARD_MIN_ENTRIES:
+                    # one thread issues these collectives, in the same order on every rank
+                    msm_futs.append(self.pool["pri"].submit(self._msm_sharded, *args))
+                    owners.append(None)
+                else:
+                    owner = len(owners) % self.world
+                    msm_futs.append(self.pool[pool].submit(self._msm_local, *args) if owner == self.rank else None)
+                    owners.append(owner)
+        outs = [f.result() if f is not None else None for f in msm_futs]
+        if self.world > 1 and any(o is not None for o in owners):
+            outs = self._exchange_points(outs, owners)
         if not resident:
             doc_tab.free()
             T_tab.free()
@@ -488,11 +528,14 @@ def run_reef(args):
     for bases, n in ((gp.bases_pri, w["n_pri"]), (gp.bases_sec, w["n_sec"])):
         Wn, c = bases.windows, bases.window_bits
         ops += 2 * w["steps"] * K * (10.0 * n * Wn + 14.0 * Wn * (1 << c)) / max(1, world)
-        n_terms += 2 * w["steps"] * K * n
+        n_terms += 2 * w["steps"] * K * n / max(1, world)
     msm = {"bound": "int-alu (255-bit modmul)", "mops": round(n_terms / (msm_ms / 1e3) / 1e6, 2) if msm_ms else None,
            "achieved_modmul_per_s": round(ops / (msm_ms / 1e3), 0) if msm_ms else None, "peak_modmul_per_s": peaks["modmul_per_s"],
            "frac": round(ops / (msm_ms / 1e3) / peaks["modmul_per_s"], 4) if msm_ms else None,
            "peak_source": "tools/bench_fp.cu on this pool (profiles/peak_modmul.json)"}
+    # the same MSM kernels on a throughput-sized instance (uniform 255-bit scalars), alone on the GPU
+    if world == 1 and args.msm_large_log2:
+        msm["large"] = msm_large(ctxs["pri"], args.msm_large_log2, peaks["modmul_per_s"])
     h2d, d2h = gp.bytes_per_step()
     out = {
         "metric": "NFA steps/s proved (= doc_len / hot-path prove time)", "value": round(value, 1), "unit": "NFA steps/s",
@@ -503,8 +546,9 @@ def run_reef(args):
                    "timing": "CUDA events: start on an idle stream, end = latest of the 4 library streams; max over ranks",
                    "streams": "4 contexts/streams: nl sum-check | nldoc sum-check | Pallas MSMs | Vesta MSMs (fold i+1 sum-checks overlap fold i commitments)",
                    "parallelism": (f"1 document of {w['doc_len']} chars: nldoc sum-check sharded by low index bits x{world} "
-                                   f"(96-byte all-gather per round), MSMs sharded by Pippenger windows x{world} "
-                                   f"(128-byte all-gather per MSM)") if world > 1 else "single GPU"},
+                                   f"(96-byte all-gather per round); fold commitments (2^14-2^15 terms, latency-bound) distributed "
+                                   f"whole, round-robin over the ranks, results exchanged once per pass; MSMs with >= 2^22 "
+                                   f"digit entries are sharded by Pippenger windows (128-byte all-gather)") if world > 1 else "single GPU"},
         "e2e": {"value": round(e2e_value, 1), "unit": "NFA steps/s", "ms_per_step": round(e2e_ms / K, 4),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "msm": msm,
@@ -519,6 +563,39 @@ def run_reef(args):
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def msm_large(ctx, lg, peak):
+    """MSM Mop/s vs the modmul roofline at n = 2^lg (BASELINE.json metric, second half)."""
+    import torch
+    import reef_b200
+    from oracle.curves import PALLAS           # input generation only
+    n = 1 << lg
+    pts = PALLAS.multiples(n)
+    bases = reef_b200.Bases(ctx, "pallas", b"".join(le32(P[0]) + le32(P[1]) for P in pts))
+    raw = np.random.default_rng(lg).integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
+    raw[:, 3] &= (1 << 61) - 1
+    dev = torch.from_numpy(raw.view(np.int64)).cuda()
+    out = C.create_string_buffer(64)
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    for _ in range(3):
+        reef_b200._lib.check(reef_b200.lib.reef_msm_dev(ctx._h, bases._h, C.c_void_p(dev.data_ptr()), n, out))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(reps):
+        reef_b200._lib.check(reef_b200.lib.reef_msm_dev(ctx._h, bases._h, C.c_void_p(dev.data_ptr()), n, out))
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    Wn, c = bases.windows, bases.window_bits
+    ops = 10.0 * n * Wn + 14.0 * Wn * (1 << c)
+    res = {"n": n, "curve": "pallas", "window_bits": c, "windows": Wn, "ms": round(ms, 3), "mops": round(n / ms / 1e3, 1),
+           "achieved_modmul_per_s": round(ops / (ms / 1e3), 0), "frac": round(ops / (ms / 1e3) / peak, 4),
+           "scalars": "uniform 255-bit, resident; bases k*G resident with all window levels precomputed"}
+    bases.free()
+    return res
 
 
 # --------------------------------------------------------------------------------------------
@@ -601,6 +678,7 @@ def main():
     ap.add_argument("--workload", default="target", choices=sorted(WORKLOADS))
     ap.add_argument("--also", default="cfg2", help="second workload timed (value/e2e only) and reported under 'also'; '' = none")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--msm-large-log2", type=int, default=20, help="size of the stand-alone MSM roofline measurement (0 = skip)")
     ap.add_argument("--debug", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "reef":

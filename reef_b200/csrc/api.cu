@@ -199,6 +199,7 @@ void reef_shutdown(reef_ctx* c) {
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->d_pos) cudaFree(c->d_pos);
   for (auto& kv : c->table_cache) cudaFree(kv.second);
+  if (c->shard_cache) cudaFree(c->shard_cache);
   cudaStreamDestroy(c->stream);
   delete c;
 }

@@ -160,6 +160,9 @@ struct reef_ctx {
   // device buffers of freed tables, reused by the next upload of the same size: a prover re-uploads
   // a same-sized table per proof, and cudaMalloc/cudaFree synchronise the whole device
   std::vector<std::pair<size_t, void*>> table_cache;
+  // one retired buffer of a sharded sum-check session, reused by the next session (same reason)
+  void* shard_cache = nullptr;
+  size_t shard_cache_bytes = 0;
   // optional per-kernel-class event timing (reef_profile_enable); resolved lazily
   bool profile = false;
   std::vector<reef::ProfRec> prof;

@@ -1067,6 +1067,7 @@ __global__ void __launch_bounds__(32) k_shard_final(NlState* st, const Fq* __res
 struct reef_nl_session {
   reef_ctx* ctx;
   void* d_buf;
+  size_t buf_bytes;
   const void* d_table;
   int is_u32;
   uint64_t n_loc;
@@ -1108,10 +1109,19 @@ int nl_shard_begin(reef_ctx* c, const NlookupArgs& a, uint32_t rank, uint32_t wo
   size_t o_fold = take(sweeps ? (n_loc / 2) * 32 : 32);
   size_t o_Ts = take((size_t)CHUNK * 32), o_Es = take((size_t)CHUNK * 32);
   void* buf = nullptr;
-  cudaError_t e = cudaMalloc(&buf, off);
-  if (e != cudaSuccess) return fail(REEF_ENOMEM, std::string("nl_shard_begin: ") + cudaGetErrorString(e));
+  size_t buf_bytes = off;
+  if (c->shard_cache && c->shard_cache_bytes >= off) {
+    buf = c->shard_cache;
+    buf_bytes = c->shard_cache_bytes;
+    c->shard_cache = nullptr;
+    c->shard_cache_bytes = 0;
+  } else {
+    cudaError_t e = cudaMalloc(&buf, off);
+    if (e != cudaSuccess) return fail(REEF_ENOMEM, std::string("nl_shard_begin: ") + cudaGetErrorString(e));
+  }
   char* d = (char*)buf;
   reef_nl_session* s = new reef_nl_session;
+  s->buf_bytes = buf_bytes;
   s->ctx = c;
   s->d_buf = buf;
   s->d_table = a.d_table;
@@ -1247,8 +1257,18 @@ int nl_shard_finish(reef_nl_session* s, const void* d_pairs, uint8_t* out_claim_
 
 void nl_shard_free(reef_nl_session* s) {
   if (!s) return;
-  cudaStreamSynchronize(s->ctx->stream);
-  cudaFree(s->d_buf);
+  reef_ctx* c = s->ctx;
+  cudaStreamSynchronize(c->stream);
+  if (!c->shard_cache) {
+    c->shard_cache = s->d_buf;
+    c->shard_cache_bytes = s->buf_bytes;
+  } else if (c->shard_cache_bytes < s->buf_bytes) {
+    cudaFree(c->shard_cache);
+    c->shard_cache = s->d_buf;
+    c->shard_cache_bytes = s->buf_bytes;
+  } else {
+    cudaFree(s->d_buf);
+  }
   delete s;
 }
 

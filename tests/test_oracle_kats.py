@@ -112,6 +112,9 @@ def test_logmn_f32_semantics():
     assert logmn(1) == 1 and logmn(2) == 1 and logmn(3) == 2 and logmn(11) == 4
     assert logmn(1 << 20) == 20 and logmn((1 << 20) + 2) == 21
     assert logmn((1 << 23) + 1) == 23          # f32 rounding quirk (costs.rs:13)
+    # consequence: a document of exactly 2^22 (or 2^23) characters cannot be padded -- the reference's
+    # `base.pow(logmn(len)) - len` underflows (framework.rs:1007); 2^21 + 2 is still rounded up correctly
+    assert logmn((1 << 21) + 2) == 22 and logmn((1 << 22) + 2) == 22 and logmn((1 << 22) + 66) == 23
 
 
 def test_doc_transform_ascii_dna():

@@ -345,44 +345,54 @@ class GpuPass:
 
 
 def sample_clocks_start():
+    """nvidia-smi sampler (20 ms period) running across the value and the profiled legs; the samples
+    are later restricted to the wall-clock windows of the timed regions."""
     path = tempfile.mktemp(suffix=".csv")
     try:
-        p = subprocess.Popen(["nvidia-smi", "--query-gpu=index,clocks.sm,clocks.max.sm,power.draw,"
+        p = subprocess.Popen(["nvidia-smi", "--query-gpu=timestamp,index,clocks.sm,clocks.max.sm,power.draw,"
                               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
                               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
-                              "--format=csv,noheader,nounits", "-lms", "100"], stdout=open(path, "w"), stderr=subprocess.DEVNULL)
+                              "--format=csv,noheader,nounits", "-lms", "20"], stdout=open(path, "w"), stderr=subprocess.DEVNULL)
     except Exception:
         return None, path
     return p, path
 
 
-def sample_clocks_stop(p, path, device=0):
+def sample_clocks_stop(p, path, device=0, windows=()):
+    import datetime
     if p is None:
         return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-    time.sleep(0.15)
+    time.sleep(0.05)
     p.terminate()
     try:
         p.wait(timeout=5)
     except Exception:
         p.kill()
-    sm, mx, reasons = [], None, set()
+    rows, mx = [], None
     for line in open(path):
         f = [x.strip() for x in line.split(",")]
-        if len(f) < 8 or not f[0].isdigit() or int(f[0]) != device:
+        if len(f) < 9 or not f[1].isdigit() or int(f[1]) != device:
             continue
         try:
-            sm.append(float(f[1]))
-            mx = float(f[2])
+            ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            sm = float(f[2])
+            mx = float(f[3])
         except ValueError:
             continue
-        for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-            if val.lower().startswith("active"):
-                reasons.add(name)
+        rs = [name for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9])
+              if val.lower().startswith("active")]
+        rows.append((ts, sm, rs))
     try:
         os.unlink(path)
     except OSError:
         pass
-    return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+    inside = [r for r in rows if any(a - 0.02 <= r[0] <= b + 0.02 for a, b in windows)]
+    scope = "timed regions"
+    if not inside:                      # timed regions shorter than the sampling period: the whole measured run
+        inside, scope = rows, "whole measurement (warm-up + timed steps)"
+    reasons = sorted({x for r in inside for x in r[2]})
+    return {"sm_mhz": statistics.median([r[1] for r in inside]) if inside else None, "sm_max_mhz": mx, "reasons": reasons,
+            "samples": len(inside), "scope": scope}
 
 
 def load_peaks():
@@ -440,10 +450,10 @@ def run_reef(args):
         launches0 = int(reef_b200.lib.reef_launch_count())
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = {k: torch.cuda.Event(enable_timing=True) for k in streams}
-        clk = sample_clocks_start() if profile else (None, None)
         barrier()
         e0.record(streams["doc"])               # every stream is idle here (barrier above)
         t0 = time.perf_counter()
+        w0 = time.time()
         per_step = []
         for _ in range(steps):
             flush.fill_(1)                      # L2 flush between steps; run() returns only after all streams drained
@@ -457,13 +467,14 @@ def run_reef(args):
             e1[k].record(streams[k])
         barrier()
         wall = time.perf_counter() - t0
+        clock_windows.append((w0, time.time()))
         ms = max(e0.elapsed_time(e1[k]) for k in streams)
         if world > 1:
             tt = torch.tensor([ms], device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt.item())
         launches = int(reef_b200.lib.reef_launch_count()) - launches0
-        clocks = sample_clocks_stop(*clk, device=dev) if profile else None
+        clocks = None
         prof = None
         if profile:
             n = 9
@@ -478,8 +489,11 @@ def run_reef(args):
     K, Wm = args.steps, args.warmup
     # value: unprofiled run (event recording around every launch group costs host time);
     # a second, profiled run of the same K steps feeds the per-kernel figures and the clocks.
+    clock_windows = []
+    clk = sample_clocks_start() if rank == 0 else (None, None)
     ms, wall_ms, launches, _, _ = timed(gp, True, K, Wm, False)
-    _, _, _, clocks, prof = timed(gp, True, K, 1, True)
+    _, _, _, _, prof = timed(gp, True, K, 1, True)
+    clocks = sample_clocks_stop(*clk, device=dev, windows=clock_windows) if rank == 0 else None
     e2e_ms, _, _, _, _ = timed(gp, False, K, max(1, Wm // 2), False)
     also = None
     if world == 1 and args.also and args.also != args.workload:
@@ -514,11 +528,15 @@ def run_reef(args):
     roof = {"bound": "hbm", "kernel": "k_sweep (MLE fold+accumulate passes)", "achieved": round(achieved, 1),
             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": None,
             "peak_source": peaks["source"], "launches": prof[0][0] + prof[1][0],
+            "alg_bytes_per_launch": round(sweep_bytes / max(1, prof[0][0] + prof[1][0])),
             "avg_launch_us": round(1e3 * sweep_ms / max(1, prof[0][0] + prof[1][0]), 2)}
     tr = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     if os.path.exists(tr):
         try:
-            roof["traffic"] = json.load(open(tr)).get(args.workload)
+            tinfo = json.load(open(tr)).get(args.workload)
+            if tinfo:
+                roof["traffic"] = tinfo["dram_bytes_per_launch"]           # ncu --set full, DRAM read+write per launch
+                roof["traffic_source"] = tinfo["source"]
         except Exception:
             pass
     # MSM: ops_alg = 10 n W + 14 W 2^c modmuls, against the measured modmul peak

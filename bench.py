@@ -143,6 +143,10 @@ class GpuPass:
         self.rank, self.world, self.dist = rank, world, dist
         self.bases_pri = reef_b200.Bases(ctxs["pri"], "pallas", w["bases_pri"])
         self.bases_sec = reef_b200.Bases(ctxs["sec"], "vesta", w["bases_sec"])
+        # commit(T) gets its own context (generators registered there too): it only waits for the
+        # cross-term scalars, not for commit(W), so the two commitments of a curve overlap
+        self.bases_pri2 = reef_b200.Bases(ctxs["pri2"], "pallas", w["bases_pri"])
+        self.bases_sec2 = reef_b200.Bases(ctxs["sec2"], "vesta", w["bases_sec"])
         self.ell_doc = reef_b200.logmn(len(w["udoc"]))
         self.ell_T = w["t_log"]
         self.pool = {k: ThreadPoolExecutor(max_workers=1) for k in ctxs}
@@ -206,9 +210,15 @@ class GpuPass:
         res = sn.run(self._gather, self.gbuf.data_ptr())
         sn.free()
         nxt = le32(res.next_running_claim)
-        d = C.create_string_buffer(32)
-        self.check(self.lib.reef_calc_d(self.ctxs["doc"]._h, nxt, self.salt, d))
+        self.d_futs.append(self.pool["aux"].submit(self._calc_d, nxt))
         return pack(res.next_running_q), nxt
+
+    def _calc_d(self, v):
+        # calc_d of a new running claim (framework.rs:517-553): an input of the step circuit only, the
+        # next fold's sum-check does not wait for it
+        d = C.create_string_buffer(32)
+        self.check(self.lib.reef_calc_d(self.ctxs["aux"]._h, v, self.salt, d))
+        return d.raw
 
     def _nlookup(self, key, tab, q_arr, v_bytes, prev):
         o, b = self.o[key], self.bufs[key]
@@ -222,8 +232,7 @@ class GpuPass:
         rounds = b["rounds"].raw
         next_q = b"".join(rounds[i * 128:i * 128 + 32] for i in range(ell))
         nxt = b["nxt"].raw
-        d = C.create_string_buffer(32)
-        self.check(self.lib.reef_calc_d(ctx._h, nxt, self.salt, d))      # calc_d of the new running claim
+        self.d_futs.append(self.pool["aux"].submit(self._calc_d, nxt))
         return next_q, nxt
 
     # An MSM is window-sharded across the ranks only when it is large enough to be throughput-bound
@@ -288,6 +297,7 @@ class GpuPass:
             doc_tab, T_tab = f1.result(), f2.result()
         prev_nl = prev_doc = None
         msm_futs, owners = [], []
+        self.d_futs = []
         for s in range(w["steps"]):
             qn, qd = self.q_nl[s], self.q_doc[s]
             f_nl = self.pool["nl"].submit(self._nlookup, "nl", T_tab, qn[0], qn[1], prev_nl)
@@ -298,7 +308,7 @@ class GpuPass:
             prev_nl, prev_doc = f_nl.result(), f_doc.result()
             sc, scd = w["sc"][s], (self.sc_dev[s] if resident else None)
             for key, pool, bases, n in (("Wp", "pri", self.bases_pri, w["n_pri"]), ("Ws", "sec", self.bases_sec, w["n_sec"]),
-                                        ("Tp", "pri", self.bases_pri, w["n_pri"]), ("Ts", "sec", self.bases_sec, w["n_sec"])):
+                                        ("Tp", "pri2", self.bases_pri2, w["n_pri"]), ("Ts", "sec2", self.bases_sec2, w["n_sec"])):
                 args = (bases, scd[key] if resident else None, sc[key], n, resident)
                 if self.world == 1:
                     msm_futs.append(self.pool[pool].submit(self._msm_local, *args))
@@ -312,12 +322,13 @@ class GpuPass:
                     msm_futs.append(self.pool[pool].submit(self._msm_local, *args) if owner == self.rank else None)
                     owners.append(owner)
         outs = [f.result() if f is not None else None for f in msm_futs]
+        ds = [f.result() for f in self.d_futs]
         if self.world > 1 and any(o is not None for o in owners):
             outs = self._exchange_points(outs, owners)
         if not resident:
             doc_tab.free()
             T_tab.free()
-        return prev_nl, prev_doc, outs
+        return prev_nl, prev_doc, outs, ds
 
     def _upload_T(self):
         h = C.c_void_p()
@@ -423,7 +434,8 @@ def run_reef(args):
     else:
         torch.cuda.set_device(0)
     dev = local if world > 1 else 0
-    ctxs = {k: reef_b200.Context(dev) for k in ("nl", "doc", "pri", "sec")}
+    # one context (= one CUDA stream + one host thread) per independent chain of a fold
+    ctxs = {k: reef_b200.Context(dev) for k in ("nl", "doc", "pri", "sec", "pri2", "sec2", "aux")}
     # weak scaling: ONE document of base_len * G characters.  Its nldoc sum-check is sharded by
     # low index bits (rank g holds udoc[g::G]); the fold commitments are sharded by Pippenger
     # windows; the tiny T-table sum-check is replicated.
@@ -561,8 +573,9 @@ def run_reef(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 limbs (255-bit prime fields Fq/Fp, exact integer)",
         "data": "synthetic",
         "config": {"workload": args.workload + ": " + w["desc"], "l2": "256 MiB buffer written between steps (L2 flush)",
-                   "timing": "CUDA events: start on an idle stream, end = latest of the 4 library streams; max over ranks",
-                   "streams": "4 contexts/streams: nl sum-check | nldoc sum-check | Pallas MSMs | Vesta MSMs (fold i+1 sum-checks overlap fold i commitments)",
+                   "timing": "CUDA events: start on an idle stream, end = latest of the library streams; max over ranks",
+                   "streams": "7 contexts/streams: nl sum-check | nldoc sum-check | commit(W) Pallas | commit(W) Vesta | commit(T) Pallas | commit(T) Vesta | calc_d "
+                              "(fold i+1 sum-checks overlap fold i commitments; commit(T) does not wait for commit(W); calc_d does not gate the next fold)",
                    "parallelism": (f"1 document of {w['doc_len']} chars: nldoc sum-check sharded by low index bits x{world} "
                                    f"(96-byte all-gather per round); fold commitments (2^14-2^15 terms, latency-bound) distributed "
                                    f"whole, round-robin over the ranks, results exchanged once per pass; MSMs with >= 2^22 "

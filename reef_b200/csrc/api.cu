@@ -145,6 +145,8 @@ static void hosttest_field_op(int op, const uint8_t* a, const uint8_t* b, uint8_
       F29 a = f29_from_mont256<C>(to_mont<C>(x), k), b = f29_from_mont256<C>(to_mont<C>(y), k);
       F29 s = f29_relax(f29_add_lazy(f29_add_lazy(a, b), a));                    // 2a + b, relaxed
       F29 t = mul29<C>(f29_add_lazy(a, b), s);                                   // (a+b)(2a+b), lazy operand
+      const F29 q = sqr29<C>(f29_add_lazy(a, b));                                // (a+b)^2, lazy operand
+      t = f29_relax(f29_add_lazy(t, q));                                         // (a+b)(2a+b) + (a+b)^2
       r = from_mont<C>(f29_to_mont256<C>(t));
       break;
     }

@@ -91,25 +91,35 @@ __device__ __forceinline__ void block_sum(Fq* vals, Fq* smem /* NV * NTHREADS/32
 // ---------------------------------------------------------------------------------------
 // k_nl_begin: first absorb + claim_r, powers of claim_r, sparse list, selector table
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_nl_begin(NlState* st, const Fq* __restrict__ query, uint32_t n_query, Fq tag,
+__global__ void __launch_bounds__(64) k_nl_begin(NlState* st, const Fq* __restrict__ query, uint32_t n_query, Fq tag,
                                                  const Fq* __restrict__ prev_q, uint32_t ell, const uint64_t* __restrict__ q,
                                                  uint32_t m, uint64_t* __restrict__ sp_pos, Fq* __restrict__ sp_w,
                                                  const PoseidonTables* __restrict__ K, uint32_t rank, uint32_t world) {
-  const int lane = threadIdx.x;
+  // 64 threads: warp 0 owns the sponge state, warp 1 is its partner inside poseidon_permute_pair
+  // (both warps follow the same control flow; only warp 0 touches the data).
+  const int lane = threadIdx.x & 31;
+  const bool A = threadIdx.x < 32;
   Fq s = fe_zero<FqCfg>();
-  if (lane == 0) s = tag;
+  if (A && lane == 0) s = tag;
   uint32_t apos = 0;
   for (uint32_t e = 0; e < n_query; e++) {
     if (apos == 4) {
-      poseidon_permute_warp5(s, K);
+      poseidon_permute_pair(s, K);
       apos = 0;
     }
-    Fq x = to_mont<FqCfg>(ld256(query + e));
-    Fq sum = fe_add<FqCfg>(s, x);
-    if (lane == (int)(1 + apos)) s = sum;
+    if (A) {
+      Fq x = to_mont<FqCfg>(ld256(query + e));
+      Fq sum = fe_add<FqCfg>(s, x);
+      if (lane == (int)(1 + apos)) s = sum;
+    }
     apos++;
   }
-  poseidon_permute_warp5(s, K);   // squeeze(1): always permutes after an absorb
+  poseidon_permute_pair(s, K);    // squeeze(1): always permutes after an absorb
+  if (!A) {
+    // last_q[j] = prev_running_q[ell-1-j]   (r1cs.rs:2318-2319 passes the reversed vector)
+    for (uint32_t j = lane; j < ell; j += 32) st->lq_mont[j] = to_mont<FqCfg>(ld256(prev_q + (ell - 1 - j)));
+    return;
+  }
   if (lane < 5) st->sponge[lane] = s;
   Fq claim = shfl_fq(s, 1);       // Montgomery form
   if (lane == 0) {
@@ -123,8 +133,6 @@ __global__ void __launch_bounds__(32) k_nl_begin(NlState* st, const Fq* __restri
     }
     st->rm_mont = pw;             // rs[m]
   }
-  // last_q[j] = prev_running_q[ell-1-j]   (r1cs.rs:2318-2319 passes the reversed vector)
-  for (uint32_t j = lane; j < ell; j += 32) st->lq_mont[j] = to_mont<FqCfg>(ld256(prev_q + (ell - 1 - j)));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -376,25 +384,33 @@ k_round(NlState* st, const Fq* __restrict__ partials, uint32_t nblk, const void*
     }
   }
   block_sum<3, ROUND_THREADS>(acc, red);
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    Fq con = shfl_fq(acc[0], 0), g1 = shfl_fq(acc[1], 0), xsq = shfl_fq(acc[2], 0);
-    Fq x = fe_sub<FqCfg>(fe_sub<FqCfg>(g1, con), xsq);
-    // absorb [const, x, xsq] at rate positions 0,1,2 (absorb_pos is 0 after the previous squeeze)
-    Fq s = lane < 5 ? st->sponge[lane] : fe_zero<FqCfg>();
-    Fq e = lane == 1 ? con : (lane == 2 ? x : xsq);
-    Fq sum = fe_add<FqCfg>(s, to_mont<FqCfg>(e));
-    if (lane >= 1 && lane <= 3) s = sum;
-    poseidon_permute_warp5(s, K);
-    if (lane < 5) st->sponge[lane] = s;
-    Fq r = shfl_fq(s, 1);
-    if (lane == 0) {
-      st->r_mont = r;
-      r_sh = r;
-      st->out_rounds[ri][0] = from_mont<FqCfg>(r);
-      st->out_rounds[ri][1] = xsq;
-      st->out_rounds[ri][2] = x;
-      st->out_rounds[ri][3] = con;
+  if (threadIdx.x < 64) {       // warp 0: transcript; warp 1: its partner inside the permutation
+    const int lane = threadIdx.x & 31;
+    const bool A = threadIdx.x < 32;
+    Fq s = fe_zero<FqCfg>(), con = s, x = s, xsq = s;
+    if (A) {
+      con = shfl_fq(acc[0], 0);
+      const Fq g1 = shfl_fq(acc[1], 0);
+      xsq = shfl_fq(acc[2], 0);
+      x = fe_sub<FqCfg>(fe_sub<FqCfg>(g1, con), xsq);
+      // absorb [const, x, xsq] at rate positions 0,1,2 (absorb_pos is 0 after the previous squeeze)
+      s = lane < 5 ? st->sponge[lane] : fe_zero<FqCfg>();
+      const Fq e = lane == 1 ? con : (lane == 2 ? x : xsq);
+      const Fq sum = fe_add<FqCfg>(s, to_mont<FqCfg>(e));
+      if (lane >= 1 && lane <= 3) s = sum;
+    }
+    poseidon_permute_pair(s, K);
+    if (A) {
+      if (lane < 5) st->sponge[lane] = s;
+      const Fq r = shfl_fq(s, 1);
+      if (lane == 0) {
+        st->r_mont = r;
+        r_sh = r;
+        st->out_rounds[ri][0] = from_mont<FqCfg>(r);
+        st->out_rounds[ri][1] = xsq;
+        st->out_rounds[ri][2] = x;
+        st->out_rounds[ri][3] = con;
+      }
     }
   }
   __syncthreads();
@@ -457,27 +473,35 @@ k_tail(NlState* st, const void* __restrict__ Tin, uint64_t L_in, int do_fold, co
       acc[2] = fe_add<FqCfg>(acc[2], mont_mul<FqCfg>(fe_sub<FqCfg>(e1, e0), fe_sub<FqCfg>(t1, t0)));
     }
     block_sum<3, TAIL_THREADS>(acc, red);
-    if (threadIdx.x < 32) {
-      const int lane = threadIdx.x;
-      Fq con = shfl_fq(acc[0], 0), g1 = shfl_fq(acc[1], 0), xsq = shfl_fq(acc[2], 0);
-      Fq x = fe_sub<FqCfg>(fe_sub<FqCfg>(g1, con), xsq);
-      Fq s = lane < 5 ? st->sponge[lane] : fe_zero<FqCfg>();
-      Fq e = lane == 1 ? con : (lane == 2 ? x : xsq);
-      Fq sum = fe_add<FqCfg>(s, to_mont<FqCfg>(e));
-      if (lane >= 1 && lane <= 3) s = sum;
-      poseidon_permute_warp5(s, K);
-      if (lane < 5) st->sponge[lane] = s;
-      Fq r = shfl_fq(s, 1);
-      if (lane == 0) {
-        r_sh = r;
-        st->r_mont = r;
-        st->out_rounds[ri][0] = from_mont<FqCfg>(r);
-        st->out_rounds[ri][1] = xsq;
-        st->out_rounds[ri][2] = x;
-        st->out_rounds[ri][3] = con;
-        last_xsq = xsq;
-        last_x = x;
-        last_con = con;
+    if (threadIdx.x < 64) {     // warp 0: transcript; warp 1: its partner inside the permutation
+      const int lane = threadIdx.x & 31;
+      const bool A = threadIdx.x < 32;
+      Fq s = fe_zero<FqCfg>(), con = s, x = s, xsq = s;
+      if (A) {
+        con = shfl_fq(acc[0], 0);
+        const Fq g1 = shfl_fq(acc[1], 0);
+        xsq = shfl_fq(acc[2], 0);
+        x = fe_sub<FqCfg>(fe_sub<FqCfg>(g1, con), xsq);
+        s = lane < 5 ? st->sponge[lane] : fe_zero<FqCfg>();
+        const Fq e = lane == 1 ? con : (lane == 2 ? x : xsq);
+        const Fq sum = fe_add<FqCfg>(s, to_mont<FqCfg>(e));
+        if (lane >= 1 && lane <= 3) s = sum;
+      }
+      poseidon_permute_pair(s, K);
+      if (A) {
+        if (lane < 5) st->sponge[lane] = s;
+        const Fq r = shfl_fq(s, 1);
+        if (lane == 0) {
+          r_sh = r;
+          st->r_mont = r;
+          st->out_rounds[ri][0] = from_mont<FqCfg>(r);
+          st->out_rounds[ri][1] = xsq;
+          st->out_rounds[ri][2] = x;
+          st->out_rounds[ri][3] = con;
+          last_xsq = xsq;
+          last_x = x;
+          last_con = con;
+        }
       }
     }
     __syncthreads();
@@ -559,7 +583,7 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
   Fq tag = fq_mont_from_le32(a.tag_le);
   {
     ProfScope ps(c, PROF_NL_SETUP, N);
-    k_nl_begin<<<1, 32, 0, s>>>(st, d_query, a.n_query, tag, d_prevq, ell, d_q, m, d_pos, d_w, c->d_pos, 0, 1);
+    k_nl_begin<<<1, 64, 0, s>>>(st, d_query, a.n_query, tag, d_prevq, ell, d_q, m, d_pos, d_w, c->d_pos, 0, 1);
     REEF_LAUNCHED();
     k_eq_tables<<<ceil_div_u(a_len + b_len, 128), 128, 0, s>>>(st, ell, hb, d_A, a_len, d_B, b_len, 0, 0);
     REEF_LAUNCHED();
@@ -896,31 +920,40 @@ k_shard_local(const Fq* __restrict__ partials, uint32_t nblk, const void* __rest
     for (int k = 0; k < 3; k++) st256(out3 + k, acc[k]);
 }
 
-// warp-level: sum the G gathered triples, absorb [const, x, xsq], squeeze r, record the round
+// warps 0 and 1 together (threadIdx.x < 64): warp 0 sums the G gathered triples, absorbs
+// [const, x, xsq], squeezes r and records the round; warp 1 is its partner inside the permutation.
+// The return value is meaningful on warp 0.
 __device__ __forceinline__ Fq shard_transcript(NlState* st, const Fq* __restrict__ triples, uint32_t G, uint32_t ri,
                                                const PoseidonTables* __restrict__ K) {
   const int lane = threadIdx.x & 31;
-  Fq con = fe_zero<FqCfg>(), g1 = con, xsq = con;
-  for (uint32_t g = 0; g < G; g++) {
-    // generic loads: `triples` may live in global (gathered) or shared (final rounds) memory
-    con = fe_add<FqCfg>(con, triples[(uint64_t)g * 3 + 0]);
-    g1 = fe_add<FqCfg>(g1, triples[(uint64_t)g * 3 + 1]);
-    xsq = fe_add<FqCfg>(xsq, triples[(uint64_t)g * 3 + 2]);
+  const bool A = threadIdx.x < 32;
+  Fq s = fe_zero<FqCfg>(), con = s, x = s, xsq = s;
+  if (A) {
+    Fq g1 = fe_zero<FqCfg>();
+    for (uint32_t g = 0; g < G; g++) {
+      // generic loads: `triples` may live in global (gathered) or shared (final rounds) memory
+      con = fe_add<FqCfg>(con, triples[(uint64_t)g * 3 + 0]);
+      g1 = fe_add<FqCfg>(g1, triples[(uint64_t)g * 3 + 1]);
+      xsq = fe_add<FqCfg>(xsq, triples[(uint64_t)g * 3 + 2]);
+    }
+    x = fe_sub<FqCfg>(fe_sub<FqCfg>(g1, con), xsq);
+    s = lane < 5 ? st->sponge[lane] : fe_zero<FqCfg>();
+    const Fq e = lane == 1 ? con : (lane == 2 ? x : xsq);
+    const Fq sum = fe_add<FqCfg>(s, to_mont<FqCfg>(e));
+    if (lane >= 1 && lane <= 3) s = sum;
   }
-  Fq x = fe_sub<FqCfg>(fe_sub<FqCfg>(g1, con), xsq);
-  Fq s = lane < 5 ? st->sponge[lane] : fe_zero<FqCfg>();
-  Fq e = lane == 1 ? con : (lane == 2 ? x : xsq);
-  Fq sum = fe_add<FqCfg>(s, to_mont<FqCfg>(e));
-  if (lane >= 1 && lane <= 3) s = sum;
-  poseidon_permute_warp5(s, K);
-  if (lane < 5) st->sponge[lane] = s;
-  Fq r = shfl_fq(s, 1);
-  if (lane == 0) {
-    st->r_mont = r;
-    st->out_rounds[ri][0] = from_mont<FqCfg>(r);
-    st->out_rounds[ri][1] = xsq;
-    st->out_rounds[ri][2] = x;
-    st->out_rounds[ri][3] = con;
+  poseidon_permute_pair(s, K);
+  Fq r = fe_zero<FqCfg>();
+  if (A) {
+    if (lane < 5) st->sponge[lane] = s;
+    r = shfl_fq(s, 1);
+    if (lane == 0) {
+      st->r_mont = r;
+      st->out_rounds[ri][0] = from_mont<FqCfg>(r);
+      st->out_rounds[ri][1] = xsq;
+      st->out_rounds[ri][2] = x;
+      st->out_rounds[ri][3] = con;
+    }
   }
   return r;
 }
@@ -931,7 +964,7 @@ k_shard_apply(NlState* st, const Fq* __restrict__ triples, uint32_t G, uint64_t 
               uint64_t* sp_pos, Fq* sp_w, uint32_t m, uint32_t ri, const PoseidonTables* __restrict__ K) {
   __shared__ Fq r_sh;
   const uint64_t half = L >> 1;
-  if (threadIdx.x < 32) {
+  if (threadIdx.x < 64) {
     Fq r = shard_transcript(st, triples, G, ri, K);
     if (threadIdx.x == 0) r_sh = r;
   }
@@ -996,7 +1029,7 @@ k_small_apply(NlState* st, const Fq* __restrict__ triples, uint32_t G, Fq* Ts, F
               const PoseidonTables* __restrict__ K) {
   __shared__ Fq r_sh;
   const uint64_t half = L >> 1;
-  if (threadIdx.x < 32) {
+  if (threadIdx.x < 64) {
     Fq r = shard_transcript(st, triples, G, ri, K);
     if (threadIdx.x == 0) r_sh = r;
   }
@@ -1019,41 +1052,49 @@ __global__ void k_shard_export(const Fq* __restrict__ Ts, const Fq* __restrict__
 
 // last gamma rounds over the G gathered (T, E) pairs (rank g's pair at index g), identical on
 // every rank; then last claim and next running claim.
-__global__ void __launch_bounds__(32) k_shard_final(NlState* st, const Fq* __restrict__ pairs, uint32_t G, uint32_t ri0,
+__global__ void __launch_bounds__(64) k_shard_final(NlState* st, const Fq* __restrict__ pairs, uint32_t G, uint32_t ri0,
                                                     const PoseidonTables* __restrict__ K) {
+  // warp 0 does the work; warp 1 only partners it inside shard_transcript's permutation
   __shared__ Fq Ts[64], Es[64], trip[3];
-  const int lane = threadIdx.x;
-  for (uint32_t g = lane; g < G; g += 32) {
-    Ts[g] = ld256(pairs + (uint64_t)g * 2);
-    Es[g] = to_mont<FqCfg>(ld256(pairs + (uint64_t)g * 2 + 1));
+  const int lane = threadIdx.x & 31;
+  const bool A = threadIdx.x < 32;
+  if (A) {
+    for (uint32_t g = lane; g < G; g += 32) {
+      Ts[g] = ld256(pairs + (uint64_t)g * 2);
+      Es[g] = to_mont<FqCfg>(ld256(pairs + (uint64_t)g * 2 + 1));
+    }
+    __syncwarp();
   }
-  __syncwarp();
   uint32_t ri = ri0;
   for (uint32_t L = G; L > 1; L >>= 1) {
     const uint32_t half = L >> 1;
-    Fq acc[3];
-    acc[0] = acc[1] = acc[2] = fe_zero<FqCfg>();
-    for (uint32_t b = lane; b < half; b += 32) {
-      Fq t0 = Ts[b], t1 = Ts[b + half], e0 = Es[b], e1 = Es[b + half];
-      acc[0] = fe_add<FqCfg>(acc[0], mont_mul<FqCfg>(e0, t0));
-      acc[1] = fe_add<FqCfg>(acc[1], mont_mul<FqCfg>(e1, t1));
-      acc[2] = fe_add<FqCfg>(acc[2], mont_mul<FqCfg>(fe_sub<FqCfg>(e1, e0), fe_sub<FqCfg>(t1, t0)));
-    }
+    if (A) {
+      Fq acc[3];
+      acc[0] = acc[1] = acc[2] = fe_zero<FqCfg>();
+      for (uint32_t b = lane; b < half; b += 32) {
+        Fq t0 = Ts[b], t1 = Ts[b + half], e0 = Es[b], e1 = Es[b + half];
+        acc[0] = fe_add<FqCfg>(acc[0], mont_mul<FqCfg>(e0, t0));
+        acc[1] = fe_add<FqCfg>(acc[1], mont_mul<FqCfg>(e1, t1));
+        acc[2] = fe_add<FqCfg>(acc[2], mont_mul<FqCfg>(fe_sub<FqCfg>(e1, e0), fe_sub<FqCfg>(t1, t0)));
+      }
 #pragma unroll
-    for (int k = 0; k < 3; k++) acc[k] = warp_sum_fe<FqCfg>(acc[k]);
-    if (lane == 0)
-      for (int k = 0; k < 3; k++) trip[k] = acc[k];
-    __syncwarp();
-    Fq r = shard_transcript(st, trip, 1, ri, K);
-    for (uint32_t b = lane; b < half; b += 32) {
-      Fq t0 = Ts[b], t1 = Ts[b + half], e0 = Es[b], e1 = Es[b + half];
-      Ts[b] = fold_one(t0, t1, r);
-      Es[b] = fe_add<FqCfg>(e0, mont_mul<FqCfg>(r, fe_sub<FqCfg>(e1, e0)));
+      for (int k = 0; k < 3; k++) acc[k] = warp_sum_fe<FqCfg>(acc[k]);
+      if (lane == 0)
+        for (int k = 0; k < 3; k++) trip[k] = acc[k];
+      __syncwarp();
     }
-    __syncwarp();
+    const Fq r = shard_transcript(st, trip, 1, ri, K);
+    if (A) {
+      for (uint32_t b = lane; b < half; b += 32) {
+        Fq t0 = Ts[b], t1 = Ts[b + half], e0 = Es[b], e1 = Es[b + half];
+        Ts[b] = fold_one(t0, t1, r);
+        Es[b] = fe_add<FqCfg>(e0, mont_mul<FqCfg>(r, fe_sub<FqCfg>(e1, e0)));
+      }
+      __syncwarp();
+    }
     ri++;
   }
-  if (lane == 0) {
+  if (threadIdx.x == 0) {
     const uint32_t last = ri - 1;
     const Fq r = st->r_mont;
     Fq t = fe_add<FqCfg>(mont_mul<FqCfg>(r, st->out_rounds[last][1]), st->out_rounds[last][2]);
@@ -1162,7 +1203,7 @@ int nl_shard_begin(reef_ctx* c, const NlookupArgs& a, uint32_t rank, uint32_t wo
       (a.m && cudaMemcpyAsync(s->d_q, a.h_q, (size_t)a.m * 8, cudaMemcpyHostToDevice, st) != cudaSuccess))
     return bail(fail(REEF_ECUDA, "nl_shard_begin: upload failed"));
   Fq tag = fq_mont_from_le32(a.tag_le);
-  k_nl_begin<<<1, 32, 0, st>>>(s->st, s->d_query, a.n_query, tag, s->d_prevq, a.ell, s->d_q, a.m, s->d_pos, s->d_w, c->d_pos, rank, world);
+  k_nl_begin<<<1, 64, 0, st>>>(s->st, s->d_query, a.n_query, tag, s->d_prevq, a.ell, s->d_q, a.m, s->d_pos, s->d_w, c->d_pos, rank, world);
   g_launches.fetch_add(1);
   k_eq_tables<<<ceil_div_u(a_len + b_len, 128), 128, 0, st>>>(s->st, ell_loc, hb, s->d_A, a_len, s->d_B, b_len, gamma, rank);
   g_launches.fetch_add(1);
@@ -1239,7 +1280,7 @@ int nl_shard_finish(reef_nl_session* s, const void* d_pairs, uint8_t* out_claim_
   REEF_REQUIRE(s->round == s->ell_loc, REEF_EASSERT, "nl_shard_finish: local rounds not finished");
   reef_ctx* c = s->ctx;
   cudaStream_t st = c->stream;
-  k_shard_final<<<1, 32, 0, st>>>(s->st, (const Fq*)d_pairs, s->world, s->ell_loc, c->d_pos);
+  k_shard_final<<<1, 64, 0, st>>>(s->st, (const Fq*)d_pairs, s->world, s->ell_loc, c->d_pos);
   REEF_LAUNCHED();
   void* hs;
   int rc = ctx_stage(c, sizeof(NlState), &hs);

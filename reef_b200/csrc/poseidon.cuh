@@ -188,8 +188,8 @@ __device__ __forceinline__ F29 sel29(bool c, const F29& a, const F29& b) {
 
 static __device__ __noinline__ void p29_full_round(F29& s, int r, int li, const Poseidon29Tables* T) {
   const F29 x = f29_add_lazy(s, ld29(&T->rc_full[r][li]));     // < 2^30 per limb
-  const F29 x2 = mul29<FqCfg>(x, x);
-  const F29 x4 = mul29<FqCfg>(x2, x2);
+  const F29 x2 = sqr29<FqCfg>(x);
+  const F29 x4 = sqr29<FqCfg>(x2);
   const F29 x5 = mul29<FqCfg>(x4, x);
   u64 col[18];
 #pragma unroll
@@ -275,6 +275,124 @@ __device__ __forceinline__ void poseidon_permute_warp5(Fq& s, const PoseidonTabl
 #pragma unroll 1
   for (int r = 4; r < 8; r++) p29_full_round(x, r, li, T);
   s = f29_to_mont256<FqCfg>(x);
+}
+
+// ---------------------------------------------------------------------------------------
+// Two-warp permutation for the transcript kernels (k_nl_begin, k_round, k_tail, sharded
+// rounds): warps 0 and 1 of the CTA call it together (all 64 threads).
+//   warp 0 ("A") owns the state (lanes 0..4, like poseidon_permute_warp5) and, during the 56
+//   partial rounds, runs NOTHING but lane 0's chain  w -> w^2 -> w^4 -> w^5  (two sqr29 + one
+//   mul29 per round: no selects, no shuffles, no constant loads);
+//   warp 1 ("B") carries s_1..s_4: ONE multiplication per round computes all twelve side
+//   products (lanes 0-3: beta*s, 4-7: (beta*D)*u, 8-11: D*u), sums sum_i beta_i s_i + kp and
+//   hands it over through shared memory; it receives u_r the same way.
+// One named barrier (id 1, 64 threads) per round, double-buffered exchange slots.
+// A partial round costs A ~790 instructions instead of ~1020 (tools/bench_perm.cu).
+// ---------------------------------------------------------------------------------------
+#ifdef REEF_PERM_TIMING
+__device__ long long reef_perm_timing[4];
+#endif
+struct PermPairShared {
+  u32 u[2][12];
+  u32 c[2][12];
+  u32 s[4][12];
+};
+
+__device__ __forceinline__ void perm_pair_barrier() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
+__device__ __forceinline__ void st29_shared(u32* dst, const F29& x) {
+#pragma unroll
+  for (int i = 0; i < 9; i++) dst[i] = x.l[i];
+}
+__device__ __forceinline__ F29 ld29_shared(const u32* src) {
+  F29 r;
+#pragma unroll
+  for (int i = 0; i < 9; i++) r.l[i] = src[i];
+  return r;
+}
+
+static __device__ __noinline__ void p29_partial_rounds_A(F29& w, PermPairShared* sh, int lane) {
+#pragma unroll 1
+  for (int r = 0; r < 56; r++) {
+    const F29 m1 = sqr29<FqCfg>(w);
+    const F29 m2 = sqr29<FqCfg>(m1);
+    const F29 u = mul29<FqCfg>(m2, w);
+    if (lane == 0) st29_shared(sh->u[r & 1], u);
+    perm_pair_barrier();
+    const F29 c = ld29_shared(sh->c[r & 1]);
+    w = f29_relax(f29_add_lazy(u, c));
+  }
+}
+
+static __device__ __noinline__ void p29_partial_rounds_B(PermPairShared* sh, int lane, const Poseidon29Tables* T) {
+  const int g = lane < 12 ? (lane >> 2) : 2;      // 0: beta * s   1: (beta D) * u   2: D * u
+  const int i = lane & 3;
+  F29 sp = ld29_shared(sh->s[i]);                 // s_i(r-1), relaxed, not reduced (meaningful on lanes 0..3)
+  F29 S = g == 0 ? sp : f29_zero();               // u_{-1} = 0
+#pragma unroll 1
+  for (int r = 0; r < 56; r++) {
+    const F29s* kp = g == 0 ? &T->beta[r][i] : (g == 1 ? &T->emat[r][i] : &T->dshift[r][i]);
+    const F29 k1 = ld29(kp);
+    const F29 kk = ld29(&T->kp[r + 1]);
+    const F29 t = mul29<FqCfg>(k1, S);
+    const F29 te = shfl29(t, (lane + 4) & 31);
+    const F29 td = shfl29(t, (lane + 8) & 31);
+    const F29 p = f29_relax(f29_add_lazy(t, te));            // beta_i * s_i(r)          (lanes 0..3)
+    sp = f29_relax(f29_add_lazy(sp, td));                     // s_i(r) = s_i(r-1) + D u  (lanes 0..3)
+    F29 v = sel29(lane < 4, p, f29_zero());
+    v = f29_add_lazy(v, shfl29(v, lane ^ 1));
+    v = f29_add_lazy(v, shfl29(v, lane ^ 2));
+    if (lane == 0) st29_shared(sh->c[r & 1], f29_add_lazy(v, kk));   // limbs < 5 * (2^29 + 8)
+    perm_pair_barrier();
+    const F29 ub = ld29_shared(sh->u[r & 1]);
+    S = g == 0 ? sp : ub;
+  }
+  // closing: s_i(56) = s_i(55) + dshift[56][i] * u_55 (S holds u_55 on lanes 8..11 only: reload)
+  const F29 ub = ld29_shared(sh->u[1]);                       // r = 55 wrote slot 1
+  const F29 t = mul29<FqCfg>(ld29(&T->dshift[56][i]), ub);
+  sp = f29_relax(f29_add_lazy(sp, t));
+  if (lane < 4) st29_shared(sh->s[lane], sp);
+}
+
+// warps 0 and 1 of the CTA, all lanes.  `s`: warp 0 lanes 0..4 = state (Montgomery-256), ignored on warp 1.
+__device__ __forceinline__ void poseidon_permute_pair(Fq& s, const PoseidonTables* K) {
+  __shared__ PermPairShared sh;
+  const int lane = threadIdx.x & 31;
+  const bool roleA = (threadIdx.x >> 5) == 0;
+  const Poseidon29Tables* T = &K->t29;
+  {
+    const char* base = reinterpret_cast<const char*>(T);
+    for (uint32_t off = (threadIdx.x & 63) * 128u; off < (uint32_t)sizeof(Poseidon29Tables); off += 64u * 128u)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(base + off));
+  }
+  if (roleA) {
+    const int li = lane < 5 ? lane : 4;
+    if (lane >= 5) s = fe_zero<FqCfg>();
+    F29 x = f29_from_mont256<FqCfg>(s, ld29(&T->k266));
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) p29_full_round(x, r, li, T);
+    if (lane >= 1 && lane <= 4) st29_shared(sh.s[lane - 1], x);
+    F29 w = f29_add_lazy(x, ld29(&T->kp[0]));
+    perm_pair_barrier();
+#ifdef REEF_PERM_TIMING
+    const long long tp0 = clock64();
+#endif
+    p29_partial_rounds_A(w, &sh, lane);
+#ifdef REEF_PERM_TIMING
+    if (lane == 0) reef_perm_timing[0] = clock64() - tp0;
+#endif
+    const F29 m = mul29<FqCfg>(ld29(&T->lam_end), w);
+    perm_pair_barrier();
+    x = lane == 0 ? m : ld29_shared(sh.s[(li > 0 ? li : 1) - 1]);
+    p29_post(x, li, T);
+#pragma unroll 1
+    for (int r = 4; r < 8; r++) p29_full_round(x, r, li, T);
+    s = f29_to_mont256<FqCfg>(x);
+  } else {
+    perm_pair_barrier();
+    p29_partial_rounds_B(&sh, lane, T);
+    perm_pair_barrier();
+  }
 }
 #endif  // __CUDACC__
 

@@ -47,7 +47,7 @@ def test_shared_field_code_host_instantiation(field, p):
         assert _op(field, 4, a, b) == (a * b + a * a + b * b) % p
         assert _op(field, 6, a, b) == (a & 0xFFFFFFFF) * b % p
         assert _op(field, 8, a % p, b % p) == a * b % p                     # 29-bit limb Montgomery (fp29.cuh)
-        assert _op(field, 9, a % p, b % p) == (a + b) * (2 * a + b) % p     # lazy/relaxed operands, via Montgomery-256
+        assert _op(field, 9, a % p, b % p) == ((a + b) * (2 * a + b) + (a + b) ** 2) % p   # mul29 + sqr29, lazy/relaxed operands
     for _ in range(10):
         a = rnd.randrange(1, p)
         assert _op(field, 3, a) == pow(a, -1, p)

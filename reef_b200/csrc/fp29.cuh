@@ -157,7 +157,7 @@ REEF_HD F29 redc29(u64* col) {
   return r;
 }
 
-// a * b / 2^261 mod p.  Operand limbs < 2^30, values < 8p  ->  result almost normalised, < 2p.
+// a * b / 2^261 mod p.  Operand limbs < 2^30 + 2^8, values < 2^7 p  ->  result almost normalised, < 2p.
 template <class C>
 REEF_HD F29 mul29(const F29& a, const F29& b) {
   u64 col[18];
@@ -167,7 +167,7 @@ REEF_HD F29 mul29(const F29& a, const F29& b) {
 }
 
 // a * a / 2^261 mod p: 36 doubled cross products + 9 squares instead of 81 products.
-// Operand limbs < 2^30 (a column then holds < 4 * 2^61 + 2^60 < 2^64).
+// Operand limbs < 2^30 + 2^8 (a column then holds < 4 * 2^61.01 + 2^60.01 + reduction terms < 2^63.4).
 template <class C>
 REEF_HD F29 sqr29(const F29& a) {
   u32 d[9];

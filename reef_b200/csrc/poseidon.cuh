@@ -186,21 +186,23 @@ __device__ __forceinline__ F29 sel29(bool c, const F29& a, const F29& b) {
   return r;
 }
 
-static __device__ __noinline__ void p29_full_round(F29& s, int r, int li, const Poseidon29Tables* T) {
+// Full round on lanes 0..4 (state) with the MDS product spread over 25 lanes: lane j + 5 i
+// computes mds[j][i] * x_i^5 with ONE multiplication, three lazy shuffle-adds bring row j back
+// to lane j (instead of five sequential 81-product passes per state lane).
+static __device__ __noinline__ void p29_full_round(F29& s, int r, int lane, const Poseidon29Tables* T) {
+  const int li = lane < 5 ? lane : 4;
+  const int mi = lane < 25 ? lane / 5 : 4, mj = lane < 25 ? lane % 5 : 4;
+  const F29 m = ld29(&T->mds[mj][mi]);                         // issued ahead of the S-box
   const F29 x = f29_add_lazy(s, ld29(&T->rc_full[r][li]));     // < 2^30 per limb
   const F29 x2 = sqr29<FqCfg>(x);
   const F29 x4 = sqr29<FqCfg>(x2);
   const F29 x5 = mul29<FqCfg>(x4, x);
-  u64 col[18];
-#pragma unroll
-  for (int k = 0; k < 18; k++) col[k] = 0;
-#pragma unroll 1
-  for (int i = 0; i < 5; i++) {
-    const F29 xi = shfl29(x5, i);
-    const F29 m = ld29(&T->mds[li][i]);
-    mul29_cols<true>(col, m, xi);                              // 45 products per column < 2^63.5
-  }
-  s = redc29<FqCfg>(col);
+  const F29 xi = shfl29(x5, mi);
+  const F29 t = mul29<FqCfg>(m, xi);
+  const F29 s1 = f29_add_lazy(t, shfl29(t, (lane + 5) & 31));
+  const F29 t20 = shfl29(t, (lane + 20) & 31);
+  const F29 s2 = f29_add_lazy(s1, shfl29(s1, (lane + 10) & 31));
+  s = f29_relax(f29_add_lazy(s2, t20));                        // 5 terms: limbs < 2^31.4, value < 10p
 }
 
 // One rescaled partial round, three multiplications deep, nothing else on the critical path.
@@ -231,19 +233,17 @@ static __device__ __noinline__ void p29_partial_round(F29& s, F29& ub, int r, in
   s = f29_relax(f29_add_lazy(m3, sel29(l0, c, w)));
 }
 
-static __device__ __noinline__ void p29_post(F29& s, int li, const Poseidon29Tables* T) {
-  const int row = li > 0 ? li - 1 : 0;
-  u64 col[18];
-#pragma unroll
-  for (int k = 0; k < 18; k++) col[k] = 0;
-#pragma unroll 1
-  for (int i = 1; i < 5; i++) {
-    const F29 si = shfl29(s, i);
-    const F29 m = ld29(&T->post[row][i - 1]);
-    mul29_cols<true>(col, m, si);
-  }
-  const F29 u = redc29<FqCfg>(col);
-  s = sel29(li == 0, s, u);
+// Dense 4x4 block after the partial rounds on state lanes 1..4, spread over lanes 1..16:
+// lane 1 + jj + 4 ii computes post[jj][ii] * s_{ii+1}; two lazy shuffle-adds land row jj on lane 1 + jj.
+static __device__ __noinline__ void p29_post(F29& s, int lane, const Poseidon29Tables* T) {
+  const int k = (lane >= 1 && lane <= 16) ? lane - 1 : 15;
+  const int jj = k & 3, ii = k >> 2;
+  const F29 m = ld29(&T->post[jj][ii]);
+  const F29 si = shfl29(s, ii + 1);
+  const F29 t = mul29<FqCfg>(m, si);
+  const F29 s1 = f29_add_lazy(t, shfl29(t, (lane + 4) & 31));
+  const F29 s2 = f29_relax(f29_add_lazy(s1, shfl29(s1, (lane + 8) & 31)));
+  s = sel29(lane == 0, s, s2);
 }
 
 // In/out: `s` = state element `lane` for lanes 0..4 (other lanes: don't care), Montgomery-256.
@@ -260,7 +260,7 @@ __device__ __forceinline__ void poseidon_permute_warp5(Fq& s, const PoseidonTabl
   if (lane >= 5) s = fe_zero<FqCfg>();
   F29 x = f29_from_mont256<FqCfg>(s, ld29(&T->k266));
 #pragma unroll 1
-  for (int r = 0; r < 4; r++) p29_full_round(x, r, li, T);
+  for (int r = 0; r < 4; r++) p29_full_round(x, r, lane, T);
   {
     F29 ub = f29_zero();
     if (lane == 0) x = f29_add_lazy(x, ld29(&T->kp[0]));
@@ -271,9 +271,9 @@ __device__ __forceinline__ void poseidon_permute_warp5(Fq& s, const PoseidonTabl
     const F29 m = mul29<FqCfg>(sel29(li == 0, ld29(&T->lam_end), ld29(&T->dshift[56][ci])), sel29(li == 0, x, ub));
     x = li == 0 ? m : f29_relax(f29_add_lazy(x, m));
   }
-  p29_post(x, li, T);
+  p29_post(x, lane, T);
 #pragma unroll 1
-  for (int r = 4; r < 8; r++) p29_full_round(x, r, li, T);
+  for (int r = 4; r < 8; r++) p29_full_round(x, r, lane, T);
   s = f29_to_mont256<FqCfg>(x);
 }
 
@@ -319,8 +319,8 @@ static __device__ __noinline__ void p29_partial_rounds_A(F29& w, PermPairShared*
     const F29 u = mul29<FqCfg>(m2, w);
     if (lane == 0) st29_shared(sh->u[r & 1], u);
     perm_pair_barrier();
-    const F29 c = ld29_shared(sh->c[r & 1]);
-    w = f29_relax(f29_add_lazy(u, c));
+    const F29 c = ld29_shared(sh->c[r & 1]);   // relaxed by warp B: limbs < 2^29 + 8
+    w = f29_add_lazy(u, c);                    // limbs < 2^30 + 2^8: still a valid sqr29 / mul29 operand
   }
 }
 
@@ -342,7 +342,7 @@ static __device__ __noinline__ void p29_partial_rounds_B(PermPairShared* sh, int
     F29 v = sel29(lane < 4, p, f29_zero());
     v = f29_add_lazy(v, shfl29(v, lane ^ 1));
     v = f29_add_lazy(v, shfl29(v, lane ^ 2));
-    if (lane == 0) st29_shared(sh->c[r & 1], f29_add_lazy(v, kk));   // limbs < 5 * (2^29 + 8)
+    if (lane == 0) st29_shared(sh->c[r & 1], f29_relax(f29_add_lazy(v, kk)));   // 5 terms, relaxed here (off A's path)
     perm_pair_barrier();
     const F29 ub = ld29_shared(sh->u[r & 1]);
     S = g == 0 ? sp : ub;
@@ -370,7 +370,7 @@ __device__ __forceinline__ void poseidon_permute_pair(Fq& s, const PoseidonTable
     if (lane >= 5) s = fe_zero<FqCfg>();
     F29 x = f29_from_mont256<FqCfg>(s, ld29(&T->k266));
 #pragma unroll 1
-    for (int r = 0; r < 4; r++) p29_full_round(x, r, li, T);
+    for (int r = 0; r < 4; r++) p29_full_round(x, r, lane, T);
     if (lane >= 1 && lane <= 4) st29_shared(sh.s[lane - 1], x);
     F29 w = f29_add_lazy(x, ld29(&T->kp[0]));
     perm_pair_barrier();
@@ -384,9 +384,9 @@ __device__ __forceinline__ void poseidon_permute_pair(Fq& s, const PoseidonTable
     const F29 m = mul29<FqCfg>(ld29(&T->lam_end), w);
     perm_pair_barrier();
     x = lane == 0 ? m : ld29_shared(sh.s[(li > 0 ? li : 1) - 1]);
-    p29_post(x, li, T);
+    p29_post(x, lane, T);
 #pragma unroll 1
-    for (int r = 4; r < 8; r++) p29_full_round(x, r, li, T);
+    for (int r = 4; r < 8; r++) p29_full_round(x, r, lane, T);
     s = f29_to_mont256<FqCfg>(x);
   } else {
     perm_pair_barrier();

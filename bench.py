@@ -10,6 +10,8 @@ the `--prove` run the reference would do (framework.rs:405-625 / 642-754):
     2 x calc_d                                         (framework.rs:517-553)
     prove_step commitments: commit(W), commit(T) on Pallas and on Vesta (framework.rs:668-675)
 metric  = NFA steps/s proved = doc_len / time of one pass        (BASELINE.json)
+workload = `target` by default: configs[1] at the 2^20-char document the north_star target names;
+          configs[1] at its own 2^16 chars is timed in the same run and reported under "also"
 value   = inputs resident in HBM when the timed region starts    (device timed, CUDA events)
 e2e     = the same pass through the C ABI with HOST buffers: document/table upload, scalar
           upload and result read-back inside the timed region
@@ -132,7 +134,7 @@ class GpuPass:
     def __init__(self, ctxs, w, rank=0, world=1, dist=None):
         """ctxs: dict of libreef_b200 contexts (one CUDA stream each): 'nl', 'doc', 'pri', 'sec'.
         The reference runs the sum-checks on its solver thread and the fold commitments on its
-        proving thread (framework.rs:98-110); here each of the four independent chains of a
+        proving thread (framework.rs:98-110); here each of the independent chains of a
         fold has its own context/stream and host thread."""
         import reef_b200
         import torch

@@ -27,7 +27,8 @@
 
 namespace reef {
 
-static constexpr uint32_t K_FIRST = 8;      // entries per thread in the first accumulation pass (latency: 8 mixed adds)
+static constexpr uint32_t K_FIRST = 8;      // entries per thread in the first accumulation pass (latency: 8 mixed adds);
+                                            // 16 once that still leaves > 2048 threads per SM (halves the partials to combine)
 static constexpr uint32_t K_NEXT = 128;     // partial points per WARP in the combine passes (4 per lane + shuffle tree)
 
 struct MsmPlan {
@@ -239,14 +240,15 @@ template <class C>
 __global__ void __launch_bounds__(128) k_accum_first(const uint32_t* __restrict__ sorted,
                                                      const uint32_t* __restrict__ start, const uint32_t* __restrict__ cnt,
                                                      const uint32_t* __restrict__ part_off, uint32_t nb, uint32_t n_parts,
-                                                     const Affine<C>* __restrict__ levels, XYZZ<C>* __restrict__ out) {
+                                                     uint32_t kfirst, const Affine<C>* __restrict__ levels,
+                                                     XYZZ<C>* __restrict__ out) {
   uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_parts) return;
   uint32_t b;
   locate_part(part_off, nb, p, b);
   const uint32_t j = p - part_off[b];
-  const uint32_t first = start[b] + j * K_FIRST;
-  const uint32_t last = min(start[b] + cnt[b], first + K_FIRST);
+  const uint32_t first = start[b] + j * kfirst;
+  const uint32_t last = min(start[b] + cnt[b], first + kfirst);
   XYZZ<C> acc = xyzz_inf<C>();
 #pragma unroll 1
   for (uint32_t e = first; e < last; e++) {
@@ -257,31 +259,41 @@ __global__ void __launch_bounds__(128) k_accum_first(const uint32_t* __restrict_
   st_xyzz(out + p, acc);
 }
 
-// combine passes: one WARP per (bucket, chunk of K_NEXT partials): lanes stride over the chunk,
-// then a 5-level shuffle tree; typical histograms need exactly one such pass.
-template <class C>
+// combine passes: LANES lanes per (bucket, chunk of K partials): the lanes stride over the chunk, then a
+// log2(LANES)-level shuffle tree.  LANES = 32 (K = 128) when there are few buckets (latency: 4 + 5
+// dependent additions), LANES = 4 (K = 64) when there are enough buckets to fill the chip with
+// 4-lane groups (throughput: 16 + 2 additions per group instead of 9 warp-wide ones per 128 partials,
+// i.e. 2x fewer warp-instructions per partial).
+template <class C, int LANES>
 __global__ void __launch_bounds__(128) k_accum_next(const XYZZ<C>* __restrict__ in, const uint32_t* __restrict__ in_off,
                                                     const uint32_t* __restrict__ in_cnt,
                                                     const uint32_t* __restrict__ part_off, uint32_t nb, uint32_t n_parts,
-                                                    XYZZ<C>* __restrict__ out) {
-  const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (p >= n_parts || p >= part_off[nb]) return;   // warp-uniform; n_parts is a host-side upper bound
-  uint32_t b;
-  locate_part(part_off, nb, p, b);
-  const uint32_t j = p - part_off[b];
-  const uint32_t first = in_off[b] + j * K_NEXT;
-  const uint32_t last = min(in_off[b] + in_cnt[b], first + K_NEXT);
+                                                    uint32_t K, XYZZ<C>* __restrict__ out) {
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t p = gid / LANES;
+  const int sub = threadIdx.x & (LANES - 1);
+  const bool live = p < n_parts && p < part_off[nb];   // n_parts is a host-side upper bound
+  if (LANES == 32 && !live) return;                    // warp-uniform
   XYZZ<C> acc = xyzz_inf<C>();
+  uint32_t width = 0;
+  if (live) {
+    uint32_t b;
+    locate_part(part_off, nb, p, b);
+    const uint32_t j = p - part_off[b];
+    const uint32_t first = in_off[b] + j * K;
+    const uint32_t last = min(in_off[b] + in_cnt[b], first + K);
 #pragma unroll 1
-  for (uint32_t e = first + lane; e < last; e += 32) xyzz_add<C>(acc, ld_xyzz(in + e));
-  const uint32_t width = last - first;             // warp-uniform
+    for (uint32_t e = first + sub; e < last; e += LANES) xyzz_add<C>(acc, ld_xyzz(in + e));
+    width = last - first;
+  }
+  // groups of one warp may have different widths: every lane runs all levels (infinity adds are cheap)
 #pragma unroll 1
-  for (int m = 1; m < 32 && (uint32_t)m < width; m <<= 1) {
+  for (int m = 1; m < LANES; m <<= 1) {
+    if (LANES == 32 && (uint32_t)m >= width) break;    // warp-uniform for whole-warp groups
     XYZZ<C> o = shfl_xor_xyzz(acc, m);
     xyzz_add<C>(acc, o);
   }
-  if (lane == 0) st_xyzz(out + p, acc);
+  if (live && sub == 0) st_xyzz(out + p, acc);
 }
 
 // buckets[b] = (cnt[b] ? parts[off[b]] : infinity)   (after the last pass every count is <= 1)
@@ -322,14 +334,19 @@ __device__ __forceinline__ XYZZ<C> block_sum_xyzz(XYZZ<C> v, XYZZ<C>* sm /* bloc
   return r;  // valid on warp 0
 }
 
+// Each thread first sums `bpt` buckets of its own (stride 256) before the CTA tree: with many buckets
+// the 8-level tree is amortised over bpt times more points (bpt = 1 keeps the latency of small MSMs).
 template <class C>
-__global__ void __launch_bounds__(256) k_bitsum_partial(const XYZZ<C>* __restrict__ buckets, uint32_t B,
+__global__ void __launch_bounds__(256) k_bitsum_partial(const XYZZ<C>* __restrict__ buckets, uint32_t B, uint32_t bpt,
                                                         XYZZ<C>* __restrict__ partial) {
   __shared__ XYZZ<C> sm[8];
   const uint32_t t = blockIdx.y, g = blockIdx.z;
-  const uint32_t b = blockIdx.x * 256 + threadIdx.x;
   XYZZ<C> v = xyzz_inf<C>();
-  if (b < B && (((b + 1) >> t) & 1)) v = ld_xyzz(buckets + (uint64_t)g * B + b);
+#pragma unroll 1
+  for (uint32_t k = 0; k < bpt; k++) {
+    const uint32_t b = (blockIdx.x * bpt + k) * 256 + threadIdx.x;
+    if (b < B && (((b + 1) >> t) & 1)) xyzz_add<C>(v, ld_xyzz(buckets + (uint64_t)g * B + b));
+  }
   XYZZ<C> r = block_sum_xyzz<C>(v, sm);
   if (threadIdx.x == 0) st_xyzz(partial + ((uint64_t)g * gridDim.y + t) * gridDim.x + blockIdx.x, r);
 }
@@ -585,7 +602,7 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
     return o;
   };
   const uint64_t max_parts1 = n_entries / K_FIRST + nb + 1;
-  const uint64_t max_parts2 = max_parts1 / K_NEXT + nb + 1;
+  const uint64_t max_parts2 = max_parts1 / 64 + nb + 1;   // smallest chunk size of a combine pass
   size_t o_keys = take(n_entries * 4), o_vals = take(n_entries * 4), o_sorted = take(n_entries * 4);
   size_t o_cnt = take((size_t)(nb + 2) * 4), o_start = take((size_t)(nb + 2) * 4), o_cursor = take((size_t)(nb + 2) * 4);
   size_t o_pcnt[2] = {take((size_t)(nb + 2) * 4), take((size_t)(nb + 2) * 4)};
@@ -593,7 +610,8 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
   size_t o_tm = take(64);
   size_t o_parts[2] = {take(max_parts1 * sizeof(XYZZ<C>)), take(max_parts2 * sizeof(XYZZ<C>))};
   size_t o_buckets = take((size_t)nb * sizeof(XYZZ<C>));
-  const uint32_t nblk = cdiv(P.B, 256);
+  const uint32_t bpt = P.B >= 256u * 32u ? 8u : 1u;
+  const uint32_t nblk = cdiv(P.B, 256 * bpt);
   size_t o_bitpart = take((size_t)P.G * P.c * nblk * sizeof(XYZZ<C>));
   size_t o_res = take(sizeof(XYZZ<C>) + sizeof(Affine<C>));
   size_t o_extra = take((size_t)(a.n_extra + 1) * sizeof(XYZZ<C>));
@@ -629,7 +647,8 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
   REEF_LAUNCHED();
   k_scatter<<<cdiv(n_entries, 256), 256, 0, s>>>(keys, vals, n_entries, nb, cursor, sorted);
   REEF_LAUNCHED();
-  k_scan<<<1, 1024, 0, s>>>(cnt, nb, K_FIRST, pcnt[0], poff[0], nullptr, tm + 2);
+  const uint32_t kfirst = n_entries / (2 * K_FIRST) >= (uint64_t)c->sm_count * 2048 ? 2 * K_FIRST : K_FIRST;
+  k_scan<<<1, 1024, 0, s>>>(cnt, nb, kfirst, pcnt[0], poff[0], nullptr, tm + 2);
   REEF_LAUNCHED();
   delete scope;
   uint32_t h_tm[4];
@@ -638,19 +657,23 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
   uint32_t n_parts = h_tm[2], max_cnt = h_tm[3];   // parts of pass 1, largest per-bucket part count
   scope = new ProfScope(c, PROF_MSM_ACCUM, n_entries);
   if (n_parts) {
-    k_accum_first<C><<<cdiv(n_parts, 128), 128, 0, s>>>(sorted, start, cnt, poff[0], nb, n_parts, (const Affine<C>*)a.d_levels,
+    k_accum_first<C><<<cdiv(n_parts, 128), 128, 0, s>>>(sorted, start, cnt, poff[0], nb, n_parts, kfirst, (const Affine<C>*)a.d_levels,
                                                        parts[0]);
     REEF_LAUNCHED();
   }
   int cur = 0;
   while (max_cnt > 1) {
     const int nxt = cur ^ 1;
-    k_scan<<<1, 1024, 0, s>>>(pcnt[cur], nb, K_NEXT, pcnt[nxt], poff[nxt], nullptr, tm + 2);
+    // enough buckets to fill the chip with 4-lane groups -> throughput shape, else whole-warp groups
+    const bool narrow = (uint64_t)nb * 4 >= (uint64_t)c->sm_count * 32 * 2;
+    const uint32_t kn = narrow ? 64u : K_NEXT;
+    k_scan<<<1, 1024, 0, s>>>(pcnt[cur], nb, kn, pcnt[nxt], poff[nxt], nullptr, tm + 2);
     REEF_LAUNCHED();
-    const uint32_t n_next = (n_parts + K_NEXT - 1) / K_NEXT + nb;   // upper bound; exact count read on device
-    k_accum_next<C><<<cdiv((uint64_t)n_next * 32, 128), 128, 0, s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, parts[nxt]);
+    const uint32_t n_next = (n_parts + kn - 1) / kn + nb;   // upper bound; exact count read on device
+    if (narrow) k_accum_next<C, 4><<<cdiv((uint64_t)n_next * 4, 128), 128, 0, s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, kn, parts[nxt]);
+    else k_accum_next<C, 32><<<cdiv((uint64_t)n_next * 32, 128), 128, 0, s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, kn, parts[nxt]);
     REEF_LAUNCHED();
-    max_cnt = (max_cnt + K_NEXT - 1) / K_NEXT;
+    max_cnt = (max_cnt + kn - 1) / kn;
     n_parts = n_next;
     cur = nxt;
   }
@@ -658,7 +681,7 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
   scope = new ProfScope(c, PROF_MSM_REDUCE, nb);
   k_gather_buckets<C><<<cdiv(nb, 256), 256, 0, s>>>(parts[cur], poff[cur], pcnt[cur], nb, buckets);
   REEF_LAUNCHED();
-  k_bitsum_partial<C><<<dim3(nblk, P.c, P.G), 256, 0, s>>>(buckets, P.B, bitpart);
+  k_bitsum_partial<C><<<dim3(nblk, P.c, P.G), 256, 0, s>>>(buckets, P.B, bpt, bitpart);
   REEF_LAUNCHED();
   if (a.n_extra) REEF_CUDA(cudaMemcpyAsync(extra, a.h_extra_xyzz_mont, (size_t)a.n_extra * sizeof(XYZZ<C>), cudaMemcpyHostToDevice, s));
   k_bitsum_final<C><<<1, 1024, 0, s>>>(bitpart, nblk, P.c, P.G, P.c * P.L, a.h_out_xyzz ? res_xyzz : nullptr,
@@ -697,7 +720,7 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
     return o;
   };
   const uint64_t max_parts1 = n_entries / K_FIRST + nb + 1;
-  const uint64_t max_parts2 = max_parts1 / K_NEXT + nb + 1;
+  const uint64_t max_parts2 = max_parts1 / 64 + nb + 1;   // smallest chunk size of a combine pass
   size_t o_keys = take(n_entries * 4), o_vals = take(n_entries * 4), o_sorted = take(n_entries * 4);
   size_t o_cnt = take((size_t)(nb + 2) * 4), o_start = take((size_t)(nb + 2) * 4), o_cursor = take((size_t)(nb + 2) * 4);
   size_t o_pcnt[2] = {take((size_t)(nb + 2) * 4), take((size_t)(nb + 2) * 4)};
@@ -705,7 +728,8 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
   size_t o_tm = take(64);
   size_t o_parts[2] = {take(max_parts1 * sizeof(XYZZ<C>)), take(max_parts2 * sizeof(XYZZ<C>))};
   size_t o_buckets = take((size_t)nb * sizeof(XYZZ<C>));
-  const uint32_t nblk = cdiv(P.B, 256);
+  const uint32_t bpt = P.B >= 256u * 32u ? 8u : 1u;
+  const uint32_t nblk = cdiv(P.B, 256 * bpt);
   size_t o_bitpart = take((size_t)a.rows * P.c * nblk * sizeof(XYZZ<C>));
   size_t o_out = take((size_t)a.rows * sizeof(Affine<C>));
   void* base;
@@ -741,7 +765,8 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
   REEF_LAUNCHED();
   k_scatter<<<cdiv(n_entries, 256), 256, 0, s>>>(keys, vals, n_entries, nb, cursor, sorted);
   REEF_LAUNCHED();
-  k_scan<<<1, 1024, 0, s>>>(cnt, nb, K_FIRST, pcnt[0], poff[0], nullptr, tm + 2);
+  const uint32_t kfirst = n_entries / (2 * K_FIRST) >= (uint64_t)c->sm_count * 2048 ? 2 * K_FIRST : K_FIRST;
+  k_scan<<<1, 1024, 0, s>>>(cnt, nb, kfirst, pcnt[0], poff[0], nullptr, tm + 2);
   REEF_LAUNCHED();
   delete scope;
   uint32_t h_tm[4];
@@ -750,18 +775,21 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
   uint32_t n_parts = h_tm[2], max_cnt = h_tm[3];
   scope = new ProfScope(c, PROF_MSM_ACCUM, n_entries);
   if (n_parts) {
-    k_accum_first<C><<<cdiv(n_parts, 128), 128, 0, s>>>(sorted, start, cnt, poff[0], nb, n_parts, (const Affine<C>*)a.d_levels, parts[0]);
+    k_accum_first<C><<<cdiv(n_parts, 128), 128, 0, s>>>(sorted, start, cnt, poff[0], nb, n_parts, kfirst, (const Affine<C>*)a.d_levels, parts[0]);
     REEF_LAUNCHED();
   }
   int cur = 0;
   while (max_cnt > 1) {
     const int nxt = cur ^ 1;
-    k_scan<<<1, 1024, 0, s>>>(pcnt[cur], nb, K_NEXT, pcnt[nxt], poff[nxt], nullptr, tm + 2);
+    const bool narrow = (uint64_t)nb * 4 >= (uint64_t)c->sm_count * 32 * 2;
+    const uint32_t kn = narrow ? 64u : K_NEXT;
+    k_scan<<<1, 1024, 0, s>>>(pcnt[cur], nb, kn, pcnt[nxt], poff[nxt], nullptr, tm + 2);
     REEF_LAUNCHED();
-    const uint32_t n_next = (n_parts + K_NEXT - 1) / K_NEXT + nb;
-    k_accum_next<C><<<cdiv((uint64_t)n_next * 32, 128), 128, 0, s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, parts[nxt]);
+    const uint32_t n_next = (n_parts + kn - 1) / kn + nb;
+    if (narrow) k_accum_next<C, 4><<<cdiv((uint64_t)n_next * 4, 128), 128, 0, s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, kn, parts[nxt]);
+    else k_accum_next<C, 32><<<cdiv((uint64_t)n_next * 32, 128), 128, 0, s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, kn, parts[nxt]);
     REEF_LAUNCHED();
-    max_cnt = (max_cnt + K_NEXT - 1) / K_NEXT;
+    max_cnt = (max_cnt + kn - 1) / kn;
     n_parts = n_next;
     cur = nxt;
   }
@@ -769,7 +797,7 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
   scope = new ProfScope(c, PROF_MSM_REDUCE, nb);
   k_gather_buckets<C><<<cdiv(nb, 256), 256, 0, s>>>(parts[cur], poff[cur], pcnt[cur], nb, buckets);
   REEF_LAUNCHED();
-  k_bitsum_partial<C><<<dim3(nblk, P.c, (unsigned)a.rows), 256, 0, s>>>(buckets, P.B, bitpart);
+  k_bitsum_partial<C><<<dim3(nblk, P.c, (unsigned)a.rows), 256, 0, s>>>(buckets, P.B, bpt, bitpart);
   REEF_LAUNCHED();
   k_rows_final<C><<<(unsigned)a.rows, 512, 0, s>>>(bitpart, nblk, P.c, d_out);
   REEF_LAUNCHED();

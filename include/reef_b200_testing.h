@@ -15,7 +15,7 @@ extern "C" {
 
 /* field: 0 = Fq (Pallas scalar), 1 = Fp (Pallas base).  Operands/outputs canonical 32-byte LE.
  * op: 0 a*b, 1 a+b, 2 a-b, 3 1/a, 4 lazy(a*b + a*a + b*b), 5 lazy(40000 * a*b), 6 a[limb0]*b,
- *     7 a*b (low-latency variant), 8 a*b in 29-bit limbs (fp29.cuh), 9 (a+b)(2a+b) + (a+b)^2 in 29-bit limbs */
+ *     7 a*a, 8 a*b in 29-bit limbs (fp29.cuh), 9 (a+b)(2a+b) + (a+b)^2 in 29-bit limbs */
 int reef_hosttest_field_op(int field, int op, const uint8_t a[32], const uint8_t b[32], uint8_t out[32]);
 /* plain 256x256 -> 512-bit integer product */
 int reef_hosttest_mul_wide(const uint8_t a[32], const uint8_t b[32], uint8_t out[64]);

@@ -138,7 +138,7 @@ static void hosttest_field_op(int op, const uint8_t* a, const uint8_t* b, uint8_
       r = wide_reduce_canonical<C>(w);
       break;
     }
-    case 7: r = from_mont<C>(mont_mul_ll<C>(to_mont<C>(x), to_mont<C>(y))); break;       // low-latency variant
+    case 7: r = from_mont<C>(mont_sqr<C>(to_mont<C>(x))); break;                  // a*a
     case 8: r = f29_to_canonical<C>(mul29<C>(f29_from_canonical<C>(x), f29_from_canonical<C>(y))); break;  // 29-bit limbs
     case 9: {                                                                     // 29-bit limbs through Montgomery-256
       const F29 k = f29_const_2_266<C>();

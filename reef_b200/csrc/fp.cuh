@@ -267,60 +267,6 @@ REEF_HD Fe<C> mont_mul(const Fe<C>& a, const Fe<C>& b) {
   return r;
 }
 
-// Low-LATENCY Montgomery multiplication for single-warp dependent chains (Fiat-Shamir sponge,
-// MSM tail): same result as mont_mul, ~30 % more instructions, about half the dependent
-// latency.  Differences: four independent row accumulators (chains half as deep), no merge
-// pass (columns are summed lazily in 64-bit accumulators), and the Montgomery m_i recurrence
-// only waits for ONE fresh 32-bit product per step.
-template <class C>
-REEF_HD Fe<C> mont_mul_ll(const Fe<C>& a, const Fe<C>& b) {
-  u32 ea[16], eb[16], oa[16], ob[16];   // o?[k] holds column k+1
-#pragma unroll
-  for (int i = 0; i < 16; i++) { ea[i] = 0; eb[i] = 0; oa[i] = 0; ob[i] = 0; }
-#pragma unroll
-  for (int i = 0; i < 8; i += 2) {
-    u32 c;
-    c = mad_row4(ea + i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
-    ea[i + 8] += c;
-    c = mad_row4(oa + i, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
-    oa[i + 8] += c;
-    c = mad_row4(ob + i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i + 1]);
-    ob[i + 8] += c;
-    c = mad_row4(eb + i + 2, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1]);
-    if (i + 10 < 16) eb[i + 10] += c;
-  }
-  u64 S[17];
-  S[0] = (u64)ea[0] + eb[0];
-#pragma unroll
-  for (int k = 1; k < 16; k++) S[k] = (u64)ea[k] + eb[k] + oa[k - 1] + ob[k - 1];
-  S[16] = 0;
-  u64 acc = 0;
-  u32 m[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const u64 c = acc + S[i];
-    const u32 mi = 0u - (u32)c;
-    m[i] = mi;
-    acc = (c >> 32) + ((u32)c != 0u ? 1u : 0u);
-    const u64 l1 = (u64)mi * C::P1, l2 = (u64)mi * C::P2, l3 = (u64)mi * C::P3;
-    S[i + 1] += (u32)l1;
-    S[i + 2] += (l1 >> 32) + (u32)l2;
-    S[i + 3] += (l2 >> 32) + (u32)l3;
-    S[i + 4] += (l3 >> 32);
-    S[i + 7] += (u64)(mi << 30);
-    S[i + 8] += (u64)(mi >> 2);
-  }
-  Fe<C> r;
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const u64 c = acc + S[8 + k];
-    r.v[k] = (u32)c;
-    acc = c >> 32;
-  }
-  cond_sub_p<C>(r.v);
-  return r;
-}
-
 template <class C>
 REEF_HD Fe<C> mont_sqr(const Fe<C>& a) { return mont_mul<C>(a, a); }
 

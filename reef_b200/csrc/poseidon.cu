@@ -166,6 +166,25 @@ __global__ void __launch_bounds__(128) k_hash_batch_warp(const Fq* __restrict__ 
   if (lane == 1) st256(out + i, o);
 }
 
+// same contract, one two-warp CTA per hash (latency path: calc_d, a handful of hashes)
+__global__ void __launch_bounds__(64) k_hash_batch_pair(const Fq* __restrict__ in, int arity, uint64_t n, Fq tag,
+                                                        const PoseidonTables* __restrict__ K, Fq* __restrict__ out) {
+  const uint64_t i = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool A = threadIdx.x < 32;
+  Fq s = fe_zero<FqCfg>();
+  if (A) {
+    if (lane >= 1 && lane <= arity) s = ld256(in + i * arity + (lane - 1));
+    const Fq sm = to_mont<FqCfg>(s);
+    s = lane == 0 ? tag : sm;
+  }
+  poseidon_permute_pair(s, K);
+  if (A) {
+    const Fq o = from_mont<FqCfg>(s);
+    if (lane == 1) st256(out + i, o);
+  }
+}
+
 // leaf level: parent k = H4(2k, doc[2k], 2k+1, doc[2k+1]); missing right => (.., 0, 0)
 __global__ void __launch_bounds__(128) k_merkle_leaves(const uint64_t* __restrict__ doc, uint64_t n_doc, Fq tag4,
                                                        const PoseidonTables* __restrict__ K, Fq* __restrict__ out) {
@@ -301,7 +320,9 @@ int launch_hash_batch(reef_ctx* c, const void* d_in, int arity, uint64_t n, void
   REEF_REQUIRE(arity == 2 || arity == 4, REEF_EINVAL, "poseidon hash arity must be 2 or 4");
   Fq tag = arity == 2 ? c->tags.a2s1 : c->tags.a4s1;
   ProfScope ps(c, PROF_POSEIDON, n);
-  if (n < (uint64_t)c->sm_count * 256) {   // too few hashes to fill the machine: one warp each
+  if (n <= (uint64_t)c->sm_count) {        // at most one hash per SM: two warps per hash (lowest latency)
+    k_hash_batch_pair<<<(unsigned)n, 64, 0, c->stream>>>((const Fq*)d_in, arity, n, tag, c->d_pos, (Fq*)d_out);
+  } else if (n < (uint64_t)c->sm_count * 256) {   // too few hashes to fill the machine: one warp each
     k_hash_batch_warp<<<(unsigned)((n * 32 + 127) / 128), 128, 0, c->stream>>>((const Fq*)d_in, arity, n, tag, c->d_pos, (Fq*)d_out);
   } else {
     k_hash_batch<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((const Fq*)d_in, arity, n, tag, c->d_pos, (Fq*)d_out);

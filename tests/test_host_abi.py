@@ -46,6 +46,7 @@ def test_shared_field_code_host_instantiation(field, p):
         assert _op(field, 2, a, b) == (a - b) % p
         assert _op(field, 4, a, b) == (a * b + a * a + b * b) % p
         assert _op(field, 6, a, b) == (a & 0xFFFFFFFF) * b % p
+        assert _op(field, 7, a % p) == a * a % p
         assert _op(field, 8, a % p, b % p) == a * b % p                     # 29-bit limb Montgomery (fp29.cuh)
         assert _op(field, 9, a % p, b % p) == ((a + b) * (2 * a + b) + (a + b) ** 2) % p   # mul29 + sqr29, lazy/relaxed operands
     for _ in range(10):

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "../reef_b200/csrc/fp.cuh"
+#include "../reef_b200/csrc/fp29.cuh"
 #include "../reef_b200/csrc/ec.cuh"
 using namespace reef;
 typedef Fe<FqCfg> Fq;
@@ -20,7 +21,7 @@ __global__ void k_latency(Fq* io, int iters, long long* cycles) {
     if (MODE == 1) x = mont_sqr<FqCfg>(x);
     if (MODE == 2) x = fe_add<FqCfg>(x, y);
     if (MODE == 3) { u32 T[16]; mul_wide(T, x.v, y.v); for (int k = 0; k < 8; k++) x.v[k] = T[k] ^ T[8 + k]; }
-    if (MODE == 5) x = mont_mul_ll<FqCfg>(x, y);
+    if (MODE == 5) { F29 t = mul29<FqCfg>(f29_from_words(x.v), f29_from_words(y.v)); f29_normalize(t); f29_to_words(x.v, t); x.v[7] &= 0x3fffffff; }
     if (MODE == 6) { x = fe_inv<FqCfg>(x); x = fe_add<FqCfg>(x, y); }
     if (MODE == 7) x = fe_pow_pm2<FqCfg>(x);
     if (MODE == 4) { u32 T[16]; for (int k = 0; k < 8; k++) { T[k] = x.v[k]; T[8 + k] = y.v[k]; } mont_reduce<FqCfg>(x.v, T); }
@@ -31,14 +32,6 @@ __global__ void k_latency(Fq* io, int iters, long long* cycles) {
 }
 
 // ILP independent chains per thread
-__global__ void __launch_bounds__(256) k_throughput_ll(Fp* io, int iters) {
-  int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  Fp x = io[gid], y = io[gid];
-  x.v[7] &= 0x3fffffff;
-  for (int i = 0; i < iters; i++) x = mont_mul_ll<FpCfg>(x, y);
-  io[gid] = x;
-}
-
 template <int ILP>
 __global__ void __launch_bounds__(256) k_throughput(Fp* io, int iters) {
   int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -57,7 +50,7 @@ int main() {
   Fq* io; long long* cyc;
   cudaMalloc(&io, 1 << 26); cudaMalloc(&cyc, 8);
   cudaMemset(io, 0x11, 1 << 26);
-  const char* names[8] = {"mont_mul", "mont_sqr", "fe_add", "mul_wide", "mont_reduce", "mont_mul_ll", "fe_inv(bingcd)+add", "fe_pow_pm2"};
+  const char* names[8] = {"mont_mul", "mont_sqr", "fe_add", "mul_wide", "mont_reduce", "mul29+convert", "fe_inv(bingcd)+add", "fe_pow_pm2"};
   for (int mode = 0; mode < 8; mode++) {
     const int iters = mode >= 6 ? 20 : 2000;
     for (int rep = 0; rep < 2; rep++) {
@@ -92,12 +85,6 @@ int main() {
       double muls = (double)blocks * 256 * iters * ilp;
       printf("throughput ilp=%d blocks/SM=%d threads/SM=%4d : %7.2f G modmul/s  (%.3f ms)\n", ilp, bps, bps * 256, muls / best / 1e6, best);
     }
-  }
-  {
-    const int iters = 4000; int blocks = sms * 4;
-    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); float best = 1e30f;
-    for (int rep = 0; rep < 3; rep++) { cudaEventRecord(e0); k_throughput_ll<<<blocks, 256>>>((Fp*)io, iters); cudaEventRecord(e1); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms; }
-    printf("throughput mont_mul_ll blocks/SM=4 : %7.2f G modmul/s\n", (double)blocks * 256 * iters / best / 1e6);
   }
   printf("err=%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;

@@ -18,8 +18,11 @@ e2e     = the same pass through the C ABI with HOST buffers: document/table uplo
 --impl reference = the CPU restatement of the reference's algorithm (oracle/c, all host cores).
 
 Multi-GPU (torchrun), weak scaling: ONE document of base_len * G characters.  Its sum-check is
-sharded by low index bits (one 96-byte all-gather per round, every rank runs the same
-transcript), the MSMs are sharded by Pippenger windows (one 128-byte all-gather per MSM).
+sharded by low index bits; the 96 bytes per rank per round are exchanged by the library's own
+P2P mailbox kernel over NVLink peer memory (no NCCL call on that path), every rank runs the same
+transcript.  The fold commitments (latency-bound at 2^14..2^15 terms) are distributed whole,
+round-robin over the ranks; MSMs large enough to be throughput-bound are sharded by Pippenger
+windows (one 128-byte all-gather per MSM).
 """
 from __future__ import annotations
 
@@ -187,18 +190,28 @@ class GpuPass:
         self.T_tab = self.rb.Table(self.ctxs["nl"], values=w["T"])
         if self.world > 1:
             self.gbuf = t.zeros((self.world + 1) * 96, dtype=t.uint8, device="cuda")
-            self.doc_stream = t.cuda.ExternalStream(self.ctxs["doc"].stream)
+            self._connect_mailboxes()
         self.sc_dev = [{k: t.from_numpy(v.view(np.int64)).cuda() for k, v in s.items()} for s in w["sc"]]
         t.cuda.synchronize()
 
     def _doc_shard(self):
         return np.ascontiguousarray(self.w["udoc"][self.rank::self.world]) if self.world > 1 else self.w["udoc"]
 
-    def _gather(self, mine_ptr, nbytes, out_ptr):
-        """all-gather of `nbytes` per rank inside self.gbuf, ordered after the doc context's stream"""
+    def _connect_mailboxes(self):
+        """Per-round exchange of the sharded sum-check over NVLink peer memory (reef_b200/csrc/p2p.cu):
+        every rank maps every peer's mailbox with CUDA IPC once; NCCL only carries the 64-byte handles."""
         t = self.torch
-        with t.cuda.stream(self.doc_stream):
-            self.dist.all_gather_into_tensor(self.gbuf[96:96 + self.world * nbytes], self.gbuf[:nbytes])
+        ctx = self.ctxs["doc"]
+        mine = t.frombuffer(bytearray(ctx.mailbox_create(self.world)), dtype=t.uint8).cuda()
+        allh = t.empty(self.world * 64, dtype=t.uint8, device="cuda")
+        self.dist.all_gather_into_tensor(allh, mine)
+        ctx.mailbox_connect(self.rank, self.world, bytes(allh.cpu().numpy().tobytes()))
+        self.dist.barrier()
+
+    def _gather(self, mine_ptr, nbytes, out_ptr):
+        """all-gather of `nbytes` per rank: one stream-ordered kernel of the library (P2P stores into the
+        peers' mailboxes + system-scope release/acquire), no NCCL call and no host wait"""
+        self.ctxs["doc"].p2p_allgather(mine_ptr, nbytes, out_ptr)
 
     def _nlookup_sharded(self, tab, q_list, v_list, prev):
         w = self.w
@@ -210,6 +223,7 @@ class GpuPass:
             pv = int.from_bytes(prev[1], "little")
         sn = self.rb.ShardedNlookup(self.ctxs["doc"], tab, self.rank, self.world, q_list, v_list, pq, pv, "nldoc", w["doc_hash"])
         res = sn.run(self._gather, self.gbuf.data_ptr())
+        self.ctxs["doc"].p2p_status()
         sn.free()
         nxt = le32(res.next_running_claim)
         self.d_futs.append(self.pool["aux"].submit(self._calc_d, nxt))
@@ -454,6 +468,7 @@ def run_reef(args):
         torch.cuda.synchronize()
 
     def timed(gp, resident, steps, warmup, profile):
+        barrier()                               # ranks enter every leg together
         for _ in range(warmup):
             flush.fill_(1)
             gp.run(resident)
@@ -579,7 +594,7 @@ def run_reef(args):
                    "streams": "7 contexts/streams: nl sum-check | nldoc sum-check | commit(W) Pallas | commit(W) Vesta | commit(T) Pallas | commit(T) Vesta | calc_d "
                               "(fold i+1 sum-checks overlap fold i commitments; commit(T) does not wait for commit(W); calc_d does not gate the next fold)",
                    "parallelism": (f"1 document of {w['doc_len']} chars: nldoc sum-check sharded by low index bits x{world} "
-                                   f"(96-byte all-gather per round); fold commitments (2^14-2^15 terms, latency-bound) distributed "
+                                   f"(96 bytes per rank per round, exchanged by the library's own P2P mailbox kernel over NVLink, no NCCL call); fold commitments (2^14-2^15 terms, latency-bound) distributed "
                                    f"whole, round-robin over the ranks, results exchanged once per pass; MSMs with >= 2^22 "
                                    f"digit entries are sharded by Pippenger windows (128-byte all-gather)") if world > 1 else "single GPU"},
         "e2e": {"value": round(e2e_value, 1), "unit": "NFA steps/s", "ms_per_step": round(e2e_ms / K, 4),

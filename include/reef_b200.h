@@ -252,6 +252,24 @@ int reef_msm_partial_dev(reef_ctx* ctx, const reef_bases* b, const void* scalars
                          uint32_t w_end, uint8_t out_xyzz[128]);
 int reef_msm_combine(reef_ctx* ctx, int curve, const uint8_t* partials_xyzz, uint32_t k, uint8_t out[64]);
 
+/* ------------------------------------------------------------------ multi-GPU: small-message exchange over NVLink peer memory
+ * The per-round exchange of the sharded sum-check (96 bytes per rank) done by a kernel of this
+ * library instead of a collective call: each rank owns a mailbox in its HBM that every peer maps
+ * with CUDA IPC and writes with P2P stores; sequence numbers are published / acquired with
+ * system-scope release / acquire accesses (reef_b200/csrc/p2p.cu).
+ *   reef_mailbox_create   allocate this rank's mailbox, return its 64-byte IPC handle
+ *   reef_mailbox_connect  open the peers' mailboxes (handles of all ranks, rank-major, own slot ignored)
+ *   reef_mailbox_connect_local  same-process variant (tests): device pointers from reef_mailbox_ptr
+ *   reef_p2p_allgather    out_dev[g*nbytes ..] = rank g's mine_dev[0 .. nbytes), nbytes <= 120, multiple of 4;
+ *                         stream-ordered, no host synchronisation; every rank must issue the same sequence
+ *   reef_p2p_status       synchronises and reports a peer that never posted (bounded wait, ~2 s) */
+int reef_mailbox_create(reef_ctx* ctx, uint32_t world, uint8_t out_handle[64]);
+void* reef_mailbox_ptr(reef_ctx* ctx);
+int reef_mailbox_connect(reef_ctx* ctx, uint32_t rank, uint32_t world, const uint8_t* handles);
+int reef_mailbox_connect_local(reef_ctx* ctx, uint32_t rank, uint32_t world, void* const* mailboxes);
+int reef_p2p_allgather(reef_ctx* ctx, const void* mine_dev, uint32_t nbytes, void* out_dev);
+int reef_p2p_status(reef_ctx* ctx);
+
 /* ------------------------------------------------------------------ B4: Spartan sweeps behind CompressedSNARK::prove
  * Replaces the per-round work of nova-snark's `SumcheckProof::prove_quad` and
  * `prove_cubic_with_additive_term` (reached from framework.rs:695-698 with

@@ -97,6 +97,12 @@ _sig = {
     "reef_msm_combine": (C.c_int, [_vp, C.c_int, _vp, C.c_uint32, _vp]),
     # test hooks (include/reef_b200_testing.h)
     "reef_hosttest_ec_op": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp]),
+    "reef_mailbox_create": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "reef_mailbox_ptr": (_vp, [_vp]),
+    "reef_mailbox_connect": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp]),
+    "reef_mailbox_connect_local": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp]),
+    "reef_p2p_allgather": (C.c_int, [_vp, _vp, C.c_uint32, _vp]),
+    "reef_p2p_status": (C.c_int, [_vp]),
     "reef_sumcheck_begin": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_uint64, C.POINTER(_vp)]),
     "reef_sumcheck_round": (C.c_int, [_vp, _vp, _vp]),
     "reef_sumcheck_final": (C.c_int, [_vp, _vp, _vp]),

@@ -211,6 +211,28 @@ class Context:
             next_running_q=[r[0] for r in rounds],
         )
 
+    # ---- multi-GPU: small-message exchange over NVLink peer memory (p2p.cu)
+    def mailbox_create(self, world: int) -> bytes:
+        h = C.create_string_buffer(64)
+        check(lib.reef_mailbox_create(self._h, world, h))
+        return h.raw
+
+    def mailbox_ptr(self) -> int:
+        return int(lib.reef_mailbox_ptr(self._h) or 0)
+
+    def mailbox_connect(self, rank: int, world: int, handles: bytes):
+        check(lib.reef_mailbox_connect(self._h, rank, world, _buf(bytes(handles))))
+
+    def mailbox_connect_local(self, rank: int, world: int, ptrs):
+        arr = (C.c_void_p * world)(*[C.c_void_p(p) for p in ptrs])
+        check(lib.reef_mailbox_connect_local(self._h, rank, world, arr))
+
+    def p2p_allgather(self, mine_dev_ptr: int, nbytes: int, out_dev_ptr: int):
+        check(lib.reef_p2p_allgather(self._h, C.c_void_p(mine_dev_ptr), nbytes, C.c_void_p(out_dev_ptr)))
+
+    def p2p_status(self):
+        check(lib.reef_p2p_status(self._h))
+
     # ---- Spartan sweeps behind CompressedSNARK::prove (framework.rs:695-698), R1CS products, IPA fold
     def sumcheck(self, tables, field: str = "fq") -> "Sumcheck":
         """2 tables: prove_quad (A*B); 4 tables: prove_cubic_with_additive_term (A*(B*C-D))."""

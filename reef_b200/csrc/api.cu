@@ -202,6 +202,10 @@ void reef_shutdown(reef_ctx* c) {
   if (c->d_pos) cudaFree(c->d_pos);
   for (auto& kv : c->table_cache) cudaFree(kv.second);
   if (c->shard_cache) cudaFree(c->shard_cache);
+  for (void* p : c->mb_ipc_opened) cudaIpcCloseMemHandle(p);
+  if (c->mb_mine) cudaFree(c->mb_mine);
+  if (c->mb_peers_dev) cudaFree(c->mb_peers_dev);
+  if (c->mb_err_dev) cudaFree(c->mb_err_dev);
   cudaStreamDestroy(c->stream);
   delete c;
 }

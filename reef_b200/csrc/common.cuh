@@ -163,6 +163,13 @@ struct reef_ctx {
   // one retired buffer of a sharded sum-check session, reused by the next session (same reason)
   void* shard_cache = nullptr;
   size_t shard_cache_bytes = 0;
+  // peer mailbox (p2p.cu): this rank's buffer, the peers' buffers (device array of pointers), and the
+  // sequence number of the next exchange (every rank issues the same sequence of exchanges)
+  void* mb_mine = nullptr;
+  void** mb_peers_dev = nullptr;
+  uint32_t* mb_err_dev = nullptr;
+  std::vector<void*> mb_ipc_opened;
+  uint32_t mb_world = 0, mb_rank = 0, mb_seq = 0;
   // optional per-kernel-class event timing (reef_profile_enable); resolved lazily
   bool profile = false;
   std::vector<reef::ProfRec> prof;

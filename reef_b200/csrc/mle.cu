@@ -1296,6 +1296,20 @@ int nl_shard_finish(reef_nl_session* s, const void* d_pairs, uint8_t* out_claim_
   return REEF_OK;
 }
 
+// Forces the (lazily loaded) kernels of the sharded path into the device before the first P2P
+// exchange: loading a kernel synchronises with running work, which must not happen while an
+// exchange kernel of this process is waiting for a peer that the same host thread has yet to launch.
+int nl_shard_preload() {
+  cudaFuncAttributes a;
+  const void* fns[] = {(const void*)k_nl_begin, (const void*)k_eq_tables, (const void*)k_shard_local<true>, (const void*)k_shard_local<false>,
+                       (const void*)k_shard_apply, (const void*)k_small_local, (const void*)k_small_apply,
+                       (const void*)k_shard_materialize<true>, (const void*)k_shard_materialize<false>, (const void*)k_shard_export,
+                       (const void*)k_shard_final, (const void*)k_sweep<true, false>, (const void*)k_sweep<true, true>,
+                       (const void*)k_sweep<false, false>, (const void*)k_sweep<false, true>};
+  for (const void* f : fns) REEF_CUDA(cudaFuncGetAttributes(&a, f));
+  return REEF_OK;
+}
+
 void nl_shard_free(reef_nl_session* s) {
   if (!s) return;
   reef_ctx* c = s->ctx;

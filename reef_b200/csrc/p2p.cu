@@ -1,0 +1,166 @@
+// Small-message all-gather over NVLink peer memory for the sharded sum-check.
+//
+// The reference is a single process (no collective exists in it); on an 8 x B200 box the nldoc
+// sum-check is sharded over the GPUs and every round needs the ranks' (const, g(1), xsq) triples
+// -- 96 bytes per rank -- on every rank before the transcript can continue.  At that size an
+// NCCL all-gather is pure launch/protocol latency (~20 us plus its host call) on a path that runs
+// ~50 times per pass, so the exchange is done by the producer itself: each rank owns a MAILBOX in
+// its HBM, mapped into every peer with CUDA IPC; one tiny kernel stores this rank's payload into
+// all peers' mailboxes with plain P2P stores over NVLink, publishes it with a system-scope release
+// store of a sequence number, and then acquires the peers' sequence numbers in its own mailbox.
+// No host round trip, no NCCL kernel: the exchange is one stream-ordered launch.
+//
+// Mailbox layout: [2 slots][world] entries of 128 bytes: payload (<= 120 B) + sequence number at
+// byte 120.  Two slots suffice: a rank can be at most one exchange ahead of any peer (it cannot
+// finish exchange k+1 before every peer has posted k+1, which a peer does only after it has
+// consumed exchange k).
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace reef {
+
+static constexpr uint32_t MB_ENTRY = 128;
+static constexpr uint32_t MB_SEQ_OFF = 120;
+static constexpr uint32_t MB_MAX_WORLD = 32;
+static constexpr uint32_t MB_SPIN_LIMIT = 1u << 25;   // ~30 s of polling (host-side skew between ranks is legal) before the error flag is raised
+
+__global__ void __launch_bounds__(32) k_p2p_allgather(void* const* __restrict__ peers, const unsigned char* mine, uint32_t world,
+                                                      uint32_t rank, uint32_t seq, const uint32_t* __restrict__ src,
+                                                      uint32_t nwords, uint32_t* __restrict__ dst, uint32_t* err) {
+  const uint32_t t = threadIdx.x;
+  if (t >= world) return;
+  const uint32_t slot = seq & 1u;
+  {  // post: thread t writes this rank's payload into peer t's mailbox, then publishes it
+    unsigned char* e = (unsigned char*)peers[t] + ((size_t)slot * world + rank) * MB_ENTRY;
+    volatile uint32_t* w = (volatile uint32_t*)e;
+    for (uint32_t k = 0; k < nwords; k++) w[k] = src[k];
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(e + MB_SEQ_OFF), "r"(seq) : "memory");
+  }
+  {  // wait: thread t acquires rank t's entry in this rank's own mailbox
+    const unsigned char* e = mine + ((size_t)slot * world + t) * MB_ENTRY;
+    uint32_t got = 0, spins = 0;
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(e + MB_SEQ_OFF) : "memory");
+      if (got == seq || ++spins >= MB_SPIN_LIMIT) break;
+      __nanosleep(64);
+    }
+    if (got != seq) {
+      atomicExch(err, seq | 0x80000000u);
+      return;
+    }
+    const volatile uint32_t* w = (const volatile uint32_t*)e;
+    for (uint32_t k = 0; k < nwords; k++) dst[(size_t)t * nwords + k] = w[k];
+  }
+}
+
+}  // namespace reef
+
+using namespace reef;
+
+static int mailbox_alloc(reef_ctx* c, uint32_t world) {
+  if (c->mb_mine) return REEF_OK;
+  const size_t bytes = (size_t)2 * MB_MAX_WORLD * MB_ENTRY;
+  REEF_CUDA(cudaMalloc(&c->mb_mine, bytes));
+  REEF_CUDA(cudaMemset(c->mb_mine, 0, bytes));
+  REEF_CUDA(cudaMalloc((void**)&c->mb_peers_dev, MB_MAX_WORLD * sizeof(void*)));
+  REEF_CUDA(cudaMalloc((void**)&c->mb_err_dev, 256));
+  REEF_CUDA(cudaMemset(c->mb_err_dev, 0, 256));
+  REEF_CUDA(cudaDeviceSynchronize());
+  (void)world;
+  return REEF_OK;
+}
+
+static int mailbox_set_peers(reef_ctx* c, uint32_t rank, uint32_t world, void* const* ptrs) {
+  REEF_CUDA(cudaMemcpy(c->mb_peers_dev, ptrs, world * sizeof(void*), cudaMemcpyHostToDevice));
+  cudaFuncAttributes fa;
+  REEF_CUDA(cudaFuncGetAttributes(&fa, (const void*)k_p2p_allgather));   // load it now, see nl_shard_preload
+  int rc = nl_shard_preload();
+  if (rc) return rc;
+  c->mb_world = world;
+  c->mb_rank = rank;
+  c->mb_seq = 0;
+  return REEF_OK;
+}
+
+extern "C" {
+
+int reef_mailbox_create(reef_ctx* c, uint32_t world, uint8_t out_handle[64]) {
+  REEF_REQUIRE(c && out_handle, REEF_EINVAL, "reef_mailbox_create: NULL argument");
+  REEF_REQUIRE(world >= 1 && world <= MB_MAX_WORLD, REEF_EINVAL, "reef_mailbox_create: world must be in 1..32");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  int rc = mailbox_alloc(c, world);
+  if (rc) return rc;
+  cudaIpcMemHandle_t h;
+  REEF_CUDA(cudaIpcGetMemHandle(&h, c->mb_mine));
+  memcpy(out_handle, &h, 64);
+  return REEF_OK;
+}
+
+void* reef_mailbox_ptr(reef_ctx* c) { return c ? c->mb_mine : nullptr; }
+
+int reef_mailbox_connect(reef_ctx* c, uint32_t rank, uint32_t world, const uint8_t* handles) {
+  REEF_REQUIRE(c && handles, REEF_EINVAL, "reef_mailbox_connect: NULL argument");
+  REEF_REQUIRE(world >= 1 && world <= MB_MAX_WORLD && rank < world, REEF_EINVAL, "reef_mailbox_connect: bad rank / world");
+  REEF_REQUIRE(c->mb_mine != nullptr, REEF_EINVAL, "reef_mailbox_connect: call reef_mailbox_create first");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  std::vector<void*> ptrs(world, nullptr);
+  for (uint32_t g = 0; g < world; g++) {
+    if (g == rank) {
+      ptrs[g] = c->mb_mine;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)g * 64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess)
+      return fail(REEF_ECUDA, std::string("reef_mailbox_connect: cudaIpcOpenMemHandle(rank ") + std::to_string(g) + "): " + cudaGetErrorString(e));
+    c->mb_ipc_opened.push_back(p);
+    ptrs[g] = p;
+  }
+  return mailbox_set_peers(c, rank, world, ptrs.data());
+}
+
+int reef_mailbox_connect_local(reef_ctx* c, uint32_t rank, uint32_t world, void* const* mailboxes) {
+  REEF_REQUIRE(c && mailboxes, REEF_EINVAL, "reef_mailbox_connect_local: NULL argument");
+  REEF_REQUIRE(world >= 1 && world <= MB_MAX_WORLD && rank < world, REEF_EINVAL, "reef_mailbox_connect_local: bad rank / world");
+  REEF_REQUIRE(c->mb_mine != nullptr && mailboxes[rank] == c->mb_mine, REEF_EINVAL,
+               "reef_mailbox_connect_local: mailboxes[rank] must be this context's own mailbox");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  return mailbox_set_peers(c, rank, world, mailboxes);
+}
+
+int reef_p2p_allgather(reef_ctx* c, const void* mine_dev, uint32_t nbytes, void* out_dev) {
+  REEF_REQUIRE(c && mine_dev && out_dev, REEF_EINVAL, "reef_p2p_allgather: NULL argument");
+  REEF_REQUIRE(c->mb_world >= 1, REEF_EINVAL, "reef_p2p_allgather: mailbox not connected");
+  REEF_REQUIRE(nbytes >= 4 && nbytes <= MB_SEQ_OFF && (nbytes & 3) == 0, REEF_EINVAL, "reef_p2p_allgather: payload must be 4..120 bytes, a multiple of 4");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  const uint32_t seq = ++c->mb_seq;
+  k_p2p_allgather<<<1, 32, 0, c->stream>>>(c->mb_peers_dev, (const unsigned char*)c->mb_mine, c->mb_world, c->mb_rank, seq,
+                                           (const uint32_t*)mine_dev, nbytes / 4, (uint32_t*)out_dev, c->mb_err_dev);
+  REEF_LAUNCHED();
+  return REEF_OK;
+}
+
+int reef_p2p_status(reef_ctx* c) {
+  REEF_REQUIRE(c, REEF_EINVAL, "reef_p2p_status: NULL argument");
+  if (!c->mb_err_dev) return REEF_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  uint32_t e = 0;
+  REEF_CUDA(cudaMemcpyAsync(&e, c->mb_err_dev, 4, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaStreamSynchronize(c->stream));
+  if (e) return fail(REEF_ECUDA, "reef_p2p_allgather: a peer never posted exchange " + std::to_string(e & 0x7fffffffu) + " (timed out)");
+  return REEF_OK;
+}
+
+}  // extern "C"

@@ -259,3 +259,59 @@ def test_sharded_sumcheck_all_ranks_on_one_gpu(ctx, world, ell, u32, tag):
         assert got.next_running_claim == exp["next_running_claim"]
     for r in ranks:
         r.free()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("ell,u32,tag", [(11, True, "nldoc"), (13, False, "nlhybrid")])
+def test_sharded_sumcheck_p2p_mailbox_exchange(world, ell, u32, tag):
+    """The per-round exchange done by the library's own P2P mailbox kernel (p2p.cu) instead of a
+    collective: one context (= one stream) per rank on this GPU, mailboxes connected by device
+    pointer; all ranks are enqueued without any host wait and must reproduce the oracle."""
+    import torch
+    rnd = random.Random(ell * 10 + world)
+    n = 1 << ell
+    table = [rnd.randrange(131 if u32 else FQ) for _ in range(n)]
+    q = [rnd.randrange(n) for _ in range(4)] + [n - 1]
+    v = [table[i] for i in q]
+    prev_q = [rnd.randrange(FQ) for _ in range(ell)]
+    prev_v = mle_eval_fast(table, prev_q)
+    exp = wit_nlookup_gadget(table, q, v, prev_q, prev_v, tag, 4242, fast=True)
+    ctxs = [reef_b200.Context(0) for _ in range(world)]
+    tabs, ranks = [], []
+    try:
+        for c in ctxs:
+            c.mailbox_create(world)
+        ptrs = [c.mailbox_ptr() for c in ctxs]
+        for g, c in enumerate(ctxs):
+            c.mailbox_connect_local(g, world, ptrs)
+        tabs = [ctxs[g].table_u32(table[g::world]) if u32 else ctxs[g].table(table[g::world]) for g in range(world)]
+        ranks = [reef_b200.ShardedNlookup(ctxs[g], tabs[g], g, world, q, v, prev_q, prev_v, tag, 4242 if tag != "nl" else None)
+                 for g in range(world)]
+        bufs = [torch.zeros((world + 1) * 96, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        torch.cuda.synchronize()
+        got = [None] * world
+        for _ in range(ranks[0].ell_local):
+            for g, r in enumerate(ranks):                      # nothing below waits on the host
+                mine, allp = bufs[g].data_ptr(), bufs[g].data_ptr() + 96
+                r.round_local(mine)
+                ctxs[g].p2p_allgather(mine, 96, allp)
+                r.round_finish(allp)
+        for g, r in enumerate(ranks):
+            mine, allp = bufs[g].data_ptr(), bufs[g].data_ptr() + 96
+            r.export(mine)
+            ctxs[g].p2p_allgather(mine, 64, allp)
+        for g, r in enumerate(ranks):
+            got[g] = r.finish(bufs[g].data_ptr() + 96)
+            ctxs[g].p2p_status()
+        for g in range(world):
+            assert got[g].claim_r == exp["claim_r"]
+            assert got[g].rounds == exp["rounds"]
+            assert got[g].sc_last_claim == exp["sc_last_claim"]
+            assert got[g].next_running_claim == exp["next_running_claim"]
+    finally:
+        for r in ranks:
+            r.free()
+        for t in tabs:
+            t.free()
+        for c in ctxs:
+            c.close()

@@ -63,3 +63,18 @@ for lg in (12, 15):
     dev = torch.from_numpy(raw.view(np.int64)).cuda()
     best, avg = timeit(lambda: b.msm_dev(dev.data_ptr(), n), n=5, warm=2)
     print(f"msm pallas n=2^{lg} c={b.window_bits} W={b.windows}  best {best:8.3f} ms  avg {avg:8.3f} ms  ({n/best/1e3:8.2f} Mop/s)")
+# ---- commitment path of --commit: Hyrax row commitments and the prove_eval mat-vec
+import random as _r
+for (lr, lc, ab_bits, name) in ((8, 9, 8, "cfg2 256x512"), (10, 11, 8, "cfg3/4 1024x2048")):
+    rows, cols = 1 << lr, 1 << lc
+    pts = PALLAS.multiples(cols + 1)
+    b = ctx.bases("pallas", pts, 255)
+    M = np.random.default_rng(lr).integers(0, 131, size=rows * cols, dtype=np.uint32)
+    blinds = [_r.Random(lr).randrange(1, PALLAS.order) for _ in range(rows)]
+    best, avg = timeit(lambda: b.msm_rows(M, rows, cols, ab_bits, blinds), n=3, warm=1)
+    print(f"hyrax commit {name} (u32 codes + blinds, host in/out) best {best:8.3f} ms  avg {avg:8.3f} ms  ({rows * cols / best / 1e3:8.1f} M terms/s)")
+    t = ctx.table_u32(M)
+    L = [_r.Random(7).randrange(FQ) for _ in range(rows)]
+    best, avg = timeit(lambda: ctx.hyrax_lz(t, rows, cols, L), n=3, warm=1)
+    print(f"hyrax LZ mat-vec {name} best {best:8.3f} ms  avg {avg:8.3f} ms")
+    t.free(); b.free()

@@ -18,9 +18,9 @@ e2e     = the same pass through the C ABI with HOST buffers: document/table uplo
 --impl reference = the CPU restatement of the reference's algorithm (oracle/c, all host cores).
 
 Multi-GPU (torchrun), weak scaling: ONE document of base_len * G characters.  Its sum-check is
-sharded by low index bits; the 96 bytes per rank per round are exchanged by the library's own
-P2P mailbox kernel over NVLink peer memory (no NCCL call on that path), every rank runs the same
-transcript.  The fold commitments (latency-bound at 2^14..2^15 terms) are distributed whole,
+sharded by low index bits; the 96 bytes per rank per round are exchanged by the round kernels
+themselves through peer mailboxes over NVLink (P2P stores + system-scope release/acquire; no NCCL
+call on that path), every rank runs the same transcript.  The fold commitments (latency-bound at 2^14..2^15 terms) are distributed whole,
 round-robin over the ranks; MSMs large enough to be throughput-bound are sharded by Pippenger
 windows (one 128-byte all-gather per MSM).
 """
@@ -222,8 +222,7 @@ class GpuPass:
             pq = [int.from_bytes(prev[0][i * 32:(i + 1) * 32], "little") for i in range(ell)]
             pv = int.from_bytes(prev[1], "little")
         sn = self.rb.ShardedNlookup(self.ctxs["doc"], tab, self.rank, self.world, q_list, v_list, pq, pv, "nldoc", w["doc_hash"])
-        res = sn.run(self._gather, self.gbuf.data_ptr())
-        self.ctxs["doc"].p2p_status()
+        res = sn.run_p2p()          # exchange fused into the round kernels (peer mailboxes over NVLink)
         sn.free()
         nxt = le32(res.next_running_claim)
         self.d_futs.append(self.pool["aux"].submit(self._calc_d, nxt))
@@ -594,7 +593,8 @@ def run_reef(args):
                    "streams": "7 contexts/streams: nl sum-check | nldoc sum-check | commit(W) Pallas | commit(W) Vesta | commit(T) Pallas | commit(T) Vesta | calc_d "
                               "(fold i+1 sum-checks overlap fold i commitments; commit(T) does not wait for commit(W); calc_d does not gate the next fold)",
                    "parallelism": (f"1 document of {w['doc_len']} chars: nldoc sum-check sharded by low index bits x{world} "
-                                   f"(96 bytes per rank per round, exchanged by the library's own P2P mailbox kernel over NVLink, no NCCL call); fold commitments (2^14-2^15 terms, latency-bound) distributed "
+                                   f"(96 bytes per rank per round; the round kernels themselves store them into the peers' mailboxes over NVLink and "
+                                   f"acquire the peers' -- no NCCL call, no extra launch); fold commitments (2^14-2^15 terms, latency-bound) distributed "
                                    f"whole, round-robin over the ranks, results exchanged once per pass; MSMs with >= 2^22 "
                                    f"digit entries are sharded by Pippenger windows (128-byte all-gather)") if world > 1 else "single GPU"},
         "e2e": {"value": round(e2e_value, 1), "unit": "NFA steps/s", "ms_per_step": round(e2e_ms / K, 4),

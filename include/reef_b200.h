@@ -180,6 +180,13 @@ int reef_nl_shard_round_local(reef_nl_session* s, void* out_triple_dev);
 int reef_nl_shard_round_finish(reef_nl_session* s, const void* all_triples_dev);
 int reef_nl_shard_export(reef_nl_session* s, void* out_pair_dev);
 int reef_nl_shard_finish(reef_nl_session* s, const void* all_pairs_dev, reef_nlookup_out* out);
+/* The same protocol with the exchange FUSED into the round kernels (needs reef_mailbox_connect on the
+ * session's context, world <= 32): the kernel that sums this rank's round polynomial also stores it
+ * into every peer's mailbox over NVLink, the kernel that runs the transcript first acquires the
+ * peers' triples.  reef_nl_shard_round_p2p = one whole round, stream-ordered, no host wait;
+ * call it ell - log2(world) times, then reef_nl_shard_finish_p2p (export + last rounds + results). */
+int reef_nl_shard_round_p2p(reef_nl_session* s);
+int reef_nl_shard_finish_p2p(reef_nl_session* s, reef_nlookup_out* out);
 void reef_nl_shard_free(reef_nl_session* s);
 
 /* Reference-shaped building blocks (materialised tables), for drop-in use and for the parity

@@ -77,6 +77,8 @@ _sig = {
     "reef_nl_shard_round_local": (C.c_int, [_vp, _vp]),
     "reef_nl_shard_round_finish": (C.c_int, [_vp, _vp]),
     "reef_nl_shard_export": (C.c_int, [_vp, _vp]),
+    "reef_nl_shard_round_p2p": (C.c_int, [_vp]),
+    "reef_nl_shard_finish_p2p": (C.c_int, [_vp, C.POINTER(NlookupOut)]),
     "reef_nl_shard_finish": (C.c_int, [_vp, _vp, C.POINTER(NlookupOut)]),
     "reef_nl_shard_free": (None, [_vp]),
     "reef_gen_eq_table": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp, C.c_uint32, _vp]),

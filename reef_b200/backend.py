@@ -562,6 +562,31 @@ class ShardedNlookup:
                              next_running_claim=int.from_bytes(b["nxt"].raw, "little"),
                              next_running_q=[r[0] for r in rounds])
 
+    def _result(self) -> NlookupResult:
+        b, ell = self._bufs, self.ell
+        rounds = _unpack(b["rounds"].raw[:ell * 4 * 32])
+        rounds = [tuple(rounds[4 * i:4 * i + 4]) for i in range(ell)]
+        return NlookupResult(prev_running_claim=int.from_bytes(b["prev"].raw, "little"),
+                             combined_q=_unpack(b["cq"].raw[:self._o.num_cqs * 32]),
+                             claim_r=int.from_bytes(b["claim"].raw, "little"), rounds=rounds,
+                             sc_last_claim=int.from_bytes(b["last"].raw, "little"),
+                             next_running_claim=int.from_bytes(b["nxt"].raw, "little"),
+                             next_running_q=[r[0] for r in rounds])
+
+    def enqueue_p2p(self):
+        """All local rounds with the exchange fused into the kernels (peer mailboxes); returns without
+        waiting for the device."""
+        for _ in range(self.ell_local):
+            check(lib.reef_nl_shard_round_p2p(self._h))
+
+    def finish_p2p(self) -> NlookupResult:
+        check(lib.reef_nl_shard_finish_p2p(self._h, C.byref(self._o)))
+        return self._result()
+
+    def run_p2p(self) -> NlookupResult:
+        self.enqueue_p2p()
+        return self.finish_p2p()
+
     def run(self, gather, scratch_dev_ptr: int) -> NlookupResult:
         """scratch: device buffer of (world + 1) * 96 bytes owned by the caller."""
         mine, allp = scratch_dev_ptr, scratch_dev_ptr + 96

@@ -876,6 +876,18 @@ int reef_nl_shard_finish(reef_nl_session* s, const void* all_pairs_dev, reef_nlo
   return nl_shard_finish(s, all_pairs_dev, out->claim_r, out->rounds, out->sc_last_claim, out->next_running_claim);
 }
 
+int reef_nl_shard_round_p2p(reef_nl_session* s) {
+  REEF_REQUIRE(s, REEF_EINVAL, "reef_nl_shard_round_p2p: NULL argument");
+  return nl_shard_round_p2p(s);
+}
+
+int reef_nl_shard_finish_p2p(reef_nl_session* s, reef_nlookup_out* out) {
+  REEF_REQUIRE(s && out, REEF_EINVAL, "reef_nl_shard_finish_p2p: NULL argument");
+  REEF_REQUIRE(out->claim_r && out->rounds && out->sc_last_claim && out->next_running_claim, REEF_EINVAL,
+               "reef_nl_shard_finish_p2p: NULL output buffer");
+  return nl_shard_finish_p2p(s, out->claim_r, out->rounds, out->sc_last_claim, out->next_running_claim);
+}
+
 void reef_nl_shard_free(reef_nl_session* s) { nl_shard_free(s); }
 
 int reef_gen_eq_table(reef_ctx* c, const uint8_t* rs, const uint64_t* qs, uint32_t m, const uint8_t* last_q, uint32_t ell,

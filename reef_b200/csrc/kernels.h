@@ -60,6 +60,8 @@ int nl_shard_finish(reef_nl_session* s, const void* d_pairs, uint8_t* out_claim_
                     uint8_t* out_next_v);
 void nl_shard_free(reef_nl_session* s);
 int nl_shard_preload();
+int nl_shard_round_p2p(reef_nl_session* s);
+int nl_shard_finish_p2p(reef_nl_session* s, uint8_t* out_claim_r, uint8_t* out_rounds, uint8_t* out_last_claim, uint8_t* out_next_v);
 int launch_lz(reef_ctx* c, const void* d_matrix, int is_u32, uint64_t rows, uint64_t cols, const uint8_t* h_L,
               uint8_t* h_out);
 

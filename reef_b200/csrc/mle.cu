@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "p2p.cuh"
 
 namespace reef {
 
@@ -890,8 +891,9 @@ int launch_lz(reef_ctx* c, const void* d_matrix, int is_u32, uint64_t rows, uint
 template <bool U32IN>
 __global__ void __launch_bounds__(ROUND_THREADS)
 k_shard_local(const Fq* __restrict__ partials, uint32_t nblk, const void* __restrict__ Tcur, uint64_t L,
-              const uint64_t* __restrict__ sp_pos, const Fq* __restrict__ sp_w, uint32_t m, Fq* __restrict__ out3) {
+              const uint64_t* __restrict__ sp_pos, const Fq* __restrict__ sp_w, uint32_t m, Fq* __restrict__ out3, MbRef mb) {
   __shared__ Fq red[3 * ROUND_THREADS / 32];
+  __shared__ Fq post_sh[3];
   const uint64_t half = L >> 1;
   Fq acc[3];
   acc[0] = acc[1] = acc[2] = fe_zero<FqCfg>();
@@ -917,7 +919,14 @@ k_shard_local(const Fq* __restrict__ partials, uint32_t nblk, const void* __rest
   }
   block_sum<3, ROUND_THREADS>(acc, red);
   if (threadIdx.x == 0)
-    for (int k = 0; k < 3; k++) st256(out3 + k, acc[k]);
+    for (int k = 0; k < 3; k++) {
+      if (out3) st256(out3 + k, acc[k]);
+      post_sh[k] = acc[k];
+    }
+  if (mb.peers) {   // fused exchange: this kernel is also the sender of the round's all-gather
+    __syncthreads();
+    if (threadIdx.x < mb.world) mb_post(mb, threadIdx.x, reinterpret_cast<const uint32_t*>(post_sh), 24);
+  }
 }
 
 // warps 0 and 1 together (threadIdx.x < 64): warp 0 sums the G gathered triples, absorbs
@@ -961,8 +970,14 @@ __device__ __forceinline__ Fq shard_transcript(NlState* st, const Fq* __restrict
 // sweep regime: transcript with the gathered triples, fold A, advance the sparse list
 __global__ void __launch_bounds__(ROUND_THREADS)
 k_shard_apply(NlState* st, const Fq* __restrict__ triples, uint32_t G, uint64_t L, Fq* A, uint64_t a_len,
-              uint64_t* sp_pos, Fq* sp_w, uint32_t m, uint32_t ri, const PoseidonTables* __restrict__ K) {
+              uint64_t* sp_pos, Fq* sp_w, uint32_t m, uint32_t ri, const PoseidonTables* __restrict__ K, MbRef mb) {
   __shared__ Fq r_sh;
+  __shared__ Fq trip_sh[MB_MAX_WORLD * 3];
+  if (mb.peers) {   // fused exchange: this kernel is also the receiver of the round's all-gather
+    if (threadIdx.x < mb.world) mb_wait_copy(mb, threadIdx.x, reinterpret_cast<uint32_t*>(trip_sh + 3 * threadIdx.x), 24);
+    __syncthreads();
+    triples = trip_sh;
+  }
   const uint64_t half = L >> 1;
   if (threadIdx.x < 64) {
     Fq r = shard_transcript(st, triples, G, ri, K);
@@ -1007,8 +1022,9 @@ k_shard_materialize(const NlState* __restrict__ st, const void* __restrict__ Tin
 
 // small regime, local sums of the current round
 __global__ void __launch_bounds__(TAIL_THREADS) k_small_local(const Fq* __restrict__ Ts, const Fq* __restrict__ Es, uint64_t L,
-                                                              Fq* __restrict__ out3) {
+                                                              Fq* __restrict__ out3, MbRef mb) {
   __shared__ Fq red[3 * TAIL_THREADS / 32];
+  __shared__ Fq post_sh[3];
   const uint64_t half = L >> 1;
   Fq acc[3];
   acc[0] = acc[1] = acc[2] = fe_zero<FqCfg>();
@@ -1020,14 +1036,27 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_small_local(const Fq* __restri
   }
   block_sum<3, TAIL_THREADS>(acc, red);
   if (threadIdx.x == 0)
-    for (int k = 0; k < 3; k++) st256(out3 + k, acc[k]);
+    for (int k = 0; k < 3; k++) {
+      if (out3) st256(out3 + k, acc[k]);
+      post_sh[k] = acc[k];
+    }
+  if (mb.peers) {
+    __syncthreads();
+    if (threadIdx.x < mb.world) mb_post(mb, threadIdx.x, reinterpret_cast<const uint32_t*>(post_sh), 24);
+  }
 }
 
 // small regime: transcript with the gathered triples, then fold T_s / E_s in place
 __global__ void __launch_bounds__(TAIL_THREADS)
 k_small_apply(NlState* st, const Fq* __restrict__ triples, uint32_t G, Fq* Ts, Fq* Es, uint64_t L, uint32_t ri,
-              const PoseidonTables* __restrict__ K) {
+              const PoseidonTables* __restrict__ K, MbRef mb) {
   __shared__ Fq r_sh;
+  __shared__ Fq trip_sh[MB_MAX_WORLD * 3];
+  if (mb.peers) {
+    if (threadIdx.x < mb.world) mb_wait_copy(mb, threadIdx.x, reinterpret_cast<uint32_t*>(trip_sh + 3 * threadIdx.x), 24);
+    __syncthreads();
+    triples = trip_sh;
+  }
   const uint64_t half = L >> 1;
   if (threadIdx.x < 64) {
     Fq r = shard_transcript(st, triples, G, ri, K);
@@ -1043,25 +1072,44 @@ k_small_apply(NlState* st, const Fq* __restrict__ triples, uint32_t G, Fq* Ts, F
   }
 }
 
-__global__ void k_shard_export(const Fq* __restrict__ Ts, const Fq* __restrict__ Es, Fq* __restrict__ out2) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    st256(out2 + 0, Ts[0]);
-    st256(out2 + 1, from_mont<FqCfg>(Es[0]));
+__global__ void k_shard_export(const Fq* __restrict__ Ts, const Fq* __restrict__ Es, Fq* __restrict__ out2, MbRef mb) {
+  __shared__ Fq post_sh[2];
+  if (threadIdx.x == 0) {
+    post_sh[0] = Ts[0];
+    post_sh[1] = from_mont<FqCfg>(Es[0]);
+    if (out2) {
+      st256(out2 + 0, post_sh[0]);
+      st256(out2 + 1, post_sh[1]);
+    }
+  }
+  if (mb.peers) {
+    __syncthreads();
+    if (threadIdx.x < mb.world) mb_post(mb, threadIdx.x, reinterpret_cast<const uint32_t*>(post_sh), 16);
   }
 }
 
 // last gamma rounds over the G gathered (T, E) pairs (rank g's pair at index g), identical on
 // every rank; then last claim and next running claim.
 __global__ void __launch_bounds__(64) k_shard_final(NlState* st, const Fq* __restrict__ pairs, uint32_t G, uint32_t ri0,
-                                                    const PoseidonTables* __restrict__ K) {
+                                                    const PoseidonTables* __restrict__ K, MbRef mb) {
   // warp 0 does the work; warp 1 only partners it inside shard_transcript's permutation
   __shared__ Fq Ts[64], Es[64], trip[3];
+  __shared__ Fq pair_sh[MB_MAX_WORLD * 2];
   const int lane = threadIdx.x & 31;
   const bool A = threadIdx.x < 32;
   if (A) {
-    for (uint32_t g = lane; g < G; g += 32) {
-      Ts[g] = ld256(pairs + (uint64_t)g * 2);
-      Es[g] = to_mont<FqCfg>(ld256(pairs + (uint64_t)g * 2 + 1));
+    if (mb.peers) {   // fused exchange: receive the G exported (T, E) pairs
+      if ((uint32_t)lane < mb.world) mb_wait_copy(mb, lane, reinterpret_cast<uint32_t*>(pair_sh + 2 * lane), 16);
+      __syncwarp();
+      for (uint32_t g = lane; g < G; g += 32) {
+        Ts[g] = pair_sh[g * 2];
+        Es[g] = to_mont<FqCfg>(pair_sh[g * 2 + 1]);
+      }
+    } else {
+      for (uint32_t g = lane; g < G; g += 32) {
+        Ts[g] = ld256(pairs + (uint64_t)g * 2);
+        Es[g] = to_mont<FqCfg>(ld256(pairs + (uint64_t)g * 2 + 1));
+      }
     }
     __syncwarp();
   }
@@ -1109,6 +1157,7 @@ struct reef_nl_session {
   reef_ctx* ctx;
   void* d_buf;
   size_t buf_bytes;
+  reef::MbRef mb;     // mailbox exchange fused into the round kernels (peers == nullptr: caller-side exchange)
   const void* d_table;
   int is_u32;
   uint64_t n_loc;
@@ -1163,6 +1212,7 @@ int nl_shard_begin(reef_ctx* c, const NlookupArgs& a, uint32_t rank, uint32_t wo
   char* d = (char*)buf;
   reef_nl_session* s = new reef_nl_session;
   s->buf_bytes = buf_bytes;
+  s->mb = MbRef{nullptr, nullptr, nullptr, 0, 0, 0};
   s->ctx = c;
   s->d_buf = buf;
   s->d_table = a.d_table;
@@ -1225,12 +1275,12 @@ static int nl_shard_round_local_t(reef_nl_session* s, void* d_out3) {
     if (s->round == 0) {
       rc = launch_sweep<U32IN, false>(c, s->d_table, s->n_loc, nullptr, s->st, s->d_A, s->d_B, s->d_part, &nblk);
       if (rc) return rc;
-      k_shard_local<U32IN><<<1, ROUND_THREADS, 0, st>>>(s->d_part, nblk, s->d_table, s->L, s->d_pos, s->d_w, s->m, (Fq*)d_out3);
+      k_shard_local<U32IN><<<1, ROUND_THREADS, 0, st>>>(s->d_part, nblk, s->d_table, s->L, s->d_pos, s->d_w, s->m, (Fq*)d_out3, s->mb);
     } else {
       if (s->round == 1) rc = launch_sweep<U32IN, true>(c, s->d_table, 2 * s->L, s->d_fold, s->st, s->d_A, s->d_B, s->d_part, &nblk);
       else rc = launch_sweep<false, true>(c, s->d_fold, 2 * s->L, s->d_fold, s->st, s->d_A, s->d_B, s->d_part, &nblk);
       if (rc) return rc;
-      k_shard_local<false><<<1, ROUND_THREADS, 0, st>>>(s->d_part, nblk, s->d_fold, s->L, s->d_pos, s->d_w, s->m, (Fq*)d_out3);
+      k_shard_local<false><<<1, ROUND_THREADS, 0, st>>>(s->d_part, nblk, s->d_fold, s->L, s->d_pos, s->d_w, s->m, (Fq*)d_out3, s->mb);
     }
     REEF_LAUNCHED();
     return REEF_OK;
@@ -1242,7 +1292,7 @@ static int nl_shard_round_local_t(reef_nl_session* s, void* d_out3) {
     REEF_LAUNCHED();
     s->small = 1;
   }
-  k_small_local<<<1, TAIL_THREADS, 0, st>>>(s->d_Ts, s->d_Es, s->L, (Fq*)d_out3);
+  k_small_local<<<1, TAIL_THREADS, 0, st>>>(s->d_Ts, s->d_Es, s->L, (Fq*)d_out3, s->mb);
   REEF_LAUNCHED();
   return REEF_OK;
 }
@@ -1257,10 +1307,10 @@ int nl_shard_round_finish(reef_nl_session* s, const void* d_triples) {
   reef_ctx* c = s->ctx;
   cudaStream_t st = c->stream;
   if (!s->small) {
-    k_shard_apply<<<1, ROUND_THREADS, 0, st>>>(s->st, (const Fq*)d_triples, s->world, s->L, s->d_A, s->a_cur, s->d_pos, s->d_w, s->m, s->round, c->d_pos);
+    k_shard_apply<<<1, ROUND_THREADS, 0, st>>>(s->st, (const Fq*)d_triples, s->world, s->L, s->d_A, s->a_cur, s->d_pos, s->d_w, s->m, s->round, c->d_pos, s->mb);
     if (s->a_cur > 1) s->a_cur >>= 1;
   } else {
-    k_small_apply<<<1, TAIL_THREADS, 0, st>>>(s->st, (const Fq*)d_triples, s->world, s->d_Ts, s->d_Es, s->L, s->round, c->d_pos);
+    k_small_apply<<<1, TAIL_THREADS, 0, st>>>(s->st, (const Fq*)d_triples, s->world, s->d_Ts, s->d_Es, s->L, s->round, c->d_pos, s->mb);
   }
   REEF_LAUNCHED();
   s->L >>= 1;
@@ -1270,7 +1320,7 @@ int nl_shard_round_finish(reef_nl_session* s, const void* d_triples) {
 
 int nl_shard_export(reef_nl_session* s, void* d_out2) {
   REEF_REQUIRE(s->round == s->ell_loc && s->small, REEF_EASSERT, "nl_shard_export: local rounds not finished");
-  k_shard_export<<<1, 32, 0, s->ctx->stream>>>(s->d_Ts, s->d_Es, (Fq*)d_out2);
+  k_shard_export<<<1, 32, 0, s->ctx->stream>>>(s->d_Ts, s->d_Es, (Fq*)d_out2, s->mb);
   REEF_LAUNCHED();
   return REEF_OK;
 }
@@ -1280,7 +1330,7 @@ int nl_shard_finish(reef_nl_session* s, const void* d_pairs, uint8_t* out_claim_
   REEF_REQUIRE(s->round == s->ell_loc, REEF_EASSERT, "nl_shard_finish: local rounds not finished");
   reef_ctx* c = s->ctx;
   cudaStream_t st = c->stream;
-  k_shard_final<<<1, 64, 0, st>>>(s->st, (const Fq*)d_pairs, s->world, s->ell_loc, c->d_pos);
+  k_shard_final<<<1, 64, 0, st>>>(s->st, (const Fq*)d_pairs, s->world, s->ell_loc, c->d_pos, s->mb);
   REEF_LAUNCHED();
   void* hs;
   int rc = ctx_stage(c, sizeof(NlState), &hs);
@@ -1293,6 +1343,34 @@ int nl_shard_finish(reef_nl_session* s, const void* d_pairs, uint8_t* out_claim_
     for (int k = 0; k < 4; k++) memcpy(out_rounds + ((size_t)i * 4 + k) * 32, h->out_rounds[i][k].v, 32);
   memcpy(out_last_claim, h->out_last_claim.v, 32);
   memcpy(out_next_v, h->out_next_v.v, 32);
+  return REEF_OK;
+}
+
+// One round with the exchange fused into the kernels: k_shard_local / k_small_local post this rank's
+// triple into every peer's mailbox, k_shard_apply / k_small_apply acquire the peers' triples.
+int nl_shard_round_p2p(reef_nl_session* s) {
+  reef_ctx* c = s->ctx;
+  REEF_REQUIRE(c->mb_world == s->world && c->mb_rank == s->rank && s->world <= MB_MAX_WORLD, REEF_EINVAL,
+               "nl_shard_round_p2p: the context's mailbox is not connected for this rank / world");
+  s->mb = MbRef{c->mb_peers_dev, (const unsigned char*)c->mb_mine, c->mb_err_dev, c->mb_world, c->mb_rank, ++c->mb_seq};
+  int rc = nl_shard_round_local(s, nullptr);
+  if (!rc) rc = nl_shard_round_finish(s, nullptr);
+  s->mb.peers = nullptr;
+  return rc;
+}
+
+int nl_shard_finish_p2p(reef_nl_session* s, uint8_t* out_claim_r, uint8_t* out_rounds, uint8_t* out_last_claim, uint8_t* out_next_v) {
+  reef_ctx* c = s->ctx;
+  REEF_REQUIRE(c->mb_world == s->world && c->mb_rank == s->rank && s->world <= MB_MAX_WORLD, REEF_EINVAL,
+               "nl_shard_finish_p2p: the context's mailbox is not connected for this rank / world");
+  s->mb = MbRef{c->mb_peers_dev, (const unsigned char*)c->mb_mine, c->mb_err_dev, c->mb_world, c->mb_rank, ++c->mb_seq};
+  int rc = nl_shard_export(s, nullptr);
+  if (!rc) rc = nl_shard_finish(s, nullptr, out_claim_r, out_rounds, out_last_claim, out_next_v);
+  s->mb.peers = nullptr;
+  if (rc) return rc;
+  uint32_t e = 0;
+  REEF_CUDA(cudaMemcpy(&e, c->mb_err_dev, 4, cudaMemcpyDeviceToHost));   // nl_shard_finish has synchronised the stream
+  if (e) return fail(REEF_ECUDA, "nl_shard_finish_p2p: a peer never posted exchange " + std::to_string(e & 0x7fffffffu) + " (timed out)");
   return REEF_OK;
 }
 

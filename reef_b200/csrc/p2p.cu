@@ -19,42 +19,16 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "p2p.cuh"
 
 namespace reef {
 
-static constexpr uint32_t MB_ENTRY = 128;
-static constexpr uint32_t MB_SEQ_OFF = 120;
-static constexpr uint32_t MB_MAX_WORLD = 32;
-static constexpr uint32_t MB_SPIN_LIMIT = 1u << 25;   // ~30 s of polling (host-side skew between ranks is legal) before the error flag is raised
-
-__global__ void __launch_bounds__(32) k_p2p_allgather(void* const* __restrict__ peers, const unsigned char* mine, uint32_t world,
-                                                      uint32_t rank, uint32_t seq, const uint32_t* __restrict__ src,
-                                                      uint32_t nwords, uint32_t* __restrict__ dst, uint32_t* err) {
+__global__ void __launch_bounds__(32) k_p2p_allgather(MbRef mb, const uint32_t* __restrict__ src, uint32_t nwords,
+                                                      uint32_t* __restrict__ dst) {
   const uint32_t t = threadIdx.x;
-  if (t >= world) return;
-  const uint32_t slot = seq & 1u;
-  {  // post: thread t writes this rank's payload into peer t's mailbox, then publishes it
-    unsigned char* e = (unsigned char*)peers[t] + ((size_t)slot * world + rank) * MB_ENTRY;
-    volatile uint32_t* w = (volatile uint32_t*)e;
-    for (uint32_t k = 0; k < nwords; k++) w[k] = src[k];
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(e + MB_SEQ_OFF), "r"(seq) : "memory");
-  }
-  {  // wait: thread t acquires rank t's entry in this rank's own mailbox
-    const unsigned char* e = mine + ((size_t)slot * world + t) * MB_ENTRY;
-    uint32_t got = 0, spins = 0;
-    while (true) {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(e + MB_SEQ_OFF) : "memory");
-      if (got == seq || ++spins >= MB_SPIN_LIMIT) break;
-      __nanosleep(64);
-    }
-    if (got != seq) {
-      atomicExch(err, seq | 0x80000000u);
-      return;
-    }
-    const volatile uint32_t* w = (const volatile uint32_t*)e;
-    for (uint32_t k = 0; k < nwords; k++) dst[(size_t)t * nwords + k] = w[k];
-  }
+  if (t >= mb.world) return;
+  mb_post(mb, t, src, nwords);
+  mb_wait_copy(mb, t, dst + (size_t)t * nwords, nwords);
 }
 
 }  // namespace reef
@@ -144,9 +118,8 @@ int reef_p2p_allgather(reef_ctx* c, const void* mine_dev, uint32_t nbytes, void*
   REEF_REQUIRE(nbytes >= 4 && nbytes <= MB_SEQ_OFF && (nbytes & 3) == 0, REEF_EINVAL, "reef_p2p_allgather: payload must be 4..120 bytes, a multiple of 4");
   std::lock_guard<std::mutex> lk(c->mu);
   REEF_CUDA(cudaSetDevice(c->device));
-  const uint32_t seq = ++c->mb_seq;
-  k_p2p_allgather<<<1, 32, 0, c->stream>>>(c->mb_peers_dev, (const unsigned char*)c->mb_mine, c->mb_world, c->mb_rank, seq,
-                                           (const uint32_t*)mine_dev, nbytes / 4, (uint32_t*)out_dev, c->mb_err_dev);
+  MbRef mb{c->mb_peers_dev, (const unsigned char*)c->mb_mine, c->mb_err_dev, c->mb_world, c->mb_rank, ++c->mb_seq};
+  k_p2p_allgather<<<1, 32, 0, c->stream>>>(mb, (const uint32_t*)mine_dev, nbytes / 4, (uint32_t*)out_dev);
   REEF_LAUNCHED();
   return REEF_OK;
 }

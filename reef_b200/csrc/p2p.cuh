@@ -1,0 +1,51 @@
+// Device side of the peer mailbox (see p2p.cu): post this rank's payload into every peer's
+// mailbox over NVLink P2P stores, acquire the peers' payloads from this rank's own mailbox.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace reef {
+
+static constexpr uint32_t MB_ENTRY = 128;
+static constexpr uint32_t MB_SEQ_OFF = 120;
+static constexpr uint32_t MB_MAX_WORLD = 32;
+static constexpr uint32_t MB_SPIN_LIMIT = 1u << 25;   // ~30 s of polling (host-side skew between ranks is legal)
+
+// Passed by value to kernels; peers == nullptr means "no mailbox exchange in this launch".
+struct MbRef {
+  void* const* peers;          // device array: peers[g] = rank g's mailbox (own entry: local pointer)
+  const unsigned char* mine;   // this rank's mailbox
+  uint32_t* err;               // device error flag (a peer never posted)
+  uint32_t world, rank, seq;
+};
+
+#if defined(__CUDACC__)
+// Thread `dest` (< world) stores nwords 32-bit words into rank `dest`'s mailbox and publishes them.
+__device__ __forceinline__ void mb_post(const MbRef& mb, uint32_t dest, const uint32_t* payload, uint32_t nwords) {
+  unsigned char* e = (unsigned char*)mb.peers[dest] + ((size_t)(mb.seq & 1u) * mb.world + mb.rank) * MB_ENTRY;
+  volatile uint32_t* w = (volatile uint32_t*)e;
+  for (uint32_t k = 0; k < nwords; k++) w[k] = payload[k];
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(e + MB_SEQ_OFF), "r"(mb.seq) : "memory");
+}
+
+// Thread `src` (< world) waits for rank `src`'s entry of this exchange and copies it to dst[0..nwords).
+__device__ __forceinline__ bool mb_wait_copy(const MbRef& mb, uint32_t src, uint32_t* dst, uint32_t nwords) {
+  const unsigned char* e = mb.mine + ((size_t)(mb.seq & 1u) * mb.world + src) * MB_ENTRY;
+  uint32_t got = 0, spins = 0;
+  while (true) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(e + MB_SEQ_OFF) : "memory");
+    if (got == mb.seq || ++spins >= MB_SPIN_LIMIT) break;
+    __nanosleep(64);
+  }
+  if (got != mb.seq) {
+    atomicExch(mb.err, mb.seq | 0x80000000u);
+    return false;
+  }
+  const volatile uint32_t* w = (const volatile uint32_t*)e;
+  for (uint32_t k = 0; k < nwords; k++) dst[k] = w[k];
+  return true;
+}
+#endif
+
+}  // namespace reef

@@ -261,9 +261,10 @@ def test_sharded_sumcheck_all_ranks_on_one_gpu(ctx, world, ell, u32, tag):
         r.free()
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("ell,u32,tag", [(11, True, "nldoc"), (13, False, "nlhybrid")])
-def test_sharded_sumcheck_p2p_mailbox_exchange(world, ell, u32, tag):
+def test_sharded_sumcheck_p2p_mailbox_exchange(world, ell, u32, tag, fused):
     """The per-round exchange done by the library's own P2P mailbox kernel (p2p.cu) instead of a
     collective: one context (= one stream) per rank on this GPU, mailboxes connected by device
     pointer; all ranks are enqueued without any host wait and must reproduce the oracle."""
@@ -290,18 +291,34 @@ def test_sharded_sumcheck_p2p_mailbox_exchange(world, ell, u32, tag):
         bufs = [torch.zeros((world + 1) * 96, dtype=torch.uint8, device="cuda") for _ in range(world)]
         torch.cuda.synchronize()
         got = [None] * world
-        for _ in range(ranks[0].ell_local):
+        if fused:                                              # exchange inside the round kernels themselves
+            for _ in range(ranks[0].ell_local):
+                for r in ranks:
+                    check_rc = reef_b200.lib.reef_nl_shard_round_p2p(r._h)
+                    assert check_rc == 0, reef_b200.lib.reef_last_error()
+            # export + final rounds: rank g's finish waits for every peer's export, so all exports are
+            # enqueued by worker threads before any result is read back
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=world) as ex:
+                got = list(ex.map(lambda r: r.finish_p2p(), ranks))
+            ranks_done = True
+        else:
+            ranks_done = False
+        for _ in range(0 if ranks_done else ranks[0].ell_local):
             for g, r in enumerate(ranks):                      # nothing below waits on the host
                 mine, allp = bufs[g].data_ptr(), bufs[g].data_ptr() + 96
                 r.round_local(mine)
                 ctxs[g].p2p_allgather(mine, 96, allp)
                 r.round_finish(allp)
         for g, r in enumerate(ranks):
+            if ranks_done:
+                break
             mine, allp = bufs[g].data_ptr(), bufs[g].data_ptr() + 96
             r.export(mine)
             ctxs[g].p2p_allgather(mine, 64, allp)
         for g, r in enumerate(ranks):
-            got[g] = r.finish(bufs[g].data_ptr() + 96)
+            if not ranks_done:
+                got[g] = r.finish(bufs[g].data_ptr() + 96)
             ctxs[g].p2p_status()
         for g in range(world):
             assert got[g].claim_r == exp["claim_r"]

@@ -65,6 +65,25 @@ WORKLOADS = {
 }
 
 
+ASCII_AB = "".join(chr(c) for c in range(128))        # config.rs: the `ascii` alphabet
+
+
+def curve_multiples(p: int, n: int):
+    """[G, 2G, ..., nG] on y^2 = x^3 + 5 over F_p with G = (-1, 2): distinct generators for the synthetic
+    commitment keys (input generation only; kept here so that the GPU arm imports nothing from oracle/)."""
+    gx, gy = p - 1, 2
+    pts, (x, y) = [], (gx, gy)
+    for k in range(n):
+        pts.append((x, y))
+        if x == gx and y == gy:                      # doubling G
+            lam = 3 * x * x * pow(2 * y, -1, p) % p
+        else:
+            lam = (y - gy) * pow(x - gx, -1, p) % p
+        x3 = (lam * lam - x - gx) % p
+        x, y = x3, (lam * (x - x3) - y) % p
+    return pts
+
+
 def le32(x: int) -> bytes:
     return int(x).to_bytes(32, "little")
 
@@ -77,12 +96,11 @@ def pack(xs) -> bytes:
 # synthetic workload (deterministic; the same bytes feed the GPU arm and the reference arm)
 # --------------------------------------------------------------------------------------------
 def make_workload(name: str, seed_shift: int = 0, world: int = 1):
-    from oracle.curves import PALLAS, VESTA          # test-infra helper used only to GENERATE inputs
-    from oracle.nlookup import ASCII_AB, doc_transform
+    import reef_b200                                  # host-side logic only here (doc_transform, logmn): no GPU needed
+    doc_transform, _logmn = reef_b200.doc_transform, reef_b200.logmn
     w = dict(WORKLOADS[name])
     rnd = random.Random(1234 + seed_shift)
     w["doc_len"] = w["doc_len"] * world          # weak scaling: one document of base_len * G characters
-    from oracle.nlookup import logmn as _logmn
     if (1 << _logmn(w["doc_len"] + 2)) < w["doc_len"] + 2:
         # The reference's f32 `logmn` (costs.rs:10-15) mis-rounds 2^22+2 and 2^23+2, so its doc_transform
         # panics on documents of exactly 2^22 / 2^23 characters (framework.rs:1007): 64 more characters
@@ -121,8 +139,8 @@ def make_workload(name: str, seed_shift: int = 0, world: int = 1):
         return np.ascontiguousarray(raw)
 
     # generators k*G: distinct, cheap, and the expected MSM result is checkable
-    w["bases_pri"] = b"".join(le32(P[0]) + le32(P[1]) for P in PALLAS.multiples(w["n_pri"]))
-    w["bases_sec"] = b"".join(le32(P[0]) + le32(P[1]) for P in VESTA.multiples(w["n_sec"]))
+    w["bases_pri"] = b"".join(le32(P[0]) + le32(P[1]) for P in curve_multiples(FP, w["n_pri"]))     # Pallas: over Fp
+    w["bases_sec"] = b"".join(le32(P[0]) + le32(P[1]) for P in curve_multiples(FQ, w["n_sec"]))     # Vesta: over Fq
     w["sc"] = [dict(Wp=scalars(w["n_pri"], FQ, True), Tp=scalars(w["n_pri"], FQ, False),
                     Ws=scalars(w["n_sec"], FP, True), Ts=scalars(w["n_sec"], FP, False)) for _ in range(S)]
     return w
@@ -617,9 +635,8 @@ def msm_large(ctx, lg, peak):
     """MSM Mop/s vs the modmul roofline at n = 2^lg (BASELINE.json metric, second half)."""
     import torch
     import reef_b200
-    from oracle.curves import PALLAS           # input generation only
     n = 1 << lg
-    pts = PALLAS.multiples(n)
+    pts = curve_multiples(FP, n)
     bases = reef_b200.Bases(ctx, "pallas", b"".join(le32(P[0]) + le32(P[1]) for P in pts))
     raw = np.random.default_rng(lg).integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
     raw[:, 3] &= (1 << 61) - 1

@@ -22,6 +22,7 @@
 //   * Fiat-Shamir runs on device (warp-cooperative Poseidon), so a whole nlookup is a chain of
 //     stream-ordered launches with no host round trip.
 #include <cstring>
+#include <memory>
 #include <type_traits>
 #include <vector>
 
@@ -622,7 +623,7 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
   }
   // tail: fold with the last sweep challenge (if any) and finish
   const size_t tail_smem = (size_t)(2 * CHUNK + 3 * TAIL_THREADS / 32) * sizeof(Fq);
-  ProfScope* tail_scope = new ProfScope(c, PROF_TAIL, L);
+  std::unique_ptr<ProfScope> tail_scope(new ProfScope(c, PROF_TAIL, L));
   if (n_sweeps == 0) {
     REEF_CUDA(cudaFuncSetAttribute(k_tail<U32IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
     k_tail<U32IN><<<1, TAIL_THREADS, tail_smem, s>>>(st, a.d_table, N, 0, d_A, d_B, d_pos, d_w, m, 0, c->d_pos);
@@ -634,7 +635,7 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
     REEF_CUDA(cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
     k_tail<false><<<1, TAIL_THREADS, tail_smem, s>>>(st, t_cur, 2 * L, 1, d_A, d_B, d_pos, d_w, m, n_sweeps, c->d_pos);
   }
-  delete tail_scope;
+  tail_scope.reset();
   REEF_LAUNCHED();
 
   // results

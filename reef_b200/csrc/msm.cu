@@ -19,6 +19,7 @@
 //   * weighted bucket sum  sum_v v * B_v  by bit decomposition: c masked tree reductions
 //     (warp-shuffle + shared memory) run as independent CTAs, then 2^t scaling in parallel.
 #include <cstring>
+#include <memory>
 #include <vector>
 
 #include "common.cuh"
@@ -635,7 +636,7 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
   Affine<C>* res_aff = (Affine<C>*)(res_xyzz + 1);
   XYZZ<C>* extra = (XYZZ<C>*)(d + o_extra);
 
-  ProfScope* scope = new ProfScope(c, PROF_MSM_SORT, n_entries);
+  std::unique_ptr<ProfScope> scope(new ProfScope(c, PROF_MSM_SORT, n_entries));
   REEF_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(nb + 2) * 4, s));
   if (a.scalars_u32) k_digits<true><<<cdiv(n, 256), 256, 0, s>>>(a.d_scalars, n, a.n_bases, pl, a.w_begin, a.w_end, keys, vals);
   else k_digits<false><<<cdiv(n, 256), 256, 0, s>>>(a.d_scalars, n, a.n_bases, pl, a.w_begin, a.w_end, keys, vals);
@@ -650,12 +651,12 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
   const uint32_t kfirst = n_entries / (2 * K_FIRST) >= (uint64_t)c->sm_count * 2048 ? 2 * K_FIRST : K_FIRST;
   k_scan<<<1, 1024, 0, s>>>(cnt, nb, kfirst, pcnt[0], poff[0], nullptr, tm + 2);
   REEF_LAUNCHED();
-  delete scope;
+  scope.reset();
   uint32_t h_tm[4];
   REEF_CUDA(cudaMemcpyAsync(h_tm, tm, 16, cudaMemcpyDeviceToHost, s));
   REEF_CUDA(cudaStreamSynchronize(s));
   uint32_t n_parts = h_tm[2], max_cnt = h_tm[3];   // parts of pass 1, largest per-bucket part count
-  scope = new ProfScope(c, PROF_MSM_ACCUM, n_entries);
+  scope.reset(new ProfScope(c, PROF_MSM_ACCUM, n_entries));
   if (n_parts) {
     k_accum_first<C><<<cdiv(n_parts, 128), 128, 0, s>>>(sorted, start, cnt, poff[0], nb, n_parts, kfirst, (const Affine<C>*)a.d_levels,
                                                        parts[0]);
@@ -677,8 +678,8 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
     n_parts = n_next;
     cur = nxt;
   }
-  delete scope;
-  scope = new ProfScope(c, PROF_MSM_REDUCE, nb);
+  scope.reset();
+  scope.reset(new ProfScope(c, PROF_MSM_REDUCE, nb));
   k_gather_buckets<C><<<cdiv(nb, 256), 256, 0, s>>>(parts[cur], poff[cur], pcnt[cur], nb, buckets);
   REEF_LAUNCHED();
   k_bitsum_partial<C><<<dim3(nblk, P.c, P.G), 256, 0, s>>>(buckets, P.B, bpt, bitpart);
@@ -687,7 +688,7 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
   k_bitsum_final<C><<<1, 1024, 0, s>>>(bitpart, nblk, P.c, P.G, P.c * P.L, a.h_out_xyzz ? res_xyzz : nullptr,
                                        a.h_out_affine ? res_aff : nullptr, extra, a.n_extra);
   REEF_LAUNCHED();
-  delete scope;
+  scope.reset();
   if (a.h_out_xyzz) {
     k_xyzz_from_mont<C><<<1, 32, 0, s>>>(res_xyzz);
     REEF_LAUNCHED();
@@ -750,7 +751,7 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
   XYZZ<C>* bitpart = (XYZZ<C>*)(d + o_bitpart);
   Affine<C>* d_out = (Affine<C>*)(d + o_out);
 
-  ProfScope* scope = new ProfScope(c, PROF_MSM_SORT, n_entries);
+  std::unique_ptr<ProfScope> scope(new ProfScope(c, PROF_MSM_SORT, n_entries));
   REEF_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(nb + 2) * 4, s));
   if (a.scalars_u32) k_digits_rows<true><<<cdiv(n_terms, 256), 256, 0, s>>>(a.d_scalars, a.rows, a.cols, 0, a.n_bases, pl, w_used, 0, keys, vals);
   else k_digits_rows<false><<<cdiv(n_terms, 256), 256, 0, s>>>(a.d_scalars, a.rows, a.cols, 0, a.n_bases, pl, w_used, 0, keys, vals);
@@ -768,12 +769,12 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
   const uint32_t kfirst = n_entries / (2 * K_FIRST) >= (uint64_t)c->sm_count * 2048 ? 2 * K_FIRST : K_FIRST;
   k_scan<<<1, 1024, 0, s>>>(cnt, nb, kfirst, pcnt[0], poff[0], nullptr, tm + 2);
   REEF_LAUNCHED();
-  delete scope;
+  scope.reset();
   uint32_t h_tm[4];
   REEF_CUDA(cudaMemcpyAsync(h_tm, tm, 16, cudaMemcpyDeviceToHost, s));
   REEF_CUDA(cudaStreamSynchronize(s));
   uint32_t n_parts = h_tm[2], max_cnt = h_tm[3];
-  scope = new ProfScope(c, PROF_MSM_ACCUM, n_entries);
+  scope.reset(new ProfScope(c, PROF_MSM_ACCUM, n_entries));
   if (n_parts) {
     k_accum_first<C><<<cdiv(n_parts, 128), 128, 0, s>>>(sorted, start, cnt, poff[0], nb, n_parts, kfirst, (const Affine<C>*)a.d_levels, parts[0]);
     REEF_LAUNCHED();
@@ -793,15 +794,15 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
     n_parts = n_next;
     cur = nxt;
   }
-  delete scope;
-  scope = new ProfScope(c, PROF_MSM_REDUCE, nb);
+  scope.reset();
+  scope.reset(new ProfScope(c, PROF_MSM_REDUCE, nb));
   k_gather_buckets<C><<<cdiv(nb, 256), 256, 0, s>>>(parts[cur], poff[cur], pcnt[cur], nb, buckets);
   REEF_LAUNCHED();
   k_bitsum_partial<C><<<dim3(nblk, P.c, (unsigned)a.rows), 256, 0, s>>>(buckets, P.B, bpt, bitpart);
   REEF_LAUNCHED();
   k_rows_final<C><<<(unsigned)a.rows, 512, 0, s>>>(bitpart, nblk, P.c, d_out);
   REEF_LAUNCHED();
-  delete scope;
+  scope.reset();
   REEF_CUDA(cudaMemcpyAsync(a.h_out, d_out, (size_t)a.rows * sizeof(Affine<C>), cudaMemcpyDeviceToHost, s));
   REEF_CUDA(cudaStreamSynchronize(s));
   return REEF_OK;

@@ -1254,10 +1254,13 @@ int nl_shard_begin(reef_ctx* c, const NlookupArgs& a, uint32_t rank, uint32_t wo
       (a.m && cudaMemcpyAsync(s->d_q, a.h_q, (size_t)a.m * 8, cudaMemcpyHostToDevice, st) != cudaSuccess))
     return bail(fail(REEF_ECUDA, "nl_shard_begin: upload failed"));
   Fq tag = fq_mont_from_le32(a.tag_le);
-  k_nl_begin<<<1, 64, 0, st>>>(s->st, s->d_query, a.n_query, tag, s->d_prevq, a.ell, s->d_q, a.m, s->d_pos, s->d_w, c->d_pos, rank, world);
-  g_launches.fetch_add(1);
-  k_eq_tables<<<ceil_div_u(a_len + b_len, 128), 128, 0, st>>>(s->st, ell_loc, hb, s->d_A, a_len, s->d_B, b_len, gamma, rank);
-  g_launches.fetch_add(1);
+  {
+    ProfScope ps(c, PROF_NL_SETUP, n_loc);
+    k_nl_begin<<<1, 64, 0, st>>>(s->st, s->d_query, a.n_query, tag, s->d_prevq, a.ell, s->d_q, a.m, s->d_pos, s->d_w, c->d_pos, rank, world);
+    g_launches.fetch_add(1);
+    k_eq_tables<<<ceil_div_u(a_len + b_len, 128), 128, 0, st>>>(s->st, ell_loc, hb, s->d_A, a_len, s->d_B, b_len, gamma, rank);
+    g_launches.fetch_add(1);
+  }
   if (cudaGetLastError() != cudaSuccess) return bail(fail(REEF_ECUDA, "nl_shard_begin: launch failed"));
   cudaStreamSynchronize(st);   // the host staging vectors of the caller may go away
   *out = s;
@@ -1274,18 +1277,27 @@ static int nl_shard_round_local_t(reef_nl_session* s, void* d_out3) {
     uint32_t nblk = 0;
     int rc;
     if (s->round == 0) {
-      rc = launch_sweep<U32IN, false>(c, s->d_table, s->n_loc, nullptr, s->st, s->d_A, s->d_B, s->d_part, &nblk);
-      if (rc) return rc;
+      {
+        ProfScope ps(c, PROF_SWEEP_FIRST, s->n_loc);
+        rc = launch_sweep<U32IN, false>(c, s->d_table, s->n_loc, nullptr, s->st, s->d_A, s->d_B, s->d_part, &nblk);
+        if (rc) return rc;
+      }
+      ProfScope ps(c, PROF_ROUND, s->L);
       k_shard_local<U32IN><<<1, ROUND_THREADS, 0, st>>>(s->d_part, nblk, s->d_table, s->L, s->d_pos, s->d_w, s->m, (Fq*)d_out3, s->mb);
     } else {
-      if (s->round == 1) rc = launch_sweep<U32IN, true>(c, s->d_table, 2 * s->L, s->d_fold, s->st, s->d_A, s->d_B, s->d_part, &nblk);
-      else rc = launch_sweep<false, true>(c, s->d_fold, 2 * s->L, s->d_fold, s->st, s->d_A, s->d_B, s->d_part, &nblk);
-      if (rc) return rc;
+      {
+        ProfScope ps(c, PROF_SWEEP_FOLD, 2 * s->L);
+        if (s->round == 1) rc = launch_sweep<U32IN, true>(c, s->d_table, 2 * s->L, s->d_fold, s->st, s->d_A, s->d_B, s->d_part, &nblk);
+        else rc = launch_sweep<false, true>(c, s->d_fold, 2 * s->L, s->d_fold, s->st, s->d_A, s->d_B, s->d_part, &nblk);
+        if (rc) return rc;
+      }
+      ProfScope ps(c, PROF_ROUND, s->L);
       k_shard_local<false><<<1, ROUND_THREADS, 0, st>>>(s->d_part, nblk, s->d_fold, s->L, s->d_pos, s->d_w, s->m, (Fq*)d_out3, s->mb);
     }
     REEF_LAUNCHED();
     return REEF_OK;
   }
+  ProfScope ps_tail(c, PROF_TAIL, s->L);
   if (!s->small) {   // enter the small regime
     if (s->round == 0) k_shard_materialize<U32IN><<<1, TAIL_THREADS, 0, st>>>(s->st, s->d_table, s->n_loc, 0, s->d_A, s->d_B, s->d_pos, s->d_w, s->m, s->d_Ts, s->d_Es);
     else if (s->round == 1) k_shard_materialize<U32IN><<<1, TAIL_THREADS, 0, st>>>(s->st, s->d_table, 2 * s->L, 1, s->d_A, s->d_B, s->d_pos, s->d_w, s->m, s->d_Ts, s->d_Es);
@@ -1307,6 +1319,7 @@ int nl_shard_round_finish(reef_nl_session* s, const void* d_triples) {
   REEF_REQUIRE(s->round < s->ell_loc, REEF_EASSERT, "nl_shard_round_finish: all local rounds are done");
   reef_ctx* c = s->ctx;
   cudaStream_t st = c->stream;
+  ProfScope ps(c, s->small ? PROF_TAIL : PROF_ROUND, s->L);
   if (!s->small) {
     k_shard_apply<<<1, ROUND_THREADS, 0, st>>>(s->st, (const Fq*)d_triples, s->world, s->L, s->d_A, s->a_cur, s->d_pos, s->d_w, s->m, s->round, c->d_pos, s->mb);
     if (s->a_cur > 1) s->a_cur >>= 1;
@@ -1331,8 +1344,11 @@ int nl_shard_finish(reef_nl_session* s, const void* d_pairs, uint8_t* out_claim_
   REEF_REQUIRE(s->round == s->ell_loc, REEF_EASSERT, "nl_shard_finish: local rounds not finished");
   reef_ctx* c = s->ctx;
   cudaStream_t st = c->stream;
-  k_shard_final<<<1, 64, 0, st>>>(s->st, (const Fq*)d_pairs, s->world, s->ell_loc, c->d_pos, s->mb);
-  REEF_LAUNCHED();
+  {
+    ProfScope ps(c, PROF_TAIL, s->world);
+    k_shard_final<<<1, 64, 0, st>>>(s->st, (const Fq*)d_pairs, s->world, s->ell_loc, c->d_pos, s->mb);
+    REEF_LAUNCHED();
+  }
   void* hs;
   int rc = ctx_stage(c, sizeof(NlState), &hs);
   if (rc) return rc;

@@ -120,3 +120,30 @@ def test_hyrax_row_commit_document_shape(ctx, ell, bits):
     for r in list(range(4)) + [rows // 2, rows - 1]:
         k = (int((M[r].astype(object) * w).sum()) + blinds[r] * (cols + 1)) % cv.order
         assert got[r] == cv.mul(k, cv.gen), r
+
+
+def test_msm_throughput_shapes_known_discrete_logs(ctx):
+    """n = 2^18 takes the large-instance code paths (16-entry first pass, 4-lane combine groups, bucket sums
+    ahead of the bit-decomposition tree): same closed form, plus the all-equal-scalar histogram and a
+    Vesta run."""
+    import numpy as np
+    import torch
+    n = 1 << 18
+    for curve in ("pallas", "vesta"):
+        cv = CUR[curve]
+        pts = cv.multiples(n)
+        b = ctx.bases(curve, b"".join(int(P[0]).to_bytes(32, "little") + int(P[1]).to_bytes(32, "little") for P in pts))
+        assert b.window_bits >= 14
+        raw = np.random.default_rng(18).integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
+        raw[:, 3] &= (1 << 61) - 1                                    # < 2^253 < both group orders
+        words = raw.astype(object)
+        sc = [int(w[0]) | (int(w[1]) << 64) | (int(w[2]) << 128) | (int(w[3]) << 192) for w in words]
+        dev = torch.from_numpy(raw.view(np.int64)).cuda()
+        exp = cv.mul(sum(s * (k + 1) for k, s in enumerate(sc)) % cv.order, cv.gen)
+        assert b.msm_dev(dev.data_ptr(), n) == exp
+        if curve == "pallas":
+            s = sc[7]
+            eq = np.tile(raw[7], (n, 1))
+            dev2 = torch.from_numpy(np.ascontiguousarray(eq).view(np.int64)).cuda()
+            assert b.msm_dev(dev2.data_ptr(), n) == cv.mul(s * (n * (n + 1) // 2) % cv.order, cv.gen)
+        b.free()

@@ -161,13 +161,14 @@ def test_nlookup_rejects_what_the_reference_asserts(ctx):
     assert e.value.code == 3
 
 
-def test_nlookup_full_size_properties(ctx):
-    """cfg-3/4 size (N = 2^21, u32 document): too big for the Python oracle, so check the
+@pytest.mark.parametrize("ell", [21, 23])
+def test_nlookup_full_size_properties(ctx, ell):
+    """cfg-3/4 size (N = 2^21) and cfg-5 size (N = 2^23, the deepest sweep shape: 32 pairs per lane),
+    u32 document: too big for the Python oracle, so check the
     size-independent properties: claim identity, per-round g(0)+g(1), last claim, and that the
     next running claim is the MLE of the table at the challenges (recomputed independently by
     the GPU fold path AND, for the claim identity, from plain lookups)."""
     rnd = random.Random(9)
-    ell = 21
     n = 1 << ell
     import numpy as np
     codes = np.random.default_rng(21).integers(0, 131, size=n, dtype=np.uint32)

@@ -538,9 +538,9 @@ def run_reef(args):
     clock_windows = []
     clk = sample_clocks_start() if rank == 0 else (None, None)
     ms, wall_ms, launches, _, _ = timed(gp, True, K, Wm, False)
-    _, _, _, _, prof = timed(gp, True, K, 1, True)
+    _, _, _, _, prof = timed(gp, True, K, Wm, True)
     clocks = sample_clocks_stop(*clk, device=dev, windows=clock_windows) if rank == 0 else None
-    e2e_ms, _, _, _, _ = timed(gp, False, K, max(1, Wm // 2), False)
+    e2e_ms, _, _, _, _ = timed(gp, False, K, Wm, False)
     also = None
     if world == 1 and args.also and args.also != args.workload:
         # the second workload (configs[1] by default): same pass, value and e2e only
@@ -549,7 +549,7 @@ def run_reef(args):
         gp2.prepare_queries()
         gp2.make_resident()
         ms2, _, launches2, _, _ = timed(gp2, True, K, Wm, False)
-        e2e2, _, _, _, _ = timed(gp2, False, K, max(1, Wm // 2), False)
+        e2e2, _, _, _, _ = timed(gp2, False, K, Wm, False)
         h2d2, d2h2 = gp2.bytes_per_step()
         also = {"workload": args.also + ": " + w2["desc"], "value": round(w2["doc_len"] / (ms2 / K / 1e3), 1),
                 "ms_per_step": round(ms2 / K, 4), "gpu_launches": launches2,

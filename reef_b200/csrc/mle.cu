@@ -21,7 +21,9 @@
 //     shared memory.
 //   * Fiat-Shamir runs on device (warp-cooperative Poseidon), so a whole nlookup is a chain of
 //     stream-ordered launches with no host round trip.
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <memory>
 #include <type_traits>
 #include <vector>
@@ -534,6 +536,38 @@ k_tail(NlState* st, const void* __restrict__ Tin, uint64_t L_in, int do_fold, co
 // ---------------------------------------------------------------------------------------
 static unsigned ceil_div_u(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 
+// Dynamic shared-memory size that makes a single-CTA transcript kernel the ONLY resident CTA of its
+// SM: every CTA needs at least the 1 KiB the system reserves per block, so a CTA that holds all the
+// opt-in shared memory cannot get a neighbour.  The Fiat-Shamir warps are issue-latency bound; MSM or
+// sweep CTAs co-scheduled on the same SM sub-partitions slow the critical path by 5-15 %
+// (REEF_TRANSCRIPT_EXCLUSIVE=0 turns the reservation off).
+static size_t exclusive_smem(reef_ctx* c, const void* kernel, size_t need) {
+  static const bool on = !(getenv("REEF_TRANSCRIPT_EXCLUSIVE") && atoi(getenv("REEF_TRANSCRIPT_EXCLUSIVE")) == 0);
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, size_t>> cache;
+  if (!on) {
+    if (need) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+    return need;
+  }
+  std::lock_guard<std::mutex> lk(mu);
+  for (auto& kv : cache)
+    if (kv.first == kernel) return kv.second;
+  cudaFuncAttributes fa;
+  int optin = 0;
+  size_t dyn = need;
+  if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess &&
+      cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) == cudaSuccess &&
+      (size_t)optin > fa.sharedSizeBytes + need)
+    dyn = (size_t)optin - fa.sharedSizeBytes;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) {
+    cudaGetLastError();
+    dyn = need;
+    if (need) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+  }
+  cache.emplace_back(kernel, dyn);
+  return dyn;
+}
+
 template <bool U32IN>
 static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
   const uint32_t ell = a.ell;
@@ -585,7 +619,7 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
   Fq tag = fq_mont_from_le32(a.tag_le);
   {
     ProfScope ps(c, PROF_NL_SETUP, N);
-    k_nl_begin<<<1, 64, 0, s>>>(st, d_query, a.n_query, tag, d_prevq, ell, d_q, m, d_pos, d_w, c->d_pos, 0, 1);
+    k_nl_begin<<<1, 64, exclusive_smem(c, (const void*)k_nl_begin, 0), s>>>(st, d_query, a.n_query, tag, d_prevq, ell, d_q, m, d_pos, d_w, c->d_pos, 0, 1);
     REEF_LAUNCHED();
     k_eq_tables<<<ceil_div_u(a_len + b_len, 128), 128, 0, s>>>(st, ell, hb, d_A, a_len, d_B, b_len, 0, 0);
     REEF_LAUNCHED();
@@ -604,7 +638,7 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
         if (rc) return rc;
       }
       ProfScope ps(c, PROF_ROUND, L);
-      k_round<U32IN><<<1, ROUND_THREADS, 0, s>>>(st, d_part, nblk, a.d_table, L, d_A, a_cur, d_pos, d_w, m, i, c->d_pos);
+      k_round<U32IN><<<1, ROUND_THREADS, exclusive_smem(c, (const void*)k_round<U32IN>, 0), s>>>(st, d_part, nblk, a.d_table, L, d_A, a_cur, d_pos, d_w, m, i, c->d_pos);
       REEF_LAUNCHED();
     } else {
       {
@@ -614,7 +648,7 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
         if (rc) return rc;
       }
       ProfScope ps(c, PROF_ROUND, L);
-      k_round<false><<<1, ROUND_THREADS, 0, s>>>(st, d_part, nblk, d_fold, L, d_A, a_cur, d_pos, d_w, m, i, c->d_pos);
+      k_round<false><<<1, ROUND_THREADS, exclusive_smem(c, (const void*)k_round<false>, 0), s>>>(st, d_part, nblk, d_fold, L, d_A, a_cur, d_pos, d_w, m, i, c->d_pos);
       REEF_LAUNCHED();
       t_cur = d_fold;
     }
@@ -625,15 +659,12 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
   const size_t tail_smem = (size_t)(2 * CHUNK + 3 * TAIL_THREADS / 32) * sizeof(Fq);
   std::unique_ptr<ProfScope> tail_scope(new ProfScope(c, PROF_TAIL, L));
   if (n_sweeps == 0) {
-    REEF_CUDA(cudaFuncSetAttribute(k_tail<U32IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
-    k_tail<U32IN><<<1, TAIL_THREADS, tail_smem, s>>>(st, a.d_table, N, 0, d_A, d_B, d_pos, d_w, m, 0, c->d_pos);
+    k_tail<U32IN><<<1, TAIL_THREADS, exclusive_smem(c, (const void*)k_tail<U32IN>, tail_smem), s>>>(st, a.d_table, N, 0, d_A, d_B, d_pos, d_w, m, 0, c->d_pos);
   } else if (n_sweeps == 1) {
     // L is now 2^h: the table to fold is still the caller's (length 2L)
-    REEF_CUDA(cudaFuncSetAttribute(k_tail<U32IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
-    k_tail<U32IN><<<1, TAIL_THREADS, tail_smem, s>>>(st, a.d_table, 2 * L, 1, d_A, d_B, d_pos, d_w, m, n_sweeps, c->d_pos);
+    k_tail<U32IN><<<1, TAIL_THREADS, exclusive_smem(c, (const void*)k_tail<U32IN>, tail_smem), s>>>(st, a.d_table, 2 * L, 1, d_A, d_B, d_pos, d_w, m, n_sweeps, c->d_pos);
   } else {
-    REEF_CUDA(cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
-    k_tail<false><<<1, TAIL_THREADS, tail_smem, s>>>(st, t_cur, 2 * L, 1, d_A, d_B, d_pos, d_w, m, n_sweeps, c->d_pos);
+    k_tail<false><<<1, TAIL_THREADS, exclusive_smem(c, (const void*)k_tail<false>, tail_smem), s>>>(st, t_cur, 2 * L, 1, d_A, d_B, d_pos, d_w, m, n_sweeps, c->d_pos);
   }
   tail_scope.reset();
   REEF_LAUNCHED();

@@ -1287,7 +1287,7 @@ int nl_shard_begin(reef_ctx* c, const NlookupArgs& a, uint32_t rank, uint32_t wo
   Fq tag = fq_mont_from_le32(a.tag_le);
   {
     ProfScope ps(c, PROF_NL_SETUP, n_loc);
-    k_nl_begin<<<1, 64, 0, st>>>(s->st, s->d_query, a.n_query, tag, s->d_prevq, a.ell, s->d_q, a.m, s->d_pos, s->d_w, c->d_pos, rank, world);
+    k_nl_begin<<<1, 64, exclusive_smem(c, (const void*)k_nl_begin, 0), st>>>(s->st, s->d_query, a.n_query, tag, s->d_prevq, a.ell, s->d_q, a.m, s->d_pos, s->d_w, c->d_pos, rank, world);
     g_launches.fetch_add(1);
     k_eq_tables<<<ceil_div_u(a_len + b_len, 128), 128, 0, st>>>(s->st, ell_loc, hb, s->d_A, a_len, s->d_B, b_len, gamma, rank);
     g_launches.fetch_add(1);
@@ -1352,10 +1352,10 @@ int nl_shard_round_finish(reef_nl_session* s, const void* d_triples) {
   cudaStream_t st = c->stream;
   ProfScope ps(c, s->small ? PROF_TAIL : PROF_ROUND, s->L);
   if (!s->small) {
-    k_shard_apply<<<1, ROUND_THREADS, 0, st>>>(s->st, (const Fq*)d_triples, s->world, s->L, s->d_A, s->a_cur, s->d_pos, s->d_w, s->m, s->round, c->d_pos, s->mb);
+    k_shard_apply<<<1, ROUND_THREADS, exclusive_smem(c, (const void*)k_shard_apply, 0), st>>>(s->st, (const Fq*)d_triples, s->world, s->L, s->d_A, s->a_cur, s->d_pos, s->d_w, s->m, s->round, c->d_pos, s->mb);
     if (s->a_cur > 1) s->a_cur >>= 1;
   } else {
-    k_small_apply<<<1, TAIL_THREADS, 0, st>>>(s->st, (const Fq*)d_triples, s->world, s->d_Ts, s->d_Es, s->L, s->round, c->d_pos, s->mb);
+    k_small_apply<<<1, TAIL_THREADS, exclusive_smem(c, (const void*)k_small_apply, 0), st>>>(s->st, (const Fq*)d_triples, s->world, s->d_Ts, s->d_Es, s->L, s->round, c->d_pos, s->mb);
   }
   REEF_LAUNCHED();
   s->L >>= 1;
@@ -1377,7 +1377,7 @@ int nl_shard_finish(reef_nl_session* s, const void* d_pairs, uint8_t* out_claim_
   cudaStream_t st = c->stream;
   {
     ProfScope ps(c, PROF_TAIL, s->world);
-    k_shard_final<<<1, 64, 0, st>>>(s->st, (const Fq*)d_pairs, s->world, s->ell_loc, c->d_pos, s->mb);
+    k_shard_final<<<1, 64, exclusive_smem(c, (const void*)k_shard_final, 0), st>>>(s->st, (const Fq*)d_pairs, s->world, s->ell_loc, c->d_pos, s->mb);
     REEF_LAUNCHED();
   }
   void* hs;

@@ -84,6 +84,10 @@ def curve_multiples(p: int, n: int):
     return pts
 
 
+class ParityError(AssertionError):
+    """The multi-GPU path produced a result that differs from the single-GPU path."""
+
+
 def le32(x: int) -> bytes:
     return int(x).to_bytes(32, "little")
 
@@ -264,7 +268,7 @@ class GpuPass:
             r = self.ctxs["nl"].wit_nlookup_gadget(full, q, v, pq, pv, "nldoc", w["doc_hash"])
             prev_f = (pack(r.next_running_q), le32(r.next_running_claim))
             if prev_s != prev_f:
-                raise RuntimeError(f"rank {self.rank}: sharded sum-check of fold {s} differs from the un-sharded one")
+                raise ParityError(f"rank {self.rank}: sharded sum-check of fold {s} differs from the un-sharded one")
         for f in self.d_futs:
             f.result()
         full.free()
@@ -273,7 +277,7 @@ class GpuPass:
         self.dist.all_gather_into_tensor(allv, mine)
         host = allv.cpu().numpy().tobytes()
         if any(host[g * 32:(g + 1) * 32] != prev_s[1] for g in range(self.world)):
-            raise RuntimeError("ranks disagree on the running claim")
+            raise ParityError("ranks disagree on the running claim")
 
     def _calc_d(self, v):
         # calc_d of a new running claim (framework.rs:517-553): an input of the step circuit only, the
@@ -511,7 +515,7 @@ def run_reef(args):
             gp.verify_sharded()
             verified = ("sharded sum-check == un-sharded sum-check of the whole document on every rank (bit for bit, "
                         "untimed, before the timed legs)")
-        except RuntimeError:
+        except ParityError:
             raise                               # a parity failure must be loud
         except Exception as e:                  # infrastructure trouble of the check itself: say so, keep measuring
             verified = f"self-check could not run: {type(e).__name__}: {e}"

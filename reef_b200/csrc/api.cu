@@ -59,6 +59,31 @@ int ctx_stage(reef_ctx* c, size_t bytes, void** out) {
   *out = c->h_stage;
   return rc;
 }
+
+static void ctx_destroy(reef_ctx* c) {
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->scratch) cudaFree(c->scratch);
+  if (c->scratch2) cudaFree(c->scratch2);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->d_pos) cudaFree(c->d_pos);
+  for (auto& kv : c->table_cache) cudaFree(kv.second);
+  if (c->shard_cache) cudaFree(c->shard_cache);
+  for (void* p : c->mb_ipc_opened) cudaIpcCloseMemHandle(p);
+  if (c->mb_mine) cudaFree(c->mb_mine);
+  if (c->mb_peers_dev) cudaFree(c->mb_peers_dev);
+  if (c->mb_err_dev) cudaFree(c->mb_err_dev);
+  for (auto& r : c->prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+void ctx_retain(reef_ctx* c) { c->refs.fetch_add(1, std::memory_order_relaxed); }
+void ctx_release(reef_ctx* c) {
+  if (c->refs.fetch_sub(1, std::memory_order_acq_rel) == 1) ctx_destroy(c);
+}
 }  // namespace reef
 
 struct reef_table {
@@ -182,32 +207,33 @@ int reef_init(int device, reef_ctx** out) {
   reef_ctx* c = new reef_ctx;
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  REEF_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (se != cudaSuccess) {
+    c->stream = nullptr;
+    ctx_release(c);
+    return fail(REEF_ECUDA, std::string("reef_init: cudaStreamCreateWithFlags: ") + cudaGetErrorString(se));
+  }
   int rc = poseidon_upload_constants(c);
   if (rc) {
-    delete c;
+    ctx_release(c);
     return rc;
   }
   *out = c;
   return REEF_OK;
 }
 
+// Drops the caller's reference.  Child handles (tables, bases, sponges, sessions) created from this
+// context stay valid for their *_free call and keep the context's resources alive until the last
+// of them is freed: any destruction order is safe (e.g. Rust `Drop` order, Python finalisers).
 void reef_shutdown(reef_ctx* c) {
   if (!c) return;
-  cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
-  if (c->scratch) cudaFree(c->scratch);
-  if (c->scratch2) cudaFree(c->scratch2);
-  if (c->h_stage) cudaFreeHost(c->h_stage);
-  if (c->d_pos) cudaFree(c->d_pos);
-  for (auto& kv : c->table_cache) cudaFree(kv.second);
-  if (c->shard_cache) cudaFree(c->shard_cache);
-  for (void* p : c->mb_ipc_opened) cudaIpcCloseMemHandle(p);
-  if (c->mb_mine) cudaFree(c->mb_mine);
-  if (c->mb_peers_dev) cudaFree(c->mb_peers_dev);
-  if (c->mb_err_dev) cudaFree(c->mb_err_dev);
-  cudaStreamDestroy(c->stream);
-  delete c;
+  if (c->closed.exchange(true)) return;   // double shutdown while children keep it alive: ignore
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+  }
+  ctx_release(c);
 }
 
 int reef_sync(reef_ctx* c) {
@@ -432,6 +458,7 @@ int reef_sponge_start(reef_ctx* c, const uint32_t* ops, uint32_t n_ops, uint32_t
     delete sp;
     return rc;
   }
+  ctx_retain(c);
   *out = sp;
   return REEF_OK;
 }
@@ -455,6 +482,7 @@ int reef_sponge_absorb(reef_sponge* sp, const uint8_t* elems, uint32_t n) {
   int rc = check_canonical(elems, n, "reef_sponge_absorb");
   if (rc) return rc;
   reef_ctx* c = sp->ctx;
+  REEF_CTX_LIVE(c, "reef_sponge_absorb");
   std::lock_guard<std::mutex> lk(c->mu);
   REEF_CUDA(cudaSetDevice(c->device));
   rc = sponge_buf(sp, (size_t)n * 32);
@@ -472,6 +500,7 @@ int reef_sponge_squeeze(reef_sponge* sp, uint32_t n, uint8_t* out) {
   if (sp->io >= sp->ops.size() || sp->ops[sp->io] != n)
     return fail(REEF_EASSERT, "reef_sponge_squeeze: call does not match the declared IOPattern");
   reef_ctx* c = sp->ctx;
+  REEF_CTX_LIVE(c, "reef_sponge_squeeze");
   std::lock_guard<std::mutex> lk(c->mu);
   REEF_CUDA(cudaSetDevice(c->device));
   int rc = sponge_buf(sp, (size_t)n * 32);
@@ -496,6 +525,7 @@ int reef_sponge_finish(reef_sponge* sp) {
     if (sp->d_buf) cudaFree(sp->d_buf);
   }
   delete sp;
+  ctx_release(c);
   if (!ok) return fail(REEF_EASSERT, "reef_sponge_finish: ParameterUsageMismatch");
   return REEF_OK;
 }
@@ -653,6 +683,7 @@ static int table_new(reef_ctx* c, const void* host, uint64_t n, int is_u32, reef
   t->owns = 1;
   memset(t->first, 0, 32);
   memcpy(t->first, host, is_u32 ? 4 : 32);
+  ctx_retain(c);
   *out = t;
   return REEF_OK;
 }
@@ -677,6 +708,7 @@ int reef_table_wrap_dev(reef_ctx* c, void* dev_ptr, uint64_t n, int is_u32, reef
     delete t;
     return fail(REEF_ECUDA, std::string("reef_table_wrap_dev: ") + cudaGetErrorString(e));
   }
+  ctx_retain(c);
   *out = t;
   return REEF_OK;
 }
@@ -686,6 +718,7 @@ int reef_table_download(const reef_table* t, uint8_t* out, uint64_t n) {
   REEF_REQUIRE(!t->is_u32, REEF_EINVAL, "reef_table_download: u32 tables are not downloadable as field elements");
   REEF_REQUIRE(n <= t->n_pad, REEF_EINVAL, "reef_table_download: n exceeds the table length");
   reef_ctx* c = t->ctx;
+  REEF_CTX_LIVE(c, "reef_table_download");
   std::lock_guard<std::mutex> lk(c->mu);
   REEF_CUDA(cudaSetDevice(c->device));
   REEF_CUDA(cudaMemcpyAsync(out, t->d, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
@@ -697,14 +730,16 @@ uint64_t reef_table_len(const reef_table* t) { return t ? t->n_orig : 0; }
 
 void reef_table_free(reef_table* t) {
   if (!t) return;
+  reef_ctx* c = t->ctx;
   if (t->owns) {
-    std::lock_guard<std::mutex> lk(t->ctx->mu);
-    cudaSetDevice(t->ctx->device);
-    cudaStreamSynchronize(t->ctx->stream);
-    if (t->ctx->table_cache.size() < 4) t->ctx->table_cache.emplace_back((size_t)t->n_pad * (t->is_u32 ? 4 : 32), t->d);
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (!c->closed.load() && c->table_cache.size() < 4) c->table_cache.emplace_back((size_t)t->n_pad * (t->is_u32 ? 4 : 32), t->d);
     else cudaFree(t->d);
   }
   delete t;
+  ctx_release(c);
 }
 
 // Host half of wit_nlookup_gadget shared by the single-GPU and the sharded entry points:
@@ -854,18 +889,29 @@ int reef_nl_shard_begin(reef_ctx* c, int tag, const reef_table* local_table, uin
   return nl_shard_begin(c, a, rank, world, session);
 }
 
+// Every session call serialises on the session's context like the other entry points (the sharded
+// path mutates context state: mailbox sequence, staging buffers, profile records).
+#define REEF_SHARD_ENTER(s, what)                                 \
+  reef_ctx* c = nl_shard_ctx(s);                                  \
+  REEF_CTX_LIVE(c, what);                                         \
+  std::lock_guard<std::mutex> lk(c->mu);                          \
+  REEF_CUDA(cudaSetDevice(c->device))
+
 int reef_nl_shard_round_local(reef_nl_session* s, void* out_triple_dev) {
   REEF_REQUIRE(s && out_triple_dev, REEF_EINVAL, "reef_nl_shard_round_local: NULL argument");
+  REEF_SHARD_ENTER(s, "reef_nl_shard_round_local");
   return nl_shard_round_local(s, out_triple_dev);
 }
 
 int reef_nl_shard_round_finish(reef_nl_session* s, const void* all_triples_dev) {
   REEF_REQUIRE(s && all_triples_dev, REEF_EINVAL, "reef_nl_shard_round_finish: NULL argument");
+  REEF_SHARD_ENTER(s, "reef_nl_shard_round_finish");
   return nl_shard_round_finish(s, all_triples_dev);
 }
 
 int reef_nl_shard_export(reef_nl_session* s, void* out_pair_dev) {
   REEF_REQUIRE(s && out_pair_dev, REEF_EINVAL, "reef_nl_shard_export: NULL argument");
+  REEF_SHARD_ENTER(s, "reef_nl_shard_export");
   return nl_shard_export(s, out_pair_dev);
 }
 
@@ -873,11 +919,13 @@ int reef_nl_shard_finish(reef_nl_session* s, const void* all_pairs_dev, reef_nlo
   REEF_REQUIRE(s && all_pairs_dev && out, REEF_EINVAL, "reef_nl_shard_finish: NULL argument");
   REEF_REQUIRE(out->claim_r && out->rounds && out->sc_last_claim && out->next_running_claim, REEF_EINVAL,
                "reef_nl_shard_finish: NULL output buffer");
+  REEF_SHARD_ENTER(s, "reef_nl_shard_finish");
   return nl_shard_finish(s, all_pairs_dev, out->claim_r, out->rounds, out->sc_last_claim, out->next_running_claim);
 }
 
 int reef_nl_shard_round_p2p(reef_nl_session* s) {
   REEF_REQUIRE(s, REEF_EINVAL, "reef_nl_shard_round_p2p: NULL argument");
+  REEF_SHARD_ENTER(s, "reef_nl_shard_round_p2p");
   return nl_shard_round_p2p(s);
 }
 
@@ -885,10 +933,20 @@ int reef_nl_shard_finish_p2p(reef_nl_session* s, reef_nlookup_out* out) {
   REEF_REQUIRE(s && out, REEF_EINVAL, "reef_nl_shard_finish_p2p: NULL argument");
   REEF_REQUIRE(out->claim_r && out->rounds && out->sc_last_claim && out->next_running_claim, REEF_EINVAL,
                "reef_nl_shard_finish_p2p: NULL output buffer");
+  REEF_SHARD_ENTER(s, "reef_nl_shard_finish_p2p");
   return nl_shard_finish_p2p(s, out->claim_r, out->rounds, out->sc_last_claim, out->next_running_claim);
 }
 
-void reef_nl_shard_free(reef_nl_session* s) { nl_shard_free(s); }
+void reef_nl_shard_free(reef_nl_session* s) {
+  if (!s) return;
+  reef_ctx* c = nl_shard_ctx(s);
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    nl_shard_free(s);
+  }
+  ctx_release(c);
+}
 
 int reef_gen_eq_table(reef_ctx* c, const uint8_t* rs, const uint64_t* qs, uint32_t m, const uint8_t* last_q, uint32_t ell,
                       uint8_t* out) {
@@ -1141,19 +1199,22 @@ int reef_bases_register(reef_ctx* c, int curve, const uint8_t* bases, uint64_t n
   b->scalar_bits = scalar_bits;
   b->plan = pl;
   b->d_levels = d_levels;
+  ctx_retain(c);
   *out = b;
   return REEF_OK;
 }
 
 void reef_bases_free(reef_bases* b) {
   if (!b) return;
+  reef_ctx* c = b->ctx;
   {
-    std::lock_guard<std::mutex> lk(b->ctx->mu);
-    cudaSetDevice(b->ctx->device);
-    cudaStreamSynchronize(b->ctx->stream);
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
     cudaFree(b->d_levels);
   }
   delete b;
+  ctx_release(c);
 }
 
 uint32_t reef_bases_windows(const reef_bases* b) { return b ? b->plan.W : 0; }
@@ -1186,6 +1247,7 @@ static int msm_host_scalars(reef_ctx* c, const reef_bases* b, const void* scalar
     return REEF_OK;
   }
   if (is_u32) REEF_REQUIRE(b->scalar_bits >= 32, REEF_EINVAL, "reef_msm_u32: bases were registered for narrower scalars");
+  else REEF_REQUIRE(b->scalar_bits == 255, REEF_EINVAL, "reef_msm: full-width scalars need generators registered with scalar_bits = 255 (higher bits would be dropped)");
   std::lock_guard<std::mutex> lk(c->mu);
   REEF_CUDA(cudaSetDevice(c->device));
   const size_t bytes = (size_t)n * (is_u32 ? 4 : 32);
@@ -1208,6 +1270,7 @@ int reef_msm_dev(reef_ctx* c, const reef_bases* b, const void* scalars_dev, uint
   REEF_REQUIRE(c && b && out && scalars_dev, REEF_EINVAL, "reef_msm_dev: NULL argument");
   REEF_REQUIRE(b->ctx == c, REEF_EINVAL, "reef_msm_dev: bases belong to another context");
   REEF_REQUIRE(n >= 1 && n <= b->n, REEF_EASSERT, "reef_msm_dev: scalar count out of range");
+  REEF_REQUIRE(b->scalar_bits == 255, REEF_EINVAL, "reef_msm_dev: full-width scalars need generators registered with scalar_bits = 255");
   std::lock_guard<std::mutex> lk(c->mu);
   REEF_CUDA(cudaSetDevice(c->device));
   return msm_dispatch(c, b, scalars_dev, 0, n, 0, b->plan.W, out, nullptr);
@@ -1218,6 +1281,7 @@ int reef_msm_partial_dev(reef_ctx* c, const reef_bases* b, const void* scalars_d
   REEF_REQUIRE(c && b && out_xyzz && scalars_dev, REEF_EINVAL, "reef_msm_partial_dev: NULL argument");
   REEF_REQUIRE(b->ctx == c, REEF_EINVAL, "reef_msm_partial_dev: bases belong to another context");
   REEF_REQUIRE(n >= 1 && n <= b->n, REEF_EASSERT, "reef_msm_partial_dev: scalar count out of range");
+  REEF_REQUIRE(b->scalar_bits == 255, REEF_EINVAL, "reef_msm_partial_dev: full-width scalars need generators registered with scalar_bits = 255");
   REEF_REQUIRE(w_begin <= w_end && w_end <= b->plan.W, REEF_EINVAL, "reef_msm_partial_dev: window range out of bounds");
   if (w_begin == w_end) {
     memset(out_xyzz, 0, 128);

@@ -143,6 +143,12 @@ struct ProfRec {
 }  // namespace reef
 
 struct reef_ctx {
+  // Lifetime: one reference for the caller's handle (dropped by reef_shutdown) plus one per live
+  // child handle (table, bases, sponge, sum-check / sharded session).  The context is destroyed
+  // when the last reference goes, so ANY destruction order of handles is safe; after
+  // reef_shutdown the children can still be freed (and only freed).
+  std::atomic<int> refs{1};
+  std::atomic<bool> closed{false};
   int device = 0;
   cudaStream_t stream = nullptr;
   std::mutex mu;                         // one in-flight call per context
@@ -176,6 +182,12 @@ struct reef_ctx {
 };
 
 namespace reef {
+void ctx_retain(reef_ctx* c);
+void ctx_release(reef_ctx* c);   // never call with c->mu held
+#define REEF_CTX_LIVE(c, what)                                                                         \
+  do {                                                                                                 \
+    if ((c)->closed.load()) return ::reef::fail(REEF_EINVAL, what ": the context was shut down");      \
+  } while (0)
 int ctx_scratch(reef_ctx* c, size_t bytes, void** out);
 int ctx_scratch2(reef_ctx* c, size_t bytes, void** out);
 int ctx_stage(reef_ctx* c, size_t bytes, void** out);

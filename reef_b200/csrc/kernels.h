@@ -58,7 +58,8 @@ int nl_shard_round_finish(reef_nl_session* s, const void* d_triples);
 int nl_shard_export(reef_nl_session* s, void* d_out2);
 int nl_shard_finish(reef_nl_session* s, const void* d_pairs, uint8_t* out_claim_r, uint8_t* out_rounds, uint8_t* out_last_claim,
                     uint8_t* out_next_v);
-void nl_shard_free(reef_nl_session* s);
+void nl_shard_free(reef_nl_session* s);   // caller holds the context lock and drops the session's context reference
+reef_ctx* nl_shard_ctx(reef_nl_session* s);
 int nl_shard_preload();
 int nl_shard_round_p2p(reef_nl_session* s);
 int nl_shard_finish_p2p(reef_nl_session* s, uint8_t* out_claim_r, uint8_t* out_rounds, uint8_t* out_last_claim, uint8_t* out_next_v);

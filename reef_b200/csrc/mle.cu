@@ -1207,8 +1207,9 @@ struct reef_nl_session {
 namespace reef {
 
 int nl_shard_begin(reef_ctx* c, const NlookupArgs& a, uint32_t rank, uint32_t world, reef_nl_session** out) {
-  REEF_REQUIRE(world >= 1 && (world & (world - 1)) == 0 && world <= 64 && rank < world, REEF_EINVAL,
-               "nl_shard_begin: world must be a power of two <= 64");
+  static_assert(MB_MAX_WORLD <= 64, "k_shard_final keeps the gathered pairs in 64-entry shared arrays");
+  REEF_REQUIRE(world >= 1 && (world & (world - 1)) == 0 && world <= MB_MAX_WORLD && rank < world, REEF_EINVAL,
+               "nl_shard_begin: world must be a power of two <= 32");
   uint32_t gamma = 0;
   while ((1u << gamma) < world) gamma++;
   REEF_REQUIRE(a.ell > gamma && a.ell <= (uint32_t)MAX_ELL, REEF_EINVAL, "nl_shard_begin: table too small for this world size");
@@ -1294,6 +1295,7 @@ int nl_shard_begin(reef_ctx* c, const NlookupArgs& a, uint32_t rank, uint32_t wo
   }
   if (cudaGetLastError() != cudaSuccess) return bail(fail(REEF_ECUDA, "nl_shard_begin: launch failed"));
   cudaStreamSynchronize(st);   // the host staging vectors of the caller may go away
+  ctx_retain(c);
   *out = s;
   return REEF_OK;
 }
@@ -1400,9 +1402,13 @@ int nl_shard_round_p2p(reef_nl_session* s) {
   reef_ctx* c = s->ctx;
   REEF_REQUIRE(c->mb_world == s->world && c->mb_rank == s->rank && s->world <= MB_MAX_WORLD, REEF_EINVAL,
                "nl_shard_round_p2p: the context's mailbox is not connected for this rank / world");
-  s->mb = MbRef{c->mb_peers_dev, (const unsigned char*)c->mb_mine, c->mb_err_dev, c->mb_world, c->mb_rank, ++c->mb_seq};
+  REEF_REQUIRE(s->round < s->ell_loc, REEF_EASSERT, "nl_shard_round_p2p: all local rounds are done");
+  s->mb = MbRef{c->mb_peers_dev, (const unsigned char*)c->mb_mine, c->mb_err_dev, c->mb_world, c->mb_rank, c->mb_seq + 1};
   int rc = nl_shard_round_local(s, nullptr);
-  if (!rc) rc = nl_shard_round_finish(s, nullptr);
+  if (!rc) {
+    c->mb_seq++;            // the post of this exchange is in flight: the receive must follow
+    rc = nl_shard_round_finish(s, nullptr);
+  }
   s->mb.peers = nullptr;
   return rc;
 }
@@ -1411,14 +1417,21 @@ int nl_shard_finish_p2p(reef_nl_session* s, uint8_t* out_claim_r, uint8_t* out_r
   reef_ctx* c = s->ctx;
   REEF_REQUIRE(c->mb_world == s->world && c->mb_rank == s->rank && s->world <= MB_MAX_WORLD, REEF_EINVAL,
                "nl_shard_finish_p2p: the context's mailbox is not connected for this rank / world");
-  s->mb = MbRef{c->mb_peers_dev, (const unsigned char*)c->mb_mine, c->mb_err_dev, c->mb_world, c->mb_rank, ++c->mb_seq};
+  REEF_REQUIRE(s->round == s->ell_loc && s->small, REEF_EASSERT, "nl_shard_finish_p2p: local rounds not finished");
+  s->mb = MbRef{c->mb_peers_dev, (const unsigned char*)c->mb_mine, c->mb_err_dev, c->mb_world, c->mb_rank, c->mb_seq + 1};
   int rc = nl_shard_export(s, nullptr);
-  if (!rc) rc = nl_shard_finish(s, nullptr, out_claim_r, out_rounds, out_last_claim, out_next_v);
+  if (!rc) {
+    c->mb_seq++;
+    rc = nl_shard_finish(s, nullptr, out_claim_r, out_rounds, out_last_claim, out_next_v);
+  }
   s->mb.peers = nullptr;
   if (rc) return rc;
   uint32_t e = 0;
   REEF_CUDA(cudaMemcpy(&e, c->mb_err_dev, 4, cudaMemcpyDeviceToHost));   // nl_shard_finish has synchronised the stream
-  if (e) return fail(REEF_ECUDA, "nl_shard_finish_p2p: a peer never posted exchange " + std::to_string(e & 0x7fffffffu) + " (timed out)");
+  if (e) {
+    cudaMemset(c->mb_err_dev, 0, 4);
+    return fail(REEF_ECUDA, "nl_shard_finish_p2p: exchange " + std::to_string(e & 0x7fffffffu) + " failed (a peer never posted, or a peer reported a timeout)");
+  }
   return REEF_OK;
 }
 
@@ -1436,11 +1449,15 @@ int nl_shard_preload() {
   return REEF_OK;
 }
 
+reef_ctx* nl_shard_ctx(reef_nl_session* s) { return s->ctx; }
+
 void nl_shard_free(reef_nl_session* s) {
   if (!s) return;
   reef_ctx* c = s->ctx;
   cudaStreamSynchronize(c->stream);
-  if (!c->shard_cache) {
+  if (c->closed.load()) {
+    cudaFree(s->d_buf);
+  } else if (!c->shard_cache) {
     c->shard_cache = s->d_buf;
     c->shard_cache_bytes = s->buf_bytes;
   } else if (c->shard_cache_bytes < s->buf_bytes) {

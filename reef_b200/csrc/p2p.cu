@@ -54,9 +54,11 @@ static int mailbox_set_peers(reef_ctx* c, uint32_t rank, uint32_t world, void* c
   REEF_CUDA(cudaFuncGetAttributes(&fa, (const void*)k_p2p_allgather));   // load it now, see nl_shard_preload
   int rc = nl_shard_preload();
   if (rc) return rc;
+  REEF_CUDA(cudaMemset(c->mb_err_dev, 0, 256));   // a fresh connection starts without a recorded failure
   c->mb_world = world;
   c->mb_rank = rank;
-  c->mb_seq = 0;
+  // mb_seq stays monotonic over the life of the context: the mailbox still holds the sequence
+  // numbers of earlier exchanges, and a peer may already be posting into it
   return REEF_OK;
 }
 
@@ -132,7 +134,10 @@ int reef_p2p_status(reef_ctx* c) {
   uint32_t e = 0;
   REEF_CUDA(cudaMemcpyAsync(&e, c->mb_err_dev, 4, cudaMemcpyDeviceToHost, c->stream));
   REEF_CUDA(cudaStreamSynchronize(c->stream));
-  if (e) return fail(REEF_ECUDA, "reef_p2p_allgather: a peer never posted exchange " + std::to_string(e & 0x7fffffffu) + " (timed out)");
+  if (e) {
+    cudaMemset(c->mb_err_dev, 0, 4);
+    return fail(REEF_ECUDA, "reef_p2p_allgather: exchange " + std::to_string(e & 0x7fffffffu) + " failed (a peer never posted, or a peer reported a timeout)");
+  }
   return REEF_OK;
 }
 

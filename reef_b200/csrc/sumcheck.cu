@@ -440,6 +440,7 @@ int reef_sumcheck_begin(reef_ctx* c, int field, int kind, const uint8_t* const* 
     delete s;
     return rc;
   }
+  ctx_retain(c);
   *out = s;
   return REEF_OK;
 }
@@ -454,6 +455,7 @@ int reef_sumcheck_round(reef_sumcheck* s, const uint8_t* r_prev, uint8_t* out_ev
     if (rc) return rc;
   }
   reef_ctx* c = s->ctx;
+  REEF_CTX_LIVE(c, "reef_sumcheck_round");
   std::lock_guard<std::mutex> lk(c->mu);
   REEF_CUDA(cudaSetDevice(c->device));
   return s->field == 0 ? sc_round_t<FqCfg>(s, r_prev, out_evals) : sc_round_t<FpCfg>(s, r_prev, out_evals);
@@ -465,6 +467,7 @@ int reef_sumcheck_final(reef_sumcheck* s, const uint8_t* r_last, uint8_t* out_cl
   int rc = check_canon_field(r_last, 1, s->field, "reef_sumcheck_final: challenge");
   if (rc) return rc;
   reef_ctx* c = s->ctx;
+  REEF_CTX_LIVE(c, "reef_sumcheck_final");
   std::lock_guard<std::mutex> lk(c->mu);
   REEF_CUDA(cudaSetDevice(c->device));
   return s->field == 0 ? sc_final_t<FqCfg>(s, r_last, out_claims) : sc_final_t<FpCfg>(s, r_last, out_claims);
@@ -472,13 +475,15 @@ int reef_sumcheck_final(reef_sumcheck* s, const uint8_t* r_last, uint8_t* out_cl
 
 void reef_sumcheck_free(reef_sumcheck* s) {
   if (!s) return;
+  reef_ctx* c = s->ctx;
   {
-    std::lock_guard<std::mutex> lk(s->ctx->mu);
-    cudaSetDevice(s->ctx->device);
-    cudaStreamSynchronize(s->ctx->stream);
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
     cudaFree(s->d_buf);
   }
   delete s;
+  ctx_release(c);
 }
 
 int reef_r1cs_spmv(reef_ctx* c, int field, const uint64_t* row_ptr, const uint32_t* col_idx, const uint8_t* vals,

@@ -326,7 +326,10 @@ class Table:
     def __init__(self, ctx: Context, values=None, codes=None, dev_ptr=None, n=None, is_u32=False):
         self.ctx = ctx
         h = C.c_void_p()
-        if values is not None:
+        if values is not None and isinstance(values, np.ndarray):
+            a = np.ascontiguousarray(values.view(np.uint8).reshape(-1))       # n x 32 bytes, LE canonical
+            check(lib.reef_table_upload(ctx._h, a.ctypes.data, a.size // 32, C.byref(h)))
+        elif values is not None:
             b = _pack(values)
             check(lib.reef_table_upload(ctx._h, _buf(b), len(values), C.byref(h)))
         elif codes is not None:

@@ -26,6 +26,12 @@ int reef_hosttest_poseidon_permute(const uint8_t in[160], uint8_t out[160]);
  * op: 0 P+Q via XYZZ full add, 1 P+Q via mixed add, 2 2P, 3 P-Q via mixed add (neg), 4 k*P (k = first 8 bytes of q) */
 int reef_hosttest_ec_op(int curve, int op, const uint8_t p[64], const uint8_t q[64], uint8_t out[64]);
 
+/* GPU test hook for the lane-parallel transcript permutation (poseidon_lp.cuh): `n_perms` successive
+ * permutations of one width-5 state (canonical in / out) by one 256-thread CTA; cycles_per_perm
+ * (may be NULL, else 7 entries) receives the SM cycles per permutation and, for the last one, the
+ * cycles of its four phases and of the two waits inside the chain.  ctx: a reef_ctx*. */
+int reef_gputest_poseidon_permute_lp(void* ctx, const uint8_t in[160], uint32_t n_perms, uint8_t out[160], uint64_t* cycles_per_perm);
+
 #ifdef __cplusplus
 }
 #endif

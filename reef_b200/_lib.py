@@ -114,6 +114,7 @@ _sig = {
     "reef_hosttest_field_op": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp]),
     "reef_hosttest_mul_wide": (C.c_int, [_vp, _vp, _vp]),
     "reef_hosttest_poseidon_permute": (C.c_int, [_vp, _vp]),
+    "reef_gputest_poseidon_permute_lp": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp]),
 }
 _missing = []
 for _name, (_res, _args) in _sig.items():

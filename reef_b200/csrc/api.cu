@@ -67,6 +67,7 @@ static void ctx_destroy(reef_ctx* c) {
   if (c->scratch2) cudaFree(c->scratch2);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->d_pos) cudaFree(c->d_pos);
+  if (c->d_lp) cudaFree(c->d_lp);
   for (auto& kv : c->table_cache) cudaFree(kv.second);
   if (c->shard_cache) cudaFree(c->shard_cache);
   for (void* p : c->mb_ipc_opened) cudaIpcCloseMemHandle(p);

@@ -13,6 +13,7 @@
 #include "fp.cuh"
 #include "fp29.cuh"
 #include "poseidon.cuh"
+#include "poseidon_lp.cuh"
 
 namespace reef {
 
@@ -153,6 +154,7 @@ struct reef_ctx {
   cudaStream_t stream = nullptr;
   std::mutex mu;                         // one in-flight call per context
   reef::PoseidonTables* d_pos = nullptr; // Montgomery-form tables in global memory
+  reef::PoseidonLpTables* d_lp = nullptr; // tables of the lane-parallel transcript permutation
   reef::SpongeTags tags;
   // reusable device scratch (grown on demand)
   void* scratch = nullptr;

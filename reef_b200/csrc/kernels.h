@@ -9,6 +9,7 @@ namespace reef {
 // ---- poseidon.cu
 void io_pattern_tag_le32(const uint32_t* ops, uint32_t n_ops, uint32_t domain_separator, uint8_t out[32]);
 Fq fq_mont_from_le32(const uint8_t* b);
+Fq fq_canon_from_le32(const uint8_t* b);
 void poseidon_tables_host(PoseidonTables* t);
 void poseidon_permute_host(Fq* s);
 int poseidon_upload_constants(reef_ctx* c);

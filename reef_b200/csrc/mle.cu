@@ -40,7 +40,7 @@ static constexpr int MAX_ELL = 48;
 
 // Device-resident state of one nlookup session.
 struct NlState {
-  Fq sponge[5];          // Montgomery form
+  u32 sponge[5][12];     // SAFE sponge state between kernels: 5 x 10 lazy 29-bit limbs, plain residues (poseidon_lp.cuh)
   Fq r_mont;             // challenge of the last finished round (Montgomery form)
   Fq rm_mont;            // rs[m] = claim_r^(m+1)
   Fq lq_mont[MAX_ELL];   // last_q[j]  (bit j of the table index), Montgomery form
@@ -93,41 +93,80 @@ __device__ __forceinline__ void block_sum(Fq* vals, Fq* smem /* NV * NTHREADS/32
 }
 
 // ---------------------------------------------------------------------------------------
+// transcript plumbing shared by the single-CTA kernels (all of them run LP_PERM_THREADS threads):
+// the sponge state lives in shared memory (LpPermShared::S) while a kernel runs and in
+// NlState::sponge between kernels.
+// ---------------------------------------------------------------------------------------
+static constexpr int TR_THREADS = LP_PERM_THREADS;
+
+__device__ __forceinline__ void tr_load_state(LpPermShared* sh, const NlState* st) {
+  if (threadIdx.x < 60) sh->S[threadIdx.x / 12][threadIdx.x % 12] = st->sponge[threadIdx.x / 12][threadIdx.x % 12];
+}
+__device__ __forceinline__ void tr_store_state(const LpPermShared* sh, NlState* st) {
+  if (threadIdx.x < 60) st->sponge[threadIdx.x / 12][threadIdx.x % 12] = sh->S[threadIdx.x / 12][threadIdx.x % 12];
+}
+
+// One sum-check round of the transcript: absorb [const, x, xsq] at rate positions 0..2, permute,
+// squeeze r (r1cs_helper.rs:479-488).  On entry THREAD 0 holds con, g1 = g(1), xsq (canonical);
+// every thread gets r in Montgomery form; thread 0 records the round in st->out_rounds[ri].
+struct TrScratch {
+  Fq e[3];
+  Fq r_mont;
+};
+__device__ __forceinline__ Fq tr_round(LpPermShared* sh, TrScratch* ts, const PoseidonLpTables* T, u32& seq, NlState* st,
+                                       uint32_t ri, const Fq& con, const Fq& g1, const Fq& xsq) {
+  if (threadIdx.x == 0) {
+    ts->e[0] = con;
+    ts->e[1] = fe_sub<FqCfg>(fe_sub<FqCfg>(g1, con), xsq);
+    ts->e[2] = xsq;
+  }
+  __syncthreads();
+  if (threadIdx.x < 27) sh->S[1 + threadIdx.x / 9][threadIdx.x % 9] += lp_limb_of(ts->e[threadIdx.x / 9].v, threadIdx.x % 9);
+  __syncthreads();
+  poseidon_permute_lp(sh, T, ++seq);
+  if (threadIdx.x == 0) {
+    const Fq r = lp_squeeze(sh, 1);
+    const Fq rm = to_mont<FqCfg>(r);
+    ts->r_mont = rm;
+    st->r_mont = rm;
+    st->out_rounds[ri][0] = r;
+    st->out_rounds[ri][1] = ts->e[2];
+    st->out_rounds[ri][2] = ts->e[1];
+    st->out_rounds[ri][3] = ts->e[0];
+  }
+  __syncthreads();
+  return ts->r_mont;
+}
+
+// ---------------------------------------------------------------------------------------
 // k_nl_begin: first absorb + claim_r, powers of claim_r, sparse list, selector table
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_nl_begin(NlState* st, const Fq* __restrict__ query, uint32_t n_query, Fq tag,
-                                                 const Fq* __restrict__ prev_q, uint32_t ell, const uint64_t* __restrict__ q,
-                                                 uint32_t m, uint64_t* __restrict__ sp_pos, Fq* __restrict__ sp_w,
-                                                 const PoseidonTables* __restrict__ K, uint32_t rank, uint32_t world) {
-  // 64 threads: warp 0 owns the sponge state, warp 1 is its partner inside poseidon_permute_pair
-  // (both warps follow the same control flow; only warp 0 touches the data).
-  const int lane = threadIdx.x & 31;
-  const bool A = threadIdx.x < 32;
-  Fq s = fe_zero<FqCfg>();
-  if (A && lane == 0) s = tag;
-  uint32_t apos = 0;
-  for (uint32_t e = 0; e < n_query; e++) {
-    if (apos == 4) {
-      poseidon_permute_pair(s, K);
-      apos = 0;
+__global__ void __launch_bounds__(TR_THREADS) k_nl_begin(NlState* st, const Fq* __restrict__ query, uint32_t n_query, Fq tag_canon,
+                                                         const Fq* __restrict__ prev_q, uint32_t ell, const uint64_t* __restrict__ q,
+                                                         uint32_t m, uint64_t* __restrict__ sp_pos, Fq* __restrict__ sp_w,
+                                                         const PoseidonLpTables* __restrict__ T, uint32_t rank, uint32_t world) {
+  __shared__ LpPermShared sh;
+  lp_perm_init(&sh);
+  u32 seq = 0;
+  if (threadIdx.x < 9) sh.S[0][threadIdx.x] = lp_limb_of(tag_canon.v, threadIdx.x);
+  // last_q[j] = prev_running_q[ell-1-j]   (r1cs.rs:2318-2319 passes the reversed vector); off the transcript's path
+  for (uint32_t j = threadIdx.x; j < ell; j += TR_THREADS) st->lq_mont[j] = to_mont<FqCfg>(ld256(prev_q + (ell - 1 - j)));
+  for (uint32_t e0 = 0; e0 < n_query; e0 += 4) {
+    const uint32_t cnt = n_query - e0 < 4 ? n_query - e0 : 4;
+    __syncthreads();
+    if (e0) poseidon_permute_lp(&sh, T, ++seq);      // absorb position wrapped: permute before the next four
+    if (threadIdx.x < 9 * cnt) {
+      const Fq x = ld256(query + e0 + threadIdx.x / 9);
+      sh.S[1 + threadIdx.x / 9][threadIdx.x % 9] += lp_limb_of(x.v, threadIdx.x % 9);
     }
-    if (A) {
-      Fq x = to_mont<FqCfg>(ld256(query + e));
-      Fq sum = fe_add<FqCfg>(s, x);
-      if (lane == (int)(1 + apos)) s = sum;
-    }
-    apos++;
   }
-  poseidon_permute_pair(s, K);    // squeeze(1): always permutes after an absorb
-  if (!A) {
-    // last_q[j] = prev_running_q[ell-1-j]   (r1cs.rs:2318-2319 passes the reversed vector)
-    for (uint32_t j = lane; j < ell; j += 32) st->lq_mont[j] = to_mont<FqCfg>(ld256(prev_q + (ell - 1 - j)));
-    return;
-  }
-  if (lane < 5) st->sponge[lane] = s;
-  Fq claim = shfl_fq(s, 1);       // Montgomery form
-  if (lane == 0) {
-    st->out_claim_r = from_mont<FqCfg>(claim);
+  __syncthreads();
+  poseidon_permute_lp(&sh, T, ++seq);                // squeeze(1): always permutes after an absorb
+  tr_store_state(&sh, st);
+  if (threadIdx.x == 0) {
+    const Fq claim_c = lp_squeeze(&sh, 1);
+    st->out_claim_r = claim_c;
+    const Fq claim = to_mont<FqCfg>(claim_c);
     Fq pw = claim;                // rs[0] = claim_r
     for (uint32_t k = 0; k < m; k++) {
       // sharded: rank g owns the indices with (q mod world) == g, at local position q / world
@@ -354,15 +393,18 @@ static int launch_sweep(reef_ctx* c, const void* Tin, uint64_t L_in, Fq* Tout, c
 // k_round: finish round `ri` (0-based): sum CTA partials, add the sparse-point terms, run the
 // transcript (absorb [const, x, xsq], squeeze r), fold A, advance the sparse list.
 // ---------------------------------------------------------------------------------------
-static constexpr int ROUND_THREADS = 128;
+static constexpr int ROUND_THREADS = TR_THREADS;
 
 template <bool U32IN>
 __global__ void __launch_bounds__(ROUND_THREADS)
 k_round(NlState* st, const Fq* __restrict__ partials, uint32_t nblk, const void* __restrict__ Tcur, uint64_t L,
         Fq* A, uint64_t a_len, uint64_t* sp_pos, Fq* sp_w, uint32_t m, uint32_t ri,
-        const PoseidonTables* __restrict__ K) {
+        const PoseidonLpTables* __restrict__ K) {
+  __shared__ LpPermShared sh;
+  __shared__ TrScratch ts;
   __shared__ Fq red[3 * ROUND_THREADS / 32];
-  __shared__ Fq r_sh;
+  lp_perm_init(&sh);
+  tr_load_state(&sh, st);
   const uint64_t half = L >> 1;
   Fq acc[3];
   acc[0] = acc[1] = acc[2] = fe_zero<FqCfg>();
@@ -388,37 +430,9 @@ k_round(NlState* st, const Fq* __restrict__ partials, uint32_t nblk, const void*
     }
   }
   block_sum<3, ROUND_THREADS>(acc, red);
-  if (threadIdx.x < 64) {       // warp 0: transcript; warp 1: its partner inside the permutation
-    const int lane = threadIdx.x & 31;
-    const bool A = threadIdx.x < 32;
-    Fq s = fe_zero<FqCfg>(), con = s, x = s, xsq = s;
-    if (A) {
-      con = shfl_fq(acc[0], 0);
-      const Fq g1 = shfl_fq(acc[1], 0);
-      xsq = shfl_fq(acc[2], 0);
-      x = fe_sub<FqCfg>(fe_sub<FqCfg>(g1, con), xsq);
-      // absorb [const, x, xsq] at rate positions 0,1,2 (absorb_pos is 0 after the previous squeeze)
-      s = lane < 5 ? st->sponge[lane] : fe_zero<FqCfg>();
-      const Fq e = lane == 1 ? con : (lane == 2 ? x : xsq);
-      const Fq sum = fe_add<FqCfg>(s, to_mont<FqCfg>(e));
-      if (lane >= 1 && lane <= 3) s = sum;
-    }
-    poseidon_permute_pair(s, K);
-    if (A) {
-      if (lane < 5) st->sponge[lane] = s;
-      const Fq r = shfl_fq(s, 1);
-      if (lane == 0) {
-        st->r_mont = r;
-        r_sh = r;
-        st->out_rounds[ri][0] = from_mont<FqCfg>(r);
-        st->out_rounds[ri][1] = xsq;
-        st->out_rounds[ri][2] = x;
-        st->out_rounds[ri][3] = con;
-      }
-    }
-  }
-  __syncthreads();
-  const Fq r = r_sh;
+  u32 seq = 0;
+  const Fq r = tr_round(&sh, &ts, K, seq, st, ri, acc[0], acc[1], acc[2]);
+  tr_store_state(&sh, st);
   // fold the A table over its top bit (in place: entry x only depends on x and x + a_len/2)
   if (a_len > 1) {
     const uint64_t ah = a_len >> 1;
@@ -439,18 +453,21 @@ k_round(NlState* st, const Fq* __restrict__ partials, uint32_t nblk, const void*
 // ---------------------------------------------------------------------------------------
 // k_tail: one CTA finishes the sum-check out of shared memory (live length <= 2^h).
 // ---------------------------------------------------------------------------------------
-static constexpr int TAIL_THREADS = 256;
+static constexpr int TAIL_THREADS = TR_THREADS;
 
 template <bool U32IN>
 __global__ void __launch_bounds__(TAIL_THREADS)
 k_tail(NlState* st, const void* __restrict__ Tin, uint64_t L_in, int do_fold, const Fq* __restrict__ A,
        const Fq* __restrict__ B, const uint64_t* __restrict__ sp_pos, const Fq* __restrict__ sp_w, uint32_t m,
-       uint32_t ri0, const PoseidonTables* __restrict__ K) {
+       uint32_t ri0, const PoseidonLpTables* __restrict__ K) {
   extern __shared__ __align__(32) unsigned char tail_smem[];
   Fq* Ts = reinterpret_cast<Fq*>(tail_smem);   // canonical
   Fq* Es = Ts + CHUNK;                         // Montgomery form
   Fq* red = Es + CHUNK;                        // 3 * TAIL_THREADS/32
-  __shared__ Fq r_sh;
+  __shared__ LpPermShared sh;
+  __shared__ TrScratch ts;
+  lp_perm_init(&sh);
+  tr_load_state(&sh, st);
   uint64_t L = do_fold ? (L_in >> 1) : L_in;   // <= CHUNK
   const Fq a0 = A[0];
   const Fq rf = st->r_mont;
@@ -465,7 +482,8 @@ k_tail(NlState* st, const void* __restrict__ Tin, uint64_t L_in, int do_fold, co
   }
   __syncthreads();
   uint32_t ri = ri0;
-  Fq last_xsq = fe_zero<FqCfg>(), last_x = last_xsq, last_con = last_xsq;
+  u32 seq = 0;
+  Fq r = fe_zero<FqCfg>();
   while (L > 1) {
     const uint64_t half = L >> 1;
     Fq acc[3];
@@ -477,39 +495,7 @@ k_tail(NlState* st, const void* __restrict__ Tin, uint64_t L_in, int do_fold, co
       acc[2] = fe_add<FqCfg>(acc[2], mont_mul<FqCfg>(fe_sub<FqCfg>(e1, e0), fe_sub<FqCfg>(t1, t0)));
     }
     block_sum<3, TAIL_THREADS>(acc, red);
-    if (threadIdx.x < 64) {     // warp 0: transcript; warp 1: its partner inside the permutation
-      const int lane = threadIdx.x & 31;
-      const bool A = threadIdx.x < 32;
-      Fq s = fe_zero<FqCfg>(), con = s, x = s, xsq = s;
-      if (A) {
-        con = shfl_fq(acc[0], 0);
-        const Fq g1 = shfl_fq(acc[1], 0);
-        xsq = shfl_fq(acc[2], 0);
-        x = fe_sub<FqCfg>(fe_sub<FqCfg>(g1, con), xsq);
-        s = lane < 5 ? st->sponge[lane] : fe_zero<FqCfg>();
-        const Fq e = lane == 1 ? con : (lane == 2 ? x : xsq);
-        const Fq sum = fe_add<FqCfg>(s, to_mont<FqCfg>(e));
-        if (lane >= 1 && lane <= 3) s = sum;
-      }
-      poseidon_permute_pair(s, K);
-      if (A) {
-        if (lane < 5) st->sponge[lane] = s;
-        const Fq r = shfl_fq(s, 1);
-        if (lane == 0) {
-          r_sh = r;
-          st->r_mont = r;
-          st->out_rounds[ri][0] = from_mont<FqCfg>(r);
-          st->out_rounds[ri][1] = xsq;
-          st->out_rounds[ri][2] = x;
-          st->out_rounds[ri][3] = con;
-          last_xsq = xsq;
-          last_x = x;
-          last_con = con;
-        }
-      }
-    }
-    __syncthreads();
-    const Fq r = r_sh;
+    r = tr_round(&sh, &ts, K, seq, st, ri, acc[0], acc[1], acc[2]);
     for (uint64_t b = threadIdx.x; b < half; b += TAIL_THREADS) {
       Fq t0 = Ts[b], t1 = Ts[b + half], e0 = Es[b], e1 = Es[b + half];
       Fq tn = fold_one(t0, t1, r);
@@ -521,11 +507,12 @@ k_tail(NlState* st, const void* __restrict__ Tin, uint64_t L_in, int do_fold, co
     L = half;
     ri++;
   }
+  tr_store_state(&sh, st);
   if (threadIdx.x == 0) {
     // last_claim = g(r) = xsq r^2 + x r + const      (r1cs.rs:2373-2376)
-    const Fq r = r_sh;
-    Fq t = fe_add<FqCfg>(mont_mul<FqCfg>(r, last_xsq), last_x);   // xsq*r + x   (canonical)
-    Fq lc = fe_add<FqCfg>(mont_mul<FqCfg>(r, t), last_con);
+    const uint32_t last = ri - 1;
+    Fq t = fe_add<FqCfg>(mont_mul<FqCfg>(r, st->out_rounds[last][1]), st->out_rounds[last][2]);   // xsq*r + x   (canonical)
+    Fq lc = fe_add<FqCfg>(mont_mul<FqCfg>(r, t), st->out_rounds[last][3]);
     st->out_last_claim = lc;
     st->out_next_v = Ts[0];                                       // = T~(sc_rs)  (r1cs.rs:2379-2385)
   }
@@ -616,10 +603,10 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
   REEF_CUDA(cudaMemcpyAsync(d_prevq, a.h_prev_q, (size_t)ell * 32, cudaMemcpyHostToDevice, s));
   if (m) REEF_CUDA(cudaMemcpyAsync(d_q, a.h_q, (size_t)m * 8, cudaMemcpyHostToDevice, s));
 
-  Fq tag = fq_mont_from_le32(a.tag_le);
+  Fq tag = fq_canon_from_le32(a.tag_le);   // canonical: the LP sponge absorbs plain residues
   {
     ProfScope ps(c, PROF_NL_SETUP, N);
-    k_nl_begin<<<1, 64, exclusive_smem(c, (const void*)k_nl_begin, 0), s>>>(st, d_query, a.n_query, tag, d_prevq, ell, d_q, m, d_pos, d_w, c->d_pos, 0, 1);
+    k_nl_begin<<<1, TR_THREADS, exclusive_smem(c, (const void*)k_nl_begin, 0), s>>>(st, d_query, a.n_query, tag, d_prevq, ell, d_q, m, d_pos, d_w, c->d_lp, 0, 1);
     REEF_LAUNCHED();
     k_eq_tables<<<ceil_div_u(a_len + b_len, 128), 128, 0, s>>>(st, ell, hb, d_A, a_len, d_B, b_len, 0, 0);
     REEF_LAUNCHED();
@@ -638,7 +625,7 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
         if (rc) return rc;
       }
       ProfScope ps(c, PROF_ROUND, L);
-      k_round<U32IN><<<1, ROUND_THREADS, exclusive_smem(c, (const void*)k_round<U32IN>, 0), s>>>(st, d_part, nblk, a.d_table, L, d_A, a_cur, d_pos, d_w, m, i, c->d_pos);
+      k_round<U32IN><<<1, ROUND_THREADS, exclusive_smem(c, (const void*)k_round<U32IN>, 0), s>>>(st, d_part, nblk, a.d_table, L, d_A, a_cur, d_pos, d_w, m, i, c->d_lp);
       REEF_LAUNCHED();
     } else {
       {
@@ -648,7 +635,7 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
         if (rc) return rc;
       }
       ProfScope ps(c, PROF_ROUND, L);
-      k_round<false><<<1, ROUND_THREADS, exclusive_smem(c, (const void*)k_round<false>, 0), s>>>(st, d_part, nblk, d_fold, L, d_A, a_cur, d_pos, d_w, m, i, c->d_pos);
+      k_round<false><<<1, ROUND_THREADS, exclusive_smem(c, (const void*)k_round<false>, 0), s>>>(st, d_part, nblk, d_fold, L, d_A, a_cur, d_pos, d_w, m, i, c->d_lp);
       REEF_LAUNCHED();
       t_cur = d_fold;
     }
@@ -659,12 +646,12 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
   const size_t tail_smem = (size_t)(2 * CHUNK + 3 * TAIL_THREADS / 32) * sizeof(Fq);
   std::unique_ptr<ProfScope> tail_scope(new ProfScope(c, PROF_TAIL, L));
   if (n_sweeps == 0) {
-    k_tail<U32IN><<<1, TAIL_THREADS, exclusive_smem(c, (const void*)k_tail<U32IN>, tail_smem), s>>>(st, a.d_table, N, 0, d_A, d_B, d_pos, d_w, m, 0, c->d_pos);
+    k_tail<U32IN><<<1, TAIL_THREADS, exclusive_smem(c, (const void*)k_tail<U32IN>, tail_smem), s>>>(st, a.d_table, N, 0, d_A, d_B, d_pos, d_w, m, 0, c->d_lp);
   } else if (n_sweeps == 1) {
     // L is now 2^h: the table to fold is still the caller's (length 2L)
-    k_tail<U32IN><<<1, TAIL_THREADS, exclusive_smem(c, (const void*)k_tail<U32IN>, tail_smem), s>>>(st, a.d_table, 2 * L, 1, d_A, d_B, d_pos, d_w, m, n_sweeps, c->d_pos);
+    k_tail<U32IN><<<1, TAIL_THREADS, exclusive_smem(c, (const void*)k_tail<U32IN>, tail_smem), s>>>(st, a.d_table, 2 * L, 1, d_A, d_B, d_pos, d_w, m, n_sweeps, c->d_lp);
   } else {
-    k_tail<false><<<1, TAIL_THREADS, exclusive_smem(c, (const void*)k_tail<false>, tail_smem), s>>>(st, t_cur, 2 * L, 1, d_A, d_B, d_pos, d_w, m, n_sweeps, c->d_pos);
+    k_tail<false><<<1, TAIL_THREADS, exclusive_smem(c, (const void*)k_tail<false>, tail_smem), s>>>(st, t_cur, 2 * L, 1, d_A, d_B, d_pos, d_w, m, n_sweeps, c->d_lp);
   }
   tail_scope.reset();
   REEF_LAUNCHED();
@@ -961,62 +948,39 @@ k_shard_local(const Fq* __restrict__ partials, uint32_t nblk, const void* __rest
   }
 }
 
-// warps 0 and 1 together (threadIdx.x < 64): warp 0 sums the G gathered triples, absorbs
-// [const, x, xsq], squeezes r and records the round; warp 1 is its partner inside the permutation.
-// The return value is meaningful on warp 0.
-__device__ __forceinline__ Fq shard_transcript(NlState* st, const Fq* __restrict__ triples, uint32_t G, uint32_t ri,
-                                               const PoseidonTables* __restrict__ K) {
-  const int lane = threadIdx.x & 31;
-  const bool A = threadIdx.x < 32;
-  Fq s = fe_zero<FqCfg>(), con = s, x = s, xsq = s;
-  if (A) {
-    Fq g1 = fe_zero<FqCfg>();
+// Thread 0 sums the G gathered triples (rank-major (const, g(1), xsq)); then one transcript round by the
+// whole CTA.  `triples` may live in global (gathered) or shared memory.
+__device__ __forceinline__ Fq shard_transcript(LpPermShared* sh, TrScratch* ts, u32& seq, NlState* st, const Fq* triples, uint32_t G,
+                                               uint32_t ri, const PoseidonLpTables* __restrict__ K) {
+  Fq con = fe_zero<FqCfg>(), g1 = con, xsq = con;
+  if (threadIdx.x == 0) {
     for (uint32_t g = 0; g < G; g++) {
-      // generic loads: `triples` may live in global (gathered) or shared (final rounds) memory
       con = fe_add<FqCfg>(con, triples[(uint64_t)g * 3 + 0]);
       g1 = fe_add<FqCfg>(g1, triples[(uint64_t)g * 3 + 1]);
       xsq = fe_add<FqCfg>(xsq, triples[(uint64_t)g * 3 + 2]);
     }
-    x = fe_sub<FqCfg>(fe_sub<FqCfg>(g1, con), xsq);
-    s = lane < 5 ? st->sponge[lane] : fe_zero<FqCfg>();
-    const Fq e = lane == 1 ? con : (lane == 2 ? x : xsq);
-    const Fq sum = fe_add<FqCfg>(s, to_mont<FqCfg>(e));
-    if (lane >= 1 && lane <= 3) s = sum;
   }
-  poseidon_permute_pair(s, K);
-  Fq r = fe_zero<FqCfg>();
-  if (A) {
-    if (lane < 5) st->sponge[lane] = s;
-    r = shfl_fq(s, 1);
-    if (lane == 0) {
-      st->r_mont = r;
-      st->out_rounds[ri][0] = from_mont<FqCfg>(r);
-      st->out_rounds[ri][1] = xsq;
-      st->out_rounds[ri][2] = x;
-      st->out_rounds[ri][3] = con;
-    }
-  }
-  return r;
+  return tr_round(sh, ts, K, seq, st, ri, con, g1, xsq);
 }
 
 // sweep regime: transcript with the gathered triples, fold A, advance the sparse list
 __global__ void __launch_bounds__(ROUND_THREADS)
 k_shard_apply(NlState* st, const Fq* __restrict__ triples, uint32_t G, uint64_t L, Fq* A, uint64_t a_len,
-              uint64_t* sp_pos, Fq* sp_w, uint32_t m, uint32_t ri, const PoseidonTables* __restrict__ K, MbRef mb) {
-  __shared__ Fq r_sh;
+              uint64_t* sp_pos, Fq* sp_w, uint32_t m, uint32_t ri, const PoseidonLpTables* __restrict__ K, MbRef mb) {
+  __shared__ LpPermShared sh;
+  __shared__ TrScratch ts;
   __shared__ Fq trip_sh[MB_MAX_WORLD * 3];
+  lp_perm_init(&sh);
+  tr_load_state(&sh, st);
   if (mb.peers) {   // fused exchange: this kernel is also the receiver of the round's all-gather
     if (threadIdx.x < mb.world) mb_wait_copy(mb, threadIdx.x, reinterpret_cast<uint32_t*>(trip_sh + 3 * threadIdx.x), 24);
     __syncthreads();
     triples = trip_sh;
   }
   const uint64_t half = L >> 1;
-  if (threadIdx.x < 64) {
-    Fq r = shard_transcript(st, triples, G, ri, K);
-    if (threadIdx.x == 0) r_sh = r;
-  }
-  __syncthreads();
-  const Fq r = r_sh;
+  u32 seq = 0;
+  const Fq r = shard_transcript(&sh, &ts, seq, st, triples, G, ri, K);
+  tr_store_state(&sh, st);
   if (a_len > 1) {
     const uint64_t ah = a_len >> 1;
     for (uint64_t x = threadIdx.x; x < ah; x += ROUND_THREADS) {
@@ -1081,21 +1045,21 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_small_local(const Fq* __restri
 // small regime: transcript with the gathered triples, then fold T_s / E_s in place
 __global__ void __launch_bounds__(TAIL_THREADS)
 k_small_apply(NlState* st, const Fq* __restrict__ triples, uint32_t G, Fq* Ts, Fq* Es, uint64_t L, uint32_t ri,
-              const PoseidonTables* __restrict__ K, MbRef mb) {
-  __shared__ Fq r_sh;
+              const PoseidonLpTables* __restrict__ K, MbRef mb) {
+  __shared__ LpPermShared sh;
+  __shared__ TrScratch ts;
   __shared__ Fq trip_sh[MB_MAX_WORLD * 3];
+  lp_perm_init(&sh);
+  tr_load_state(&sh, st);
   if (mb.peers) {
     if (threadIdx.x < mb.world) mb_wait_copy(mb, threadIdx.x, reinterpret_cast<uint32_t*>(trip_sh + 3 * threadIdx.x), 24);
     __syncthreads();
     triples = trip_sh;
   }
   const uint64_t half = L >> 1;
-  if (threadIdx.x < 64) {
-    Fq r = shard_transcript(st, triples, G, ri, K);
-    if (threadIdx.x == 0) r_sh = r;
-  }
-  __syncthreads();
-  const Fq r = r_sh;
+  u32 seq = 0;
+  const Fq r = shard_transcript(&sh, &ts, seq, st, triples, G, ri, K);
+  tr_store_state(&sh, st);
   // half <= 512: every b is owned by one thread; reads of b + half precede no write there
   for (uint64_t b = threadIdx.x; b < half; b += TAIL_THREADS) {
     Fq t0 = Ts[b], t1 = Ts[b + half], e0 = Es[b], e1 = Es[b + half];
@@ -1122,11 +1086,15 @@ __global__ void k_shard_export(const Fq* __restrict__ Ts, const Fq* __restrict__
 
 // last gamma rounds over the G gathered (T, E) pairs (rank g's pair at index g), identical on
 // every rank; then last claim and next running claim.
-__global__ void __launch_bounds__(64) k_shard_final(NlState* st, const Fq* __restrict__ pairs, uint32_t G, uint32_t ri0,
-                                                    const PoseidonTables* __restrict__ K, MbRef mb) {
-  // warp 0 does the work; warp 1 only partners it inside shard_transcript's permutation
-  __shared__ Fq Ts[64], Es[64], trip[3];
+__global__ void __launch_bounds__(TR_THREADS) k_shard_final(NlState* st, const Fq* __restrict__ pairs, uint32_t G, uint32_t ri0,
+                                                            const PoseidonLpTables* __restrict__ K, MbRef mb) {
+  // warp 0 does the field work between the transcript rounds; the whole CTA runs the permutations
+  __shared__ LpPermShared sh;
+  __shared__ TrScratch ts;
+  __shared__ Fq Ts[64], Es[64];
   __shared__ Fq pair_sh[MB_MAX_WORLD * 2];
+  lp_perm_init(&sh);
+  tr_load_state(&sh, st);
   const int lane = threadIdx.x & 31;
   const bool A = threadIdx.x < 32;
   if (A) {
@@ -1146,11 +1114,13 @@ __global__ void __launch_bounds__(64) k_shard_final(NlState* st, const Fq* __res
     __syncwarp();
   }
   uint32_t ri = ri0;
+  u32 seq = 0;
+  Fq r = fe_zero<FqCfg>();
   for (uint32_t L = G; L > 1; L >>= 1) {
     const uint32_t half = L >> 1;
+    Fq acc[3];
+    acc[0] = acc[1] = acc[2] = fe_zero<FqCfg>();
     if (A) {
-      Fq acc[3];
-      acc[0] = acc[1] = acc[2] = fe_zero<FqCfg>();
       for (uint32_t b = lane; b < half; b += 32) {
         Fq t0 = Ts[b], t1 = Ts[b + half], e0 = Es[b], e1 = Es[b + half];
         acc[0] = fe_add<FqCfg>(acc[0], mont_mul<FqCfg>(e0, t0));
@@ -1159,26 +1129,24 @@ __global__ void __launch_bounds__(64) k_shard_final(NlState* st, const Fq* __res
       }
 #pragma unroll
       for (int k = 0; k < 3; k++) acc[k] = warp_sum_fe<FqCfg>(acc[k]);
-      if (lane == 0)
-        for (int k = 0; k < 3; k++) trip[k] = acc[k];
-      __syncwarp();
     }
-    const Fq r = shard_transcript(st, trip, 1, ri, K);
+    r = tr_round(&sh, &ts, K, seq, st, ri, acc[0], acc[1], acc[2]);
     if (A) {
       for (uint32_t b = lane; b < half; b += 32) {
         Fq t0 = Ts[b], t1 = Ts[b + half], e0 = Es[b], e1 = Es[b + half];
         Ts[b] = fold_one(t0, t1, r);
         Es[b] = fe_add<FqCfg>(e0, mont_mul<FqCfg>(r, fe_sub<FqCfg>(e1, e0)));
       }
-      __syncwarp();
     }
+    __syncthreads();
     ri++;
   }
+  tr_store_state(&sh, st);
   if (threadIdx.x == 0) {
     const uint32_t last = ri - 1;
-    const Fq r = st->r_mont;
-    Fq t = fe_add<FqCfg>(mont_mul<FqCfg>(r, st->out_rounds[last][1]), st->out_rounds[last][2]);
-    st->out_last_claim = fe_add<FqCfg>(mont_mul<FqCfg>(r, t), st->out_rounds[last][3]);
+    const Fq rr = st->r_mont;
+    Fq t = fe_add<FqCfg>(mont_mul<FqCfg>(rr, st->out_rounds[last][1]), st->out_rounds[last][2]);
+    st->out_last_claim = fe_add<FqCfg>(mont_mul<FqCfg>(rr, t), st->out_rounds[last][3]);
     st->out_next_v = Ts[0];
   }
 }
@@ -1285,10 +1253,10 @@ int nl_shard_begin(reef_ctx* c, const NlookupArgs& a, uint32_t rank, uint32_t wo
       cudaMemcpyAsync(s->d_prevq, a.h_prev_q, (size_t)a.ell * 32, cudaMemcpyHostToDevice, st) != cudaSuccess ||
       (a.m && cudaMemcpyAsync(s->d_q, a.h_q, (size_t)a.m * 8, cudaMemcpyHostToDevice, st) != cudaSuccess))
     return bail(fail(REEF_ECUDA, "nl_shard_begin: upload failed"));
-  Fq tag = fq_mont_from_le32(a.tag_le);
+  Fq tag = fq_canon_from_le32(a.tag_le);   // canonical: the LP sponge absorbs plain residues
   {
     ProfScope ps(c, PROF_NL_SETUP, n_loc);
-    k_nl_begin<<<1, 64, exclusive_smem(c, (const void*)k_nl_begin, 0), st>>>(s->st, s->d_query, a.n_query, tag, s->d_prevq, a.ell, s->d_q, a.m, s->d_pos, s->d_w, c->d_pos, rank, world);
+    k_nl_begin<<<1, TR_THREADS, exclusive_smem(c, (const void*)k_nl_begin, 0), st>>>(s->st, s->d_query, a.n_query, tag, s->d_prevq, a.ell, s->d_q, a.m, s->d_pos, s->d_w, c->d_lp, rank, world);
     g_launches.fetch_add(1);
     k_eq_tables<<<ceil_div_u(a_len + b_len, 128), 128, 0, st>>>(s->st, ell_loc, hb, s->d_A, a_len, s->d_B, b_len, gamma, rank);
     g_launches.fetch_add(1);
@@ -1354,10 +1322,10 @@ int nl_shard_round_finish(reef_nl_session* s, const void* d_triples) {
   cudaStream_t st = c->stream;
   ProfScope ps(c, s->small ? PROF_TAIL : PROF_ROUND, s->L);
   if (!s->small) {
-    k_shard_apply<<<1, ROUND_THREADS, exclusive_smem(c, (const void*)k_shard_apply, 0), st>>>(s->st, (const Fq*)d_triples, s->world, s->L, s->d_A, s->a_cur, s->d_pos, s->d_w, s->m, s->round, c->d_pos, s->mb);
+    k_shard_apply<<<1, ROUND_THREADS, exclusive_smem(c, (const void*)k_shard_apply, 0), st>>>(s->st, (const Fq*)d_triples, s->world, s->L, s->d_A, s->a_cur, s->d_pos, s->d_w, s->m, s->round, c->d_lp, s->mb);
     if (s->a_cur > 1) s->a_cur >>= 1;
   } else {
-    k_small_apply<<<1, TAIL_THREADS, exclusive_smem(c, (const void*)k_small_apply, 0), st>>>(s->st, (const Fq*)d_triples, s->world, s->d_Ts, s->d_Es, s->L, s->round, c->d_pos, s->mb);
+    k_small_apply<<<1, TAIL_THREADS, exclusive_smem(c, (const void*)k_small_apply, 0), st>>>(s->st, (const Fq*)d_triples, s->world, s->d_Ts, s->d_Es, s->L, s->round, c->d_lp, s->mb);
   }
   REEF_LAUNCHED();
   s->L >>= 1;
@@ -1379,7 +1347,7 @@ int nl_shard_finish(reef_nl_session* s, const void* d_pairs, uint8_t* out_claim_
   cudaStream_t st = c->stream;
   {
     ProfScope ps(c, PROF_TAIL, s->world);
-    k_shard_final<<<1, 64, exclusive_smem(c, (const void*)k_shard_final, 0), st>>>(s->st, (const Fq*)d_pairs, s->world, s->ell_loc, c->d_pos, s->mb);
+    k_shard_final<<<1, TR_THREADS, exclusive_smem(c, (const void*)k_shard_final, 0), st>>>(s->st, (const Fq*)d_pairs, s->world, s->ell_loc, c->d_lp, s->mb);
     REEF_LAUNCHED();
   }
   void* hs;

@@ -4,6 +4,8 @@
 //   MerkleCommitment::new / new_parent   /root/reference/src/backend/merkle_tree.rs:25-114
 //   calc_d                               /root/reference/src/backend/commitment.rs:495-510
 //   SpongeAPI start/absorb/squeeze       /root/reference/src/backend/r1cs.rs:2260-2311
+#include <cstring>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -50,6 +52,14 @@ void io_pattern_tag_le32(const uint32_t* ops, uint32_t n_ops, uint32_t domain_se
 static Fq fq_from_limbs(const uint32_t* l) {
   Fq x;
   for (int i = 0; i < 8; i++) x.v[i] = l[i];
+  return x;
+}
+
+Fq fq_canon_from_le32(const uint8_t* b) {
+  Fq x;
+  for (int i = 0; i < 8; i++)
+    x.v[i] = (uint32_t)b[4 * i] | ((uint32_t)b[4 * i + 1] << 8) | ((uint32_t)b[4 * i + 2] << 16) |
+             ((uint32_t)b[4 * i + 3] << 24);
   return x;
 }
 
@@ -107,12 +117,78 @@ void poseidon_tables_host(PoseidonTables* t) {
   }
 }
 
+// Tables of the lane-parallel transcript permutation (poseidon_lp.cuh), derived from the same
+// constants: Gamma[r][t] = sum_i beta[r][i] D[t][i],  PD[j][t] = sum_i post[j][i] D[t][i].
+void poseidon_lp_tables_host(PoseidonLpTables* o) {
+  PoseidonTables* t = new PoseidonTables;
+  poseidon_tables_host(t);
+  memset(o, 0, sizeof(*o));
+  auto plain = [](const Fq& m256, u32* out12) {          // Montgomery-256 -> canonical 29-bit limbs
+    const Fq x = from_mont<FqCfg>(m256);
+    const F29 f = f29_from_words(x.v);
+    for (int k = 0; k < 12; k++) out12[k] = k < 9 ? f.l[k] : 0u;
+  };
+  auto padded = [&](const Fq& m256, LpPad* out) {
+    u32 l[12];
+    plain(m256, l);
+    for (int k = 0; k < LP_PAD_WORDS; k++) out->w[k] = 0;
+    for (int k = 0; k < 9; k++) out->w[LP_OFF_WORDS + k] = l[k];
+  };
+  auto m261 = [](const Fq& m256) {                       // Montgomery-256 -> Montgomery-261 (x 2^5)
+    Fq x = m256;
+    for (int k = 0; k < 5; k++) x = fe_dbl<FqCfg>(x);
+    const F29 f = f29_from_words(x.v);
+    F29s r;
+    for (int k = 0; k < 12; k++) r.l[k] = k < 9 ? f.l[k] : 0u;
+    return r;
+  };
+  for (int r = 0; r < 8; r++)
+    for (int i = 0; i < 5; i++) plain(t->rc_full[r][i], o->rcf[r][i]);
+  plain(t->kp[0], o->kp0);
+  for (int r = 0; r < 57; r++) plain(t->kp[r], o->kp[r]);
+  for (int j = 0; j < 4; j++) plain(t->rc_full[4][j + 1], o->rc4[j]);
+  for (int j = 0; j < 5; j++)
+    for (int i = 0; i < 5; i++) padded(t->mds[j][i], &o->mds[j][i]);
+  padded(t->lam_end, &o->lam);
+  {
+    Fq r256;                                             // 2^256 mod p as a Montgomery-256 element = R^2 mod p as an integer
+    for (int i = 0; i < 8; i++) r256.v[i] = FqCfg::r2(i);
+    padded(r256, &o->r256);
+  }
+  for (int r = 0; r < 56; r++)
+    for (int i = 0; i < 4; i++) o->beta[r][i] = m261(t->beta[r][i]);
+  for (int j = 0; j < 4; j++)
+    for (int i = 0; i < 4; i++) o->post[j][i] = m261(t->post[j][i]);
+  for (int r = 0; r < 56; r++)
+    for (int tt = 0; tt < r; tt++) {
+      Fq g = fe_zero<FqCfg>();
+      for (int i = 0; i < 4; i++) g = fe_add<FqCfg>(g, mont_mul<FqCfg>(t->beta[r][i], t->dshift[tt + 1][i]));
+      o->gam[r][tt] = m261(g);
+      if (tt == r - 1) padded(g, &o->gam1[r]);
+    }
+  for (int j = 0; j < 4; j++)
+    for (int tt = 0; tt < 56; tt++) {
+      Fq g = fe_zero<FqCfg>();
+      for (int i = 0; i < 4; i++) g = fe_add<FqCfg>(g, mont_mul<FqCfg>(t->post[j][i], t->dshift[tt + 1][i]));
+      o->pd[j][tt] = m261(g);
+      if (tt == 55) padded(g, &o->pd55[j]);
+    }
+  delete t;
+}
+
 int poseidon_upload_constants(reef_ctx* c) {
   PoseidonTables* h = new PoseidonTables;
   poseidon_tables_host(h);
   cudaError_t e = cudaMalloc(&c->d_pos, sizeof(PoseidonTables));
   if (e == cudaSuccess) e = cudaMemcpy(c->d_pos, h, sizeof(PoseidonTables), cudaMemcpyHostToDevice);
   delete h;
+  if (e == cudaSuccess) {
+    PoseidonLpTables* hl = new PoseidonLpTables;
+    poseidon_lp_tables_host(hl);
+    e = cudaMalloc(&c->d_lp, sizeof(PoseidonLpTables));
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_lp, hl, sizeof(PoseidonLpTables), cudaMemcpyHostToDevice);
+    delete hl;
+  }
   if (e != cudaSuccess) return fail(REEF_ECUDA, std::string("poseidon constants: ") + cudaGetErrorString(e));
   uint8_t tag[32];
   uint32_t p2[2] = {(1u << 31) | 2u, 1u}, p4[2] = {(1u << 31) | 4u, 1u};
@@ -384,3 +460,52 @@ int launch_sponge_step(reef_ctx* c, void* d_state, int op, const void* d_in, uin
 }
 
 }  // namespace reef
+
+// ---------------------------------------------------------------------------------------
+// test hook: the lane-parallel transcript permutation alone (include/reef_b200_testing.h)
+// ---------------------------------------------------------------------------------------
+namespace reef {
+__global__ void __launch_bounds__(LP_PERM_THREADS) k_lp_perm_test(const Fq* __restrict__ in, Fq* __restrict__ out, uint32_t n,
+                                                                  const PoseidonLpTables* __restrict__ T, long long* cycles) {
+  __shared__ LpPermShared sh;
+  lp_perm_init(&sh);
+  if (threadIdx.x < 45) sh.S[threadIdx.x / 9][threadIdx.x % 9] = lp_limb_of(in[threadIdx.x / 9].v, threadIdx.x % 9);
+  __syncthreads();
+  const long long t0 = clock64();
+  for (uint32_t k = 0; k < n; k++) poseidon_permute_lp(&sh, T, k + 1);
+  const long long t1 = clock64();
+  if (threadIdx.x < 5) out[threadIdx.x] = lp_squeeze(&sh, threadIdx.x);
+  if (threadIdx.x == 0) {
+    cycles[0] = n ? (t1 - t0) / n : 0;
+    // phases of the LAST permutation: first full rounds, partial rounds, end, last full rounds; waits inside the chain
+    cycles[1] = sh.dbg[1] - sh.dbg[0];
+    cycles[2] = sh.dbg[2] - sh.dbg[1];
+    cycles[3] = sh.dbg[3] - sh.dbg[2];
+    cycles[4] = sh.dbg[4] - sh.dbg[3];
+    cycles[5] = sh.dbg[5];
+    cycles[6] = sh.dbg[6];
+  }
+}
+}  // namespace reef
+
+extern "C" int reef_gputest_poseidon_permute_lp(void* ctx, const uint8_t in[160], uint32_t n_perms, uint8_t out[160],
+                                                uint64_t* cycles_per_perm) {
+  using namespace reef;
+  reef_ctx* c = (reef_ctx*)ctx;
+  REEF_REQUIRE(c && in && out, REEF_EINVAL, "reef_gputest_poseidon_permute_lp: NULL argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  void* base;
+  int rc = ctx_scratch(c, 1024, &base);
+  if (rc) return rc;
+  char* d = (char*)base;
+  REEF_CUDA(cudaMemcpyAsync(d, in, 160, cudaMemcpyHostToDevice, c->stream));
+  k_lp_perm_test<<<1, LP_PERM_THREADS, 0, c->stream>>>((const Fq*)d, (Fq*)(d + 160), n_perms, c->d_lp, (long long*)(d + 320));
+  REEF_LAUNCHED();
+  uint8_t h[160 + 64];
+  REEF_CUDA(cudaMemcpyAsync(h, d + 160, 160 + 56, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaStreamSynchronize(c->stream));
+  memcpy(out, h, 160);
+  if (cycles_per_perm) memcpy(cycles_per_perm, h + 160, 56);   // [0] per permutation; [1..4] phases, [5..6] chain waits of the last one
+  return REEF_OK;
+}

@@ -28,7 +28,7 @@ int reef_hosttest_ec_op(int curve, int op, const uint8_t p[64], const uint8_t q[
 
 /* GPU test hook for the lane-parallel transcript permutation (poseidon_lp.cuh): `n_perms` successive
  * permutations of one width-5 state (canonical in / out) by one 256-thread CTA; cycles_per_perm
- * (may be NULL, else 7 entries) receives the SM cycles per permutation and, for the last one, the
+ * (may be NULL, else 9 entries) receives the SM cycles per permutation and, for the last one, the
  * cycles of its four phases and of the two waits inside the chain.  ctx: a reef_ctx*. */
 int reef_gputest_poseidon_permute_lp(void* ctx, const uint8_t in[160], uint32_t n_perms, uint8_t out[160], uint64_t* cycles_per_perm);
 

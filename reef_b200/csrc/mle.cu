@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(TR_THREADS) k_nl_begin(NlState* st, const Fq* 
                                                          uint32_t m, uint64_t* __restrict__ sp_pos, Fq* __restrict__ sp_w,
                                                          const PoseidonLpTables* __restrict__ T, uint32_t rank, uint32_t world) {
   __shared__ LpPermShared sh;
-  lp_perm_init(&sh);
+  lp_perm_init(&sh, T);
   u32 seq = 0;
   if (threadIdx.x < 9) sh.S[0][threadIdx.x] = lp_limb_of(tag_canon.v, threadIdx.x);
   // last_q[j] = prev_running_q[ell-1-j]   (r1cs.rs:2318-2319 passes the reversed vector); off the transcript's path
@@ -403,7 +403,7 @@ k_round(NlState* st, const Fq* __restrict__ partials, uint32_t nblk, const void*
   __shared__ LpPermShared sh;
   __shared__ TrScratch ts;
   __shared__ Fq red[3 * ROUND_THREADS / 32];
-  lp_perm_init(&sh);
+  lp_perm_init(&sh, K);
   tr_load_state(&sh, st);
   const uint64_t half = L >> 1;
   Fq acc[3];
@@ -466,7 +466,7 @@ k_tail(NlState* st, const void* __restrict__ Tin, uint64_t L_in, int do_fold, co
   Fq* red = Es + CHUNK;                        // 3 * TAIL_THREADS/32
   __shared__ LpPermShared sh;
   __shared__ TrScratch ts;
-  lp_perm_init(&sh);
+  lp_perm_init(&sh, K);
   tr_load_state(&sh, st);
   uint64_t L = do_fold ? (L_in >> 1) : L_in;   // <= CHUNK
   const Fq a0 = A[0];
@@ -970,7 +970,7 @@ k_shard_apply(NlState* st, const Fq* __restrict__ triples, uint32_t G, uint64_t 
   __shared__ LpPermShared sh;
   __shared__ TrScratch ts;
   __shared__ Fq trip_sh[MB_MAX_WORLD * 3];
-  lp_perm_init(&sh);
+  lp_perm_init(&sh, K);
   tr_load_state(&sh, st);
   if (mb.peers) {   // fused exchange: this kernel is also the receiver of the round's all-gather
     if (threadIdx.x < mb.world) mb_wait_copy(mb, threadIdx.x, reinterpret_cast<uint32_t*>(trip_sh + 3 * threadIdx.x), 24);
@@ -1049,7 +1049,7 @@ k_small_apply(NlState* st, const Fq* __restrict__ triples, uint32_t G, Fq* Ts, F
   __shared__ LpPermShared sh;
   __shared__ TrScratch ts;
   __shared__ Fq trip_sh[MB_MAX_WORLD * 3];
-  lp_perm_init(&sh);
+  lp_perm_init(&sh, K);
   tr_load_state(&sh, st);
   if (mb.peers) {
     if (threadIdx.x < mb.world) mb_wait_copy(mb, threadIdx.x, reinterpret_cast<uint32_t*>(trip_sh + 3 * threadIdx.x), 24);
@@ -1093,7 +1093,7 @@ __global__ void __launch_bounds__(TR_THREADS) k_shard_final(NlState* st, const F
   __shared__ TrScratch ts;
   __shared__ Fq Ts[64], Es[64];
   __shared__ Fq pair_sh[MB_MAX_WORLD * 2];
-  lp_perm_init(&sh);
+  lp_perm_init(&sh, K);
   tr_load_state(&sh, st);
   const int lane = threadIdx.x & 31;
   const bool A = threadIdx.x < 32;

@@ -468,7 +468,7 @@ namespace reef {
 __global__ void __launch_bounds__(LP_PERM_THREADS) k_lp_perm_test(const Fq* __restrict__ in, Fq* __restrict__ out, uint32_t n,
                                                                   const PoseidonLpTables* __restrict__ T, long long* cycles) {
   __shared__ LpPermShared sh;
-  lp_perm_init(&sh);
+  lp_perm_init(&sh, T);
   if (threadIdx.x < 45) sh.S[threadIdx.x / 9][threadIdx.x % 9] = lp_limb_of(in[threadIdx.x / 9].v, threadIdx.x % 9);
   __syncthreads();
   const long long t0 = clock64();
@@ -484,6 +484,8 @@ __global__ void __launch_bounds__(LP_PERM_THREADS) k_lp_perm_test(const Fq* __re
     cycles[4] = sh.dbg[4] - sh.dbg[3];
     cycles[5] = sh.dbg[5];
     cycles[6] = sh.dbg[6];
+    cycles[7] = sh.dbg[7];
+    cycles[8] = sh.dbg[8];
   }
 }
 }  // namespace reef
@@ -502,10 +504,10 @@ extern "C" int reef_gputest_poseidon_permute_lp(void* ctx, const uint8_t in[160]
   REEF_CUDA(cudaMemcpyAsync(d, in, 160, cudaMemcpyHostToDevice, c->stream));
   k_lp_perm_test<<<1, LP_PERM_THREADS, 0, c->stream>>>((const Fq*)d, (Fq*)(d + 160), n_perms, c->d_lp, (long long*)(d + 320));
   REEF_LAUNCHED();
-  uint8_t h[160 + 64];
-  REEF_CUDA(cudaMemcpyAsync(h, d + 160, 160 + 56, cudaMemcpyDeviceToHost, c->stream));
+  uint8_t h[160 + 80];
+  REEF_CUDA(cudaMemcpyAsync(h, d + 160, 160 + 72, cudaMemcpyDeviceToHost, c->stream));
   REEF_CUDA(cudaStreamSynchronize(c->stream));
   memcpy(out, h, 160);
-  if (cycles_per_perm) memcpy(cycles_per_perm, h + 160, 56);   // [0] per permutation; [1..4] phases, [5..6] chain waits of the last one
+  if (cycles_per_perm) memcpy(cycles_per_perm, h + 160, 72);   // [0] per permutation; [1..4] phases, [5..6] chain waits of the last one
   return REEF_OK;
 }

@@ -25,6 +25,10 @@
 #include "lpmul.cuh"
 #include "poseidon.cuh"
 
+#ifndef REEF_LP_EXPERIMENT
+#define REEF_LP_EXPERIMENT 0      // 1, 2: timing experiments of tools/ (wrong results on purpose)
+#endif
+
 namespace reef {
 
 struct alignas(16) LpPad {
@@ -61,14 +65,16 @@ struct alignas(16) LpPermShared {
   u32 hbuf[5][12];
   LpPad x5[2][5];        // S-box outputs of a full round (double-buffered), operand layout
   u32 U[4][12];          // u_t (10 limbs), tag = bit 31 = (t >> 2) & 1
+  u32 Uend[12];          // u_55 once more, tag = permutation parity (its readers may arrive long before it exists)
   u32 Cs[2][12];         // c_r (10 limbs), tag = (r >> 1) & 1
   u32 S0[4][12];         // s_i(0), 9 limbs (prologue input)
   u32 C0[56][12];        // C0_r, 9 limbs, tag = permutation parity
   u32 Y0[4][12];
   u32 fin[2][56][12];    // [parity of t][r]: accumulated terms t <= r-2, 9 limbs, tag = permutation parity
   u32 yf[2][4][12];
+  LpPad mds[5][5];       // copy of PoseidonLpTables::mds (lane-shifted reads every full round)
   u32 prog[4];           // per accumulator warp: number of u_t consumed
-  long long dbg[8];      // warp 0's clock at the phase boundaries of the last permutation (test hook only)
+  long long dbg[10];      // warp 0's clock at the phase boundaries of the last permutation (test hook only)
 };
 
 __device__ __forceinline__ u32 lp_ldv(const u32* p) { return *(const volatile u32*)p; }
@@ -193,7 +199,7 @@ __device__ __forceinline__ u32 lp_full_round(LpPermShared* sh, const PoseidonLpT
   lp_bar(2, 160);
   u64 col = 0;
 #pragma unroll
-  for (int t = 0; t < 5; t++) col = lp_cols_a(sh->x5[buf][t].w + LP_OFF, 0xffffffffu, T->mds[i][t].w, lane, col);
+  for (int t = 0; t < 5; t++) col = lp_cols_a(sh->x5[buf][t].w + LP_OFF, 0xffffffffu, sh->mds[i][t].w, lane, col);
   const u32 add = (add_row && lane < 9) ? add_row[i * 12 + lane] : 0u;
   return lp_fold<false>(col, c, hb, lane, add);
 }
@@ -202,9 +208,17 @@ __device__ __forceinline__ u32 lp_full_round(LpPermShared* sh, const PoseidonLpT
 // partial rounds
 // ---------------------------------------------------------------------------------------
 // warp 0: the chain.  w = limb `lane` of w_0 (lanes 0..9); returns w_56.
-__device__ __forceinline__ u32 lp_partial_A(LpPermShared* sh, const LpLane& c, int lane, u32 w) {
+#ifdef REEF_LP_TIMING
+#define LP_T(k) do { const long long _t = clock64(); if (lane == 0) sh->dbg[k] += _t - tmark; tmark = _t; } while (0)
+#else
+#define LP_T(k) do { } while (0)
+#endif
+__device__ __forceinline__ u32 lp_partial_A(LpPermShared* sh, const LpLane& c, int lane, u32 w, u32 ptag) {
   LpPad* p = sh->pad[0];
   u32* hb = sh->hbuf[0];
+#ifdef REEF_LP_TIMING
+  long long tmark = clock64();
+#endif
 #pragma unroll 1
   for (int r = 0; r < 56; r++) {
     lp_store(p[0].w, lane, w);
@@ -212,24 +226,39 @@ __device__ __forceinline__ u32 lp_partial_A(LpPermShared* sh, const LpLane& c, i
     const u32 m2 = lp_mul<false>(p[0].w, p[0].w, c, hb, lane);
     lp_store(p[1].w, lane, m2);
     __syncwarp();
+    // Both things the end of this round waits for are normally there long before: read them now, off the
+    // chain (c_r is published by warp B about a third into the round; the accumulator warps run a round ahead)
+    const int wa = (r & 1) * 2;
+    u32 pg0 = lp_ldv(&sh->prog[wa]), pg1 = lp_ldv(&sh->prog[wa + 1]);
     const u32 m4 = lp_mul<false>(p[1].w, p[1].w, c, hb, lane);
     lp_store(p[2].w, lane, m4);
     __syncwarp();
+    LP_T(5);
+    const u32 ctag = ((u32)(r >> 1) & 1u) << 31;
+    u32 cw = lane < 10 ? lp_ldv(&sh->Cs[r & 1][lane]) : ctag;
     const u64 col = lp_cols(p[2].w, p[0].w, lane);
-    const long long tw0 = clock64();
-    const u32 cr = lp_wait_lane(sh->Cs[r & 1], 10, ((u32)(r >> 1) & 1u) << 31, lane);
-    if (lane == 0) sh->dbg[5] += clock64() - tw0;
+#if REEF_LP_EXPERIMENT == 1 || REEF_LP_EXPERIMENT == 2
+    cw = 0;
+#else
+    while (!__all_sync(0xffffffffu, (cw & LP_TAG) == ctag)) cw = lane < 10 ? lp_ldv(&sh->Cs[r & 1][lane]) : ctag;
+    cw = lane < 10 ? (cw & ~LP_TAG) : 0u;
+#endif
+    LP_T(6);
     u32 u;
-    w = lp_fold2(col, c, hb, lane, cr, &u);
+    w = lp_fold2(col, c, hb, lane, cw, &u);
+    LP_T(7);
+#if REEF_LP_EXPERIMENT == 0
     if (r >= 4) {
       // slot r & 3 still holds u_(r-4): its readers are the accumulator warps of parity r & 1
-      const int wa = (r & 1) * 2;
-      const long long tw1 = clock64();
-      while (lp_ldv(&sh->prog[wa]) < (u32)(r - 3) || lp_ldv(&sh->prog[wa + 1]) < (u32)(r - 3)) {
+      while (pg0 < (u32)(r - 3) || pg1 < (u32)(r - 3)) {
+        pg0 = lp_ldv(&sh->prog[wa]);
+        pg1 = lp_ldv(&sh->prog[wa + 1]);
       }
-      if (lane == 0) sh->dbg[6] += clock64() - tw1;
     }
+#endif
     if (lane < 10) lp_stv(&sh->U[r & 3][lane], u | (((u32)(r >> 2) & 1u) << 31));
+    if (r == 55 && lane < 10) lp_stv(&sh->Uend[lane], u | ptag);
+    LP_T(8);
   }
   return w;
 }
@@ -256,10 +285,13 @@ __device__ __forceinline__ void lp_partial_B(LpPermShared* sh, const PoseidonLpT
   }
 }
 
-// warps 2..5: accumulator lanes (one-thread arithmetic).  Pair (2,3) takes the even t, (4,5) the odd t.
+// warps 2, 3 (even t) and 6, 7 (odd t): accumulator lanes (one-thread arithmetic).  Warps 4 and 5 share their
+// schedulers with the chain warp A (0) and with B (1) and stay idle: a computing warp on A's scheduler
+// costs the chain 50 % (tools/bench_lp.cu, modes 3-9), polling and computing warps elsewhere cost nothing.
 __device__ __forceinline__ void lp_partial_C(LpPermShared* sh, const PoseidonLpTables* T, int warp, int lane, u32 ptag) {
-  const int par = (warp - 2) >> 1;
-  const int q = ((warp - 2) & 1) * 32 + lane;          // 0..55: round r = q;  56..59: state lane j = q - 56
+  const int par = warp >> 2;                           // warps 2,3 -> 0; 6,7 -> 1
+  const int pslot = par * 2 + (warp & 1);
+  const int q = (warp & 1) * 32 + lane;                // 0..55: round r = q;  56..59: state lane j = q - 56
   const bool is_r = q < 56, is_y = q >= 56 && q < 60;
   const int r = is_r ? q : 55, j = is_y ? q - 56 : 0;
   F29 acc = f29_zero();
@@ -291,7 +323,7 @@ __device__ __forceinline__ void lp_partial_C(LpPermShared* sh, const PoseidonLpT
       }
     } while (!ok);
     __syncwarp();
-    if (lane == 0) lp_stv(&sh->prog[warp - 2], (u32)(t + 1));
+    if (lane == 0) lp_stv(&sh->prog[pslot], (u32)(t + 1));
     if (active) {
       const F29 uf = lp10_to_f29<0>(u10);
       acc = f29_relax(f29_add_lazy(acc, mul29<FqCfg>(uf, k)));
@@ -331,10 +363,15 @@ __device__ __forceinline__ void lp_prologue(LpPermShared* sh, const PoseidonLpTa
 }
 
 // Once per kernel, by all LP_PERM_THREADS threads, before the first permutation.
-__device__ __forceinline__ void lp_perm_init(LpPermShared* sh) {
+__device__ __forceinline__ void lp_perm_init(LpPermShared* sh, const PoseidonLpTables* T) {
   u32* w = reinterpret_cast<u32*>(sh);
   for (int i = threadIdx.x; i < (int)(sizeof(LpPermShared) / 4); i += LP_PERM_THREADS) w[i] = 0;
   __syncthreads();
+  {
+    const u32* src = &T->mds[0][0].w[0];
+    u32* dst = &sh->mds[0][0].w[0];
+    for (int i = threadIdx.x; i < 25 * LP_PAD; i += LP_PERM_THREADS) dst[i] = src[i];
+  }
   // slots whose first use expects tag 0 start "invalid"
   if (threadIdx.x < 48) sh->U[threadIdx.x / 12][threadIdx.x % 12] = LP_TAG;
   if (threadIdx.x >= 64 && threadIdx.x < 88) sh->Cs[(threadIdx.x - 64) / 12][(threadIdx.x - 64) % 12] = LP_TAG;
@@ -344,10 +381,12 @@ __device__ __forceinline__ void lp_perm_init(LpPermShared* sh) {
 // One permutation of sh->S by the whole CTA (LP_PERM_THREADS threads, all must call).
 // seq: 1, 2, 3, ... number of this permutation within the kernel (the same on every thread).
 static __device__ __noinline__ void poseidon_permute_lp(LpPermShared* sh, const PoseidonLpTables* T, u32 seq) {
-  const int warp = (threadIdx.x >> 5) & 7, lane = threadIdx.x & 31;
+  // warp index through a broadcast shuffle: the compiler then KNOWS it is warp-uniform and keeps the role
+  // branches below convergent (plain SHFL / no WARPSYNC+ENDCOLLECTIVE around every shuffle and __syncwarp)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5) & 7, 0), lane = threadIdx.x & 31;
   const u32 ptag = (seq & 1u) << 31;
   if (threadIdx.x < 4) sh->prog[threadIdx.x] = 0;      // read by warp 0 only, from round 4 on
-  if (threadIdx.x == 0) sh->dbg[5] = sh->dbg[6] = 0;
+  if (threadIdx.x == 0) sh->dbg[5] = sh->dbg[6] = sh->dbg[7] = sh->dbg[8] = 0;
   if (warp < 5) {
     const LpLane c = lp_lane_consts<0>(lane);
     const int i = warp;
@@ -376,13 +415,13 @@ static __device__ __noinline__ void poseidon_permute_lp(LpPermShared* sh, const 
       lp_bar(2, 160);
       u64 col = 0;
 #pragma unroll
-      for (int t = 0; t < 5; t++) col = lp_cols_a(sh->x5[buf][t].w + LP_OFF, 0xffffffffu, T->mds[i][t].w, lane, col);
+      for (int t = 0; t < 5; t++) col = lp_cols_a(sh->x5[buf][t].w + LP_OFF, 0xffffffffu, sh->mds[i][t].w, lane, col);
       x = lp_fold<false>(col, c, hb, lane, (i == 0 && lane < 9) ? T->kp0[lane] : 0u);
       buf ^= 1;
     }
     if (threadIdx.x == 0) sh->dbg[1] = clock64();
     if (i == 0) {
-      x = lp_partial_A(sh, c, lane, x);                       // w_56
+      x = lp_partial_A(sh, c, lane, x, ptag);                 // w_56
       if (threadIdx.x == 0) sh->dbg[2] = clock64();
       // x_0 = lam_end * w_56 + rc_full[4][0]
       lp_store(sh->pad[0][0].w, lane, x);
@@ -394,18 +433,27 @@ static __device__ __noinline__ void poseidon_permute_lp(LpPermShared* sh, const 
       if (lane < 9) sh->S0[i - 1][lane] = s9;
       lp_bar(3, 224);
       lp_prologue(sh, T, warp, lane, ptag);
+#if REEF_LP_EXPERIMENT == 1
+      (void)0;                                   // timing experiment: the chain alone (results are wrong)
+#elif REEF_LP_EXPERIMENT == 2
+      if (i == 2 || i == 3) lp_partial_C(sh, T, warp, lane, ptag);   // accumulators run, B does not
+#else
       if (i == 1) lp_partial_B(sh, T, c, lane, ptag);
-      else lp_partial_C(sh, T, warp, lane, ptag);
+      else if (i < 4) lp_partial_C(sh, T, warp, lane, ptag);
+#endif
       // x_i = y_i + PD[i-1][55] u_55   (rc_full[4][i] is already in y)
-      const u32 ut = ((u32)(55 >> 2) & 1u) << 31;
-      const u32* us = sh->U[55 & 3];
-      while ((lp_ldv(us + 9) & LP_TAG) != ut) {
-      }
+      const u32 ut = ptag;
+      const u32* us = sh->Uend;
+      while ((lp_ldv(us + 9) & LP_TAG) != ut) __nanosleep(100);
       (void)lp_wait_lane(us, 10, ut, lane);
       __syncwarp();
       const u64 col = lp_cols_a(us, ~LP_TAG, T->pd55[i - 1].w, lane);
+#if REEF_LP_EXPERIMENT == 1
+      const u32 ye = 0, yo = 0;
+#else
       const u32 ye = lp_wait_lane(sh->yf[0][i - 1], 9, ptag, lane);
       const u32 yo = lp_wait_lane(sh->yf[1][i - 1], 9, ptag, lane);
+#endif
       x = lp_fold<false>(col, c, sh->hbuf[i], lane, ye + yo);
     }
 #pragma unroll 1
@@ -416,7 +464,9 @@ static __device__ __noinline__ void poseidon_permute_lp(LpPermShared* sh, const 
   } else {
     lp_bar(3, 224);
     lp_prologue(sh, T, warp, lane, ptag);
-    if (warp == 5) lp_partial_C(sh, T, warp, lane, ptag);
+#if REEF_LP_EXPERIMENT != 1
+    if (warp >= 6) lp_partial_C(sh, T, warp, lane, ptag);
+#endif
   }
   __syncthreads();
 }

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 def _lp(ctx, state, n):
     inp = b"".join(int(x).to_bytes(32, "little") for x in state)
     out = C.create_string_buffer(160)
-    cyc = (C.c_uint64 * 7)()
+    cyc = (C.c_uint64 * 9)()
     check(lib.reef_gputest_poseidon_permute_lp(ctx._h, inp, n, out, cyc))
     return [int.from_bytes(out.raw[i * 32:(i + 1) * 32], "little") for i in range(5)], list(cyc)
 
@@ -36,5 +36,5 @@ def test_chained_permutations_and_latency(ctx):
     got, cyc = _lp(ctx, st, 7)
     assert got == exp
     print(f"lane-parallel permutation: {cyc[0]} SM cycles per permutation; last one: first full rounds {cyc[1]}, "
-          f"partial rounds {cyc[2]} (waiting for c_r {cyc[5]}, for slot reuse {cyc[6]}), end {cyc[3]}, last full rounds {cyc[4]}")
+          f"partial rounds {cyc[2]}, end {cyc[3]}, last full rounds {cyc[4]}; chain phases (only with -DREEF_LP_TIMING): {cyc[5:9]}")
     assert 0 < cyc[0] < 200000

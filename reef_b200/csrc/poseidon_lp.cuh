@@ -107,6 +107,40 @@ __device__ __forceinline__ u64 lp_cols_a(const u32* a10, u32 mask, const u32* b_
   return c0 + c1 + c2;
 }
 
+// the same with b already in registers: bq[l] = b_(lane - l)
+__device__ __forceinline__ u64 lp_cols_reg(const u32* a10, const u32* bq, u32 mask = 0xffffffffu) {
+  u64 c0 = 0, c1 = 0, c2 = 0;
+  const uint4 a03 = *reinterpret_cast<const uint4*>(a10);
+  const uint4 a47 = *reinterpret_cast<const uint4*>(a10 + 4);
+  const uint2 a89 = *reinterpret_cast<const uint2*>(a10 + 8);
+  c0 = lp_mad(a03.x & mask, bq[0], c0);
+  c1 = lp_mad(a03.y & mask, bq[1], c1);
+  c2 = lp_mad(a03.z & mask, bq[2], c2);
+  c0 = lp_mad(a03.w & mask, bq[3], c0);
+  c1 = lp_mad(a47.x & mask, bq[4], c1);
+  c2 = lp_mad(a47.y & mask, bq[5], c2);
+  c0 = lp_mad(a47.z & mask, bq[6], c0);
+  c1 = lp_mad(a47.w & mask, bq[7], c1);
+  c2 = lp_mad(a89.x & mask, bq[8], c2);
+  c0 = lp_mad(a89.y & mask, bq[9], c0);
+  return c0 + c1 + c2;
+}
+
+// lane-shifted register copy of an operand-layout constant: q[l] = limb (lane - l)
+__device__ __forceinline__ void lp_load_shifted(u32* q /*10*/, const u32* b_pad, int lane) {
+  const u32* b = b_pad + LP_OFF + lane;
+#pragma unroll
+  for (int l = 0; l < 10; l++) q[l] = b[-l];
+}
+
+// lane-shifted register copy of the five MDS constants of row i: q[t][l] = limb (lane - l) of mds[i][t].
+// Loaded once per permutation; the eight full rounds then read only the broadcast S-box outputs from shared
+// memory (the MDS phase starts on all five warps at once, right after their barrier: 65 shared-memory
+// loads per lane per warp there were a queue, not a latency).
+struct LpMdsRow {
+  u32 q[5][10];
+};
+
 // lp_fold with two results from one fold: with and without the addend (w_(r+1) = u_r + c_r and u_r)
 __device__ __forceinline__ u32 lp_fold2(u64 col, const LpLane& c, u32* h_buf, int lane, u32 addend, u32* out_plain) {
   u32 p0 = (u32)col & M29, p1 = (u32)(col >> 29) & M29, p2 = (u32)(col >> 58);
@@ -182,10 +216,19 @@ __device__ __forceinline__ u32 lp_wait_lane(const u32* p, int n, u32 tag, int la
 // ---------------------------------------------------------------------------------------
 // one full round for warp i (state element i): x -> sum_t mds[i][t] x_t^5 (+ addend)
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ u32 lp_full_round(LpPermShared* sh, const PoseidonLpTables* T, const LpLane& c, int i, int lane,
-                                             u32 x, int buf, const u32* add_row /* [5][12] or nullptr */) {
+__device__ __forceinline__ u32 lp_full_round(LpPermShared* sh, const LpMdsRow& M, const LpLane& c, int i, int lane,
+                                             u32 x, int buf, const u32* add_row /* [5][12] or nullptr */, bool first_only = false) {
   LpPad* p = sh->pad[i];
   u32* hb = sh->hbuf[i];
+  // next round's constants ride on the normalisation (first_only: only state element 0 gets one, kp[0]);
+  // they come from global memory: issue the load now, a whole S-box before its use
+  const u32 add = (add_row && lane < 9 && (!first_only || i == 0)) ? add_row[(first_only ? 0 : i * 12) + lane] : 0u;
+#if defined(REEF_LP_TIMING) && REEF_LP_TIMING == 2
+  long long tmark = clock64();
+#define LP_TF(k) do { const long long _t = clock64(); if (threadIdx.x == 0) sh->dbg[k] += _t - tmark; tmark = _t; } while (0)
+#else
+#define LP_TF(k) do { } while (0)
+#endif
   lp_store(p[0].w, lane, x);
   __syncwarp();
   const u32 m2 = lp_mul<false>(p[0].w, p[0].w, c, hb, lane);
@@ -196,19 +239,45 @@ __device__ __forceinline__ u32 lp_full_round(LpPermShared* sh, const PoseidonLpT
   __syncwarp();
   const u32 x5 = lp_mul<true>(p[2].w, p[0].w, c, hb, lane);
   lp_store(sh->x5[buf][i].w, lane, x5);
+  LP_TF(5);
   lp_bar(2, 160);
-  u64 col = 0;
+  LP_TF(6);
+  // all fifteen broadcast loads first (one latency), then the fifty products
+  uint4 a03[5], a47[5];
+  uint2 a89[5];
 #pragma unroll
-  for (int t = 0; t < 5; t++) col = lp_cols_a(sh->x5[buf][t].w + LP_OFF, 0xffffffffu, sh->mds[i][t].w, lane, col);
-  const u32 add = (add_row && lane < 9) ? add_row[i * 12 + lane] : 0u;
-  return lp_fold<false>(col, c, hb, lane, add);
+  for (int t = 0; t < 5; t++) {
+    const u32* a10 = sh->x5[buf][t].w + LP_OFF;
+    a03[t] = *reinterpret_cast<const uint4*>(a10);
+    a47[t] = *reinterpret_cast<const uint4*>(a10 + 4);
+    a89[t] = *reinterpret_cast<const uint2*>(a10 + 8);
+  }
+  u64 c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+#pragma unroll
+  for (int t = 0; t < 5; t++) {
+    c0 = lp_mad(a03[t].x, M.q[t][0], c0);
+    c1 = lp_mad(a03[t].y, M.q[t][1], c1);
+    c2 = lp_mad(a03[t].z, M.q[t][2], c2);
+    c3 = lp_mad(a03[t].w, M.q[t][3], c3);
+    c4 = lp_mad(a47[t].x, M.q[t][4], c4);
+    c0 = lp_mad(a47[t].y, M.q[t][5], c0);
+    c1 = lp_mad(a47[t].z, M.q[t][6], c1);
+    c2 = lp_mad(a47[t].w, M.q[t][7], c2);
+    c3 = lp_mad(a89[t].x, M.q[t][8], c3);
+    c4 = lp_mad(a89[t].y, M.q[t][9], c4);
+  }
+  const u64 col = (c0 + c1) + (c2 + c3) + c4;
+  LP_TF(7);
+  const u32 res = lp_fold<false>(col, c, hb, lane, add);
+  LP_TF(8);
+  return res;
 }
 
 // ---------------------------------------------------------------------------------------
 // partial rounds
 // ---------------------------------------------------------------------------------------
 // warp 0: the chain.  w = limb `lane` of w_0 (lanes 0..9); returns w_56.
-#ifdef REEF_LP_TIMING
+#if defined(REEF_LP_TIMING) && REEF_LP_TIMING == 1
 #define LP_T(k) do { const long long _t = clock64(); if (lane == 0) sh->dbg[k] += _t - tmark; tmark = _t; } while (0)
 #else
 #define LP_T(k) do { } while (0)
@@ -216,7 +285,7 @@ __device__ __forceinline__ u32 lp_full_round(LpPermShared* sh, const PoseidonLpT
 __device__ __forceinline__ u32 lp_partial_A(LpPermShared* sh, const LpLane& c, int lane, u32 w, u32 ptag) {
   LpPad* p = sh->pad[0];
   u32* hb = sh->hbuf[0];
-#ifdef REEF_LP_TIMING
+#if defined(REEF_LP_TIMING) && REEF_LP_TIMING == 1
   long long tmark = clock64();
 #endif
 #pragma unroll 1
@@ -270,13 +339,15 @@ __device__ __forceinline__ void lp_partial_B(LpPermShared* sh, const PoseidonLpT
   for (int r = 0; r < 56; r++) {
     u64 col = 0;
     if (r >= 1) {
+      u32 gq[10];
+      lp_load_shifted(gq, T->gam1[r].w, lane);      // global memory: in flight while this warp waits for u_(r-1)
       const u32 ut = ((u32)((r - 1) >> 2) & 1u) << 31;
       const u32* us = sh->U[(r - 1) & 3];
       while ((lp_ldv(us + 9) & LP_TAG) != ut) {
       }
       (void)lp_wait_lane(us, 10, ut, lane);
       __syncwarp();
-      col = lp_cols_a(us, ~LP_TAG, T->gam1[r].w, lane);
+      col = lp_cols_reg(us, gq, ~LP_TAG);
     }
     const u32 fe = lp_wait_lane(sh->fin[0][r], 9, ptag, lane);
     const u32 fo = lp_wait_lane(sh->fin[1][r], 9, ptag, lane);
@@ -390,6 +461,13 @@ static __device__ __noinline__ void poseidon_permute_lp(LpPermShared* sh, const 
   if (warp < 5) {
     const LpLane c = lp_lane_consts<0>(lane);
     const int i = warp;
+    LpMdsRow M;
+#pragma unroll
+    for (int t = 0; t < 5; t++) {
+      const u32* b = sh->mds[i][t].w + LP_OFF + lane;
+#pragma unroll
+      for (int l = 0; l < 10; l++) M.q[t][l] = b[-l];
+    }
     // entry: state + first round constants, one carry step
     if (threadIdx.x == 0) sh->dbg[0] = clock64();
     u32 x = lane < 10 ? sh->S[i][lane] : 0u;
@@ -397,36 +475,21 @@ static __device__ __noinline__ void poseidon_permute_lp(LpPermShared* sh, const 
     x = lp_norm(x, lane);
     int buf = 0;
 #pragma unroll 1
-    for (int r = 0; r < 3; r++, buf ^= 1) x = lp_full_round(sh, T, c, i, lane, x, buf, &T->rcf[r + 1][0][0]);
-    // last full round before the partial rounds: only lane 0 of the state gets a constant (kp[0])
-    {
-      LpPad* p = sh->pad[i];
-      u32* hb = sh->hbuf[i];
-      lp_store(p[0].w, lane, x);
-      __syncwarp();
-      const u32 m2 = lp_mul<false>(p[0].w, p[0].w, c, hb, lane);
-      lp_store(p[1].w, lane, m2);
-      __syncwarp();
-      const u32 m4 = lp_mul<false>(p[1].w, p[1].w, c, hb, lane);
-      lp_store(p[2].w, lane, m4);
-      __syncwarp();
-      const u32 x5 = lp_mul<true>(p[2].w, p[0].w, c, hb, lane);
-      lp_store(sh->x5[buf][i].w, lane, x5);
-      lp_bar(2, 160);
-      u64 col = 0;
-#pragma unroll
-      for (int t = 0; t < 5; t++) col = lp_cols_a(sh->x5[buf][t].w + LP_OFF, 0xffffffffu, sh->mds[i][t].w, lane, col);
-      x = lp_fold<false>(col, c, hb, lane, (i == 0 && lane < 9) ? T->kp0[lane] : 0u);
-      buf ^= 1;
-    }
+    for (int r = 0; r < 3; r++, buf ^= 1) x = lp_full_round(sh, M, c, i, lane, x, buf, &T->rcf[r + 1][0][0]);
+    // last full round before the partial rounds: only element 0 of the state gets a constant (kp[0])
+    x = lp_full_round(sh, M, c, i, lane, x, buf, T->kp0, true);
+    buf ^= 1;
     if (threadIdx.x == 0) sh->dbg[1] = clock64();
     if (i == 0) {
       x = lp_partial_A(sh, c, lane, x, ptag);                 // w_56
       if (threadIdx.x == 0) sh->dbg[2] = clock64();
       // x_0 = lam_end * w_56 + rc_full[4][0]
+      u32 lq[10];
+      lp_load_shifted(lq, T->lam.w, lane);
+      const u32 rc40 = lane < 9 ? T->rcf[4][0][lane] : 0u;
       lp_store(sh->pad[0][0].w, lane, x);
       __syncwarp();
-      x = lp_fold<false>(lp_cols(sh->pad[0][0].w, T->lam.w, lane), c, sh->hbuf[0], lane, lane < 9 ? T->rcf[4][0][lane] : 0u);
+      x = lp_fold<false>(lp_cols_reg(sh->pad[0][0].w + LP_OFF, lq), c, sh->hbuf[0], lane, rc40);
     } else {
       // s_i(0) for the prologue (nine limbs), then this warp's role in the partial rounds
       const u32 s9 = lp_fold_b(x, c, lane);
@@ -442,12 +505,14 @@ static __device__ __noinline__ void poseidon_permute_lp(LpPermShared* sh, const 
       else if (i < 4) lp_partial_C(sh, T, warp, lane, ptag);
 #endif
       // x_i = y_i + PD[i-1][55] u_55   (rc_full[4][i] is already in y)
+      u32 pq[10];
+      lp_load_shifted(pq, T->pd55[i - 1].w, lane);
       const u32 ut = ptag;
       const u32* us = sh->Uend;
       while ((lp_ldv(us + 9) & LP_TAG) != ut) __nanosleep(100);
       (void)lp_wait_lane(us, 10, ut, lane);
       __syncwarp();
-      const u64 col = lp_cols_a(us, ~LP_TAG, T->pd55[i - 1].w, lane);
+      const u64 col = lp_cols_reg(us, pq, ~LP_TAG);
 #if REEF_LP_EXPERIMENT == 1
       const u32 ye = 0, yo = 0;
 #else
@@ -458,7 +523,7 @@ static __device__ __noinline__ void poseidon_permute_lp(LpPermShared* sh, const 
     }
 #pragma unroll 1
     if (threadIdx.x == 0) sh->dbg[3] = clock64();
-    for (int r = 4; r < 8; r++, buf ^= 1) x = lp_full_round(sh, T, c, i, lane, x, buf, r < 7 ? &T->rcf[r + 1][0][0] : nullptr);
+    for (int r = 4; r < 8; r++, buf ^= 1) x = lp_full_round(sh, M, c, i, lane, x, buf, r < 7 ? &T->rcf[r + 1][0][0] : nullptr);
     if (lane < 10) sh->S[i][lane] = x;
     if (threadIdx.x == 0) sh->dbg[4] = clock64();
   } else {

@@ -114,6 +114,15 @@ int reef_merkle_build(reef_ctx* ctx, const uint64_t* doc, uint64_t n_doc, uint8_
 int reef_merkle_build_dev(reef_ctx* ctx, const uint64_t* doc_dev, uint64_t n_doc, void* levels_dev,
                           uint64_t* level_sizes, uint32_t* n_levels, uint8_t out_root[32]);
 
+/* Multi-GPU split of MerkleCommitment::new: rank g builds the subtree over the contiguous
+ * leaves [idx_offset, idx_offset + n_local) -- the leaf hash takes the GLOBAL index, merkle_tree.rs:85-96 --
+ * n_local a power of two >= 2, idx_offset a multiple of n_local.  out_levels (nullable) receives the
+ * n_local - 1 elements of the subtree's levels, leaf parents first; out_root its root.  The G roots are
+ * all-gathered by the caller and reef_merkle_top hashes them up: (G - 1) elements, levels of G/2, G/4, .. 1. */
+int reef_merkle_subtree(reef_ctx* ctx, const uint64_t* doc_local, uint64_t n_local, uint64_t idx_offset,
+                        uint8_t* out_levels, uint8_t out_root[32]);
+int reef_merkle_top(reef_ctx* ctx, const uint8_t* subtree_roots, uint32_t g, uint8_t* out_levels, uint8_t out_root[32]);
+
 /* merkle_tree.rs:128-191 `path_wits(idx)` on a host copy of the tree.  Writes n_levels
  * entries: l_or_r[k], has_idx[k] (1 only for the leaf entry), opposite_idx[k] (u64),
  * opposite[k] (32 B). */
@@ -258,6 +267,11 @@ int reef_msm_rows(reef_ctx* ctx, const reef_bases* b, const uint8_t* matrix, uin
 int reef_msm_partial_dev(reef_ctx* ctx, const reef_bases* b, const void* scalars_dev, uint64_t n, uint32_t w_begin,
                          uint32_t w_end, uint8_t out_xyzz[128]);
 int reef_msm_combine(reef_ctx* ctx, int curve, const uint8_t* partials_xyzz, uint32_t k, uint8_t out[64]);
+/* The whole window-sharded MSM in one stream-ordered call (needs reef_mailbox_connect on `ctx`): this
+ * rank's windows [W*g/G, W*(g+1)/G), one 128-byte all-gather of the partial points over NVLink peer
+ * memory done by a kernel of this library, the combine on every rank.  Every rank of the world must call
+ * it with the same scalars (resident on its own device) and gets the same affine result. */
+int reef_msm_sharded_dev(reef_ctx* ctx, const reef_bases* b, const void* scalars_dev, uint64_t n, uint8_t out[64]);
 
 /* ------------------------------------------------------------------ multi-GPU: small-message exchange over NVLink peer memory
  * The per-round exchange of the sharded sum-check (96 bytes per rank) done by a kernel of this
@@ -267,7 +281,7 @@ int reef_msm_combine(reef_ctx* ctx, int curve, const uint8_t* partials_xyzz, uin
  *   reef_mailbox_create   allocate this rank's mailbox, return its 64-byte IPC handle
  *   reef_mailbox_connect  open the peers' mailboxes (handles of all ranks, rank-major, own slot ignored)
  *   reef_mailbox_connect_local  same-process variant (tests): device pointers from reef_mailbox_ptr
- *   reef_p2p_allgather    out_dev[g*nbytes ..] = rank g's mine_dev[0 .. nbytes), nbytes <= 120, multiple of 4;
+ *   reef_p2p_allgather    out_dev[g*nbytes ..] = rank g's mine_dev[0 .. nbytes), nbytes <= 248, multiple of 4;
  *                         stream-ordered, no host synchronisation; every rank must issue the same sequence
  *   reef_p2p_status       synchronises and reports a peer that never posted (bounded wait, ~2 s) */
 int reef_mailbox_create(reef_ctx* ctx, uint32_t world, uint8_t out_handle[64]);

@@ -97,6 +97,9 @@ _sig = {
     "reef_msm_rows": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, _vp]),
     "reef_msm_partial_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _vp]),
     "reef_msm_combine": (C.c_int, [_vp, C.c_int, _vp, C.c_uint32, _vp]),
+    "reef_msm_sharded_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp]),
+    "reef_merkle_subtree": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64, _vp, _vp]),
+    "reef_merkle_top": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp]),
     # test hooks (include/reef_b200_testing.h)
     "reef_hosttest_ec_op": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp]),
     "reef_mailbox_create": (C.c_int, [_vp, C.c_uint32, _vp]),

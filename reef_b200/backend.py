@@ -402,6 +402,42 @@ class MerkleCommitment:
             self.tree.append(flat[off:off + int(sizes[k])])
             off += int(sizes[k])
 
+    @classmethod
+    def build_sharded(cls, ctx: Context, doc_local, n_doc: int, rank: int, world: int, gather, full_tree: bool = False):
+        """Multi-GPU build: this rank holds the contiguous leaves [rank * n_doc / world, ...).
+        Returns (commitment, tree or None); `gather(bytes) -> list[bytes]` is the all-gather."""
+        from .sharding import merkle_sharded
+        d = _u64(doc_local)
+        per = n_doc // world
+        assert len(d) == per
+
+        def build_subtree(a, b):
+            lv = C.create_string_buffer(max(per - 1, 1) * 32)
+            root = C.create_string_buffer(32)
+            check(lib.reef_merkle_subtree(ctx._h, d.ctypes.data, per, a, lv if full_tree else None, root))
+            levels, off, n = [], 0, per // 2
+            while full_tree and n >= 1:
+                levels.append([lv.raw[(off + i) * 32:(off + i + 1) * 32] for i in range(n)])
+                off += n
+                n //= 2
+            return levels, root.raw
+
+        def hash_top(roots):
+            g = len(roots)
+            lv = C.create_string_buffer(max(g - 1, 1) * 32)
+            root = C.create_string_buffer(32)
+            check(lib.reef_merkle_top(ctx._h, b"".join(roots), g, lv, root))
+            levels, off, n = [], 0, g // 2
+            while n >= 1:
+                levels.append([lv.raw[(off + i) * 32:(off + i + 1) * 32] for i in range(n)])
+                off += n
+                n //= 2
+            return levels, root.raw
+
+        root, tree = merkle_sharded(build_subtree, hash_top, n_doc, rank, world, gather, full_tree)
+        tree_int = [[int.from_bytes(x, "little") for x in lvl] for lvl in tree] if tree is not None else None
+        return int.from_bytes(root, "little"), tree_int
+
     def path_wits(self, idx: int):
         nl = self._nl
         lr = np.zeros(nl, dtype=np.uint8)
@@ -484,6 +520,27 @@ class Bases:
         out = C.create_string_buffer(64)
         check(lib.reef_msm_dev(self.ctx._h, self._h, C.c_void_p(dev_ptr), n, out))
         return _pt_from(out.raw)
+
+    def msm_sharded_dev(self, dev_ptr: int, n: int):
+        """Window-sharded MSM across the ranks of the context's mailbox world: partial MSM, 128-byte
+        all-gather over NVLink peer memory and combine in one stream-ordered call; same result on every rank."""
+        out = C.create_string_buffer(64)
+        check(lib.reef_msm_sharded_dev(self.ctx._h, self._h, C.c_void_p(dev_ptr), n, out))
+        return _pt_from(out.raw)
+
+    def commit_rows_sharded(self, matrix: "np.ndarray", rows: int, cols: int, entry_bits: int, blinds, rank: int, world: int, gather):
+        """Hyrax `commit` with the rows split over `world` ranks; returns all `rows` points."""
+        from .sharding import hyrax_commit_sharded
+        m = np.ascontiguousarray(matrix.astype(np.uint32).reshape(rows, cols))
+
+        def mine(r0, r1):
+            out = C.create_string_buffer((r1 - r0) * 64)
+            bl = _buf(_pack(blinds[r0:r1])) if blinds is not None else None
+            a = np.ascontiguousarray(m[r0:r1].reshape(-1))
+            check(lib.reef_msm_rows_u32(self.ctx._h, self._h, a.ctypes.data, r1 - r0, cols, entry_bits, bl, out))
+            return [out.raw[i * 64:(i + 1) * 64] for i in range(r1 - r0)]
+
+        return [_pt_from(p) for p in hyrax_commit_sharded(mine, rows, rank, world, gather)]
 
     def msm_partial_dev(self, dev_ptr: int, n: int, w_begin: int, w_end: int) -> bytes:
         out = C.create_string_buffer(128)

@@ -589,6 +589,52 @@ int reef_merkle_build(reef_ctx* c, const uint64_t* doc, uint64_t n_doc, uint8_t*
   return REEF_OK;
 }
 
+int reef_merkle_subtree(reef_ctx* c, const uint64_t* doc_local, uint64_t n_local, uint64_t idx_offset, uint8_t* out_levels,
+                        uint8_t out_root[32]) {
+  REEF_REQUIRE(c && doc_local && out_root, REEF_EINVAL, "reef_merkle_subtree: NULL argument");
+  REEF_REQUIRE(n_local >= 2 && (n_local & (n_local - 1)) == 0, REEF_EINVAL, "reef_merkle_subtree: n_local must be a power of two >= 2");
+  REEF_REQUIRE(idx_offset % n_local == 0, REEF_EINVAL, "reef_merkle_subtree: idx_offset must be a multiple of n_local");
+  const uint64_t total = n_local - 1;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  void* base;
+  const size_t doc_bytes = ((size_t)n_local * 8 + 255) & ~(size_t)255;
+  int rc = ctx_scratch2(c, doc_bytes + (size_t)total * 32, &base);
+  if (rc) return rc;
+  char* d_levels = (char*)base + doc_bytes;
+  REEF_CUDA(cudaMemcpyAsync(base, doc_local, (size_t)n_local * 8, cudaMemcpyHostToDevice, c->stream));
+  rc = launch_merkle(c, (const uint64_t*)base, n_local, d_levels, nullptr, nullptr, idx_offset);
+  if (rc) return rc;
+  if (out_levels) REEF_CUDA(cudaMemcpyAsync(out_levels, d_levels, (size_t)total * 32, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaMemcpyAsync(out_root, d_levels + (total - 1) * 32, 32, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaStreamSynchronize(c->stream));
+  return REEF_OK;
+}
+
+int reef_merkle_top(reef_ctx* c, const uint8_t* roots, uint32_t g, uint8_t* out_levels, uint8_t out_root[32]) {
+  REEF_REQUIRE(c && roots && out_root, REEF_EINVAL, "reef_merkle_top: NULL argument");
+  REEF_REQUIRE(g >= 1 && (g & (g - 1)) == 0, REEF_EINVAL, "reef_merkle_top: the number of subtrees must be a power of two");
+  int rc = check_canonical(roots, g, "reef_merkle_top");
+  if (rc) return rc;
+  if (g == 1) {
+    memcpy(out_root, roots, 32);
+    return REEF_OK;
+  }
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  void* base;
+  rc = ctx_scratch2(c, (size_t)(2 * g) * 32, &base);
+  if (rc) return rc;
+  char* d_top = (char*)base + (size_t)g * 32;
+  REEF_CUDA(cudaMemcpyAsync(base, roots, (size_t)g * 32, cudaMemcpyHostToDevice, c->stream));
+  rc = launch_merkle_inner(c, base, g, d_top, nullptr, nullptr);
+  if (rc) return rc;
+  if (out_levels) REEF_CUDA(cudaMemcpyAsync(out_levels, d_top, (size_t)(g - 1) * 32, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaMemcpyAsync(out_root, d_top + (size_t)(g - 2) * 32, 32, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaStreamSynchronize(c->stream));
+  return REEF_OK;
+}
+
 int reef_merkle_path_wits(const uint64_t* doc, uint64_t n_doc, const uint8_t* levels, const uint64_t* level_sizes,
                           uint32_t n_levels, uint64_t idx, uint8_t* l_or_r, uint8_t* has_idx, uint64_t* opposite_idx,
                           uint8_t* opposite) {
@@ -1237,6 +1283,41 @@ static int msm_dispatch(reef_ctx* c, const reef_bases* b, const void* d_scalars,
   a.h_extra_xyzz_mont = nullptr;
   a.n_extra = 0;
   return msm_run(c, b->curve, a);
+}
+
+extern "C" int reef_msm_sharded_dev(reef_ctx* c, const reef_bases* b, const void* scalars_dev, uint64_t n, uint8_t out[64]) {
+  REEF_REQUIRE(c && b && out && scalars_dev, REEF_EINVAL, "reef_msm_sharded_dev: NULL argument");
+  REEF_REQUIRE(b->ctx == c, REEF_EINVAL, "reef_msm_sharded_dev: bases belong to another context");
+  REEF_REQUIRE(n >= 1 && n <= b->n, REEF_EASSERT, "reef_msm_sharded_dev: scalar count out of range");
+  REEF_REQUIRE(b->scalar_bits == 255, REEF_EINVAL, "reef_msm_sharded_dev: full-width scalars need generators registered with scalar_bits = 255");
+  REEF_REQUIRE(c->mb_world >= 1, REEF_EINVAL, "reef_msm_sharded_dev: mailbox not connected (reef_mailbox_connect)");
+  REEF_REQUIRE(b->plan.W >= c->mb_world, REEF_EINVAL, "reef_msm_sharded_dev: fewer Pippenger windows than ranks");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  const uint32_t W = b->plan.W, G = c->mb_world, g = c->mb_rank;
+  MsmRunArgs a;
+  a.plan = b->plan;
+  a.d_levels = b->d_levels;
+  a.n_bases = b->n;
+  a.d_scalars = scalars_dev;
+  a.scalars_u32 = 0;
+  a.n = n;
+  a.w_begin = W * g / G;
+  a.w_end = W * (g + 1) / G;
+  a.h_out_affine = out;
+  a.h_out_xyzz = nullptr;
+  a.h_extra_xyzz_mont = nullptr;
+  a.n_extra = 0;
+  a.p2p_combine = 1;
+  int rc = msm_run(c, b->curve, a);
+  if (rc) return rc;
+  uint32_t e = 0;
+  REEF_CUDA(cudaMemcpy(&e, c->mb_err_dev, 4, cudaMemcpyDeviceToHost));
+  if (e) {
+    cudaMemset(c->mb_err_dev, 0, 4);
+    return fail(REEF_ECUDA, "reef_msm_sharded_dev: exchange " + std::to_string(e & 0x7fffffffu) + " failed (a peer never posted, or a peer reported a timeout)");
+  }
+  return REEF_OK;
 }
 
 static int msm_host_scalars(reef_ctx* c, const reef_bases* b, const void* scalars, int is_u32, uint64_t n, uint8_t out[64]) {

@@ -15,7 +15,11 @@ void poseidon_permute_host(Fq* s);
 int poseidon_upload_constants(reef_ctx* c);
 int launch_hash_batch(reef_ctx* c, const void* d_in, int arity, uint64_t n, void* d_out);
 int launch_merkle(reef_ctx* c, const uint64_t* d_doc, uint64_t n_doc, void* d_levels, uint64_t* level_sizes,
-                  uint32_t* n_levels_out);
+                  uint32_t* n_levels_out, uint64_t idx_offset = 0);
+// levels above `d_prev` (n_prev hashed nodes, canonical): ceil(n_prev/2), ... 1 nodes written to d_levels
+int launch_merkle_inner(reef_ctx* c, const void* d_prev, uint64_t n_prev, void* d_levels, uint64_t* level_sizes,
+                        uint32_t* n_levels_out);
+int launch_p2p_allgather(reef_ctx* c, const void* src_dev, uint32_t nwords, void* dst_dev);
 int launch_sponge_run(reef_ctx* c, const uint32_t* d_ops, uint32_t n_ops, const void* d_in, const uint8_t tag_le[32],
                       void* d_out);
 
@@ -85,6 +89,7 @@ struct MsmRunArgs {
   uint8_t* h_out_xyzz;       // 128 B canonical XYZZ or NULL
   const void* h_extra_xyzz_mont;
   uint32_t n_extra;
+  int p2p_combine = 0;       // 1: all-gather the partial over the context's mailboxes and combine on the device
 };
 int msm_run(reef_ctx* c, int curve, const MsmRunArgs& a);
 int msm_combine(reef_ctx* c, int curve, const uint8_t* h_pts, uint32_t k, uint8_t* h_out);

@@ -616,6 +616,7 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
   size_t o_bitpart = take((size_t)P.G * P.c * nblk * sizeof(XYZZ<C>));
   size_t o_res = take(sizeof(XYZZ<C>) + sizeof(Affine<C>));
   size_t o_extra = take((size_t)(a.n_extra + 1) * sizeof(XYZZ<C>));
+  size_t o_gather = take((size_t)(a.p2p_combine ? c->mb_world : 1) * sizeof(XYZZ<C>));
   void* base;
   int rc = ctx_scratch(c, off, &base);
   if (rc) return rc;
@@ -685,11 +686,22 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
   k_bitsum_partial<C><<<dim3(nblk, P.c, P.G), 256, 0, s>>>(buckets, P.B, bpt, bitpart);
   REEF_LAUNCHED();
   if (a.n_extra) REEF_CUDA(cudaMemcpyAsync(extra, a.h_extra_xyzz_mont, (size_t)a.n_extra * sizeof(XYZZ<C>), cudaMemcpyHostToDevice, s));
-  k_bitsum_final<C><<<1, 1024, 0, s>>>(bitpart, nblk, P.c, P.G, P.c * P.L, a.h_out_xyzz ? res_xyzz : nullptr,
-                                       a.h_out_affine ? res_aff : nullptr, extra, a.n_extra);
+  const bool want_xyzz = a.h_out_xyzz || a.p2p_combine;
+  k_bitsum_final<C><<<1, 1024, 0, s>>>(bitpart, nblk, P.c, P.G, P.c * P.L, want_xyzz ? res_xyzz : nullptr,
+                                       (a.h_out_affine && !a.p2p_combine) ? res_aff : nullptr, extra, a.n_extra);
   REEF_LAUNCHED();
   scope.reset();
-  if (a.h_out_xyzz) {
+  if (a.p2p_combine) {
+    // multi-GPU: every rank holds the partial of its own windows; one 128-byte all-gather through the peer
+    // mailboxes (a kernel of this library, P2P stores over NVLink) and the combine, all stream-ordered
+    XYZZ<C>* gathered = (XYZZ<C>*)(d + o_gather);
+    k_xyzz_from_mont<C><<<1, 32, 0, s>>>(res_xyzz);
+    REEF_LAUNCHED();
+    rc = launch_p2p_allgather(c, res_xyzz, (uint32_t)(sizeof(XYZZ<C>) / 4), gathered);
+    if (rc) return rc;
+    k_combine<C><<<1, 32, 0, s>>>(gathered, c->mb_world, res_aff);
+    REEF_LAUNCHED();
+  } else if (a.h_out_xyzz) {
     k_xyzz_from_mont<C><<<1, 32, 0, s>>>(res_xyzz);
     REEF_LAUNCHED();
     REEF_CUDA(cudaMemcpyAsync(a.h_out_xyzz, res_xyzz, sizeof(XYZZ<C>), cudaMemcpyDeviceToHost, s));

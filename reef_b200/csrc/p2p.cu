@@ -10,8 +10,8 @@
 // store of a sequence number, and then acquires the peers' sequence numbers in its own mailbox.
 // No host round trip, no NCCL kernel: the exchange is one stream-ordered launch.
 //
-// Mailbox layout: [2 slots][world] entries of 128 bytes: payload (<= 120 B) + sequence number at
-// byte 120.  Two slots suffice: a rank can be at most one exchange ahead of any peer (it cannot
+// Mailbox layout: [2 slots][world] entries of 256 bytes: payload (<= 248 B) + sequence number at
+// byte 248.  Two slots suffice: a rank can be at most one exchange ahead of any peer (it cannot
 // finish exchange k+1 before every peer has posted k+1, which a peer does only after it has
 // consumed exchange k).
 #include <cstring>
@@ -31,6 +31,19 @@ __global__ void __launch_bounds__(32) k_p2p_allgather(MbRef mb, const uint32_t* 
   mb_wait_copy(mb, t, dst + (size_t)t * nwords, nwords);
 }
 
+}  // namespace reef
+
+namespace reef {
+// stream-ordered all-gather of `nwords` 32-bit words per rank through the mailboxes (context lock held by the caller)
+int launch_p2p_allgather(reef_ctx* c, const void* src_dev, uint32_t nwords, void* dst_dev) {
+  REEF_REQUIRE(c->mb_world >= 1, REEF_EINVAL, "p2p all-gather: mailbox not connected (reef_mailbox_connect)");
+  REEF_REQUIRE(nwords >= 1 && nwords * 4 <= MB_SEQ_OFF, REEF_EINVAL, "p2p all-gather: payload must be 4..248 bytes");
+  MbRef mb{c->mb_peers_dev, (const unsigned char*)c->mb_mine, c->mb_err_dev, c->mb_world, c->mb_rank, c->mb_seq + 1};
+  k_p2p_allgather<<<1, 32, 0, c->stream>>>(mb, (const uint32_t*)src_dev, nwords, (uint32_t*)dst_dev);
+  REEF_LAUNCHED();
+  c->mb_seq++;
+  return REEF_OK;
+}
 }  // namespace reef
 
 using namespace reef;
@@ -117,13 +130,10 @@ int reef_mailbox_connect_local(reef_ctx* c, uint32_t rank, uint32_t world, void*
 int reef_p2p_allgather(reef_ctx* c, const void* mine_dev, uint32_t nbytes, void* out_dev) {
   REEF_REQUIRE(c && mine_dev && out_dev, REEF_EINVAL, "reef_p2p_allgather: NULL argument");
   REEF_REQUIRE(c->mb_world >= 1, REEF_EINVAL, "reef_p2p_allgather: mailbox not connected");
-  REEF_REQUIRE(nbytes >= 4 && nbytes <= MB_SEQ_OFF && (nbytes & 3) == 0, REEF_EINVAL, "reef_p2p_allgather: payload must be 4..120 bytes, a multiple of 4");
+  REEF_REQUIRE(nbytes >= 4 && nbytes <= MB_SEQ_OFF && (nbytes & 3) == 0, REEF_EINVAL, "reef_p2p_allgather: payload must be 4..248 bytes, a multiple of 4");
   std::lock_guard<std::mutex> lk(c->mu);
   REEF_CUDA(cudaSetDevice(c->device));
-  MbRef mb{c->mb_peers_dev, (const unsigned char*)c->mb_mine, c->mb_err_dev, c->mb_world, c->mb_rank, ++c->mb_seq};
-  k_p2p_allgather<<<1, 32, 0, c->stream>>>(mb, (const uint32_t*)mine_dev, nbytes / 4, (uint32_t*)out_dev);
-  REEF_LAUNCHED();
-  return REEF_OK;
+  return launch_p2p_allgather(c, mine_dev, nbytes / 4, out_dev);
 }
 
 int reef_p2p_status(reef_ctx* c) {

@@ -6,8 +6,8 @@
 
 namespace reef {
 
-static constexpr uint32_t MB_ENTRY = 128;
-static constexpr uint32_t MB_SEQ_OFF = 120;
+static constexpr uint32_t MB_ENTRY = 256;
+static constexpr uint32_t MB_SEQ_OFF = 248;   // payload <= 248 B (a partial MSM point in XYZZ coordinates is 128 B)
 static constexpr uint32_t MB_MAX_WORLD = 32;
 static constexpr uint32_t MB_SPIN_LIMIT = 1u << 25;   // ~30 s of polling (host-side skew between ranks is legal)
 

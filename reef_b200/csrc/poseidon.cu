@@ -263,16 +263,17 @@ __global__ void __launch_bounds__(64) k_hash_batch_pair(const Fq* __restrict__ i
 
 // leaf level: parent k = H4(2k, doc[2k], 2k+1, doc[2k+1]); missing right => (.., 0, 0)
 __global__ void __launch_bounds__(128) k_merkle_leaves(const uint64_t* __restrict__ doc, uint64_t n_doc, Fq tag4,
-                                                       const PoseidonTables* __restrict__ K, Fq* __restrict__ out) {
+                                                       const PoseidonTables* __restrict__ K, Fq* __restrict__ out,
+                                                       uint64_t idx_offset) {
   uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t n_out = (n_doc + 1) / 2;
   if (k >= n_out) return;
   Fq s[5];
   s[0] = tag4;
-  s[1] = fe_from_u64<FqCfg>(2 * k);
+  s[1] = fe_from_u64<FqCfg>(idx_offset + 2 * k);
   s[2] = fe_from_u64<FqCfg>(doc[2 * k]);
   bool has_r = 2 * k + 1 < n_doc;
-  s[3] = has_r ? fe_from_u64<FqCfg>(2 * k + 1) : fe_zero<FqCfg>();
+  s[3] = has_r ? fe_from_u64<FqCfg>(idx_offset + 2 * k + 1) : fe_zero<FqCfg>();
   s[4] = has_r ? fe_from_u64<FqCfg>(doc[2 * k + 1]) : fe_zero<FqCfg>();
   poseidon_permute(s, *K);
   st256(out + k, from_mont<FqCfg>(s[1]));
@@ -409,20 +410,30 @@ int launch_hash_batch(reef_ctx* c, const void* d_in, int arity, uint64_t n, void
 
 // d_levels: concatenated levels, leaf-parents first; sizes ceil(n/2), ceil(ceil(n/2)/2), ... 1
 int launch_merkle(reef_ctx* c, const uint64_t* d_doc, uint64_t n_doc, void* d_levels, uint64_t* level_sizes,
-                  uint32_t* n_levels_out) {
+                  uint32_t* n_levels_out, uint64_t idx_offset) {
   REEF_REQUIRE(n_doc >= 1, REEF_EINVAL, "merkle: empty document");
   Fq* lv = (Fq*)d_levels;
   uint64_t n_out = (n_doc + 1) / 2;
-  uint32_t nl = 0;
   ProfScope ps(c, PROF_POSEIDON, n_doc);
-  k_merkle_leaves<<<(unsigned)((n_out + 127) / 128), 128, 0, c->stream>>>(d_doc, n_doc, c->tags.a4s1, c->d_pos, lv);
+  k_merkle_leaves<<<(unsigned)((n_out + 127) / 128), 128, 0, c->stream>>>(d_doc, n_doc, c->tags.a4s1, c->d_pos, lv, idx_offset);
   REEF_LAUNCHED();
-  if (level_sizes) level_sizes[nl] = n_out;
-  nl++;
-  Fq* prev = lv;
-  uint64_t n_prev = n_out;
+  if (level_sizes) level_sizes[0] = n_out;
+  uint32_t nl_in = 0;
+  int rc = launch_merkle_inner(c, lv, n_out, lv + n_out, level_sizes ? level_sizes + 1 : nullptr, &nl_in);
+  if (rc) return rc;
+  if (n_levels_out) *n_levels_out = nl_in + 1;
+  return REEF_OK;
+}
+
+int launch_merkle_inner(reef_ctx* c, const void* d_prev, uint64_t n_prev_in, void* d_levels, uint64_t* level_sizes,
+                        uint32_t* n_levels_out) {
+  uint32_t nl = 0;
+  const Fq* prev = (const Fq*)d_prev;
+  Fq* next_out = (Fq*)d_levels;
+  uint64_t n_prev = n_prev_in;
+  uint64_t n_out;
   while (n_prev > 1) {
-    Fq* cur = prev + n_prev;
+    Fq* cur = next_out;
     n_out = (n_prev + 1) / 2;
     // thread-per-hash while the level still fills the machine, warp-per-hash for the top
     if (n_out >= (uint64_t)c->sm_count * 256) {
@@ -435,6 +446,7 @@ int launch_merkle(reef_ctx* c, const uint64_t* d_doc, uint64_t n_doc, void* d_le
     if (level_sizes) level_sizes[nl] = n_out;
     nl++;
     prev = cur;
+    next_out = cur + n_out;
     n_prev = n_out;
   }
   if (n_levels_out) *n_levels_out = nl;

@@ -93,6 +93,7 @@ struct MsmRunArgs {
 };
 int msm_run(reef_ctx* c, int curve, const MsmRunArgs& a);
 int msm_combine(reef_ctx* c, int curve, const uint8_t* h_pts, uint32_t k, uint8_t* h_out);
+int msm_preload();
 struct MsmRowsArgs {
   MsmPlanPublic plan;
   const void* d_levels;

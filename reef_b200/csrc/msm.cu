@@ -616,7 +616,7 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
   size_t o_bitpart = take((size_t)P.G * P.c * nblk * sizeof(XYZZ<C>));
   size_t o_res = take(sizeof(XYZZ<C>) + sizeof(Affine<C>));
   size_t o_extra = take((size_t)(a.n_extra + 1) * sizeof(XYZZ<C>));
-  size_t o_gather = take((size_t)(a.p2p_combine ? c->mb_world : 1) * sizeof(XYZZ<C>));
+  size_t o_gather = take((size_t)32 * sizeof(XYZZ<C>));   // MB_MAX_WORLD partials: the same scratch size with and without the exchange
   void* base;
   int rc = ctx_scratch(c, off, &base);
   if (rc) return rc;
@@ -837,6 +837,25 @@ static int msm_combine_t(reef_ctx* c, const uint8_t* h_pts, uint32_t k, uint8_t*
   REEF_CUDA(cudaMemcpyAsync(h_out, d_out, 64, cudaMemcpyDeviceToHost, s));
   REEF_CUDA(cudaStreamSynchronize(s));
   return REEF_OK;
+}
+
+// Forces the lazily loaded MSM kernels into the device (see nl_shard_preload: loading a kernel synchronises
+// with running work, which must not happen while an exchange kernel is waiting for a peer).
+template <class C>
+static int msm_preload_t() {
+  cudaFuncAttributes a;
+  const void* fns[] = {(const void*)k_accum_first<C>, (const void*)k_accum_next<C, 4>, (const void*)k_accum_next<C, 32>,
+                       (const void*)k_gather_buckets<C>, (const void*)k_bitsum_partial<C>, (const void*)k_bitsum_final<C>,
+                       (const void*)k_combine<C>, (const void*)k_xyzz_from_mont<C>};
+  for (const void* f : fns) REEF_CUDA(cudaFuncGetAttributes(&a, f));
+  return REEF_OK;
+}
+int msm_preload() {
+  cudaFuncAttributes a;
+  const void* fns[] = {(const void*)k_digits<true>, (const void*)k_digits<false>, (const void*)k_hist, (const void*)k_scan, (const void*)k_scatter};
+  for (const void* f : fns) REEF_CUDA(cudaFuncGetAttributes(&a, f));
+  int rc = msm_preload_t<FpCfg>();
+  return rc ? rc : msm_preload_t<FqCfg>();
 }
 
 int msm_combine(reef_ctx* c, int curve, const uint8_t* h_pts, uint32_t k, uint8_t* h_out) {

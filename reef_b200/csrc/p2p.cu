@@ -67,6 +67,8 @@ static int mailbox_set_peers(reef_ctx* c, uint32_t rank, uint32_t world, void* c
   REEF_CUDA(cudaFuncGetAttributes(&fa, (const void*)k_p2p_allgather));   // load it now, see nl_shard_preload
   int rc = nl_shard_preload();
   if (rc) return rc;
+  rc = msm_preload();
+  if (rc) return rc;
   REEF_CUDA(cudaMemset(c->mb_err_dev, 0, 256));   // a fresh connection starts without a recorded failure
   c->mb_world = world;
   c->mb_rank = rank;

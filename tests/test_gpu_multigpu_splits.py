@@ -25,7 +25,10 @@ def _world(world):
     return ctxs
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
+# world <= 4 here: with all ranks on ONE device their streams share its 8 hardware work queues
+# (CUDA_DEVICE_MAX_CONNECTIONS), and a rank queued behind a peer's waiting exchange kernel can never post;
+# on a real box every rank has its own device (bench.py --gpus 8 runs this path on 8 GPUs)
+@pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("curve,n", [("pallas", 1 << 10), ("vesta", 3000)])
 def test_msm_window_sharded_with_mailbox_gather(world, curve, n):
     import torch
@@ -38,7 +41,9 @@ def test_msm_window_sharded_with_mailbox_gather(world, curve, n):
     bases = []
     try:
         bases = [c.bases(curve, gens) for c in ctxs]
-        whole = bases[0].msm(sc)                      # un-sharded on one context
+        # un-sharded on every context first: the reference result, and on ONE GPU it also sizes each context's
+        # scratch up front (a cudaMalloc while a peer's exchange kernel spins would dead-lock this device)
+        whole = [b.msm(sc) for b in bases][0]
         dev = torch.from_numpy(raw.copy()).cuda()
         torch.cuda.synchronize()
         with ThreadPoolExecutor(max_workers=world) as ex:      # every rank's call waits for its peers' partials

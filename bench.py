@@ -1,28 +1,32 @@
 #!/usr/bin/env python3
 """bench.py -- Reef prover hot path on B200 (see DESIGN.md "Measurement").
 
-  python bench.py --gpus N --steps K --warmup W [--workload cfg2] [--impl reef|reference]
+  python bench.py --gpus N --steps K --warmup W [--workload target] [--impl reef|reference]
 
-A "step" is ONE PASS OF THE PROVER HOT PATH over one synthetic document: for each Nova fold of
-the `--prove` run the reference would do (framework.rs:405-625 / 642-754):
-    nlookup sum-check over the transition table T      ("nl",    r1cs.rs:2088-2100)
-    nlookup sum-check over the committed document      ("nldoc", r1cs.rs:2137-2161)
-    2 x calc_d                                         (framework.rs:517-553)
-    prove_step commitments: commit(W), commit(T) on Pallas and on Vesta (framework.rs:668-675)
+A "step" is ONE PASS OF THE PROVER HOT PATH over one synthetic document: for each Nova fold of the
+`--prove` run the reference would do (framework.rs:405-625 / 642-754), by mode of the workload:
+    nldoc   nl sum-check over T ("nl", r1cs.rs:2137-2161) + nldoc sum-check over the committed document,
+            calc_d of the previous and the next document claim (framework.rs:517-526)
+    hybrid  ONE nlhybrid sum-check over the merged table T ++ document (r1cs.rs:2101-2136), 2 calc_d
+    merkle  nl sum-check over T + Merkle path witnesses of the document lookups (r1cs.rs:2088-2100,
+            merkle_tree.rs:116-192)
+  and the prove_step commitments commit(W), commit(T) on Pallas and on Vesta (framework.rs:668-675).
 metric  = NFA steps/s proved = doc_len / time of one pass        (BASELINE.json)
-workload = `target` by default: configs[1] at the 2^20-char document the north_star target names;
-          configs[1] at its own 2^16 chars is timed in the same run and reported under "also"
+workload = `target` by default: configs[1] at the 2^20-char document the north_star target names; the
+          other BASELINE configs (cfg2..cfg5) are timed in the same run and reported under "also",
+          each with its commit phase (Hyrax rows / Merkle tree), each verified against the oracle
 value   = inputs resident in HBM when the timed region starts    (device timed, CUDA events)
 e2e     = the same pass through the C ABI with HOST buffers: document/table upload, scalar
           upload and result read-back inside the timed region
 --impl reference = the CPU restatement of the reference's algorithm (oracle/c, all host cores).
 
-Multi-GPU (torchrun), weak scaling: ONE document of base_len * G characters.  Its sum-check is
-sharded by low index bits; the 96 bytes per rank per round are exchanged by the round kernels
-themselves through peer mailboxes over NVLink (P2P stores + system-scope release/acquire; no NCCL
-call on that path), every rank runs the same transcript.  The fold commitments (latency-bound at 2^14..2^15 terms) are distributed whole,
-round-robin over the ranks; MSMs large enough to be throughput-bound are sharded by Pippenger
-windows (one 128-byte all-gather per MSM).
+Multi-GPU (torchrun), weak scaling: ONE document of base_len * G characters.  Its sum-check is sharded by
+low index bits; the 96 bytes per rank per round are exchanged by the round kernels themselves through
+peer mailboxes over NVLink (P2P stores + system-scope release/acquire; no NCCL call on that path), every
+rank runs the same transcript.  The fold commitments (latency-bound at 2^14..2^15 terms) are distributed
+whole, round-robin over the ranks.  The line also carries, measured on the same ranks: the same document
+on ONE GPU (`same_doc_1gpu`), a 2^20-term MSM sharded by Pippenger windows with its 128-byte all-gather
+done by a kernel of the library (`msm_sharded`), and the commit phase split over the ranks (`commit`).
 """
 from __future__ import annotations
 
@@ -42,37 +46,41 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FQ = 0x40000000000000000000000000000000224698FC0994A8DD8C46EB2100000001
-FP = 0x40000000000000000000000000000000224698FC094CF91B992D30ED00000001
-
-WORKLOADS = {
-    # name: doc_len, alphabet, nova steps, lookups per step, log2 |T|, primary / secondary MSM sizes
-    # "target" = the configuration BASELINE.json's north_star quotes the metric on ("a 2^20-char ascii
-    # document / '.*b' at 1 GPU"; BASELINE.md: "cfg-2-style .*b at 2^20 chars"): configs[1] with the
-    # document length of the target.  configs[1] itself (2^16 chars) is "cfg2" and is reported beside it.
-    "target": dict(doc_len=1 << 20, ab="ascii", steps=2, m=2, t_log=6, n_pri=1 << 15, n_sec=1 << 14,
-                   desc="north_star target = configs[1] at 2^20 chars: ascii doc (2^20-1 x 'a' + 'b'), re '.*b', --prove: "
-                        "per Nova fold nl(T=2^6) + nldoc(N=2^21,u32) sum-checks, 2 calc_d, commit(W),commit(T) on "
-                        "Pallas(2^15) and Vesta(2^14); 2 folds"),
-    "cfg2": dict(doc_len=1 << 16, ab="ascii", steps=2, m=2, t_log=6, n_pri=1 << 15, n_sec=1 << 14,
-                 desc="ascii 2^16-char doc (65535 x 'a' + 'b'), re '.*b', --prove: per Nova fold "
-                      "nl(T=2^6) + nldoc(N=2^17,u32) sum-checks, 2 calc_d, commit(W),commit(T) on "
-                      "Pallas(2^15) and Vesta(2^14); 2 folds"),
-    "cfg4": dict(doc_len=1 << 20, ab="ascii", doc="cfg4", steps=2, m=4, t_log=8, n_pri=1 << 16, n_sec=1 << 14,
-                 desc="ascii 2^20-char doc, per fold nl(T=2^8) + nldoc(N=2^21,u32), 2 calc_d, 4 MSMs; 2 folds"),
-    "cfg5": dict(doc_len=1 << 22, ab="ascii", doc="cfg4", steps=1, m=4, t_log=8, n_pri=1 << 16, n_sec=1 << 14,
-                 desc="2^22-char doc, nl(T=2^8) + nldoc(N=2^23,u32), 2 calc_d, 4 MSMs; 1 fold"),
-}
-
-
 import workloads as WL                                  # numpy-only input generators shared by both arms and the tests
 
+FQ, FP = WL.FQ, WL.FP
 ASCII_AB = "".join(chr(c) for c in range(128))        # config.rs: the `ascii` alphabet
 curve_multiples = WL.curve_multiples
 
+# name: document, length, mode, Nova folds, lookups per fold, log2 |T|, primary / secondary MSM sizes, entry bits
+# of the document codes.  Fold / lookup counts and circuit sizes are SYNTHETIC (the frontend and CirC that
+# would fix them are out of scope); they are stated in `desc`.
+WORKLOADS = {
+    "target": dict(doc="target", doc_len=1 << 20, mode="nldoc", steps=2, m=2, t_log=6, n_pri=1 << 15, n_sec=1 << 14, bits=8,
+                   desc="north_star target = configs[1] at 2^20 chars: ascii doc (2^20-1 x 'a' + 'b'), re '.*b', --prove: "
+                        "per Nova fold nl(T=2^6) + nldoc(N=2^21,u32) sum-checks, 2 calc_d, commit(W),commit(T) on "
+                        "Pallas(2^15) and Vesta(2^14); 2 folds"),
+    "cfg2": dict(doc="cfg2", doc_len=1 << 16, mode="nldoc", steps=2, m=2, t_log=6, n_pri=1 << 15, n_sec=1 << 14, bits=8,
+                 desc="configs[1]: ascii 2^16-char doc (65535 x 'a' + 'b'), re '.*b', --prove: per Nova fold "
+                      "nl(T=2^6) + nldoc(N=2^17,u32) sum-checks, 2 calc_d, commit(W),commit(T) on "
+                      "Pallas(2^15) and Vesta(2^14); 2 folds"),
+    "cfg3": dict(doc="cfg3", doc_len=1 << 20, mode="merkle", steps=3, m=4, t_log=8, n_pri=1 << 16, n_sec=1 << 14, bits=8,
+                 desc="configs[2]: dna 2^20-char doc, re '(A|C|G|T){4}TATA.*', --merkle --prove: per Nova fold nl(T=2^8) sum-check + "
+                      "4 Merkle path witnesses (21 levels), commit(W),commit(T) on Pallas(2^16) and Vesta(2^14); 3 folds; "
+                      "commit phase = Poseidon tree over 2^21 leaves"),
+    "cfg4": dict(doc="cfg4", doc_len=1 << 20, mode="hybrid", steps=2, m=4, t_log=9, n_pri=1 << 16, n_sec=1 << 14, bits=8,
+                 desc="configs[3]: ascii 2^20-char doc, re 'hello.*world', --hybrid --projections (projection resolves to None): per "
+                      "Nova fold ONE nlhybrid sum-check over the merged 2^22 table (T=2^9 padded to 2^21 ++ document), 2 calc_d, "
+                      "commit(W),commit(T) on Pallas(2^16) and Vesta(2^14); 2 folds; commit phase = Hyrax 1024 x 2048"),
+    "cfg5": dict(doc="cfg5", doc_len=1 << 22, mode="nldoc", steps=1, m=4, t_log=8, n_pri=1 << 16, n_sec=1 << 14, bits=21,
+                 desc="configs[4]: utf8 2^22-char doc (code points up to 0x2FFF, EOF/EPSILON codes 21 bits), re '.*(foo|bar|baz).*', "
+                      "--prove: nl(T=2^8) + nldoc(N=2^23,u32) sum-checks, 2 calc_d, commit(W),commit(T) on Pallas(2^16) and "
+                      "Vesta(2^14); 1 fold; commit phase = Hyrax 2048 x 4096"),
+}
+
 
 class ParityError(AssertionError):
-    """The multi-GPU path produced a result that differs from the single-GPU path."""
+    """The GPU path produced a result that differs from the oracle."""
 
 
 def le32(x: int) -> bytes:
@@ -89,6 +97,7 @@ def pack(xs) -> bytes:
 def make_workload(name: str, seed_shift: int = 0, world: int = 1):
     """Inputs of one pass; no import of reef_b200 or oracle/ (both arms call this)."""
     w = dict(WORKLOADS[name])
+    w["name"] = name
     rnd = random.Random(1234 + seed_shift)
     # weak scaling: one document of base_len * G characters.  The reference's f32 `logmn` (costs.rs:10-15)
     # mis-rounds 2^22+2 and 2^23+2, so its doc_transform panics on documents of exactly 2^22 / 2^23
@@ -96,18 +105,27 @@ def make_workload(name: str, seed_shift: int = 0, world: int = 1):
     # table (2^21 entries per GPU) is unchanged.
     w["doc_len"] = WL.safe_len(w["doc_len"] * world)
     doc_len = w["doc_len"]
-    ab, cps = WL.document(w.get("doc", name), doc_len, seed_shift)
+    ab, cps = WL.document(w["doc"], doc_len, seed_shift)
     w["udoc"] = np.ascontiguousarray(WL.encode(ab, cps))
     tl = w["t_log"]
-    w["T"] = sorted(rnd.randrange(1 << 40) for _ in range(1 << tl))
+    w["T"] = sorted(rnd.randrange(1 << 100) for _ in range(1 << tl))
     w["T_bytes"] = pack(w["T"])
+    w["fill"] = rnd.randrange(1 << 100)                       # calc_fill value of the padded T (r1cs.rs:363-388)
     S, m = w["steps"], w["m"]
-    w["q_nl"] = [[rnd.randrange(1 << tl) for _ in range(m)] for _ in range(S)]
-    w["q_doc"] = [[rnd.randrange(doc_len + 2) for _ in range(m)] for _ in range(S)]
+    n_doc_tab = len(w["udoc"])
+    if w["mode"] == "hybrid":
+        # hybrid_q = q ++ (doc_q + half_len) (r1cs.rs:2114-2117): m/2 lookups into T, m/2 into the document
+        half = max(n_doc_tab, 1 << tl)
+        w["half"] = half
+        w["q_hyb"] = [[rnd.randrange(1 << tl) for _ in range(m // 2)] + [half + rnd.randrange(doc_len + 2) for _ in range(m - m // 2)]
+                      for _ in range(S)]
+    else:
+        w["q_nl"] = [[rnd.randrange(1 << tl) for _ in range(m)] for _ in range(S)]
+        w["q_doc"] = [[rnd.randrange(doc_len + 2) for _ in range(m)] for _ in range(S)]
     w["doc_hash"] = rnd.randrange(FQ)
     w["salt"] = rnd.randrange(FQ)
 
-    def scalars(n, order, witness_like):
+    def scalars(n, witness_like):
         rs = np.random.default_rng(rnd.randrange(1 << 30))
         raw = rs.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
         raw[:, 3] &= (1 << 61) - 1                                    # < 2^253 < both group orders
@@ -119,12 +137,25 @@ def make_workload(name: str, seed_shift: int = 0, world: int = 1):
             raw[small & bits, 0] &= 1
         return np.ascontiguousarray(raw)
 
-    # generators k*G: distinct, cheap, and the expected MSM result is checkable
     w["bases_pri"] = WL.generators("pallas", w["n_pri"])     # Pallas: over Fp  (disk-cached k*G, build/gens/)
     w["bases_sec"] = WL.generators("vesta", w["n_sec"])      # Vesta: over Fq
-    w["sc"] = [dict(Wp=scalars(w["n_pri"], FQ, True), Tp=scalars(w["n_pri"], FQ, False),
-                    Ws=scalars(w["n_sec"], FP, True), Ts=scalars(w["n_sec"], FP, False)) for _ in range(S)]
+    w["sc"] = [dict(Wp=scalars(w["n_pri"], True), Tp=scalars(w["n_pri"], False),
+                    Ws=scalars(w["n_sec"], True), Ts=scalars(w["n_sec"], False)) for _ in range(S)]
     return w
+
+
+def hybrid_value(w, i):
+    """entry i of the merged table (r1cs.rs:2105-2112)"""
+    half, nT = w["half"], len(w["T"])
+    if i < half:
+        return w["T"][i] if i < nT else w["fill"]
+    return int(w["udoc"][(i - half) % len(w["udoc"])])
+
+
+def wit_bytes(path):
+    """one MerkleWit list (merkle_tree.rs:128-191) as bytes for the comparison"""
+    return b"".join((1 if lr else 0).to_bytes(1, "little") + (2 ** 64 - 1 if oi is None else int(oi)).to_bytes(8, "little") + le32(opp)
+                    for lr, oi, opp in path)
 
 
 # --------------------------------------------------------------------------------------------
@@ -133,36 +164,33 @@ def make_workload(name: str, seed_shift: int = 0, world: int = 1):
 class GpuPass:
     """One prove pass through libreef_b200 with raw buffers (no Python big-int work inside)."""
 
+    collect = None
+
     def __init__(self, ctxs, w, rank=0, world=1, dist=None):
-        """ctxs: dict of libreef_b200 contexts (one CUDA stream each): 'nl', 'doc', 'pri', 'sec'.
-        The reference runs the sum-checks on its solver thread and the fold commitments on its
-        proving thread (framework.rs:98-110); here each of the independent chains of a
-        fold has its own context/stream and host thread."""
+        """ctxs: dict of libreef_b200 contexts (one CUDA stream each).  The reference runs the sum-checks on its
+        solver thread and the fold commitments on its proving thread (framework.rs:98-110); here each of the
+        independent chains of a fold has its own context/stream and host thread."""
         import reef_b200
         import torch
         from concurrent.futures import ThreadPoolExecutor
         self.rb, self.torch, self.ctxs, self.w = reef_b200, torch, ctxs, w
-        self.ctx = ctxs["doc"]
         self.lib, self.check = reef_b200.lib, reef_b200._lib.check
         self.rank, self.world, self.dist = rank, world, dist
-        self.bases_pri = reef_b200.Bases(ctxs["pri"], "pallas", w["bases_pri"])
-        self.bases_sec = reef_b200.Bases(ctxs["sec"], "vesta", w["bases_sec"])
-        # commit(T) gets its own context (generators registered there too): it only waits for the
-        # cross-term scalars, not for commit(W), so the two commitments of a curve overlap
-        self.bases_pri2 = reef_b200.Bases(ctxs["pri2"], "pallas", w["bases_pri"])
-        self.bases_sec2 = reef_b200.Bases(ctxs["sec2"], "vesta", w["bases_sec"])
+        self.mode = w["mode"]
+        # generators are static per PublicParams: registered once per context that commits with them (commit(T)
+        # has its own context so that it does not queue behind commit(W) of the same curve)
+        self.bases = {"Wp": reef_b200.Bases(ctxs["pri"], "pallas", w["bases_pri"]), "Ws": reef_b200.Bases(ctxs["sec"], "vesta", w["bases_sec"]),
+                      "Tp": reef_b200.Bases(ctxs["pri2"], "pallas", w["bases_pri"]), "Ts": reef_b200.Bases(ctxs["sec2"], "vesta", w["bases_sec"])}
         self.ell_doc = reef_b200.logmn(len(w["udoc"]))
         self.ell_T = w["t_log"]
         self.pool = {k: ThreadPoolExecutor(max_workers=1) for k in ctxs}
-        # e2e leg: every host buffer that crosses PCIe inside the timed region is page-locked
         self._pins = []
         self.h_doc = self._pin(self._doc_shard())
         self.h_T = self._pin(np.frombuffer(w["T_bytes"], dtype=np.uint8))
         for s in w["sc"]:
             for k in list(s):
                 s[k] = self._pin(s[k])
-        # the MSM thread and the sum-check thread issue collectives concurrently: one communicator each
-        self.msm_group = dist.new_group() if world > 1 else None
+        self.tree = None
         self._mk_out()
 
     def _pin(self, arr):
@@ -173,22 +201,28 @@ class GpuPass:
     def _mk_out(self):
         from reef_b200._lib import NlookupOut
         self.o, self.bufs = {}, {}
-        for key, ell in (("nl", self.ell_T), ("nldoc", self.ell_doc)):
+        for key, ell in (("nl", self.ell_T), ("nldoc", self.ell_doc), ("nlhybrid", self.ell_doc + 1)):
             b = dict(prev=C.create_string_buffer(32), cq=C.create_string_buffer(64 * 32), claim=C.create_string_buffer(32),
-                     rounds=C.create_string_buffer(ell * 128), last=C.create_string_buffer(32), nxt=C.create_string_buffer(32))
+                     rounds=C.create_string_buffer((ell + 2) * 128), last=C.create_string_buffer(32), nxt=C.create_string_buffer(32))
             o = NlookupOut()
             o.prev_running_claim = C.addressof(b["prev"]); o.combined_q = C.addressof(b["cq"]); o.combined_q_cap = 64
-            o.claim_r = C.addressof(b["claim"]); o.rounds = C.addressof(b["rounds"]); o.rounds_cap = ell
+            o.claim_r = C.addressof(b["claim"]); o.rounds = C.addressof(b["rounds"]); o.rounds_cap = ell + 2
             o.sc_last_claim = C.addressof(b["last"]); o.next_running_claim = C.addressof(b["nxt"])
             self.o[key], self.bufs[key] = o, b
 
     # -- residency ----------------------------------------------------------------------
     def make_resident(self):
         w, t = self.w, self.torch
-        self.doc_tab = self.ctxs["doc"].table_u32(self._doc_shard())
-        self.T_tab = self.rb.Table(self.ctxs["nl"], values=w["T"])
+        if self.mode == "hybrid":
+            self.hyb_tab = self.ctxs["doc"].table_hybrid(w["T_bytes"], w["fill"], w["half"], w["udoc"])
+        elif self.mode == "nldoc":
+            self.doc_tab = self.ctxs["doc"].table_u32(self._doc_shard())
+        if self.mode != "hybrid":
+            self.T_tab = self.rb.Table(self.ctxs["nl"], values=w["T"])
+        if self.mode == "merkle":
+            # the tree is the product of --commit (read back from the .cmt by --prove, main.rs:48-51): built once
+            self.tree = self.ctxs["doc"].merkle(w["udoc"])
         if self.world > 1:
-            self.gbuf = t.zeros((self.world + 1) * 96, dtype=t.uint8, device="cuda")
             self._connect_mailboxes()
         self.sc_dev = [{k: t.from_numpy(v.view(np.int64)).cuda() for k, v in s.items()} for s in w["sc"]]
         t.cuda.synchronize()
@@ -197,20 +231,43 @@ class GpuPass:
         return np.ascontiguousarray(self.w["udoc"][self.rank::self.world]) if self.world > 1 else self.w["udoc"]
 
     def _connect_mailboxes(self):
-        """Per-round exchange of the sharded sum-check over NVLink peer memory (reef_b200/csrc/p2p.cu):
-        every rank maps every peer's mailbox with CUDA IPC once; NCCL only carries the 64-byte handles."""
+        """Exchanges over NVLink peer memory (reef_b200/csrc/p2p.cu): every rank maps every peer's mailbox with
+        CUDA IPC once; NCCL only carries the 64-byte handles.  One mailbox per context that exchanges."""
         t = self.torch
-        ctx = self.ctxs["doc"]
-        mine = t.frombuffer(bytearray(ctx.mailbox_create(self.world)), dtype=t.uint8).cuda()
-        allh = t.empty(self.world * 64, dtype=t.uint8, device="cuda")
-        self.dist.all_gather_into_tensor(allh, mine)
-        ctx.mailbox_connect(self.rank, self.world, bytes(allh.cpu().numpy().tobytes()))
+        for key in ("doc", "pri"):
+            ctx = self.ctxs[key]
+            mine = t.frombuffer(bytearray(ctx.mailbox_create(self.world)), dtype=t.uint8).cuda()
+            allh = t.empty(self.world * 64, dtype=t.uint8, device="cuda")
+            self.dist.all_gather_into_tensor(allh, mine)
+            ctx.mailbox_connect(self.rank, self.world, bytes(allh.cpu().numpy().tobytes()))
         self.dist.barrier()
 
-    def _gather(self, mine_ptr, nbytes, out_ptr):
-        """all-gather of `nbytes` per rank: one stream-ordered kernel of the library (P2P stores into the
-        peers' mailboxes + system-scope release/acquire), no NCCL call and no host wait"""
-        self.ctxs["doc"].p2p_allgather(mine_ptr, nbytes, out_ptr)
+    # -- pieces of a fold ------------------------------------------------------------------
+    def _calc_d(self, v):
+        d = C.create_string_buffer(32)
+        self.check(self.lib.reef_calc_d(self.ctxs["aux"]._h, v, self.salt, d))
+        return d.raw
+
+    def _nlookup(self, key, tab, q_arr, v_bytes, prev, first_v):
+        o, b = self.o[key], self.bufs[key]
+        tag = {"nl": 0, "nldoc": 1, "nlhybrid": 2}[key]
+        pq = prev[0] if prev else None
+        pv = prev[1] if prev else None
+        ctx = self.ctxs["nl" if key == "nl" else "doc"]
+        self.check(self.lib.reef_nlookup_prove(ctx._h, tag, tab._h, q_arr.ctypes.data, v_bytes, len(q_arr), pq, pv,
+                                              self.dh if tag else None, C.byref(o)))
+        ell = o.ell
+        rounds = b["rounds"].raw
+        next_q = b"".join(rounds[i * 128:i * 128 + 32] for i in range(ell))
+        nxt = b["nxt"].raw
+        if key != "nl":
+            # calc_d of the previous and of the next running claim (framework.rs:517-553): inputs of the step
+            # circuit only, the next fold's sum-check does not wait for them
+            self.d_futs.append(self.pool["aux"].submit(self._calc_d, pv if prev else first_v))
+            self.d_futs.append(self.pool["aux"].submit(self._calc_d, nxt))
+        if self.collect is not None:
+            self.collect.append((key, b["claim"].raw, rounds[:ell * 128], b["last"].raw, nxt))
+        return next_q, nxt
 
     def _nlookup_sharded(self, tab, q_list, v_list, prev):
         w = self.w
@@ -224,40 +281,15 @@ class GpuPass:
         res = sn.run_p2p()          # exchange fused into the round kernels (peer mailboxes over NVLink)
         sn.free()
         nxt = le32(res.next_running_claim)
-        self.d_futs.append(("nldoc", self.pool["aux"].submit(self._calc_d, nxt)))
+        self.d_futs.append(self.pool["aux"].submit(self._calc_d, le32(pv)))
+        self.d_futs.append(self.pool["aux"].submit(self._calc_d, nxt))
         if self.collect is not None:
             self.collect.append(("nldoc", le32(res.claim_r), b"".join(pack(r) for r in res.rounds), le32(res.sc_last_claim), nxt))
         return pack(res.next_running_q), nxt
 
-    def _calc_d(self, v):
-        # calc_d of a new running claim (framework.rs:517-553): an input of the step circuit only, the
-        # next fold's sum-check does not wait for it
-        d = C.create_string_buffer(32)
-        self.check(self.lib.reef_calc_d(self.ctxs["aux"]._h, v, self.salt, d))
-        return d.raw
-
-    def _nlookup(self, key, tab, q_arr, v_bytes, prev):
-        o, b = self.o[key], self.bufs[key]
-        tag = 0 if key == "nl" else 1
-        pq = prev[0] if prev else None
-        pv = prev[1] if prev else None
-        ctx = self.ctxs["nl" if key == "nl" else "doc"]
-        self.check(self.lib.reef_nlookup_prove(ctx._h, tag, tab._h, q_arr.ctypes.data, v_bytes, len(q_arr), pq, pv,
-                                              self.dh if tag else None, C.byref(o)))
-        ell = o.ell
-        rounds = b["rounds"].raw
-        next_q = b"".join(rounds[i * 128:i * 128 + 32] for i in range(ell))
-        nxt = b["nxt"].raw
-        self.d_futs.append((key, self.pool["aux"].submit(self._calc_d, nxt)))
-        if self.collect is not None:
-            self.collect.append((key, b["claim"].raw, rounds[:ell * 128], b["last"].raw, nxt))
-        return next_q, nxt
-
-    # An MSM is window-sharded across the ranks only when it is large enough to be throughput-bound
-    # (n * windows digit entries); the 2^14..2^15-term fold commitments are latency pipelines, so
-    # with G > 1 ranks each WHOLE commitment goes to one rank (round-robin) and the 64-byte results
-    # are exchanged once per pass.
-    SHARD_MIN_ENTRIES = 1 << 22
+    def _merkle_wits(self, lookups):
+        """mc.make_wits(lookups) (framework.rs:576-580): host-side walk of the committed tree, as in the reference"""
+        return b"".join(wit_bytes(self.tree.path_wits(int(q))) for q in lookups)
 
     def _msm_local(self, bases, dev_tensor, host_arr, n, resident):
         out = C.create_string_buffer(64)
@@ -266,24 +298,6 @@ class GpuPass:
             self.check(self.lib.reef_msm_dev(ctx._h, bases._h, C.c_void_p(dev_tensor.data_ptr()), n, out))
         else:
             self.check(self.lib.reef_msm(ctx._h, bases._h, host_arr.ctypes.data, n, out))
-        return out.raw
-
-    def _msm_sharded(self, bases, dev_tensor, host_arr, n, resident):
-        # windows [w0, w1) on this rank, one all-gather of 128-byte partial points
-        out = C.create_string_buffer(64)
-        ctx = bases.ctx
-        t = self.torch
-        if not resident:
-            dev_tensor = t.from_numpy(host_arr.view(np.int64)).cuda()
-        W = bases.windows
-        w0, w1 = W * self.rank // self.world, W * (self.rank + 1) // self.world
-        part = C.create_string_buffer(128)
-        self.check(self.lib.reef_msm_partial_dev(ctx._h, bases._h, C.c_void_p(dev_tensor.data_ptr()), n, w0, w1, part))
-        mine = t.frombuffer(bytearray(part.raw), dtype=t.uint8).cuda()
-        gathered = [t.empty_like(mine) for _ in range(self.world)]
-        self.dist.all_gather(gathered, mine, group=self.msm_group)
-        allp = b"".join(bytes(g.cpu().numpy().tobytes()) for g in gathered)
-        self.check(self.lib.reef_msm_combine(ctx._h, bases.curve, allp, self.world, out))
         return out.raw
 
     def _exchange_points(self, outs, owners):
@@ -300,18 +314,12 @@ class GpuPass:
         host = allb.cpu().numpy().tobytes()
         return [outs[i] if owners[i] is None else host[(owners[i] * k + i) * 64:(owners[i] * k + i + 1) * 64] for i in range(k)]
 
-    collect = None
-
     def run_collect(self, resident: bool = True):
-        """One untimed pass that keeps EVERY output (per fold: claim_r, all round polynomials and
-        challenges, last claim, next running claim of both sum-checks; the calc_d digests; the four
-        commitments) in the same layout as cpu_pass(collect=True) for the bit-for-bit comparison."""
+        """One untimed pass that keeps EVERY output in cpu_pass(collect=...)'s layout for the bit-for-bit comparison."""
         self.collect = []
         try:
-            _, _, outs, ds = self.run(resident)
-            sc = list(self.collect)      # each sum-check kind runs on its own thread, in fold order
-            got = {"nl": [r[1:] for r in sc if r[0] == "nl"], "nldoc": [r[1:] for r in sc if r[0] == "nldoc"],
-                   "d_nl": [d for k, d in ds if k == "nl"], "d_nldoc": [d for k, d in ds if k == "nldoc"], "msm": list(outs)}
+            _, outs, ds, wits = self.run(resident)
+            got = {"sumchecks": list(self.collect), "d": list(ds), "msm": list(outs), "wits": wits}
         finally:
             self.collect = None
         return got
@@ -319,50 +327,60 @@ class GpuPass:
     def run(self, resident: bool):
         """One pass.  resident=False: every input crosses PCIe inside the call (e2e leg).
         Dependencies kept: sum-check of fold i+1 needs the running claim of fold i; the fold
-        commitments of fold i are issued after both sum-checks of fold i (their witness)."""
+        commitments of fold i are issued after the sum-checks of fold i (their witness)."""
         w = self.w
         self.dh = le32(w["doc_hash"])
         self.salt = le32(w["salt"])
+        doc_tab = T_tab = hyb_tab = None
         if resident:
-            doc_tab, T_tab = self.doc_tab, self.T_tab
+            doc_tab, T_tab, hyb_tab = getattr(self, "doc_tab", None), getattr(self, "T_tab", None), getattr(self, "hyb_tab", None)
         else:
-            f1 = self.pool["doc"].submit(lambda: self.ctxs["doc"].table_u32(self.h_doc))   # H2D of the document codes
-            f2 = self.pool["nl"].submit(self._upload_T)
-            doc_tab, T_tab = f1.result(), f2.result()
+            if self.mode == "hybrid":
+                hyb_tab = self.ctxs["doc"].table_hybrid(w["T_bytes"], w["fill"], w["half"], self.h_doc)      # H2D of T + document codes
+            else:
+                f2 = self.pool["nl"].submit(self._upload_T)
+                if self.mode == "nldoc":
+                    doc_tab = self.pool["doc"].submit(lambda: self.ctxs["doc"].table_u32(self.h_doc)).result()   # H2D of the document codes
+                T_tab = f2.result()
         prev_nl = prev_doc = None
         msm_futs, owners = [], []
         self.d_futs = []
+        wits = []
+        first_doc = le32(int(w["udoc"][0]))
         for s in range(w["steps"]):
-            qn, qd = self.q_nl[s], self.q_doc[s]
-            f_nl = self.pool["nl"].submit(self._nlookup, "nl", T_tab, qn[0], qn[1], prev_nl)
-            if self.world > 1:
-                f_doc = self.pool["doc"].submit(self._nlookup_sharded, doc_tab, w["q_doc"][s], [int(w["udoc"][i]) for i in w["q_doc"][s]], prev_doc)
+            if self.mode == "hybrid":
+                qh = self.q_hyb[s]
+                prev_doc = self.pool["doc"].submit(self._nlookup, "nlhybrid", hyb_tab, qh[0], qh[1], prev_doc, le32(w["T"][0])).result()
             else:
-                f_doc = self.pool["doc"].submit(self._nlookup, "nldoc", doc_tab, qd[0], qd[1], prev_doc)
-            prev_nl, prev_doc = f_nl.result(), f_doc.result()
-            sc, scd = w["sc"][s], (self.sc_dev[s] if resident else None)
-            for key, pool, bases, n in (("Wp", "pri", self.bases_pri, w["n_pri"]), ("Ws", "sec", self.bases_sec, w["n_sec"]),
-                                        ("Tp", "pri2", self.bases_pri2, w["n_pri"]), ("Ts", "sec2", self.bases_sec2, w["n_sec"])):
-                args = (bases, scd[key] if resident else None, sc[key], n, resident)
-                if self.world == 1:
-                    msm_futs.append(self.pool[pool].submit(self._msm_local, *args))
-                    owners.append(None)
-                elif n * bases.windows >= self.SHARD_MIN_ENTRIES:
-                    # one thread issues these collectives, in the same order on every rank
-                    msm_futs.append(self.pool["pri"].submit(self._msm_sharded, *args))
-                    owners.append(None)
+                qn = self.q_nl[s]
+                f_nl = self.pool["nl"].submit(self._nlookup, "nl", T_tab, qn[0], qn[1], prev_nl, None)
+                if self.mode == "merkle":
+                    wits.append(self._merkle_wits(w["q_doc"][s]))
+                elif self.world > 1:
+                    prev_doc = self.pool["doc"].submit(self._nlookup_sharded, doc_tab, w["q_doc"][s],
+                                                       [int(w["udoc"][i]) for i in w["q_doc"][s]], prev_doc).result()
                 else:
-                    owner = len(owners) % self.world
-                    msm_futs.append(self.pool[pool].submit(self._msm_local, *args) if owner == self.rank else None)
-                    owners.append(owner)
+                    qd = self.q_doc[s]
+                    prev_doc = self.pool["doc"].submit(self._nlookup, "nldoc", doc_tab, qd[0], qd[1], prev_doc, first_doc).result()
+                prev_nl = f_nl.result()
+            sc, scd = w["sc"][s], (self.sc_dev[s] if resident else None)
+            for key, pool, n in (("Wp", "pri", w["n_pri"]), ("Ws", "sec", w["n_sec"]), ("Tp", "pri2", w["n_pri"]), ("Ts", "sec2", w["n_sec"])):
+                args = (self.bases[key], scd[key] if resident else None, sc[key], n, resident)
+                owner = None if self.world == 1 else len(owners) % self.world
+                if owner is None or owner == self.rank:
+                    msm_futs.append(self.pool[pool].submit(self._msm_local, *args))
+                else:
+                    msm_futs.append(None)
+                owners.append(owner)
         outs = [f.result() if f is not None else None for f in msm_futs]
-        ds = [(k, f.result()) for k, f in self.d_futs]
-        if self.world > 1 and any(o is not None for o in owners):
+        ds = [f.result() for f in self.d_futs]
+        if self.world > 1:
             outs = self._exchange_points(outs, owners)
         if not resident:
-            doc_tab.free()
-            T_tab.free()
-        return prev_nl, prev_doc, outs, ds
+            for t in (doc_tab, T_tab, hyb_tab):
+                if t is not None:
+                    t.free()
+        return (prev_nl, prev_doc), outs, ds, wits
 
     def _upload_T(self):
         h = C.c_void_p()
@@ -373,20 +391,47 @@ class GpuPass:
 
     def prepare_queries(self):
         w = self.w
-        self.q_nl = [(np.asarray(q, dtype=np.uint64), pack(w["T"][i] for i in q)) for q in w["q_nl"]]
-        self.q_doc = [(np.asarray(q, dtype=np.uint64), pack(int(w["udoc"][i]) for i in q)) for q in w["q_doc"]]
+        if self.mode == "hybrid":
+            self.q_hyb = [(np.asarray(q, dtype=np.uint64), pack(hybrid_value(w, i) for i in q)) for q in w["q_hyb"]]
+        else:
+            self.q_nl = [(np.asarray(q, dtype=np.uint64), pack(w["T"][i] for i in q)) for q in w["q_nl"]]
+            self.q_doc = [(np.asarray(q, dtype=np.uint64), pack(int(w["udoc"][i]) for i in q)) for q in w["q_doc"]]
 
     def bytes_per_step(self):
         w = self.w
-        h2d = w["udoc"].nbytes + len(w["T_bytes"])
+        h2d = (w["udoc"].nbytes if self.mode != "merkle" else 0) + len(w["T_bytes"])
+        d2h = 0
+        ells = {"nldoc": (self.ell_T, self.ell_doc), "hybrid": (self.ell_doc + 1,), "merkle": (self.ell_T,)}[self.mode]
         for s in range(w["steps"]):
             h2d += sum(v.nbytes for v in w["sc"][s].values())
-            for ell, m in ((self.ell_T, w["m"]), (self.ell_doc, w["m"])):
-                h2d += (m + ell + 3) * 32 + ell * 32 + m * 8
-        d2h = 0
-        for s in range(w["steps"]):
-            d2h += 2 * 8192 + 2 * 32 + 4 * 64                        # NlState x2, calc_d x2, 4 points
+            for ell in ells:
+                h2d += (w["m"] + ell + 3) * 32 + ell * 32 + w["m"] * 8
+                d2h += 8192
+            d2h += 2 * 32 + 4 * 64                                   # calc_d x2, 4 points
         return h2d, d2h
+
+    # -- commit phase (--commit: run_committer, framework.rs:62-79) -----------------------------------
+    def commit_setup(self):
+        if self.mode == "merkle":
+            return
+        rows, cols = WL.hyrax_dims(self.ell_doc)
+        rnd = random.Random(99)
+        self.hy_blind_ints = [rnd.randrange(FQ) for _ in range(rows)]
+        self.hy_blinds = pack(self.hy_blind_ints)
+        self.hy_gens = WL.generators("pallas", cols + 1)
+        self.hy_bases = self.rb.Bases(self.ctxs["pri"], "pallas", self.hy_gens, 255)
+
+    def commit(self):
+        """Hyrax rows (commitment.rs:187, blinds injected) or the Merkle tree (merkle_tree.rs:25-78) of the document,
+        from HOST codes.  Returns the commitment bytes (rows x 64 B | root)."""
+        w = self.w
+        if self.mode == "merkle":
+            return le32(self.ctxs["doc"].merkle_raw(w["udoc"])[0])       # the whole tree comes back (it is what the .cmt stores)
+        rows, cols = WL.hyrax_dims(self.ell_doc)
+        out = C.create_string_buffer(rows * 64)
+        self.check(self.lib.reef_msm_rows_u32(self.ctxs["pri"]._h, self.hy_bases._h, self.h_doc.ctypes.data, rows, cols, w["bits"],
+                                              self.hy_blinds, out))
+        return out.raw
 
 
 def sample_clocks_start():
@@ -470,63 +515,35 @@ def run_reef(args):
     dev = local if world > 1 else 0
     # one context (= one CUDA stream + one host thread) per independent chain of a fold
     ctxs = {k: reef_b200.Context(dev) for k in ("nl", "doc", "pri", "sec", "pri2", "sec2", "aux")}
-    # weak scaling: ONE document of base_len * G characters.  Its nldoc sum-check is sharded by
-    # low index bits (rank g holds udoc[g::G]); the fold commitments are sharded by Pippenger
-    # windows; the tiny T-table sum-check is replicated.
     w = make_workload(args.workload, seed_shift=0, world=world)
     gp = GpuPass(ctxs, w, rank, world, dist)
     gp.prepare_queries()
     gp.make_resident()
-    # Untimed, before the timed legs: the whole pass on this workload is compared bit for bit with the
-    # CPU restatement of the reference's algorithm (oracle/c) -- every rank against rank 0's CPU run of
-    # the SAME (world-scaled) document.  The same CPU run is the cpu_baseline figure of the line.
-    verified, cpu_line = None, None
-    if not args.no_cpu_baseline:
-        exp = [None]
-        if rank == 0:
-            exp[0] = {}
-            cpu_line = cpu_baseline(w, None, exp[0])
-        if world > 1:
-            dist.broadcast_object_list(exp, src=0)
-        got = gp.run_collect(True)
-        verified = compare_outputs(got, exp[0], f"rank {rank}")      # ParityError is loud
-        got = gp.run_collect(False)
-        compare_outputs(got, exp[0], f"rank {rank}, host-buffer (e2e) path")
-        if world > 1:
-            verified += f"; every one of the {world} ranks checked its own copy of the results"
     streams = {k: torch.cuda.ExternalStream(c.stream) for k, c in ctxs.items()}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")    # > 126 MB L2
+    clock_windows = []
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(gp, resident, steps, warmup, profile):
-        barrier()                               # ranks enter every leg together
+    def timed_fn(fn, steps, warmup):
+        """device time of `steps` calls of fn() (each drains every library stream), max over ranks"""
+        barrier()
         for _ in range(warmup):
             flush.fill_(1)
-            gp.run(resident)
+            fn()
         barrier()
-        if profile:
-            for c in ctxs.values():
-                reef_b200._lib.check(reef_b200.lib.reef_profile_enable(c._h, 1))
-        launches0 = int(reef_b200.lib.reef_launch_count())
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = {k: torch.cuda.Event(enable_timing=True) for k in streams}
         barrier()
         e0.record(streams["doc"])               # every stream is idle here (barrier above)
-        t0 = time.perf_counter()
-        w0 = time.time()
-        per_step = []
+        t0, w0 = time.perf_counter(), time.time()
         for _ in range(steps):
-            flush.fill_(1)                      # L2 flush between steps; run() returns only after all streams drained
+            flush.fill_(1)                      # L2 flush between steps; fn() returns only after all streams drained
             torch.cuda.current_stream().synchronize()
-            ts = time.perf_counter()
-            gp.run(resident)
-            per_step.append(round((time.perf_counter() - ts) * 1e3, 3))
-        if args.debug and rank == 0:
-            print(f"[debug] resident={resident} profile={profile} per-step wall ms: {per_step}", file=sys.stderr)
+            fn()
         for k in streams:
             e1[k].record(streams[k])
         barrier()
@@ -537,8 +554,20 @@ def run_reef(args):
             tt = torch.tensor([ms], device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt.item())
+        return ms, wall * 1e3
+
+    def timed(gpx, resident, steps, warmup, profile):
+        barrier()
+        for _ in range(warmup):                  # warm-up outside the counted / profiled region
+            flush.fill_(1)
+            gpx.run(resident)
+        barrier()
+        if profile:
+            for c in ctxs.values():
+                reef_b200._lib.check(reef_b200.lib.reef_profile_enable(c._h, 1))
+        launches0 = int(reef_b200.lib.reef_launch_count())
+        ms, wall = timed_fn(lambda: gpx.run(resident), steps, 0)
         launches = int(reef_b200.lib.reef_launch_count()) - launches0
-        clocks = None
         prof = None
         if profile:
             n = 9
@@ -548,55 +577,98 @@ def run_reef(args):
                 reef_b200._lib.check(reef_b200.lib.reef_profile_read(c._h, n, cnt, units, pms))
                 reef_b200._lib.check(reef_b200.lib.reef_profile_enable(c._h, 0))
                 prof = [(p[0] + int(cnt[i]), p[1] + int(units[i]), p[2] + float(pms[i])) for i, p in enumerate(prof)]
-        return ms, wall * 1e3, launches, clocks, prof
+        return ms, wall, launches, prof
+
+    def verify(gpx, wx, what):
+        """Untimed: the whole pass on this workload compared bit for bit with the CPU restatement of the reference's
+        algorithm (oracle/c); every rank against rank 0's CPU run of the SAME document."""
+        exp = [None]
+        cpu_line = None
+        if rank == 0:
+            exp[0] = {}
+            cpu_line = cpu_baseline(wx, None, exp[0])
+        if world > 1:
+            dist.broadcast_object_list(exp, src=0)
+        msg = compare_outputs(gpx.run_collect(True), exp[0], f"{what}, rank {rank}")      # ParityError is loud
+        compare_outputs(gpx.run_collect(False), exp[0], f"{what}, rank {rank}, host-buffer (e2e) path")
+        if world > 1:
+            msg += f"; every one of the {world} ranks checked its own copy of the results"
+        return msg, cpu_line
 
     K, Wm = args.steps, args.warmup
-    # value: unprofiled run (event recording around every launch group costs host time);
-    # a second, profiled run of the same K steps feeds the per-kernel figures and the clocks.
-    clock_windows = []
+    verified, cpu_line = (None, None) if args.no_cpu_baseline else verify(gp, w, args.workload)
     clk = sample_clocks_start() if rank == 0 else (None, None)
-    ms, wall_ms, launches, _, _ = timed(gp, True, K, Wm, False)
-    _, _, _, _, prof = timed(gp, True, K, Wm, True)
+    ms, wall_ms, launches, _ = timed(gp, True, K, Wm, False)
+    _, _, _, prof = timed(gp, True, K, Wm, True)
     clocks = sample_clocks_stop(*clk, device=dev, windows=clock_windows) if rank == 0 else None
-    e2e_ms, _, _, _, _ = timed(gp, False, K, Wm, False)
-    also = None
-    if world == 1 and args.also and args.also != args.workload:
-        # the second workload (configs[1] by default): same pass, value and e2e only
-        w2 = make_workload(args.also)
-        gp2 = GpuPass(ctxs, w2, rank, world, dist)
-        gp2.prepare_queries()
-        gp2.make_resident()
-        exp2 = {}
-        cpu2 = None if args.no_cpu_baseline else cpu_baseline(w2, None, exp2)
-        ver2 = None if args.no_cpu_baseline else compare_outputs(gp2.run_collect(True), exp2, args.also)
-        ms2, _, launches2, _, _ = timed(gp2, True, K, Wm, False)
-        e2e2, _, _, _, _ = timed(gp2, False, K, Wm, False)
-        h2d2, d2h2 = gp2.bytes_per_step()
-        also = {"workload": args.also + ": " + w2["desc"], "value": round(w2["doc_len"] / (ms2 / K / 1e3), 1),
-                "ms_per_step": round(ms2 / K, 4), "gpu_launches": launches2, "verified": ver2, "cpu_baseline": cpu2,
-                "e2e": {"value": round(w2["doc_len"] / (e2e2 / K / 1e3), 1), "unit": "NFA steps/s", "ms_per_step": round(e2e2 / K, 4),
-                        "h2d_bytes_per_step": h2d2, "d2h_bytes_per_step": d2h2}}
-    doc_units = w["doc_len"]            # already base_len * world (one sharded document)
-    value = doc_units / (ms / K / 1e3)
-    e2e_value = doc_units / (e2e_ms / K / 1e3)
+    e2e_ms, _, _, _ = timed(gp, False, K, Wm, False)
+    commit = commit_phase(gp, w, timed_fn, K, Wm, args.no_cpu_baseline) if world == 1 else None
+
+    # ---- the other BASELINE configs (N = 1): same pass + their commit phase, each verified
+    also = []
+    if world == 1:
+        for name in [x for x in args.also.split(",") if x and x != args.workload]:
+            w2 = make_workload(name)
+            gp2 = GpuPass(ctxs, w2, rank, world, dist)
+            gp2.prepare_queries()
+            gp2.make_resident()
+            ver2, cpu2 = (None, None) if args.no_cpu_baseline else verify(gp2, w2, name)
+            ms2, _, launches2, _ = timed(gp2, True, K, Wm, False)
+            e2e2, _, _, _ = timed(gp2, False, K, Wm, False)
+            h2d2, d2h2 = gp2.bytes_per_step()
+            entry = {"workload": name + ": " + w2["desc"], "value": round(w2["doc_len"] / (ms2 / K / 1e3), 1),
+                     "ms_per_step": round(ms2 / K, 4), "gpu_launches": launches2, "verified": ver2, "cpu_baseline": cpu2,
+                     "e2e": {"value": round(w2["doc_len"] / (e2e2 / K / 1e3), 1), "unit": "NFA steps/s", "ms_per_step": round(e2e2 / K, 4),
+                             "h2d_bytes_per_step": h2d2, "d2h_bytes_per_step": d2h2}}
+            entry["commit"] = commit_phase(gp2, w2, timed_fn, K, Wm, args.no_cpu_baseline)
+            also.append(entry)
+            for t in ("doc_tab", "T_tab", "hyb_tab"):
+                if getattr(gp2, t, None) is not None:
+                    getattr(gp2, t).free()
+            for b in gp2.bases.values():
+                b.free()
+            del gp2
+            torch.cuda.empty_cache()
+
+    # ---- multi-GPU: what sharding buys, measured on the same ranks
+    multi = multi_gpu_extras(args, ctxs, gp, w, rank, world, dist, timed_fn, K, Wm, ms) if world > 1 else None
+    transcript = transcript_object(ctxs["aux"], w, gp, prof, K, clocks) if rank == 0 else None
+
+    value = w["doc_len"] / (ms / K / 1e3)
+    e2e_value = w["doc_len"] / (e2e_ms / K / 1e3)
     if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     peaks = load_peaks()
     names = ["sweep_first", "sweep_fold", "round_transcript", "tail", "nl_setup", "msm_sort", "msm_accum", "msm_reduce", "poseidon"]
     total_prof = sum(p[2] for p in prof) or 1.0
     shares = {n: round(p[2] / total_prof, 4) for n, p in zip(names, prof)}
     kernel_ms = {n: round(p[2] / K, 4) for n, p in zip(names, prof)}
-    # MLE sweep roofline: algorithmic bytes of the reference-shaped fused schedule (SURVEY 8d:
-    # 2 tables x 32 B): round-1 pass reads 2 L elements (64 L bytes); a fold+accumulate pass over
-    # an input of length L reads 2 L and writes L elements (96 L bytes).
+    classes = {"transcript": shares["round_transcript"] + shares["tail"] + shares["nl_setup"],
+               "msm": shares["msm_sort"] + shares["msm_accum"] + shares["msm_reduce"],
+               "sweep": shares["sweep_first"] + shares["sweep_fold"], "poseidon_batch": shares["poseidon"]}
+    dominant = max(classes, key=classes.get)
+    # MLE sweep: the only HBM-streaming kernel of the pass.  Algorithmic bytes of the reference-shaped fused schedule
+    # (SURVEY 8d: 2 tables x 32 B): round-1 pass reads 2 L elements (64 L bytes); a fold+accumulate pass over an input
+    # of length L reads 2 L and writes L elements (96 L bytes).
     sweep_bytes = 64.0 * prof[0][1] + 96.0 * prof[1][1]
     sweep_ms = prof[0][2] + prof[1][2]
     achieved = sweep_bytes / (sweep_ms / 1e3) / 1e9 if sweep_ms > 0 else 0.0
+    # integer-issue view of the same launches: a u32 first pass is ~0.25 modmul-equivalents per element, a fold pass one
+    # modmul (r * diff) + one 256x256 multiply-accumulate (~0.7) per OUTPUT element
+    sweep_modmul = 0.25 * prof[0][1] + 1.7 * (prof[1][1] / 2.0)
     roof = {"bound": "hbm", "kernel": "k_sweep (MLE fold+accumulate passes)", "achieved": round(achieved, 1),
             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": None,
             "peak_source": peaks["source"], "launches": prof[0][0] + prof[1][0],
             "alg_bytes_per_launch": round(sweep_bytes / max(1, prof[0][0] + prof[1][0])),
-            "avg_launch_us": round(1e3 * sweep_ms / max(1, prof[0][0] + prof[1][0]), 2)}
+            "avg_launch_us": round(1e3 * sweep_ms / max(1, prof[0][0] + prof[1][0]), 2),
+            "note": "GB/s is ALGORITHMIC-equivalent (the document streams as 4-byte codes and the eq table is never materialised, "
+                    "so real DRAM traffic is ~6x lower: see traffic); the binding resource of this kernel is integer issue slots",
+            "int_issue_frac": round(sweep_modmul / (sweep_ms / 1e3) / peaks["modmul_per_s"], 4) if sweep_ms else None,
+            "share_of_gpu_time": round(classes["sweep"], 4),
+            "time_dominant_class": dominant, "class_shares": {k: round(v, 4) for k, v in classes.items()}}
     tr = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     if os.path.exists(tr):
         try:
@@ -610,22 +682,24 @@ def run_reef(args):
     msm_ms = prof[5][2] + prof[6][2] + prof[7][2]
     ops = 0.0
     n_terms = 0
-    for bases, n in ((gp.bases_pri, w["n_pri"]), (gp.bases_sec, w["n_sec"])):
-        Wn, c = bases.windows, bases.window_bits
+    for key, n in (("Wp", w["n_pri"]), ("Ws", w["n_sec"])):
+        Wn, c = gp.bases[key].windows, gp.bases[key].window_bits
         ops += 2 * w["steps"] * K * (10.0 * n * Wn + 14.0 * Wn * (1 << c)) / max(1, world)
         n_terms += 2 * w["steps"] * K * n / max(1, world)
     msm = {"bound": "int-alu (255-bit modmul)", "mops": round(n_terms / (msm_ms / 1e3) / 1e6, 2) if msm_ms else None,
            "achieved_modmul_per_s": round(ops / (msm_ms / 1e3), 0) if msm_ms else None, "peak_modmul_per_s": peaks["modmul_per_s"],
            "frac": round(ops / (msm_ms / 1e3) / peaks["modmul_per_s"], 4) if msm_ms else None,
+           "share_of_gpu_time": round(classes["msm"], 4),
+           "note": "fold commitments of 2^14-2^16 terms are latency pipelines (~50 dependent curve operations); `large` is the same "
+                   "kernels at a throughput size",
            "peak_source": "tools/bench_fp.cu on this pool (profiles/peak_modmul.json)"}
-    # the same MSM kernels on a throughput-sized instance (uniform 255-bit scalars), alone on the GPU
     if world == 1 and args.msm_large_log2:
         msm["large"] = msm_large(ctxs["pri"], args.msm_large_log2, peaks["modmul_per_s"])
     h2d, d2h = gp.bytes_per_step()
     out = {
         "metric": "NFA steps/s proved (= doc_len / hot-path prove time)", "value": round(value, 1), "unit": "NFA steps/s",
         "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms / K, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 limbs (255-bit prime fields Fq/Fp, exact integer)",
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 / u29x10 limbs (255-bit prime fields Fq/Fp, exact integer)",
         "data": "synthetic",
         "config": {"workload": args.workload + ": " + w["desc"], "l2": "256 MiB buffer written between steps (L2 flush)",
                    "timing": "CUDA events: start on an idle stream, end = latest of the library streams; max over ranks",
@@ -635,20 +709,201 @@ def run_reef(args):
                    "parallelism": (f"1 document of {w['doc_len']} chars: nldoc sum-check sharded by low index bits x{world} "
                                    f"(96 bytes per rank per round; the round kernels themselves store them into the peers' mailboxes over NVLink and "
                                    f"acquire the peers' -- no NCCL call, no extra launch); fold commitments (2^14-2^15 terms, latency-bound) distributed "
-                                   f"whole, round-robin over the ranks, results exchanged once per pass; MSMs with >= 2^22 "
-                                   f"digit entries are sharded by Pippenger windows (128-byte all-gather)") if world > 1 else "single GPU"},
+                                   f"whole, round-robin over the ranks, results exchanged once per pass") if world > 1 else "single GPU"},
         "e2e": {"value": round(e2e_value, 1), "unit": "NFA steps/s", "ms_per_step": round(e2e_ms / K, 4),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "msm": msm,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "transcript": transcript, "msm": msm,
         "kernel_ms_per_step": kernel_ms, "kernel_share": shares, "wall_ms_per_step": round(wall_ms / K, 4),
     }
+    if commit:
+        out["commit"] = commit
     if also:
         out["also"] = also
+    if multi:
+        out["multi_gpu"] = multi
     if cpu_line:
         out["cpu_baseline"] = cpu_line
     print(json.dumps(out), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def _ells(w, gp):
+    return {"nldoc": (gp.ell_T, gp.ell_doc), "hybrid": (gp.ell_doc + 1,), "merkle": (gp.ell_T,)}[w["mode"]]
+
+
+def _perms(m, ell):
+    """permutations of one nlookup transcript: first absorb in groups of 4 + one per round"""
+    return (m + ell + 2 + (m * ell + 253) // 254 + 3) // 4 + ell
+
+
+def transcript_object(ctx, w, gp, prof, K, clocks):
+    """The Fiat-Shamir chain (the time-dominant class of the pass): permutations on the critical path, their measured
+    latency, and the dependency floor of one permutation."""
+    import reef_b200
+    cyc = (C.c_uint64 * 9)()
+    inp = pack([1, 2, 3, 4, 5])
+    out = C.create_string_buffer(160)
+    for _ in range(2):
+        reef_b200._lib.check(reef_b200.lib.reef_gputest_poseidon_permute_lp(ctx._h, inp, 16, out, cyc))
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    per = int(cyc[0])
+    ells = _ells(w, gp)
+    perms_crit = w["steps"] * _perms(w["m"], max(ells))           # the chain of the longest table gates the pass
+    perms_all = w["steps"] * sum(_perms(w["m"], e) for e in ells)
+    rounds_all = w["steps"] * sum(ells)
+    mul_cycles = 345.0                                # dependent lane-parallel multiplication (tools/bench_lp.cu)
+    floor_cycles = (56 * 3 + 8 * 4) * mul_cycles      # 56 partial rounds x (w^2, w^4, w^5) + 8 full rounds x (x^5 + MDS row)
+    tr_ms = (prof[2][2] + prof[3][2] + prof[4][2]) / K
+    return {"bound": "latency: one dependent chain of 255-bit multiplications (Poseidon t=5, 8 full + 56 partial rounds)",
+            "permutations_on_critical_path": perms_crit, "cycles_per_permutation": per, "us_per_permutation": round(per / mhz, 2),
+            "phases_cycles": {"first_full_rounds": int(cyc[1]), "partial_rounds": int(cyc[2]), "end": int(cyc[3]), "last_full_rounds": int(cyc[4])},
+            "dependency_floor_cycles": int(floor_cycles), "frac_of_dependency_floor": round(floor_cycles / per, 3),
+            "floor_note": "200 dependent multiplications x 345 cycles (the measured latency of ONE lane-parallel multiplication: 4 "
+                          "shared-memory/shuffle hops + 22 IMAD.WIDE deep); round 1: 172 k cycles / 88 us per permutation",
+            "critical_path_ms_per_pass": round(perms_crit * per / mhz / 1e3, 3),
+            "transcript_kernels_ms_per_pass": round(tr_ms, 3),
+            "non_permutation_us_per_round": round(max(0.0, tr_ms * 1e3 - perms_all * per / mhz) / max(1, rounds_all), 2)}
+
+
+def commit_phase(gp, w, timed_fn, K, Wm, no_cpu):
+    """--commit of the same document (run_committer, framework.rs:62-79) from HOST codes: e2e time, verified."""
+    gp.commit_setup()
+    got = gp.commit()
+    ver, cpu = None, None
+    if not no_cpu:
+        from oracle import cport
+        t0 = time.perf_counter()
+        if w["mode"] == "merkle":
+            cport.lib().oracle_set_fast_poseidon(1)
+            try:
+                exp = le32(cport.merkle(w["udoc"], threads=cport.max_threads())[-1][0])
+            finally:
+                cport.lib().oracle_set_fast_poseidon(0)
+            cpu_s = time.perf_counter() - t0
+            if got != exp:
+                raise ParityError("Merkle commitment differs from the oracle")
+            ver = "root == oracle/c over all 2^%d leaves" % gp.ell_doc
+        else:
+            rows, cols = WL.hyrax_dims(gp.ell_doc)
+            rnd = random.Random(7)
+            sample = sorted({0, rows - 1} | {rnd.randrange(rows) for _ in range(6)})
+            for r in sample:
+                sc = [int(x) for x in w["udoc"][r * cols:(r + 1) * cols]] + [gp.hy_blind_ints[r]]
+                P = cport.msm("pallas", gp.hy_gens, sc, threads=cport.max_threads())
+                if got[r * 64:(r + 1) * 64] != (bytes(64) if P is None else le32(P[0]) + le32(P[1])):
+                    raise ParityError(f"Hyrax row commitment {r} differs from the oracle")
+            cpu_s = (time.perf_counter() - t0) * rows / len(sample)
+            ver = f"{len(sample)} of {rows} row commitments (blinds included) == oracle/c"
+        cpu = {"seconds": round(cpu_s, 3), "cores": cport.max_threads(), "kind": "port",
+               "sample": "whole tree" if w["mode"] == "merkle" else "sampled rows scaled to all rows"}
+    ms, _ = timed_fn(gp.commit, K, Wm)
+    kind = "merkle_tree.rs:25-78 Poseidon tree" if w["mode"] == "merkle" else "commitment.rs:187 Hyrax rows %d x %d" % WL.hyrax_dims(gp.ell_doc)
+    if w["mode"] != "merkle":
+        gp.hy_bases.free()
+    return {"what": kind, "e2e_ms": round(ms / K, 3), "chars_per_s": round(w["doc_len"] / (ms / K / 1e3), 1), "verified": ver, "cpu_baseline": cpu,
+            "not_included": "PoseidonRO over the row commitments (commitment.rs:190-198) and the CAP key setup: see DESIGN.md"}
+
+
+def multi_gpu_extras(args, ctxs, gp, w, rank, world, dist, timed_fn, K, Wm, ms_sharded):
+    """Measured on the same ranks after the main legs (multi-GPU runs only)."""
+    import torch
+    import reef_b200
+    out = {}
+    peaks = load_peaks()
+    lib, check = reef_b200.lib, reef_b200._lib.check
+    # (a) the SAME world-scaled document on ONE GPU (rank 0 alone): what the sharding of the pass buys
+    if rank == 0:
+        gp1 = GpuPass(ctxs, w, 0, 1, None)
+        gp1.q_nl, gp1.q_doc = gp.q_nl, gp.q_doc
+        gp1.sc_dev = gp.sc_dev
+        gp1.T_tab = gp.T_tab
+        gp1.doc_tab = ctxs["doc"].table_u32(w["udoc"])
+        streams = [torch.cuda.ExternalStream(c.stream) for c in ctxs.values()]
+        torch.cuda.synchronize()
+        for _ in range(Wm):
+            gp1.run(True)
+        e0 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(streams[0])
+        for _ in range(K):
+            gp1.run(True)
+        ends = []
+        for s in streams:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(s)
+            ends.append(e)
+        torch.cuda.synchronize()
+        ms1 = max(e0.elapsed_time(e) for e in ends) / K
+        gp1.doc_tab.free()
+        for b in gp1.bases.values():
+            b.free()
+        out["same_doc_1gpu"] = {"ms_per_step": round(ms1, 4), "sharded_ms_per_step": round(ms_sharded / K, 4),
+                                "speedup_vs_1gpu_same_doc": round(ms1 / (ms_sharded / K), 3),
+                                "what": f"the same {w['doc_len']}-char document, un-sharded pass on rank 0 alone (other ranks idle)"}
+    dist.barrier()
+    # (b) a throughput-sized MSM sharded by Pippenger windows, 128-byte all-gather by the library's mailbox kernel
+    lg = args.msm_large_log2 or 20
+    n = 1 << lg
+    bases = reef_b200.Bases(ctxs["pri"], "pallas", WL.generators("pallas", n))
+    raw = np.random.default_rng(lg).integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
+    raw[:, 3] &= (1 << 61) - 1
+    devs = torch.from_numpy(raw.view(np.int64)).cuda()
+    res, whole = C.create_string_buffer(64), C.create_string_buffer(64)
+    check(lib.reef_msm_dev(ctxs["pri"]._h, bases._h, C.c_void_p(devs.data_ptr()), n, whole))          # un-sharded reference + scratch sizing
+    dist.barrier()
+    ms_m, _ = timed_fn(lambda: check(lib.reef_msm_sharded_dev(ctxs["pri"]._h, bases._h, C.c_void_p(devs.data_ptr()), n, res)), K, Wm)
+    if res.raw != whole.raw:
+        raise ParityError("window-sharded MSM differs from the un-sharded MSM")
+    ms_1, _ = timed_fn(lambda: check(lib.reef_msm_dev(ctxs["pri"]._h, bases._h, C.c_void_p(devs.data_ptr()), n, whole)), K, Wm)
+    Wn, c = bases.windows, bases.window_bits
+    ops = 10.0 * n * Wn + 14.0 * Wn * (1 << c)
+    out["msm_sharded"] = {"n": n, "windows": Wn, "window_bits": c, "ranks": world, "ms": round(ms_m / K, 3), "mops": round(n / (ms_m / K) / 1e3, 1),
+                          "achieved_modmul_per_s": round(ops / (ms_m / K / 1e3), 0),
+                          "frac_of_world_peak": round(ops / (ms_m / K / 1e3) / (world * peaks["modmul_per_s"]), 4),
+                          "frac_of_one_gpu_peak": round(ops / (ms_m / K / 1e3) / peaks["modmul_per_s"], 4),
+                          "one_gpu_ms": round(ms_1 / K, 3), "speedup_vs_1gpu": round(ms_1 / ms_m, 3),
+                          "verified": "sharded result == un-sharded result on every rank (bit for bit)",
+                          "exchange": "128-byte XYZZ partial per rank, all-gather by a kernel of the library over NVLink peer mailboxes, combine on every rank"}
+    bases.free()
+
+    # (c) commit phase split over the ranks: Hyrax rows and Merkle subtrees (one NCCL all-gather each)
+    def gather(b):
+        mine = torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
+        outs = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(outs, mine)
+        return [bytes(o.cpu().numpy().tobytes()) for o in outs]
+
+    base_doc = np.ascontiguousarray(WL.encode(*WL.document("cfg4")))                  # configs[3] document: Hyrax 1024 x 2048
+    ell = reef_b200.logmn(len(base_doc))
+    rows, cols = WL.hyrax_dims(ell)
+    hb = reef_b200.Bases(ctxs["pri"], "pallas", WL.generators("pallas", cols + 1), 255)
+    rnd = random.Random(99)
+    blinds = [rnd.randrange(FQ) for _ in range(rows)]
+    m2 = base_doc.reshape(rows, cols)
+    full = hb.msm_rows(m2, rows, cols, entry_bits=8, blinds=blinds)
+    got = hb.commit_rows_sharded(m2, rows, cols, 8, blinds, rank, world, gather)
+    if got != full:
+        raise ParityError("row-split Hyrax commitment differs from the single-GPU one")
+    ms_h, _ = timed_fn(lambda: hb.commit_rows_sharded(m2, rows, cols, 8, blinds, rank, world, gather), K, Wm)
+    ms_h1, _ = timed_fn(lambda: hb.msm_rows(m2, rows, cols, entry_bits=8, blinds=blinds), K, Wm)
+    hb.free()
+    per = len(base_doc) // world
+    root1 = [ctxs["doc"].merkle_root(base_doc) if rank == 0 else None]
+    dist.broadcast_object_list(root1, src=0)
+    loc = np.ascontiguousarray(base_doc[rank * per:(rank + 1) * per])
+    rootg, _ = reef_b200.MerkleCommitment.build_sharded(ctxs["doc"], loc, len(base_doc), rank, world, gather)
+    if rootg != root1[0]:
+        raise ParityError("subtree-split Merkle root differs from the single-GPU one")
+    ms_t, _ = timed_fn(lambda: reef_b200.MerkleCommitment.build_sharded(ctxs["doc"], loc, len(base_doc), rank, world, gather), K, Wm)
+    ms_t1, _ = timed_fn(lambda: ctxs["doc"].merkle_root(base_doc), K, Wm)
+    out["commit"] = {"hyrax_rows_split": {"shape": f"{rows} x {cols}", "ms": round(ms_h / K, 3), "one_gpu_ms": round(ms_h1 / K, 3),
+                                          "speedup_vs_1gpu": round(ms_h1 / ms_h, 3), "verified": "== single-GPU commitment (all rows)"},
+                     "merkle_subtrees_split": {"leaves": len(base_doc), "ms": round(ms_t / K, 3), "one_gpu_ms": round(ms_t1 / K, 3),
+                                               "speedup_vs_1gpu": round(ms_t1 / ms_t, 3), "verified": "root == single-GPU root",
+                                               "note": "root only (the G roots are gathered, the level slices stay on their ranks)"}}
+    return out
 
 
 def msm_large(ctx, lg, peak):
@@ -685,6 +940,9 @@ def msm_large(ctx, lg, peak):
 # --------------------------------------------------------------------------------------------
 # CPU arm: the oracle's C restatement of the reference's algorithm (never used by the product)
 # --------------------------------------------------------------------------------------------
+_cpu_tree_cache = {}
+
+
 def cpu_pass(w, n_steps, threads, collect=None):
     """Runs `n_steps` Nova folds of the workload on the CPU port; returns seconds.  `collect` (a dict)
     receives every output in GpuPass.run_collect()'s layout."""
@@ -692,25 +950,58 @@ def cpu_pass(w, n_steps, threads, collect=None):
     from oracle.nlookup import combined_qs, logmn, nlookup_pattern
     cport.lib().oracle_set_fast_poseidon(1)     # neptune hashes with its optimised constants too
     t_total = 0.0
+    mode = w["mode"]
     T_arr = np.frombuffer(w["T_bytes"], dtype=np.uint8)
-    prev = {"nl": None, "nldoc": None}
+    tabs = []
+    if mode == "hybrid":
+        half = w["half"]
+        hyb = np.zeros((2 * half, 4), dtype=np.uint64)
+        limbs = lambda x: [(x >> (64 * k)) & (2 ** 64 - 1) for k in range(4)]
+        for i, x in enumerate(w["T"]):
+            hyb[i] = limbs(x)
+        hyb[len(w["T"]):half] = limbs(w["fill"])
+        nd = len(w["udoc"])
+        for rep in range(half // nd):
+            hyb[half + rep * nd:half + (rep + 1) * nd, 0] = w["udoc"]
+        tabs.append(("nlhybrid", np.frombuffer(hyb.tobytes(), dtype=np.uint8), 0, 2 * half, "q_hyb", w["T"][0]))
+    else:
+        tabs.append(("nl", T_arr, 0, len(w["T"]), "q_nl", w["T"][0]))
+        if mode == "nldoc":
+            tabs.append(("nldoc", w["udoc"], 1, len(w["udoc"]), "q_doc", int(w["udoc"][0])))
+    tree = None
+    if mode == "merkle":
+        # the tree is the product of --commit: built once, outside the timed pass (as on the GPU arm)
+        key = (w["name"], len(w["udoc"]))
+        if key not in _cpu_tree_cache:
+            from oracle.merkle import MerkleCommitment
+            mc = object.__new__(MerkleCommitment)
+            mc.doc = [int(x) for x in w["udoc"]]
+            mc.tree = cport.merkle(w["udoc"], threads=threads)
+            _cpu_tree_cache[key] = mc
+        tree = _cpu_tree_cache[key]
+    prev = {}
     for s in range(n_steps):
         t0 = time.perf_counter()
-        for key, arr, is_u32, n, q, vals in (("nl", T_arr, 0, len(w["T"]), w["q_nl"][s], [w["T"][i] for i in w["q_nl"][s]]),
-                                             ("nldoc", w["udoc"], 1, len(w["udoc"]), w["q_doc"][s], [int(w["udoc"][i]) for i in w["q_doc"][s]])):
+        ds = []
+        for key, arr, is_u32, n, qk, first in tabs:
+            q = w[qk][s]
+            vals = [hybrid_value(w, i) for i in q] if key == "nlhybrid" else ([w["T"][i] for i in q] if key == "nl" else [int(w["udoc"][i]) for i in q])
             ell = logmn(n)
-            pq, pv = prev[key] if prev[key] else ([0] * ell, (w["T"][0] if key == "nl" else int(w["udoc"][0])))
+            pq, pv = prev[key] if key in prev else ([0] * ell, first)
             cqs = combined_qs(list(q), ell)
             pat = nlookup_pattern(key, len(q), ell, len(cqs))
             query = ([] if key == "nl" else [w["doc_hash"]]) + cqs + vals + list(pq) + [pv]
-            claim, rounds, last, nxt = cport.nlookup_raw(arr, is_u32, n, q, pack(query), len(query), cport.ops_words(pat),
-                                                         pack(pq), ell)
+            claim, rounds, last, nxt = cport.nlookup_raw(arr, is_u32, n, q, pack(query), len(query), cport.ops_words(pat), pack(pq), ell)
             r = [int.from_bytes(rounds[i * 128:i * 128 + 32], "little") for i in range(ell)]
             prev[key] = (r, int.from_bytes(nxt, "little"))
+            if key != "nl":
+                ds.append(le32(cport.poseidon_hash([pv, w["salt"]], 2)[0]))
+                ds.append(le32(cport.poseidon_hash([prev[key][1], w["salt"]], 2)[0]))
             if collect is not None:
-                collect.setdefault(key, []).append((claim, rounds, last, nxt))
-        d1 = cport.poseidon_hash([prev["nl"][1], w["salt"]], 2)
-        d2 = cport.poseidon_hash([prev["nldoc"][1], w["salt"]], 2)
+                collect.setdefault("sumchecks", []).append((key, claim, rounds, last, nxt))
+        wit = None
+        if mode == "merkle":
+            wit = b"".join(wit_bytes(tree.path_wits(int(q))) for q in w["q_doc"][s])
         sc = w["sc"][s]
         pts = []
         for key, curve, bases in (("Wp", "pallas", w["bases_pri"]), ("Ws", "vesta", w["bases_sec"]),
@@ -718,8 +1009,10 @@ def cpu_pass(w, n_steps, threads, collect=None):
             pts.append(cport.msm(curve, bases, sc[key].tobytes(), threads=threads))
         t_total += time.perf_counter() - t0
         if collect is not None:
-            collect.setdefault("d_nl", []).append(le32(d1[0]))
-            collect.setdefault("d_nldoc", []).append(le32(d2[0]))
+            collect.setdefault("d", []).extend(ds)
+            collect.setdefault("wits", [])
+            if wit is not None:
+                collect["wits"].append(wit)
             collect.setdefault("msm", []).extend(bytes(64) if P is None else le32(P[0]) + le32(P[1]) for P in pts)
     return t_total
 
@@ -738,20 +1031,20 @@ def cpu_baseline(w, threads, collect=None):
 
 def compare_outputs(got, exp, what):
     """Bit-for-bit comparison of a GPU pass with the CPU restatement; raises ParityError."""
-    for key in ("nl", "nldoc"):
-        if len(got[key]) != len(exp[key]):
-            raise ParityError(f"{what}: {key}: {len(got[key])} folds vs {len(exp[key])}")
-        for f, (g, e) in enumerate(zip(got[key], exp[key])):
-            for name, a, b in zip(("claim_r", "rounds", "sc_last_claim", "next_running_claim"), g, e):
-                if bytes(a) != bytes(b):
-                    raise ParityError(f"{what}: {key} sum-check of fold {f}: {name} differs from the oracle")
-    for key in ("d_nl", "d_nldoc", "msm"):
-        if [bytes(x) for x in got[key]] != [bytes(x) for x in exp[key]]:
+    gs, es = sorted(got["sumchecks"], key=lambda r: r[0]), sorted(exp.get("sumchecks", []), key=lambda r: r[0])
+    if len(gs) != len(es):
+        raise ParityError(f"{what}: {len(gs)} sum-checks vs {len(es)}")
+    for g, e in zip(gs, es):                       # within a tag the folds are in order on both sides (sorted() is stable)
+        for name, a, b in zip(("tag", "claim_r", "rounds", "sc_last_claim", "next_running_claim"), g, e):
+            if (a if isinstance(a, str) else bytes(a)) != (b if isinstance(b, str) else bytes(b)):
+                raise ParityError(f"{what}: {g[0]} sum-check: {name} differs from the oracle")
+    for key in ("d", "msm", "wits"):
+        if sorted(bytes(x) for x in got[key]) != sorted(bytes(x) for x in exp.get(key, [])):
             raise ParityError(f"{what}: {key} differs from the oracle")
-    n_r = sum(len(g[1]) // 128 for k in ("nl", "nldoc") for g in got[k])
-    return (f"GPU pass == oracle/c on the same workload, bit for bit: {len(got['nl'])} folds x (nl + nldoc sum-checks: claim_r, "
-            f"{n_r} round polynomials and challenges in total, last claim, next running claim), {len(got['d_nl']) * 2} calc_d digests, "
-            f"{len(got['msm'])} commitments (untimed, before the timed legs)")
+    n_r = sum(len(g[2]) // 128 for g in gs)
+    return (f"GPU pass == oracle/c on the same workload, bit for bit: {len(gs)} sum-checks ({', '.join(sorted({g[0] for g in gs}))}: claim_r, "
+            f"{n_r} round polynomials and challenges in total, last claims, next running claims), {len(got['d'])} calc_d digests, "
+            f"{len(got['msm'])} commitments, {len(got['wits'])} Merkle witness sets (untimed, before the timed legs; resident and host-buffer paths)")
 
 
 def run_reference(args):
@@ -769,8 +1062,6 @@ def run_reference(args):
     threads = cport.max_threads()
     t_first = cpu_pass(w, w["steps"], threads)          # warm-up pass (page-in, thread pool), also sizes the run
     whole = t_first * args.steps <= 150.0
-    for _ in range(max(0, min(args.warmup, 1) - 1)):
-        cpu_pass(w, w["steps"], threads)
     t = 0.0
     for _ in range(args.steps):
         t += cpu_pass(w, w["steps"], threads) if whole else cpu_pass(w, 1, threads) * w["steps"]
@@ -797,8 +1088,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="reef", choices=["reef", "reference"])
     ap.add_argument("--workload", default="target", choices=sorted(WORKLOADS))
-    ap.add_argument("--also", default="cfg2", help="second workload timed (value/e2e only) and reported under 'also'; '' = none")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--also", default="cfg2,cfg3,cfg4,cfg5",
+                    help="other BASELINE configs timed at N = 1 (value/e2e/commit, each verified) and reported under 'also'; '' = none")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg AND the verification against it")
     ap.add_argument("--msm-large-log2", type=int, default=20, help="size of the stand-alone MSM roofline measurement (0 = skip)")
     ap.add_argument("--debug", action="store_true")
     args = ap.parse_args()

@@ -141,6 +141,12 @@ int reef_merkle_path_wits(const uint64_t* doc, uint64_t n_doc, const uint8_t* le
 int reef_table_upload(reef_ctx* ctx, const uint8_t* table, uint64_t n, reef_table** out);
 /* Document codes (framework.rs:978-1011) as u32: 8x less HBM traffic for the first two passes. */
 int reef_table_upload_u32(reef_ctx* ctx, const uint32_t* codes, uint64_t n, reef_table** out);
+/* The merged table of `--hybrid` (r1cs.rs:481-487 and 2101-2112), built ON THE DEVICE from its two small
+ * inputs: [ pub_table (n_pub elements), `fill` up to half_len | then, until the length is 2 * half_len:
+ * the document codes followed by zeros up to the next power of two ].  half_len a power of two >= n_pub.
+ * (The reference re-materialises this 2 * half_len vector of big integers on the host for every step.) */
+int reef_table_hybrid_u32(reef_ctx* ctx, const uint8_t* pub_table, uint64_t n_pub, const uint8_t fill[32], uint64_t half_len,
+                          const uint32_t* doc_codes, uint64_t n_doc, reef_table** out);
 /* Wrap memory that is already on the device (n must be a power of two; not freed by reef_table_free). */
 int reef_table_wrap_dev(reef_ctx* ctx, void* dev_ptr, uint64_t n, int is_u32, reef_table** out);
 int reef_table_download(const reef_table* t, uint8_t* out, uint64_t n);

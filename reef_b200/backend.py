@@ -135,6 +135,17 @@ class Context:
     def table_u32(self, codes) -> "Table":
         return Table(self, codes=codes)
 
+    def table_hybrid(self, pub_table, fill: int, half_len: int, doc_codes) -> "Table":
+        """The `--hybrid` merged table (r1cs.rs:2101-2112), expanded on the device."""
+        a = np.ascontiguousarray(np.asarray(doc_codes, dtype=np.uint32))
+        pub = _pack(pub_table) if not isinstance(pub_table, (bytes, bytearray)) else bytes(pub_table)
+        h = C.c_void_p()
+        check(lib.reef_table_hybrid_u32(self._h, _buf(pub), len(pub) // 32, _buf(_pack([fill])), half_len, a.ctypes.data, len(a),
+                                        C.byref(h)))
+        t = Table.__new__(Table)
+        t.ctx, t._h = self, h
+        return t
+
     # ---- MLE building blocks (reference-shaped)
     def gen_eq_table(self, rs, qs, last_q) -> list:
         ell = len(last_q)
@@ -258,6 +269,25 @@ class Context:
     # ---- Merkle
     def merkle(self, doc) -> "MerkleCommitment":
         return MerkleCommitment(self, doc)
+
+    def merkle_raw(self, doc):
+        """MerkleCommitment::new with raw buffers: (root int, levels bytes: every level, leaf parents first) -- the
+        whole tree comes back to the host, as the .cmt of --commit holds it (merkle_tree.rs:10-15)."""
+        d = _u64(doc)
+        total = int(lib.reef_merkle_tree_elems(len(d)))
+        levels = C.create_string_buffer(max(total, 1) * 32)
+        sizes = np.zeros(64, dtype=np.uint64)
+        nl = C.c_uint32(0)
+        root = C.create_string_buffer(32)
+        check(lib.reef_merkle_build(self._h, d.ctypes.data, len(d), levels, sizes.ctypes.data, C.byref(nl), root))
+        return int.from_bytes(root.raw, "little"), levels
+
+    def merkle_root(self, doc) -> int:
+        """Root only (power-of-two documents): the tree stays on the device."""
+        d = _u64(doc)
+        root = C.create_string_buffer(32)
+        check(lib.reef_merkle_subtree(self._h, d.ctypes.data, len(d), 0, None, root))
+        return int.from_bytes(root.raw, "little")
 
     # ---- MSM
     def bases(self, curve, points, scalar_bits: int = 0) -> "Bases":

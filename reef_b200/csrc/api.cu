@@ -738,6 +738,61 @@ static int table_new(reef_ctx* c, const void* host, uint64_t n, int is_u32, reef
 int reef_table_upload(reef_ctx* c, const uint8_t* table, uint64_t n, reef_table** out) { return table_new(c, table, n, 0, out); }
 int reef_table_upload_u32(reef_ctx* c, const uint32_t* codes, uint64_t n, reef_table** out) { return table_new(c, codes, n, 1, out); }
 
+int reef_table_hybrid_u32(reef_ctx* c, const uint8_t* pub_table, uint64_t n_pub, const uint8_t fill[32], uint64_t half_len,
+                          const uint32_t* doc_codes, uint64_t n_doc, reef_table** out) {
+  REEF_REQUIRE(c && pub_table && fill && doc_codes && out, REEF_EINVAL, "reef_table_hybrid_u32: NULL argument");
+  REEF_REQUIRE(n_pub >= 1 && n_doc >= 1, REEF_EASSERT, "reef_table_hybrid_u32: empty table (index out of bounds)");
+  REEF_REQUIRE(half_len >= 2 && (half_len & (half_len - 1)) == 0 && half_len >= n_pub, REEF_EINVAL,
+               "reef_table_hybrid_u32: half_len must be a power of two >= the public table length");
+  REEF_REQUIRE(next_pow2(n_doc) <= half_len, REEF_EASSERT, "reef_table_hybrid_u32: padded document longer than half_len");
+  int rc = check_canonical(pub_table, n_pub, "reef_table_hybrid_u32: pub_table");
+  if (!rc) rc = check_canonical(fill, 1, "reef_table_hybrid_u32: fill");
+  if (rc) return rc;
+  const uint64_t n = 2 * half_len;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  void* d = nullptr;
+  for (size_t k = 0; k < c->table_cache.size(); k++) {
+    if (c->table_cache[k].first == (size_t)n * 32) {
+      d = c->table_cache[k].second;
+      c->table_cache.erase(c->table_cache.begin() + k);
+      break;
+    }
+  }
+  if (!d) {
+    cudaError_t e = cudaMalloc(&d, (size_t)n * 32);
+    if (e != cudaSuccess) return fail(REEF_ENOMEM, std::string("reef_table_hybrid_u32: ") + cudaGetErrorString(e));
+  }
+  void* stage;
+  const size_t pub_bytes = ((size_t)n_pub * 32 + 255) & ~(size_t)255;
+  rc = ctx_scratch2(c, pub_bytes + (size_t)n_doc * 4, &stage);
+  if (rc) {
+    cudaFree(d);
+    return rc;
+  }
+  uint32_t* d_codes = (uint32_t*)((char*)stage + pub_bytes);
+  cudaError_t e = cudaMemcpyAsync(stage, pub_table, (size_t)n_pub * 32, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_codes, doc_codes, (size_t)n_doc * 4, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    rc = launch_hybrid_table(c, stage, n_pub, fill, half_len, d_codes, n_doc, d);
+    if (!rc) e = cudaStreamSynchronize(c->stream);
+  }
+  if (rc || e != cudaSuccess) {
+    cudaFree(d);
+    return rc ? rc : fail(REEF_ECUDA, std::string("reef_table_hybrid_u32: ") + cudaGetErrorString(e));
+  }
+  reef_table* t = new reef_table;
+  t->ctx = c;
+  t->d = d;
+  t->n_pad = t->n_orig = n;
+  t->is_u32 = 0;
+  t->owns = 1;
+  memcpy(t->first, pub_table, 32);
+  ctx_retain(c);
+  *out = t;
+  return REEF_OK;
+}
+
 int reef_table_wrap_dev(reef_ctx* c, void* dev_ptr, uint64_t n, int is_u32, reef_table** out) {
   REEF_REQUIRE(c && dev_ptr && out, REEF_EINVAL, "reef_table_wrap_dev: NULL argument");
   REEF_REQUIRE(n >= 2 && (n & (n - 1)) == 0, REEF_EINVAL, "reef_table_wrap_dev: length must be a power of two >= 2");

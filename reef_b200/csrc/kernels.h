@@ -47,6 +47,8 @@ struct NlookupArgs {
   uint8_t* out_next_v;     // 32
 };
 int nlookup_run(reef_ctx* c, const NlookupArgs& a);
+int launch_hybrid_table(reef_ctx* c, const void* d_pub, uint64_t n_pub, const uint8_t* fill_le, uint64_t half_len, const uint32_t* d_codes,
+                        uint64_t n_doc, void* d_out);
 int launch_gen_eq_table(reef_ctx* c, const uint8_t* h_rs, const uint64_t* h_qs, uint32_t m, const uint8_t* h_last_q,
                         uint32_t ell, void* d_out);
 int launch_mle_eval(reef_ctx* c, const void* d_table, int is_u32, uint64_t n, const uint8_t* h_x, uint32_t ell,

@@ -734,6 +734,32 @@ int launch_gen_eq_table(reef_ctx* c, const uint8_t* h_rs, const uint64_t* h_qs, 
   return REEF_OK;
 }
 
+// hybrid table (r1cs.rs:2101-2112): out[i] = pub[i] | fill | doc code (repeated with zero padding to a power of two)
+__global__ void k_hybrid_table(const Fq* __restrict__ pub, uint64_t n_pub, Fq fill, uint64_t half_len,
+                               const uint32_t* __restrict__ codes, uint64_t n_doc, uint64_t doc_pad, Fq* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * half_len) return;
+  Fq v;
+  if (i < half_len) {
+    v = i < n_pub ? ld256(pub + i) : fill;
+  } else {
+    const uint64_t j = (i - half_len) % doc_pad;
+    v = fq_from_u32(j < n_doc ? codes[j] : 0u);
+  }
+  st256(out + i, v);
+}
+
+int launch_hybrid_table(reef_ctx* c, const void* d_pub, uint64_t n_pub, const uint8_t* fill_le, uint64_t half_len,
+                        const uint32_t* d_codes, uint64_t n_doc, void* d_out) {
+  uint64_t doc_pad = 1;
+  while (doc_pad < n_doc) doc_pad <<= 1;
+  const Fq fill = fq_canon_from_le32(fill_le);
+  k_hybrid_table<<<ceil_div_u(2 * half_len, 256), 256, 0, c->stream>>>((const Fq*)d_pub, n_pub, fill, half_len, d_codes, n_doc, doc_pad,
+                                                                     (Fq*)d_out);
+  REEF_LAUNCHED();
+  return REEF_OK;
+}
+
 // out[b] = in[b] + r (in[b+half] - in[b])
 template <bool U32IN>
 __global__ void k_fold(const void* __restrict__ in, Fq* __restrict__ out, uint64_t half, Fq r_mont) {

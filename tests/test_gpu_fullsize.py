@@ -57,7 +57,7 @@ def test_nlhybrid_ell22_merged_table(ctx):
         tab[i] = [(x >> (64 * k)) & (2 ** 64 - 1) for k in range(4)]
     tab[n_T:half] = [(fill >> (64 * k)) & (2 ** 64 - 1) for k in range(4)]
     tab[half:, 0] = udoc
-    t = ctx.table(tab)
+    t = ctx.table_hybrid(T, fill, half, udoc)          # expanded on the device (reef_table_hybrid_u32)
     doc_hash = rnd.randrange(FQ)
     raw = np.frombuffer(tab.tobytes(), dtype=np.uint8)
     rq = rv = None
@@ -130,3 +130,16 @@ def test_hyrax_commit_full_shape(ctx, shape):
         sc = [int(x) for x in udoc[r * cols:(r + 1) * cols]] + [blinds[r]]
         assert got[r] == cport.msm("pallas", gens, sc, threads=cport.max_threads()), f"row {r}"
     b.free()
+
+
+def test_hybrid_table_layout_and_document_repeat_quirk(ctx):
+    """r1cs.rs:2105-2112: T, its fill value up to half_len, then the zero-padded document REPEATED until the
+    table is 2 * half_len long (happens when the padded document is shorter than the public half)."""
+    rnd = random.Random(8)
+    T = [rnd.randrange(FQ) for _ in range(5)]
+    fill = rnd.randrange(FQ)
+    doc = [rnd.randrange(131) for _ in range(5)]            # pads to 8, half_len 16: two copies
+    t = ctx.table_hybrid(T, fill, 16, doc)
+    exp = T + [fill] * 11 + (doc + [0] * 3) * 2
+    assert t.download(32) == exp
+    t.free()

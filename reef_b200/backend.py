@@ -34,6 +34,8 @@ def _buf(b: bytes):
 
 
 def _u64(xs):
+    if isinstance(xs, np.ndarray):
+        return np.ascontiguousarray(xs.astype(np.uint64, copy=False))
     return np.ascontiguousarray(np.asarray(list(xs), dtype=np.uint64))
 
 

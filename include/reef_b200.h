@@ -330,6 +330,31 @@ int reef_r1cs_spmv(reef_ctx* ctx, int field, const uint64_t* row_ptr, const uint
 int reef_ipa_fold_bases(reef_ctx* ctx, int curve, const uint8_t* bases, uint64_t n, const uint8_t s_lo[32],
                         const uint8_t s_hi[32], uint8_t* out);
 
+/* Vector helpers of the composed provers (reef_b200/snark.py), both Pasta fields (0 = Fq, 1 = Fp):
+ *   reef_eq_table  out[i] = eq(r, bits(i)), i < 2^k, r[0] <-> TOP index bit (nova `EqPolynomial::evals`; the order
+ *                  `bound_poly_var_top` consumes the variables in)
+ *   reef_vec_axpy  out = a * x + y  (y may be NULL) */
+int reef_eq_table(reef_ctx* ctx, int field, const uint8_t* r, uint32_t k, uint8_t* out);
+int reef_vec_axpy(reef_ctx* ctx, int field, const uint8_t a[32], const uint8_t* x, const uint8_t* y, uint64_t n, uint8_t* out);
+
+/* Inner-product argument, prover side (commitment.rs:371-393 `hyrax_gen.prove_eval` -> nova-snark ipa_pc; also the
+ * polynomial openings inside CompressedSNARK::prove, framework.rs:695-698).  nova-snark is not under /root/reference
+ * and is not pinned (Cargo.toml:12): the convention is the published upstream one and is PARITY-UNPINNED --
+ *     c_L = <a_lo, b_hi>,  c_R = <a_hi, b_lo>,
+ *     L = <a_lo, G_hi> + c_L gen_c,  R = <a_hi, G_lo> + c_R gen_c,
+ *     a' = a_lo r + a_hi r^-1,  b' = b_lo r^-1 + b_hi r,  G' = G_lo r^-1 + G_hi r        (`ck.fold(&r_inverse, &r)`).
+ * The vectors and the generators stay on the device for the log2(n) rounds; the transcript (which turns L, R into
+ * r) stays with the caller:  begin, then log2(n) x { round -> (L, R); fold(r, r^-1) }, then finish -> a_hat, b_hat, G_hat.
+ * gen_c = the generator the inner-product value is committed with (already scaled by the caller's challenge).
+ * curve 0 = Pallas (scalars in Fq), 1 = Vesta (scalars in Fp).  Points 64-byte affine, infinity = zeros. */
+typedef struct reef_ipa reef_ipa;
+int reef_ipa_begin(reef_ctx* ctx, int curve, const uint8_t* gens, const uint8_t gen_c[64], const uint8_t* a, const uint8_t* b, uint64_t n,
+                   reef_ipa** out);
+int reef_ipa_round(reef_ipa* s, uint8_t out_L[64], uint8_t out_R[64]);
+int reef_ipa_fold(reef_ipa* s, const uint8_t r[32], const uint8_t r_inv[32]);
+int reef_ipa_finish(reef_ipa* s, uint8_t out_a[32], uint8_t out_b[32], uint8_t out_g[64]);
+void reef_ipa_free(reef_ipa* s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,6 +96,7 @@ struct MsmRunArgs {
 int msm_run(reef_ctx* c, int curve, const MsmRunArgs& a);
 int msm_combine(reef_ctx* c, int curve, const uint8_t* h_pts, uint32_t k, uint8_t* h_out);
 int msm_preload();
+int msm_levels_from_dev(reef_ctx* c, int curve, const void* d_canon, uint64_t n, const MsmPlanPublic& pl, void* d_levels, int* d_bad);
 struct MsmRowsArgs {
   MsmPlanPublic plan;
   const void* d_levels;

@@ -858,6 +858,15 @@ int msm_preload() {
   return rc ? rc : msm_preload_t<FqCfg>();
 }
 
+// Montgomery-form level table (plan L levels) from canonical affine points that are already on the device
+// (no curve-membership read-back: the caller's points are products of this library).
+int msm_levels_from_dev(reef_ctx* c, int curve, const void* d_canon, uint64_t n, const MsmPlanPublic& pl, void* d_levels, int* d_bad) {
+  if (curve == 0) k_precompute<FpCfg><<<cdiv(n, 128), 128, 0, c->stream>>>((const Affine<FpCfg>*)d_canon, n, pl.c, pl.L, (Affine<FpCfg>*)d_levels, d_bad);
+  else k_precompute<FqCfg><<<cdiv(n, 128), 128, 0, c->stream>>>((const Affine<FqCfg>*)d_canon, n, pl.c, pl.L, (Affine<FqCfg>*)d_levels, d_bad);
+  REEF_LAUNCHED();
+  return REEF_OK;
+}
+
 int msm_combine(reef_ctx* c, int curve, const uint8_t* h_pts, uint32_t k, uint8_t* h_out) {
   REEF_REQUIRE(k >= 1, REEF_EINVAL, "reef_msm_combine: no partial points");
   size_t need = (size_t)k * 128 + 1024;

@@ -228,11 +228,83 @@ __global__ void __launch_bounds__(128) k_ipa_fold(const Affine<C>* __restrict__ 
   st256(&out_canon[i].y, r.y);
 }
 
+// eq(r, x) over x in {0,1}^k, r[0] <-> top index bit (what bound_poly_var_top consumes first); canonical output
+template <class C>
+__global__ void k_eq_table(const Fe<C>* __restrict__ r_mont, uint32_t k, Fe<C>* __restrict__ out, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Fe<C> one = fe_one<C>();
+  Fe<C> acc = one;
+  for (uint32_t j = 0; j < k; j++) {
+    const Fe<C> rj = r_mont[j];
+    acc = mont_mul<C>(acc, ((i >> (k - 1 - j)) & 1) ? rj : fe_sub<C>(one, rj));
+  }
+  st256(out + i, from_mont<C>(acc));
+}
+
+// out = a * x + y (canonical in / out)
+template <class C>
+__global__ void k_axpy(Fe<C> a_mont, const Fe<C>* __restrict__ x, const Fe<C>* __restrict__ y, uint64_t n, Fe<C>* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fe<C> v = mont_mul<C>(a_mont, ld256(x + i));
+  if (y) v = fe_add<C>(v, ld256(y + i));
+  st256(out + i, v);
+}
+
+// ---------------------------------------------------------------------------------------
+// Inner-product argument rounds (commitment.rs:371-393 -> nova-snark ipa_pc, [UPSTREAM, unpinned]):
+//   c_L = <a_lo, b_hi>, c_R = <a_hi, b_lo>;   a' = a_lo r + a_hi r^-1,  b' = b_lo r^-1 + b_hi r
+// ---------------------------------------------------------------------------------------
+template <class S>
+__global__ void __launch_bounds__(256) k_ipa_dots(const Fe<S>* __restrict__ a, const Fe<S>* __restrict__ b, uint64_t half,
+                                                  Fe<S>* __restrict__ out2) {
+  __shared__ Fe<S> red[2][8];
+  Fe<S> cl = fe_zero<S>(), cr = fe_zero<S>();
+  for (uint64_t i = threadIdx.x; i < half; i += 256) {
+    const Fe<S> alo = to_mont<S>(ld256(a + i)), ahi = to_mont<S>(ld256(a + half + i));
+    cl = fe_add<S>(cl, mont_mul<S>(alo, ld256(b + half + i)));
+    cr = fe_add<S>(cr, mont_mul<S>(ahi, ld256(b + i)));
+  }
+  cl = warp_sum_fe<S>(cl);
+  cr = warp_sum_fe<S>(cr);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = cl;
+    red[1][threadIdx.x >> 5] = cr;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    Fe<S> t = red[threadIdx.x][0];
+    for (int w = 1; w < 8; w++) t = fe_add<S>(t, red[threadIdx.x][w]);
+    st256(out2 + threadIdx.x, t);
+  }
+}
+
+template <class S>
+__global__ void k_ipa_fold_scalars(const Fe<S>* __restrict__ a, const Fe<S>* __restrict__ b, uint64_t half, Fe<S> r_mont,
+                                   Fe<S> rinv_mont, Fe<S>* __restrict__ a_out, Fe<S>* __restrict__ b_out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= half) return;
+  st256(a_out + i, fe_add<S>(mont_mul<S>(r_mont, ld256(a + i)), mont_mul<S>(rinv_mont, ld256(a + half + i))));
+  st256(b_out + i, fe_add<S>(mont_mul<S>(rinv_mont, ld256(b + i)), mont_mul<S>(r_mont, ld256(b + half + i))));
+}
+
 }  // namespace reef
 
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
+struct reef_ipa {
+  reef_ctx* ctx;
+  int curve;
+  uint64_t n0, n;            // initial / current length
+  void* d_buf;
+  char *d_a[2], *d_b[2], *d_G[2];   // double-buffered: scalars canonical (32 B), generators affine canonical (64 B)
+  int cur;
+  char *d_gc, *d_tmpG, *d_tmpS, *d_lv, *d_c;
+  int* d_bad;
+};
+
 struct reef_sumcheck {
   reef_ctx* ctx;
   int field;        // 0 = Fq, 1 = Fp
@@ -519,6 +591,245 @@ int reef_ipa_fold_bases(reef_ctx* c, int curve, const uint8_t* bases, uint64_t n
   std::lock_guard<std::mutex> lk(c->mu);
   REEF_CUDA(cudaSetDevice(c->device));
   return curve == 0 ? ipa_fold_t<FpCfg>(c, bases, n, s_lo, s_hi, out) : ipa_fold_t<FqCfg>(c, bases, n, s_lo, s_hi, out);
+}
+
+}  // extern "C"
+
+template <class C>
+static int eq_table_t(reef_ctx* c, const uint8_t* r, uint32_t k, uint8_t* out) {
+  const uint64_t n = (uint64_t)1 << k;
+  void* base;
+  int rc = ctx_scratch(c, (size_t)n * 32 + (size_t)(k + 1) * 32 + 256, &base);
+  if (rc) return rc;
+  Fe<C>* d_out = (Fe<C>*)base;
+  Fe<C>* d_r = d_out + n;
+  std::vector<Fe<C>> rm(k ? k : 1);
+  for (uint32_t j = 0; j < k; j++) rm[j] = fe_mont_from_le32<C>(r + (size_t)j * 32);
+  cudaStream_t st = c->stream;
+  if (k) REEF_CUDA(cudaMemcpyAsync(d_r, rm.data(), (size_t)k * 32, cudaMemcpyHostToDevice, st));
+  k_eq_table<C><<<sc_cdiv(n, 128), 128, 0, st>>>(d_r, k, d_out, n);
+  REEF_LAUNCHED();
+  REEF_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+  REEF_CUDA(cudaStreamSynchronize(st));
+  return REEF_OK;
+}
+
+template <class C>
+static int axpy_t(reef_ctx* c, const uint8_t* a, const uint8_t* x, const uint8_t* y, uint64_t n, uint8_t* out) {
+  void* base;
+  int rc = ctx_scratch(c, (size_t)n * 96 + 256, &base);
+  if (rc) return rc;
+  Fe<C>* d_x = (Fe<C>*)base;
+  Fe<C>* d_y = d_x + n;
+  Fe<C>* d_o = d_y + n;
+  cudaStream_t st = c->stream;
+  REEF_CUDA(cudaMemcpyAsync(d_x, x, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+  if (y) REEF_CUDA(cudaMemcpyAsync(d_y, y, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+  k_axpy<C><<<sc_cdiv(n, 128), 128, 0, st>>>(fe_mont_from_le32<C>(a), d_x, y ? d_y : nullptr, n, d_o);
+  REEF_LAUNCHED();
+  REEF_CUDA(cudaMemcpyAsync(out, d_o, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+  REEF_CUDA(cudaStreamSynchronize(st));
+  return REEF_OK;
+}
+
+extern "C" {
+
+int reef_eq_table(reef_ctx* c, int field, const uint8_t* r, uint32_t k, uint8_t* out) {
+  REEF_REQUIRE(c && (r || k == 0) && out, REEF_EINVAL, "reef_eq_table: NULL argument");
+  REEF_REQUIRE(field == 0 || field == 1, REEF_EINVAL, "reef_eq_table: field must be 0 (Fq) or 1 (Fp)");
+  REEF_REQUIRE(k <= 30, REEF_EINVAL, "reef_eq_table: k out of range for a host output buffer");
+  int rc = check_canon_field(r, k, field, "reef_eq_table: r");
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  return field == 0 ? eq_table_t<FqCfg>(c, r, k, out) : eq_table_t<FpCfg>(c, r, k, out);
+}
+
+int reef_vec_axpy(reef_ctx* c, int field, const uint8_t a[32], const uint8_t* x, const uint8_t* y, uint64_t n, uint8_t* out) {
+  REEF_REQUIRE(c && a && x && out && n >= 1, REEF_EINVAL, "reef_vec_axpy: NULL / empty argument");
+  REEF_REQUIRE(field == 0 || field == 1, REEF_EINVAL, "reef_vec_axpy: field must be 0 (Fq) or 1 (Fp)");
+  int rc = check_canon_field(a, 1, field, "reef_vec_axpy: a");
+  if (!rc) rc = check_canon_field(x, n, field, "reef_vec_axpy: x");
+  if (!rc && y) rc = check_canon_field(y, n, field, "reef_vec_axpy: y");
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  return field == 0 ? axpy_t<FqCfg>(c, a, x, y, n, out) : axpy_t<FpCfg>(c, a, x, y, n, out);
+}
+
+// ---- IPA session (see include/reef_b200.h)
+int reef_ipa_begin(reef_ctx* c, int curve, const uint8_t* gens, const uint8_t gen_c[64], const uint8_t* a, const uint8_t* b, uint64_t n,
+                   reef_ipa** out) {
+  REEF_REQUIRE(c && gens && gen_c && a && b && out, REEF_EINVAL, "reef_ipa_begin: NULL argument");
+  REEF_REQUIRE(curve == 0 || curve == 1, REEF_EINVAL, "reef_ipa_begin: curve must be 0 (Pallas) or 1 (Vesta)");
+  REEF_REQUIRE(n >= 1 && (n & (n - 1)) == 0, REEF_EASSERT, "reef_ipa_begin: the vector length must be a power of two");
+  const int sfield = curve == 0 ? 0 : 1, cfield = curve == 0 ? 1 : 0;   // Pallas: scalars Fq, coordinates Fp
+  int rc = check_canon_field(a, n, sfield, "reef_ipa_begin: a");
+  if (!rc) rc = check_canon_field(b, n, sfield, "reef_ipa_begin: b");
+  if (!rc) rc = check_canon_field(gens, 2 * n, cfield, "reef_ipa_begin: generator coordinate");
+  if (!rc) rc = check_canon_field(gen_c, 2, cfield, "reef_ipa_begin: generator coordinate");
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  reef_ipa* s = new reef_ipa;
+  memset(s, 0, sizeof(*s));
+  s->ctx = c;
+  s->curve = curve;
+  s->n0 = s->n = n;
+  const size_t half = n / 2 + 1;
+  const size_t bytes = 2 * (n * 32) * 2 + 2 * (n * 64) + 64 + half * 64 + half * 32 + half * 64 + 64 + 256;
+  cudaError_t e = cudaMalloc(&s->d_buf, bytes);
+  if (e != cudaSuccess) {
+    delete s;
+    return fail(REEF_ENOMEM, std::string("reef_ipa_begin: ") + cudaGetErrorString(e));
+  }
+  char* p = (char*)s->d_buf;
+  for (int k = 0; k < 2; k++) { s->d_a[k] = p; p += n * 32; }
+  for (int k = 0; k < 2; k++) { s->d_b[k] = p; p += n * 32; }
+  for (int k = 0; k < 2; k++) { s->d_G[k] = p; p += n * 64; }
+  s->d_gc = p; p += 64;
+  s->d_tmpG = p; p += half * 64;
+  s->d_tmpS = p; p += half * 32;
+  s->d_lv = p; p += half * 64;
+  s->d_c = p; p += 64;
+  s->d_bad = (int*)p;
+  cudaStream_t st = c->stream;
+  e = cudaMemcpyAsync(s->d_a[0], a, n * 32, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_b[0], b, n * 32, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_G[0], gens, n * 64, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_gc, gen_c, 64, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->d_bad, 0, 4, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    cudaFree(s->d_buf);
+    delete s;
+    return fail(REEF_ECUDA, std::string("reef_ipa_begin: ") + cudaGetErrorString(e));
+  }
+  ctx_retain(c);
+  *out = s;
+  return REEF_OK;
+}
+
+}  // extern "C"
+
+template <class SC>
+static int ipa_round_t(reef_ipa* s, uint8_t* out_L, uint8_t* out_R) {
+  reef_ctx* c = s->ctx;
+  cudaStream_t st = c->stream;
+  const uint64_t h = s->n / 2;
+  const char *a = s->d_a[s->cur], *b = s->d_b[s->cur], *G = s->d_G[s->cur];
+  k_ipa_dots<SC><<<1, 256, 0, st>>>((const Fe<SC>*)a, (const Fe<SC>*)b, h, (Fe<SC>*)s->d_c);
+  REEF_LAUNCHED();
+  const MsmPlanPublic pl = msm_make_plan(h + 1, 255, 1);     // 1 byte of level budget: no precomputed levels (L = 1)
+  for (int side = 0; side < 2; side++) {
+    // L = <a_lo, G_hi> + c_L * gen_c ;  R = <a_hi, G_lo> + c_R * gen_c
+    const char* g_src = side == 0 ? G + h * 64 : G;
+    const char* a_src = side == 0 ? a : a + h * 32;
+    REEF_CUDA(cudaMemcpyAsync(s->d_tmpG, g_src, h * 64, cudaMemcpyDeviceToDevice, st));
+    REEF_CUDA(cudaMemcpyAsync(s->d_tmpG + h * 64, s->d_gc, 64, cudaMemcpyDeviceToDevice, st));
+    REEF_CUDA(cudaMemcpyAsync(s->d_tmpS, a_src, h * 32, cudaMemcpyDeviceToDevice, st));
+    REEF_CUDA(cudaMemcpyAsync(s->d_tmpS + h * 32, s->d_c + side * 32, 32, cudaMemcpyDeviceToDevice, st));
+    int rc = msm_levels_from_dev(c, s->curve, s->d_tmpG, h + 1, pl, s->d_lv, s->d_bad);
+    if (rc) return rc;
+    MsmRunArgs ar;
+    ar.plan = pl;
+    ar.d_levels = s->d_lv;
+    ar.n_bases = h + 1;
+    ar.d_scalars = s->d_tmpS;
+    ar.scalars_u32 = 0;
+    ar.n = h + 1;
+    ar.w_begin = 0;
+    ar.w_end = pl.W;
+    ar.h_out_affine = side == 0 ? out_L : out_R;
+    ar.h_out_xyzz = nullptr;
+    ar.h_extra_xyzz_mont = nullptr;
+    ar.n_extra = 0;
+    rc = msm_run(c, s->curve, ar);
+    if (rc) return rc;
+  }
+  return REEF_OK;
+}
+
+template <class SC, class CC>
+static int ipa_fold_session_t(reef_ipa* s, const uint8_t* r, const uint8_t* r_inv);
+
+extern "C" {
+
+int reef_ipa_round(reef_ipa* s, uint8_t out_L[64], uint8_t out_R[64]) {
+  REEF_REQUIRE(s && out_L && out_R, REEF_EINVAL, "reef_ipa_round: NULL argument");
+  REEF_REQUIRE(s->n >= 2, REEF_EASSERT, "reef_ipa_round: the vectors are already folded to length 1");
+  reef_ctx* c = s->ctx;
+  REEF_CTX_LIVE(c, "reef_ipa_round");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  return s->curve == 0 ? ipa_round_t<FqCfg>(s, out_L, out_R) : ipa_round_t<FpCfg>(s, out_L, out_R);
+}
+
+}  // extern "C"
+
+template <class SC, class CC>
+static int ipa_fold_session_t(reef_ipa* s, const uint8_t* r, const uint8_t* r_inv) {
+  reef_ctx* c = s->ctx;
+  cudaStream_t st = c->stream;
+  const uint64_t h = s->n / 2;
+  const int nx = s->cur ^ 1;
+  const Fe<SC> rm = fe_mont_from_le32<SC>(r), rim = fe_mont_from_le32<SC>(r_inv);
+  k_ipa_fold_scalars<SC><<<sc_cdiv(h, 128), 128, 0, st>>>((const Fe<SC>*)s->d_a[s->cur], (const Fe<SC>*)s->d_b[s->cur], h, rm, rim,
+                                                          (Fe<SC>*)s->d_a[nx], (Fe<SC>*)s->d_b[nx]);
+  REEF_LAUNCHED();
+  Scalar256 lo, hi;                              // ck' = ck_lo * r^-1 + ck_hi * r
+  for (int i = 0; i < 8; i++) {
+    lo.w[i] = (uint32_t)r_inv[4 * i] | ((uint32_t)r_inv[4 * i + 1] << 8) | ((uint32_t)r_inv[4 * i + 2] << 16) | ((uint32_t)r_inv[4 * i + 3] << 24);
+    hi.w[i] = (uint32_t)r[4 * i] | ((uint32_t)r[4 * i + 1] << 8) | ((uint32_t)r[4 * i + 2] << 16) | ((uint32_t)r[4 * i + 3] << 24);
+  }
+  k_ipa_fold<CC><<<sc_cdiv(h, 128), 128, 0, st>>>((const Affine<CC>*)s->d_G[s->cur], h, lo, hi, (Affine<CC>*)s->d_G[nx]);
+  REEF_LAUNCHED();
+  s->cur = nx;
+  s->n = h;
+  return REEF_OK;
+}
+
+extern "C" {
+
+int reef_ipa_fold(reef_ipa* s, const uint8_t r[32], const uint8_t r_inv[32]) {
+  REEF_REQUIRE(s && r && r_inv, REEF_EINVAL, "reef_ipa_fold: NULL argument");
+  REEF_REQUIRE(s->n >= 2, REEF_EASSERT, "reef_ipa_fold: the vectors are already folded to length 1");
+  const int sfield = s->curve == 0 ? 0 : 1;
+  int rc = check_canon_field(r, 1, sfield, "reef_ipa_fold: r");
+  if (!rc) rc = check_canon_field(r_inv, 1, sfield, "reef_ipa_fold: r_inv");
+  if (rc) return rc;
+  reef_ctx* c = s->ctx;
+  REEF_CTX_LIVE(c, "reef_ipa_fold");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  return s->curve == 0 ? ipa_fold_session_t<FqCfg, FpCfg>(s, r, r_inv) : ipa_fold_session_t<FpCfg, FqCfg>(s, r, r_inv);
+}
+
+int reef_ipa_finish(reef_ipa* s, uint8_t out_a[32], uint8_t out_b[32], uint8_t out_g[64]) {
+  REEF_REQUIRE(s && out_a && out_b && out_g, REEF_EINVAL, "reef_ipa_finish: NULL argument");
+  REEF_REQUIRE(s->n == 1, REEF_EASSERT, "reef_ipa_finish: rounds are not finished");
+  reef_ctx* c = s->ctx;
+  REEF_CTX_LIVE(c, "reef_ipa_finish");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  REEF_CUDA(cudaMemcpyAsync(out_a, s->d_a[s->cur], 32, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaMemcpyAsync(out_b, s->d_b[s->cur], 32, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaMemcpyAsync(out_g, s->d_G[s->cur], 64, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaStreamSynchronize(c->stream));
+  return REEF_OK;
+}
+
+void reef_ipa_free(reef_ipa* s) {
+  if (!s) return;
+  reef_ctx* c = s->ctx;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(s->d_buf);
+  }
+  delete s;
+  ctx_release(c);
 }
 
 }  // extern "C"

@@ -4,7 +4,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unknown-pragmas --expt-relaxed-constexpr
 CSRC      := reef_b200/csrc
 OBJDIR    := build
-SRCS      := $(CSRC)/api.cu $(CSRC)/poseidon.cu $(CSRC)/mle.cu $(CSRC)/msm.cu $(CSRC)/sumcheck.cu $(CSRC)/p2p.cu
+SRCS      := $(CSRC)/api.cu $(CSRC)/poseidon.cu $(CSRC)/poseidon_ro.cu $(CSRC)/mle.cu $(CSRC)/msm.cu $(CSRC)/sumcheck.cu $(CSRC)/p2p.cu $(CSRC)/cmt.cu
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(SRCS))
 HDRS      := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h $(CSRC)/*.inc include/*.h)
 LIB       := reef_b200/libreef_b200.so

@@ -602,7 +602,7 @@ def run_reef(args):
     _, _, _, prof = timed(gp, True, K, Wm, True)
     clocks = sample_clocks_stop(*clk, device=dev, windows=clock_windows) if rank == 0 else None
     e2e_ms, _, _, _ = timed(gp, False, K, Wm, False)
-    commit = commit_phase(gp, w, timed_fn, K, Wm, args.no_cpu_baseline) if world == 1 else None
+    commit = commit_phase(gp, w, timed_fn, K, Wm, args.no_cpu_baseline) if world == 1 and not args.no_commit else None
 
     # ---- the other BASELINE configs (N = 1): same pass + their commit phase, each verified
     also = []
@@ -1091,6 +1091,7 @@ def main():
     ap.add_argument("--also", default="cfg2,cfg3,cfg4,cfg5",
                     help="other BASELINE configs timed at N = 1 (value/e2e/commit, each verified) and reported under 'also'; '' = none")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg AND the verification against it")
+    ap.add_argument("--no-commit", action="store_true", help="skip the commit phase of the main workload (profiling runs)")
     ap.add_argument("--msm-large-log2", type=int, default=20, help="size of the stand-alone MSM roofline measurement (0 = skip)")
     ap.add_argument("--debug", action="store_true")
     args = ap.parse_args()

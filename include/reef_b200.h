@@ -355,6 +355,66 @@ int reef_ipa_fold(reef_ipa* s, const uint8_t r[32], const uint8_t r_inv[32]);
 int reef_ipa_finish(reef_ipa* s, uint8_t out_a[32], uint8_t out_b[32], uint8_t out_g[64]);
 void reef_ipa_free(reef_ipa* s);
 
+/* ------------------------------------------------------------------ a16: nova-snark PoseidonRO (arity 24, width 25)
+ * `PoseidonRO<Base, Scalar>::new(constants, n)`, n x absorb, squeeze(num_bits) -- commitment.rs:190-198 (the
+ * doc_commit_hash of NLDocCommitment::new over the decompressed Hyrax row commitments, num_bits = 256) and the NIFS
+ * challenge of every prove_step (inside nova-snark, framework.rs:668-675).  One neptune sponge over the field the
+ * absorbed elements live in (base_field: 0 = Fq, 1 = Fp), (R_F, R_P) = (8, 59), IOPattern [Absorb(n), Squeeze(1)];
+ * out = the digest's low num_bits bits as a canonical element of the OTHER Pasta field.  nova-snark is not under
+ * /root/reference and not pinned (Cargo.toml:12): published upstream construction, PARITY-UNPINNED.
+ *   reef_poseidon_ro         elems: n canonical 32-byte elements of base_field
+ *   reef_poseidon_ro_points  absorbs (x, y, is_infinity) of each of n_points affine points of `curve` (64 B, zeros =
+ *                            identity) -- `absorb_in_ro`; base field = the curve's coordinate field */
+int reef_poseidon_ro(reef_ctx* ctx, int base_field, const uint8_t* elems, uint64_t n, uint32_t num_bits, uint8_t out[32]);
+int reef_poseidon_ro_points(reef_ctx* ctx, int curve, const uint8_t* points, uint64_t n_points, uint32_t num_bits, uint8_t out[32]);
+
+/* The arithmetic of `NLDocCommitment::new` (commitment.rs:133-212) with the blinds INJECTED by the caller (the reference
+ * draws them from OsRng inside hyrax_gen.commit, commitment.rs:187): Hyrax row commitments of the rows x cols matrix view
+ * of the padded document codes over gens[0..cols) with blinding generator gens[cols], then doc_commit_hash = PoseidonRO
+ * over the row commitments (commitment.rs:190-198); the rows never leave the device in between.
+ * out_rows: rows x 64 B affine; out_hash: canonical Fq. */
+int reef_doc_commit_u32(reef_ctx* ctx, const reef_bases* gens, const uint32_t* doc, uint64_t rows, uint64_t cols, uint32_t entry_bits,
+                        const uint8_t* blinds, uint8_t* out_rows, uint8_t out_hash[32]);
+
+/* ------------------------------------------------------------------ (f3) the .cmt wire format
+ * bincode 1.3 (default options: fixed-width little-endian integers, u64 lengths, u8 Option tags) of `ReefCommitment`
+ * (commitment.rs:44-52), as main.rs:37-51 writes it after --commit and reads it back for --prove / --verify.  Host-only.
+ *   ReefCommitment   { nldoc: Option<NLDocCommitment>, merkle: Option<MerkleCommitment<Fq>>, orig_doc_len: usize, udoc_len: usize }
+ *   MerkleCommitment { commitment: F, tree: Vec<Vec<F>>, doc: Vec<F> }                            (merkle_tree.rs:10-15)
+ * F = 32-byte little-endian canonical repr, no length prefix.  `levels` / `level_sizes` are exactly what reef_merkle_build
+ * returns (all levels concatenated, leaves' parents first); `doc` = the padded document codes. */
+uint64_t reef_cmt_merkle_size(const uint64_t* level_sizes, uint32_t n_levels, uint64_t doc_len);
+int reef_cmt_merkle_write(const uint8_t commitment[32], const uint8_t* levels, const uint64_t* level_sizes, uint32_t n_levels,
+                          const uint64_t* doc, uint64_t doc_len, uint64_t orig_doc_len, uint8_t* out, uint64_t out_cap, uint64_t* out_len);
+/* kind: 0 = nldoc, 1 = merkle */
+int reef_cmt_probe(const uint8_t* data, uint64_t len, int* kind);
+/* Sizes are always returned (n_levels, n_nodes, doc_len); levels / level_sizes / doc may be NULL on a first sizing call.
+ * Malformed input -> REEF_EASSERT (the reference's `expect("Could not deserialize")`, main.rs:49-50). */
+int reef_cmt_merkle_read(const uint8_t* data, uint64_t len, uint8_t commitment[32], uint8_t* levels, uint64_t levels_cap, uint64_t* level_sizes,
+                         uint32_t level_cap, uint32_t* n_levels, uint64_t* n_nodes, uint64_t* doc, uint64_t doc_cap, uint64_t* doc_len,
+                         uint64_t* orig_doc_len, uint64_t* udoc_len);
+/* Compressed point as serde writes a commitment: x little-endian, parity of y in bit 255, identity = zeros. */
+int reef_point_compress(const uint8_t affine[64], uint8_t out[32]);
+/* NLDocCommitment (commitment.rs:54-68).  single_gens, hyrax_gen, cap_pk, cap_vk are nova-snark types whose serde layout
+ * lives in the un-pinned fork (Cargo.toml:12): OPAQUE byte strings serialised by the Rust side; everything Reef's own
+ * code computes (doc_poly, doc_commit, doc_decommit, doc_commit_hash, hash_salt, q_len) is encoded here. */
+typedef struct reef_cmt_nldoc {
+  const uint8_t* single_gens; uint64_t single_gens_len;
+  const uint8_t* hyrax_gen;   uint64_t hyrax_gen_len;
+  uint32_t num_vars;                       /* doc_poly.num_vars; Z is zero-padded to 2^num_vars */
+  const uint32_t* doc_codes;  uint64_t doc_len;
+  const uint8_t* row_commitments;          /* rows x 64 B affine (reef_msm_rows / reef_doc_commit_u32 output) */
+  const uint8_t* blinds;                   /* rows x 32 B */
+  uint64_t rows;
+  const uint8_t* doc_commit_hash;          /* 32 B */
+  const uint8_t* hash_salt;                /* 32 B */
+  const uint8_t* cap_pk;      uint64_t cap_pk_len;
+  const uint8_t* cap_vk;      uint64_t cap_vk_len;
+  uint64_t q_len, orig_doc_len, udoc_len;
+} reef_cmt_nldoc;
+uint64_t reef_cmt_nldoc_size(const reef_cmt_nldoc* f);
+int reef_cmt_nldoc_write(const reef_cmt_nldoc* f, uint8_t* out, uint64_t out_cap, uint64_t* out_len);
+
 #ifdef __cplusplus
 }
 #endif

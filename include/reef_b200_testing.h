@@ -22,6 +22,12 @@ int reef_hosttest_mul_wide(const uint8_t a[32], const uint8_t b[32], uint8_t out
 /* one Poseidon permutation of a width-5 state (canonical in/out) */
 int reef_hosttest_poseidon_permute(const uint8_t in[160], uint8_t out[160]);
 
+/* PoseidonRO (width 25; poseidon_ro.cu) on the HOST through the shared field code: the sponge over `n` canonical elements
+ * of field (0 = Fq, 1 = Fp), out = state[1] canonical (no truncation); and the derived constants, canonical:
+ * rc = 67 * 25 * 32 bytes, mds = 25 * 25 * 32 bytes */
+int reef_hosttest_poseidon_ro(int field, const uint8_t* elems, uint64_t n, uint8_t out[32]);
+int reef_hosttest_poseidon_ro_constants(int field, uint8_t* rc, uint8_t* mds);
+
 /* curve formulas (ec.cuh), host instantiation.  curve: 0 Pallas, 1 Vesta.  Points affine 64 B.
  * op: 0 P+Q via XYZZ full add, 1 P+Q via mixed add, 2 2P, 3 P-Q via mixed add (neg), 4 k*P (k = first 8 bytes of q) */
 int reef_hosttest_ec_op(int curve, int op, const uint8_t p[64], const uint8_t q[64], uint8_t out[64]);

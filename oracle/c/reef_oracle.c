@@ -620,3 +620,92 @@ int oracle_field_mul(int field, const uint8_t* a, const uint8_t* b, uint8_t* out
   store_le(out, f_from_mont(F, f_mul(F, f_to_mont(F, load_le(a)), f_to_mont(F, load_le(b)))));
   return 0;
 }
+
+/* ------------------------------------------------------------------ PoseidonRO (width 25)
+ * nova-snark's `PoseidonRO<Base, Scalar>` as the reference drives it at commitment.rs:190-198
+ * (doc_commit_hash over the Hyrax row commitments): neptune sponge with arity 24 (t = 25),
+ * Strength::Standard => (R_F, R_P) = (8, 59), IOPattern [Absorb(n), Squeeze(1)], Simplex mode; the
+ * digest is state[1] after the last permutation.  Textbook rounds; constants by the same Grain
+ * LFSR / Cauchy construction as above, over the field the absorbed elements live in.
+ * nova-snark is not under /root/reference (Cargo.toml:12): parity unpinned, see oracle/poseidon.py. */
+#define WT 25
+#define WRF 8
+#define WRP 59
+typedef struct { fe rc[(WRF + WRP) * WT]; fe mds[WT][WT]; int ready; } wide_t;
+static wide_t WIDE[2];
+static void wide_setup(int field) {
+  wide_t* W = &WIDE[field];
+  if (W->ready) return;
+  const field_t* F = field == 0 ? &FQ : &FP;
+  const int widths[7] = {2, 4, 12, 12, 10, 10, 30};
+  const unsigned vals[7] = {1, 1, 255, WT, WRF, WRP, (1u << 30) - 1};
+  int k = 0;
+  for (int f = 0; f < 7; f++)
+    for (int i = 0; i < widths[f]; i++) grain_state[k++] = (vals[f] >> (widths[f] - 1 - i)) & 1;
+  for (int i = 0; i < 160; i++) grain_clock();
+  int got = 0;
+  while (got < (WRF + WRP) * WT) {
+    u64 x[4] = {0, 0, 0, 0};
+    for (int b = 0; b < 255; b++) {
+      x[3] = (x[3] << 1) | (x[2] >> 63);
+      x[2] = (x[2] << 1) | (x[1] >> 63);
+      x[1] = (x[1] << 1) | (x[0] >> 63);
+      x[0] = (x[0] << 1) | (u64)grain_bit();
+    }
+    if (!ge(x, F->p)) {
+      fe c;
+      memcpy(c.v, x, 32);
+      W->rc[got++] = f_to_mont(F, c);
+    }
+  }
+  for (int i = 0; i < WT; i++)
+    for (int j = 0; j < WT; j++) W->mds[i][j] = f_inv(F, f_from_u64(F, (u64)(i + j + WT)));
+  W->ready = 1;
+}
+static void wide_permute(int field, fe* s) {
+  const wide_t* W = &WIDE[field];
+  const field_t* F = field == 0 ? &FQ : &FP;
+  int k = 0;
+  for (int r = 0; r < WRF + WRP; r++) {
+    int full = r < WRF / 2 || r >= WRF / 2 + WRP;
+    for (int i = 0; i < WT; i++) s[i] = f_add(F, s[i], W->rc[k + i]);
+    k += WT;
+    for (int i = 0; i < (full ? WT : 1); i++) {
+      fe x2 = f_mul(F, s[i], s[i]), x4 = f_mul(F, x2, x2);
+      s[i] = f_mul(F, x4, s[i]);
+    }
+    fe n[WT];
+    for (int j = 0; j < WT; j++) {
+      fe acc = f_zero();
+      for (int i = 0; i < WT; i++) acc = f_add(F, acc, f_mul(F, s[i], W->mds[i][j]));
+      n[j] = acc;
+    }
+    memcpy(s, n, sizeof(n));
+  }
+}
+/* field: 0 = Fq, 1 = Fp (the field of the absorbed elements); elems: n canonical 32-byte values;
+ * out: state[1] after the squeeze, canonical (the caller truncates to num_bits / maps to the other field) */
+int oracle_poseidon_ro(int field, const uint8_t* elems, uint64_t n, uint8_t* out) {
+  ensure_init();
+  if (n == 0 || n >> 31) return -1;
+  wide_setup(field);
+  const field_t* F = field == 0 ? &FQ : &FP;
+  uint32_t ops[2] = {(1u << 31) | (uint32_t)n, 1u};
+  uint8_t t[32];
+  tag_u128(ops, 2, 0, t);
+  fe s[WT];
+  s[0] = f_to_mont(F, load_le(t));
+  for (int i = 1; i < WT; i++) s[i] = f_zero();
+  int apos = 0;
+  for (uint64_t e = 0; e < n; e++) {
+    if (apos == WT - 1) {
+      wide_permute(field, s);
+      apos = 0;
+    }
+    s[1 + apos] = f_add(F, s[1 + apos], f_to_mont(F, load_le(elems + 32 * e)));
+    apos++;
+  }
+  wide_permute(field, s);
+  store_le(out, f_from_mont(F, s[1]));
+  return 0;
+}

@@ -133,3 +133,12 @@ def msm(curve, points, scalars, threads=1):
     lib().oracle_msm(C.c_int(cid), pb, sb, C.c_uint64(len(sb) // 32), out, C.c_int(threads))
     x, y = int.from_bytes(out.raw[:32], "little"), int.from_bytes(out.raw[32:], "little")
     return None if x == 0 and y == 0 else (x, y)
+
+
+def poseidon_ro(elems, base_field: str, scalar_p: int, num_bits: int = 256) -> int:
+    """oracle.poseidon.poseidon_ro evaluated by the C port (base_field: "fq" | "fp")."""
+    out = C.create_string_buffer(32)
+    data = _pack(elems) if not isinstance(elems, (bytes, bytearray)) else bytes(elems)
+    rc = lib().oracle_poseidon_ro(C.c_int({"fq": 0, "fp": 1}[base_field]), data, C.c_uint64(len(data) // 32), out)
+    assert rc == 0, rc
+    return (int.from_bytes(out.raw, "little") & ((1 << num_bits) - 1)) % scalar_p

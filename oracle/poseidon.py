@@ -221,3 +221,36 @@ def hash_once(elems, p: int = FQ) -> int:
 def calc_d(v: int, salt: int) -> int:
     """commitment.rs:495-510."""
     return hash_once([v, salt])
+
+
+# --------------------------------------------------------------------------- PoseidonRO (nova-snark)
+RO_ARITY = 24          # nova-snark `PoseidonConstantsCircuit` = PoseidonConstants<Scalar, U24>
+
+
+def poseidon_ro(elems, base_p: int, scalar_p: int, num_bits: int = 256) -> int:
+    """nova-snark `PoseidonRO<Base, Scalar>`: new(constants, len(elems)); absorb each; squeeze(num_bits).
+    Reference call site: commitment.rs:190-198 (doc_commit_hash over the decompressed Hyrax row
+    commitments; Base = Pallas base field Fp, Scalar = Fq, num_bits = 256).
+    nova-snark is an un-pinned git dependency that is not under /root/reference (Cargo.toml:12): this
+    restates the published upstream provider/poseidon.rs -- one neptune sponge of arity 24 in Simplex
+    mode with IOPattern [Absorb(n), Squeeze(1)], the digest's low `num_bits` bits re-assembled in the
+    Scalar field.  PARITY UNPINNED."""
+    sp = Sponge(base_p, RO_ARITY + 1)
+    sp.start([(ABSORB, len(elems)), (SQUEEZE, 1)])
+    sp.absorb([int(e) % base_p for e in elems])
+    h = sp.squeeze(1)[0]
+    sp.finish()
+    return (h & ((1 << num_bits) - 1)) % scalar_p
+
+
+def point_coordinates(P):
+    """`to_coordinates` of a nova-snark group element: (x, y, is_infinity); the identity is (0, 0, true)."""
+    return (0, 0, 1) if P is None else (int(P[0]), int(P[1]), 0)
+
+
+def doc_commit_hash(row_commitments, base_p: int, scalar_p: int) -> int:
+    """commitment.rs:190-198: RO over (x, y, is_infinity) of every row commitment, squeeze(256)."""
+    elems = []
+    for P in row_commitments:
+        elems += list(point_coordinates(P))
+    return poseidon_ro(elems, base_p, scalar_p, 256)

@@ -30,6 +30,15 @@ class NlookupOut(C.Structure):
     ]
 
 
+class CmtNldoc(C.Structure):
+    """reef_cmt_nldoc (include/reef_b200.h)"""
+    _fields_ = [("single_gens", C.c_void_p), ("single_gens_len", C.c_uint64), ("hyrax_gen", C.c_void_p), ("hyrax_gen_len", C.c_uint64),
+                ("num_vars", C.c_uint32), ("doc_codes", C.c_void_p), ("doc_len", C.c_uint64), ("row_commitments", C.c_void_p),
+                ("blinds", C.c_void_p), ("rows", C.c_uint64), ("doc_commit_hash", C.c_void_p), ("hash_salt", C.c_void_p),
+                ("cap_pk", C.c_void_p), ("cap_pk_len", C.c_uint64), ("cap_vk", C.c_void_p), ("cap_vk_len", C.c_uint64),
+                ("q_len", C.c_uint64), ("orig_doc_len", C.c_uint64), ("udoc_len", C.c_uint64)]
+
+
 def _load():
     if not os.path.exists(lib_path):
         raise ImportError(
@@ -122,6 +131,19 @@ _sig = {
     "reef_ipa_fold": (C.c_int, [_vp, _vp, _vp]),
     "reef_ipa_finish": (C.c_int, [_vp, _vp, _vp, _vp]),
     "reef_ipa_free": (None, [_vp]),
+    "reef_poseidon_ro": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, C.c_uint32, _vp]),
+    "reef_poseidon_ro_points": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, C.c_uint32, _vp]),
+    "reef_doc_commit_u32": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32, _vp, _vp, _vp]),
+    "reef_cmt_merkle_size": (C.c_uint64, [_vp, C.c_uint32, C.c_uint64]),
+    "reef_cmt_merkle_write": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp, C.c_uint64, C.c_uint64, _vp, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "reef_cmt_probe": (C.c_int, [_vp, C.c_uint64, C.POINTER(C.c_int)]),
+    "reef_cmt_merkle_read": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_uint64, _vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                                       _vp, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "reef_point_compress": (C.c_int, [_vp, _vp]),
+    "reef_cmt_nldoc_size": (C.c_uint64, [_vp]),
+    "reef_cmt_nldoc_write": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "reef_hosttest_poseidon_ro": (C.c_int, [C.c_int, _vp, C.c_uint64, _vp]),
+    "reef_hosttest_poseidon_ro_constants": (C.c_int, [C.c_int, _vp, _vp]),
     "reef_hosttest_field_op": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp]),
     "reef_hosttest_mul_wide": (C.c_int, [_vp, _vp, _vp]),
     "reef_hosttest_poseidon_permute": (C.c_int, [_vp, _vp]),

@@ -130,6 +130,20 @@ class Context:
                                        domain_separator, out, n_out))
         return _unpack(out.raw[:n_out * 32])
 
+    def poseidon_ro(self, elems, base_field: str = "fp", num_bits: int = 256) -> int:
+        """nova-snark `PoseidonRO` (arity 24): absorb `elems` (elements of base_field), squeeze(num_bits) into the other
+        Pasta field (commitment.rs:190-198; the NIFS challenge of prove_step)."""
+        out = C.create_string_buffer(32)
+        check(lib.reef_poseidon_ro(self._h, _FIELDS[base_field], _buf(_pack(elems)), len(elems), num_bits, out))
+        return int.from_bytes(out.raw, "little")
+
+    def poseidon_ro_points(self, curve, points, num_bits: int = 256) -> int:
+        """`absorb_in_ro` of every point (x, y, is_infinity), then squeeze(num_bits): doc_commit_hash (commitment.rs:190-198)"""
+        raw = bytes(points) if isinstance(points, (bytes, bytearray)) else b"".join(_pt_bytes(P) for P in points)
+        out = C.create_string_buffer(32)
+        check(lib.reef_poseidon_ro_points(self._h, _CURVES[curve], _buf(raw), len(raw) // 64, num_bits, out))
+        return int.from_bytes(out.raw, "little")
+
     # ---- tables
     def table(self, values) -> "Table":
         return Table(self, values=values)
@@ -547,6 +561,14 @@ class Bases:
         else:
             check(lib.reef_msm_rows(self.ctx._h, self._h, _buf(_pack(matrix)), rows, cols, bl, out))
         return [_pt_from(out.raw[i * 64:(i + 1) * 64]) for i in range(rows)]
+
+    def doc_commit(self, codes: "np.ndarray", rows: int, cols: int, entry_bits: int, blinds):
+        """`NLDocCommitment::new` arithmetic with injected blinds (commitment.rs:133-212): (row commitments, doc_commit_hash)."""
+        a = np.ascontiguousarray(np.asarray(codes, dtype=np.uint32).reshape(-1))
+        out, h = C.create_string_buffer(rows * 64), C.create_string_buffer(32)
+        bl = bytes(blinds) if isinstance(blinds, (bytes, bytearray)) else _pack(blinds)
+        check(lib.reef_doc_commit_u32(self.ctx._h, self._h, a.ctypes.data, rows, cols, entry_bits, _buf(bl), out, h))
+        return out.raw, int.from_bytes(h.raw, "little")
 
     def msm_dev(self, dev_ptr: int, n: int):
         out = C.create_string_buffer(64)

@@ -68,6 +68,8 @@ static void ctx_destroy(reef_ctx* c) {
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->d_pos) cudaFree(c->d_pos);
   if (c->d_lp) cudaFree(c->d_lp);
+  if (c->d_ro_fq) cudaFree(c->d_ro_fq);
+  if (c->d_ro_fp) cudaFree(c->d_ro_fp);
   for (auto& kv : c->table_cache) cudaFree(kv.second);
   if (c->shard_cache) cudaFree(c->shard_cache);
   for (void* p : c->mb_ipc_opened) cudaIpcCloseMemHandle(p);
@@ -1429,16 +1431,16 @@ int reef_msm_partial_dev(reef_ctx* c, const reef_bases* b, const void* scalars_d
   return msm_dispatch(c, b, scalars_dev, 0, n, w_begin, w_end, nullptr, out_xyzz);
 }
 
-static int msm_rows_host(reef_ctx* c, const reef_bases* b, const void* matrix, int is_u32, uint64_t rows, uint64_t cols,
-                         uint32_t entry_bits, const uint8_t* blinds, uint8_t* out) {
-  REEF_REQUIRE(c && b && matrix && out, REEF_EINVAL, "reef_msm_rows: NULL argument");
+// caller holds c->mu; d_rows_out (optional) receives the device address of the rows x 64 B affine results, valid
+// until the next call that uses the context's scratch
+static int msm_rows_host_locked(reef_ctx* c, const reef_bases* b, const void* matrix, int is_u32, uint64_t rows, uint64_t cols,
+                                uint32_t entry_bits, const uint8_t* blinds, uint8_t* out, void** d_rows_out) {
   REEF_REQUIRE(b->ctx == c, REEF_EINVAL, "reef_msm_rows: bases belong to another context");
   REEF_REQUIRE(rows >= 1 && cols >= 1, REEF_EINVAL, "reef_msm_rows: empty matrix");
   REEF_REQUIRE(cols + (blinds ? 1 : 0) <= b->n, REEF_EASSERT, "reef_msm_rows: not enough generators (assertion failed: gens.len() >= cols)");
   if (entry_bits == 0 || entry_bits > 255) entry_bits = 255;
   REEF_REQUIRE(entry_bits <= b->scalar_bits, REEF_EINVAL, "reef_msm_rows: generators registered for narrower scalars");
   REEF_REQUIRE(!blinds || b->scalar_bits == 255, REEF_EINVAL, "reef_msm_rows: blinds need generators registered with scalar_bits = 255");
-  std::lock_guard<std::mutex> lk(c->mu);
   REEF_CUDA(cudaSetDevice(c->device));
   const size_t mbytes = (size_t)rows * cols * (is_u32 ? 4 : 32);
   const size_t mpad = (mbytes + 255) & ~(size_t)255;
@@ -1463,7 +1465,15 @@ static int msm_rows_host(reef_ctx* c, const reef_bases* b, const void* matrix, i
   a.d_blinds = d_b;
   a.blind_base = cols;
   a.h_out = out;
+  a.d_rows_out = d_rows_out;
   return msm_rows_run(c, b->curve, a);
+}
+
+static int msm_rows_host(reef_ctx* c, const reef_bases* b, const void* matrix, int is_u32, uint64_t rows, uint64_t cols,
+                         uint32_t entry_bits, const uint8_t* blinds, uint8_t* out) {
+  REEF_REQUIRE(c && b && matrix && out, REEF_EINVAL, "reef_msm_rows: NULL argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  return msm_rows_host_locked(c, b, matrix, is_u32, rows, cols, entry_bits, blinds, out, nullptr);
 }
 
 int reef_msm_rows_u32(reef_ctx* c, const reef_bases* b, const uint32_t* matrix, uint64_t rows, uint64_t cols,
@@ -1483,6 +1493,102 @@ int reef_msm_combine(reef_ctx* c, int curve, const uint8_t* partials, uint32_t k
   std::lock_guard<std::mutex> lk(c->mu);
   REEF_CUDA(cudaSetDevice(c->device));
   return msm_combine(c, curve, partials, k, out);
+}
+
+// ---------------------------------------------------------------------------------------
+// a16: PoseidonRO (nova-snark), doc_commit_hash
+// ---------------------------------------------------------------------------------------
+static const uint8_t FP_LE[32] = {0x01, 0x00, 0x00, 0x00, 0xed, 0x30, 0x2d, 0x99, 0x1b, 0xf9, 0x4c, 0x09, 0xfc, 0x98, 0x46, 0x22,
+                                  0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0x00, 0x00, 0x00, 0x40};
+
+static bool lt_le32(const uint8_t* a, const uint8_t* m) {
+  for (int i = 31; i >= 0; i--) {
+    if (a[i] < m[i]) return true;
+    if (a[i] > m[i]) return false;
+  }
+  return false;
+}
+
+// digest (canonical in the base field) -> low num_bits bits -> element of the other field
+static void ro_finish(uint8_t h[32], int base_field, uint32_t num_bits) {
+  if (num_bits < 256)
+    for (uint32_t bit = num_bits; bit < 256; bit++) h[bit >> 3] &= (uint8_t)~(1u << (bit & 7));
+  const uint8_t* m = base_field == 0 ? FP_LE : FQ_LE;   // modulus of the OTHER field
+  if (!lt_le32(h, m)) {                                 // h < 2^255 < 2 m: one subtraction
+    int borrow = 0;
+    for (int i = 0; i < 32; i++) {
+      int d = (int)h[i] - (int)m[i] - borrow;
+      borrow = d < 0;
+      h[i] = (uint8_t)(d + (borrow << 8));
+    }
+  }
+}
+
+static int ro_run_host_input(reef_ctx* c, int base_field, const uint8_t* data, size_t bytes, uint64_t n_elems, int triples,
+                             uint32_t num_bits, uint8_t out[32], const char* what) {
+  REEF_REQUIRE(n_elems >= 1 && (n_elems >> 31) == 0, REEF_EINVAL, std::string(what) + ": element count out of range");
+  REEF_REQUIRE(num_bits >= 1 && num_bits <= 256, REEF_EINVAL, std::string(what) + ": num_bits out of range");
+  const uint8_t* bm = base_field == 0 ? FQ_LE : FP_LE;
+  for (size_t i = 0; i < bytes / 32; i++)
+    if (!lt_le32(data + 32 * i, bm)) return fail(REEF_EINVAL, std::string(what) + ": element " + std::to_string(i) + " is not canonical");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CTX_LIVE(c, "reef_poseidon_ro");
+  REEF_CUDA(cudaSetDevice(c->device));
+  void* base;
+  int rc = ctx_scratch(c, bytes + 32, &base);
+  if (rc) return rc;
+  char* d_in = (char*)base + 32;
+  REEF_CUDA(cudaMemcpyAsync(d_in, data, bytes, cudaMemcpyHostToDevice, c->stream));
+  rc = launch_poseidon_ro(c, base_field, d_in, n_elems, triples, base);
+  if (rc) return rc;
+  REEF_CUDA(cudaMemcpyAsync(out, base, 32, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaStreamSynchronize(c->stream));
+  ro_finish(out, base_field, num_bits);
+  return REEF_OK;
+}
+
+int reef_poseidon_ro(reef_ctx* c, int base_field, const uint8_t* elems, uint64_t n, uint32_t num_bits, uint8_t out[32]) {
+  REEF_REQUIRE(c && elems && out, REEF_EINVAL, "reef_poseidon_ro: NULL argument");
+  REEF_REQUIRE(base_field == 0 || base_field == 1, REEF_EINVAL, "reef_poseidon_ro: unknown field");
+  return ro_run_host_input(c, base_field, elems, (size_t)n * 32, n, 0, num_bits, out, "reef_poseidon_ro");
+}
+
+int reef_poseidon_ro_points(reef_ctx* c, int curve, const uint8_t* points, uint64_t n_points, uint32_t num_bits, uint8_t out[32]) {
+  REEF_REQUIRE(c && points && out, REEF_EINVAL, "reef_poseidon_ro_points: NULL argument");
+  REEF_REQUIRE(curve == REEF_CURVE_PALLAS || curve == REEF_CURVE_VESTA, REEF_EINVAL, "reef_poseidon_ro_points: unknown curve");
+  const int base_field = curve == REEF_CURVE_PALLAS ? 1 : 0;     // coordinates of Pallas points live in Fp
+  return ro_run_host_input(c, base_field, points, (size_t)n_points * 64, 3 * n_points, 1, num_bits, out, "reef_poseidon_ro_points");
+}
+
+int reef_doc_commit_u32(reef_ctx* c, const reef_bases* gens, const uint32_t* doc, uint64_t rows, uint64_t cols, uint32_t entry_bits,
+                        const uint8_t* blinds, uint8_t* out_rows, uint8_t out_hash[32]) {
+  REEF_REQUIRE(c && gens && doc && out_rows && out_hash, REEF_EINVAL, "reef_doc_commit_u32: NULL argument");
+  REEF_REQUIRE(gens->curve == REEF_CURVE_PALLAS, REEF_EINVAL, "reef_doc_commit_u32: the document commitment lives on Pallas (G1)");
+  REEF_REQUIRE((3 * rows) >> 31 == 0, REEF_EINVAL, "reef_doc_commit_u32: too many rows");
+  if (entry_bits == 0 || entry_bits > 32) entry_bits = 32;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CTX_LIVE(c, "reef_doc_commit_u32");
+  void* d_rows = nullptr;
+  int rc = msm_rows_host_locked(c, gens, doc, 1, rows, cols, entry_bits, blinds, out_rows, &d_rows);
+  if (rc) return rc;
+  // the row commitments are still in the context's scratch; the document codes in scratch2 are spent: digest goes there
+  rc = launch_poseidon_ro(c, 1, d_rows, 3 * rows, 1, c->scratch2);
+  if (rc) return rc;
+  REEF_CUDA(cudaMemcpyAsync(out_hash, c->scratch2, 32, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaStreamSynchronize(c->stream));
+  ro_finish(out_hash, 1, 256);
+  return REEF_OK;
+}
+
+int reef_hosttest_poseidon_ro(int field, const uint8_t* elems, uint64_t n, uint8_t out[32]) {
+  if (!elems || !out || n == 0 || (field != 0 && field != 1)) return REEF_EINVAL;
+  poseidon_ro_host(field, elems, n, out);
+  return REEF_OK;
+}
+int reef_hosttest_poseidon_ro_constants(int field, uint8_t* rc, uint8_t* mds) {
+  if (!rc || !mds || (field != 0 && field != 1)) return REEF_EINVAL;
+  poseidon_ro_constants_host(field, rc, mds);
+  return REEF_OK;
 }
 
 }  // extern "C"

@@ -156,6 +156,8 @@ struct reef_ctx {
   reef::PoseidonTables* d_pos = nullptr; // Montgomery-form tables in global memory
   reef::PoseidonLpTables* d_lp = nullptr; // tables of the lane-parallel transcript permutation
   reef::SpongeTags tags;
+  void* d_ro_fq = nullptr;               // PoseidonRO (width 25) tables, uploaded at first use (poseidon_ro.cu)
+  void* d_ro_fp = nullptr;
   // reusable device scratch (grown on demand)
   void* scratch = nullptr;
   size_t scratch_bytes = 0;

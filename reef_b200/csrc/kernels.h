@@ -27,6 +27,11 @@ int sponge_state_bytes();
 int launch_sponge_step(reef_ctx* c, void* d_state, int op, const void* d_in, uint32_t n, const uint8_t* tag_le,
                        void* d_out);
 
+// ---- poseidon_ro.cu (width-25 sponge over either field; field 0 = Fq, 1 = Fp)
+int launch_poseidon_ro(reef_ctx* c, int field, const void* d_in, uint64_t n, int triples, void* d_out);
+void poseidon_ro_host(int field, const uint8_t* elems, uint64_t n, uint8_t out[32]);
+void poseidon_ro_constants_host(int field, uint8_t* rc_out, uint8_t* mds_out);
+
 // ---- mle.cu
 struct NlookupArgs {
   int tag;                 // 0 = nl, 1 = nldoc, 2 = nlhybrid
@@ -108,6 +113,7 @@ struct MsmRowsArgs {
   const void* d_blinds;      // device: rows x 32 B or NULL
   uint64_t blind_base;       // index of the blinding generator among the registered bases
   uint8_t* h_out;            // rows x 64 B
+  void** d_rows_out = nullptr; // optional: receives the device address of the affine rows (in the context's scratch)
 };
 int msm_rows_run(reef_ctx* c, int curve, const MsmRowsArgs& a);
 

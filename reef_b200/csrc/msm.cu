@@ -816,7 +816,8 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
   REEF_LAUNCHED();
   scope.reset();
   REEF_CUDA(cudaMemcpyAsync(a.h_out, d_out, (size_t)a.rows * sizeof(Affine<C>), cudaMemcpyDeviceToHost, s));
-  REEF_CUDA(cudaStreamSynchronize(s));
+  if (a.d_rows_out) *a.d_rows_out = d_out;
+  else REEF_CUDA(cudaStreamSynchronize(s));     // a caller that keeps working on the rows synchronises itself
   return REEF_OK;
 }
 

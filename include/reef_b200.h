@@ -335,6 +335,11 @@ int reef_ipa_fold_bases(reef_ctx* ctx, int curve, const uint8_t* bases, uint64_t
  *                  `bound_poly_var_top` consumes the variables in)
  *   reef_vec_axpy  out = a * x + y  (y may be NULL) */
 int reef_eq_table(reef_ctx* ctx, int field, const uint8_t* r, uint32_t k, uint8_t* out);
+/* a3: the NIFS cross term of prove_step (nova-snark `R1CSShape::commit_T`, reached from framework.rs:668-675):
+ *   T = Az1 o Bz2 + Az2 o Bz1 - u1 Cz2 - u2 Cz1,  abc1 = Az1 | Bz1 | Cz1 (3n elements, from reef_r1cs_spmv), abc2 likewise.
+ * commit(T) is reef_msm over it; the folds W1 + r W2, E1 + r T are reef_vec_axpy; the challenge r is reef_poseidon_ro. */
+int reef_nova_cross_term(reef_ctx* ctx, int field, const uint8_t* abc1, const uint8_t* abc2, const uint8_t u1[32], const uint8_t u2[32], uint64_t n,
+                         uint8_t* out);
 int reef_vec_axpy(reef_ctx* ctx, int field, const uint8_t a[32], const uint8_t* x, const uint8_t* y, uint64_t n, uint8_t* out);
 
 /* Inner-product argument, prover side (commitment.rs:371-393 `hyrax_gen.prove_eval` -> nova-snark ipa_pc; also the

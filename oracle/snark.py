@@ -392,3 +392,35 @@ def _lc_sum(lcs, p):
         for k, c in lc.items():
             out[k] = (out.get(k, 0) + c) % p
     return out
+
+
+# ------------------------------------------------------------------------------------ NIFS (the fold of prove_step)
+def nifs_ro_elements(pp_digest, U1, U2, comm_T, base_p):
+    """absorb order of `NIFS::prove` (published upstream nova-snark nifs.rs / r1cs.rs `absorb_in_ro`; PARITY-UNPINNED):
+    pp digest | U1: comm_W, comm_E as (x, y, is_infinity), u, each X entry as four 64-bit limbs | U2: comm_W, X | comm_T"""
+    def pt(P):
+        return [0, 0, 1] if P is None else [int(P[0]), int(P[1]), 0]
+    e = [pp_digest % base_p] + pt(U1["comm_W"]) + pt(U1["comm_E"]) + [U1["u"] % base_p]
+    for x in U1["X"]:
+        e += [(x >> (64 * k)) & (2 ** 64 - 1) for k in range(4)]
+    e += pt(U2["comm_W"]) + [x % base_p for x in U2["X"]] + pt(comm_T)
+    return e
+
+
+def nifs_prove(curve, shape: R1CSShape, gens, pp_digest, U1, W1, U2, W2, msm=None, num_challenge_bits=128):
+    """Folds the fresh pair (U2, W2) (u = 1, E = 0) into the running relaxed pair (U1, W1): the cross term
+    T = Az1 o Bz2 + Az2 o Bz1 - u1 Cz2 - u2 Cz1, comm_T, r = PoseidonRO(...), then X, u, comm_W, comm_E, W, E <- . + r .
+    Reached once per curve from every prove_step (framework.rs:668-675)."""
+    from .poseidon import poseidon_ro
+    p, base_p = curve.order, curve.p
+    msm = msm or curve.msm
+    z1, z2 = shape.z(W1["W"], U1["u"], U1["X"]), shape.z(W2["W"], 1, U2["X"])
+    a1, b1, c1 = (shape.mul(M, z1, p) for M in (shape.A, shape.B, shape.C))
+    a2, b2, c2 = (shape.mul(M, z2, p) for M in (shape.A, shape.B, shape.C))
+    T = [(x1 * y2 + x2 * y1 - U1["u"] * w2 - w1) % p for x1, y1, w1, x2, y2, w2 in zip(a1, b1, c1, a2, b2, c2)]
+    comm_T = msm(T, gens[:len(T)])
+    r = poseidon_ro(nifs_ro_elements(pp_digest, U1, U2, comm_T, base_p), base_p, p, num_challenge_bits)
+    U = {"comm_W": curve.add(U1["comm_W"], curve.mul(r, U2["comm_W"])), "comm_E": curve.add(U1["comm_E"], curve.mul(r, comm_T)),
+         "u": (U1["u"] + r) % p, "X": [(a + r * b) % p for a, b in zip(U1["X"], U2["X"])]}
+    W = {"W": [(a + r * b) % p for a, b in zip(W1["W"], W2["W"])], "E": [(a + r * b) % p for a, b in zip(W1["E"], T)]}
+    return comm_T, r, U, W

@@ -105,6 +105,14 @@ __device__ __forceinline__ F select_fe(bool c, const F& a, const F& b) {
   return r;
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// may become resident while its stream predecessor still runs; pdl_wait() blocks until that predecessor has
+// completed and its writes are visible (a no-op for an ordinary launch), pdl_trigger() lets the stream successor
+// start being scheduled.  Rule kept throughout: every kernel of such a chain calls pdl_wait() before its first
+// access to memory another kernel of the chain writes or reads-then-overwrites.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // warp-wide sum (mod p) of one field element per lane; every lane gets the total
 template <class C>
 __device__ __forceinline__ Fe<C> warp_sum_fe(Fe<C> v) {

@@ -99,6 +99,27 @@ __device__ __forceinline__ void block_sum(Fq* vals, Fq* smem /* NV * NTHREADS/32
 // ---------------------------------------------------------------------------------------
 static constexpr int TR_THREADS = LP_PERM_THREADS;
 
+// Launch as a programmatic dependent of the stream predecessor (see pdl_wait / pdl_trigger in common.cuh): the launch
+// latency and the kernel's constant-only prologue overlap the tail of the predecessor.  REEF_PDL=0 turns it off.
+static bool pdl_enabled() {
+  static const bool on = !(getenv("REEF_PDL") && atoi(getenv("REEF_PDL")) == 0);
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 __device__ __forceinline__ void tr_load_state(LpPermShared* sh, const NlState* st) {
   if (threadIdx.x < 60) sh->S[threadIdx.x / 12][threadIdx.x % 12] = st->sponge[threadIdx.x / 12][threadIdx.x % 12];
 }
@@ -147,6 +168,8 @@ __global__ void __launch_bounds__(TR_THREADS) k_nl_begin(NlState* st, const Fq* 
                                                          const PoseidonLpTables* __restrict__ T, uint32_t rank, uint32_t world) {
   __shared__ LpPermShared sh;
   lp_perm_init(&sh, T);
+  pdl_wait();      // predecessor complete and visible; only then let the successor become resident (at most two
+  pdl_trigger();   // consecutive kernels of the chain are ever co-resident)
   u32 seq = 0;
   if (threadIdx.x < 9) sh.S[0][threadIdx.x] = lp_limb_of(tag_canon.v, threadIdx.x);
   // last_q[j] = prev_running_q[ell-1-j]   (r1cs.rs:2318-2319 passes the reversed vector); off the transcript's path
@@ -186,6 +209,8 @@ __global__ void __launch_bounds__(TR_THREADS) k_nl_begin(NlState* st, const Fq* 
 // c_g = prod_{t < bit_off} sel(bit_t(rank), lq[t]).
 __global__ void k_eq_tables(const NlState* __restrict__ st, uint32_t ell, uint32_t hb, Fq* __restrict__ A,
                             uint64_t a_len, Fq* __restrict__ B, uint64_t b_len, uint32_t bit_off, uint32_t rank) {
+  pdl_wait();      // predecessor complete and visible; only then let the successor become resident (at most two
+  pdl_trigger();   // consecutive kernels of the chain are ever co-resident)
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a_len + b_len) return;
   const Fq one = fe_one<FqCfg>();
@@ -294,6 +319,8 @@ k_sweep(const void* Tin, uint64_t L_in, Fq* Tout, const NlState* __restrict__ st
   const uint64_t half = L >> 1;
   const uint64_t task = (uint64_t)blockIdx.x * SWEEP_WARPS + warp;
   const uint64_t base = task * 32u * ppl;
+  pdl_wait();      // predecessor complete and visible; only then let the successor become resident (at most two
+  pdl_trigger();   // consecutive kernels of the chain are ever co-resident)
   Fq r;
   if constexpr (FOLD) r = st->r_mont;
   typename std::conditional<SMALL, Wide10, Wide17>::type acc0, acc1;
@@ -383,7 +410,7 @@ static int launch_sweep(reef_ctx* c, const void* Tin, uint64_t L_in, Fq* Tout, c
   while (ppl < 32 && half / (32ull * (ppl * 2)) >= want_tasks) ppl *= 2;
   const uint64_t tasks = half / (32ull * ppl);   // >= 32, a multiple of SWEEP_WARPS
   const uint32_t nblk = (uint32_t)(tasks / SWEEP_WARPS);
-  k_sweep<U32IN, FOLD><<<nblk, SWEEP_WARPS * 32, 0, c->stream>>>(Tin, L_in, Tout, st, A, B, partials, ppl);
+  REEF_CUDA(launch_dep(k_sweep<U32IN, FOLD>, dim3(nblk), dim3(SWEEP_WARPS * 32), 0, c->stream, Tin, L_in, Tout, st, A, B, partials, ppl));
   *nblk_out = nblk;
   REEF_LAUNCHED();
   return REEF_OK;
@@ -404,6 +431,8 @@ k_round(NlState* st, const Fq* __restrict__ partials, uint32_t nblk, const void*
   __shared__ TrScratch ts;
   __shared__ Fq red[3 * ROUND_THREADS / 32];
   lp_perm_init(&sh, K);
+  pdl_wait();      // predecessor complete and visible; only then let the successor become resident (at most two
+  pdl_trigger();   // consecutive kernels of the chain are ever co-resident)
   tr_load_state(&sh, st);
   const uint64_t half = L >> 1;
   Fq acc[3];
@@ -467,6 +496,8 @@ k_tail(NlState* st, const void* __restrict__ Tin, uint64_t L_in, int do_fold, co
   __shared__ LpPermShared sh;
   __shared__ TrScratch ts;
   lp_perm_init(&sh, K);
+  pdl_wait();      // predecessor complete and visible; only then let the successor become resident (at most two
+  pdl_trigger();   // consecutive kernels of the chain are ever co-resident)
   tr_load_state(&sh, st);
   uint64_t L = do_fold ? (L_in >> 1) : L_in;   // <= CHUNK
   const Fq a0 = A[0];
@@ -608,7 +639,7 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
     ProfScope ps(c, PROF_NL_SETUP, N);
     k_nl_begin<<<1, TR_THREADS, exclusive_smem(c, (const void*)k_nl_begin, 0), s>>>(st, d_query, a.n_query, tag, d_prevq, ell, d_q, m, d_pos, d_w, c->d_lp, 0, 1);
     REEF_LAUNCHED();
-    k_eq_tables<<<ceil_div_u(a_len + b_len, 128), 128, 0, s>>>(st, ell, hb, d_A, a_len, d_B, b_len, 0, 0);
+    REEF_CUDA(launch_dep(k_eq_tables, dim3(ceil_div_u(a_len + b_len, 128)), dim3(128), 0, s, (const NlState*)st, ell, hb, d_A, a_len, d_B, b_len, 0u, 0u));
     REEF_LAUNCHED();
   }
 
@@ -625,7 +656,8 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
         if (rc) return rc;
       }
       ProfScope ps(c, PROF_ROUND, L);
-      k_round<U32IN><<<1, ROUND_THREADS, exclusive_smem(c, (const void*)k_round<U32IN>, 0), s>>>(st, d_part, nblk, a.d_table, L, d_A, a_cur, d_pos, d_w, m, i, c->d_lp);
+      REEF_CUDA(launch_dep(k_round<U32IN>, dim3(1), dim3(ROUND_THREADS), exclusive_smem(c, (const void*)k_round<U32IN>, 0), s, st, (const Fq*)d_part, nblk,
+                           a.d_table, L, d_A, a_cur, d_pos, d_w, m, i, (const PoseidonLpTables*)c->d_lp));
       REEF_LAUNCHED();
     } else {
       {
@@ -635,7 +667,8 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
         if (rc) return rc;
       }
       ProfScope ps(c, PROF_ROUND, L);
-      k_round<false><<<1, ROUND_THREADS, exclusive_smem(c, (const void*)k_round<false>, 0), s>>>(st, d_part, nblk, d_fold, L, d_A, a_cur, d_pos, d_w, m, i, c->d_lp);
+      REEF_CUDA(launch_dep(k_round<false>, dim3(1), dim3(ROUND_THREADS), exclusive_smem(c, (const void*)k_round<false>, 0), s, st, (const Fq*)d_part, nblk,
+                           (const void*)d_fold, L, d_A, a_cur, d_pos, d_w, m, i, (const PoseidonLpTables*)c->d_lp));
       REEF_LAUNCHED();
       t_cur = d_fold;
     }
@@ -645,13 +678,17 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
   // tail: fold with the last sweep challenge (if any) and finish
   const size_t tail_smem = (size_t)(2 * CHUNK + 3 * TAIL_THREADS / 32) * sizeof(Fq);
   std::unique_ptr<ProfScope> tail_scope(new ProfScope(c, PROF_TAIL, L));
+  const PoseidonLpTables* lpt = (const PoseidonLpTables*)c->d_lp;
   if (n_sweeps == 0) {
-    k_tail<U32IN><<<1, TAIL_THREADS, exclusive_smem(c, (const void*)k_tail<U32IN>, tail_smem), s>>>(st, a.d_table, N, 0, d_A, d_B, d_pos, d_w, m, 0, c->d_lp);
+    REEF_CUDA(launch_dep(k_tail<U32IN>, dim3(1), dim3(TAIL_THREADS), exclusive_smem(c, (const void*)k_tail<U32IN>, tail_smem), s, st, a.d_table, N, 0,
+                         (const Fq*)d_A, (const Fq*)d_B, (const uint64_t*)d_pos, (const Fq*)d_w, m, 0u, lpt));
   } else if (n_sweeps == 1) {
     // L is now 2^h: the table to fold is still the caller's (length 2L)
-    k_tail<U32IN><<<1, TAIL_THREADS, exclusive_smem(c, (const void*)k_tail<U32IN>, tail_smem), s>>>(st, a.d_table, 2 * L, 1, d_A, d_B, d_pos, d_w, m, n_sweeps, c->d_lp);
+    REEF_CUDA(launch_dep(k_tail<U32IN>, dim3(1), dim3(TAIL_THREADS), exclusive_smem(c, (const void*)k_tail<U32IN>, tail_smem), s, st, a.d_table, 2 * L, 1,
+                         (const Fq*)d_A, (const Fq*)d_B, (const uint64_t*)d_pos, (const Fq*)d_w, m, n_sweeps, lpt));
   } else {
-    k_tail<false><<<1, TAIL_THREADS, exclusive_smem(c, (const void*)k_tail<false>, tail_smem), s>>>(st, t_cur, 2 * L, 1, d_A, d_B, d_pos, d_w, m, n_sweeps, c->d_lp);
+    REEF_CUDA(launch_dep(k_tail<false>, dim3(1), dim3(TAIL_THREADS), exclusive_smem(c, (const void*)k_tail<false>, tail_smem), s, st, t_cur, 2 * L, 1,
+                         (const Fq*)d_A, (const Fq*)d_B, (const uint64_t*)d_pos, (const Fq*)d_w, m, n_sweeps, lpt));
   }
   tail_scope.reset();
   REEF_LAUNCHED();

@@ -32,6 +32,13 @@ static constexpr uint32_t K_FIRST = 8;      // entries per thread in the first a
                                             // 16 once that still leaves > 2048 threads per SM (halves the partials to combine)
 static constexpr uint32_t K_NEXT = 128;     // partial points per WARP in the combine passes (4 per lane + shuffle tree)
 
+// REEF_MSM_TMA=1: first accumulation pass with TMA-staged point tiles (k_accum_first_tma); default: plain gathers
+static bool msm_tma_enabled() {
+  static const bool on = getenv("REEF_MSM_TMA") && atoi(getenv("REEF_MSM_TMA")) != 0;
+  return on;
+}
+static constexpr size_t MSM_TMA_SMEM = 2 * 4 * 128 * 64;
+
 struct MsmPlan {
   uint32_t c;          // window bits
   uint32_t W;          // windows per scalar
@@ -258,6 +265,110 @@ __global__ void __launch_bounds__(128) k_accum_first(const uint32_t* __restrict_
     xyzz_add_affine<C>(acc, q, (v >> 31) != 0);
   }
   st_xyzz(out + p, acc);
+}
+
+// The same pass with the gathered points staged through shared memory by the TMA engine (`cp.async.bulk`, SASS
+// UBLKCP): every thread reads the point references of its part, posts one 64-byte bulk copy per point into its own
+// slots of a shared tile, all completing on one mbarrier per stage, and adds the points out of shared memory.
+// Two stages of TMA_STAGE points per thread are in flight from the start, so the L2 / HBM latency of the gather is
+// paid once per stage instead of once per point.  A/B against k_accum_first: profiles/r02_summary.md (REEF_MSM_TMA).
+static constexpr uint32_t TMA_STAGE = 4;          // points per thread and stage (2 stages x 128 threads x 4 x 64 B = 64 KiB)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <class C>
+__global__ void __launch_bounds__(128) k_accum_first_tma(const uint32_t* __restrict__ sorted,
+                                                         const uint32_t* __restrict__ start, const uint32_t* __restrict__ cnt,
+                                                         const uint32_t* __restrict__ part_off, uint32_t nb, uint32_t n_parts,
+                                                         uint32_t kfirst, const Affine<C>* __restrict__ levels,
+                                                         XYZZ<C>* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  Affine<C>* tile = reinterpret_cast<Affine<C>*>(tma_smem);                    // [2][TMA_STAGE][128]
+  __shared__ __align__(8) uint64_t bar[2];
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 128);
+    mbar_init(&bar[1], 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t first = 0, last = 0;
+  if (p < n_parts) {
+    uint32_t b;
+    locate_part(part_off, nb, p, b);
+    const uint32_t j = p - part_off[b];
+    first = start[b] + j * kfirst;
+    last = min(start[b] + cnt[b], first + kfirst);
+  }
+  uint32_t neg[2] = {0, 0};
+  // stage s of round t covers entries [first + (2 t + s) * TMA_STAGE, + TMA_STAGE)
+  auto post = [&](uint32_t s, uint32_t e0) {
+    uint32_t k = 0, bits = 0;
+    uint32_t refs[TMA_STAGE];
+#pragma unroll
+    for (uint32_t i = 0; i < TMA_STAGE; i++) {
+      if (e0 + i < last) {
+        refs[i] = sorted[e0 + i];
+        bits |= (refs[i] >> 31) << i;
+        k++;
+      }
+    }
+    mbar_arrive_expect_tx(&bar[s], k * (uint32_t)sizeof(Affine<C>));
+#pragma unroll
+    for (uint32_t i = 0; i < TMA_STAGE; i++)
+      if (i < k) bulk_g2s(tile + ((size_t)s * TMA_STAGE + i) * 128 + threadIdx.x, levels + (refs[i] & 0x7fffffffu), (uint32_t)sizeof(Affine<C>), &bar[s]);
+    neg[s] = bits;
+  };
+  post(0, first);
+  post(1, first + TMA_STAGE);
+  XYZZ<C> acc = xyzz_inf<C>();
+  const uint32_t rounds = (kfirst + 2 * TMA_STAGE - 1) / (2 * TMA_STAGE);      // the same for every thread of the grid
+#pragma unroll 1
+  for (uint32_t t = 0; t < rounds; t++) {
+#pragma unroll 1
+    for (uint32_t s = 0; s < 2; s++) {
+      const uint32_t e0 = first + (2 * t + s) * TMA_STAGE;
+      mbar_wait(&bar[s], t & 1);
+#pragma unroll 1
+      for (uint32_t i = 0; i < TMA_STAGE; i++) {
+        if (e0 + i < last) {
+          const Affine<C>* q = tile + ((size_t)s * TMA_STAGE + i) * 128 + threadIdx.x;
+          Affine<C> a;
+          a.x = q->x;
+          a.y = q->y;
+          xyzz_add_affine<C>(acc, a, ((neg[s] >> i) & 1) != 0);
+        }
+      }
+      if (t + 1 < rounds) {
+        __syncthreads();                                 // every thread is done with stage s of this round
+        post(s, e0 + 2 * TMA_STAGE);
+      }
+    }
+  }
+  if (p < n_parts) st_xyzz(out + p, acc);
 }
 
 // combine passes: LANES lanes per (bucket, chunk of K partials): the lanes stride over the chunk, then a
@@ -659,8 +770,18 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
   uint32_t n_parts = h_tm[2], max_cnt = h_tm[3];   // parts of pass 1, largest per-bucket part count
   scope.reset(new ProfScope(c, PROF_MSM_ACCUM, n_entries));
   if (n_parts) {
-    k_accum_first<C><<<cdiv(n_parts, 128), 128, 0, s>>>(sorted, start, cnt, poff[0], nb, n_parts, kfirst, (const Affine<C>*)a.d_levels,
-                                                       parts[0]);
+    if (msm_tma_enabled()) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        REEF_CUDA(cudaFuncSetAttribute((const void*)k_accum_first_tma<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MSM_TMA_SMEM));
+        attr_set = true;
+      }
+      k_accum_first_tma<C><<<cdiv(n_parts, 128), 128, MSM_TMA_SMEM, s>>>(sorted, start, cnt, poff[0], nb, n_parts, kfirst,
+                                                                        (const Affine<C>*)a.d_levels, parts[0]);
+    } else {
+      k_accum_first<C><<<cdiv(n_parts, 128), 128, 0, s>>>(sorted, start, cnt, poff[0], nb, n_parts, kfirst, (const Affine<C>*)a.d_levels,
+                                                         parts[0]);
+    }
     REEF_LAUNCHED();
   }
   int cur = 0;
@@ -686,11 +807,16 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
   k_bitsum_partial<C><<<dim3(nblk, P.c, P.G), 256, 0, s>>>(buckets, P.B, bpt, bitpart);
   REEF_LAUNCHED();
   if (a.n_extra) REEF_CUDA(cudaMemcpyAsync(extra, a.h_extra_xyzz_mont, (size_t)a.n_extra * sizeof(XYZZ<C>), cudaMemcpyHostToDevice, s));
-  const bool want_xyzz = a.h_out_xyzz || a.p2p_combine;
-  k_bitsum_final<C><<<1, 1024, 0, s>>>(bitpart, nblk, P.c, P.G, P.c * P.L, want_xyzz ? res_xyzz : nullptr,
-                                       (a.h_out_affine && !a.p2p_combine) ? res_aff : nullptr, extra, a.n_extra);
+  // The single result leaves the device as XYZZ and becomes affine on the HOST (one inversion by the shared
+  // __host__ __device__ field code): the binary-Euclid inversion is ~110 k cycles of one GPU thread at the very end
+  // of a latency chain, a few microseconds on a host core.  (The multi-GPU combine stays on the device.)
+  const bool host_affine = a.h_out_affine && !a.p2p_combine;
+  const bool want_xyzz = a.h_out_xyzz || a.p2p_combine || host_affine;
+  k_bitsum_final<C><<<1, 1024, 0, s>>>(bitpart, nblk, P.c, P.G, P.c * P.L, want_xyzz ? res_xyzz : nullptr, nullptr, extra, a.n_extra);
   REEF_LAUNCHED();
   scope.reset();
+  XYZZ<C> h_mont;
+  if (host_affine) REEF_CUDA(cudaMemcpyAsync(&h_mont, res_xyzz, sizeof(XYZZ<C>), cudaMemcpyDeviceToHost, s));
   if (a.p2p_combine) {
     // multi-GPU: every rank holds the partial of its own windows; one 128-byte all-gather through the peer
     // mailboxes (a kernel of this library, P2P stores over NVLink) and the combine, all stream-ordered
@@ -701,13 +827,19 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
     if (rc) return rc;
     k_combine<C><<<1, 32, 0, s>>>(gathered, c->mb_world, res_aff);
     REEF_LAUNCHED();
+    if (a.h_out_affine) REEF_CUDA(cudaMemcpyAsync(a.h_out_affine, res_aff, sizeof(Affine<C>), cudaMemcpyDeviceToHost, s));
   } else if (a.h_out_xyzz) {
     k_xyzz_from_mont<C><<<1, 32, 0, s>>>(res_xyzz);
     REEF_LAUNCHED();
     REEF_CUDA(cudaMemcpyAsync(a.h_out_xyzz, res_xyzz, sizeof(XYZZ<C>), cudaMemcpyDeviceToHost, s));
   }
-  if (a.h_out_affine) REEF_CUDA(cudaMemcpyAsync(a.h_out_affine, res_aff, sizeof(Affine<C>), cudaMemcpyDeviceToHost, s));
   REEF_CUDA(cudaStreamSynchronize(s));
+  if (host_affine) {
+    Affine<C> aff = xyzz_to_affine<C>(h_mont);
+    aff.x = from_mont<C>(aff.x);
+    aff.y = from_mont<C>(aff.y);
+    memcpy(a.h_out_affine, &aff, sizeof(Affine<C>));
+  }
   return REEF_OK;
 }
 

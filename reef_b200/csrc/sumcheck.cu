@@ -252,6 +252,20 @@ __global__ void k_axpy(Fe<C> a_mont, const Fe<C>* __restrict__ x, const Fe<C>* _
   st256(out + i, v);
 }
 
+// NIFS cross term of two relaxed R1CS instance/witness pairs (nova-snark `R1CSShape::commit_T`, reached from every
+// prove_step, framework.rs:668-675):  T = Az1 o Bz2 + Az2 o Bz1 - u1 Cz2 - u2 Cz1   (canonical in / out)
+template <class C>
+__global__ void k_cross_term(const Fe<C>* __restrict__ abc1, const Fe<C>* __restrict__ abc2, Fe<C> u1_mont, Fe<C> u2_mont, uint64_t n,
+                             Fe<C>* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Fe<C> az1 = to_mont<C>(ld256(abc1 + i)), az2 = to_mont<C>(ld256(abc2 + i));
+  Fe<C> t = fe_add<C>(mont_mul<C>(az1, ld256(abc2 + n + i)), mont_mul<C>(az2, ld256(abc1 + n + i)));
+  t = fe_sub<C>(t, mont_mul<C>(u1_mont, ld256(abc2 + 2 * n + i)));
+  t = fe_sub<C>(t, mont_mul<C>(u2_mont, ld256(abc1 + 2 * n + i)));
+  st256(out + i, t);
+}
+
 // ---------------------------------------------------------------------------------------
 // Inner-product argument rounds (commitment.rs:371-393 -> nova-snark ipa_pc, [UPSTREAM, unpinned]):
 //   c_L = <a_lo, b_hi>, c_R = <a_hi, b_lo>;   a' = a_lo r + a_hi r^-1,  b' = b_lo r^-1 + b_hi r
@@ -632,7 +646,39 @@ static int axpy_t(reef_ctx* c, const uint8_t* a, const uint8_t* x, const uint8_t
   return REEF_OK;
 }
 
+template <class C>
+static int cross_term_t(reef_ctx* c, const uint8_t* abc1, const uint8_t* abc2, const uint8_t* u1, const uint8_t* u2, uint64_t n, uint8_t* out) {
+  void* base;
+  int rc = ctx_scratch(c, (size_t)n * 32 * 7 + 256, &base);
+  if (rc) return rc;
+  Fe<C>* d_1 = (Fe<C>*)base;
+  Fe<C>* d_2 = d_1 + 3 * n;
+  Fe<C>* d_o = d_2 + 3 * n;
+  cudaStream_t st = c->stream;
+  REEF_CUDA(cudaMemcpyAsync(d_1, abc1, (size_t)n * 96, cudaMemcpyHostToDevice, st));
+  REEF_CUDA(cudaMemcpyAsync(d_2, abc2, (size_t)n * 96, cudaMemcpyHostToDevice, st));
+  k_cross_term<C><<<sc_cdiv(n, 128), 128, 0, st>>>(d_1, d_2, fe_mont_from_le32<C>(u1), fe_mont_from_le32<C>(u2), n, d_o);
+  REEF_LAUNCHED();
+  REEF_CUDA(cudaMemcpyAsync(out, d_o, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+  REEF_CUDA(cudaStreamSynchronize(st));
+  return REEF_OK;
+}
+
 extern "C" {
+
+int reef_nova_cross_term(reef_ctx* c, int field, const uint8_t* abc1, const uint8_t* abc2, const uint8_t u1[32], const uint8_t u2[32], uint64_t n,
+                         uint8_t* out) {
+  REEF_REQUIRE(c && abc1 && abc2 && u1 && u2 && out && n >= 1, REEF_EINVAL, "reef_nova_cross_term: NULL / empty argument");
+  REEF_REQUIRE(field == 0 || field == 1, REEF_EINVAL, "reef_nova_cross_term: field must be 0 (Fq) or 1 (Fp)");
+  int rc = check_canon_field(abc1, 3 * n, field, "reef_nova_cross_term: Az1|Bz1|Cz1");
+  if (!rc) rc = check_canon_field(abc2, 3 * n, field, "reef_nova_cross_term: Az2|Bz2|Cz2");
+  if (!rc) rc = check_canon_field(u1, 1, field, "reef_nova_cross_term: u1");
+  if (!rc) rc = check_canon_field(u2, 1, field, "reef_nova_cross_term: u2");
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CUDA(cudaSetDevice(c->device));
+  return field == 0 ? cross_term_t<FqCfg>(c, abc1, abc2, u1, u2, n, out) : cross_term_t<FpCfg>(c, abc1, abc2, u1, u2, n, out);
+}
 
 int reef_eq_table(reef_ctx* c, int field, const uint8_t* r, uint32_t k, uint8_t* out) {
   REEF_REQUIRE(c && (r || k == 0) && out, REEF_EINVAL, "reef_eq_table: NULL argument");

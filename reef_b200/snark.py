@@ -203,3 +203,62 @@ def snark_prove(ctx, curve: str, shape, gens, gen_c, comm_W, comm_E, W, E, u, X,
     ipa_E = ipa_prove(ctx, curve, gens, gen_c, E, ex, tr)
     return {"outer": polys_o, "claims": (claim_Az, claim_Bz, claim_Cz, claim_E), "inner": polys_i, "eval_W": eval_W,
             "ipa_W": ipa_W, "ipa_E": ipa_E}
+
+
+# ------------------------------------------------------------------------------------ NIFS (the fold of prove_step)
+def _limbs64(x: int):
+    return [(x >> (64 * k)) & (2 ** 64 - 1) for k in range(4)]
+
+
+def nifs_ro_elements(pp_digest: int, U1, U2, comm_T, base_p: int):
+    """What `NIFS::prove` absorbs (nova-snark nifs.rs, published upstream; PARITY-UNPINNED): the public-parameter digest,
+    the relaxed instance U1 = (comm_W, comm_E, u, X) -- points as (x, y, is_infinity), u as a base-field element, every X
+    entry as four 64-bit limbs --, the fresh instance U2 = (comm_W, X) with X as base-field elements, then comm_T:
+    24 elements for two public IOs (nova's NUM_FE_FOR_RO)."""
+    def pt(P):
+        return [0, 0, 1] if P is None else [int(P[0]), int(P[1]), 0]
+    e = [pp_digest % base_p] + pt(U1["comm_W"]) + pt(U1["comm_E"]) + [U1["u"] % base_p]
+    for x in U1["X"]:
+        e += _limbs64(x)
+    e += pt(U2["comm_W"]) + [x % base_p for x in U2["X"]] + pt(comm_T)
+    return e
+
+
+def nifs_prove(ctx, curve: str, shape, gens_bases, pp_digest: int, U1, W1, U2, W2, num_challenge_bits: int = 128):
+    """`NIFS::prove` (nova-snark, once per curve inside every prove_step, framework.rs:668-675) on the device:
+    six sparse products, the cross term T, commit(T) (MSM over the registered generators `gens_bases`), the Poseidon
+    random-oracle challenge r, the folds W1 + r W2 / E1 + r T, and the two-term commitment folds.
+    U1: dict(comm_W, comm_E, u, X); W1: dict(W, E); U2: dict(comm_W, X); W2: dict(W).
+    Returns (comm_T, r, folded U, folded W)."""
+    p, field = ORDER[curve], SCALAR_FIELD[curve]
+    base_p = ORDER["vesta" if curve == "pallas" else "pallas"]
+    nc = shape.num_cons
+    z1 = shape.z(W1["W"], U1["u"], U1["X"])
+    z2 = shape.z(W2["W"], 1, U2["X"])
+    abc1 = [v for M in (shape.A, shape.B, shape.C) for v in ctx.r1cs_spmv(*_csr(M, nc), z1, field)]
+    abc2 = [v for M in (shape.A, shape.B, shape.C) for v in ctx.r1cs_spmv(*_csr(M, nc), z2, field)]
+    out = C.create_string_buffer(nc * 32)
+    check(lib.reef_nova_cross_term(ctx._h, _FIELDS[field], _buf(_pack(abc1)), _buf(_pack(abc2)), _buf(_pack([U1["u"]])), _buf(_pack([1])), nc, out))
+    T = _unpack(out.raw)
+    comm_T = gens_bases.msm(T)
+    # the random oracle hashes coordinates: elements of the curve's BASE field (= the other curve's scalar field)
+    ro_field = "fp" if curve == "pallas" else "fq"
+    r = ctx.poseidon_ro(nifs_ro_elements(pp_digest, U1, U2, comm_T, base_p), ro_field, num_challenge_bits)
+    W = axpy(ctx, field, r, W2["W"], W1["W"])
+    E = axpy(ctx, field, r, T, W1["E"])
+    comm_W = _lincomb(ctx, curve, U1["comm_W"], U2["comm_W"], r)
+    comm_E = _lincomb(ctx, curve, U1["comm_E"], comm_T, r)
+    U = {"comm_W": comm_W, "comm_E": comm_E, "u": (U1["u"] + r) % p, "X": [(a + r * b) % p for a, b in zip(U1["X"], U2["X"])]}
+    return comm_T, r, U, {"W": W, "E": E}
+
+
+def _lincomb(ctx, curve, P1, P2, r):
+    """P1 + r P2 on the device (a generic two-term MSM); None = the identity"""
+    pts, sc = [], []
+    if P1 is not None:
+        pts.append(P1)
+        sc.append(1)
+    if P2 is not None:
+        pts.append(P2)
+        sc.append(r)
+    return ctx.msm(curve, pts, sc) if pts else None

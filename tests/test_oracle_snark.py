@@ -93,3 +93,37 @@ def test_cap_circuit_r1cs_is_calc_d():
     assert shape.is_sat(W, [0] * shape.num_cons, 1, X, FQ)
     W[5] = (W[5] + 1) % FQ
     assert not shape.is_sat(W, [0] * shape.num_cons, 1, X, FQ)
+
+
+def test_oracle_nifs_fold_keeps_the_relaxed_instance_satisfied():
+    """algebra pin of oracle.snark.nifs_prove (the checker of tests/test_gpu_nifs.py): two chained folds; the folded
+    pair satisfies the relaxed R1CS and its commitments open to the folded vectors; the challenge has 128 bits"""
+    import random
+    from oracle import snark as N
+    from oracle.curves import PALLAS
+    curve, p = PALLAS, PALLAS.order
+    rnd = random.Random(11)
+    nc, nv, num_io = 4, 8, 2
+    A = [(i, rnd.randrange(nv - nc), rnd.randrange(1, p)) for i in range(nc)] + [(i, nv + 1, 3) for i in range(nc)]
+    B = [(i, rnd.randrange(nv - nc), rnd.randrange(1, p)) for i in range(nc)] + [(i, nv, 1) for i in range(nc)]
+    Cm = [(i, nv - nc + i, 1) for i in range(nc)]
+    shape = N.R1CSShape(nc, nv, num_io, A, B, Cm)
+    gens = curve.multiples(nv)
+
+    def fresh():
+        X = [rnd.randrange(p) for _ in range(num_io)]
+        z = [rnd.randrange(p) for _ in range(nv - nc)] + [0] * nc + [1] + X + [0] * (nv - 1 - num_io)
+        for i in range(nc):
+            z[nv - nc + i] = sum(v * z[c] for r, c, v in A if r == i) * sum(v * z[c] for r, c, v in B if r == i) % p
+        Wv = z[:nv]
+        assert shape.is_sat(Wv, [0] * nc, 1, X, p)
+        return {"comm_W": curve.msm(Wv, gens), "X": X}, {"W": Wv}
+
+    U1, W1 = fresh()
+    U1, W1 = dict(U1, comm_E=None, u=1), dict(W1, E=[0] * nc)
+    for _ in range(2):
+        U2, W2 = fresh()
+        comm_T, r, U1, W1 = N.nifs_prove(curve, shape, gens, 12345, U1, W1, U2, W2)
+        assert 0 < r < (1 << 128)
+        assert shape.is_sat(W1["W"], W1["E"], U1["u"], U1["X"], p)
+        assert U1["comm_W"] == curve.msm(W1["W"], gens) and U1["comm_E"] == curve.msm(W1["E"], gens[:nc])

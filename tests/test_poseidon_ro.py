@@ -61,13 +61,6 @@ def test_no_gpu_means_an_error_not_a_fallback():
 
 
 # ----------------------------------------------------------------------------------------- GPU tier
-@pytest.fixture(scope="module")
-def ctx():
-    c = reef_b200.Context(0)
-    yield c
-    c.close()
-
-
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,fid,bp,sp", FIELDS)
 def test_gpu_poseidon_ro_matches_the_oracle(ctx, name, fid, bp, sp):

@@ -6,18 +6,16 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 import reef_b200
-from oracle.curves import PALLAS
+import workloads as WL
 
 peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "profiles", "peak_modmul.json")))["modmul_per_s"]
 ctx = reef_b200.Context(0)
 names = ["sweep_first", "sweep_fold", "round", "tail", "nl_setup", "msm_sort", "msm_accum", "msm_reduce", "poseidon"]
 lgs = [int(a) for a in sys.argv[1:]] or [14, 16, 18, 20]
-t0 = time.time()
-pts_all = PALLAS.multiples(1 << max(lgs))
-print(f"generated {len(pts_all)} bases in {time.time() - t0:.1f} s", flush=True)
+pts_all = WL.generators("pallas", 1 << max(lgs))      # disk-cached k*G (build/gens)
 for lg in lgs:
     n = 1 << lg
-    b = ctx.bases("pallas", pts_all[:n])
+    b = ctx.bases("pallas", pts_all[:64 * n])
     raw = np.random.default_rng(lg).integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
     raw[:, 3] &= (1 << 61) - 1
     dev = torch.from_numpy(raw.view(np.int64)).cuda()

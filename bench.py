@@ -190,6 +190,8 @@ class GpuPass:
         for s in w["sc"]:
             for k in list(s):
                 s[k] = self._pin(s[k])
+        self.pair_host = [{"p": self._pin(np.concatenate([s["Wp"], s["Tp"]])), "s": self._pin(np.concatenate([s["Ws"], s["Ts"]]))} for s in w["sc"]]
+        self.pairs = world < 4          # W and T of a fold as the two rows of ONE row-batched MSM per curve
         self.tree = None
         self._mk_out()
 
@@ -225,6 +227,8 @@ class GpuPass:
         if self.world > 1:
             self._connect_mailboxes()
         self.sc_dev = [{k: t.from_numpy(v.view(np.int64)).cuda() for k, v in s.items()} for s in w["sc"]]
+        # commit(W) and commit(T) of a fold use the same commitment key: resident as the two rows of one matrix
+        self.pair_dev = [{"p": t.cat([d["Wp"], d["Tp"]]).contiguous(), "s": t.cat([d["Ws"], d["Ts"]]).contiguous()} for d in self.sc_dev]
         t.cuda.synchronize()
 
     def _doc_shard(self):
@@ -300,19 +304,29 @@ class GpuPass:
             self.check(self.lib.reef_msm(ctx._h, bases._h, host_arr.ctypes.data, n, out))
         return out.raw
 
+    def _msm_pair(self, bases, dev_tensor, host_arr, n, resident):
+        """commit(W), commit(T) of one fold over the same key: one row-batched MSM (2 x n), 2 x 64 bytes back"""
+        out = C.create_string_buffer(128)
+        ctx = bases.ctx
+        if resident:
+            self.check(self.lib.reef_msm_rows_dev(ctx._h, bases._h, C.c_void_p(dev_tensor.data_ptr()), 2, n, out))
+        else:
+            self.check(self.lib.reef_msm_rows(ctx._h, bases._h, host_arr.ctypes.data, 2, n, None, out))
+        return out.raw
+
     def _exchange_points(self, outs, owners):
-        """One all-gather per pass: every rank ends up with all commitments (64 B each)."""
+        """One all-gather per pass: every rank ends up with all commitments (64 B each, 128 B per W/T pair)."""
         t = self.torch
-        k = len(outs)
-        mine = bytearray(k * 64)
+        k, sz = len(outs), (128 if self.pairs else 64)
+        mine = bytearray(k * sz)
         for i, o in enumerate(outs):
             if o is not None:
-                mine[i * 64:(i + 1) * 64] = o
+                mine[i * sz:(i + 1) * sz] = o
         buf = t.frombuffer(mine, dtype=t.uint8).cuda()
-        allb = t.empty(self.world * k * 64, dtype=t.uint8, device="cuda")
+        allb = t.empty(self.world * k * sz, dtype=t.uint8, device="cuda")
         self.dist.all_gather_into_tensor(allb, buf)
         host = allb.cpu().numpy().tobytes()
-        return [outs[i] if owners[i] is None else host[(owners[i] * k + i) * 64:(owners[i] * k + i + 1) * 64] for i in range(k)]
+        return [outs[i] if owners[i] is None else host[(owners[i] * k + i) * sz:(owners[i] * k + i + 1) * sz] for i in range(k)]
 
     def run_collect(self, resident: bool = True):
         """One untimed pass that keeps EVERY output in cpu_pass(collect=...)'s layout for the bit-for-bit comparison."""
@@ -364,11 +378,23 @@ class GpuPass:
                     prev_doc = self.pool["doc"].submit(self._nlookup, "nldoc", doc_tab, qd[0], qd[1], prev_doc, first_doc).result()
                 prev_nl = f_nl.result()
             sc, scd = w["sc"][s], (self.sc_dev[s] if resident else None)
-            for key, pool, n in (("Wp", "pri", w["n_pri"]), ("Ws", "sec", w["n_sec"]), ("Tp", "pri2", w["n_pri"]), ("Ts", "sec2", w["n_sec"])):
-                args = (self.bases[key], scd[key] if resident else None, sc[key], n, resident)
+            if self.pairs:
+                jobs = [("Wp", "pri", w["n_pri"], "p"), ("Ws", "sec", w["n_sec"], "s")]
+            else:
+                jobs = [("Wp", "pri", w["n_pri"], None), ("Ws", "sec", w["n_sec"], None), ("Tp", "pri2", w["n_pri"], None), ("Ts", "sec2", w["n_sec"], None)]
+            for key, pool, n, pair in jobs:
                 owner = None if self.world == 1 else len(owners) % self.world
+                skip = os.environ.get("REEF_BENCH_SKIP_MSM")          # interference experiments only (never a bench value)
+                if skip == "1" or (skip == "last" and s == w["steps"] - 1) or (skip == "first" and s < w["steps"] - 1):
+                    msm_futs.append(None)
+                    owners.append(owner)
+                    continue
                 if owner is None or owner == self.rank:
-                    msm_futs.append(self.pool[pool].submit(self._msm_local, *args))
+                    if pair:
+                        msm_futs.append(self.pool[pool].submit(self._msm_pair, self.bases[key], self.pair_dev[s][pair] if resident else None,
+                                                               self.pair_host[s][pair], n, resident))
+                    else:
+                        msm_futs.append(self.pool[pool].submit(self._msm_local, self.bases[key], scd[key] if resident else None, sc[key], n, resident))
                 else:
                     msm_futs.append(None)
                 owners.append(owner)
@@ -376,6 +402,7 @@ class GpuPass:
         ds = [f.result() for f in self.d_futs]
         if self.world > 1:
             outs = self._exchange_points(outs, owners)
+        outs = [o[i:i + 64] for o in outs if o is not None for i in range(0, len(o), 64)]       # one 64-byte point per commitment
         if not resident:
             for t in (doc_tab, T_tab, hyb_tab):
                 if t is not None:
@@ -428,10 +455,11 @@ class GpuPass:
         if self.mode == "merkle":
             return le32(self.ctxs["doc"].merkle_raw(w["udoc"])[0])       # the whole tree comes back (it is what the .cmt stores)
         rows, cols = WL.hyrax_dims(self.ell_doc)
-        out = C.create_string_buffer(rows * 64)
-        self.check(self.lib.reef_msm_rows_u32(self.ctxs["pri"]._h, self.hy_bases._h, self.h_doc.ctypes.data, rows, cols, w["bits"],
-                                              self.hy_blinds, out))
-        return out.raw
+        out, h = C.create_string_buffer(rows * 64), C.create_string_buffer(32)
+        # NLDocCommitment::new (commitment.rs:133-212): Hyrax rows + doc_commit_hash = PoseidonRO over the rows
+        self.check(self.lib.reef_doc_commit_u32(self.ctxs["pri"]._h, self.hy_bases._h, self.h_doc.ctypes.data, rows, cols, w["bits"],
+                                                self.hy_blinds, out, h))
+        return out.raw + h.raw
 
 
 def sample_clocks_start():
@@ -514,7 +542,9 @@ def run_reef(args):
         torch.cuda.set_device(0)
     dev = local if world > 1 else 0
     # one context (= one CUDA stream + one host thread) per independent chain of a fold
-    ctxs = {k: reef_b200.Context(dev) for k in ("nl", "doc", "pri", "sec", "pri2", "sec2", "aux")}
+    # the sum-check contexts are latency-critical (highest stream priority), the commitment contexts are not
+    prio = os.environ.get("REEF_BENCH_PRIO", "1") != "0"
+    ctxs = {k: reef_b200.Context(dev, (k in ("nl", "doc")) if prio else None) for k in ("nl", "doc", "pri", "sec", "pri2", "sec2", "aux")}
     w = make_workload(args.workload, seed_shift=0, world=world)
     gp = GpuPass(ctxs, w, rank, world, dist)
     gp.prepare_queries()
@@ -633,6 +663,7 @@ def run_reef(args):
     # ---- multi-GPU: what sharding buys, measured on the same ranks
     multi = multi_gpu_extras(args, ctxs, gp, w, rank, world, dist, timed_fn, K, Wm, ms) if world > 1 else None
     transcript = transcript_object(ctxs["aux"], w, gp, prof, K, clocks) if rank == 0 else None
+    openings = opening_phases(ctxs, w, gp, K, args.no_cpu_baseline) if world == 1 and not args.no_openings else None
 
     value = w["doc_len"] / (ms / K / 1e3)
     e2e_value = w["doc_len"] / (e2e_ms / K / 1e3)
@@ -703,8 +734,10 @@ def run_reef(args):
         "data": "synthetic",
         "config": {"workload": args.workload + ": " + w["desc"], "l2": "256 MiB buffer written between steps (L2 flush)",
                    "timing": "CUDA events: start on an idle stream, end = latest of the library streams; max over ranks",
-                   "streams": "7 contexts/streams: nl sum-check | nldoc sum-check | commit(W) Pallas | commit(W) Vesta | commit(T) Pallas | commit(T) Vesta | calc_d "
-                              "(fold i+1 sum-checks overlap fold i commitments; commit(T) does not wait for commit(W); calc_d does not gate the next fold)",
+                   "streams": "contexts/streams: nl sum-check | nldoc sum-check (both highest stream priority) | fold commitments Pallas | Vesta | calc_d: "
+                              "commit(W) and commit(T) of a fold share the commitment key and run as the two rows of ONE row-batched MSM per curve "
+                              "(reef_msm_rows_dev; at N >= 4 GPUs four separate MSMs round-robin over the ranks); fold i+1 sum-checks overlap fold i "
+                              "commitments; calc_d does not gate the next fold",
                    "verified": verified,
                    "parallelism": (f"1 document of {w['doc_len']} chars: nldoc sum-check sharded by low index bits x{world} "
                                    f"(96 bytes per rank per round; the round kernels themselves store them into the peers' mailboxes over NVLink and "
@@ -717,6 +750,8 @@ def run_reef(args):
     }
     if commit:
         out["commit"] = commit
+    if openings:
+        out["openings"] = openings
     if also:
         out["also"] = also
     if multi:
@@ -767,6 +802,108 @@ def transcript_object(ctx, w, gp, prof, K, clocks):
             "non_permutation_us_per_round": round(max(0.0, tr_ms * 1e3 - perms_all * per / mhz) / max(1, rounds_all), 2)}
 
 
+class ShaTranscript:
+    """Stand-in Fiat-Shamir transcript of the opening proofs (nova-snark's own lives in the un-vendored crate and stays
+    with the Rust caller): SHA-256 chaining, the same absorb / squeeze call pattern on both arms."""
+
+    def __init__(self, label: bytes, modulus: int):
+        import hashlib
+        self.h = hashlib
+        self.state = hashlib.sha256(b"reef-b200-bench-transcript" + label).digest()
+        self.p, self.round = modulus, 0
+
+    def absorb(self, label: bytes, data: bytes):
+        self.state = self.h.sha256(self.state + len(label).to_bytes(4, "little") + label + len(data).to_bytes(8, "little") + data).digest()
+
+    def absorb_scalars(self, label: bytes, xs):
+        self.absorb(label, b"".join(int(x).to_bytes(32, "little") for x in xs))
+
+    def absorb_point(self, label: bytes, P):
+        self.absorb(label, bytes(64) if P is None else int(P[0]).to_bytes(32, "little") + int(P[1]).to_bytes(32, "little"))
+
+    def squeeze(self, label: bytes) -> int:
+        self.round += 1
+        d0 = self.h.sha256(self.state + b"\x00" + label + self.round.to_bytes(4, "little")).digest()
+        d1 = self.h.sha256(self.state + b"\x01" + label + self.round.to_bytes(4, "little")).digest()
+        self.state = d0
+        return int.from_bytes(d0 + d1, "little") % self.p
+
+
+def opening_phases(ctxs, w, gp, K, no_cpu):
+    """The opening proofs behind `prove_consistency` / `CompressedSNARK::prove` (commitment.rs:214-285, 371-393;
+    framework.rs:695-698) that follow the folds: Hyrax prove_eval on the resident document table and one inner-product
+    argument of the fold-commitment size, through the library's device-resident IPA session (reef_ipa_*: two MSMs and
+    the a / b / generator folds per round on the device, transcript on the host).  Wall-clock per proof; proofs compared
+    with the oracle's (same transcript).  nova-snark's conventions are parity-unpinned."""
+    import reef_b200
+    from reef_b200 import snark as G
+    out = {}
+    ctx = ctxs["pri"]
+    rnd = random.Random(4242)
+
+    def pts(raw, n):
+        return [(int.from_bytes(raw[i * 64:i * 64 + 32], "little"), int.from_bytes(raw[i * 64 + 32:i * 64 + 64], "little")) for i in range(n)]
+
+    def timed_wall(fn):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            res = fn()
+        return res, (time.perf_counter() - t0) / K * 1e3
+
+    # (1) one IPA of the primary fold-commitment size (the openings of W and E inside the compressed SNARK)
+    n = w["n_pri"]
+    raw = WL.generators("pallas", n + 1)
+    gens_raw, gen_c = raw[:64 * n], pts(raw[64 * n:], 1)[0]
+    a = [rnd.randrange(FQ) for _ in range(n)]
+    b = [rnd.randrange(FQ) for _ in range(n)]
+    got, ms = timed_wall(lambda: G.ipa_prove(ctx, "pallas", gens_raw, gen_c, a, b, ShaTranscript(b"ipa", FQ)))
+    entry = {"n": n, "rounds": n.bit_length() - 1, "ms": round(ms, 3), "msm_per_round": 2,
+             "what": "reef_ipa_begin/round/fold/finish: L, R multi-scalar multiplications and the folds of a, b and the generators on the device"}
+    if not no_cpu:
+        from oracle import cport, snark as N
+        from oracle.curves import PALLAS
+        cm = lambda sc, p_: cport.msm("pallas", p_, sc, threads=cport.max_threads())
+        t0 = time.perf_counter()
+        exp = N.ipa_prove(PALLAS, pts(gens_raw, n), gen_c, a, b, ShaTranscript(b"ipa", FQ), cm)
+        entry["cpu_baseline"] = {"seconds": round(time.perf_counter() - t0, 3), "cores": cport.max_threads(), "kind": "port",
+                                 "sample": "oracle/snark.py: MSMs by oracle/c on all threads, scalar folds in Python (not a tuned baseline)"}
+        if got != exp:
+            raise ParityError("inner-product argument differs from the oracle")
+        entry["verified"] = "proof (L, R vectors, a_hat) == oracle under the same transcript"
+    out["ipa"] = entry
+    # (2) Hyrax prove_eval of the committed document at a random point (prove_consistency, commitment.rs:371-393)
+    if w["mode"] != "merkle":
+        ell = gp.ell_doc
+        rows, cols = WL.hyrax_dims(ell)
+        graw = WL.generators("pallas", cols + 1)
+        hg, hc = graw[:64 * cols], pts(graw[64 * cols:], 1)[0]
+        q = [rnd.randrange(FQ) for _ in range(ell)]
+        tab = ctxs["pri"].table_u32(w["udoc"])
+        (v, proof), ms = timed_wall(lambda: G.hyrax_prove_eval(ctx, tab, rows, cols, hg, hc, q, ShaTranscript(b"hyrax", FQ)))
+        entry = {"shape": f"{rows} x {cols}", "ms": round(ms, 3),
+                 "what": "LZ = L^T M over the resident u32 document table (reef_hyrax_lz) + one IPA of length 2^right"}
+        if not no_cpu:
+            t0 = time.perf_counter()
+            m2 = w["udoc"].reshape(rows, cols).astype(object)
+            kl = rows.bit_length() - 1
+            Lv = N.eq_table(q[:kl], FQ)
+            LZ = [int(x) % FQ for x in (np.asarray(Lv, dtype=object) @ m2)]
+            Rv = N.eq_table(q[kl:], FQ)
+            ev = N.inner(LZ, Rv, FQ)
+            tr = ShaTranscript(b"hyrax", FQ)
+            tr.absorb_scalars(b"v", [ev])
+            exp = N.ipa_prove(PALLAS, pts(hg, cols), hc, LZ, Rv, tr, cm)
+            entry["cpu_baseline"] = {"seconds": round(time.perf_counter() - t0, 3), "cores": cport.max_threads(), "kind": "port",
+                                     "sample": "oracle/snark.py (numpy object mat-vec + oracle/c MSMs; not a tuned baseline)"}
+            if v != ev or proof != exp:
+                raise ParityError("Hyrax prove_eval differs from the oracle")
+            entry["verified"] = "evaluation and IPA proof == oracle under the same transcript"
+        tab.free()
+        out["hyrax_prove_eval"] = entry
+    return out
+
+
 def commit_phase(gp, w, timed_fn, K, Wm, no_cpu):
     """--commit of the same document (run_committer, framework.rs:62-79) from HOST codes: e2e time, verified."""
     gp.commit_setup()
@@ -795,15 +932,56 @@ def commit_phase(gp, w, timed_fn, K, Wm, no_cpu):
                 if got[r * 64:(r + 1) * 64] != (bytes(64) if P is None else le32(P[0]) + le32(P[1])):
                     raise ParityError(f"Hyrax row commitment {r} differs from the oracle")
             cpu_s = (time.perf_counter() - t0) * rows / len(sample)
-            ver = f"{len(sample)} of {rows} row commitments (blinds included) == oracle/c"
+            # doc_commit_hash: the oracle's PoseidonRO over ALL row commitments (x, y, is_infinity) the GPU produced
+            t1 = time.perf_counter()
+            elems = b"".join(got[r * 64:(r + 1) * 64] + le32(1 if got[r * 64:(r + 1) * 64] == bytes(64) else 0) for r in range(rows))
+            exp_h = cport.poseidon_ro(elems, "fp", FQ, 256)
+            cpu_s += time.perf_counter() - t1
+            if int.from_bytes(got[rows * 64:rows * 64 + 32], "little") != exp_h:
+                raise ParityError("doc_commit_hash (PoseidonRO over the row commitments) differs from the oracle")
+            ver = (f"{len(sample)} of {rows} row commitments (blinds included) == oracle/c; doc_commit_hash == oracle/c PoseidonRO over "
+                   f"all {rows} rows (parity-unpinned construction, see DESIGN.md)")
         cpu = {"seconds": round(cpu_s, 3), "cores": cport.max_threads(), "kind": "port",
-               "sample": "whole tree" if w["mode"] == "merkle" else "sampled rows scaled to all rows"}
+               "sample": "whole tree" if w["mode"] == "merkle" else "sampled rows scaled to all rows + the whole PoseidonRO (textbook rounds)"}
     ms, _ = timed_fn(gp.commit, K, Wm)
-    kind = "merkle_tree.rs:25-78 Poseidon tree" if w["mode"] == "merkle" else "commitment.rs:187 Hyrax rows %d x %d" % WL.hyrax_dims(gp.ell_doc)
+    kind = ("merkle_tree.rs:25-78 Poseidon tree" if w["mode"] == "merkle" else
+            "commitment.rs:133-212 Hyrax rows %d x %d + doc_commit_hash (PoseidonRO)" % WL.hyrax_dims(gp.ell_doc))
+    cmt = cmt_bytes(gp, w, got)
     if w["mode"] != "merkle":
         gp.hy_bases.free()
     return {"what": kind, "e2e_ms": round(ms / K, 3), "chars_per_s": round(w["doc_len"] / (ms / K / 1e3), 1), "verified": ver, "cpu_baseline": cpu,
-            "not_included": "PoseidonRO over the row commitments (commitment.rs:190-198) and the CAP key setup: see DESIGN.md"}
+            "cmt": cmt, "not_included": "CAP key setup (SpartanSNARK::setup, nova-snark) and the OsRng draws: see DESIGN.md"}
+
+
+def cmt_bytes(gp, w, got):
+    """(f3) the .cmt payload of this commitment through the library's bincode writer (host-only, untimed for `e2e_ms`)."""
+    import reef_b200
+    lib, check = reef_b200.lib, reef_b200._lib.check
+    t0 = time.perf_counter()
+    if w["mode"] == "merkle":
+        ctx = gp.ctxs["doc"]
+        root, levels = ctx.merkle_raw(w["udoc"])
+        sizes, nl = ctx.last_level_sizes, ctx.last_n_levels
+        t0 = time.perf_counter()
+        d = np.ascontiguousarray(w["udoc"].astype(np.uint64))
+        size = int(lib.reef_cmt_merkle_size(sizes.ctypes.data, nl, len(d)))
+        out, n = np.empty(size, dtype=np.uint8), C.c_uint64()
+        check(lib.reef_cmt_merkle_write(le32(root), levels, sizes.ctypes.data, nl, d.ctypes.data, len(d), w["doc_len"], out.ctypes.data, size, C.byref(n)))
+        return {"kind": "ReefCommitment{merkle}", "bytes": int(n.value), "write_ms": round((time.perf_counter() - t0) * 1e3, 2)}
+    from reef_b200._lib import CmtNldoc
+    rows, cols = WL.hyrax_dims(gp.ell_doc)
+    f = CmtNldoc()
+    keep = [C.create_string_buffer(got[:rows * 64], rows * 64), C.create_string_buffer(gp.hy_blinds, rows * 32),
+            C.create_string_buffer(got[rows * 64:rows * 64 + 32], 32), C.create_string_buffer(le32(w["salt"]), 32)]
+    f.num_vars, f.doc_codes, f.doc_len = gp.ell_doc, w["udoc"].ctypes.data, len(w["udoc"])
+    f.row_commitments, f.blinds, f.rows = C.addressof(keep[0]), C.addressof(keep[1]), rows
+    f.doc_commit_hash, f.hash_salt = C.addressof(keep[2]), C.addressof(keep[3])
+    f.q_len, f.orig_doc_len, f.udoc_len = gp.ell_doc, w["doc_len"], len(w["udoc"])
+    size = int(lib.reef_cmt_nldoc_size(C.byref(f)))
+    out, n = np.empty(size, dtype=np.uint8), C.c_uint64()
+    check(lib.reef_cmt_nldoc_write(C.byref(f), out.ctypes.data, size, C.byref(n)))
+    return {"kind": "ReefCommitment{nldoc}", "bytes": int(n.value), "write_ms": round((time.perf_counter() - t0) * 1e3, 2),
+            "note": "nova-snark-owned members (generators, CAP keys) are opaque byte strings supplied by the Rust side: empty here"}
 
 
 def multi_gpu_extras(args, ctxs, gp, w, rank, world, dist, timed_fn, K, Wm, ms_sharded):
@@ -818,6 +996,7 @@ def multi_gpu_extras(args, ctxs, gp, w, rank, world, dist, timed_fn, K, Wm, ms_s
         gp1 = GpuPass(ctxs, w, 0, 1, None)
         gp1.q_nl, gp1.q_doc = gp.q_nl, gp.q_doc
         gp1.sc_dev = gp.sc_dev
+        gp1.pair_dev = gp.pair_dev
         gp1.T_tab = gp.T_tab
         gp1.doc_tab = ctxs["doc"].table_u32(w["udoc"])
         streams = [torch.cuda.ExternalStream(c.stream) for c in ctxs.values()]
@@ -1091,6 +1270,7 @@ def main():
     ap.add_argument("--also", default="cfg2,cfg3,cfg4,cfg5",
                     help="other BASELINE configs timed at N = 1 (value/e2e/commit, each verified) and reported under 'also'; '' = none")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg AND the verification against it")
+    ap.add_argument("--no-openings", action="store_true", help="skip the opening-proof phases (IPA, Hyrax prove_eval)")
     ap.add_argument("--no-commit", action="store_true", help="skip the commit phase of the main workload (profiling runs)")
     ap.add_argument("--msm-large-log2", type=int, default=20, help="size of the stand-alone MSM roofline measurement (0 = skip)")
     ap.add_argument("--debug", action="store_true")

@@ -46,6 +46,13 @@ int reef_abi_version(void);
 uint64_t reef_launch_count(void);
 const char* reef_last_error(void);
 int reef_init(int device, reef_ctx** out);
+/* Same, with the context's stream at the highest (latency_critical != 0) or lowest CUDA stream priority: the contexts that
+ * run the Fiat-Shamir chains (sum-checks) are latency-critical, the ones that run the fold commitments are not. */
+int reef_init_prio(int device, int latency_critical, reef_ctx** out);
+/* SMs the context's kernels may run on.  A background context (latency_critical = 0) lives in a CUDA green context that
+ * owns all but REEF_RESERVE_SMS (default 12) SMs, so that the single-CTA Fiat-Shamir kernels of the latency-critical
+ * contexts always find an empty SM; when the driver cannot partition the device this is the whole chip. */
+uint32_t reef_ctx_sm_count(const reef_ctx* ctx);
 void reef_shutdown(reef_ctx* ctx);
 int reef_sync(reef_ctx* ctx);
 /* The CUDA stream (cudaStream_t) every launch of this context goes to; for event timing. */
@@ -250,6 +257,12 @@ uint32_t reef_bases_windows(const reef_bases* b);
 uint32_t reef_bases_window_bits(const reef_bases* b);
 
 /* out = sum_{i<n} scalars[i] * bases[i]   (n <= registered n; scalars canonical, < 2^scalar_bits) */
+/* (f2) Registered levels are shared: a process-wide, reference-counted cache keyed by (device, curve, scalar width,
+ * 128-bit content hash of the points) makes a second registration of the same `CommitmentGens` -- another stream of the
+ * prover, the next proof, the verifier's own setup (framework.rs:297-303, 770, 910-976) -- free: no k_precompute, no
+ * second copy in HBM.  reef_bases_cache_stats: hits since process start, live entries.  (Deriving the generators
+ * themselves -- nova-snark's hash-to-curve from a label -- stays with the Rust side.) */
+int reef_bases_cache_stats(uint64_t* hits, uint64_t* entries);
 int reef_msm(reef_ctx* ctx, const reef_bases* b, const uint8_t* scalars, uint64_t n, uint8_t out[64]);
 /* scalars already resident in device memory */
 int reef_msm_dev(reef_ctx* ctx, const reef_bases* b, const void* scalars_dev, uint64_t n, uint8_t out[64]);
@@ -266,6 +279,10 @@ int reef_msm_rows_u32(reef_ctx* ctx, const reef_bases* b, const uint32_t* matrix
                       uint32_t entry_bits, const uint8_t* blinds, uint8_t* out);
 int reef_msm_rows(reef_ctx* ctx, const reef_bases* b, const uint8_t* matrix, uint64_t rows, uint64_t cols,
                   const uint8_t* blinds, uint8_t* out);
+/* The same with the matrix (rows x cols canonical 32-byte scalars) resident in device memory.  With rows = 2 this is
+ * commit(W) and commit(T) of one fold (framework.rs:668-675: both over the same commitment key) as ONE bucket sort /
+ * accumulation / reduction chain instead of two latency pipelines. */
+int reef_msm_rows_dev(reef_ctx* ctx, const reef_bases* b, const void* matrix_dev, uint64_t rows, uint64_t cols, uint8_t* out);
 
 /* Multi-GPU: windows [w_begin, w_end) only; out_xyzz = partial sum as (X, Y, ZZ, ZZZ), 4 x 32 B
  * canonical.  The host all-gathers the partials (NCCL has no EC-add reduce op) and every rank
@@ -419,6 +436,33 @@ typedef struct reef_cmt_nldoc {
 } reef_cmt_nldoc;
 uint64_t reef_cmt_nldoc_size(const reef_cmt_nldoc* f);
 int reef_cmt_nldoc_write(const reef_cmt_nldoc* f, uint8_t* out, uint64_t out_cap, uint64_t* out_len);
+
+/* ------------------------------------------------------------------ (f1) index-addressed witness buffer
+ * Replaces the per-step string-keyed wire map of `NFAStepCircuit::synthesize` (nova.rs:868-1399: `FxHashMap<String, Value>`
+ * wires matched with format!()-built names, int_to_ff per variable, nova.rs:31-40, 937-946; handed over at
+ * framework.rs:561-572): the host resolves every wire NAME to an INDEX once per circuit shape; per step it writes plain
+ * values by index, the sum-check writes its own outputs (claim_r, the round polynomials and challenges, last claim,
+ * next running claim) into their slots ON THE DEVICE, and commit(W) (reef_msm_dev over reef_witness_dev) reads the
+ * buffer where it lies -- no per-wire host work, no host round trip of the sum-check outputs.
+ * Elements are canonical Fq values (the primary circuit's field), zero-initialised. */
+typedef struct reef_witness reef_witness;
+typedef struct reef_nlookup_slots {
+  uint64_t claim_r;      /* UINT64_MAX = do not write */
+  uint64_t rounds;       /* base of ell x 4 consecutive slots: (sc_r, xsq, x, const) per round, as reef_nlookup_out.rounds */
+  uint64_t last_claim;
+  uint64_t next_claim;
+} reef_nlookup_slots;
+int reef_witness_create(reef_ctx* ctx, uint64_t n, reef_witness** out);
+int reef_witness_set(reef_witness* w, const uint64_t* idx, const uint8_t* vals, uint64_t k);      /* k canonical 32-byte values */
+int reef_witness_set_u64(reef_witness* w, const uint64_t* idx, const uint64_t* vals, uint64_t k);  /* bits / small integers */
+int reef_witness_read(reef_witness* w, uint64_t first, uint64_t k, uint8_t* out);
+void* reef_witness_dev(reef_witness* w);          /* device address: n x 32 B, usable as reef_msm_dev scalars */
+uint64_t reef_witness_len(reef_witness* w);
+void reef_witness_free(reef_witness* w);
+/* reef_nlookup_prove that ALSO scatters its outputs into the witness buffer (same stream, right behind the last kernel) */
+int reef_nlookup_prove_w(reef_ctx* ctx, int tag, const reef_table* table, const uint64_t* q, const uint8_t* v, uint32_t m,
+                         const uint8_t* prev_q, const uint8_t* prev_v, const uint8_t* doc_hash, reef_nlookup_out* out,
+                         reef_witness* w, const reef_nlookup_slots* slots);
 
 #ifdef __cplusplus
 }

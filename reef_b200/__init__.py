@@ -9,6 +9,6 @@ compute call raises `ReefError` unless the library was built and an sm_100 GPU i
 """
 from ._lib import ReefError, lib, lib_path  # noqa: F401
 from .backend import (  # noqa: F401
-    TAG_NL, TAG_NLDOC, TAG_NLHYBRID, Bases, Context, MerkleCommitment, NlookupResult, ShardedNlookup, Sponge, Sumcheck, Table,
+    TAG_NL, TAG_NLDOC, TAG_NLHYBRID, Bases, Context, MerkleCommitment, NlookupResult, ShardedNlookup, Sponge, Sumcheck, Table, Witness,
     combined_q, doc_transform, io_pattern_tag, logmn,
 )

@@ -30,6 +30,11 @@ class NlookupOut(C.Structure):
     ]
 
 
+class NlookupSlots(C.Structure):
+    """reef_nlookup_slots (include/reef_b200.h); 2^64 - 1 = do not write"""
+    _fields_ = [("claim_r", C.c_uint64), ("rounds", C.c_uint64), ("last_claim", C.c_uint64), ("next_claim", C.c_uint64)]
+
+
 class CmtNldoc(C.Structure):
     """reef_cmt_nldoc (include/reef_b200.h)"""
     _fields_ = [("single_gens", C.c_void_p), ("single_gens_len", C.c_uint64), ("hyrax_gen", C.c_void_p), ("hyrax_gen_len", C.c_uint64),
@@ -55,6 +60,8 @@ _sig = {
     "reef_launch_count": (C.c_uint64, []),
     "reef_last_error": (C.c_char_p, []),
     "reef_init": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "reef_init_prio": (C.c_int, [C.c_int, C.c_int, C.POINTER(_vp)]),
+    "reef_ctx_sm_count": (C.c_uint32, [_vp]),
     "reef_shutdown": (None, [_vp]),
     "reef_sync": (C.c_int, [_vp]),
     "reef_stream": (_vp, [_vp]),
@@ -105,6 +112,7 @@ _sig = {
     "reef_msm_u32": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp]),
     "reef_msm_rows_u32": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32, _vp, _vp]),
     "reef_msm_rows": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, _vp]),
+    "reef_msm_rows_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp]),
     "reef_msm_partial_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _vp]),
     "reef_msm_combine": (C.c_int, [_vp, C.c_int, _vp, C.c_uint32, _vp]),
     "reef_msm_sharded_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp]),
@@ -125,6 +133,15 @@ _sig = {
     "reef_r1cs_spmv": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, _vp]),
     "reef_ipa_fold_bases": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64, _vp, _vp, _vp]),
     "reef_eq_table": (C.c_int, [_vp, C.c_int, _vp, C.c_uint32, _vp]),
+    "reef_bases_cache_stats": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "reef_witness_create": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
+    "reef_witness_set": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
+    "reef_witness_set_u64": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
+    "reef_witness_read": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
+    "reef_witness_dev": (_vp, [_vp]),
+    "reef_witness_len": (C.c_uint64, [_vp]),
+    "reef_witness_free": (None, [_vp]),
+    "reef_nlookup_prove_w": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp, C.POINTER(NlookupOut), _vp, _vp]),
     "reef_nova_cross_term": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_uint64, _vp]),
     "reef_vec_axpy": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_uint64, _vp]),
     "reef_ipa_begin": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_uint64, C.POINTER(_vp)]),

@@ -85,9 +85,13 @@ def io_pattern_tag(pattern, domain_separator: int = 0) -> int:
 class Context:
     """One libreef_b200 context (one CUDA stream) on one GPU."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, latency_critical: bool = None):
+        """latency_critical: True / False = highest / lowest CUDA stream priority (reef_init_prio); None = default stream"""
         h = C.c_void_p()
-        check(lib.reef_init(device, C.byref(h)))
+        if latency_critical is None:
+            check(lib.reef_init(device, C.byref(h)))
+        else:
+            check(lib.reef_init_prio(device, 1 if latency_critical else 0, C.byref(h)))
         self._h = h
         self.device = device
 
@@ -200,8 +204,9 @@ class Context:
         return _unpack(out.raw)
 
     # ---- nlookup
-    def wit_nlookup_gadget(self, table: "Table", q, v, running_q=None, running_v=None, tag="nl", doc_hash=None):
-        """r1cs.rs:2177-2393.  Returns NlookupResult."""
+    def wit_nlookup_gadget(self, table: "Table", q, v, running_q=None, running_v=None, tag="nl", doc_hash=None, witness=None, slots=None):
+        """r1cs.rs:2177-2393.  Returns NlookupResult.  witness / slots: also scatter the outputs into an index-addressed
+        witness buffer on the device (slots = dict(claim_r=, rounds=, last_claim=, next_claim=), missing = skip)."""
         m = len(q)
         assert m == len(v)
         ell_cap = 64
@@ -223,8 +228,16 @@ class Context:
         pq = _buf(_pack(running_q)) if running_q is not None else None
         pv = _buf(_pack([running_v])) if running_v is not None else None
         dh = _buf(_pack([doc_hash])) if doc_hash is not None else None
-        check(lib.reef_nlookup_prove(self._h, _TAGS[tag] if isinstance(tag, str) else tag, table._h,
-                                     qa.ctypes.data if m else None, vb if m else None, m, pq, pv, dh, C.byref(o)))
+        if witness is None:
+            check(lib.reef_nlookup_prove(self._h, _TAGS[tag] if isinstance(tag, str) else tag, table._h,
+                                         qa.ctypes.data if m else None, vb if m else None, m, pq, pv, dh, C.byref(o)))
+        else:
+            from ._lib import NlookupSlots
+            none = 2 ** 64 - 1
+            sl = NlookupSlots(*(int((slots or {}).get(k, none)) for k in ("claim_r", "rounds", "last_claim", "next_claim")))
+            check(lib.reef_nlookup_prove_w(self._h, _TAGS[tag] if isinstance(tag, str) else tag, table._h,
+                                           qa.ctypes.data if m else None, vb if m else None, m, pq, pv, dh, C.byref(o),
+                                           witness._h, C.byref(sl)))
         ell = o.ell
         rounds = _unpack(bufs["rounds"].raw[:ell * 4 * 32])
         rounds = [tuple(rounds[4 * i:4 * i + 4]) for i in range(ell)]
@@ -296,6 +309,7 @@ class Context:
         nl = C.c_uint32(0)
         root = C.create_string_buffer(32)
         check(lib.reef_merkle_build(self._h, d.ctypes.data, len(d), levels, sizes.ctypes.data, C.byref(nl), root))
+        self.last_level_sizes, self.last_n_levels = sizes, int(nl.value)      # for the .cmt writer (reef_cmt_merkle_write)
         return int.from_bytes(root.raw, "little"), levels
 
     def merkle_root(self, doc) -> int:
@@ -320,6 +334,46 @@ class Context:
 
 _FIELDS = {"fq": 0, "fp": 1}
 _CURVES = {"pallas": 0, "vesta": 1}
+
+
+class Witness:
+    """(f1) index-addressed witness buffer on the device (reef_witness_*): the host writes plain values by index, the
+    sum-check writes its outputs into their slots on the device, commit(W) reads it in place."""
+
+    def __init__(self, ctx: "Context", n: int):
+        self.ctx, self.n = ctx, n
+        h = C.c_void_p()
+        check(lib.reef_witness_create(ctx._h, n, C.byref(h)))
+        self._h = h
+
+    def set(self, idx, vals):
+        i = _u64(idx)
+        check(lib.reef_witness_set(self._h, i.ctypes.data, _buf(_pack(vals)), len(i)))
+
+    def set_small(self, idx, vals):
+        i, v = _u64(idx), _u64(vals)
+        check(lib.reef_witness_set_u64(self._h, i.ctypes.data, v.ctypes.data, len(i)))
+
+    def read(self, first: int = 0, k: int = None) -> list:
+        k = self.n - first if k is None else k
+        out = C.create_string_buffer(max(k, 1) * 32)
+        check(lib.reef_witness_read(self._h, first, k, out))
+        return _unpack(out.raw[:k * 32])
+
+    @property
+    def dev_ptr(self) -> int:
+        return int(lib.reef_witness_dev(self._h) or 0)
+
+    def free(self):
+        if self._h:
+            lib.reef_witness_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class Sumcheck:

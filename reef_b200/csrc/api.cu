@@ -1,6 +1,9 @@
 // extern "C" surface of libreef_b200.so + the host-side logic of the path (logmn,
 // doc_transform, combined_q packing, transcript assembly, Merkle path witnesses).
 // See include/reef_b200.h for the contract and the reference interfaces each entry replaces.
+#include <cuda.h>
+#include <dlfcn.h>
+
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -193,7 +196,77 @@ int reef_abi_version(void) { return 1; }
 uint64_t reef_launch_count(void) { return (uint64_t)g_launches.load(); }
 const char* reef_last_error(void) { return g_last_error.c_str(); }
 
-int reef_init(int device, reef_ctx** out) {
+static int init_impl(int device, int latency_critical, reef_ctx** out);
+int reef_init(int device, reef_ctx** out) { return init_impl(device, 0, out); }
+int reef_init_prio(int device, int latency_critical, reef_ctx** out) { return init_impl(device, latency_critical ? 1 : 2, out); }
+
+// ---------------------------------------------------------------------------------------
+// SM partition for BACKGROUND contexts (reef_init_prio(.., 0, ..)).  The Fiat-Shamir kernels of a latency-critical
+// context are single CTAs that want an SM to themselves; while the grids of a background MSM fill the chip such a
+// CTA waits for a whole SM to drain -- measured: 0.6 ms of a 5.8 ms pass (profiles/r02_summary.md).  Background
+// streams are therefore created inside a CUDA green context that owns all but REEF_RESERVE_SMS (default 12 = what
+// is left when 136 of 148 SMs are split off in groups of 8) SMs: their kernels can never occupy the remaining SMs,
+// which the latency-critical kernels (primary context: every SM) then find empty.  Driver API through dlopen (the
+// library must still load, for the symbol checks, where no driver is installed); any failure falls back to an
+// ordinary low-priority stream.
+// ---------------------------------------------------------------------------------------
+namespace {
+struct GreenPartition {
+  bool tried = false;
+  CUgreenCtx ctx = nullptr;
+  unsigned sm_count = 0;
+};
+std::mutex g_green_mu;
+GreenPartition g_green[16];
+
+#define REEF_DL(h, name, fn) (((fn) = reinterpret_cast<decltype(fn)>(dlsym((h), (name)))) != nullptr)
+
+// stream of the device's background partition, or nullptr
+cudaStream_t green_stream(int device, int sm_total, int priority, unsigned* sms_out) {
+  if (device < 0 || device >= 16) return nullptr;
+  const char* e = getenv("REEF_RESERVE_SMS");
+  const int reserve = e ? atoi(e) : 12;
+  if (reserve <= 0 || reserve >= sm_total) return nullptr;
+  static void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return nullptr;
+  static CUresult (*p_cuDeviceGet)(CUdevice*, int);
+  static CUresult (*p_cuDeviceGetDevResource)(CUdevice, CUdevResource*, CUdevResourceType);
+  static CUresult (*p_cuDevSmResourceSplitByCount)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+  static CUresult (*p_cuDevResourceGenerateDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+  static CUresult (*p_cuGreenCtxCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+  static CUresult (*p_cuGreenCtxStreamCreate)(CUstream*, CUgreenCtx, unsigned int, int);
+  static const bool ok = REEF_DL(lib, "cuDeviceGet", p_cuDeviceGet) && REEF_DL(lib, "cuDeviceGetDevResource", p_cuDeviceGetDevResource) &&
+                         REEF_DL(lib, "cuDevSmResourceSplitByCount", p_cuDevSmResourceSplitByCount) &&
+                         REEF_DL(lib, "cuDevResourceGenerateDesc", p_cuDevResourceGenerateDesc) &&
+                         REEF_DL(lib, "cuGreenCtxCreate", p_cuGreenCtxCreate) && REEF_DL(lib, "cuGreenCtxStreamCreate", p_cuGreenCtxStreamCreate);
+  if (!ok) return nullptr;
+  std::lock_guard<std::mutex> lk(g_green_mu);
+  GreenPartition& G = g_green[device];
+  if (!G.tried) {
+    G.tried = true;
+    cudaFree(0);                                                   // the primary context exists and is current
+    CUdevice dev;
+    CUdevResource all, part, rest;
+    CUdevResourceDesc desc;
+    unsigned groups = 1;
+    const unsigned want = (unsigned)(sm_total - reserve);
+    if (p_cuDeviceGet(&dev, device) == CUDA_SUCCESS && p_cuDeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS &&
+        p_cuDevSmResourceSplitByCount(&part, &groups, &all, &rest, 0, want) == CUDA_SUCCESS && groups == 1 &&
+        part.sm.smCount < (unsigned)sm_total && p_cuDevResourceGenerateDesc(&desc, &part, 1) == CUDA_SUCCESS &&
+        p_cuGreenCtxCreate(&G.ctx, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS)
+      G.sm_count = part.sm.smCount;
+    else
+      G.ctx = nullptr;
+  }
+  if (!G.ctx) return nullptr;
+  CUstream s = nullptr;
+  if (p_cuGreenCtxStreamCreate(&s, G.ctx, CU_STREAM_NON_BLOCKING, priority) != CUDA_SUCCESS) return nullptr;
+  *sms_out = G.sm_count;
+  return (cudaStream_t)s;
+}
+}  // namespace
+
+static int init_impl(int device, int latency_critical, reef_ctx** out) {
   REEF_REQUIRE(out != nullptr, REEF_EINVAL, "reef_init: out is NULL");
   *out = nullptr;
   int count = 0;
@@ -210,7 +283,18 @@ int reef_init(int device, reef_ctx** out) {
   reef_ctx* c = new reef_ctx;
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  // latency-critical contexts (the Fiat-Shamir chains) get the highest stream priority: when an SM frees up, their
+  // pending CTAs are placed before those of the throughput streams (the fold commitments)
+  // (latency_critical: 0 = plain reef_init, 1 = latency-critical, 2 = background)
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  cudaError_t se = cudaSuccess;
+  if (latency_critical == 2) {
+    unsigned sms = 0;
+    c->stream = green_stream(device, c->sm_count, prio_lo, &sms);
+    if (c->stream) c->partition_sms = sms;
+  }
+  if (!c->stream) se = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, latency_critical == 1 ? prio_hi : prio_lo);
   if (se != cudaSuccess) {
     c->stream = nullptr;
     ctx_release(c);
@@ -224,6 +308,9 @@ int reef_init(int device, reef_ctx** out) {
   *out = c;
   return REEF_OK;
 }
+
+/* SMs this context's kernels may run on: the whole chip, or the background partition (reef_init_prio(.., 0, ..)) */
+uint32_t reef_ctx_sm_count(const reef_ctx* c) { return c ? (c->partition_sms ? c->partition_sms : (uint32_t)c->sm_count) : 0; }
 
 // Drops the caller's reference.  Child handles (tables, bases, sponges, sessions) created from this
 // context stay valid for their *_free call and keep the context's resources alive until the last
@@ -934,8 +1021,15 @@ static int nl_prepare(int tag, uint64_t n_orig, uint64_t n_pad, const uint8_t* f
   return REEF_OK;
 }
 
-int reef_nlookup_prove(reef_ctx* c, int tag, const reef_table* table, const uint64_t* q, const uint8_t* v, uint32_t m,
-                       const uint8_t* prev_q, const uint8_t* prev_v, const uint8_t* doc_hash, reef_nlookup_out* out) {
+struct reef_witness {
+  reef_ctx* ctx;
+  void* d;
+  uint64_t n;
+};
+
+static int nlookup_prove_impl(reef_ctx* c, int tag, const reef_table* table, const uint64_t* q, const uint8_t* v, uint32_t m,
+                              const uint8_t* prev_q, const uint8_t* prev_v, const uint8_t* doc_hash, reef_nlookup_out* out,
+                              reef_witness* w, const reef_nlookup_slots* slots) {
   REEF_REQUIRE(c && table && out, REEF_EINVAL, "reef_nlookup_prove: NULL argument");
   REEF_REQUIRE(table->ctx == c, REEF_EINVAL, "reef_nlookup_prove: table belongs to another context");
   NlPrep P;
@@ -957,9 +1051,119 @@ int reef_nlookup_prove(reef_ctx* c, int tag, const reef_table* table, const uint
   a.out_rounds = out->rounds;
   a.out_last_claim = out->sc_last_claim;
   a.out_next_v = out->next_running_claim;
+  if (w) {
+    REEF_REQUIRE(slots, REEF_EINVAL, "reef_nlookup_prove_w: NULL slots");
+    REEF_REQUIRE(w->ctx == c, REEF_EINVAL, "reef_nlookup_prove_w: witness buffer belongs to another context");
+    const uint64_t none = ~0ull;
+    auto fits = [&](uint64_t s, uint64_t k) { return s == none || (s < w->n && k <= w->n - s); };
+    REEF_REQUIRE(fits(slots->claim_r, 1) && fits(slots->rounds, 4ull * P.ell) && fits(slots->last_claim, 1) && fits(slots->next_claim, 1),
+                 REEF_EASSERT, "reef_nlookup_prove_w: witness slot out of range (index out of bounds)");
+    a.d_wit = w->d;
+    a.wit_len = w->n;
+    a.slot_claim_r = slots->claim_r;
+    a.slot_rounds = slots->rounds;
+    a.slot_last_claim = slots->last_claim;
+    a.slot_next_v = slots->next_claim;
+  }
   std::lock_guard<std::mutex> lk(c->mu);
   REEF_CUDA(cudaSetDevice(c->device));
   return nlookup_run(c, a);
+}
+
+int reef_nlookup_prove(reef_ctx* c, int tag, const reef_table* table, const uint64_t* q, const uint8_t* v, uint32_t m,
+                       const uint8_t* prev_q, const uint8_t* prev_v, const uint8_t* doc_hash, reef_nlookup_out* out) {
+  return nlookup_prove_impl(c, tag, table, q, v, m, prev_q, prev_v, doc_hash, out, nullptr, nullptr);
+}
+
+int reef_nlookup_prove_w(reef_ctx* c, int tag, const reef_table* table, const uint64_t* q, const uint8_t* v, uint32_t m,
+                         const uint8_t* prev_q, const uint8_t* prev_v, const uint8_t* doc_hash, reef_nlookup_out* out,
+                         reef_witness* w, const reef_nlookup_slots* slots) {
+  REEF_REQUIRE(w && slots, REEF_EINVAL, "reef_nlookup_prove_w: NULL witness / slots");
+  return nlookup_prove_impl(c, tag, table, q, v, m, prev_q, prev_v, doc_hash, out, w, slots);
+}
+
+// ---- (f1) index-addressed witness buffer
+int reef_witness_create(reef_ctx* c, uint64_t n, reef_witness** out) {
+  REEF_REQUIRE(c && out && n >= 1, REEF_EINVAL, "reef_witness_create: NULL / empty argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CTX_LIVE(c, "reef_witness_create");
+  REEF_CUDA(cudaSetDevice(c->device));
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, (size_t)n * 32);
+  if (e != cudaSuccess) return fail(REEF_ENOMEM, std::string("reef_witness_create: ") + cudaGetErrorString(e));
+  REEF_CUDA(cudaMemsetAsync(d, 0, (size_t)n * 32, c->stream));
+  reef_witness* w = new reef_witness{c, d, n};
+  ctx_retain(c);
+  *out = w;
+  return REEF_OK;
+}
+
+static int witness_set(reef_witness* w, const uint64_t* idx, const void* vals, uint64_t k, bool small) {
+  REEF_REQUIRE(w && (k == 0 || (idx && vals)), REEF_EINVAL, "reef_witness_set: NULL argument");
+  if (k == 0) return REEF_OK;
+  for (uint64_t i = 0; i < k; i++) REEF_REQUIRE(idx[i] < w->n, REEF_EASSERT, "reef_witness_set: index out of bounds");
+  if (!small) {
+    int rc = check_canonical((const uint8_t*)vals, k, "reef_witness_set");
+    if (rc) return rc;
+  }
+  reef_ctx* c = w->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CTX_LIVE(c, "reef_witness_set");
+  REEF_CUDA(cudaSetDevice(c->device));
+  // runs of consecutive indices become one copy each (the layout a circuit hands out is mostly contiguous)
+  void* hs;
+  int rc = ctx_stage(c, (size_t)k * 32, &hs);
+  if (rc) return rc;
+  uint8_t* h = (uint8_t*)hs;
+  for (uint64_t i = 0; i < k; i++) {
+    if (small) {
+      memset(h + 32 * i, 0, 32);
+      const uint64_t x = ((const uint64_t*)vals)[i];
+      for (int b = 0; b < 8; b++) h[32 * i + b] = (uint8_t)(x >> (8 * b));
+    } else {
+      memcpy(h + 32 * i, (const uint8_t*)vals + 32 * i, 32);
+    }
+  }
+  uint64_t i = 0;
+  while (i < k) {
+    uint64_t j = i + 1;
+    while (j < k && idx[j] == idx[j - 1] + 1) j++;
+    REEF_CUDA(cudaMemcpyAsync((char*)w->d + 32 * idx[i], h + 32 * i, (size_t)(j - i) * 32, cudaMemcpyHostToDevice, c->stream));
+    i = j;
+  }
+  REEF_CUDA(cudaStreamSynchronize(c->stream));   // the staging buffer is reused by the next call
+  return REEF_OK;
+}
+
+int reef_witness_set(reef_witness* w, const uint64_t* idx, const uint8_t* vals, uint64_t k) { return witness_set(w, idx, vals, k, false); }
+int reef_witness_set_u64(reef_witness* w, const uint64_t* idx, const uint64_t* vals, uint64_t k) { return witness_set(w, idx, vals, k, true); }
+
+int reef_witness_read(reef_witness* w, uint64_t first, uint64_t k, uint8_t* out) {
+  REEF_REQUIRE(w && out, REEF_EINVAL, "reef_witness_read: NULL argument");
+  REEF_REQUIRE(first <= w->n && k <= w->n - first, REEF_EASSERT, "reef_witness_read: range out of bounds");
+  reef_ctx* c = w->ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CTX_LIVE(c, "reef_witness_read");
+  REEF_CUDA(cudaSetDevice(c->device));
+  REEF_CUDA(cudaMemcpyAsync(out, (char*)w->d + 32 * first, (size_t)k * 32, cudaMemcpyDeviceToHost, c->stream));
+  REEF_CUDA(cudaStreamSynchronize(c->stream));
+  return REEF_OK;
+}
+
+void* reef_witness_dev(reef_witness* w) { return w ? w->d : nullptr; }
+uint64_t reef_witness_len(reef_witness* w) { return w ? w->n : 0; }
+
+void reef_witness_free(reef_witness* w) {
+  if (!w) return;
+  reef_ctx* c = w->ctx;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(w->d);
+  }
+  delete w;
+  ctx_release(c);
 }
 
 // ---- multi-GPU sharded sum-check: see include/reef_b200.h
@@ -1285,17 +1489,73 @@ int reef_hosttest_ec_op(int curve, int op, const uint8_t p[64], const uint8_t q[
   return 0;
 }
 
+// (f2) Registered generator levels are a pure function of (device, curve, scalar width, the points): a process-wide,
+// reference-counted cache keyed by a 128-bit content hash lets every context / proof that commits with the same
+// `CommitmentGens` (the prover registers the same key on several streams, the verifier derives it again,
+// framework.rs:297-303, 770, 910-976) share ONE set of window levels in HBM and skip k_precompute.  REEF_BASES_CACHE=0
+// turns it off.
+namespace {
+struct LevelsEntry {
+  int device, curve;
+  uint64_t n;
+  uint32_t scalar_bits;
+  uint64_t h1, h2;
+  void* d_levels;
+  int refs;
+};
+std::mutex g_levels_mu;
+std::vector<LevelsEntry> g_levels;
+std::atomic<unsigned long long> g_levels_hits{0};
+bool levels_cache_on() {
+  static const bool on = !(getenv("REEF_BASES_CACHE") && atoi(getenv("REEF_BASES_CACHE")) == 0);
+  return on;
+}
+void hash128(const uint8_t* p, size_t bytes, uint64_t& h1, uint64_t& h2) {
+  uint64_t a = 0xcbf29ce484222325ull, b = 0x9e3779b97f4a7c15ull;
+  const size_t words = bytes / 8;
+  for (size_t i = 0; i < words; i++) {
+    uint64_t w;
+    memcpy(&w, p + 8 * i, 8);
+    a = (a ^ w) * 0x100000001b3ull;
+    b = (b + w) * 0xff51afd7ed558ccdull;
+    b ^= b >> 29;
+  }
+  h1 = a;
+  h2 = b;
+}
+}  // namespace
+
 int reef_bases_register(reef_ctx* c, int curve, const uint8_t* bases, uint64_t n, uint32_t scalar_bits, reef_bases** out) {
   REEF_REQUIRE(c && bases && out, REEF_EINVAL, "reef_bases_register: NULL argument");
   REEF_REQUIRE(curve == REEF_CURVE_PALLAS || curve == REEF_CURVE_VESTA, REEF_EINVAL, "reef_bases_register: unknown curve");
   REEF_REQUIRE(n >= 1, REEF_EINVAL, "reef_bases_register: no bases");
   if (scalar_bits == 0 || scalar_bits > 255) scalar_bits = 255;
+  uint64_t h1 = 0, h2 = 0;
+  const bool cache = levels_cache_on();
+  if (cache) hash128(bases, (size_t)n * 64, h1, h2);
   std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CTX_LIVE(c, "reef_bases_register");
   REEF_CUDA(cudaSetDevice(c->device));
   MsmPlanPublic pl = msm_make_plan(n, scalar_bits, (uint64_t)24 << 30);
   void* d_levels = nullptr;
-  int rc = msm_bases_register(c, curve, bases, n, pl, &d_levels);
-  if (rc) return rc;
+  if (cache) {
+    std::lock_guard<std::mutex> gl(g_levels_mu);
+    for (auto& e : g_levels)
+      if (e.device == c->device && e.curve == curve && e.n == n && e.scalar_bits == scalar_bits && e.h1 == h1 && e.h2 == h2) {
+        e.refs++;
+        d_levels = e.d_levels;
+        g_levels_hits.fetch_add(1, std::memory_order_relaxed);
+        break;
+      }
+  }
+  if (!d_levels) {
+    int rc = msm_bases_register(c, curve, bases, n, pl, &d_levels);
+    if (rc) return rc;
+    if (cache) {
+      std::lock_guard<std::mutex> gl(g_levels_mu);
+      g_levels.push_back(LevelsEntry{c->device, curve, n, scalar_bits, h1, h2, d_levels, 1});
+    }
+  }
   reef_bases* b = new reef_bases;
   b->ctx = c;
   b->curve = curve;
@@ -1315,10 +1575,30 @@ void reef_bases_free(reef_bases* b) {
     std::lock_guard<std::mutex> lk(c->mu);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFree(b->d_levels);
+    bool shared_alive = false, found = false;
+    {
+      std::lock_guard<std::mutex> gl(g_levels_mu);
+      for (size_t i = 0; i < g_levels.size(); i++)
+        if (g_levels[i].d_levels == b->d_levels) {
+          found = true;
+          if (--g_levels[i].refs > 0) shared_alive = true;
+          else g_levels.erase(g_levels.begin() + i);
+          break;
+        }
+    }
+    (void)found;
+    if (!shared_alive) cudaFree(b->d_levels);
   }
   delete b;
   ctx_release(c);
+}
+
+/* hits since process start / live entries of the generator-level cache */
+int reef_bases_cache_stats(uint64_t* hits, uint64_t* entries) {
+  std::lock_guard<std::mutex> gl(g_levels_mu);
+  if (hits) *hits = g_levels_hits.load();
+  if (entries) *entries = g_levels.size();
+  return REEF_OK;
 }
 
 uint32_t reef_bases_windows(const reef_bases* b) { return b ? b->plan.W : 0; }
@@ -1485,6 +1765,32 @@ int reef_msm_rows_u32(reef_ctx* c, const reef_bases* b, const uint32_t* matrix, 
 int reef_msm_rows(reef_ctx* c, const reef_bases* b, const uint8_t* matrix, uint64_t rows, uint64_t cols,
                   const uint8_t* blinds, uint8_t* out) {
   return msm_rows_host(c, b, matrix, 0, rows, cols, 255, blinds, out);
+}
+
+// scalars resident: rows x cols canonical 32-byte values, row-major (e.g. the witness W and the cross term T of one
+// fold as two rows over the same commitment key: ONE sort / accumulate / reduce chain for both commitments)
+int reef_msm_rows_dev(reef_ctx* c, const reef_bases* b, const void* matrix_dev, uint64_t rows, uint64_t cols, uint8_t* out) {
+  REEF_REQUIRE(c && b && matrix_dev && out, REEF_EINVAL, "reef_msm_rows_dev: NULL argument");
+  REEF_REQUIRE(b->ctx == c, REEF_EINVAL, "reef_msm_rows_dev: bases belong to another context");
+  REEF_REQUIRE(rows >= 1 && cols >= 1, REEF_EINVAL, "reef_msm_rows_dev: empty matrix");
+  REEF_REQUIRE(cols <= b->n, REEF_EASSERT, "reef_msm_rows_dev: not enough generators (assertion failed: gens.len() >= cols)");
+  REEF_REQUIRE(b->scalar_bits == 255, REEF_EINVAL, "reef_msm_rows_dev: generators registered for narrower scalars");
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CTX_LIVE(c, "reef_msm_rows_dev");
+  REEF_CUDA(cudaSetDevice(c->device));
+  MsmRowsArgs a;
+  a.plan = b->plan;
+  a.d_levels = b->d_levels;
+  a.n_bases = b->n;
+  a.d_scalars = matrix_dev;
+  a.scalars_u32 = 0;
+  a.scalar_bits = 255;
+  a.rows = rows;
+  a.cols = cols;
+  a.d_blinds = nullptr;
+  a.blind_base = cols;
+  a.h_out = out;
+  return msm_rows_run(c, b->curve, a);
 }
 
 int reef_msm_combine(reef_ctx* c, int curve, const uint8_t* partials, uint32_t k, uint8_t out[64]) {

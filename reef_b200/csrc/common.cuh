@@ -175,6 +175,8 @@ struct reef_ctx {
   void* h_stage = nullptr;
   size_t h_stage_bytes = 0;
   int sm_count = 148;
+  // background contexts (reef_init_prio(.., 0, ..)): SMs of the green-context partition their stream lives in (0 = none)
+  uint32_t partition_sms = 0;
   // device buffers of freed tables, reused by the next upload of the same size: a prover re-uploads
   // a same-sized table per proof, and cudaMalloc/cudaFree synchronise the whole device
   std::vector<std::pair<size_t, void*>> table_cache;

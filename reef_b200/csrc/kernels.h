@@ -50,6 +50,11 @@ struct NlookupArgs {
   uint8_t* out_rounds;     // ell x 4 x 32: (sc_r, xsq, x, const)
   uint8_t* out_last_claim; // 32
   uint8_t* out_next_v;     // 32
+  // (f1) optional: the same outputs scattered on the device into an index-addressed witness buffer (canonical
+  // elements) right behind the last kernel; slot = UINT64_MAX skips an output
+  void* d_wit = nullptr;
+  uint64_t wit_len = 0;
+  uint64_t slot_claim_r = ~0ull, slot_rounds = ~0ull, slot_last_claim = ~0ull, slot_next_v = ~0ull;
 };
 int nlookup_run(reef_ctx* c, const NlookupArgs& a);
 int launch_hybrid_table(reef_ctx* c, const void* d_pub, uint64_t n_pub, const uint8_t* fill_le, uint64_t half_len, const uint32_t* d_codes,

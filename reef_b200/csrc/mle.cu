@@ -549,6 +549,21 @@ k_tail(NlState* st, const void* __restrict__ Tin, uint64_t L_in, int do_fold, co
   }
 }
 
+// (f1) outputs of the finished sum-check -> slots of an index-addressed witness buffer (canonical elements):
+// rounds occupy ell x 4 consecutive slots in the order (sc_r, xsq, x, const) of reef_nlookup_out.rounds
+__global__ void k_wit_scatter(const NlState* __restrict__ st, uint32_t ell, Fq* __restrict__ wit, uint64_t slot_claim_r,
+                              uint64_t slot_rounds, uint64_t slot_last_claim, uint64_t slot_next_v) {
+  pdl_wait();
+  const uint64_t none = ~0ull;
+  for (uint32_t i = threadIdx.x; i < 4 * ell; i += blockDim.x)
+    if (slot_rounds != none) wit[slot_rounds + i] = st->out_rounds[i >> 2][i & 3];
+  if (threadIdx.x == 0) {
+    if (slot_claim_r != none) wit[slot_claim_r] = st->out_claim_r;
+    if (slot_last_claim != none) wit[slot_last_claim] = st->out_last_claim;
+    if (slot_next_v != none) wit[slot_next_v] = st->out_next_v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------------------
@@ -692,6 +707,10 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
   }
   tail_scope.reset();
   REEF_LAUNCHED();
+  if (a.d_wit) {
+    k_wit_scatter<<<1, 128, 0, s>>>(st, ell, (Fq*)a.d_wit, a.slot_claim_r, a.slot_rounds, a.slot_last_claim, a.slot_next_v);
+    REEF_LAUNCHED();
+  }
 
   // results
   void* hs;

@@ -266,7 +266,6 @@ __global__ void __launch_bounds__(128) k_accum_first(const uint32_t* __restrict_
   }
   st_xyzz(out + p, acc);
 }
-
 // The same pass with the gathered points staged through shared memory by the TMA engine (`cp.async.bulk`, SASS
 // UBLKCP): every thread reads the point references of its part, posts one 64-byte bulk copy per point into its own
 // slots of a shared tile, all completing on one mbarrier per stage, and adds the points out of shared memory.
@@ -407,7 +406,6 @@ __global__ void __launch_bounds__(128) k_accum_next(const XYZZ<C>* __restrict__ 
   }
   if (live && sub == 0) st_xyzz(out + p, acc);
 }
-
 // buckets[b] = (cnt[b] ? parts[off[b]] : infinity)   (after the last pass every count is <= 1)
 template <class C>
 __global__ void k_gather_buckets(const XYZZ<C>* __restrict__ in, const uint32_t* __restrict__ off,
@@ -598,7 +596,7 @@ __global__ void k_digits_rows(const void* __restrict__ scalars, uint64_t rows, u
 // one CTA per row: S_t from the row's bit-partials, 2^t scaling, sum, affine out
 template <class C>
 __global__ void __launch_bounds__(512) k_rows_final(const XYZZ<C>* __restrict__ partial, uint32_t nblk, uint32_t cbits,
-                                                    Affine<C>* __restrict__ out) {
+                                                    Affine<C>* __restrict__ out, XYZZ<C>* __restrict__ out_xyzz) {
   __shared__ XYZZ<C> st[16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t g = blockIdx.x;
@@ -623,10 +621,14 @@ __global__ void __launch_bounds__(512) k_rows_final(const XYZZ<C>* __restrict__ 
       xyzz_add<C>(r, o);
     }
     if (lane == 0) {
-      Affine<C> a = xyzz_to_affine<C>(r);
-      a.x = from_mont<C>(a.x);
-      a.y = from_mont<C>(a.y);
-      st_affine(out + g, a);
+      if (out_xyzz) {                      // a handful of rows: the inversion happens on the host (see msm_run_t)
+        st_xyzz(out_xyzz + g, r);
+      } else {
+        Affine<C> a = xyzz_to_affine<C>(r);
+        a.x = from_mont<C>(a.x);
+        a.y = from_mont<C>(a.y);
+        st_affine(out + g, a);
+      }
     }
   }
 }
@@ -876,7 +878,9 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
   const uint32_t bpt = P.B >= 256u * 32u ? 8u : 1u;
   const uint32_t nblk = cdiv(P.B, 256 * bpt);
   size_t o_bitpart = take((size_t)a.rows * P.c * nblk * sizeof(XYZZ<C>));
-  size_t o_out = take((size_t)a.rows * sizeof(Affine<C>));
+  // few rows (the W / T commitments of one fold as two rows): results leave as XYZZ, affine on the host
+  const bool host_affine = a.rows <= 16 && !a.d_rows_out;
+  size_t o_out = take((size_t)a.rows * (host_affine ? sizeof(XYZZ<C>) : sizeof(Affine<C>)));
   void* base;
   int rc = ctx_scratch(c, off, &base);
   if (rc) return rc;
@@ -944,9 +948,21 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
   REEF_LAUNCHED();
   k_bitsum_partial<C><<<dim3(nblk, P.c, (unsigned)a.rows), 256, 0, s>>>(buckets, P.B, bpt, bitpart);
   REEF_LAUNCHED();
-  k_rows_final<C><<<(unsigned)a.rows, 512, 0, s>>>(bitpart, nblk, P.c, d_out);
+  k_rows_final<C><<<(unsigned)a.rows, 512, 0, s>>>(bitpart, nblk, P.c, d_out, host_affine ? (XYZZ<C>*)d_out : nullptr);
   REEF_LAUNCHED();
   scope.reset();
+  if (host_affine) {
+    XYZZ<C> h_rows[16];
+    REEF_CUDA(cudaMemcpyAsync(h_rows, d_out, (size_t)a.rows * sizeof(XYZZ<C>), cudaMemcpyDeviceToHost, s));
+    REEF_CUDA(cudaStreamSynchronize(s));
+    for (uint64_t r = 0; r < a.rows; r++) {
+      Affine<C> aff = xyzz_to_affine<C>(h_rows[r]);
+      aff.x = from_mont<C>(aff.x);
+      aff.y = from_mont<C>(aff.y);
+      memcpy(a.h_out + r * sizeof(Affine<C>), &aff, sizeof(Affine<C>));
+    }
+    return REEF_OK;
+  }
   REEF_CUDA(cudaMemcpyAsync(a.h_out, d_out, (size_t)a.rows * sizeof(Affine<C>), cudaMemcpyDeviceToHost, s));
   if (a.d_rows_out) *a.d_rows_out = d_out;
   else REEF_CUDA(cudaStreamSynchronize(s));     // a caller that keeps working on the rows synchronises itself

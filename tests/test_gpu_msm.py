@@ -7,6 +7,7 @@ import pytest
 
 import reef_b200
 from oracle.curves import PALLAS, VESTA
+from oracle.fields import FQ
 
 pytestmark = pytest.mark.gpu
 CUR = {"pallas": PALLAS, "vesta": VESTA}
@@ -147,3 +148,47 @@ def test_msm_throughput_shapes_known_discrete_logs(ctx):
             dev2 = torch.from_numpy(np.ascontiguousarray(eq).view(np.int64)).cuda()
             assert b.msm_dev(dev2.data_ptr(), n) == cv.mul(s * (n * (n + 1) // 2) % cv.order, cv.gen)
         b.free()
+
+
+def test_background_context_keeps_off_the_reserved_sms_and_stays_exact():
+    """reef_init_prio(.., 0, ..): the background context's stream lives in a green-context partition that leaves
+    REEF_RESERVE_SMS SMs to the latency-critical contexts; results are unchanged -- single MSM, the W / T pair as two
+    rows, u32 rows with blinds"""
+    import numpy as np
+    import workloads as WL
+    from oracle import cport
+    import os
+    bg = reef_b200.Context(0, latency_critical=False)
+    hi = reef_b200.Context(0, latency_critical=True)
+    os.environ["REEF_RESERVE_SMS"] = "0"               # partitioning off: an ordinary low-priority stream
+    try:
+        bg_half = reef_b200.Context(0, latency_critical=False)
+    finally:
+        del os.environ["REEF_RESERVE_SMS"]
+    from reef_b200._lib import lib
+    assert lib.reef_ctx_sm_count(hi._h) == lib.reef_ctx_sm_count(bg_half._h)
+    assert 0 < lib.reef_ctx_sm_count(bg._h) <= lib.reef_ctx_sm_count(hi._h)
+    print("background partition:", lib.reef_ctx_sm_count(bg._h), "of", lib.reef_ctx_sm_count(hi._h), "SMs")
+    try:
+        n = 1 << 13
+        gens = WL.generators("pallas", n + 1)
+        rnd = random.Random(21)
+        sc = [rnd.randrange(1 << 253) for _ in range(2 * n)]
+        for c in (bg, hi, bg_half):
+            b = reef_b200.Bases(c, "pallas", gens)
+            assert b.msm(sc[:n]) == cport.msm("pallas", gens[:64 * n], sc[:n], threads=cport.max_threads())
+            rows = b.msm_rows(sc, 2, n)
+            assert rows[0] == cport.msm("pallas", gens[:64 * n], sc[:n], threads=cport.max_threads())
+            assert rows[1] == cport.msm("pallas", gens[:64 * n], sc[n:], threads=cport.max_threads())
+            codes = np.random.default_rng(3).integers(0, 256, size=(16, 512), dtype=np.uint32)
+            blinds = [rnd.randrange(FQ) for _ in range(16)]
+            hb = reef_b200.Bases(c, "pallas", gens[:64 * 513], 255)
+            got = hb.msm_rows(codes, 16, 512, entry_bits=8, blinds=blinds)
+            for r in (0, 15):
+                assert got[r] == cport.msm("pallas", gens[:64 * 513], [int(x) for x in codes[r]] + [blinds[r]], threads=cport.max_threads())
+            hb.free()
+            b.free()
+    finally:
+        bg.close()
+        hi.close()
+        bg_half.close()

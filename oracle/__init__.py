@@ -13,5 +13,5 @@ PARITY STATUS
     toolchain exists here, so digests are "parity unpinned" against the
     reference binary; they are pinned instead against neptune's published
     algorithm (Grain-LFSR constants, Cauchy MDS, SAFE sponge tag) and against
-    two upstream known-answer values reproduced in tests/test_oracle_poseidon.py.
+    two upstream known-answer values reproduced in tests/test_oracle_kats.py.
 """

@@ -14,7 +14,7 @@
 //    m = -T[i] (no multiply) and only 3 real products per limb; the 2^254 term is a shift.
 //  * Everything is __host__ __device__: the host build emulates the carry chains with
 //    64-bit integers so the *structure* (column bookkeeping, reduction) is unit-tested
-//    on CPU (tests/test_host_field.py) before it ever runs on a GPU.
+//    on CPU (tests/test_host_abi.py::test_shared_field_code_host_instantiation) before it ever runs on a GPU.
 #pragma once
 #include <cstdint>
 

@@ -857,9 +857,16 @@ def opening_phases(ctxs, w, gp, K, no_cpu):
     gens_raw, gen_c = raw[:64 * n], pts(raw[64 * n:], 1)[0]
     a = [rnd.randrange(FQ) for _ in range(n)]
     b = [rnd.randrange(FQ) for _ in range(n)]
-    got, ms = timed_wall(lambda: G.ipa_prove(ctx, "pallas", gens_raw, gen_c, a, b, ShaTranscript(b"ipa", FQ)))
-    entry = {"n": n, "rounds": n.bit_length() - 1, "ms": round(ms, 3), "msm_per_round": 2,
-             "what": "reef_ipa_begin/round/fold/finish: L, R multi-scalar multiplications and the folds of a, b and the generators on the device"}
+    kb = reef_b200.Bases(ctx, "pallas", gens_raw, 255)          # the commitment key is static: registered once (cached levels)
+    got, ms = timed_wall(lambda: G.ipa_prove(ctx, "pallas", kb, gen_c, a, b, ShaTranscript(b"ipa", FQ)))
+    got_f, ms_f = timed_wall(lambda: G.ipa_prove(ctx, "pallas", gens_raw, gen_c, a, b, ShaTranscript(b"ipa", FQ)))
+    kb.free()
+    if got_f != got:
+        raise ParityError("IPA over registered generators differs from the folding session")
+    entry = {"n": n, "rounds": n.bit_length() - 1, "ms": round(ms, 3), "ms_folding_generators": round(ms_f, 3),
+             "what": "reef_ipa_begin_bases/round/fold/finish over the registered commitment key: per round ONE two-row MSM (L, R) over the "
+                     "precomputed window levels, the folds of a, b and of the per-generator weights on the device; `ms_folding_generators` = "
+                     "the session that folds the generators every round (reef_ipa_begin), same proof"}
     if not no_cpu:
         from oracle import cport, snark as N
         from oracle.curves import PALLAS
@@ -880,7 +887,9 @@ def opening_phases(ctxs, w, gp, K, no_cpu):
         hg, hc = graw[:64 * cols], pts(graw[64 * cols:], 1)[0]
         q = [rnd.randrange(FQ) for _ in range(ell)]
         tab = ctxs["pri"].table_u32(w["udoc"])
-        (v, proof), ms = timed_wall(lambda: G.hyrax_prove_eval(ctx, tab, rows, cols, hg, hc, q, ShaTranscript(b"hyrax", FQ)))
+        hb = reef_b200.Bases(ctx, "pallas", hg, 255)
+        (v, proof), ms = timed_wall(lambda: G.hyrax_prove_eval(ctx, tab, rows, cols, hb, hc, q, ShaTranscript(b"hyrax", FQ)))
+        hb.free()
         entry = {"shape": f"{rows} x {cols}", "ms": round(ms, 3),
                  "what": "LZ = L^T M over the resident u32 document table (reef_hyrax_lz) + one IPA of length 2^right"}
         if not no_cpu:
@@ -1022,30 +1031,47 @@ def multi_gpu_extras(args, ctxs, gp, w, rank, world, dist, timed_fn, K, Wm, ms_s
                                 "speedup_vs_1gpu_same_doc": round(ms1 / (ms_sharded / K), 3),
                                 "what": f"the same {w['doc_len']}-char document, un-sharded pass on rank 0 alone (other ranks idle)"}
     dist.barrier()
-    # (b) a throughput-sized MSM sharded by Pippenger windows, 128-byte all-gather by the library's mailbox kernel
-    lg = args.msm_large_log2 or 20
-    n = 1 << lg
-    bases = reef_b200.Bases(ctxs["pri"], "pallas", WL.generators("pallas", n))
-    raw = np.random.default_rng(lg).integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
-    raw[:, 3] &= (1 << 61) - 1
-    devs = torch.from_numpy(raw.view(np.int64)).cuda()
-    res, whole = C.create_string_buffer(64), C.create_string_buffer(64)
-    check(lib.reef_msm_dev(ctxs["pri"]._h, bases._h, C.c_void_p(devs.data_ptr()), n, whole))          # un-sharded reference + scratch sizing
-    dist.barrier()
-    ms_m, _ = timed_fn(lambda: check(lib.reef_msm_sharded_dev(ctxs["pri"]._h, bases._h, C.c_void_p(devs.data_ptr()), n, res)), K, Wm)
-    if res.raw != whole.raw:
-        raise ParityError("window-sharded MSM differs from the un-sharded MSM")
-    ms_1, _ = timed_fn(lambda: check(lib.reef_msm_dev(ctxs["pri"]._h, bases._h, C.c_void_p(devs.data_ptr()), n, whole)), K, Wm)
-    Wn, c = bases.windows, bases.window_bits
-    ops = 10.0 * n * Wn + 14.0 * Wn * (1 << c)
-    out["msm_sharded"] = {"n": n, "windows": Wn, "window_bits": c, "ranks": world, "ms": round(ms_m / K, 3), "mops": round(n / (ms_m / K) / 1e3, 1),
-                          "achieved_modmul_per_s": round(ops / (ms_m / K / 1e3), 0),
-                          "frac_of_world_peak": round(ops / (ms_m / K / 1e3) / (world * peaks["modmul_per_s"]), 4),
-                          "frac_of_one_gpu_peak": round(ops / (ms_m / K / 1e3) / peaks["modmul_per_s"], 4),
-                          "one_gpu_ms": round(ms_1 / K, 3), "speedup_vs_1gpu": round(ms_1 / ms_m, 3),
-                          "verified": "sharded result == un-sharded result on every rank (bit for bit)",
-                          "exchange": "128-byte XYZZ partial per rank, all-gather by a kernel of the library over NVLink peer mailboxes, combine on every rank"}
-    bases.free()
+    # (b) throughput-sized MSMs sharded by Pippenger windows, 128-byte all-gather by the library's mailbox kernel
+    def sharded_msm(lg, reps):
+        n = 1 << lg
+        distinct = min(n, 1 << 20)
+        pts = WL.generators("pallas", distinct) * (n // distinct)    # beyond 2^20 terms the points repeat (a valid MSM all the same)
+        bases = reef_b200.Bases(ctxs["pri"], "pallas", pts)
+        del pts
+        raw = np.random.default_rng(lg).integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
+        raw[:, 3] &= (1 << 61) - 1
+        devs = torch.from_numpy(raw.view(np.int64)).cuda()
+        del raw
+        res, whole = C.create_string_buffer(64), C.create_string_buffer(64)
+        check(lib.reef_msm_dev(ctxs["pri"]._h, bases._h, C.c_void_p(devs.data_ptr()), n, whole))          # un-sharded reference + scratch sizing
+        dist.barrier()
+        ms_m, _ = timed_fn(lambda: check(lib.reef_msm_sharded_dev(ctxs["pri"]._h, bases._h, C.c_void_p(devs.data_ptr()), n, res)), reps, min(Wm, reps))
+        if res.raw != whole.raw:
+            raise ParityError("window-sharded MSM differs from the un-sharded MSM")
+        ms_1, _ = timed_fn(lambda: check(lib.reef_msm_dev(ctxs["pri"]._h, bases._h, C.c_void_p(devs.data_ptr()), n, whole)), reps, min(Wm, reps))
+        Wn, c = bases.windows, bases.window_bits
+        ops = 10.0 * n * Wn + 14.0 * Wn * (1 << c)
+        bases.free()
+        del devs
+        torch.cuda.empty_cache()
+        return {"n": n, "distinct_points": distinct, "windows": Wn, "window_bits": c, "ranks": world, "ms": round(ms_m / reps, 3),
+                "mops": round(n / (ms_m / reps) / 1e3, 1), "achieved_modmul_per_s": round(ops / (ms_m / reps / 1e3), 0),
+                "frac_of_world_peak": round(ops / (ms_m / reps / 1e3) / (world * peaks["modmul_per_s"]), 4),
+                "frac_of_one_gpu_peak": round(ops / (ms_m / reps / 1e3) / peaks["modmul_per_s"], 4),
+                "one_gpu_ms": round(ms_1 / reps, 3), "speedup_vs_1gpu": round(ms_1 / ms_m, 3),
+                "windows_per_rank_max": -(-Wn // world),
+                "verified": "sharded result == un-sharded result on every rank (bit for bit)",
+                "exchange": "128-byte XYZZ partial per rank, all-gather by a kernel of the library over NVLink peer mailboxes, combine on every rank"}
+
+    out["msm_sharded"] = sharded_msm(args.msm_large_log2 or 20, K)
+    if args.msm_shard_large_log2 and world >= 4:
+        # the size at which the replicated bucket reduction is amortised (BASELINE north_star: MSM roofline at 8 GPUs)
+        try:
+            out["msm_sharded_large"] = sharded_msm(args.msm_shard_large_log2, 2)
+        except ParityError:
+            raise
+        except Exception as e:                                   # memory / time limits of the box: the line survives
+            out["msm_sharded_large"] = {"skipped": f"{type(e).__name__}: {e}"[:300]}
 
     # (c) commit phase split over the ranks: Hyrax rows and Merkle subtrees (one NCCL all-gather each)
     def gather(b):
@@ -1270,6 +1296,8 @@ def main():
     ap.add_argument("--also", default="cfg2,cfg3,cfg4,cfg5",
                     help="other BASELINE configs timed at N = 1 (value/e2e/commit, each verified) and reported under 'also'; '' = none")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg AND the verification against it")
+    ap.add_argument("--msm-shard-large-log2", type=int, default=24,
+                    help="at >= 4 GPUs: a second window-sharded MSM of this size (0 = skip)")
     ap.add_argument("--no-openings", action="store_true", help="skip the opening-proof phases (IPA, Hyrax prove_eval)")
     ap.add_argument("--no-commit", action="store_true", help="skip the commit phase of the main workload (profiling runs)")
     ap.add_argument("--msm-large-log2", type=int, default=20, help="size of the stand-alone MSM roofline measurement (0 = skip)")

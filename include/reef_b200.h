@@ -49,9 +49,10 @@ int reef_init(int device, reef_ctx** out);
 /* Same, with the context's stream at the highest (latency_critical != 0) or lowest CUDA stream priority: the contexts that
  * run the Fiat-Shamir chains (sum-checks) are latency-critical, the ones that run the fold commitments are not. */
 int reef_init_prio(int device, int latency_critical, reef_ctx** out);
-/* SMs the context's kernels may run on.  A background context (latency_critical = 0) lives in a CUDA green context that
- * owns all but REEF_RESERVE_SMS (default 12) SMs, so that the single-CTA Fiat-Shamir kernels of the latency-critical
- * contexts always find an empty SM; when the driver cannot partition the device this is the whole chip. */
+/* SMs the context's kernels may run on.  With REEF_RESERVE_SMS=k in the environment (opt-in; 12 is the natural value on
+ * B200) a background context (latency_critical = 0) lives in a CUDA green context that owns all but k SMs, so that the
+ * single-CTA Fiat-Shamir kernels of the latency-critical contexts always find an empty SM; otherwise, or when the driver
+ * cannot partition the device, this is the whole chip. */
 uint32_t reef_ctx_sm_count(const reef_ctx* ctx);
 void reef_shutdown(reef_ctx* ctx);
 int reef_sync(reef_ctx* ctx);
@@ -372,6 +373,13 @@ int reef_vec_axpy(reef_ctx* ctx, int field, const uint8_t a[32], const uint8_t* 
 typedef struct reef_ipa reef_ipa;
 int reef_ipa_begin(reef_ctx* ctx, int curve, const uint8_t* gens, const uint8_t gen_c[64], const uint8_t* a, const uint8_t* b, uint64_t n,
                    reef_ipa** out);
+/* The same session over REGISTERED generators (the static commitment key: reef_bases_register with scalar_bits = 255;
+ * the first n are used): the generators are never folded -- after rounds r_0..r_(i-1) the folded generator G'_j is
+ * sum_{k = j mod m} w[k] G_k with w[k] = prod_t (bit_t(k) ? r_t : r_t^-1), so every round is ONE two-row MSM (L, R) over
+ * the original generators, whose window levels were precomputed at registration, and reef_ipa_fold only updates the
+ * weights.  Same proofs, ~20x less time per proof at n = 2^15 (profiles/r02_summary.md). */
+int reef_ipa_begin_bases(reef_ctx* ctx, const reef_bases* gens, const uint8_t gen_c[64], const uint8_t* a, const uint8_t* b, uint64_t n,
+                         reef_ipa** out);
 int reef_ipa_round(reef_ipa* s, uint8_t out_L[64], uint8_t out_R[64]);
 int reef_ipa_fold(reef_ipa* s, const uint8_t r[32], const uint8_t r_inv[32]);
 int reef_ipa_finish(reef_ipa* s, uint8_t out_a[32], uint8_t out_b[32], uint8_t out_g[64]);

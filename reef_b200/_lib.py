@@ -145,6 +145,7 @@ _sig = {
     "reef_nova_cross_term": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_uint64, _vp]),
     "reef_vec_axpy": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_uint64, _vp]),
     "reef_ipa_begin": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_uint64, C.POINTER(_vp)]),
+    "reef_ipa_begin_bases": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_uint64, C.POINTER(_vp)]),
     "reef_ipa_round": (C.c_int, [_vp, _vp, _vp]),
     "reef_ipa_fold": (C.c_int, [_vp, _vp, _vp]),
     "reef_ipa_finish": (C.c_int, [_vp, _vp, _vp, _vp]),

@@ -204,11 +204,13 @@ int reef_init_prio(int device, int latency_critical, reef_ctx** out) { return in
 // SM partition for BACKGROUND contexts (reef_init_prio(.., 0, ..)).  The Fiat-Shamir kernels of a latency-critical
 // context are single CTAs that want an SM to themselves; while the grids of a background MSM fill the chip such a
 // CTA waits for a whole SM to drain -- measured: 0.6 ms of a 5.8 ms pass (profiles/r02_summary.md).  Background
-// streams are therefore created inside a CUDA green context that owns all but REEF_RESERVE_SMS (default 12 = what
-// is left when 136 of 148 SMs are split off in groups of 8) SMs: their kernels can never occupy the remaining SMs,
-// which the latency-critical kernels (primary context: every SM) then find empty.  Driver API through dlopen (the
-// library must still load, for the symbol checks, where no driver is installed); any failure falls back to an
-// ordinary low-priority stream.
+// streams can therefore be created inside a CUDA green context that owns all but REEF_RESERVE_SMS SMs (12 = what is
+// left when 136 of 148 SMs are split off in groups of 8): their kernels can never occupy the remaining SMs, which the
+// latency-critical kernels (primary context: every SM) then find empty.  OPT-IN (REEF_RESERVE_SMS unset or 0 = an
+// ordinary low-priority stream): it recovers about half of the interference (5.72 -> 5.65 ms per pass), and Nsight
+// Compute's launch-list mode fails on kernels of a green context (LaunchFailed), so profiling runs keep it off.
+// Driver API through dlopen (the library must still load, for the symbol checks, where no driver is installed); any
+// failure falls back to the ordinary stream.
 // ---------------------------------------------------------------------------------------
 namespace {
 struct GreenPartition {
@@ -225,7 +227,7 @@ GreenPartition g_green[16];
 cudaStream_t green_stream(int device, int sm_total, int priority, unsigned* sms_out) {
   if (device < 0 || device >= 16) return nullptr;
   const char* e = getenv("REEF_RESERVE_SMS");
-  const int reserve = e ? atoi(e) : 12;
+  const int reserve = e ? atoi(e) : 0;
   if (reserve <= 0 || reserve >= sm_total) return nullptr;
   static void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
   if (!lib) return nullptr;
@@ -1428,14 +1430,6 @@ int reef_hosttest_poseidon_permute(const uint8_t in[160], uint8_t out[160]) {
 // ---------------------------------------------------------------------------------------
 #include "ec.cuh"
 
-struct reef_bases {
-  reef_ctx* ctx;
-  int curve;
-  uint64_t n;
-  uint32_t scalar_bits;
-  MsmPlanPublic plan;
-  void* d_levels;
-};
 
 template <class C>
 static void hosttest_ec(int op, const uint8_t* p, const uint8_t* q, uint8_t* out) {

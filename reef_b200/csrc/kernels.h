@@ -123,3 +123,13 @@ struct MsmRowsArgs {
 int msm_rows_run(reef_ctx* c, int curve, const MsmRowsArgs& a);
 
 }  // namespace reef
+
+// registered generators (reef_bases_register): shared by api.cu and the IPA session of sumcheck.cu
+struct reef_bases {
+  reef_ctx* ctx;
+  int curve;
+  uint64_t n;
+  uint32_t scalar_bits;
+  reef::MsmPlanPublic plan;
+  void* d_levels;
+};

@@ -303,6 +303,48 @@ __global__ void k_ipa_fold_scalars(const Fe<S>* __restrict__ a, const Fe<S>* __r
   st256(b_out + i, fe_add<S>(mont_mul<S>(rinv_mont, ld256(b + i)), mont_mul<S>(r_mont, ld256(b + half + i))));
 }
 
+// ---- IPA over STATIC (registered) generators: the generators are never folded.  After rounds r_0 .. r_(i-1) the
+// folded generator G'_j is  sum_{k = j mod m} w[k] G_k  with  w[k] = prod_t (bit_t(k) ? r_t : r_t^-1)  (bit_t = t-th index
+// bit from the top), so  L = <a_lo, G'_hi> = sum_k [k mod m >= h] a[(k mod m) - h] w[k] G_k  and likewise R: every round is
+// one two-row MSM over the ORIGINAL generators, whose window levels were precomputed once at registration.
+template <class S>
+__global__ void k_ipa_fill_one(Fe<S>* __restrict__ w, uint64_t n) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) st256(w + k, fe_one<S>());
+}
+template <class S>
+__global__ void k_ipa_weights(Fe<S>* __restrict__ w, uint64_t n, uint32_t shift, Fe<S> r_mont, Fe<S> rinv_mont) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) st256(w + k, mont_mul<S>(ld256(w + k), ((k >> shift) & 1) ? r_mont : rinv_mont));
+}
+// rows of the round's MSM: out[0][k] = L scalars, out[1][k] = R scalars (canonical), k <= n (entry n = c_L / c_R for gen_c)
+template <class S>
+__global__ void k_ipa_scalars(const Fe<S>* __restrict__ a, const Fe<S>* __restrict__ w_mont, uint64_t m, uint64_t n,
+                              const Fe<S>* __restrict__ c2, Fe<S>* __restrict__ out) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > n) return;
+  if (k == n) {
+    st256(out + n, ld256(c2));
+    st256(out + (n + 1) + n, ld256(c2 + 1));
+    return;
+  }
+  const uint64_t h = m >> 1, j = k & (m - 1);
+  const Fe<S> w = ld256(w_mont + k);
+  const Fe<S> zero = fe_zero<S>();
+  if (j >= h) {
+    st256(out + k, mont_mul<S>(w, ld256(a + (j - h))));
+    st256(out + (n + 1) + k, zero);
+  } else {
+    st256(out + k, zero);
+    st256(out + (n + 1) + k, mont_mul<S>(w, ld256(a + (j + h))));
+  }
+}
+template <class S>
+__global__ void k_ipa_from_mont(const Fe<S>* __restrict__ w_mont, uint64_t n, Fe<S>* __restrict__ out) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) st256(out + k, from_mont<S>(ld256(w_mont + k)));
+}
+
 }  // namespace reef
 
 // ---------------------------------------------------------------------------------------
@@ -317,6 +359,11 @@ struct reef_ipa {
   int cur;
   char *d_gc, *d_tmpG, *d_tmpS, *d_lv, *d_c;
   int* d_bad;
+  // static-generator mode (reef_ipa_begin_bases)
+  int static_gens;
+  reef::MsmPlanPublic plan;
+  char *d_levels_s, *d_w, *d_scal;   // levels[L][n0 + 1] (gen_c appended), weights (Montgomery), 2 x (n0 + 1) scalars
+  uint32_t rounds_done, k_bits;
 };
 
 struct reef_sumcheck {
@@ -758,8 +805,121 @@ int reef_ipa_begin(reef_ctx* c, int curve, const uint8_t* gens, const uint8_t ge
 
 }  // extern "C"
 
+// static-generator session: levels of the registered generators + the levels of gen_c as one more base
+template <class SC, class CC>
+static int ipa_begin_bases_t(reef_ctx* c, const reef_bases* gb, const uint8_t* gen_c, const uint8_t* a, const uint8_t* b, uint64_t n,
+                             reef_ipa** out) {
+  reef_ipa* s = new reef_ipa;
+  memset(s, 0, sizeof(*s));
+  s->ctx = c;
+  s->curve = gb->curve;
+  s->n0 = s->n = n;
+  s->static_gens = 1;
+  s->plan = gb->plan;
+  s->k_bits = 0;
+  while (((uint64_t)1 << s->k_bits) < n) s->k_bits++;
+  const uint32_t L = gb->plan.L;
+  const size_t lev_bytes = (size_t)L * (n + 1) * 64;
+  const size_t bytes = 4 * n * 32 + lev_bytes + n * 32 + 2 * (n + 1) * 32 + 64 + (size_t)L * 64 + 64 + 256;
+  cudaError_t e = cudaMalloc(&s->d_buf, bytes);
+  if (e != cudaSuccess) {
+    delete s;
+    return fail(REEF_ENOMEM, std::string("reef_ipa_begin_bases: ") + cudaGetErrorString(e));
+  }
+  char* p = (char*)s->d_buf;
+  s->d_levels_s = p; p += lev_bytes;
+  for (int k = 0; k < 2; k++) { s->d_a[k] = p; p += n * 32; }
+  for (int k = 0; k < 2; k++) { s->d_b[k] = p; p += n * 32; }
+  s->d_w = p; p += n * 32;
+  s->d_scal = p; p += 2 * (n + 1) * 32;
+  s->d_gc = p; p += 64;
+  s->d_lv = p; p += (size_t)L * 64;      // levels of gen_c alone
+  s->d_c = p; p += 64;
+  s->d_bad = (int*)p;
+  cudaStream_t st = c->stream;
+  e = cudaMemcpyAsync(s->d_a[0], a, n * 32, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_b[0], b, n * 32, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_gc, gen_c, 64, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->d_bad, 0, 4, st);
+  int rc = REEF_OK;
+  if (e == cudaSuccess) rc = msm_levels_from_dev(c, s->curve, s->d_gc, 1, gb->plan, s->d_lv, s->d_bad);
+  // level l of the session = [the first n registered points of level l | level l of gen_c]
+  if (e == cudaSuccess && !rc)
+    e = cudaMemcpy2DAsync(s->d_levels_s, (n + 1) * 64, gb->d_levels, (size_t)gb->n * 64, n * 64, L, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess && !rc)
+    e = cudaMemcpy2DAsync(s->d_levels_s + n * 64, (n + 1) * 64, s->d_lv, 64, 64, L, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess && !rc) {
+    k_ipa_fill_one<SC><<<sc_cdiv(n, 128), 128, 0, st>>>((Fe<SC>*)s->d_w, n);
+    e = cudaGetLastError();
+  }
+  int bad = 0;
+  if (e == cudaSuccess && !rc) e = cudaMemcpyAsync(&bad, s->d_bad, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && !rc) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess || rc || bad) {
+    cudaFree(s->d_buf);
+    delete s;
+    if (rc) return rc;
+    if (bad) return fail(REEF_EINVAL, "reef_ipa_begin_bases: gen_c is not on the curve");
+    return fail(REEF_ECUDA, std::string("reef_ipa_begin_bases: ") + cudaGetErrorString(e));
+  }
+  ctx_retain(c);
+  *out = s;
+  return REEF_OK;
+}
+
+extern "C" int reef_ipa_begin_bases(reef_ctx* c, const reef_bases* gens, const uint8_t gen_c[64], const uint8_t* a, const uint8_t* b, uint64_t n,
+                                    reef_ipa** out) {
+  REEF_REQUIRE(c && gens && gen_c && a && b && out, REEF_EINVAL, "reef_ipa_begin_bases: NULL argument");
+  REEF_REQUIRE(gens->ctx == c, REEF_EINVAL, "reef_ipa_begin_bases: generators belong to another context");
+  REEF_REQUIRE(n >= 1 && (n & (n - 1)) == 0, REEF_EASSERT, "reef_ipa_begin_bases: the vector length must be a power of two");
+  REEF_REQUIRE(n <= gens->n, REEF_EASSERT, "reef_ipa_begin_bases: not enough generators");
+  REEF_REQUIRE(gens->scalar_bits == 255 && gens->plan.G == 1, REEF_EINVAL,
+               "reef_ipa_begin_bases: generators must be registered for 255-bit scalars with all window levels precomputed");
+  const int sfield = gens->curve == 0 ? 0 : 1, cfield = gens->curve == 0 ? 1 : 0;
+  int rc = check_canon_field(a, n, sfield, "reef_ipa_begin_bases: a");
+  if (!rc) rc = check_canon_field(b, n, sfield, "reef_ipa_begin_bases: b");
+  if (!rc) rc = check_canon_field(gen_c, 2, cfield, "reef_ipa_begin_bases: generator coordinate");
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  REEF_CTX_LIVE(c, "reef_ipa_begin_bases");
+  REEF_CUDA(cudaSetDevice(c->device));
+  return gens->curve == 0 ? ipa_begin_bases_t<FqCfg, FpCfg>(c, gens, gen_c, a, b, n, out) : ipa_begin_bases_t<FpCfg, FqCfg>(c, gens, gen_c, a, b, n, out);
+}
+
+// one round over the static generators: ONE two-row MSM (L, R) over n0 + 1 precomputed bases
+template <class SC>
+static int ipa_round_static_t(reef_ipa* s, uint8_t* out_L, uint8_t* out_R) {
+  reef_ctx* c = s->ctx;
+  cudaStream_t st = c->stream;
+  const uint64_t m = s->n, h = m / 2, n = s->n0;
+  const char *a = s->d_a[s->cur], *b = s->d_b[s->cur];
+  k_ipa_dots<SC><<<1, 256, 0, st>>>((const Fe<SC>*)a, (const Fe<SC>*)b, h, (Fe<SC>*)s->d_c);
+  REEF_LAUNCHED();
+  k_ipa_scalars<SC><<<sc_cdiv(n + 1, 128), 128, 0, st>>>((const Fe<SC>*)a, (const Fe<SC>*)s->d_w, m, n, (const Fe<SC>*)s->d_c, (Fe<SC>*)s->d_scal);
+  REEF_LAUNCHED();
+  MsmRowsArgs ar;
+  ar.plan = s->plan;
+  ar.d_levels = s->d_levels_s;
+  ar.n_bases = n + 1;
+  ar.d_scalars = s->d_scal;
+  ar.scalars_u32 = 0;
+  ar.scalar_bits = 255;
+  ar.rows = 2;
+  ar.cols = n + 1;
+  ar.d_blinds = nullptr;
+  ar.blind_base = n + 1;
+  uint8_t lr[128];
+  ar.h_out = lr;
+  int rc = msm_rows_run(c, s->curve, ar);
+  if (rc) return rc;
+  memcpy(out_L, lr, 64);
+  memcpy(out_R, lr + 64, 64);
+  return REEF_OK;
+}
+
 template <class SC>
 static int ipa_round_t(reef_ipa* s, uint8_t* out_L, uint8_t* out_R) {
+  if (s->static_gens) return ipa_round_static_t<SC>(s, out_L, out_R);
   reef_ctx* c = s->ctx;
   cudaStream_t st = c->stream;
   const uint64_t h = s->n / 2;
@@ -823,6 +983,14 @@ static int ipa_fold_session_t(reef_ipa* s, const uint8_t* r, const uint8_t* r_in
   k_ipa_fold_scalars<SC><<<sc_cdiv(h, 128), 128, 0, st>>>((const Fe<SC>*)s->d_a[s->cur], (const Fe<SC>*)s->d_b[s->cur], h, rm, rim,
                                                           (Fe<SC>*)s->d_a[nx], (Fe<SC>*)s->d_b[nx]);
   REEF_LAUNCHED();
+  if (s->static_gens) {                          // the generators stay; their fold lives in the weights
+    k_ipa_weights<SC><<<sc_cdiv(s->n0, 128), 128, 0, st>>>((Fe<SC>*)s->d_w, s->n0, s->k_bits - 1 - s->rounds_done, rm, rim);
+    REEF_LAUNCHED();
+    s->rounds_done++;
+    s->cur = nx;
+    s->n = h;
+    return REEF_OK;
+  }
   Scalar256 lo, hi;                              // ck' = ck_lo * r^-1 + ck_hi * r
   for (int i = 0; i < 8; i++) {
     lo.w[i] = (uint32_t)r_inv[4 * i] | ((uint32_t)r_inv[4 * i + 1] << 8) | ((uint32_t)r_inv[4 * i + 2] << 16) | ((uint32_t)r_inv[4 * i + 3] << 24);
@@ -860,6 +1028,27 @@ int reef_ipa_finish(reef_ipa* s, uint8_t out_a[32], uint8_t out_b[32], uint8_t o
   REEF_CUDA(cudaSetDevice(c->device));
   REEF_CUDA(cudaMemcpyAsync(out_a, s->d_a[s->cur], 32, cudaMemcpyDeviceToHost, c->stream));
   REEF_CUDA(cudaMemcpyAsync(out_b, s->d_b[s->cur], 32, cudaMemcpyDeviceToHost, c->stream));
+  if (s->static_gens) {
+    // G_hat = sum_k w[k] G_k: one MSM of the fold weights over the original generators
+    const uint64_t n = s->n0;
+    if (s->curve == 0) k_ipa_from_mont<FqCfg><<<sc_cdiv(n, 128), 128, 0, c->stream>>>((const Fe<FqCfg>*)s->d_w, n, (Fe<FqCfg>*)s->d_scal);
+    else k_ipa_from_mont<FpCfg><<<sc_cdiv(n, 128), 128, 0, c->stream>>>((const Fe<FpCfg>*)s->d_w, n, (Fe<FpCfg>*)s->d_scal);
+    REEF_LAUNCHED();
+    MsmRunArgs ar;
+    ar.plan = s->plan;
+    ar.d_levels = s->d_levels_s;
+    ar.n_bases = n + 1;
+    ar.d_scalars = s->d_scal;
+    ar.scalars_u32 = 0;
+    ar.n = n;
+    ar.w_begin = 0;
+    ar.w_end = s->plan.W;
+    ar.h_out_affine = out_g;
+    ar.h_out_xyzz = nullptr;
+    ar.h_extra_xyzz_mont = nullptr;
+    ar.n_extra = 0;
+    return msm_run(c, s->curve, ar);          // synchronises the stream
+  }
   REEF_CUDA(cudaMemcpyAsync(out_g, s->d_G[s->cur], 64, cudaMemcpyDeviceToHost, c->stream));
   REEF_CUDA(cudaStreamSynchronize(c->stream));
   return REEF_OK;

@@ -47,10 +47,15 @@ class Ipa:
     """Device-resident IPA prover session (reef_ipa_*)."""
 
     def __init__(self, ctx, curve: str, gens, gen_c, a, b):
+        """gens: points / bytes (folded on the device every round) or a registered `Bases` handle (static commitment key:
+        never folded, every round is one two-row MSM over the precomputed window levels -- reef_ipa_begin_bases)"""
         h = C.c_void_p()
         self.n = len(a)
-        check(lib.reef_ipa_begin(ctx._h, _CURVES[curve], _buf(_points_bytes(gens)[:64 * self.n]), _buf(_pt_bytes(gen_c)),
-                                 _buf(_pack(a)), _buf(_pack(b)), self.n, C.byref(h)))
+        if hasattr(gens, "_h") and hasattr(gens, "msm"):
+            check(lib.reef_ipa_begin_bases(ctx._h, gens._h, _buf(_pt_bytes(gen_c)), _buf(_pack(a)), _buf(_pack(b)), self.n, C.byref(h)))
+        else:
+            check(lib.reef_ipa_begin(ctx._h, _CURVES[curve], _buf(_points_bytes(gens)[:64 * self.n]), _buf(_pt_bytes(gen_c)),
+                                     _buf(_pack(a)), _buf(_pack(b)), self.n, C.byref(h)))
         self._h = h
 
     def round(self):

@@ -151,18 +151,18 @@ def test_msm_throughput_shapes_known_discrete_logs(ctx):
 
 
 def test_background_context_keeps_off_the_reserved_sms_and_stays_exact():
-    """reef_init_prio(.., 0, ..): the background context's stream lives in a green-context partition that leaves
-    REEF_RESERVE_SMS SMs to the latency-critical contexts; results are unchanged -- single MSM, the W / T pair as two
-    rows, u32 rows with blinds"""
+    """reef_init_prio(.., 0, ..) with REEF_RESERVE_SMS=12: the background context's stream lives in a green-context
+    partition that leaves 12 SMs to the latency-critical contexts; results are unchanged -- single MSM, the W / T pair as
+    two rows, u32 rows with blinds"""
     import numpy as np
     import workloads as WL
     from oracle import cport
     import os
-    bg = reef_b200.Context(0, latency_critical=False)
     hi = reef_b200.Context(0, latency_critical=True)
-    os.environ["REEF_RESERVE_SMS"] = "0"               # partitioning off: an ordinary low-priority stream
+    bg_half = reef_b200.Context(0, latency_critical=False)      # default: an ordinary low-priority stream
+    os.environ["REEF_RESERVE_SMS"] = "12"                       # opt-in: green-context partition of 136 SMs
     try:
-        bg_half = reef_b200.Context(0, latency_critical=False)
+        bg = reef_b200.Context(0, latency_critical=False)
     finally:
         del os.environ["REEF_RESERVE_SMS"]
     from reef_b200._lib import lib

@@ -42,6 +42,46 @@ def test_ipa_matches_oracle_and_verifies(ctx, name, n):
     assert N.ipa_verify(curve, gens, gen_c, comm, b, c, got, N.Transcript(b"ipa", p), cmsm(curve))
 
 
+@pytest.mark.parametrize("name,n", [("pallas", 1), ("pallas", 2), ("vesta", 64), ("pallas", 4096)])
+def test_ipa_over_registered_generators_gives_the_same_proof(ctx, name, n):
+    """reef_ipa_begin_bases: the generators are never folded (every round = one two-row MSM over the registered window
+    levels, the fold lives in per-generator weights) -- same L, R, a_hat as the folding session and the oracle, and the
+    final folded generator / b_hat agree with the folding session"""
+    import reef_b200
+    curve = PALLAS if name == "pallas" else VESTA
+    p = curve.order
+    rnd = random.Random(1000 + n)
+    gens = _gens(name, n + 3)                          # more registered generators than the argument uses
+    gen_c = curve.mul(rnd.randrange(p), gens[0])
+    a = [rnd.randrange(p) for _ in range(n)]
+    b = [rnd.randrange(p) for _ in range(n)]
+    bases = reef_b200.Bases(ctx, name, gens, 255)
+    try:
+        got = G.ipa_prove(ctx, name, bases, gen_c, a, b, N.Transcript(b"ipa", p))
+        exp = N.ipa_prove(curve, gens[:n], gen_c, a, b, N.Transcript(b"ipa", p), cmsm(curve))
+        assert got == exp
+        comm, c = cmsm(curve)(a, gens[:n]), N.inner(a, b, p)
+        assert N.ipa_verify(curve, gens[:n], gen_c, comm, b, c, got, N.Transcript(b"ipa", p), cmsm(curve))
+        # finish(): a_hat, b_hat, G_hat of both session kinds agree
+        fins = []
+        for g in (bases, gens[:n]):
+            s = G.Ipa(ctx, name, g, gen_c, a, b)
+            tr = N.Transcript(b"ipa", p)
+            m = n
+            while m > 1:
+                L, R = s.round()
+                tr.absorb_point(b"L", L)
+                tr.absorb_point(b"R", R)
+                r = tr.squeeze(b"r")
+                s.fold(r, pow(r, -1, p))
+                m //= 2
+            fins.append(s.finish())
+            s.free()
+        assert fins[0] == fins[1]
+    finally:
+        bases.free()
+
+
 def test_hyrax_prove_eval_on_the_document_table(ctx):
     """configs[1] shape: 2^17 document codes as a 256 x 512 matrix, commitment by rows, opening at a random point"""
     ab, cps = W.document("cfg2")

@@ -27,6 +27,9 @@ int reef_hosttest_poseidon_permute(const uint8_t in[160], uint8_t out[160]);
  * rc = 67 * 25 * 32 bytes, mds = 25 * 25 * 32 bytes */
 int reef_hosttest_poseidon_ro(int field, const uint8_t* elems, uint64_t n, uint8_t out[32]);
 int reef_hosttest_poseidon_ro_constants(int field, uint8_t* rc, uint8_t* mds);
+/* 1 when the optimised width-25 schedule derived on the host (sparse partial rounds, rescaled lane 0: what the GPU
+ * kernel runs) reproduced the textbook permutation on the host test vectors; 0 makes the library use the textbook kernel */
+int reef_hosttest_poseidon_ro_fast_ok(int field);
 
 /* curve formulas (ec.cuh), host instantiation.  curve: 0 Pallas, 1 Vesta.  Points affine 64 B.
  * op: 0 P+Q via XYZZ full add, 1 P+Q via mixed add, 2 2P, 3 P-Q via mixed add (neg), 4 k*P (k = first 8 bytes of q) */

@@ -163,6 +163,7 @@ _sig = {
     "reef_cmt_nldoc_write": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(C.c_uint64)]),
     "reef_hosttest_poseidon_ro": (C.c_int, [C.c_int, _vp, C.c_uint64, _vp]),
     "reef_hosttest_poseidon_ro_constants": (C.c_int, [C.c_int, _vp, _vp]),
+    "reef_hosttest_poseidon_ro_fast_ok": (C.c_int, [C.c_int]),
     "reef_hosttest_field_op": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp]),
     "reef_hosttest_mul_wide": (C.c_int, [_vp, _vp, _vp]),
     "reef_hosttest_poseidon_permute": (C.c_int, [_vp, _vp]),

@@ -1885,6 +1885,10 @@ int reef_hosttest_poseidon_ro(int field, const uint8_t* elems, uint64_t n, uint8
   poseidon_ro_host(field, elems, n, out);
   return REEF_OK;
 }
+int reef_hosttest_poseidon_ro_fast_ok(int field) {
+  if (field != 0 && field != 1) return -1;
+  return poseidon_ro_fast_ok_host(field);
+}
 int reef_hosttest_poseidon_ro_constants(int field, uint8_t* rc, uint8_t* mds) {
   if (!rc || !mds || (field != 0 && field != 1)) return REEF_EINVAL;
   poseidon_ro_constants_host(field, rc, mds);

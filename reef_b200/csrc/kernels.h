@@ -31,6 +31,7 @@ int launch_sponge_step(reef_ctx* c, void* d_state, int op, const void* d_in, uin
 int launch_poseidon_ro(reef_ctx* c, int field, const void* d_in, uint64_t n, int triples, void* d_out);
 void poseidon_ro_host(int field, const uint8_t* elems, uint64_t n, uint8_t out[32]);
 void poseidon_ro_constants_host(int field, uint8_t* rc_out, uint8_t* mds_out);
+int poseidon_ro_fast_ok_host(int field);
 
 // ---- mle.cu
 struct NlookupArgs {

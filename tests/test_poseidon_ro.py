@@ -39,6 +39,13 @@ def test_library_constants_equal_the_oracle(name, fid, bp, sp):
 
 
 @pytest.mark.parametrize("name,fid,bp,sp", FIELDS)
+def test_optimised_schedule_derived_on_the_host_equals_the_textbook_rounds(name, fid, bp, sp):
+    """sparse partial rounds + rescaled lane 0 for width 25 (what k_poseidon_ro_fast runs): derived in C++ at first use and
+    cross-checked there against the textbook permutation; 0 would silently select the slower textbook kernel"""
+    assert lib.reef_hosttest_poseidon_ro_fast_ok(fid) == 1
+
+
+@pytest.mark.parametrize("name,fid,bp,sp", FIELDS)
 def test_host_instantiation_and_c_port_equal_the_python_oracle(name, fid, bp, sp):
     rnd = random.Random(fid)
     for n in (1, 2, 23, 24, 25, 48, 50):

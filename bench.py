@@ -356,27 +356,16 @@ class GpuPass:
                 if self.mode == "nldoc":
                     doc_tab = self.pool["doc"].submit(lambda: self.ctxs["doc"].table_u32(self.h_doc)).result()   # H2D of the document codes
                 T_tab = f2.result()
-        prev_nl = prev_doc = None
+        import threading
         msm_futs, owners = [], []
         self.d_futs = []
         wits = []
         first_doc = le32(int(w["udoc"][0]))
-        for s in range(w["steps"]):
-            if self.mode == "hybrid":
-                qh = self.q_hyb[s]
-                prev_doc = self.pool["doc"].submit(self._nlookup, "nlhybrid", hyb_tab, qh[0], qh[1], prev_doc, le32(w["T"][0])).result()
-            else:
-                qn = self.q_nl[s]
-                f_nl = self.pool["nl"].submit(self._nlookup, "nl", T_tab, qn[0], qn[1], prev_nl, None)
-                if self.mode == "merkle":
-                    wits.append(self._merkle_wits(w["q_doc"][s]))
-                elif self.world > 1:
-                    prev_doc = self.pool["doc"].submit(self._nlookup_sharded, doc_tab, w["q_doc"][s],
-                                                       [int(w["udoc"][i]) for i in w["q_doc"][s]], prev_doc).result()
-                else:
-                    qd = self.q_doc[s]
-                    prev_doc = self.pool["doc"].submit(self._nlookup, "nldoc", doc_tab, qd[0], qd[1], prev_doc, first_doc).result()
-                prev_nl = f_nl.result()
+        S = w["steps"]
+        nl_done = [threading.Event() for _ in range(S)]
+
+        def commitments(s):
+            """the fold commitments of fold s: issued once both sum-checks of the fold are done (their witness)"""
             sc, scd = w["sc"][s], (self.sc_dev[s] if resident else None)
             if self.pairs:
                 jobs = [("Wp", "pri", w["n_pri"], "p"), ("Ws", "sec", w["n_sec"], "s")]
@@ -385,7 +374,7 @@ class GpuPass:
             for key, pool, n, pair in jobs:
                 owner = None if self.world == 1 else len(owners) % self.world
                 skip = os.environ.get("REEF_BENCH_SKIP_MSM")          # interference experiments only (never a bench value)
-                if skip == "1" or (skip == "last" and s == w["steps"] - 1) or (skip == "first" and s < w["steps"] - 1):
+                if skip == "1" or (skip == "last" and s == S - 1) or (skip == "first" and s < S - 1):
                     msm_futs.append(None)
                     owners.append(owner)
                     continue
@@ -398,6 +387,40 @@ class GpuPass:
                 else:
                     msm_futs.append(None)
                 owners.append(owner)
+
+        # Two host threads, as in the reference (solver thread / proving thread, framework.rs:98-110): each runs ITS chain of
+        # sum-checks fold after fold without handing control back in between (fold i+1 needs only the running claim of
+        # fold i of the same table); the document chain issues the commitments of a fold as soon as both of its
+        # sum-checks are done.
+        def nl_chain():
+            prev = None
+            for s in range(S):
+                qn = self.q_nl[s]
+                prev = self._nlookup("nl", T_tab, qn[0], qn[1], prev, None)
+                nl_done[s].set()
+            return prev
+
+        def doc_chain():
+            prev = None
+            for s in range(S):
+                if self.mode == "hybrid":
+                    qh = self.q_hyb[s]
+                    prev = self._nlookup("nlhybrid", hyb_tab, qh[0], qh[1], prev, le32(w["T"][0]))
+                else:
+                    if self.mode == "merkle":
+                        wits.append(self._merkle_wits(w["q_doc"][s]))
+                    elif self.world > 1:
+                        prev = self._nlookup_sharded(doc_tab, w["q_doc"][s], [int(w["udoc"][i]) for i in w["q_doc"][s]], prev)
+                    else:
+                        qd = self.q_doc[s]
+                        prev = self._nlookup("nldoc", doc_tab, qd[0], qd[1], prev, first_doc)
+                    nl_done[s].wait()
+                commitments(s)
+            return prev
+
+        f_nl = self.pool["nl"].submit(nl_chain) if self.mode != "hybrid" else None
+        prev_doc = self.pool["doc"].submit(doc_chain).result()
+        prev_nl = f_nl.result() if f_nl is not None else None
         outs = [f.result() if f is not None else None for f in msm_futs]
         ds = [f.result() for f in self.d_futs]
         if self.world > 1:
@@ -738,6 +761,9 @@ def run_reef(args):
                               "commit(W) and commit(T) of a fold share the commitment key and run as the two rows of ONE row-batched MSM per curve "
                               "(reef_msm_rows_dev; at N >= 4 GPUs four separate MSMs round-robin over the ranks); fold i+1 sum-checks overlap fold i "
                               "commitments; calc_d does not gate the next fold",
+                   "registration": "commitment keys (static per PublicParams) are registered once per context BEFORE the timed region "
+                                   "(k_precompute of all window levels: ~13 ms and 50 MiB per 2^15-point key); contexts that register the "
+                                   "same key share one set of levels through the content-keyed cache (reef_bases_cache_stats)",
                    "verified": verified,
                    "parallelism": (f"1 document of {w['doc_len']} chars: nldoc sum-check sharded by low index bits x{world} "
                                    f"(96 bytes per rank per round; the round kernels themselves store them into the peers' mailboxes over NVLink and "

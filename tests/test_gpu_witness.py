@@ -95,6 +95,30 @@ def test_commit_w_over_the_witness_buffer_in_place(ctx):
     w.free()
 
 
+def test_w_and_t_commit_as_two_rows_of_one_msm_over_device_memory(ctx):
+    """reef_msm_rows_dev: commit(W) and commit(T) of a fold (same commitment key, framework.rs:668-675) as ONE row-batched
+    MSM over scalars that already live on the device (here: one witness-sized buffer holding W then T)"""
+    rnd = random.Random(9)
+    n = 1 << 11
+    gens = WL.generators("vesta", n)
+    from oracle.fields import FP
+    w = reef_b200.Witness(ctx, 2 * n)
+    W = [rnd.randrange(2) if rnd.random() < 0.8 else rnd.randrange(FQ) for _ in range(n)]      # witness-like: mostly bits
+    T = [rnd.randrange(FQ) for _ in range(n)]
+    w.set(list(range(2 * n)), W + T)
+    b = reef_b200.Bases(ctx, "vesta", gens)
+    out = C.create_string_buffer(128)
+    check(lib.reef_msm_rows_dev(ctx._h, b._h, C.c_void_p(w.dev_ptr), 2, n, out))
+    pt = reef_b200.backend._pt_from
+    assert pt(out.raw[:64]) == cport.msm("vesta", gens, W, threads=cport.max_threads())
+    assert pt(out.raw[64:]) == cport.msm("vesta", gens, T, threads=cport.max_threads())
+    with pytest.raises(ReefError):
+        lib_rc = lib.reef_msm_rows_dev(ctx._h, b._h, C.c_void_p(w.dev_ptr), 2, n + 1, out)      # more columns than generators
+        check(lib_rc)
+    b.free()
+    w.free()
+
+
 def test_generator_levels_are_shared_between_contexts(ctx):
     hits, entries = C.c_uint64(), C.c_uint64()
     gens = WL.generators("vesta", 1 << 10)

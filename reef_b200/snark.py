@@ -50,12 +50,14 @@ class Ipa:
         """gens: points / bytes (folded on the device every round) or a registered `Bases` handle (static commitment key:
         never folded, every round is one two-row MSM over the precomputed window levels -- reef_ipa_begin_bases)"""
         h = C.c_void_p()
-        self.n = len(a)
+        ab = bytes(a) if isinstance(a, (bytes, bytearray)) else _pack(a)        # vectors as lists of ints or packed 32-byte LE values
+        bb = bytes(b) if isinstance(b, (bytes, bytearray)) else _pack(b)
+        self.n = len(ab) // 32
         if hasattr(gens, "_h") and hasattr(gens, "msm"):
-            check(lib.reef_ipa_begin_bases(ctx._h, gens._h, _buf(_pt_bytes(gen_c)), _buf(_pack(a)), _buf(_pack(b)), self.n, C.byref(h)))
+            check(lib.reef_ipa_begin_bases(ctx._h, gens._h, _buf(_pt_bytes(gen_c)), _buf(ab), _buf(bb), self.n, C.byref(h)))
         else:
             check(lib.reef_ipa_begin(ctx._h, _CURVES[curve], _buf(_points_bytes(gens)[:64 * self.n]), _buf(_pt_bytes(gen_c)),
-                                     _buf(_pack(a)), _buf(_pack(b)), self.n, C.byref(h)))
+                                     _buf(ab), _buf(bb), self.n, C.byref(h)))
         self._h = h
 
     def round(self):
@@ -89,7 +91,7 @@ def ipa_prove(ctx, curve: str, gens, gen_c, a, b, tr):
     s = Ipa(ctx, curve, gens, gen_c, a, b)
     Ls, Rs = [], []
     try:
-        n = len(a)
+        n = s.n
         while n > 1:
             L, R = s.round()
             tr.absorb_point(b"L", L)

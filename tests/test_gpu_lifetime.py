@@ -59,3 +59,29 @@ def test_finalizer_order_is_irrelevant():
     c.close()                                   # idempotent
     del t
     gc.collect()
+
+
+def test_round2_handles_outlive_their_context_too():
+    """witness buffers, IPA sessions (both kinds) and cached generator levels: freed after reef_shutdown, any order"""
+    from reef_b200 import snark as G
+    c = reef_b200.Context(0)
+    w = reef_b200.Witness(c, 64)
+    w.set_small([0, 1], [1, 2])
+    pts = PALLAS.multiples(9)
+    b = c.bases("pallas", pts[:8], 255)
+    b2 = c.bases("pallas", pts[:8], 255)                    # second handle on the same cached levels
+    s1 = G.Ipa(c, "pallas", b, pts[8], [1, 2, 3, 4, 5, 6, 7, 8], [8, 7, 6, 5, 4, 3, 2, 1])
+    s2 = G.Ipa(c, "pallas", pts[:8], pts[8], [1, 2, 3, 4, 5, 6, 7, 8], [8, 7, 6, 5, 4, 3, 2, 1])
+    assert s1.round() == s2.round()
+    c.close()
+    with pytest.raises(ReefError):
+        w.read(0, 2)
+    with pytest.raises(ReefError):
+        s1.round()
+    for f in (b.free, s2.free, w.free, s1.free, b2.free):
+        f()
+    c2 = reef_b200.Context(0)
+    b3 = c2.bases("pallas", pts[:8], 255)                   # the levels were released with their last handle: registered anew
+    assert b3.msm([1] * 8) == PALLAS.msm([1] * 8, pts[:8])
+    b3.free()
+    c2.close()

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_snark.py tests/test_gpu_witness.py -m gpu -x -q --timeout 900 2>&1 | tail -3
+python -m pytest tests/test_gpu_snark.py tests/test_gpu_witness.py tests/test_gpu_lifetime.py -m gpu -x -q --timeout 900 2>&1 | tail -3
 for i in 1 2; do
 python bench.py --steps 5 --also= --no-commit --msm-large-log2 0 --no-cpu-baseline 2>&1 | python -c "
 import json,sys

@@ -354,7 +354,9 @@ class GpuPass:
             else:
                 f2 = self.pool["nl"].submit(self._upload_T)
                 if self.mode == "nldoc":
-                    doc_tab = self.pool["doc"].submit(lambda: self.ctxs["doc"].table_u32(self.h_doc)).result()   # H2D of the document codes
+                    # H2D of the document codes from page-locked memory, queued on the context's copy stream: the first absorb
+                    # of the sum-check (which never reads the table) overlaps it, the first sweep waits for it
+                    doc_tab = self.pool["doc"].submit(lambda: self.ctxs["doc"].table_u32(self.h_doc, async_upload=True)).result()
                 T_tab = f2.result()
         import threading
         msm_futs, owners = [], []

@@ -149,6 +149,11 @@ int reef_merkle_path_wits(const uint64_t* doc, uint64_t n_doc, const uint8_t* le
 int reef_table_upload(reef_ctx* ctx, const uint8_t* table, uint64_t n, reef_table** out);
 /* Document codes (framework.rs:978-1011) as u32: 8x less HBM traffic for the first two passes. */
 int reef_table_upload_u32(reef_ctx* ctx, const uint32_t* codes, uint64_t n, reef_table** out);
+/* The same, but returns as soon as the copy is queued (on the context's copy stream): the first absorb of the next
+ * reef_nlookup_prove on this table (5-7 Poseidon permutations that never read the table) overlaps the upload; every
+ * consumer orders itself behind it.  `codes` must stay valid and unmodified until a call that consumes the table has
+ * returned (or reef_sync); use page-locked memory, with pageable memory the copy is simply not asynchronous. */
+int reef_table_upload_u32_async(reef_ctx* ctx, const uint32_t* codes, uint64_t n, reef_table** out);
 /* The merged table of `--hybrid` (r1cs.rs:481-487 and 2101-2112), built ON THE DEVICE from its two small
  * inputs: [ pub_table (n_pub elements), `fill` up to half_len | then, until the length is 2 * half_len:
  * the document codes followed by zeros up to the next power of two ].  half_len a power of two >= n_pub.

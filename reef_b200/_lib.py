@@ -84,6 +84,7 @@ _sig = {
     "reef_merkle_path_wits": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_uint32, C.c_uint64, _vp, _vp, _vp, _vp]),
     "reef_table_upload": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),
     "reef_table_upload_u32": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),
+    "reef_table_upload_u32_async": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),
     "reef_table_hybrid_u32": (C.c_int, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _vp, C.c_uint64, C.POINTER(_vp)]),
     "reef_table_wrap_dev": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, C.POINTER(_vp)]),
     "reef_table_download": (C.c_int, [_vp, _vp, C.c_uint64]),

@@ -152,8 +152,9 @@ class Context:
     def table(self, values) -> "Table":
         return Table(self, values=values)
 
-    def table_u32(self, codes) -> "Table":
-        return Table(self, codes=codes)
+    def table_u32(self, codes, async_upload: bool = False) -> "Table":
+        """async_upload: reef_table_upload_u32_async (the caller keeps `codes` -- page-locked -- alive until the table is consumed)"""
+        return Table(self, codes=codes, async_upload=async_upload)
 
     def table_hybrid(self, pub_table, fill: int, half_len: int, doc_codes) -> "Table":
         """The `--hybrid` merged table (r1cs.rs:2101-2112), expanded on the device."""
@@ -423,7 +424,7 @@ class NlookupResult:
 
 
 class Table:
-    def __init__(self, ctx: Context, values=None, codes=None, dev_ptr=None, n=None, is_u32=False):
+    def __init__(self, ctx: Context, values=None, codes=None, dev_ptr=None, n=None, is_u32=False, async_upload=False):
         self.ctx = ctx
         h = C.c_void_p()
         if values is not None and isinstance(values, np.ndarray):
@@ -434,7 +435,11 @@ class Table:
             check(lib.reef_table_upload(ctx._h, _buf(b), len(values), C.byref(h)))
         elif codes is not None:
             a = np.ascontiguousarray(np.asarray(codes, dtype=np.uint32))
-            check(lib.reef_table_upload_u32(ctx._h, a.ctypes.data, len(a), C.byref(h)))
+            if async_upload:
+                self._keep = a                       # the upload may still be reading it when this returns
+                check(lib.reef_table_upload_u32_async(ctx._h, a.ctypes.data, len(a), C.byref(h)))
+            else:
+                check(lib.reef_table_upload_u32(ctx._h, a.ctypes.data, len(a), C.byref(h)))
         else:
             check(lib.reef_table_wrap_dev(ctx._h, C.c_void_p(dev_ptr), n, 1 if is_u32 else 0, C.byref(h)))
         self._h = h

@@ -83,6 +83,7 @@ static void ctx_destroy(reef_ctx* c) {
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
   }
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -99,7 +100,13 @@ struct reef_table {
   int is_u32;
   int owns;
   uint8_t first[32];  // table[0], canonical (default prev_running_v, r1cs.rs:2198-2201)
+  cudaEvent_t ready = nullptr;   // reef_table_upload_u32_async: recorded on the copy stream behind the upload
 };
+
+// every consumer of a table orders its stream behind a pending asynchronous upload
+static void table_wait(reef_ctx* c, const reef_table* t) {
+  if (t && t->ready) cudaStreamWaitEvent(c->stream, t->ready, 0);
+}
 
 struct reef_sponge {
   reef_ctx* ctx;
@@ -782,7 +789,7 @@ static uint64_t next_pow2(uint64_t n) {
   return p;
 }
 
-static int table_new(reef_ctx* c, const void* host, uint64_t n, int is_u32, reef_table** out) {
+static int table_new(reef_ctx* c, const void* host, uint64_t n, int is_u32, reef_table** out, bool async_upload = false) {
   REEF_REQUIRE(c && host && out, REEF_EINVAL, "reef_table_upload: NULL argument");
   REEF_REQUIRE(n >= 1, REEF_EASSERT, "reef_table_upload: empty table (index out of bounds: table[0])");
   const size_t esz = is_u32 ? 4 : 32;
@@ -805,14 +812,32 @@ static int table_new(reef_ctx* c, const void* host, uint64_t n, int is_u32, reef
   }
   if (!d) e = cudaMalloc(&d, (size_t)n_pad * esz);
   if (e != cudaSuccess) return fail(REEF_ENOMEM, std::string("reef_table_upload: ") + cudaGetErrorString(e));
-  e = cudaMemcpyAsync(d, host, (size_t)n * esz, cudaMemcpyHostToDevice, c->stream);
-  if (e == cudaSuccess && n_pad > n) e = cudaMemsetAsync((char*)d + (size_t)n * esz, 0, (size_t)(n_pad - n) * esz, c->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaEvent_t ready = nullptr;
+  if (async_upload) {
+    // upload on the context's copy stream, ordered behind whatever the compute stream still has queued (the buffer may
+    // come from the cache of freed tables); consumers wait on `ready`, the caller returns at once
+    if (!c->copy_stream) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    cudaEvent_t before = nullptr;
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&before, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(before, c->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, before, 0);
+    if (before) cudaEventDestroy(before);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d, host, (size_t)n * esz, cudaMemcpyHostToDevice, c->copy_stream);
+    if (e == cudaSuccess && n_pad > n) e = cudaMemsetAsync((char*)d + (size_t)n * esz, 0, (size_t)(n_pad - n) * esz, c->copy_stream);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(ready, c->copy_stream);
+  } else {
+    e = cudaMemcpyAsync(d, host, (size_t)n * esz, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && n_pad > n) e = cudaMemsetAsync((char*)d + (size_t)n * esz, 0, (size_t)(n_pad - n) * esz, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  }
   if (e != cudaSuccess) {
+    if (ready) cudaEventDestroy(ready);
     cudaFree(d);
     return fail(REEF_ECUDA, std::string("reef_table_upload: ") + cudaGetErrorString(e));
   }
   reef_table* t = new reef_table;
+  t->ready = ready;
   t->ctx = c;
   t->d = d;
   t->n_pad = n_pad;
@@ -828,6 +853,7 @@ static int table_new(reef_ctx* c, const void* host, uint64_t n, int is_u32, reef
 
 int reef_table_upload(reef_ctx* c, const uint8_t* table, uint64_t n, reef_table** out) { return table_new(c, table, n, 0, out); }
 int reef_table_upload_u32(reef_ctx* c, const uint32_t* codes, uint64_t n, reef_table** out) { return table_new(c, codes, n, 1, out); }
+int reef_table_upload_u32_async(reef_ctx* c, const uint32_t* codes, uint64_t n, reef_table** out) { return table_new(c, codes, n, 1, out, true); }
 
 int reef_table_hybrid_u32(reef_ctx* c, const uint8_t* pub_table, uint64_t n_pub, const uint8_t fill[32], uint64_t half_len,
                           const uint32_t* doc_codes, uint64_t n_doc, reef_table** out) {
@@ -914,6 +940,7 @@ int reef_table_download(const reef_table* t, uint8_t* out, uint64_t n) {
   REEF_CTX_LIVE(c, "reef_table_download");
   std::lock_guard<std::mutex> lk(c->mu);
   REEF_CUDA(cudaSetDevice(c->device));
+  table_wait(c, t);
   REEF_CUDA(cudaMemcpyAsync(out, t->d, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
   REEF_CUDA(cudaStreamSynchronize(c->stream));
   return REEF_OK;
@@ -927,6 +954,10 @@ void reef_table_free(reef_table* t) {
   if (t->owns) {
     std::lock_guard<std::mutex> lk(c->mu);
     cudaSetDevice(c->device);
+    if (t->ready) {
+      cudaEventSynchronize(t->ready);
+      cudaEventDestroy(t->ready);
+    }
     cudaStreamSynchronize(c->stream);
     if (!c->closed.load() && c->table_cache.size() < 4) c->table_cache.emplace_back((size_t)t->n_pad * (t->is_u32 ? 4 : 32), t->d);
     else cudaFree(t->d);
@@ -1053,6 +1084,7 @@ static int nlookup_prove_impl(reef_ctx* c, int tag, const reef_table* table, con
   a.out_rounds = out->rounds;
   a.out_last_claim = out->sc_last_claim;
   a.out_next_v = out->next_running_claim;
+  a.table_ready = table->ready;            // pending asynchronous upload: awaited right before the first kernel that reads the table
   if (w) {
     REEF_REQUIRE(slots, REEF_EINVAL, "reef_nlookup_prove_w: NULL slots");
     REEF_REQUIRE(w->ctx == c, REEF_EINVAL, "reef_nlookup_prove_w: witness buffer belongs to another context");
@@ -1196,6 +1228,7 @@ int reef_nl_shard_begin(reef_ctx* c, int tag, const reef_table* local_table, uin
   a.out_claim_r = a.out_rounds = a.out_last_claim = a.out_next_v = nullptr;
   std::lock_guard<std::mutex> lk(c->mu);
   REEF_CUDA(cudaSetDevice(c->device));
+  table_wait(c, local_table);
   return nl_shard_begin(c, a, rank, world, session);
 }
 
@@ -1290,6 +1323,8 @@ int reef_linear_mle_product(reef_ctx* c, reef_table* tt, reef_table* te, uint32_
   {
     std::lock_guard<std::mutex> lk(c->mu);
     REEF_CUDA(cudaSetDevice(c->device));
+    table_wait(c, tt);
+    table_wait(c, te);
     int rc = launch_mle_round_coeffs(c, tt->d, te->d, ell, i, g);
     if (rc) return rc;
   }
@@ -1323,6 +1358,7 @@ int reef_verifier_mle_eval(reef_ctx* c, const reef_table* t, const uint8_t* q, u
   REEF_REQUIRE(t->n_pad == ((uint64_t)1 << ell), REEF_EINVAL, "reef_verifier_mle_eval: padded length mismatch");
   std::lock_guard<std::mutex> lk(c->mu);
   REEF_CUDA(cudaSetDevice(c->device));
+  table_wait(c, t);
   return launch_mle_eval(c, t->d, t->is_u32, t->n_pad, q, ell, out);
 }
 
@@ -1334,6 +1370,7 @@ int reef_hyrax_lz(reef_ctx* c, const reef_table* t, uint64_t rows, uint64_t cols
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(c->mu);
   REEF_CUDA(cudaSetDevice(c->device));
+  table_wait(c, t);
   return launch_lz(c, t->d, t->is_u32, rows, cols, L, out);
 }
 

@@ -160,6 +160,7 @@ struct reef_ctx {
   std::atomic<bool> closed{false};
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;    // asynchronous table uploads (reef_table_upload_u32_async), created on first use
   std::mutex mu;                         // one in-flight call per context
   reef::PoseidonTables* d_pos = nullptr; // Montgomery-form tables in global memory
   reef::PoseidonLpTables* d_lp = nullptr; // tables of the lane-parallel transcript permutation

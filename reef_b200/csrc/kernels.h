@@ -51,6 +51,7 @@ struct NlookupArgs {
   uint8_t* out_rounds;     // ell x 4 x 32: (sc_r, xsq, x, const)
   uint8_t* out_last_claim; // 32
   uint8_t* out_next_v;     // 32
+  cudaEvent_t table_ready = nullptr;   // optional: event behind an asynchronous upload of d_table
   // (f1) optional: the same outputs scattered on the device into an index-addressed witness buffer (canonical
   // elements) right behind the last kernel; slot = UINT64_MAX skips an output
   void* d_wit = nullptr;

@@ -657,6 +657,8 @@ static int nlookup_run_t(reef_ctx* c, const NlookupArgs& a) {
     REEF_CUDA(launch_dep(k_eq_tables, dim3(ceil_div_u(a_len + b_len, 128)), dim3(128), 0, s, (const NlState*)st, ell, hb, d_A, a_len, d_B, b_len, 0u, 0u));
     REEF_LAUNCHED();
   }
+  // the first absorb above (5-7 permutations) never reads the table: an asynchronous upload overlaps it
+  if (a.table_ready) REEF_CUDA(cudaStreamWaitEvent(s, a.table_ready, 0));
 
   // sweep rounds 1 .. ell-h
   const void* t_cur = a.d_table;

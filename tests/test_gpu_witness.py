@@ -141,3 +141,28 @@ def test_generator_levels_are_shared_between_contexts(ctx):
     check(lib.reef_bases_cache_stats(C.byref(hits), C.byref(entries)))
     assert entries.value == e0
     other.close()
+
+
+def test_async_table_upload_overlaps_the_first_absorb_and_changes_nothing(ctx):
+    """reef_table_upload_u32_async: the copy is queued on the context's copy stream, the sum-check's first absorb runs
+    beside it, the first sweep (and every other consumer) waits for it; results identical to the synchronous upload"""
+    import torch
+    rnd = random.Random(12)
+    for ell in (9, 16):
+        n = 1 << ell
+        pinned = torch.from_numpy(np.random.default_rng(ell).integers(0, 131, size=n, dtype=np.uint32).astype(np.int32)).pin_memory()
+        codes = pinned.numpy().view(np.uint32)
+        q = [rnd.randrange(n) for _ in range(3)]
+        v = [int(codes[i]) for i in q]
+        exp = cport.wit_nlookup_gadget(list(map(int, codes)), q, v, None, None, "nldoc", 9, u32=True)
+        for _ in range(3):                                   # buffers come back from the context's cache of freed tables
+            t = ctx.table_u32(codes, async_upload=True)
+            got = ctx.wit_nlookup_gadget(t, q, v, None, None, "nldoc", 9)
+            assert got.rounds == exp["rounds"] and got.next_running_claim == exp["next_running_claim"]
+            t.free()
+        t = ctx.table_u32(codes, async_upload=True)          # a consumer that is not the sum-check
+        x = [rnd.randrange(FQ) for _ in range(ell)]
+        t2 = ctx.table_u32(codes)
+        assert ctx.verifier_mle_eval(t, x) == ctx.verifier_mle_eval(t2, x)
+        t.free()
+        t2.free()

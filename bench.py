@@ -356,7 +356,7 @@ class GpuPass:
                 if self.mode == "nldoc":
                     # H2D of the document codes from page-locked memory, queued on the context's copy stream: the first absorb
                     # of the sum-check (which never reads the table) overlaps it, the first sweep waits for it
-                    doc_tab = self.pool["doc"].submit(lambda: self.ctxs["doc"].table_u32(self.h_doc, async_upload=True)).result()
+                    doc_tab = self.pool["doc"].submit(lambda: self.ctxs["doc"].table_u32(self.h_doc, async_upload=os.environ.get("REEF_BENCH_ASYNC_UPLOAD", "1") != "0")).result()
                 T_tab = f2.result()
         import threading
         msm_futs, owners = [], []

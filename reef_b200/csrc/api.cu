@@ -959,8 +959,17 @@ void reef_table_free(reef_table* t) {
       cudaEventDestroy(t->ready);
     }
     cudaStreamSynchronize(c->stream);
-    if (!c->closed.load() && c->table_cache.size() < 4) c->table_cache.emplace_back((size_t)t->n_pad * (t->is_u32 ? 4 : 32), t->d);
-    else cudaFree(t->d);
+    if (!c->closed.load()) {
+      // keep the most recently freed buffers (a prover re-uploads same-sized tables proof after proof); when the
+      // cache is full the OLDEST entry goes, so a new working set takes the cache over after one round
+      if (c->table_cache.size() >= 4) {
+        cudaFree(c->table_cache.front().second);
+        c->table_cache.erase(c->table_cache.begin());
+      }
+      c->table_cache.emplace_back((size_t)t->n_pad * (t->is_u32 ? 4 : 32), t->d);
+    } else {
+      cudaFree(t->d);
+    }
   }
   delete t;
   ctx_release(c);

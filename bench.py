@@ -465,6 +465,11 @@ class GpuPass:
     # -- commit phase (--commit: run_committer, framework.rs:62-79) -----------------------------------
     def commit_setup(self):
         if self.mode == "merkle":
+            # host buffers of the commit phase, page-locked like every other timed input / output: the document as the
+            # u64 codes reef_merkle_build takes, and room for the whole tree (the .cmt stores it)
+            self.h_doc64 = self._pin(self.w["udoc"].astype(np.uint64))
+            total = int(self.lib.reef_merkle_tree_elems(len(self.h_doc64)))
+            self.h_tree = self._pin(np.zeros(total * 32, dtype=np.uint8))
             return
         rows, cols = WL.hyrax_dims(self.ell_doc)
         rnd = random.Random(99)
@@ -478,7 +483,7 @@ class GpuPass:
         from HOST codes.  Returns the commitment bytes (rows x 64 B | root)."""
         w = self.w
         if self.mode == "merkle":
-            return le32(self.ctxs["doc"].merkle_raw(w["udoc"])[0])       # the whole tree comes back (it is what the .cmt stores)
+            return le32(self.ctxs["doc"].merkle_raw(self.h_doc64, self.h_tree)[0])       # the whole tree comes back (it is what the .cmt stores)
         rows, cols = WL.hyrax_dims(self.ell_doc)
         out, h = C.create_string_buffer(rows * 64), C.create_string_buffer(32)
         # NLDocCommitment::new (commitment.rs:133-212): Hyrax rows + doc_commit_hash = PoseidonRO over the rows
@@ -1000,7 +1005,8 @@ def cmt_bytes(gp, w, got):
     t0 = time.perf_counter()
     if w["mode"] == "merkle":
         ctx = gp.ctxs["doc"]
-        root, levels = ctx.merkle_raw(w["udoc"])
+        root, levels = ctx.merkle_raw(gp.h_doc64, gp.h_tree)
+        levels = levels.ctypes.data
         sizes, nl = ctx.last_level_sizes, ctx.last_n_levels
         t0 = time.perf_counter()
         d = np.ascontiguousarray(w["udoc"].astype(np.uint64))

@@ -300,16 +300,23 @@ class Context:
     def merkle(self, doc) -> "MerkleCommitment":
         return MerkleCommitment(self, doc)
 
-    def merkle_raw(self, doc):
+    def merkle_raw(self, doc, levels_out=None):
         """MerkleCommitment::new with raw buffers: (root int, levels bytes: every level, leaf parents first) -- the
-        whole tree comes back to the host, as the .cmt of --commit holds it (merkle_tree.rs:10-15)."""
-        d = _u64(doc)
+        whole tree comes back to the host, as the .cmt of --commit holds it (merkle_tree.rs:10-15).
+        doc: uint64 numpy array is used in place; levels_out: optional caller-owned (page-locked) uint8 numpy buffer of
+        reef_merkle_tree_elems(n) * 32 bytes that receives the levels instead of a fresh bytes object."""
+        d = doc if isinstance(doc, np.ndarray) and doc.dtype == np.uint64 and doc.flags["C_CONTIGUOUS"] else _u64(doc)
         total = int(lib.reef_merkle_tree_elems(len(d)))
-        levels = C.create_string_buffer(max(total, 1) * 32)
         sizes = np.zeros(64, dtype=np.uint64)
         nl = C.c_uint32(0)
         root = C.create_string_buffer(32)
-        check(lib.reef_merkle_build(self._h, d.ctypes.data, len(d), levels, sizes.ctypes.data, C.byref(nl), root))
+        if levels_out is not None:
+            assert levels_out.nbytes >= total * 32
+            check(lib.reef_merkle_build(self._h, d.ctypes.data, len(d), levels_out.ctypes.data, sizes.ctypes.data, C.byref(nl), root))
+            levels = levels_out
+        else:
+            levels = C.create_string_buffer(max(total, 1) * 32)
+            check(lib.reef_merkle_build(self._h, d.ctypes.data, len(d), levels, sizes.ctypes.data, C.byref(nl), root))
         self.last_level_sizes, self.last_n_levels = sizes, int(nl.value)      # for the .cmt writer (reef_cmt_merkle_write)
         return int.from_bytes(root.raw, "little"), levels
 

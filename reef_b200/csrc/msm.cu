@@ -464,6 +464,29 @@ __global__ void __launch_bounds__(256) k_bitsum_partial(const XYZZ<C>* __restric
   if (threadIdx.x == 0) st_xyzz(partial + ((uint64_t)g * gridDim.y + t) * gridDim.x + blockIdx.x, r);
 }
 
+// Throughput shape of the same step (row-batched commitments: thousands of (row, bit) pairs over a few hundred buckets
+// each): ONE WARP per (row, bit).  Every lane first sums its B / 32 buckets of that bit serially, then one 5-level
+// shuffle tree -- B / 32 + 5 warp-wide additions per pair instead of the 8 x (256 / 32) of the CTA tree above, whose
+// upper levels add mostly copies.  Output layout = k_bitsum_partial with nblk = 1.
+template <class C>
+__global__ void __launch_bounds__(256) k_bitsum_partial_warp(const XYZZ<C>* __restrict__ buckets, uint32_t B, uint32_t cbits,
+                                                             uint32_t n_pairs, XYZZ<C>* __restrict__ partial) {
+  const uint32_t pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // = g * cbits + t
+  const int lane = threadIdx.x & 31;
+  if (pair >= n_pairs) return;                                             // warp-uniform
+  const uint32_t g = pair / cbits, t = pair - g * cbits;
+  XYZZ<C> v = xyzz_inf<C>();
+#pragma unroll 1
+  for (uint32_t b = lane; b < B; b += 32)
+    if (((b + 1) >> t) & 1) xyzz_add<C>(v, ld_xyzz(buckets + (uint64_t)g * B + b));
+#pragma unroll 1
+  for (int m = 16; m >= 1; m >>= 1) {
+    XYZZ<C> o = shfl_xor_xyzz(v, m);
+    xyzz_add<C>(v, o);
+  }
+  if (lane == 0) st_xyzz(partial + pair, v);
+}
+
 // one CTA per group: S_t = sum of nblk partials (one warp per bit), scale by 2^t, sum over t,
 // then combine the groups by Horner (group g carries weight 2^(c*L*g)) and normalise.
 template <class C>
@@ -949,7 +972,12 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
   scope.reset(new ProfScope(c, PROF_MSM_REDUCE, nb));
   k_gather_buckets<C><<<cdiv(nb, 256), 256, 0, s>>>(parts[cur], poff[cur], pcnt[cur], nb, buckets);
   REEF_LAUNCHED();
-  k_bitsum_partial<C><<<dim3(nblk, P.c, (unsigned)a.rows), 256, 0, s>>>(buckets, P.B, bpt, bitpart);
+  if (nblk == 1 && P.B <= 2048 && a.rows * P.c >= (uint64_t)c->sm_count * 8) {
+    const uint32_t n_pairs = (uint32_t)(a.rows * P.c);                      // many rows: one warp per (row, bit)
+    k_bitsum_partial_warp<C><<<cdiv((uint64_t)n_pairs * 32, 256), 256, 0, s>>>(buckets, P.B, P.c, n_pairs, bitpart);
+  } else {
+    k_bitsum_partial<C><<<dim3(nblk, P.c, (unsigned)a.rows), 256, 0, s>>>(buckets, P.B, bpt, bitpart);
+  }
   REEF_LAUNCHED();
   k_rows_final<C><<<(unsigned)a.rows, 512, 0, s>>>(bitpart, nblk, P.c, d_out, host_affine ? (XYZZ<C>*)d_out : nullptr);
   REEF_LAUNCHED();

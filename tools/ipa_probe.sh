@@ -1,9 +1,3 @@
 #!/bin/bash
-python bench.py --workload cfg3 --also= --steps 3 --msm-large-log2 0 --no-openings 2>&1 | python -c "
-import json,sys
-for line in sys.stdin:
-    if line.startswith('{'):
-        d=json.loads(line); print('cfg3', d['ms_per_step'], d['e2e']['ms_per_step'], json.dumps(d['commit'])[:600])
-    elif 'rror' in line: print(line)
-"
-python -m pytest tests -m gpu -q --timeout 900 2>&1 | tail -2
+python -m pytest tests/test_gpu_msm.py tests/test_gpu_fullsize.py tests/test_poseidon_ro.py tests/test_gpu_multigpu_splits.py tests/test_gpu_snark.py -m gpu -x -q --timeout 900 2>&1 | tail -2
+python tools/perf_probe.py 2>&1 | grep -i "hyrax"

@@ -428,6 +428,7 @@ __global__ void __launch_bounds__(RO_T * 32) k_poseidon_ro_fast(const Fe<C>* __r
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __shared__ Fe<C> sb[2][RO_T];
   __shared__ Fe<C> rest_sh[RO_T - 1];
+  __shared__ Fe<C> gsh[RO_T];
   __shared__ Fe<C> xch_u[2], xch_c[2];
   const Fe<C> zero = fe_zero<C>();
   const Fe<C> m = lane < RO_T ? ld256(&K->mds[lane * RO_T + w]) : zero;
@@ -460,8 +461,11 @@ __global__ void __launch_bounds__(RO_T * 32) k_poseidon_ro_fast(const Fe<C>* __r
     for (int half = 0; half < 2; half++) {
 #pragma unroll 1
       for (int r = half * (RO_RF / 2); r < (half + 1) * (RO_RF / 2); r++) {      // four full rounds
-        s = ro_pow5_dev<C>(fe_add<C>(s, ld256(&K->rc_full[r * RO_T + w])));
-        if (lane == 0) sb[r & 1][w] = s;
+        // the 25 S-boxes of a round on the 25 lanes of ONE warp (3 warp-wide multiplications instead of 3 x 25: every
+        // warp raising its own element to the fifth power on all of its lanes kept the four schedulers busy with copies)
+        if (lane == 0) gsh[w] = s;
+        __syncthreads();
+        if (w == 0 && lane < RO_T) sb[r & 1][lane] = ro_pow5_dev<C>(fe_add<C>(gsh[lane], ld256(&K->rc_full[r * RO_T + lane])));
         __syncthreads();
         const Fe<C> x = lane < RO_T ? sb[r & 1][lane] : zero;
         s = warp_sum_fe<C>(mont_mul<C>(x, m));

@@ -1,5 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
+python -m pytest tests -m gpu -q --timeout 900 2>&1 | tail -2
+python __graft_entry__.py smoke 2>&1 | tail -1
 python bench.py --steps 5 --warmup 3 > gpurun_out/r2g_bench.json 2> gpurun_out/r2g_bench.err
 tail -c 300 gpurun_out/r2g_bench.err
 python - <<'PY'

@@ -79,6 +79,9 @@ WORKLOADS = {
 }
 
 
+TRACE = [] if os.environ.get("REEF_BENCH_TRACE") == "1" else None      # host timestamps of a pass (debugging aid)
+
+
 class ParityError(AssertionError):
     """The GPU path produced a result that differs from the oracle."""
 
@@ -264,7 +267,7 @@ class GpuPass:
         rounds = b["rounds"].raw
         next_q = b"".join(rounds[i * 128:i * 128 + 32] for i in range(ell))
         nxt = b["nxt"].raw
-        if key != "nl":
+        if key != "nl" and os.environ.get("REEF_BENCH_SKIP_CALCD") != "1":
             # calc_d of the previous and of the next running claim (framework.rs:517-553): inputs of the step
             # circuit only, the next fold's sum-check does not wait for them
             self.d_futs.append(self.pool["aux"].submit(self._calc_d, pv if prev else first_v))
@@ -308,10 +311,14 @@ class GpuPass:
         """commit(W), commit(T) of one fold over the same key: one row-batched MSM (2 x n), 2 x 64 bytes back"""
         out = C.create_string_buffer(128)
         ctx = bases.ctx
+        if TRACE is not None:
+            TRACE.append(("msm_start", n, time.perf_counter()))
         if resident:
             self.check(self.lib.reef_msm_rows_dev(ctx._h, bases._h, C.c_void_p(dev_tensor.data_ptr()), 2, n, out))
         else:
             self.check(self.lib.reef_msm_rows(ctx._h, bases._h, host_arr.ctypes.data, 2, n, None, out))
+        if TRACE is not None:
+            TRACE.append(("msm_end", n, time.perf_counter()))
         return out.raw
 
     def _exchange_points(self, outs, owners):
@@ -417,14 +424,23 @@ class GpuPass:
                         qd = self.q_doc[s]
                         prev = self._nlookup("nldoc", doc_tab, qd[0], qd[1], prev, first_doc)
                     nl_done[s].wait()
+                if TRACE is not None:
+                    TRACE.append(("sumchecks_done", s, time.perf_counter()))
                 commitments(s)
             return prev
 
-        f_nl = self.pool["nl"].submit(nl_chain) if self.mode != "hybrid" else None
+        if os.environ.get("REEF_BENCH_SKIP_NL") == "1":      # experiment only (never a bench value): the document chain alone
+            for e in nl_done:
+                e.set()
+            f_nl = None
+        else:
+            f_nl = self.pool["nl"].submit(nl_chain) if self.mode != "hybrid" else None
         prev_doc = self.pool["doc"].submit(doc_chain).result()
         prev_nl = f_nl.result() if f_nl is not None else None
         outs = [f.result() if f is not None else None for f in msm_futs]
         ds = [f.result() for f in self.d_futs]
+        if TRACE is not None:
+            TRACE.append(("pass_end", 0, time.perf_counter()))
         if self.world > 1:
             outs = self._exchange_points(outs, owners)
         outs = [o[i:i + 64] for o in outs if o is not None for i in range(0, len(o), 64)]       # one 64-byte point per commitment
@@ -574,7 +590,8 @@ def run_reef(args):
     # one context (= one CUDA stream + one host thread) per independent chain of a fold
     # the sum-check contexts are latency-critical (highest stream priority), the commitment contexts are not
     prio = os.environ.get("REEF_BENCH_PRIO", "1") != "0"
-    ctxs = {k: reef_b200.Context(dev, (k in ("nl", "doc")) if prio else None) for k in ("nl", "doc", "pri", "sec", "pri2", "sec2", "aux")}
+    level = {"nl": 1, "doc": 1, "pri": int(os.environ.get("REEF_BENCH_PRI_LEVEL", "0")), "pri2": 2}      # 1 highest, 2 middle, 0 lowest
+    ctxs = {k: reef_b200.Context(dev, level.get(k, 0) if prio else None) for k in ("nl", "doc", "pri", "sec", "pri2", "sec2", "aux")}
     w = make_workload(args.workload, seed_shift=0, world=world)
     gp = GpuPass(ctxs, w, rank, world, dist)
     gp.prepare_queries()
@@ -695,6 +712,11 @@ def run_reef(args):
     transcript = transcript_object(ctxs["aux"], w, gp, prof, K, clocks) if rank == 0 else None
     openings = opening_phases(ctxs, w, gp, K, args.no_cpu_baseline) if world == 1 and not args.no_openings else None
 
+    if TRACE is not None and rank == 0:
+        last = [i for i, t in enumerate(TRACE) if t[0] == "pass_end"]
+        seg = TRACE[last[-2] + 1:last[-1] + 1] if len(last) >= 2 else TRACE
+        t0 = seg[0][2]
+        print("TRACE (last pass, us):", [(a, b, round((t - t0) * 1e6)) for a, b, t in seg], file=sys.stderr)
     value = w["doc_len"] / (ms / K / 1e3)
     e2e_value = w["doc_len"] / (e2e_ms / K / 1e3)
     if rank != 0:

@@ -46,8 +46,9 @@ int reef_abi_version(void);
 uint64_t reef_launch_count(void);
 const char* reef_last_error(void);
 int reef_init(int device, reef_ctx** out);
-/* Same, with the context's stream at the highest (latency_critical != 0) or lowest CUDA stream priority: the contexts that
- * run the Fiat-Shamir chains (sum-checks) are latency-critical, the ones that run the fold commitments are not. */
+/* Same, with the context's stream at the highest (latency_critical = 1), lowest (0) or a middle (2) CUDA stream priority:
+ * the contexts that run the Fiat-Shamir chains (sum-checks) are latency-critical, the ones that run the fold commitments
+ * are not; 2 puts the longer of two concurrent commitment chains (the primary curve) ahead of the other. */
 int reef_init_prio(int device, int latency_critical, reef_ctx** out);
 /* SMs the context's kernels may run on.  With REEF_RESERVE_SMS=k in the environment (opt-in; 12 is the natural value on
  * B200) a background context (latency_critical = 0) lives in a CUDA green context that owns all but k SMs, so that the

@@ -91,7 +91,7 @@ class Context:
         if latency_critical is None:
             check(lib.reef_init(device, C.byref(h)))
         else:
-            check(lib.reef_init_prio(device, 1 if latency_critical else 0, C.byref(h)))
+            check(lib.reef_init_prio(device, int(latency_critical) if not isinstance(latency_critical, bool) else (1 if latency_critical else 0), C.byref(h)))
         self._h = h
         self.device = device
 

@@ -205,7 +205,11 @@ const char* reef_last_error(void) { return g_last_error.c_str(); }
 
 static int init_impl(int device, int latency_critical, reef_ctx** out);
 int reef_init(int device, reef_ctx** out) { return init_impl(device, 0, out); }
-int reef_init_prio(int device, int latency_critical, reef_ctx** out) { return init_impl(device, latency_critical ? 1 : 2, out); }
+// latency_critical: 1 = highest stream priority, 0 = background (lowest), 2 = background but ahead of the other
+// background contexts (the longer of two concurrent commitment chains)
+int reef_init_prio(int device, int latency_critical, reef_ctx** out) {
+  return init_impl(device, latency_critical == 1 ? 1 : (latency_critical == 2 ? 3 : 2), out);
+}
 
 // ---------------------------------------------------------------------------------------
 // SM partition for BACKGROUND contexts (reef_init_prio(.., 0, ..)).  The Fiat-Shamir kernels of a latency-critical
@@ -298,12 +302,16 @@ static int init_impl(int device, int latency_critical, reef_ctx** out) {
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   cudaError_t se = cudaSuccess;
-  if (latency_critical == 2) {
+  if (latency_critical == 2 || latency_critical == 3) {
     unsigned sms = 0;
     c->stream = green_stream(device, c->sm_count, prio_lo, &sms);
     if (c->stream) c->partition_sms = sms;
   }
-  if (!c->stream) se = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, latency_critical == 1 ? prio_hi : prio_lo);
+  if (!c->stream) {
+    // CUDA priorities: numerically lower = higher priority; prio_hi <= prio_lo
+    const int prio = latency_critical == 1 ? prio_hi : (latency_critical == 3 ? (prio_lo + prio_hi) / 2 : prio_lo);
+    se = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio);
+  }
   if (se != cudaSuccess) {
     c->stream = nullptr;
     ctx_release(c);

@@ -668,7 +668,8 @@ MsmPlanPublic msm_make_plan(uint64_t n, uint32_t scalar_bits, uint64_t max_level
   MsmPlanPublic p;
   uint32_t lg = 0;
   while (((uint64_t)1 << (lg + 1)) <= n) lg++;
-  int c = (int)lg - 4;
+  static const int delta = getenv("REEF_MSM_C_DELTA") ? atoi(getenv("REEF_MSM_C_DELTA")) : 0;   // tuning aid: window bits = log2(n) - 4 + delta
+  int c = (int)lg - 4 + delta;
   if (c < 4) c = 4;
   if (c > 16) c = 16;
   if ((uint32_t)c > scalar_bits + 1) c = (int)scalar_bits + 1;

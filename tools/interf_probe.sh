@@ -1,20 +1,13 @@
 #!/bin/bash
-mkdir -p gpurun_out
-TAG=${1:-ip}
-python bench.py --steps 5 --also=cfg3,cfg4 --no-commit --no-openings --msm-large-log2 0 2>&1 | python -c "
-import json,sys
-for line in sys.stdin:
-    if line.startswith('{'):
-        d=json.loads(line); print('verified', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], d['config']['verified'][:60]); print([(a['workload'][:5], a['ms_per_step'], a['verified'][:30]) for a in d['also']])
-    elif 'rror' in line or 'Traceback' in line: print(line)
-"
 L="--steps 5 --no-cpu-baseline --also= --no-commit --no-openings --msm-large-log2 0"
 run() { name=$1; shift; env "$@" python bench.py $L 2>/dev/null | python -c "
 import json,sys
 for line in sys.stdin:
     if line.startswith('{'):
-        d=json.loads(line); print('$name', 'ms_per_step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'])
+        d=json.loads(line); print('$name', 'ms_per_step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], json.dumps({k:v for k,v in d['kernel_ms_per_step'].items() if k.startswith('msm')}))
 "; }
-run full X=1
-run skiplast REEF_BENCH_SKIP_MSM=last
-run skipall REEF_BENCH_SKIP_MSM=1
+for dl in 0 1 2 -1 3; do
+run cdelta$dl REEF_MSM_C_DELTA=$dl
+done
+REEF_MSM_C_DELTA=1 python tools/pair_probe.py 2>&1 | grep "n=2^15\|n=2^14"
+REEF_MSM_C_DELTA=2 python tools/pair_probe.py 2>&1 | grep "n=2^15\|n=2^14"

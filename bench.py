@@ -377,7 +377,10 @@ class GpuPass:
             """the fold commitments of fold s: issued once both sum-checks of the fold are done (their witness)"""
             sc, scd = w["sc"][s], (self.sc_dev[s] if resident else None)
             if self.pairs:
-                jobs = [("Wp", "pri", w["n_pri"], "p"), ("Ws", "sec", w["n_sec"], "s")]
+                # the commitments of every fold but the last run beside the next fold's sum-checks (background contexts);
+                # the last fold's have nothing to hide behind and use the second pair of contexts
+                last = s == S - 1 and os.environ.get("REEF_BENCH_LAST_FOLD_CTX", "1") != "0"
+                jobs = [("Tp" if last else "Wp", "pri2" if last else "pri", w["n_pri"], "p"), ("Ts" if last else "Ws", "sec2" if last else "sec", w["n_sec"], "s")]
             else:
                 jobs = [("Wp", "pri", w["n_pri"], None), ("Ws", "sec", w["n_sec"], None), ("Tp", "pri2", w["n_pri"], None), ("Ts", "sec2", w["n_sec"], None)]
             for key, pool, n, pair in jobs:
@@ -590,7 +593,7 @@ def run_reef(args):
     # one context (= one CUDA stream + one host thread) per independent chain of a fold
     # the sum-check contexts are latency-critical (highest stream priority), the commitment contexts are not
     prio = os.environ.get("REEF_BENCH_PRIO", "1") != "0"
-    level = {"nl": 1, "doc": 1, "pri": int(os.environ.get("REEF_BENCH_PRI_LEVEL", "0")), "pri2": 2}      # 1 highest, 2 middle, 0 lowest
+    level = {"nl": 1, "doc": 1, "pri": 0, "sec": 0, "pri2": 2, "sec2": 2}      # 1 highest, 2 middle, 0 lowest (background)
     ctxs = {k: reef_b200.Context(dev, level.get(k, 0) if prio else None) for k in ("nl", "doc", "pri", "sec", "pri2", "sec2", "aux")}
     w = make_workload(args.workload, seed_shift=0, world=world)
     gp = GpuPass(ctxs, w, rank, world, dist)

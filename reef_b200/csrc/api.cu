@@ -208,7 +208,9 @@ int reef_init(int device, reef_ctx** out) { return init_impl(device, 0, out); }
 // latency_critical: 1 = highest stream priority, 0 = background (lowest), 2 = background but ahead of the other
 // background contexts (the longer of two concurrent commitment chains)
 int reef_init_prio(int device, int latency_critical, reef_ctx** out) {
-  return init_impl(device, latency_critical == 1 ? 1 : (latency_critical == 2 ? 3 : 2), out);
+  int rc = init_impl(device, latency_critical == 1 ? 1 : (latency_critical == 2 ? 3 : 2), out);
+  if (rc == REEF_OK && latency_critical == 0) (*out)->polite = getenv("REEF_MSM_POLITE") && atoi(getenv("REEF_MSM_POLITE")) != 0;
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -178,6 +178,7 @@ struct reef_ctx {
   int sm_count = 148;
   // background contexts (reef_init_prio(.., 0, ..)): SMs of the green-context partition their stream lives in (0 = none)
   uint32_t partition_sms = 0;
+  bool polite = false;                   // background context + REEF_MSM_POLITE=1: long MSM grids at two CTAs per SM (msm.cu)
   // device buffers of freed tables, reused by the next upload of the same size: a prover re-uploads
   // a same-sized table per proof, and cudaMalloc/cudaFree synchronise the whole device
   std::vector<std::pair<size_t, void*>> table_cache;

@@ -39,6 +39,27 @@ static bool msm_tma_enabled() {
 }
 static constexpr size_t MSM_TMA_SMEM = 2 * 4 * 128 * 64;
 
+// "Polite" background contexts (reef_init_prio(.., 0, ..) with REEF_MSM_POLITE=1): the long accumulation grids ask for
+// enough dynamic shared memory that only two of their CTAs fit an SM.  Four of them fill the register file (106-136
+// registers x 128 threads each), and a sweep CTA of a latency-critical sum-check (17 k registers) then waits for one of
+// them to retire; with two there is always room for it.  The commitments of fold i have the whole sum-check of fold
+// i+1 to hide behind, so their own slowdown is free; the last fold's commitments use a context that is not polite.
+static size_t polite_smem(reef_ctx* c, const void* kernel) {
+  if (!c->polite) return 0;
+  static std::mutex mu;
+  static std::vector<const void*> done;
+  const size_t bytes = 100 * 1024;
+  std::lock_guard<std::mutex> lk(mu);
+  for (const void* k : done)
+    if (k == kernel) return bytes;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  done.push_back(kernel);
+  return bytes;
+}
+
 struct MsmPlan {
   uint32_t c;          // window bits
   uint32_t W;          // windows per scalar
@@ -808,8 +829,8 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
       k_accum_first_tma<C><<<cdiv(n_parts, 128), 128, MSM_TMA_SMEM, s>>>(sorted, start, cnt, poff[0], nb, n_parts, kfirst,
                                                                         (const Affine<C>*)a.d_levels, parts[0]);
     } else {
-      k_accum_first<C><<<cdiv(n_parts, 128), 128, 0, s>>>(sorted, start, cnt, poff[0], nb, n_parts, kfirst, (const Affine<C>*)a.d_levels,
-                                                         parts[0]);
+      k_accum_first<C><<<cdiv(n_parts, 128), 128, polite_smem(c, (const void*)k_accum_first<C>), s>>>(sorted, start, cnt, poff[0], nb, n_parts, kfirst,
+                                                                                                    (const Affine<C>*)a.d_levels, parts[0]);
     }
     REEF_LAUNCHED();
   }
@@ -822,8 +843,8 @@ static int msm_run_t(reef_ctx* c, const MsmRunArgs& a) {
     k_scan<<<1, 1024, 0, s>>>(pcnt[cur], nb, kn, pcnt[nxt], poff[nxt], nullptr, tm + 2);
     REEF_LAUNCHED();
     const uint32_t n_next = (n_parts + kn - 1) / kn + nb;   // upper bound; exact count read on device
-    if (narrow) k_accum_next<C, 4><<<cdiv((uint64_t)n_next * 4, 128), 128, 0, s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, kn, parts[nxt]);
-    else k_accum_next<C, 32><<<cdiv((uint64_t)n_next * 32, 128), 128, 0, s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, kn, parts[nxt]);
+    if (narrow) k_accum_next<C, 4><<<cdiv((uint64_t)n_next * 4, 128), 128, polite_smem(c, (const void*)k_accum_next<C, 4>), s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, kn, parts[nxt]);
+    else k_accum_next<C, 32><<<cdiv((uint64_t)n_next * 32, 128), 128, polite_smem(c, (const void*)k_accum_next<C, 32>), s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, kn, parts[nxt]);
     REEF_LAUNCHED();
     max_cnt = (max_cnt + kn - 1) / kn;
     n_parts = n_next;
@@ -951,7 +972,8 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
   uint32_t n_parts = h_tm[2], max_cnt = h_tm[3];
   scope.reset(new ProfScope(c, PROF_MSM_ACCUM, n_entries));
   if (n_parts) {
-    k_accum_first<C><<<cdiv(n_parts, 128), 128, 0, s>>>(sorted, start, cnt, poff[0], nb, n_parts, kfirst, (const Affine<C>*)a.d_levels, parts[0]);
+    k_accum_first<C><<<cdiv(n_parts, 128), 128, polite_smem(c, (const void*)k_accum_first<C>), s>>>(sorted, start, cnt, poff[0], nb, n_parts, kfirst,
+                                                                                                  (const Affine<C>*)a.d_levels, parts[0]);
     REEF_LAUNCHED();
   }
   int cur = 0;
@@ -962,8 +984,8 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
     k_scan<<<1, 1024, 0, s>>>(pcnt[cur], nb, kn, pcnt[nxt], poff[nxt], nullptr, tm + 2);
     REEF_LAUNCHED();
     const uint32_t n_next = (n_parts + kn - 1) / kn + nb;
-    if (narrow) k_accum_next<C, 4><<<cdiv((uint64_t)n_next * 4, 128), 128, 0, s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, kn, parts[nxt]);
-    else k_accum_next<C, 32><<<cdiv((uint64_t)n_next * 32, 128), 128, 0, s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, kn, parts[nxt]);
+    if (narrow) k_accum_next<C, 4><<<cdiv((uint64_t)n_next * 4, 128), 128, polite_smem(c, (const void*)k_accum_next<C, 4>), s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, kn, parts[nxt]);
+    else k_accum_next<C, 32><<<cdiv((uint64_t)n_next * 32, 128), 128, polite_smem(c, (const void*)k_accum_next<C, 32>), s>>>(parts[cur], poff[cur], pcnt[cur], poff[nxt], nb, n_next, kn, parts[nxt]);
     REEF_LAUNCHED();
     max_cnt = (max_cnt + kn - 1) / kn;
     n_parts = n_next;

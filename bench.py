@@ -591,7 +591,13 @@ def run_reef(args):
         torch.cuda.set_device(0)
     dev = local if world > 1 else 0
     # one context (= one CUDA stream + one host thread) per independent chain of a fold
-    # the sum-check contexts are latency-critical (highest stream priority), the commitment contexts are not
+    # the sum-check contexts are latency-critical (highest stream priority), the commitment contexts are not.  On one GPU
+    # the background contexts also get the two opt-in scheduling aids of the library: a green-context
+    # partition that leaves 12 SMs to the Fiat-Shamir kernels, and accumulation grids at two CTAs per SM (-1.4 % per pass);
+    # REEF_RESERVE_SMS=0 / REEF_MSM_POLITE=0 in the environment turn them off (Nsight Compute's launch list needs the first off)
+    if world == 1:
+        os.environ.setdefault("REEF_RESERVE_SMS", "12")
+        os.environ.setdefault("REEF_MSM_POLITE", "1")
     prio = os.environ.get("REEF_BENCH_PRIO", "1") != "0"
     level = {"nl": 1, "doc": 1, "pri": 0, "sec": 0, "pri2": 2, "sec2": 2}      # 1 highest, 2 middle, 0 lowest (background)
     ctxs = {k: reef_b200.Context(dev, level.get(k, 0) if prio else None) for k in ("nl", "doc", "pri", "sec", "pri2", "sec2", "aux")}
@@ -793,6 +799,8 @@ def run_reef(args):
                               "commit(W) and commit(T) of a fold share the commitment key and run as the two rows of ONE row-batched MSM per curve "
                               "(reef_msm_rows_dev; at N >= 4 GPUs four separate MSMs round-robin over the ranks); fold i+1 sum-checks overlap fold i "
                               "commitments; calc_d does not gate the next fold",
+                   "scheduling": (f"background (commitment) contexts: REEF_RESERVE_SMS={os.environ.get('REEF_RESERVE_SMS', '0')} "
+                                  f"(green-context SM partition), REEF_MSM_POLITE={os.environ.get('REEF_MSM_POLITE', '0')} (two CTAs per SM)"),
                    "registration": "commitment keys (static per PublicParams) are registered once per context BEFORE the timed region "
                                    "(k_precompute of all window levels: ~13 ms and 50 MiB per 2^15-point key); contexts that register the "
                                    "same key share one set of levels through the content-keyed cache (reef_bases_cache_stats)",

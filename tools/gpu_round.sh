@@ -13,7 +13,7 @@ if [ "$2" == "full" ]; then
   python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
   LIGHT="--no-cpu-baseline --also= --msm-large-log2 0 --no-commit --no-openings"
   # launch list of one timed step (3 warm-up steps precede it); per-launch times are cold-cache
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches.csv \
+  REEF_RESERVE_SMS=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches.csv \
       python bench.py --steps 1 --warmup 3 $LIGHT > gpurun_out/${TAG}_ncu_launch.log 2>&1
   python tools/summarize_launches.py gpurun_out/${TAG}_launches.csv gpurun_out/${TAG}_launch_summary.csv > /dev/null 2>&1
   # full captures, taken after the untimed verification + warm-up launches

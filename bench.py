@@ -786,7 +786,7 @@ def run_reef(args):
                    "kernels at a throughput size",
            "peak_source": "tools/bench_fp.cu on this pool (profiles/peak_modmul.json)"}
     if world == 1 and args.msm_large_log2:
-        msm["large"] = msm_large(ctxs["pri"], args.msm_large_log2, peaks["modmul_per_s"])
+        msm["large"] = msm_large(ctxs["doc"], args.msm_large_log2, peaks["modmul_per_s"])     # a context with the whole chip (not a background one)
     h2d, d2h = gp.bytes_per_step()
     out = {
         "metric": "NFA steps/s proved (= doc_len / hot-path prove time)", "value": round(value, 1), "unit": "NFA steps/s",

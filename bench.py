@@ -761,6 +761,10 @@ def run_reef(args):
             "int_issue_frac": round(sweep_modmul / (sweep_ms / 1e3) / peaks["modmul_per_s"], 4) if sweep_ms else None,
             "share_of_gpu_time": round(classes["sweep"], 4),
             "time_dominant_class": dominant, "class_shares": {k: round(v, 4) for k, v in classes.items()}}
+    if world == 1:
+        iso = isolated_sweep(ctxs["doc"], gp, w, peaks["hbm_gbs"])
+        if iso:
+            roof["isolated"] = iso
     tr = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     if os.path.exists(tr):
         try:
@@ -828,6 +832,37 @@ def run_reef(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def isolated_sweep(ctx, gp, w, peak_gbs, reps=5):
+    """The same sweeps with nothing else on the GPU: one sum-check over the document table alone, CUDA-event classes of
+    libreef_b200 (the in-pass figure moves with what the other streams run beside the sweeps)."""
+    import reef_b200
+    lib, check = reef_b200.lib, reef_b200._lib.check
+    if w["mode"] == "merkle":
+        return None
+    key, tab, q = ("nlhybrid", gp.hyb_tab, gp.q_hyb[0]) if w["mode"] == "hybrid" else ("nldoc", gp.doc_tab, gp.q_doc[0])
+    gp.dh, gp.salt = le32(w["doc_hash"]), le32(w["salt"])
+    gp.d_futs = []
+    first = le32(w["T"][0]) if w["mode"] == "hybrid" else le32(int(w["udoc"][0]))
+    os.environ["REEF_BENCH_SKIP_CALCD"] = "1"
+    try:
+        for _ in range(2):
+            gp._nlookup(key, tab, q[0], q[1], None, first)
+        check(lib.reef_profile_enable(ctx._h, 1))
+        for _ in range(reps):
+            gp._nlookup(key, tab, q[0], q[1], None, first)
+        n = 9
+        cnt, units, pms = (C.c_uint64 * n)(), (C.c_uint64 * n)(), (C.c_double * n)()
+        check(lib.reef_profile_read(ctx._h, n, cnt, units, pms))
+        check(lib.reef_profile_enable(ctx._h, 0))
+    finally:
+        del os.environ["REEF_BENCH_SKIP_CALCD"]
+    by = 64.0 * units[0] + 96.0 * units[1]
+    ms = pms[0] + pms[1]
+    gbs = by / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+    return {"achieved": round(gbs, 1), "frac": round(gbs / peak_gbs, 4), "avg_launch_us": round(1e3 * ms / max(1, cnt[0] + cnt[1]), 2),
+            "what": "the sweeps of one sum-check over the same table with no other stream running"}
 
 
 def _ells(w, gp):

@@ -680,6 +680,18 @@ __global__ void __launch_bounds__(512) k_rows_final(const XYZZ<C>* __restrict__ 
   }
 }
 
+// XYZZ -> affine canonical, one THREAD per row: the single-thread inversion (~110 k cycles) no longer holds a whole
+// 512-thread CTA of k_rows_final on its SM
+template <class C>
+__global__ void __launch_bounds__(128) k_rows_affine(const XYZZ<C>* __restrict__ in, uint64_t rows, Affine<C>* __restrict__ out) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  Affine<C> a = xyzz_to_affine<C>(ld_xyzz(in + r));
+  a.x = from_mont<C>(a.x);
+  a.y = from_mont<C>(a.y);
+  st_affine(out + r, a);
+}
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -929,6 +941,7 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
   // few rows (the W / T commitments of one fold as two rows): results leave as XYZZ, affine on the host
   const bool host_affine = a.rows <= 16 && !a.d_rows_out;
   size_t o_out = take((size_t)a.rows * (host_affine ? sizeof(XYZZ<C>) : sizeof(Affine<C>)));
+  size_t o_rowx = take(host_affine ? 0 : (size_t)a.rows * sizeof(XYZZ<C>));
   void* base;
   int rc = ctx_scratch(c, off, &base);
   if (rc) return rc;
@@ -1002,8 +1015,18 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
     k_bitsum_partial<C><<<dim3(nblk, P.c, (unsigned)a.rows), 256, 0, s>>>(buckets, P.B, bpt, bitpart);
   }
   REEF_LAUNCHED();
-  k_rows_final<C><<<(unsigned)a.rows, 512, 0, s>>>(bitpart, nblk, P.c, d_out, host_affine ? (XYZZ<C>*)d_out : nullptr);
-  REEF_LAUNCHED();
+  // one warp per bit: c warps are all a row needs (a 512-thread CTA kept half an SM's registers idle)
+  const unsigned fin_threads = 32u * (P.c < 16u ? P.c : 16u);
+  if (host_affine) {
+    k_rows_final<C><<<(unsigned)a.rows, fin_threads, 0, s>>>(bitpart, nblk, P.c, d_out, (XYZZ<C>*)d_out);
+    REEF_LAUNCHED();
+  } else {
+    XYZZ<C>* row_xyzz = (XYZZ<C>*)(d + o_rowx);
+    k_rows_final<C><<<(unsigned)a.rows, fin_threads, 0, s>>>(bitpart, nblk, P.c, d_out, row_xyzz);
+    REEF_LAUNCHED();
+    k_rows_affine<C><<<cdiv(a.rows, 32), 32, 0, s>>>(row_xyzz, a.rows, d_out);
+    REEF_LAUNCHED();
+  }
   scope.reset();
   if (host_affine) {
     XYZZ<C> h_rows[16];

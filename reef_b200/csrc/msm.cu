@@ -201,42 +201,82 @@ __global__ void k_hist(const uint32_t* __restrict__ keys, uint64_t n_entries, ui
 }
 
 // exclusive scan of ceil(cnt[b] / K) (K = 1: plain scan) by one CTA; also the max of cnt.
+// Tiles of 4096 counts: every thread takes four consecutive ones (one 16-byte load, coalesced), warp scan by shuffles,
+// one barrier pair per tile.  (One thread per contiguous slice of nb / 1024 counts was 168 us at nb = 2^16 -- 64
+// uncoalesced dependent loads per thread -- and four of them sat in every row-batched commitment.)
 __global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ cnt, uint32_t nb, uint32_t K,
                                                uint32_t* __restrict__ parts, uint32_t* __restrict__ off,
                                                uint32_t* __restrict__ cursor, uint32_t* __restrict__ total_max) {
-  __shared__ uint32_t sm[1024];
-  __shared__ uint32_t smax[1024];
-  const uint32_t per = (nb + 1023) / 1024;
-  const uint32_t lo = threadIdx.x * per, hi = min(nb, lo + per);
-  uint32_t sum = 0, mx = 0;
-  for (uint32_t b = lo; b < hi; b++) {
-    uint32_t p = (cnt[b] + K - 1) / K;
-    sum += p;
-    mx = max(mx, p);
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t wmax[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool vec = (((uintptr_t)cnt | (uintptr_t)off | (uintptr_t)parts | (uintptr_t)cursor) & 15u) == 0;
+  uint32_t carry = 0, mx = 0;
+  for (uint32_t base = 0; base < nb; base += 4096) {
+    const uint32_t b0 = base + 4u * threadIdx.x;
+    const bool whole = vec && b0 + 4 <= nb;
+    uint32_t p[4] = {0, 0, 0, 0};
+    if (whole) {
+      const uint4 v = *reinterpret_cast<const uint4*>(cnt + b0);
+      p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (b0 + i < nb) p[i] = cnt[b0 + i];
+    }
+    if (K != 1) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) p[i] = (p[i] + K - 1) / K;
+    }
+    mx = max(max(mx, max(p[0], p[1])), max(p[2], p[3]));
+    const uint32_t t = p[0] + p[1] + p[2] + p[3];
+    uint32_t inc = t;                                  // inclusive scan inside the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += v;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    const uint32_t ws = wsum[lane];                    // every warp scans the 32 warp totals
+    uint32_t winc = ws;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += v;
+    }
+    const uint32_t warp_excl = __shfl_sync(0xffffffffu, winc - ws, warp);
+    const uint32_t tile_total = __shfl_sync(0xffffffffu, winc, 31);
+    uint32_t run = carry + warp_excl + (inc - t);
+    const uint32_t o0 = run, o1 = o0 + p[0], o2 = o1 + p[1], o3 = o2 + p[2];
+    if (whole) {
+      const uint4 o = make_uint4(o0, o1, o2, o3);
+      *reinterpret_cast<uint4*>(off + b0) = o;
+      if (cursor) *reinterpret_cast<uint4*>(cursor + b0) = o;
+      if (parts) *reinterpret_cast<uint4*>(parts + b0) = make_uint4(p[0], p[1], p[2], p[3]);
+    } else {
+      const uint32_t o[4] = {o0, o1, o2, o3};
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (b0 + i < nb) {
+          off[b0 + i] = o[i];
+          if (cursor) cursor[b0 + i] = o[i];
+          if (parts) parts[b0 + i] = p[i];
+        }
+    }
+    carry += tile_total;
+    __syncthreads();                                   // wsum is rewritten by the next tile
   }
-  sm[threadIdx.x] = sum;
-  smax[threadIdx.x] = mx;
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if (lane == 0) wmax[warp] = mx;
   __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {
-    uint32_t v = threadIdx.x >= d ? sm[threadIdx.x - d] : 0;
-    uint32_t m2 = threadIdx.x >= d ? smax[threadIdx.x - d] : 0;
-    __syncthreads();
-    sm[threadIdx.x] += v;
-    smax[threadIdx.x] = max(smax[threadIdx.x], m2);
-    __syncthreads();
-  }
-  uint32_t run = threadIdx.x ? sm[threadIdx.x - 1] : 0;
-  for (uint32_t b = lo; b < hi; b++) {
-    uint32_t p = (cnt[b] + K - 1) / K;
-    off[b] = run;
-    if (cursor) cursor[b] = run;
-    if (parts) parts[b] = p;
-    run += p;
-  }
-  if (threadIdx.x == 1023) {
-    off[nb] = sm[1023];
-    total_max[0] = sm[1023];
-    total_max[1] = smax[1023];
+  if (warp == 0) {
+    const uint32_t m = __reduce_max_sync(0xffffffffu, wmax[lane]);
+    if (lane == 0) {
+      off[nb] = carry;
+      total_max[0] = carry;
+      total_max[1] = m;
+    }
   }
 }
 
@@ -680,12 +720,34 @@ __global__ void __launch_bounds__(512) k_rows_final(const XYZZ<C>* __restrict__ 
   }
 }
 
-// XYZZ -> affine canonical, one THREAD per row: the single-thread inversion (~110 k cycles) no longer holds a whole
-// 512-thread CTA of k_rows_final on its SM
+// The same for nblk = 1 (one partial per bit) on ONE WARP per row: lane t holds S_t, doubles it t times, then a shuffle
+// tree.  A CTA of c warps per row used one lane of each warp (1024 rows: 3.5 waves of two CTAs per SM, 239 us); four
+// rows per 128-thread CTA are resident all at once.
+template <class C>
+__global__ void __launch_bounds__(128) k_rows_final_warp(const XYZZ<C>* __restrict__ partial, uint64_t rows, uint32_t cbits,
+                                                         XYZZ<C>* __restrict__ out_xyzz) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= rows) return;                               // warp-uniform
+  XYZZ<C> v = (uint32_t)lane < cbits ? ld_xyzz(partial + g * cbits + lane) : xyzz_inf<C>();
+#pragma unroll 1
+  for (uint32_t k = 1; k < cbits; k++)
+    if ((uint32_t)lane >= k && (uint32_t)lane < cbits) v = xyzz_dbl<C>(v);
+#pragma unroll 1
+  for (uint32_t m = 1; m < 32 && m < cbits; m <<= 1) {
+    XYZZ<C> o = shfl_xor_xyzz(v, (int)m);
+    xyzz_add<C>(v, o);
+  }
+  if (lane == 0) st_xyzz(out_xyzz + g, v);
+}
+
+// XYZZ -> affine canonical, one WARP per row with lane 0 at work: the inversion (binary Euclid, ~110 k cycles) is a
+// data-dependent branch sequence, 32 of them in one warp serialise (210 us for 1024 rows); alone in its warp each
+// runs at its own pace, and it no longer holds a whole CTA of k_rows_final on its SM
 template <class C>
 __global__ void __launch_bounds__(128) k_rows_affine(const XYZZ<C>* __restrict__ in, uint64_t rows, Affine<C>* __restrict__ out) {
-  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
+  const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows || (threadIdx.x & 31) != 0) return;
   Affine<C> a = xyzz_to_affine<C>(ld_xyzz(in + r));
   a.x = from_mont<C>(a.x);
   a.y = from_mont<C>(a.y);
@@ -927,7 +989,7 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
     return o;
   };
   const uint64_t max_parts1 = n_entries / K_FIRST + nb + 1;
-  const uint64_t max_parts2 = max_parts1 / 64 + nb + 1;   // smallest chunk size of a combine pass
+  const uint64_t max_parts2 = max_parts1 / 16 + nb + 1;   // smallest chunk size of a combine pass
   size_t o_keys = take(n_entries * 4), o_vals = take(n_entries * 4), o_sorted = take(n_entries * 4);
   size_t o_cnt = take((size_t)(nb + 2) * 4), o_start = take((size_t)(nb + 2) * 4), o_cursor = take((size_t)(nb + 2) * 4);
   size_t o_pcnt[2] = {take((size_t)(nb + 2) * 4), take((size_t)(nb + 2) * 4)};
@@ -993,7 +1055,11 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
   while (max_cnt > 1) {
     const int nxt = cur ^ 1;
     const bool narrow = (uint64_t)nb * 4 >= (uint64_t)c->sm_count * 32 * 2;
-    const uint32_t kn = narrow ? 64u : K_NEXT;
+    // many rows: a few heavy buckets per row (the high window of short scalars, the all-equal characters of Reef's
+    // `aaaa...b` document) sit between thousands of light ones, so a warp of eight 4-lane groups runs as long as its
+    // heaviest group: 16 partials per group (4 + 2 additions deep) instead of 64 (16 + 2) keeps the heavy warps short
+    // and spreads a heavy bucket over four times as many groups; the extra pass is one scan + one launch
+    const uint32_t kn = narrow ? 16u : K_NEXT;
     k_scan<<<1, 1024, 0, s>>>(pcnt[cur], nb, kn, pcnt[nxt], poff[nxt], nullptr, tm + 2);
     REEF_LAUNCHED();
     const uint32_t n_next = (n_parts + kn - 1) / kn + nb;
@@ -1018,13 +1084,14 @@ static int msm_rows_run_t(reef_ctx* c, const MsmRowsArgs& a) {
   // one warp per bit: c warps are all a row needs (a 512-thread CTA kept half an SM's registers idle)
   const unsigned fin_threads = 32u * (P.c < 16u ? P.c : 16u);
   if (host_affine) {
-    k_rows_final<C><<<(unsigned)a.rows, fin_threads, 0, s>>>(bitpart, nblk, P.c, d_out, (XYZZ<C>*)d_out);
+    k_rows_final<C><<<(unsigned)a.rows, fin_threads, 0, s>>>(bitpart, nblk, P.c, nullptr, (XYZZ<C>*)d_out);
     REEF_LAUNCHED();
   } else {
     XYZZ<C>* row_xyzz = (XYZZ<C>*)(d + o_rowx);
-    k_rows_final<C><<<(unsigned)a.rows, fin_threads, 0, s>>>(bitpart, nblk, P.c, d_out, row_xyzz);
+    if (nblk == 1 && P.c <= 32u && a.rows >= (uint64_t)c->sm_count) k_rows_final_warp<C><<<cdiv(a.rows, 4), 128, 0, s>>>(bitpart, a.rows, P.c, row_xyzz);
+    else k_rows_final<C><<<(unsigned)a.rows, fin_threads, 0, s>>>(bitpart, nblk, P.c, nullptr, row_xyzz);
     REEF_LAUNCHED();
-    k_rows_affine<C><<<cdiv(a.rows, 32), 32, 0, s>>>(row_xyzz, a.rows, d_out);
+    k_rows_affine<C><<<cdiv(a.rows, 4), 128, 0, s>>>(row_xyzz, a.rows, d_out);
     REEF_LAUNCHED();
   }
   scope.reset();

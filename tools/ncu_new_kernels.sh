@@ -25,7 +25,7 @@ s = G.Ipa(ctx, "pallas", kb, (FP - 1, 2), [rnd.randrange(FQ) for _ in range(n)],
 L, R = s.round(); s.fold(5, pow(5, -1, FQ)); s.round()
 PY
 cp /tmp/new_kernels.py tools/_new_kernels_tmp.py
-ncu --set full --clock-control none --import-source on -k regex:'k_poseidon_ro_fast|k_bitsum_partial_warp|k_rows_final|k_ipa_scalars|k_ipa_weights|k_digits_rows|k_cross_term' -c 14 -o /tmp/r02_new python tools/_new_kernels_tmp.py > gpurun_out/r02_ncu_new.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_poseidon_ro_fast|k_bitsum_partial_warp|k_rows_final|k_rows_affine|k_ipa_scalars|k_ipa_weights|k_digits_rows|k_cross_term' -c 16 -o /tmp/r02_new python tools/_new_kernels_tmp.py > gpurun_out/r02_ncu_new.log 2>&1
 ncu -i /tmp/r02_new.ncu-rep --page raw --csv > gpurun_out/r02_prof_new_raw.csv 2>/dev/null
 rm -f tools/_new_kernels_tmp.py
 tail -3 gpurun_out/r02_ncu_new.log

@@ -118,7 +118,7 @@ def test_hyrax_row_commit_document_shape(ctx, ell, bits):
     blinds = [rnd.randrange(cv.order) for _ in range(rows)]
     got = b.msm_rows(M, rows, cols, bits, blinds)
     w = np.arange(1, cols + 1, dtype=object)
-    for r in list(range(4)) + [rows // 2, rows - 1]:
+    for r in range(rows):                                           # every row: warp-per-row scaling / inversion kernels
         k = (int((M[r].astype(object) * w).sum()) + blinds[r] * (cols + 1)) % cv.order
         assert got[r] == cv.mul(k, cv.gen), r
 
